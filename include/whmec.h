@@ -1,0 +1,134 @@
+/*
+ * whmec.h — C ABI of the B200-native weighted-MEC / PedMEC dynamic program.
+ *
+ * This is the drop-in boundary for ONE hot path of WhatsHap: the PedigreeDPTable
+ * column sweep.  The reference exposes that path as a C++ class bound through
+ * Cython; there is no C ABI in the reference, so every entry point below names
+ * the reference interface it replaces (paths relative to the whatshap source
+ * tree):
+ *
+ *   whmec_solve            <- PedigreeDPTable::PedigreeDPTable  src/pedigreedptable.cpp:15-37
+ *                             (ctor runs compute_table :84-174) + get_super_reads :344-388
+ *                             + get_optimal_partitioning :391-406 + get_optimal_score :338-341,
+ *                             bound at whatshap/cpp.pxd:86-90 / whatshap/core.pyx:364-416
+ *   whmec_plan_*           <- same path, split into upload / forward sweep / backtrace so that
+ *                             a caller (bench.py) can keep the packed ReadSet resident in HBM
+ *   whmec_read_sort_key    <- ReadSet::read_comparator_t tie-break hash  src/readset.h:39-81
+ *
+ * Plain pointers and sizes only.  All input pointers are caller-owned host
+ * memory, read-only, and need to stay valid only for the duration of the call.
+ * Output arrays are caller-allocated.  No global mutable state; calls are
+ * re-entrant; CUDA work is issued on a stream private to the call/plan.
+ */
+#ifndef WHMEC_H
+#define WHMEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WHMEC_ABI_VERSION 1
+
+/* return codes */
+#define WHMEC_OK 0
+#define WHMEC_ERR_MENDELIAN 1   /* "Error: Mendelian conflict"   (pedigreedptable.cpp:301-303) */
+#define WHMEC_ERR_INPUT 2       /* unsorted reads / malformed arrays (columniterator.cpp:29,32) */
+#define WHMEC_ERR_CUDA 3        /* CUDA runtime failure, message in err */
+#define WHMEC_ERR_UNSUPPORTED 4 /* > 32 active reads (graycodes.cpp:12), cost range, HBM budget */
+
+/* allele codes in ent_allele (src/entry.h:8) */
+#define WHMEC_ALLELE_REF 0
+#define WHMEC_ALLELE_ALT 1
+#define WHMEC_ALLELE_BLANK 2
+#define WHMEC_ALLELE_EQUAL_SCORES 3 /* only ever produced, in sr_allele */
+
+/* genotype code meaning "no diploid biallelic genotype" (never matches an assignment) */
+#define WHMEC_GT_OTHER 255
+
+/*
+ * One DP instance = one (chromosome x family) call of the reference constructor.
+ *
+ * Reads are given in final ReadSet order (sorted by first position); that order
+ * defines the bit position of a read inside a column's bipartition index
+ * (src/columniterator.cpp:91-139).  Entries are CSR over reads; ent_col is the
+ * COLUMN INDEX (0..n_cols-1) of the entry's position and must be strictly
+ * increasing inside a read.  A read is active in columns [first, last]; columns in
+ * that span without an entry are BLANK (columniterator.cpp:131).
+ */
+typedef struct whmec_problem {
+    uint32_t n_cols;
+    const uint32_t *positions;   /* [n_cols] genomic positions (only echoed into results) */
+    uint32_t n_reads;
+    const uint64_t *read_off;    /* [n_reads+1] */
+    const uint32_t *ent_col;     /* [nnz] */
+    const uint8_t *ent_allele;   /* [nnz] 0/1/2 */
+    const uint32_t *ent_phred;   /* [nnz] */
+    const uint32_t *read_ind;    /* [n_reads] pedigree INDEX of the read's sample */
+    const uint32_t *recombcost;  /* [n_cols] */
+    uint32_t n_ind;
+    uint32_t n_trios;
+    const uint32_t *trios;       /* [3*n_trios] (father, mother, child) indices; trio r owns tv bits 2r,2r+1 */
+    uint32_t distrust;           /* distrust_genotypes */
+    const uint8_t *gt;           /* [n_ind*n_cols] canonical genotype index 0/1/2 or WHMEC_GT_OTHER */
+    const double *gl;            /* [n_ind*n_cols*3] phred GLs (0/0,0/1,1/1); required iff distrust */
+} whmec_problem;
+
+typedef struct whmec_solution {
+    uint32_t cost;               /* get_optimal_score() */
+    uint32_t *path_index;        /* [n_cols] optimal bipartition index per column (index_path[k].index) */
+    uint32_t *path_tv;           /* [n_cols] transmission value per column (index_path[k].inheritance_value) */
+    uint8_t *partition;          /* [n_reads] get_optimal_partitioning() AFTER core.pyx:414 mapping (0/1) */
+    uint8_t *sr_allele;          /* [n_ind][2][n_cols] super-read alleles in {0,1,3} */
+    uint32_t *sr_quality;        /* [n_ind][n_cols] super-read quality */
+} whmec_solution;
+
+/* Work/traffic accounting of one solve; all byte counts follow SURVEY.md §8(d). */
+typedef struct whmec_stats {
+    uint64_t cells;              /* sum_k 2^{a_k} * T */
+    uint64_t algorithmic_bytes;  /* sum_k T*(4*2^{bw_k} + (8 + 4*[T>1])*2^{f_k}) */
+    uint64_t backptr_bytes;      /* bytes of packed back-pointers actually stored in HBM */
+    uint64_t state_bytes;        /* bytes of projection state written+read to global memory */
+    uint32_t kernel_launches;    /* CUDA kernels launched by the last forward sweep */
+    uint32_t n_chains;           /* DP-independent column chains found (T==1) */
+    uint32_t max_active;         /* max_k a_k */
+    uint32_t transmissions;      /* T */
+    float sweep_ms;              /* device time of the last forward sweep (CUDA events) */
+    float h2d_ms, d2h_ms;        /* device-timed copies of the last solve */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint32_t path_kind;          /* 1 = tile kernel, 2 = column kernel, 3 = mixed */
+    uint32_t reserved;
+} whmec_stats;
+
+typedef struct whmec_plan whmec_plan;
+
+/* Library / device introspection (no GPU needed for the first two). */
+int whmec_abi_version(void);
+const char *whmec_build_info(void);
+int whmec_device_count(void);
+
+/* Pack the problem on the host, upload it to `device`, allocate state and back-pointer
+ * storage.  Host-detectable errors (Mendelian conflict, unsorted input) are reported here. */
+int whmec_plan_create(const whmec_problem *p, int device, whmec_plan **out, char *err, size_t errlen);
+/* Enqueue the forward sweep on the plan's stream and wait for it; may be called repeatedly
+ * (each call recomputes everything from the resident inputs). */
+int whmec_plan_sweep(whmec_plan *plan, char *err, size_t errlen);
+/* Download back-pointers / optimum, run the backtrace and the super-read pass. */
+int whmec_plan_finish(whmec_plan *plan, whmec_solution *s, char *err, size_t errlen);
+int whmec_plan_stats(const whmec_plan *plan, whmec_stats *st);
+void whmec_plan_destroy(whmec_plan *plan);
+
+/* One-shot: create + sweep + finish + destroy, host buffers in, host buffers out. */
+int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st_or_null,
+                char *err, size_t errlen);
+
+/* Sort key of ReadSet::sort() ties: std::hash<std::string>(name) ^ std::hash<int>(source_id)
+ * as computed by libstdc++ (64-bit murmur, seed 0xc70f6907); src/readset.h:68-72. */
+uint64_t whmec_read_sort_key(const char *name, size_t len, int32_t source_id);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WHMEC_H */

@@ -1,0 +1,271 @@
+"""Deterministic synthetic ReadSets for the BASELINE.json configurations.
+
+There is no reference generator: the reference ships no benchmark for this path.  These
+generators emit the *flat* problem (`FlatProblem`) directly; `to_objects()` turns a flat problem
+into the Python-level `ReadSet` / `Pedigree` the way `whatshap phase` would hand them to
+`PedigreeDPTable` (whatshap/cli/phase.py:542-610).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+from ._abi import FlatProblem, GT_OTHER
+
+#: seeds fixed by SURVEY.md §8(d)
+SEEDS = {"cfg2": 20250915, "cfg3": 20250920, "cfg4": 20250925, "cfg5": 20250935}
+
+
+def _csr_from_spans(first: np.ndarray, last: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """CSR offsets and column indices for reads covering [first, last] without gaps."""
+    lens = (last - first + 1).astype(np.int64)
+    off = np.zeros(first.size + 1, np.uint64)
+    np.cumsum(lens, out=off[1:])
+    nnz = int(off[-1])
+    rid = np.repeat(np.arange(first.size), lens)
+    within = np.arange(nnz) - np.repeat(off[:-1].astype(np.int64), lens)
+    cols = (first[rid] + within).astype(np.uint32)
+    return off, cols
+
+
+def _window_spans(n: int, c: int, stride: int, block_len: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Read spans so that every column has exactly `c` active reads and no read crosses a
+    block boundary.  Reads are ordered by (first column, start), i.e. ReadSet order."""
+    L = c * stride
+    firsts, lasts = [], []
+    for b0 in range(0, n, block_len):
+        B = min(block_len, n - b0)
+        s = np.arange(-(L - stride), B, stride)
+        f = np.maximum(s, 0)
+        l = np.minimum(s + L - 1, B - 1)
+        keep = (l - f + 1) >= 2  # reads with < 2 variants are dropped upstream (cli/phase.py:518)
+        firsts.append(f[keep] + b0)
+        lasts.append(l[keep] + b0)
+    return np.concatenate(firsts).astype(np.int64), np.concatenate(lasts).astype(np.int64)
+
+
+def sliding_window(
+    n: int,
+    c: int,
+    stride: int = 1,
+    block_len: int = 500,
+    err: float = 0.05,
+    seed: int = 0,
+    gap: float = 0.0,
+    max_phred: int = 40,
+) -> FlatProblem:
+    """Single diploid individual, all sites heterozygous (trusted), coverage exactly `c`."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    first, last = _window_spans(n, c, stride, block_len)
+    off, cols = _csr_from_spans(first, last)
+    nnz = cols.size
+    lens = (last - first + 1).astype(np.int64)
+    truth = rng.integers(0, 2, n, dtype=np.uint8)
+    read_hap = rng.integers(0, 2, first.size, dtype=np.uint8)
+    flips = (rng.random(nnz) < err).astype(np.uint8)
+    allele = truth[cols] ^ np.repeat(read_hap, lens) ^ flips
+    phred = rng.integers(1, max_phred + 1, nnz, dtype=np.uint32)
+    if gap > 0.0:
+        drop = rng.random(nnz) < gap
+        starts = off[:-1].astype(np.int64)
+        ends = off[1:].astype(np.int64) - 1
+        drop[starts] = False
+        drop[ends] = False
+        keep = ~drop
+        new_lens = np.add.reduceat(keep.astype(np.int64), starts)
+        off = np.zeros(first.size + 1, np.uint64)
+        np.cumsum(new_lens, out=off[1:])
+        cols, allele, phred = cols[keep], allele[keep], phred[keep]
+    recomb = np.full(n, 49, np.uint32)
+    if n:
+        recomb[0] = 0
+    return FlatProblem(
+        positions=(np.arange(n, dtype=np.uint32) + 1) * 1000,
+        read_off=off,
+        ent_col=cols,
+        ent_allele=allele,
+        ent_phred=phred,
+        read_ind=np.zeros(first.size, np.uint32),
+        recombcost=recomb,
+        n_ind=1,
+        distrust=False,
+        gt=np.ones((1, n), np.uint8),
+    )
+
+
+def trio(
+    n: int,
+    c_per_sample: int = 5,
+    block_len: int = 500,
+    err: float = 0.05,
+    seed: int = 0,
+    recomb_every: int = 5000,
+    max_phred: int = 40,
+) -> FlatProblem:
+    """Father, mother, child (indices 0,1,2; one trio), `c_per_sample` reads per sample per column."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    f1, l1 = _window_spans(n, c_per_sample, 1, block_len)
+    m = f1.size
+    first = np.concatenate([f1, f1, f1])
+    last = np.concatenate([l1, l1, l1])
+    ind = np.repeat(np.arange(3, dtype=np.uint32), m)
+    start_key = np.concatenate([np.arange(m)] * 3)
+    order = np.lexsort((ind, start_key, first))  # ReadSet order: by first column, then deterministic
+    first, last, ind = first[order], last[order], ind[order]
+    off, cols = _csr_from_spans(first, last)
+    lens = (last - first + 1).astype(np.int64)
+    nnz = cols.size
+    # parental haplotypes; child inherits one haplotype per parent with rare recombination
+    hap = rng.integers(0, 2, (2, 2, n), dtype=np.uint8)  # [parent][haplotype][col]
+    sel = np.zeros((2, n), np.uint8)
+    for par in range(2):
+        cur = int(rng.integers(0, 2))
+        brk = rng.random(n) < (1.0 / max(recomb_every, 1))
+        for k in range(n):
+            if brk[k]:
+                cur ^= 1
+            sel[par, k] = cur
+    child = np.stack([np.where(sel[0] == 0, hap[0, 0], hap[0, 1]), np.where(sel[1] == 0, hap[1, 0], hap[1, 1])])
+    haps = np.stack([hap[0], hap[1], child])  # [ind][haplotype][col]
+    gt = (haps[:, 0, :] + haps[:, 1, :]).astype(np.uint8)
+    read_hap = rng.integers(0, 2, first.size, dtype=np.uint8)
+    flips = (rng.random(nnz) < err).astype(np.uint8)
+    rid = np.repeat(np.arange(first.size), lens)
+    allele = haps[ind[rid], read_hap[rid], cols] ^ flips
+    phred = rng.integers(1, max_phred + 1, nnz, dtype=np.uint32)
+    recomb = np.full(n, 49, np.uint32)
+    if n:
+        recomb[0] = 0
+    return FlatProblem(
+        positions=(np.arange(n, dtype=np.uint32) + 1) * 1000,
+        read_off=off,
+        ent_col=cols,
+        ent_allele=allele.astype(np.uint8),
+        ent_phred=phred,
+        read_ind=ind,
+        recombcost=recomb,
+        n_ind=3,
+        trios=np.array([0, 1, 2], np.uint32),
+        distrust=False,
+        gt=gt,
+    )
+
+
+def config(name: str, n: Optional[int] = None) -> FlatProblem:
+    """The four GPU configurations of BASELINE.json (cfg2..cfg5); `n` overrides the column count."""
+    if name == "cfg2":
+        return sliding_window(n or 10_000, 15, block_len=500, seed=SEEDS[name])
+    if name == "cfg3":
+        return sliding_window(n or 50_000, 20, block_len=500, seed=SEEDS[name])
+    if name == "cfg4":
+        nn = n or 50_000
+        return sliding_window(nn, 25, block_len=nn, seed=SEEDS[name])
+    if name == "cfg5":
+        return trio(n or 20_000, 5, block_len=500, seed=SEEDS[name])
+    raise KeyError(name)
+
+
+PEDIGREES = {
+    # name: (n_ind, trios)
+    "single": (1, []),
+    "two_unrelated": (2, []),
+    "trio": (3, [0, 1, 2]),
+    "trio_child_first": (3, [1, 2, 0]),
+    "quartet": (4, [0, 1, 2, 0, 1, 3]),
+    "three_generations": (5, [0, 1, 2, 2, 3, 4]),
+}
+
+
+def random_problem(
+    rng: np.random.Generator,
+    n_cols: int,
+    max_cov: int,
+    pedigree: str = "single",
+    distrust: bool = False,
+    max_phred: int = 5,
+    gap: float = 0.15,
+    mean_len: float = 4.0,
+    conflict_free: bool = True,
+    hom_rate: float = 0.2,
+) -> FlatProblem:
+    """Irregular instance for fuzzing: random spans, interior gaps, tie-heavy small weights,
+    blank (allele 2) entries, columns without reads, coverage capped at `max_cov`."""
+    n_ind, trios = PEDIGREES[pedigree]
+    cov = np.zeros(n_cols, np.int64)
+    reads = []
+    start = 0
+    while start < n_cols:
+        burst = int(rng.integers(0, 3))
+        for _ in range(burst):
+            L = 1 + int(rng.geometric(1.0 / mean_len))
+            end = min(n_cols - 1, start + L)
+            if end == start:
+                if start == 0:
+                    continue
+                # single-variant reads are legal input for the DP (tests only need >= 1 entry)
+            if cov[start : end + 1].max() >= max_cov:
+                continue
+            cov[start : end + 1] += 1
+            reads.append((start, end))
+        start += int(rng.integers(1, 3))
+    off = [0]
+    cols, alle, phr, inds = [], [], [], []
+    for (a, b) in reads:
+        span = np.arange(a, b + 1)
+        if span.size > 2 and gap > 0:
+            keep = rng.random(span.size) >= gap
+            keep[0] = keep[-1] = True
+            span = span[keep]
+        cols.append(span)
+        al = rng.integers(0, 2, span.size)
+        blank = rng.random(span.size) < 0.03
+        al[blank] = 2
+        alle.append(al)
+        phr.append(rng.integers(0 if rng.random() < 0.2 else 1, max_phred + 1, span.size))
+        inds.append(int(rng.integers(0, n_ind)))
+        off.append(off[-1] + span.size)
+    cat = lambda xs, dt: (np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt))
+    # genotypes: Mendelian-consistent by construction unless conflict_free is False
+    T = np.array(trios, np.int64).reshape(-1, 3)
+    haps = rng.integers(0, 2, (n_ind, 2, n_cols))
+    hom = rng.random((n_ind, n_cols)) < hom_rate
+    haps[:, 1, :] = np.where(hom, haps[:, 0, :], haps[:, 1, :])
+    for (f, m, c) in T:  # parents always precede children in these pedigrees or are fixed up in order
+        pass
+    order = list(range(n_ind))
+    done = set(i for i in range(n_ind) if i not in T[:, 2].tolist()) if T.size else set(order)
+    while len(done) < n_ind:
+        for (f, m, c) in T:
+            if c not in done and f in done and m in done:
+                sf = rng.integers(0, 2, n_cols)
+                sm = rng.integers(0, 2, n_cols)
+                haps[c, 0, :] = np.where(sf == 0, haps[f, 0, :], haps[f, 1, :])
+                haps[c, 1, :] = np.where(sm == 0, haps[m, 0, :], haps[m, 1, :])
+                done.add(int(c))
+    gt = (haps[:, 0, :] + haps[:, 1, :]).astype(np.uint8)
+    if not conflict_free:
+        noise = rng.random((n_ind, n_cols)) < 0.15
+        gt = np.where(noise, rng.integers(0, 3, (n_ind, n_cols)), gt).astype(np.uint8)
+        other = rng.random((n_ind, n_cols)) < 0.01
+        gt = np.where(other, GT_OTHER, gt).astype(np.uint8)
+    gl = None
+    if distrust:
+        gl = rng.integers(0, 12, (n_ind, n_cols, 3)).astype(np.float64)
+        if rng.random() < 0.5:
+            gl += rng.random((n_ind, n_cols, 3))  # fractional GLs exercise the unsigned += double truncation
+    recomb = rng.integers(0, 8, n_cols).astype(np.uint32)
+    return FlatProblem(
+        positions=(np.arange(n_cols, dtype=np.uint32) + 1) * 10,
+        read_off=np.array(off, np.uint64),
+        ent_col=cat(cols, np.uint32),
+        ent_allele=cat(alle, np.uint8),
+        ent_phred=cat(phr, np.uint32),
+        read_ind=np.array(inds, np.uint32),
+        recombcost=recomb,
+        n_ind=n_ind,
+        trios=np.array(trios, np.uint32),
+        distrust=distrust,
+        gt=gt,
+        gl=gl,
+    )
