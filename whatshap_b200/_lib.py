@@ -1,0 +1,130 @@
+"""Loader and thin typed wrappers for libwhmec.so (the C ABI of include/whmec.h).
+
+The CUDA library is the only compute path: if it is missing or cannot be loaded this module
+raises at first use — there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from functools import lru_cache
+from typing import Optional, Tuple
+
+from ._abi import CProblem, CSolution, CStats, FlatProblem, FlatSolution, raise_for
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwhmec.so")
+
+#: every symbol include/whmec.h declares (checked by tests/test_abi.py)
+EXPORTS = (
+    "whmec_abi_version",
+    "whmec_build_info",
+    "whmec_device_count",
+    "whmec_plan_create",
+    "whmec_plan_sweep",
+    "whmec_plan_finish",
+    "whmec_plan_stats",
+    "whmec_plan_destroy",
+    "whmec_solve",
+    "whmec_read_sort_key",
+)
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libwhmec.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", os.path.join(HERE, "csrc")], capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building libwhmec.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+@lru_cache(maxsize=None)
+def lib() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(whatshap_b200 has no CPU fallback)"
+        )
+    L = C.CDLL(LIB_PATH)
+    L.whmec_abi_version.restype = C.c_int
+    L.whmec_build_info.restype = C.c_char_p
+    L.whmec_device_count.restype = C.c_int
+    L.whmec_plan_create.argtypes = [C.POINTER(CProblem), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.whmec_plan_sweep.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    L.whmec_plan_finish.argtypes = [C.c_void_p, C.POINTER(CSolution), C.c_char_p, C.c_size_t]
+    L.whmec_plan_stats.argtypes = [C.c_void_p, C.POINTER(CStats)]
+    L.whmec_plan_destroy.argtypes = [C.c_void_p]
+    L.whmec_plan_destroy.restype = None
+    L.whmec_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
+    L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
+    L.whmec_read_sort_key.restype = C.c_uint64
+    for name in ("whmec_plan_create", "whmec_plan_sweep", "whmec_plan_finish", "whmec_plan_stats", "whmec_solve"):
+        getattr(L, name).restype = C.c_int
+    return L
+
+
+def device_count() -> int:
+    return int(lib().whmec_device_count())
+
+
+def solve(prob: FlatProblem, device: int = 0) -> Tuple[FlatSolution, dict]:
+    """One-shot solve through `whmec_solve` (host buffers in, host buffers out)."""
+    sol = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+    cp, cs, st = prob.as_c(), sol.as_c(), CStats()
+    err = C.create_string_buffer(512)
+    rc = lib().whmec_solve(C.byref(cp), C.byref(cs), device, C.byref(st), err, len(err))
+    raise_for(rc, err.value.decode())
+    sol.cost = int(cs.cost)
+    return sol, st.as_dict()
+
+
+class Plan:
+    """Device-resident problem: `sweep()` can be timed repeatedly with inputs already in HBM."""
+
+    def __init__(self, prob: FlatProblem, device: int = 0):
+        self.prob = prob
+        self._h = C.c_void_p()
+        cp = prob.as_c()
+        err = C.create_string_buffer(512)
+        rc = lib().whmec_plan_create(C.byref(cp), device, C.byref(self._h), err, len(err))
+        raise_for(rc, err.value.decode())
+
+    def sweep(self) -> None:
+        err = C.create_string_buffer(512)
+        raise_for(lib().whmec_plan_sweep(self._h, err, len(err)), err.value.decode())
+
+    def finish(self) -> FlatSolution:
+        sol = FlatSolution(self.prob.n_cols, self.prob.n_reads, self.prob.n_ind)
+        cs = sol.as_c()
+        err = C.create_string_buffer(512)
+        raise_for(lib().whmec_plan_finish(self._h, C.byref(cs), err, len(err)), err.value.decode())
+        sol.cost = int(cs.cost)
+        return sol
+
+    def stats(self) -> dict:
+        st = CStats()
+        lib().whmec_plan_stats(self._h, C.byref(st))
+        return st.as_dict()
+
+    def close(self) -> None:
+        if self._h:
+            lib().whmec_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def read_sort_key(name: str, source_id: int) -> int:
+    b = name.encode("utf-8")
+    return int(lib().whmec_read_sort_key(b, len(b), source_id))

@@ -1,0 +1,179 @@
+// Per-thread pieces of the column kernel, written host/device so that the exact same code can be
+// single-stepped on the CPU by the test-only emulation harness (tests/emul) before it is run
+// on a GPU.  The product only ever calls these from __global__ kernels (whmec.cu).
+#pragma once
+#include "common.h"
+
+namespace whmec {
+
+// Value/back-pointer key of one projection entry:
+//   bits 63..32  DP value (UMAX = +inf)
+//   bits 31..tb  r  = rank-order index of the winning candidate among the 2^d of this output
+//   bits tb-1..0 j  = argmin transmission value of the previous column (smallest j on ties)
+// min() over keys reproduces the reference's strict-'<' updates in Gray-code visiting order
+// (pedigreedptable.cpp:293-296,320-324).
+constexpr uint64_t KEY_INF = 0xFFFFFFFFFFFFFFFFull;
+
+constexpr int NF_REG = 16;  // cost functions kept incrementally in registers per thread
+
+struct ColView {
+    const ColMeta *m;
+    uint32_t T, tb;
+    const uint32_t *fn_c0;     // functions of this column's transmission group i
+    const int32_t *fn_delta;   // [nf][FN_STRIDE]
+    uint32_t nf;
+    const uint32_t *prev;      // [2^bw][T] values of the previous projection (ignored if m->first)
+};
+
+// Best key over candidates r in [r0, r1) of forward-projection entry `o` for transmission value i.
+// Reference: one iteration of the Gray-code loop body (pedigreedptable.cpp:239-327), restricted
+// to the candidates projecting onto `o` and visited in the same relative order.
+WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
+    const ColMeta &m = *v.m;
+    const uint32_t drop = ~m.keep & low_mask(m.a);
+    const uint32_t kept = pdep32(o, m.keep);
+    const uint32_t cg = rank_offset(m, kept);
+    uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cg, drop);
+    const uint32_t bmask = low_mask(m.bw);
+    const bool incremental = v.nf <= (uint32_t)NF_REG;
+
+    uint32_t cost[NF_REG];
+    if (incremental) {
+#pragma unroll
+        for (int F = 0; F < NF_REG; ++F) {
+            if ((uint32_t)F < v.nf) {
+                uint32_t c = v.fn_c0[F];
+                for (uint32_t j = 0; j < m.a; ++j)
+                    if ((x >> j) & 1u) c += (uint32_t)v.fn_delta[F * FN_STRIDE + j];
+                cost[F] = c;
+            } else {
+                cost[F] = UMAX;
+            }
+        }
+    }
+
+    uint64_t best = KEY_INF;
+    for (uint32_t r = r0; r < r1; ++r) {
+        // get_cost(): min over allowed assignments (pedigreecolumncostcomputer.cpp:101-114)
+        uint32_t cur = UMAX;
+        if (incremental) {
+#pragma unroll
+            for (int F = 0; F < NF_REG; ++F)
+                if ((uint32_t)F < v.nf && cost[F] < cur) cur = cost[F];
+        } else {
+            for (uint32_t F = 0; F < v.nf; ++F) {
+                uint32_t c = v.fn_c0[F];
+                for (uint32_t j = 0; j < m.a; ++j)
+                    if ((x >> j) & 1u) c += (uint32_t)v.fn_delta[F * FN_STRIDE + j];
+                if (c < cur) cur = c;
+            }
+        }
+        // min over previous transmission values (pedigreedptable.cpp:270-297), first j wins
+        const uint32_t b = x & bmask;
+        uint32_t mn = UMAX, mj = 0;
+        for (uint32_t j = 0; j < v.T; ++j) {
+            uint32_t prev = m.first ? 0u : v.prev[(size_t)b * v.T + j];
+            uint32_t val = (cur < UMAX && prev < UMAX) ? cur + prev : UMAX;
+            if (val < UMAX) val += popc32(i ^ j) * m.rc;
+            if (val < mn) {
+                mn = val;
+                mj = j;
+            }
+        }
+        uint64_t key = ((uint64_t)mn << 32) | ((uint64_t)r << v.tb) | mj;
+        if (key < best) best = key;
+        // step to the next candidate in Gray-rank order: exactly one dropped bit flips
+        if (r + 1 < r1) {
+            const uint32_t pos = m.dpos[ctz32(r + 1)];
+            x ^= 1u << pos;
+            if (incremental) {
+                const bool set = (x >> pos) & 1u;
+#pragma unroll
+                for (int F = 0; F < NF_REG; ++F)
+                    if ((uint32_t)F < v.nf) {
+                        uint32_t dlt = (uint32_t)v.fn_delta[F * FN_STRIDE + pos];
+                        cost[F] += set ? dlt : (0u - dlt);
+                    }
+            }
+        }
+    }
+    return best;
+}
+
+// One backtrace step (pedigreedptable.cpp:155-160): given the back-pointer word of entry
+// (b, tv) of column k-1's projection, recover that column's bipartition index.
+WHMEC_HD uint32_t backpointer_to_index(const ColMeta &m, uint32_t tb, uint32_t out_index, uint32_t bp, uint32_t *argmin_j) {
+    *argmin_j = bp & low_mask(tb);
+    return candidate_index(m, out_index, bp >> tb);
+}
+
+// Read entry e of a packed back-pointer array (width in {0,1,2,4,8,16,32} bits).
+WHMEC_HD uint32_t bp_load(const uint32_t *arena, uint64_t off_words, uint32_t width, uint64_t e) {
+    if (width == 0) return 0;
+    uint64_t bit = e * width;
+    uint32_t word = arena[off_words + (bit >> 5)];
+    return (width == 32) ? word : ((word >> (bit & 31)) & ((1u << width) - 1u));
+}
+
+// Packed back-pointer store used by the host-side emulation and by single-thread writers.
+WHMEC_HD void bp_store_serial(uint32_t *arena, uint64_t off_words, uint32_t width, uint64_t e, uint32_t value) {
+    if (width == 0) return;
+    uint64_t bit = e * width;
+    uint32_t *w = &arena[off_words + (bit >> 5)];
+    if (width == 32) {
+        *w = value;
+    } else {
+        uint32_t mask = ((1u << width) - 1u) << (bit & 31);
+        *w = (*w & ~mask) | ((value << (bit & 31)) & mask);
+    }
+}
+
+struct BtView {
+    const ColMeta *cols;
+    const uint32_t *arena;
+    uint32_t T, tb;
+};
+
+// Backtrace from column k_last down to k_first (pedigreedptable.cpp:144-160).  (x, tv) is the
+// cell chosen in k_last and prev_tv the argmin transmission value it was reached from.
+WHMEC_HD void backtrace_range(const BtView &v, uint32_t k_last, uint32_t k_first, uint32_t x, uint32_t tv,
+                              uint32_t prev_tv, uint32_t *path_index, uint32_t *path_tv) {
+    path_index[k_last] = x;
+    path_tv[k_last] = tv;
+    for (uint32_t k = k_last; k > k_first; --k) {
+        const uint32_t b = x & low_mask(v.cols[k].bw);
+        const ColMeta &pm = v.cols[k - 1];
+        const uint32_t bp = bp_load(v.arena, pm.bp_off, pm.bp_width, (uint64_t)b * v.T + prev_tv);
+        uint32_t j;
+        x = backpointer_to_index(pm, v.tb, b, bp, &j);
+        tv = prev_tv;
+        prev_tv = j;
+        path_index[k - 1] = x;
+        path_tv[k - 1] = tv;
+    }
+}
+
+// Pick the optimum of the last column (pedigreedptable.cpp:306-315): smallest (value, Gray rank, i).
+WHMEC_HD void pick_optimum(const ColMeta &last, const uint32_t *vals, const uint32_t *arena, uint32_t T, uint32_t tb,
+                           uint32_t *cost, uint32_t *x, uint32_t *tv, uint32_t *prev_tv) {
+    uint32_t best_val = UMAX, best_r = UMAX, best_i = 0, best_j = 0;
+    bool have = false;
+    for (uint32_t i = 0; i < T; ++i) {
+        uint32_t bp = bp_load(arena, last.bp_off, last.bp_width, i);
+        uint32_t r = bp >> tb, val = vals[i];
+        if (val == UMAX) continue;
+        if (!have || val < best_val || (val == best_val && r < best_r)) {
+            have = true;
+            best_val = val;
+            best_r = r;
+            best_i = i;
+            best_j = bp & low_mask(tb);
+        }
+    }
+    *cost = best_val;
+    *x = candidate_index(last, 0, have ? best_r : 0);
+    *tv = best_i;
+    *prev_tv = best_j;
+}
+
+}  // namespace whmec

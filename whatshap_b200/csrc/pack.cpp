@@ -1,0 +1,367 @@
+// Host packer: ReadSet/Pedigree (flat CSR form) -> per-column records + affine cost functions,
+// and the inverse step from the optimal path to the reference's outputs.
+//
+// Restates, on the host and once per problem, what the reference recomputes per column:
+//   ColumnIterator::get_next               src/columniterator.cpp:91-139
+//   ColumnIndexingScheme ctor/set_next     src/columnindexingscheme.cpp:7-34,62-85
+//   PedigreePartitions                     src/pedigreepartitions.cpp:7-42
+//   PedigreeColumnCostComputer ctor        src/pedigreecolumncostcomputer.cpp:14-50
+//   get_alleles / get_super_reads          src/pedigreecolumncostcomputer.cpp:117-175, src/pedigreedptable.cpp:344-406
+#include "pack.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+
+namespace whmec {
+
+namespace {
+
+constexpr uint32_t MAX_IND = 16;
+constexpr uint32_t MAX_P = 10;
+
+// src/pedigreepartitions.cpp:7-42
+bool build_h2p(const whmec_problem *p, uint32_t tv, int8_t *h2p /* [n_ind][2] */) {
+    std::vector<int> triple_of(p->n_ind, -1);
+    for (uint32_t r = 0; r < p->n_trios; ++r) triple_of[p->trios[3 * r + 2]] = (int)r;
+    for (uint32_t i = 0; i < p->n_ind; ++i) h2p[2 * i] = h2p[2 * i + 1] = -1;
+    int q = 0;
+    for (uint32_t i = 0; i < p->n_ind; ++i)
+        if (triple_of[i] < 0) {
+            h2p[2 * i] = (int8_t)q;
+            h2p[2 * i + 1] = (int8_t)(q + 1);
+            q += 2;
+        }
+    // resolve children; at most n_ind rounds, otherwise the pedigree is cyclic
+    for (uint32_t round = 0; round <= p->n_ind; ++round) {
+        bool pending = false;
+        for (uint32_t i = 0; i < p->n_ind; ++i) {
+            if (h2p[2 * i] != -1) continue;
+            int r = triple_of[i];
+            uint32_t f = p->trios[3 * r], m = p->trios[3 * r + 1];
+            if (h2p[2 * f] == -1 || h2p[2 * m] == -1) {
+                pending = true;
+                continue;
+            }
+            h2p[2 * i] = h2p[2 * f + (((tv >> (2 * r)) & 1) ? 0 : 1)];
+            h2p[2 * i + 1] = h2p[2 * m + (((tv >> (2 * r + 1)) & 1) ? 0 : 1)];
+        }
+        if (!pending) return true;
+    }
+    return false;
+}
+
+}  // namespace
+
+int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
+    const uint32_t n = p->n_cols;
+    pk = Packed();
+    pk.n = n;
+    pk.n_reads = p->n_reads;
+    pk.n_ind = p->n_ind;
+    pk.n_trios = p->n_trios;
+    if (p->n_ind == 0 || p->n_ind > MAX_IND) {
+        err = "pedigree must have between 1 and 16 individuals";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
+    if (p->n_trios >= p->n_ind || p->n_trios > 4) {
+        err = "unsupported pedigree: at most 4 trio relationships (T = 4^trios <= 256)";
+        return p->n_trios > 4 ? WHMEC_ERR_UNSUPPORTED : WHMEC_ERR_INPUT;
+    }
+    pk.P = 2 * (p->n_ind - p->n_trios);
+    if (pk.P > MAX_P) {
+        err = "unsupported pedigree: more than 10 founder haplotypes";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
+    pk.tb = 2 * p->n_trios;
+    pk.T = 1u << pk.tb;
+    const uint32_t T = pk.T, P = pk.P;
+    {
+        std::vector<int> child_count(p->n_ind, 0);
+        for (uint32_t r = 0; r < p->n_trios; ++r) {
+            for (int q = 0; q < 3; ++q)
+                if (p->trios[3 * r + q] >= p->n_ind) {
+                    err = "trio refers to an individual outside the pedigree";
+                    return WHMEC_ERR_INPUT;
+                }
+            if (++child_count[p->trios[3 * r + 2]] > 1) {
+                err = "individual is the child of two trios";
+                return WHMEC_ERR_INPUT;
+            }
+        }
+    }
+    pk.h2p.assign((size_t)T * p->n_ind * 2, -1);
+    for (uint32_t t = 0; t < T; ++t)
+        if (!build_h2p(p, t, &pk.h2p[(size_t)t * p->n_ind * 2])) {
+            err = "cyclic pedigree";
+            return WHMEC_ERR_INPUT;
+        }
+    if (p->distrust && !p->gl && n > 0) {
+        err = "distrust_genotypes requires genotype likelihoods for every individual and column";
+        return WHMEC_ERR_INPUT;
+    }
+
+    // ---- read spans and the checks of the ColumnIterator constructor (columniterator.cpp:25-33)
+    std::vector<uint32_t> first(p->n_reads), last(p->n_reads);
+    uint32_t prev_first = 0;
+    uint64_t phred_total = 0;
+    for (uint32_t r = 0; r < p->n_reads; ++r) {
+        uint64_t b = p->read_off[r], e = p->read_off[r + 1];
+        if (e <= b) {
+            err = "No variants present";
+            return WHMEC_ERR_INPUT;
+        }
+        for (uint64_t q = b; q < e; ++q) {
+            if (q > b && p->ent_col[q] <= p->ent_col[q - 1]) {
+                err = "ColumnIterator: encountered read with unsorted variants.";
+                return WHMEC_ERR_INPUT;
+            }
+            if (p->ent_allele[q] > 2) {
+                err = "allele of a read entry must be 0 (REF), 1 (ALT) or 2 (BLANK)";
+                return WHMEC_ERR_INPUT;
+            }
+            phred_total += p->ent_phred[q];
+        }
+        first[r] = p->ent_col[b];
+        last[r] = p->ent_col[e - 1];
+        if (last[r] >= n) {
+            err = "read entry refers to a column outside positions";
+            return WHMEC_ERR_INPUT;
+        }
+        if (first[r] < prev_first) {
+            err = "ColumnIterator: reads in ReadSet are not sorted.";
+            return WHMEC_ERR_INPUT;
+        }
+        prev_first = first[r];
+        if (p->read_ind[r] >= p->n_ind) {
+            err = "read refers to an individual outside the pedigree";
+            return WHMEC_ERR_INPUT;
+        }
+    }
+
+    // ---- columns
+    pk.cols.resize(n);
+    pk.act_off.assign(n + 1, 0);
+    std::vector<uint32_t> active;  // ascending read index
+    std::vector<uint64_t> cursor(p->n_reads);
+    for (uint32_t r = 0; r < p->n_reads; ++r) cursor[r] = p->read_off[r];
+    uint32_t next_read = 0;
+    std::vector<uint32_t> prev_active;
+    uint32_t max_a = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        prev_active = active;
+        // retire reads that ended, admit reads that start here
+        active.erase(std::remove_if(active.begin(), active.end(), [&](uint32_t r) { return last[r] < k; }), active.end());
+        while (next_read < p->n_reads && first[next_read] == k) active.push_back(next_read++);
+        if (active.size() > MAX_ACTIVE) {
+            err = "more than 30 reads are active in one column (coverage too high)";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
+        ColMeta &m = pk.cols[k];
+        std::memset(&m, 0, sizeof m);
+        m.a = (uint32_t)active.size();
+        max_a = std::max(max_a, m.a);
+        m.rc = p->recombcost[k];
+        m.first = (k == 0);
+        // backward projection width = |active(k) ∩ active(k-1)|; those are the lowest bits
+        uint32_t w = 0;
+        for (uint32_t r : active)
+            if (std::binary_search(prev_active.begin(), prev_active.end(), r)) ++w;
+        m.bw = (k == 0) ? 0 : w;
+        for (uint32_t j = 0; j < m.a; ++j) {
+            uint32_t r = active[j];
+            while (p->ent_col[cursor[r]] < k) ++cursor[r];
+            pk.act_read.push_back(r);
+            pk.act_ind.push_back((uint8_t)p->read_ind[r]);
+            if (p->ent_col[cursor[r]] == k) {
+                pk.act_allele.push_back(p->ent_allele[cursor[r]]);
+                pk.act_phred.push_back(p->ent_phred[cursor[r]]);
+            } else {  // gap inside the read's span: BLANK entry, phred 0 (columniterator.cpp:131)
+                pk.act_allele.push_back(2);
+                pk.act_phred.push_back(0);
+            }
+            // kept in column k+1 ?
+            if (k + 1 < n && last[r] >= k + 1) m.keep |= 1u << j;
+        }
+        pk.act_off[k + 1] = pk.act_read.size();
+        m.f = popc32(m.keep);
+        m.d = m.a - m.f;
+        uint32_t di = 0;
+        for (uint32_t j = 0; j < m.a; ++j)
+            if (!((m.keep >> j) & 1)) m.dpos[di++] = (uint8_t)j;
+    }
+    if (n > 0 && next_read != p->n_reads) {
+        err = "read starts at a column that is not in positions";
+        return WHMEC_ERR_INPUT;
+    }
+
+    // ---- cost functions per (column, transmission value, allowed assignment)
+    pk.fn_group.assign((size_t)n * (T + 1), 0);
+    uint64_t base_total = 0, rc_total = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        ColMeta &m = pk.cols[k];
+        m.fn_off = (uint32_t)pk.fn_c0.size();
+        m.grp_off = k * (T + 1);
+        const uint64_t e0 = pk.act_off[k];
+        bool any = false;
+        uint32_t max_base = 0;
+        for (uint32_t t = 0; t < T; ++t) {
+            const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
+            pk.fn_group[m.grp_off + t] = (uint32_t)pk.fn_c0.size() - m.fn_off;
+            for (uint32_t A = 0; A < (1u << P); ++A) {
+                bool ok = true;
+                unsigned int base = 0;
+                for (uint32_t i = 0; i < p->n_ind; ++i) {
+                    uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
+                    if (p->distrust) {
+                        // pedigreecolumncostcomputer.cpp:37  `unsigned += double`
+                        double g = p->gl[((size_t)i * n + k) * 3 + (a0 + a1)];
+                        base = (unsigned int)((double)base + g);
+                    } else if (p->gt[(size_t)i * n + k] != a0 + a1) {
+                        ok = false;
+                        break;
+                    }
+                }
+                if (!ok) continue;
+                any = true;
+                max_base = std::max(max_base, base);
+                uint32_t c0 = base;
+                size_t doff = pk.fn_delta.size();
+                pk.fn_delta.resize(doff + FN_STRIDE, 0);
+                for (uint32_t j = 0; j < m.a; ++j) {
+                    uint8_t al = pk.act_allele[e0 + j];
+                    if (al > 1) continue;  // BLANK contributes nothing
+                    uint32_t w = pk.act_phred[e0 + j];
+                    uint32_t ind = pk.act_ind[e0 + j];
+                    // read on haplotype `bit` of its individual sits in partition h2p[ind][bit]; it costs
+                    // w when the allele assigned to that partition differs (cost computer :59-67)
+                    uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w : 0;
+                    uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w : 0;
+                    c0 += cost0;
+                    pk.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
+                }
+                pk.fn_c0.push_back(c0);
+                pk.fn_asg.push_back(A);
+                pk.fn_base.push_back(base);
+            }
+        }
+        pk.fn_group[m.grp_off + T] = (uint32_t)pk.fn_c0.size() - m.fn_off;
+        if (!any) {  // no transmission value admits any assignment: pedigreedptable.cpp:301-303
+            err = "Error: Mendelian conflict";
+            return WHMEC_ERR_MENDELIAN;
+        }
+        base_total += max_base;
+        rc_total += (uint64_t)m.rc * pk.tb;
+    }
+    pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 30);
+
+    // ---- chains, back-pointer layout, accounting
+    uint64_t words = 0;
+    whmec_stats &st = pk.stats;
+    for (uint32_t k = 0; k < n; ++k) {
+        ColMeta &m = pk.cols[k];
+        if (k == 0 || pk.cols[k - 1].f == 0) pk.chain_begin.push_back(k);
+        const bool lastcol = (k + 1 == n);
+        m.bp_width = round_bp_width(m.d + pk.tb);  // the last column stores its winner too (f == 0)
+        m.bp_off = words;
+        uint64_t entries = ((uint64_t)1 << m.f) * T;
+        words += (entries * m.bp_width + 31) / 32;
+        st.cells += ((uint64_t)1 << m.a) * T;
+        uint64_t bytes = (uint64_t)4 * T * ((uint64_t)1 << m.bw);
+        if (!lastcol) bytes += (uint64_t)(8 + (T > 1 ? 4 : 0)) * T * ((uint64_t)1 << m.f);
+        st.algorithmic_bytes += bytes;
+    }
+    pk.chain_begin.push_back(n);
+    pk.bp_words = words;
+    st.backptr_bytes = words * 4;
+    st.n_chains = n ? (uint32_t)pk.chain_begin.size() - 1 : 0;
+    st.max_active = max_a;
+    st.transmissions = T;
+    return WHMEC_OK;
+}
+
+int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *path_tv,
+                  whmec_solution *s, std::string &err) {
+    const uint32_t n = pk.n, P = pk.P;
+    if (s->path_index && path_index != s->path_index) std::memcpy(s->path_index, path_index, sizeof(uint32_t) * n);
+    if (s->path_tv && path_tv != s->path_tv) std::memcpy(s->path_tv, path_tv, sizeof(uint32_t) * n);
+    // get_optimal_partitioning (pedigreedptable.cpp:391-406) + core.pyx:414: a read is reported in
+    // partition 0 iff its bit is 0 in some column it is active in.
+    if (s->partition) {
+        std::memset(s->partition, 1, pk.n_reads);
+        for (uint32_t k = 0; k < n; ++k) {
+            const uint64_t e0 = pk.act_off[k];
+            for (uint32_t j = 0; j < pk.cols[k].a; ++j)
+                if (((path_index[k] >> j) & 1) == 0) s->partition[pk.act_read[e0 + j]] = 0;
+        }
+    }
+    if (!s->sr_allele && !s->sr_quality) return WHMEC_OK;
+    // get_super_reads -> get_alleles (pedigreecolumncostcomputer.cpp:117-175)
+    for (uint32_t k = 0; k < n; ++k) {
+        const ColMeta &m = pk.cols[k];
+        const uint32_t t = path_tv[k], x = path_index[k];
+        const int8_t *h2p = &pk.h2p[(size_t)t * pk.n_ind * 2];
+        uint32_t cp[MAX_P][2];
+        for (uint32_t q = 0; q < P; ++q) cp[q][0] = cp[q][1] = 0;
+        const uint64_t e0 = pk.act_off[k];
+        for (uint32_t j = 0; j < m.a; ++j) {
+            uint8_t al = pk.act_allele[e0 + j];
+            if (al > 1) continue;
+            int part = h2p[2 * pk.act_ind[e0 + j] + ((x >> j) & 1)];
+            cp[part][al == 0 ? 1 : 0] += pk.act_phred[e0 + j];
+        }
+        uint32_t best = UMAX;
+        uint32_t call[MAX_IND][2];
+        uint32_t bfa[MAX_IND][2][2];
+        for (uint32_t i = 0; i < pk.n_ind; ++i) {
+            call[i][0] = call[i][1] = 2;
+            bfa[i][0][0] = bfa[i][0][1] = bfa[i][1][0] = bfa[i][1][1] = UMAX;
+        }
+        const uint32_t g0 = m.fn_off + pk.fn_group[m.grp_off + t], g1 = m.fn_off + pk.fn_group[m.grp_off + t + 1];
+        for (uint32_t F = g0; F < g1; ++F) {
+            const uint32_t A = pk.fn_asg[F];
+            uint32_t cost = pk.fn_base[F];
+            for (uint32_t q = 0; q < P; ++q) cost += cp[q][(A >> q) & 1];
+            bool new_best = false;
+            if (cost <= best) {  // '<=': the LAST best assignment is reported (:131)
+                best = cost;
+                new_best = true;
+            }
+            for (uint32_t i = 0; i < pk.n_ind; ++i) {
+                uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
+                if (new_best) {
+                    call[i][0] = a0;
+                    call[i][1] = a1;
+                }
+                if (cost < bfa[i][0][a0]) bfa[i][0][a0] = cost;
+                if (cost < bfa[i][1][a1]) bfa[i][1][a1] = cost;
+            }
+        }
+        if (best == UMAX) {
+            err = "Error: Mendelian conflict";
+            return WHMEC_ERR_MENDELIAN;
+        }
+        for (uint32_t i = 0; i < pk.n_ind; ++i) {
+            uint32_t quality = 0;
+            for (uint32_t h = 0; h < 2; ++h) {
+                int q = std::abs((int)bfa[i][h][0] - (int)bfa[i][h][1]);  // (:162) int casts: UMAX -> -1
+                quality = (uint32_t)q;
+                if (q == 0) call[i][h] = WHMEC_ALLELE_EQUAL_SCORES;
+            }
+            if (s->sr_allele) {
+                s->sr_allele[((size_t)i * 2 + 0) * n + k] = (uint8_t)call[i][0];
+                s->sr_allele[((size_t)i * 2 + 1) * n + k] = (uint8_t)call[i][1];
+            }
+            if (s->sr_quality) s->sr_quality[(size_t)i * n + k] = quality;
+        }
+    }
+    return WHMEC_OK;
+}
+
+}  // namespace whmec
+
+extern "C" uint64_t whmec_read_sort_key(const char *name, size_t len, int32_t source_id) {
+    // ReadSet::name_and_source_id_hasher_t (src/readset.h:68-72): libstdc++'s std::hash on both parts.
+    return (uint64_t)(std::hash<std::string>()(std::string(name, len)) ^ std::hash<int>()((int)source_id));
+}

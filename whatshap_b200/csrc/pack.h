@@ -1,0 +1,43 @@
+// Host-side packer and result builder (C++; no CUDA in this translation unit).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/whmec.h"
+#include "common.h"
+
+namespace whmec {
+
+struct Packed {
+    uint32_t n = 0, n_reads = 0, n_ind = 0, n_trios = 0;
+    uint32_t T = 1, tb = 0, P = 2;
+    bool safe31 = false;                 // every reachable cost value < 2^30 (tile-kernel arithmetic is exact)
+    std::vector<ColMeta> cols;           // [n]
+    // active reads per column, CSR aligned with cols[k].a
+    std::vector<uint64_t> act_off;       // [n+1]
+    std::vector<uint32_t> act_read;      // read index of bit j
+    std::vector<uint8_t> act_allele;     // 0/1/2
+    std::vector<uint32_t> act_phred;
+    std::vector<uint8_t> act_ind;
+    // cost functions (see common.h), grouped per column and transmission value
+    std::vector<uint32_t> fn_c0;
+    std::vector<int32_t> fn_delta;       // [nf][FN_STRIDE]
+    std::vector<uint32_t> fn_asg;        // allele assignment A of the function
+    std::vector<uint32_t> fn_base;       // genotype-likelihood base cost of A
+    std::vector<uint32_t> fn_group;      // per column T+1 offsets relative to cols[k].fn_off
+    std::vector<int8_t> h2p;             // [T][n_ind][2]
+    // chains: maximal runs of columns with f > 0 between them (T == 1 only uses them)
+    std::vector<uint32_t> chain_begin;   // first column of each chain; chain c = [begin[c], begin[c+1])
+    uint64_t bp_words = 0;               // arena size in 32-bit words (column-kernel layout)
+    whmec_stats stats{};
+};
+
+// Returns WHMEC_OK or an error code with a reference-compatible message in `err`.
+int pack_problem(const whmec_problem *p, Packed &out, std::string &err);
+
+// get_optimal_partitioning + get_super_reads from the optimal path (pedigreedptable.cpp:344-406).
+int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *path_tv,
+                  whmec_solution *s, std::string &err);
+
+}  // namespace whmec

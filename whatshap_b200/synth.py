@@ -42,6 +42,8 @@ def _window_spans(n: int, c: int, stride: int, block_len: int) -> Tuple[np.ndarr
         keep = (l - f + 1) >= 2  # reads with < 2 variants are dropped upstream (cli/phase.py:518)
         firsts.append(f[keep] + b0)
         lasts.append(l[keep] + b0)
+    if not firsts:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
     return np.concatenate(firsts).astype(np.int64), np.concatenate(lasts).astype(np.int64)
 
 
