@@ -1,0 +1,126 @@
+// TEST-ONLY host emulation of the tile path: runs the host planner (tile_plan.cpp) and the
+// __host__ __device__ per-thread functions of tile_device.h serially.  See emul.cpp.
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../whatshap_b200/csrc/pack.h"
+#include "../../whatshap_b200/csrc/tile_plan.h"
+#include "../../whatshap_b200/csrc/tile_device.h"
+
+using namespace whmec;
+
+// returns 100 when the planner declares the problem not eligible for the tile path
+extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint32_t chunk, uint32_t *n_panels,
+                                 char *err, size_t errlen) {
+    Packed pk;
+    std::string msg;
+    auto fail = [&](int code) {
+        if (err && errlen) {
+            std::strncpy(err, msg.c_str(), errlen - 1);
+            err[errlen - 1] = 0;
+        }
+        return code;
+    };
+    int rc = pack_problem(p, pk, msg);
+    if (rc != WHMEC_OK) return fail(rc);
+    const uint32_t n = pk.n;
+    if (n == 0) {
+        s->cost = 0;
+        if (s->partition) std::memset(s->partition, 1, p->n_reads);
+        return WHMEC_OK;
+    }
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    if (!ts.eligible) {
+        msg = ts.why;
+        return fail(100);
+    }
+    if (n_panels) *n_panels = (uint32_t)ts.panels.size();
+    std::vector<uint32_t> state(ts.state_words + 1, 0xDEADBEEF), arena(ts.bp_words + 1, 0);
+    const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
+    std::vector<uint64_t> chain_key(n_chains, KEY_INF);
+    std::vector<uint32_t> bufA(1u << TILE_SMAX), bufB(1u << TILE_SMAX);
+    std::vector<int32_t> TL(TILE_TL_SIZE), TH(TILE_TH_SIZE);
+    for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
+        for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
+            const Panel &P = ts.panels[pi];
+            for (uint32_t t = 0; t < (1u << P.g); ++t) {
+                uint32_t *Sin = bufA.data(), *Sout = bufB.data();
+                if (P.fresh) Sin[0] = 0;
+                else {
+                    const uint32_t gpart = pdep32(t, P.gmask_in);
+                    for (uint32_t l = 0; l < (1u << P.s_in); ++l) Sin[l] = state[P.in_off + (pdep32(l, P.lmask_in) | gpart)];
+                }
+                for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
+                    const TileCol &tc = ts.cols[k];
+                    for (uint32_t i = 0; i < TILE_TL_SIZE; ++i) TL[i] = tile_tl_entry(tc, i);
+                    for (uint32_t i = 0; i < TILE_TH_SIZE; ++i) TH[i] = tile_th_entry(tc, t, i);
+                    TileCtx c{&tc, t, TL.data(), TH.data(), tile_cg(tc, t), Sin};
+                    const uint32_t m = tc.l_in + tc.n_new;
+                    if (tc.kind == 1) {
+                        const uint32_t gpart = pdep32(t, ~tc.lmask_col & low_mask(pk.cols[k].a));
+                        uint64_t best = KEY_INF;
+                        uint32_t step = chunk ? chunk : (1u << m);
+                        for (uint32_t x0 = 0; x0 < (1u << m); x0 += step) {
+                            uint32_t x1 = x0 + step < (1u << m) ? x0 + step : (1u << m);
+                            uint64_t key = tile_eval_end(c, gpart, x0, x1);
+                            if (key < best) best = key;
+                        }
+                        if (best < chain_key[P.chain]) chain_key[P.chain] = best;
+                    } else {
+                        const uint32_t ncand = 1u << tc.d;
+                        for (uint32_t o = 0; o < (1u << tc.l_out); ++o) {
+                            uint64_t best = KEY_INF;
+                            uint32_t step = chunk ? chunk : ncand;
+                            for (uint32_t r0 = 0; r0 < ncand; r0 += step) {
+                                uint32_t r1 = r0 + step < ncand ? r0 + step : ncand;
+                                uint64_t key = tile_eval(c, o, r0, r1);
+                                if (key < best) best = key;
+                            }
+                            Sout[o] = (uint32_t)(best >> 32);
+                            bp_store_serial(arena.data(), tc.bp_off + (uint64_t)t * tc.bp_tile_words, tc.bp_width, o, (uint32_t)best);
+                        }
+                        std::swap(Sin, Sout);
+                    }
+                }
+                if (!P.ends_chain) {
+                    const uint32_t gpart = pdep32(t, P.gmask_out);
+                    for (uint32_t l = 0; l < (1u << P.s_out); ++l) state[P.out_off + (pdep32(l, P.lmask_out) | gpart)] = Sin[l];
+                }
+            }
+        }
+    std::vector<uint32_t> pidx(n), ptv(n, 0);
+    uint64_t total = 0;
+    for (uint32_t c = 0; c < n_chains; ++c) {
+        total += chain_key[c] >> 32;
+        tile_backtrace_chain(pk.cols.data(), ts.cols.data(), arena.data(), pk.chain_begin[c], pk.chain_begin[c + 1] - 1,
+                             chain_key[c], pidx.data());
+    }
+    s->cost = (uint32_t)total;
+    rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+    if (rc != WHMEC_OK) return fail(rc);
+    return WHMEC_OK;
+}
+
+// planner statistics only (no DP): panels, rounds, total tiles, max tiles per round, state/bp words
+extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {
+    Packed pk;
+    std::string msg;
+    int rc = pack_problem(p, pk, msg);
+    if (rc != WHMEC_OK) return rc;
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    if (!ts.eligible) return 100;
+    out8[0] = ts.panels.size();
+    out8[1] = ts.round_tiles.size();
+    uint64_t tot = 0, mx = 0;
+    for (uint32_t t : ts.round_tiles) { tot += t; mx = std::max<uint64_t>(mx, t); }
+    out8[2] = tot;
+    out8[3] = mx;
+    out8[4] = ts.state_words;
+    out8[5] = ts.bp_words;
+    out8[6] = ts.state_traffic_bytes;
+    out8[7] = pk.stats.algorithmic_bytes;
+    return 0;
+}

@@ -10,12 +10,32 @@ pytestmark = pytest.mark.gpu
 PEDS = ["single", "single", "trio", "quartet", "two_unrelated", "trio_child_first", "three_generations"]
 
 
-def assert_same(gpu, checker, prob, label=""):
+def assert_same(gpu, checker, prob, label="", want_path=None):
     want, werr = solve_or_error(checker.solve, prob)
-    got, gerr = solve_or_error(lambda p: gpu.solve(p)[0], prob)
+    stats = {}
+
+    def run(p):
+        sol, st = gpu.solve(p)
+        stats.update(st)
+        return sol
+
+    got, gerr = solve_or_error(run, prob)
     assert werr == gerr, (label, werr, gerr)
     if want is not None:
         assert got.same_as(want), (label, got.diff(want))
+        if want_path is not None and prob.n_cols:
+            assert stats["path_kind"] == want_path, (label, stats)
+
+
+@pytest.fixture(params=["tile", "column"])
+def kernel_path(request, monkeypatch):
+    """Single-individual problems run on the tile kernel by default; the env hook forces the
+    general column kernel so that both CUDA paths are held to the same oracle."""
+    if request.param == "column":
+        monkeypatch.setenv("WHMEC_FORCE_COLUMN_KERNEL", "1")
+        return 2
+    monkeypatch.delenv("WHMEC_FORCE_COLUMN_KERNEL", raising=False)
+    return 1
 
 
 @pytest.mark.parametrize("seed", range(8))
@@ -41,10 +61,34 @@ def test_fuzz_irregular_instances(gpu, checker, seed):
     "n,c,stride,block,gap",
     [(120, 10, 1, 50, 0.0), (90, 8, 2, 45, 0.1), (64, 12, 1, 32, 0.0), (40, 14, 1, 20, 0.05), (30, 16, 1, 30, 0.0)],
 )
-def test_sliding_window_blocks(gpu, checker, n, c, stride, block, gap):
+def test_sliding_window_blocks(gpu, checker, kernel_path, n, c, stride, block, gap):
     """Coverage-capped single-individual ReadSets; chain ends drop up to c reads at once."""
     prob = synth.sliding_window(n, c, stride=stride, block_len=block, seed=n * 31 + c, gap=gap)
-    assert_same(gpu, checker, prob)
+    assert_same(gpu, checker, prob, want_path=kernel_path)
+
+
+@pytest.mark.parametrize("n,c,block", [(70, 17, 35), (40, 19, 40), (48, 20, 24)])
+def test_sliding_window_multi_tile(gpu, checker, kernel_path, n, c, block):
+    """Coverage above one tile (2^14 entries): the projection column is cut along global reads."""
+    prob = synth.sliding_window(n, c, block_len=block, seed=n + c)
+    assert_same(gpu, checker, prob, want_path=kernel_path)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_fuzz_single_individual_both_paths(gpu, checker, kernel_path, seed):
+    rng = np.random.default_rng(77 + seed)
+    for it in range(60):
+        prob = synth.random_problem(
+            rng,
+            int(rng.integers(1, 40)),
+            int(rng.integers(1, 11)),
+            "single",
+            distrust=bool(rng.integers(0, 2)),
+            conflict_free=bool(rng.integers(0, 4)),
+            max_phred=int(rng.integers(1, 8)),
+            mean_len=float(rng.choice([2, 4, 8])),
+        )
+        assert_same(gpu, checker, prob, f"seed={seed} it={it}", want_path=kernel_path)
 
 
 def test_trio_blocks(gpu, checker):

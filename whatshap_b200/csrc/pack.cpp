@@ -140,6 +140,9 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
         }
     }
 
+    pk.read_first = first;
+    pk.read_last = last;
+
     // ---- columns
     pk.cols.resize(n);
     pk.act_off.assign(n + 1, 0);
@@ -254,7 +257,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
         base_total += max_base;
         rc_total += (uint64_t)m.rc * pk.tb;
     }
-    pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 30);
+    pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 28);
 
     // ---- chains, back-pointer layout, accounting
     uint64_t words = 0;

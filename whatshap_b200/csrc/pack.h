@@ -27,6 +27,7 @@ struct Packed {
     std::vector<uint32_t> fn_base;       // genotype-likelihood base cost of A
     std::vector<uint32_t> fn_group;      // per column T+1 offsets relative to cols[k].fn_off
     std::vector<int8_t> h2p;             // [T][n_ind][2]
+    std::vector<uint32_t> read_first, read_last;  // column span of every read
     // chains: maximal runs of columns with f > 0 between them (T == 1 only uses them)
     std::vector<uint32_t> chain_begin;   // first column of each chain; chain c = [begin[c], begin[c+1])
     uint64_t bp_words = 0;               // arena size in 32-bit words (column-kernel layout)

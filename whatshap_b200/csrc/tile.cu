@@ -1,9 +1,292 @@
+// Tile kernel: single-individual weighted MEC with the projection column held in shared memory.
+//
+// One CTA owns one tile (2^s entries of the projection column, all bipartitions of the s
+// tile-local reads for one fixed assignment of the global reads) and sweeps a whole panel of
+// consecutive columns without touching HBM except for the packed back-pointer stream; see
+// tile_plan.h for the decomposition and tile_device.h for the per-cell arithmetic.
+// Replaces PedigreeDPTable::compute_column (src/pedigreedptable.cpp:177-335) for T == 1.
 #include "tile.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
 #include "../../include/whmec.h"
+#include "tile_device.h"
+#include "tile_plan.h"
+
 namespace whmec {
-bool tile_path_eligible(const Packed &) { return false; }
-int TilePlan::create(const Packed &, cudaStream_t, uint64_t &, std::string &msg) { msg = "tile path not built"; return WHMEC_ERR_UNSUPPORTED; }
-int TilePlan::sweep(const Packed &, cudaStream_t, std::string &msg) { msg = "tile path not built"; return WHMEC_ERR_UNSUPPORTED; }
-int TilePlan::backtrace(const Packed &, cudaStream_t, uint32_t *, uint32_t *, std::string &msg) { msg = "tile path not built"; return WHMEC_ERR_UNSUPPORTED; }
-void TilePlan::release() {}
+
+namespace {
+
+constexpr int NT = 1024;  // threads per tile
+constexpr uint32_t TILE_ENTRIES = 1u << TILE_SMAX;
+
+struct TileSmem {
+    uint32_t buf[2][TILE_ENTRIES];
+    int32_t TL[TILE_TL_SIZE];
+    int32_t TH[TILE_TH_SIZE];
+    unsigned long long keys[NT];
+    TileCol tc;
+    Panel P;
+    uint32_t cg;
+    uint32_t a_col;
+};
+
+#define CUDA_TRY(expr)                                                    \
+    do {                                                                  \
+        cudaError_t _e = (expr);                                          \
+        if (_e != cudaSuccess) {                                          \
+            msg = std::string(#expr) + ": " + cudaGetErrorString(_e);     \
+            return WHMEC_ERR_CUDA;                                        \
+        }                                                                 \
+    } while (0)
+
+__device__ __forceinline__ void bp_store_warp_tile(uint32_t *words, uint32_t width, uint32_t e, uint32_t value, bool valid) {
+    if (width == 0) return;
+    const uint32_t per = 32u / width;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t sub = lane % per;
+    uint32_t word = valid ? (value << (sub * width)) : 0u;
+    for (uint32_t off = 1; off < per; off <<= 1) word |= __shfl_xor_sync(0xFFFFFFFFu, word, off);
+    if (sub == 0 && valid) words[e / per] = word;
 }
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long key) {
+    for (int off = 16; off > 0; off >>= 1) {
+        unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = other < key ? other : key;
+    }
+    return key;
+}
+
+// pdep of an index whose low 10 bits are the thread id: split so that only the high part is
+// recomputed per iteration.
+__device__ __forceinline__ uint32_t mask_without_low_bits(uint32_t mask, uint32_t nbits) {
+    for (uint32_t i = 0; i < nbits && mask; ++i) mask &= mask - 1;
+    return mask;
+}
+
+__global__ void __launch_bounds__(NT, 1)
+tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const TileCol *__restrict__ tcols,
+                  const ColMeta *__restrict__ cols, uint32_t *__restrict__ state, uint32_t *__restrict__ arena,
+                  unsigned long long *__restrict__ chain_keys) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+
+    // which panel does this CTA belong to?  panels[] is sorted by tile_begin within the launch
+    if (tid == 0) {
+        uint32_t lo = 0, hi = n_panels;
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (panels[mid].tile_begin <= blockIdx.x) lo = mid;
+            else hi = mid;
+        }
+        S.a_col = lo;
+    }
+    __syncthreads();
+    {
+        const uint32_t pi = S.a_col;
+        __syncthreads();
+        if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[pi])[tid];
+    }
+    __syncthreads();
+    const Panel &P = S.P;
+    const uint32_t tile = blockIdx.x - P.tile_begin;
+    uint32_t cur = 0;
+
+    // ---- load the tile's slice of the incoming projection column (canonical layout in HBM)
+    if (P.fresh) {
+        if (tid == 0) S.buf[0][0] = 0;
+    } else {
+        const uint32_t nin = 1u << P.s_in;
+        const uint32_t gpart = pdep32(tile, P.gmask_in);
+        const uint32_t lo = pdep32(tid, P.lmask_in);
+        const uint32_t himask = mask_without_low_bits(P.lmask_in, 10);
+        const uint32_t *src = state + P.in_off;
+        for (uint32_t l = tid, it = 0; l < nin; l += NT, ++it) S.buf[0][l] = src[lo | pdep32(it, himask) | gpart];
+    }
+
+    for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
+        __syncthreads();
+        if (tid < sizeof(TileCol) / 4) ((uint32_t *)&S.tc)[tid] = ((const uint32_t *)&tcols[k])[tid];
+        if (tid == 1023) S.a_col = cols[k].a;
+        __syncthreads();
+        const TileCol &tc = S.tc;
+        if (tid < TILE_TL_SIZE) S.TL[tid] = tile_tl_entry(tc, tid);
+        else if (tid < TILE_TL_SIZE + TILE_TH_SIZE) S.TH[tid - TILE_TL_SIZE] = tile_th_entry(tc, tile, tid - TILE_TL_SIZE);
+        else if (tid == TILE_TL_SIZE + TILE_TH_SIZE) S.cg = tile_cg(tc, tile);
+        __syncthreads();
+        TileCtx c{&tc, tile, S.TL, S.TH, S.cg, S.buf[cur]};
+        uint32_t *Sout = S.buf[cur ^ 1];
+        const uint32_t m = tc.l_in + tc.n_new;
+
+        if (tc.kind == 1) {
+            // chain end: every read ends here -> one global minimum per chain, ordered by the
+            // reference's Gray-code visiting rank of the canonical index
+            const uint32_t ncell = 1u << m;
+            const uint32_t gpart = pdep32(tile, ~tc.lmask_col & low_mask(S.a_col));
+            const uint32_t per = ncell >= NT ? ncell / NT : 1;
+            unsigned long long key = KEY_INF;
+            if (tid * per < ncell) key = tile_eval_end(c, gpart, tid * per, tid * per + per);
+            key = warp_min_u64(key);
+            if ((tid & 31) == 0) S.keys[tid >> 5] = key;
+            __syncthreads();
+            if (tid < 32) {
+                key = warp_min_u64(S.keys[tid]);
+                if (tid == 0) atomicMin(&chain_keys[P.chain], key);
+            }
+        } else {
+            const uint32_t nout = 1u << tc.l_out;
+            const uint32_t ncand = 1u << tc.d;
+            uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
+            if (nout >= NT) {
+                for (uint32_t o = tid; o < nout; o += NT) {
+                    const unsigned long long key = tile_eval(c, o, 0, ncand);
+                    Sout[o] = (uint32_t)(key >> 32);
+                    bp_store_warp_tile(bpw, tc.bp_width, o, (uint32_t)key, true);
+                }
+            } else {
+                // few outputs: split every output's candidates over several threads
+                const uint32_t spare = 10u - tc.l_out;
+                const uint32_t log_chunks = spare < tc.d ? spare : tc.d;
+                const uint32_t items = nout << log_chunks;
+                if (tid < nout) S.keys[tid] = KEY_INF;
+                __syncthreads();
+                unsigned long long key = KEY_INF;
+                const uint32_t o = tid >> log_chunks;
+                if (tid < items) {
+                    const uint32_t ch = tid & ((1u << log_chunks) - 1);
+                    const uint32_t per = ncand >> log_chunks;
+                    key = tile_eval(c, o, ch * per, (ch + 1) * per);
+                }
+                if (log_chunks >= 5) {
+                    key = warp_min_u64(key);
+                    if ((tid & 31) == 0 && tid < items) atomicMin(&S.keys[o], key);
+                } else if (tid < items) {
+                    atomicMin(&S.keys[o], key);
+                }
+                __syncthreads();
+                key = tid < nout ? S.keys[tid] : 0ull;
+                if (tid < nout) Sout[tid] = (uint32_t)(key >> 32);
+                bp_store_warp_tile(bpw, tc.bp_width, tid, (uint32_t)key, tid < nout);
+            }
+            cur ^= 1;
+        }
+    }
+
+    // ---- write the tile back in canonical layout for the next panel
+    if (!P.ends_chain) {
+        __syncthreads();
+        const uint32_t nout = 1u << P.s_out;
+        const uint32_t gpart = pdep32(tile, P.gmask_out);
+        const uint32_t lo = pdep32(tid, P.lmask_out);
+        const uint32_t himask = mask_without_low_bits(P.lmask_out, 10);
+        uint32_t *dst = state + P.out_off;
+        for (uint32_t l = tid, it = 0; l < nout; l += NT, ++it) dst[lo | pdep32(it, himask) | gpart] = S.buf[cur][l];
+    }
+}
+
+__global__ void tile_backtrace_kernel(const ColMeta *__restrict__ cols, const TileCol *__restrict__ tcols,
+                                      const uint32_t *__restrict__ arena, const uint32_t *__restrict__ chain_begin,
+                                      uint32_t n_chains, const unsigned long long *__restrict__ chain_keys,
+                                      uint32_t *__restrict__ path_index, uint32_t *__restrict__ result) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chains) return;
+    const unsigned long long key = chain_keys[c];
+    tile_backtrace_chain(cols, tcols, arena, chain_begin[c], chain_begin[c + 1] - 1, key, path_index);
+    atomicAdd(&result[0], (uint32_t)(key >> 32));  // cost = sum over DP-independent chains
+}
+
+struct TileImpl {
+    TileSchedule ts;
+    ColMeta *d_cols = nullptr;
+    TileCol *d_tcols = nullptr;
+    Panel *d_panels = nullptr;
+    uint32_t *d_state = nullptr, *d_arena = nullptr, *d_chain_begin = nullptr;
+    unsigned long long *d_chain_keys = nullptr;
+    uint32_t n_chains = 0;
+};
+
+}  // namespace
+
+bool TilePlan::plan(const Packed &pk) {
+    TileImpl *I = new TileImpl();
+    plan_tiles(pk, I->ts);
+    if (!I->ts.eligible) {
+        why = I->ts.why;
+        delete I;
+        return false;
+    }
+    impl = I;
+    backptr_bytes = I->ts.bp_words * 4;
+    state_bytes = I->ts.state_traffic_bytes;
+    return true;
+}
+
+int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::string &msg) {
+    TileImpl *I = (TileImpl *)impl;
+    const TileSchedule &ts = I->ts;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t need = (ts.state_words + ts.bp_words + 2) * 4 + (uint64_t)pk.n * (sizeof(TileCol) + sizeof(ColMeta)) +
+                          ts.panels.size() * sizeof(Panel);
+    if (need + (512ull << 20) > free_b) {
+        msg = "tile path: state + back-pointer storage exceeds the free HBM of this device";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
+    I->n_chains = (uint32_t)pk.chain_begin.size() - 1;
+    CUDA_TRY(cudaMalloc((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta)));
+    CUDA_TRY(cudaMalloc((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol)));
+    CUDA_TRY(cudaMalloc((void **)&I->d_panels, ts.panels.size() * sizeof(Panel)));
+    CUDA_TRY(cudaMalloc((void **)&I->d_state, (ts.state_words + 1) * 4));
+    CUDA_TRY(cudaMalloc((void **)&I->d_arena, (ts.bp_words + 1) * 4));
+    CUDA_TRY(cudaMalloc((void **)&I->d_chain_begin, pk.chain_begin.size() * 4));
+    CUDA_TRY(cudaMalloc((void **)&I->d_chain_keys, (size_t)I->n_chains * 8));
+    auto up = [&](void *dst, const void *src, size_t bytes) {
+        h2d += bytes;
+        return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
+    };
+    CUDA_TRY(up(I->d_cols, pk.cols.data(), (size_t)pk.n * sizeof(ColMeta)));
+    CUDA_TRY(up(I->d_tcols, ts.cols.data(), (size_t)pk.n * sizeof(TileCol)));
+    CUDA_TRY(up(I->d_panels, ts.panels.data(), ts.panels.size() * sizeof(Panel)));
+    CUDA_TRY(up(I->d_chain_begin, pk.chain_begin.data(), pk.chain_begin.size() * 4));
+    CUDA_TRY(cudaFuncSetAttribute(tile_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    return WHMEC_OK;
+}
+
+int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
+    TileImpl *I = (TileImpl *)impl;
+    const TileSchedule &ts = I->ts;
+    CUDA_TRY(cudaMemsetAsync(I->d_chain_keys, 0xFF, (size_t)I->n_chains * 8, stream));
+    launches = 0;
+    for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r) {
+        const uint32_t p0 = ts.round_begin[r], p1 = ts.round_begin[r + 1];
+        tile_panel_kernel<<<ts.round_tiles[r], NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, I->d_tcols, I->d_cols,
+                                                                                I->d_state, I->d_arena, I->d_chain_keys);
+        ++launches;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return WHMEC_OK;
+}
+
+int TilePlan::backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg) {
+    TileImpl *I = (TileImpl *)impl;
+    CUDA_TRY(cudaMemsetAsync(d_result, 0, 16, stream));
+    tile_backtrace_kernel<<<(I->n_chains + 63) / 64, 64, 0, stream>>>(I->d_cols, I->d_tcols, I->d_arena, I->d_chain_begin,
+                                                                       I->n_chains, I->d_chain_keys, d_path_index, d_result);
+    CUDA_TRY(cudaGetLastError());
+    return WHMEC_OK;
+}
+
+void TilePlan::release() {
+    TileImpl *I = (TileImpl *)impl;
+    if (!I) return;
+    cudaFree(I->d_cols); cudaFree(I->d_tcols); cudaFree(I->d_panels); cudaFree(I->d_state);
+    cudaFree(I->d_arena); cudaFree(I->d_chain_begin); cudaFree(I->d_chain_keys);
+    delete I;
+    impl = nullptr;
+}
+
+}  // namespace whmec

@@ -8,13 +8,14 @@
 
 namespace whmec {
 
-bool tile_path_eligible(const Packed &pk);
-
 struct TilePlan {
     uint64_t backptr_bytes = 0;
-    uint64_t state_bytes = 0;
+    uint64_t state_bytes = 0;     // projection state moved through global memory by one sweep
     uint32_t launches = 0;
+    std::string why;              // reason when plan() returns false
     void *impl = nullptr;
+    // Host-only: decide whether the tile path applies and build its schedule.
+    bool plan(const Packed &pk);
     int create(const Packed &pk, cudaStream_t stream, uint64_t &h2d_bytes, std::string &msg);
     int sweep(const Packed &pk, cudaStream_t stream, std::string &msg);
     int backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg);

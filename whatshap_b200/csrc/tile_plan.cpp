@@ -1,0 +1,269 @@
+// Host planner of the tile path: cuts every DP-independent chain into panels (see tile_plan.h).
+#include "tile_plan.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace whmec {
+
+namespace {
+
+struct ChainCtx {
+    const Packed *pk;
+    uint32_t chain, k0, k1;  // columns [k0, k1], k1 is the chain end (f == 0)
+};
+
+// reads of column k in canonical order
+inline const uint32_t *col_reads(const Packed &pk, uint32_t k) { return &pk.act_read[pk.act_off[k]]; }
+
+uint32_t mask_of(const std::vector<uint32_t> &all, const std::vector<uint32_t> &subset_sorted) {
+    uint32_t m = 0;
+    for (size_t i = 0; i < all.size(); ++i)
+        if (std::binary_search(subset_sorted.begin(), subset_sorted.end(), all[i])) m |= 1u << i;
+    return m;
+}
+
+}  // namespace
+
+void plan_tiles(const Packed &pk, TileSchedule &ts) {
+    ts = TileSchedule();
+    if (pk.T != 1 || pk.n_ind != 1) {
+        ts.why = "more than one individual (the tile kernel covers the single-individual cost form)";
+        return;
+    }
+    if (!pk.safe31) {
+        ts.why = "cost range exceeds the exact range of the tile arithmetic";
+        return;
+    }
+    const uint32_t n = pk.n;
+    ts.cols.assign(n, TileCol());
+    const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
+    std::vector<std::vector<Panel>> per_chain(n_chains);
+    uint64_t state_words = 0, bp_words = 0;
+
+    for (uint32_t c = 0; c < n_chains; ++c) {
+        const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1] - 1;
+        uint32_t fmax = 0;
+        for (uint32_t k = k0; k <= k1; ++k) fmax = std::max(fmax, pk.cols[k].f);
+        const uint64_t buf_words = (uint64_t)1 << fmax;
+        const uint64_t chain_state = state_words;
+        state_words += 2 * buf_words;
+        uint32_t pcount = 0;
+
+        std::vector<uint32_t> state;  // reads kept after column k-1, canonical (ascending) order
+        uint32_t k = k0;
+        while (k <= k1) {
+            const ColMeta &m0 = pk.cols[k];
+            const uint32_t fin = (uint32_t)state.size();
+            const uint32_t n_new0 = m0.a - m0.bw;
+            if (fin != m0.bw && !(k == k0 && m0.bw == 0)) {
+                ts.why = "internal: state/backward width mismatch";
+                return;
+            }
+            // Candidates for the tile-local bits: the reads of the incoming state plus the reads
+            // that start in this column (at a panel's first column new reads may become global, which
+            // is how a chain that starts with more reads than one tile holds is cut).
+            const uint32_t *reads0 = col_reads(pk, k);
+            std::vector<uint32_t> cand = state;
+            for (uint32_t q = m0.bw; q < m0.a; ++q) cand.push_back(reads0[q]);
+            auto by_last = [&](uint32_t a, uint32_t b) { return pk.read_last[a] < pk.read_last[b]; };
+            std::vector<uint32_t> old_by_end = state, new_by_end(cand.begin() + state.size(), cand.end());
+            std::stable_sort(old_by_end.begin(), old_by_end.end(), by_last);
+            std::stable_sort(new_by_end.begin(), new_by_end.end(), by_last);
+            // Local bits: the soonest-ending old reads (as many as the input buffer holds) and then the
+            // soonest-ending new reads; everything else is global for this panel.
+            int s_try = (int)std::min<uint32_t>((uint32_t)cand.size(), TILE_MMAX);
+            bool placed = false;
+            uint32_t last_size = 0xFFFFFFFFu;
+            for (; s_try >= 0 && !placed; --s_try) {
+                const uint32_t l_old = std::min<uint32_t>({(uint32_t)state.size(), TILE_SMAX, (uint32_t)s_try});
+                const uint32_t l_new = std::min<uint32_t>(n_new0, (uint32_t)s_try - l_old);
+                const uint32_t s0 = l_old + l_new;
+                if (s0 == last_size) continue;
+                last_size = s0;
+                if (cand.size() - s0 > TILE_GMAX) break;
+                std::vector<uint32_t> Lold(old_by_end.begin(), old_by_end.begin() + l_old);
+                std::vector<uint32_t> Gold(old_by_end.begin() + l_old, old_by_end.end());
+                std::vector<uint32_t> L = Lold, G = Gold;
+                L.insert(L.end(), new_by_end.begin(), new_by_end.begin() + l_new);
+                G.insert(G.end(), new_by_end.begin() + l_new, new_by_end.end());
+                std::sort(L.begin(), L.end());
+                std::sort(G.begin(), G.end());
+                std::sort(Lold.begin(), Lold.end());
+                std::sort(Gold.begin(), Gold.end());
+                const uint32_t n_new_local0 = (uint32_t)(L.size() - Lold.size());
+                std::vector<uint32_t> Lcur = Lold;
+                std::vector<TileCol> accepted;
+                uint32_t j = k;
+                bool ends_chain = false;
+                for (; j <= k1; ++j) {
+                    const ColMeta &m = pk.cols[j];
+                    const uint32_t *reads = col_reads(pk, j);
+                    const uint32_t n_new = (j == k) ? n_new_local0 : (m.a - m.bw);
+                    const uint32_t l_in = (uint32_t)Lcur.size();
+                    const uint32_t mm = l_in + n_new;
+                    if (mm > TILE_MMAX) break;
+                    std::vector<uint32_t> cur = Lcur;
+                    for (uint32_t q = m.bw; q < m.a; ++q)  // new reads are the top bits (global ones excluded)
+                        if (j != k || std::binary_search(L.begin(), L.end(), reads[q])) cur.push_back(reads[q]);
+                    const bool chain_end = (m.f == 0);
+                    uint32_t dropmask = 0, d = 0;
+                    bool drops_global = false;
+                    for (uint32_t q = 0; q < m.a; ++q)
+                        if (!((m.keep >> q) & 1)) {
+                            auto it = std::find(cur.begin(), cur.end(), reads[q]);
+                            if (it == cur.end()) drops_global = true;
+                            else {
+                                dropmask |= 1u << (uint32_t)(it - cur.begin());
+                                ++d;
+                            }
+                        }
+                    if (!chain_end && drops_global) break;
+                    const uint32_t l_out = mm - d;
+                    if (!chain_end && l_out > TILE_SMAX) break;
+                    TileCol tc;
+                    std::memset(&tc, 0, sizeof tc);
+                    tc.l_in = (uint8_t)l_in;
+                    tc.n_new = (uint8_t)n_new;
+                    tc.kind = chain_end ? 1 : 0;
+                    tc.g = (uint8_t)G.size();
+                    if (chain_end) {
+                        tc.d = (uint8_t)mm;
+                        tc.l_out = 0;
+                        tc.dropmask = low_mask(mm);
+                    } else {
+                        tc.d = (uint8_t)d;
+                        tc.l_out = (uint8_t)l_out;
+                        tc.dropmask = dropmask;
+                    }
+                    // costs: K_A = cost of assignment A at x = 0 (pack.cpp), signed read weights
+                    uint32_t K0 = TILE_KINF, K1 = TILE_KINF, K2 = TILE_KINF;
+                    const uint32_t g0 = m.fn_off + pk.fn_group[m.grp_off], g1 = m.fn_off + pk.fn_group[m.grp_off + 1];
+                    for (uint32_t F = g0; F < g1; ++F) {
+                        const uint32_t A = pk.fn_asg[F], c0 = pk.fn_c0[F];
+                        if (A == 0 || A == 3) K0 = std::min(K0, c0);
+                        else if (A == 1) K1 = c0;
+                        else K2 = c0;
+                    }
+                    tc.K0 = K0;
+                    tc.K2 = (int32_t)K2;
+                    tc.K12 = K1 + K2;
+                    const uint64_t e0 = pk.act_off[j];
+                    auto weight_of = [&](uint32_t read) -> int32_t {
+                        for (uint32_t q = 0; q < m.a; ++q)
+                            if (reads[q] == read) {
+                                uint8_t al = pk.act_allele[e0 + q];
+                                int32_t w = (int32_t)pk.act_phred[e0 + q];
+                                return al == 0 ? w : (al == 1 ? -w : 0);
+                            }
+                        return 0;
+                    };
+                    uint32_t lmask_col = 0;
+                    for (uint32_t q = 0; q < mm; ++q) {
+                        tc.w_local[q] = weight_of(cur[q]);
+                        for (uint32_t z = 0; z < m.a; ++z)
+                            if (reads[z] == cur[q]) lmask_col |= 1u << z;
+                    }
+                    tc.lmask_col = lmask_col;
+                    for (uint32_t b = 0; b < G.size(); ++b) tc.w_global[b] = weight_of(G[b]);
+                    uint32_t di = 0;
+                    for (uint32_t q = 0; q < mm; ++q)
+                        if ((tc.dropmask >> q) & 1) {
+                            if (di < 16) {
+                                tc.dpos[di] = (uint8_t)q;
+                                uint32_t ga = 0;
+                                for (uint32_t b = 0; b < G.size(); ++b)
+                                    if (G[b] > cur[q]) ga |= 1u << b;
+                                tc.gabove[di] = ga;
+                            }
+                            ++di;
+                        }
+                    // state after this column
+                    std::vector<uint32_t> nextL;
+                    for (uint32_t q = 0; q < mm; ++q)
+                        if (!((tc.dropmask >> q) & 1)) nextL.push_back(cur[q]);
+                    if (!chain_end) {
+                        std::vector<uint32_t> kept;
+                        for (uint32_t q = 0; q < m.a; ++q)
+                            if ((m.keep >> q) & 1) kept.push_back(reads[q]);
+                        tc.gmask_out = mask_of(kept, G);
+                    }
+                    accepted.push_back(tc);
+                    Lcur.swap(nextL);
+                    if (chain_end) {
+                        ends_chain = true;
+                        ++j;
+                        break;
+                    }
+                }
+                if (accepted.empty()) continue;  // try a smaller tile
+                // commit the panel [k, j)
+                Panel P;
+                std::memset(&P, 0, sizeof P);
+                P.chain = c;
+                P.col_begin = k;
+                P.col_end = j;
+                P.g = (uint32_t)G.size();
+                P.s_in = (uint32_t)Lold.size();
+                P.lmask_in = mask_of(state, Lold);
+                P.gmask_in = mask_of(state, Gold);
+                P.ends_chain = ends_chain ? 1 : 0;
+                P.fresh = (k == k0) ? 1 : 0;
+                P.in_off = chain_state + (uint64_t)(pcount & 1) * buf_words;
+                P.out_off = chain_state + (uint64_t)((pcount + 1) & 1) * buf_words;
+                std::vector<uint32_t> kept;
+                if (!ends_chain) {
+                    const ColMeta &ml = pk.cols[j - 1];
+                    const uint32_t *reads = col_reads(pk, j - 1);
+                    for (uint32_t q = 0; q < ml.a; ++q)
+                        if ((ml.keep >> q) & 1) kept.push_back(reads[q]);
+                    P.s_out = (uint32_t)Lcur.size();
+                    P.lmask_out = mask_of(kept, Lcur);
+                    P.gmask_out = mask_of(kept, G);
+                    ts.state_traffic_bytes += 2ull * 4ull * ((uint64_t)1 << kept.size());
+                }
+                for (uint32_t q = k; q < j; ++q) {
+                    TileCol &tc = accepted[q - k];
+                    tc.bp_width = tc.kind == 1 ? 0 : round_bp_width(tc.d);
+                    tc.bp_off = bp_words;
+                    // every tile's slice starts on a word boundary
+                    uint64_t per_tile_words = ((((uint64_t)1 << tc.l_out) * tc.bp_width) + 31) / 32;
+                    tc.bp_tile_words = (uint32_t)per_tile_words;
+                    bp_words += per_tile_words << tc.g;
+                    ts.cols[q] = tc;
+                }
+                per_chain[c].push_back(P);
+                ++pcount;
+                state.swap(kept);
+                k = j;
+                placed = true;
+            }
+            if (!placed) {
+                ts.why = "a column drops more reads at once than a tile can hold";
+                return;
+            }
+        }
+    }
+
+    // launch rounds: round r = r-th panel of every chain that has one
+    size_t max_panels = 0;
+    for (auto &v : per_chain) max_panels = std::max(max_panels, v.size());
+    for (size_t r = 0; r < max_panels; ++r) {
+        ts.round_begin.push_back((uint32_t)ts.panels.size());
+        uint32_t tiles = 0;
+        for (uint32_t c = 0; c < n_chains; ++c)
+            if (r < per_chain[c].size()) {
+                Panel P = per_chain[c][r];
+                P.tile_begin = tiles;
+                tiles += 1u << P.g;
+                ts.panels.push_back(P);
+            }
+        ts.round_tiles.push_back(tiles);
+    }
+    ts.round_begin.push_back((uint32_t)ts.panels.size());
+    ts.state_words = state_words;
+    ts.bp_words = bp_words;
+    ts.eligible = true;
+}
+
+}  // namespace whmec

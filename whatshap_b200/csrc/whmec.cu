@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -239,7 +240,8 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     uint64_t h2d = 0;
 
-    pl->use_tiles = tile_path_eligible(pk);
+    const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
+    pl->use_tiles = !(force && force[0] == '1') && pl->tiles.plan(pk);
     if (pl->use_tiles) {
         rc = pl->tiles.create(pk, pl->stream, h2d, msg);
         if (rc != WHMEC_OK) return rc;
