@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the weighted-MEC / PedMEC column sweep (the hot path of `whatshap phase`).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3] [--impl ours|reference]
+
+One "step" = one complete forward sweep of the DP over the synthetic workload (all variant
+columns of all DP-independent blocks).  Metric: variant-columns per second (BASELINE.json).
+
+  value      device-timed sweep with the packed ReadSet already resident in HBM
+  e2e        the same workload through the C-ABI call `whmec_solve` with HOST buffers:
+             packing, allocation, host->device copies, sweep, device backtrace, device->host
+             copies and super-read construction are all inside the timed region
+  roofline   algorithmic bytes / device time of the dominant kernel vs the measured
+             HBM copy bandwidth of this pool (MEASURED_PEAKS.json)
+  cpu_baseline  the UNMODIFIED reference C++ (oracle/_ref) or the C restatement, single thread,
+             on a bounded prefix of the same workload
+
+`--impl reference` times the reference's own CPU implementation on all host cores (independent
+block prefixes in parallel; each instance is single-threaded like the reference).
+Multi-GPU (torchrun): every rank sweeps its own full-size workload (independent chromosomes /
+blocks; weak scaling), no data-path collective; a barrier and max-over-ranks bracket the timing.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "variant_columns_per_sec"
+UNIT = "columns/s"
+WORKLOADS = {
+    # name: (description, columns, coverage, T)
+    "cfg2": ("synthetic diploid ReadSet: 10k variants, max-coverage 15, single individual", 10_000, 15, 1),
+    "cfg3": ("synthetic diploid ReadSet: 50k variants, max-coverage 20, 100 independent blocks", 50_000, 20, 1),
+    "cfg4": ("synthetic diploid ReadSet: 50k variants, max-coverage 25, one block (2^25 bipartitions)", 50_000, 25, 1),
+    "cfg5": ("synthetic trio Pedigree (3 individuals, recombination cost on): 20k variants, coverage 15", 20_000, 15, 4),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cols", type=int, default=None, help="override the number of variant columns")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload):
+    """dram bytes per tile-kernel launch from the committed ncu capture, if one exists."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(workload)
+    return None
+
+
+def make_workload(name, cols, rank):
+    from whatshap_b200 import synth
+
+    prob = synth.config(name, cols)
+    if rank:  # other ranks phase other chromosomes: same shape, different reads
+        from whatshap_b200.synth import SEEDS, sliding_window, trio
+
+        n = prob.n_cols
+        if name == "cfg5":
+            prob = trio(n, 5, block_len=500, seed=SEEDS[name] + rank)
+        else:
+            cov = WORKLOADS[name][2]
+            prob = sliding_window(n, cov, block_len=(n if name == "cfg4" else 500), seed=SEEDS[name] + rank)
+    return prob
+
+
+def cpu_sample(name, prob, target_cols):
+    """A bounded prefix of block 0 with the same structure (reads clipped to the prefix)."""
+    from whatshap_b200 import synth
+    from whatshap_b200.synth import SEEDS
+
+    cov = WORKLOADS[name][2]
+    if name == "cfg5":
+        return synth.trio(target_cols, 5, block_len=target_cols, seed=SEEDS[name])
+    return synth.sliding_window(target_cols, cov, block_len=target_cols, seed=SEEDS[name])
+
+
+CPU_SAMPLE_COLS = {"cfg2": 4000, "cfg3": 160, "cfg4": 6, "cfg5": 1500}
+
+
+def run_cpu_baseline(name, prob):
+    from oracle import checker
+
+    ref = checker.reference()
+    cols = CPU_SAMPLE_COLS[name]
+    if ref is None:  # only the C restatement travelled: it is much slower than the reference, shrink the sample
+        ck, kind, cols = checker.port(), "port", max(2, cols // 8)
+    else:
+        ck, kind = ref, "reference"
+    sample = cpu_sample(name, prob, cols)
+    t0 = time.perf_counter()
+    ck.solve(sample)
+    dt = ck.last_seconds if kind == "reference" else time.perf_counter() - t0
+    return {"value": cols / dt, "unit": UNIT, "cores": 1, "kind": kind,
+            "sample": f"{cols}-column prefix of block 0 of {name} (same generator, same coverage), {dt:.2f} s single thread"}
+
+
+def bench_reference(args, rank, world):
+    """Reference arm: the unmodified C++ PedigreeDPTable on all host cores."""
+    if rank != 0:
+        return
+    from oracle import checker
+
+    name = args.workload
+    ref = checker.reference()
+    threads = os.cpu_count() or 1
+    from whatshap_b200 import synth
+    from whatshap_b200.synth import SEEDS
+
+    cov = WORKLOADS[name][2]
+
+    def make(cols, count):  # one independent block prefix per host thread
+        out = []
+        for i in range(count):
+            if name == "cfg5":
+                out.append(synth.trio(cols, 5, block_len=cols, seed=SEEDS[name] + 1000 + i))
+            else:
+                out.append(synth.sliding_window(cols, cov, block_len=cols, seed=SEEDS[name] + 1000 + i))
+        return out
+
+    # size a step to ~4 s of wall time on this host: calibrate with a tiny batch first (all host
+    # threads contend for memory bandwidth, so per-thread speed is far below the single-thread figure)
+    cols = 4
+    if ref is not None:
+        t_cal = ref.solve_many_timed(make(cols, threads), threads)
+        cols = int(min(max(4, cols * 4.0 / max(t_cal, 1e-3)), CPU_SAMPLE_COLS[name]))
+    probs = make(cols, threads)
+    if ref is not None:
+        kind = "reference"
+        step = lambda: ref.solve_many_timed(probs, threads)
+    else:
+        kind = "port"
+        port = checker.port()
+
+        def step():
+            t0 = time.perf_counter()
+            for p in probs[:1]:
+                port.solve(p)
+            return (time.perf_counter() - t0)
+        probs = probs[:1]
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total_cols = cols * len(probs)
+    value = total_cols * len(times) / sum(times)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": name, "description": WORKLOADS[name][0],
+                   "sample": f"{len(probs)} independent {cols}-column block prefixes per step, one per host thread"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind == "reference" else 1, "kind": kind,
+                         "sample": f"{len(probs)} x {cols} columns per step"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        bench_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from whatshap_b200 import _lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path in whatshap_b200)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    name = args.workload
+    prob = make_workload(name, args.cols, rank)
+    n_cols = prob.n_cols
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident sweep ------------------------------------------------------------
+    plan = _lib.Plan(prob, device=local_rank)
+    for _ in range(max(args.warmup, 3)):
+        plan.sweep()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    sweep_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict the previous step's state / back-pointers from L2 (not timed)
+        torch.cuda.synchronize()
+        plan.sweep()    # timed on the launching stream with CUDA events inside the library
+        sweep_ms.append(plan.stats()["sweep_ms"])
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    stats = plan.stats()
+    sol = plan.finish()
+    plan.close()
+    total_ms = sum(sweep_ms)
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cols_t = torch.tensor([float(n_cols)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cols_t, op=dist.ReduceOp.SUM)
+    max_ms = float(t.item())
+    all_cols = float(cols_t.item())
+    value = all_cols * args.steps / (max_ms / 1e3)
+
+    # ---- end to end through the C ABI with host buffers ------------------------------------
+    _lib.solve(prob, device=local_rank)  # warm-up (context, allocator)
+    barrier()
+    e2e_t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        sol2, st2 = _lib.solve(prob, device=local_rank)
+    barrier()
+    e2e_dt = time.perf_counter() - e2e_t0
+    assert sol2.same_as(sol), "resident and end-to-end runs disagree"
+    e2e_t = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = all_cols * e2e_steps / float(e2e_t.item())
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        launches = int(stats["kernel_launches"])
+        achieved = stats["algorithmic_bytes"] / (statistics.mean(sweep_ms) / 1e3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": {
+                "workload": name, "description": WORKLOADS[name][0], "columns_per_gpu": n_cols,
+                "coverage": WORKLOADS[name][2], "transmission_vectors": WORKLOADS[name][3],
+                "chains": int(stats["n_chains"]), "kernel_path": {1: "tile", 2: "column"}.get(int(stats["path_kind"]), "mixed"),
+                "l2": "512 MiB buffer rewritten between timed steps (L2 flush)", "sharding": "one full-size workload per GPU, no collective on the data path",
+                "optimal_cost_rank0": int(sol.cost), "wall_s_timed_region": wall,
+            },
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": recorded_traffic(name), "peak_source": peak_src,
+                "kernel": "tile_panel_kernel" if int(stats["path_kind"]) == 1 else "col_direct_kernel",
+                "algorithmic_bytes_per_step": int(stats["algorithmic_bytes"]), "launches_per_step": launches,
+                "bytes_moved_per_step": {"backpointers": int(stats["backptr_bytes"]), "state": int(stats["state_bytes"])},
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
+                    "ms_per_step": 1e3 * float(e2e_t.item()) / e2e_steps, "steps": e2e_steps,
+                    "note": "whmec_solve: host CSR arrays in, host result arrays out (pack + alloc + H2D + sweep + backtrace + D2H)"},
+            "gpu_launches": launches * args.steps,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = run_cpu_baseline(name, prob)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

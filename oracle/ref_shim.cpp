@@ -171,3 +171,20 @@ int whref_solve_many(const whmec_problem *const *ps, uint32_t n, uint32_t n_thre
 const char *whref_info(void) { return "whatshap reference C++ (PedigreeDPTable), compiled in place by oracle/Makefile"; }
 
 }  // extern "C"
+
+// ReadSet::sort() of the reference (src/readset.cpp:42-51, comparator src/readset.h:39-66) on
+// reads given by (name, source_id, first position): writes the resulting order.  Lets the tests pin
+// the product's ReadSet.sort() tie-breaking to the real thing.
+extern "C" int whref_sort_order(uint32_t n, const char *const *names, const int32_t *source_ids, const int32_t *firsts,
+                                uint32_t *order) {
+    ReadSet rs;
+    for (uint32_t i = 0; i < n; ++i) {
+        Read *r = new Read(names[i], 0, source_ids[i], (int)i);  // sample id carries the input index
+        r->addVariant(firsts[i], 0, 1);
+        r->addVariant(firsts[i] + 5, 1, 1);
+        rs.add(r);
+    }
+    rs.sort();
+    for (uint32_t i = 0; i < n; ++i) order[i] = (uint32_t)rs.get(i)->getSampleID();
+    return 0;
+}
