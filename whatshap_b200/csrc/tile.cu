@@ -22,16 +22,70 @@ namespace {
 constexpr int NT = 1024;  // threads per tile
 constexpr uint32_t TILE_ENTRIES = 1u << TILE_SMAX;
 
+constexpr uint32_t TC_CHUNK = 16;  // column descriptors staged in shared memory at a time
+
 struct TileSmem {
     uint32_t buf[2][TILE_ENTRIES];
-    int32_t TL[TILE_TL_SIZE];
-    int32_t TH[TILE_TH_SIZE];
+    int32_t TL[2][TILE_TL_SIZE];
+    int32_t TH[2][TILE_TH_SIZE];
     unsigned long long keys[NT];
-    TileCol tc;
+    TileCol tcs[TC_CHUNK];
     Panel P;
-    uint32_t cg;
-    uint32_t a_col;
+    uint32_t cg[2];
+    uint32_t a_col[TC_CHUNK];
+    uint32_t panel_index;
 };
+
+// Tables of one column (see tile_device.h): threads 0..384 each produce one entry.
+__device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uint32_t tile, uint32_t which, uint32_t tid) {
+    if (tid < TILE_TL_SIZE) S.TL[which][tid] = tile_tl_entry(tc, tid);
+    else if (tid < TILE_TL_SIZE + TILE_TH_SIZE) S.TH[which][tid - TILE_TL_SIZE] = tile_th_entry(tc, tile, tid - TILE_TL_SIZE);
+    else if (tid == TILE_TL_SIZE + TILE_TH_SIZE) S.cg[which] = tile_cg(tc, tile);
+}
+
+// Steady-state column: exactly one read ends (d == 1), at least one output per thread.
+// Per output: two candidate cells that differ in the dropped bit; the reference's visiting order
+// makes the candidate whose dropped bit equals the parity of the bits above it the earlier one.
+__device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *__restrict__ TL, const int32_t *__restrict__ TH,
+                                             uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout,
+                                             uint32_t *__restrict__ bpw, uint32_t tid) {
+    const uint32_t p = tc.dpos[0];
+    const uint32_t lowm = (1u << p) - 1u;
+    const uint32_t pbit = 1u << p;
+    const uint32_t inmask = low_mask(tc.l_in);
+    const uint32_t wp = (uint32_t)tc.w_local[p];
+    const uint32_t K0 = tc.K0, K12 = tc.K12, cg0 = cg & 1u;
+    const uint32_t nout = 1u << tc.l_out;
+#pragma unroll 4
+    for (uint32_t o = tid; o < nout; o += NT) {
+        const uint32_t hi = o >> p;
+        const uint32_t x0 = ((hi << 1) << p) | (o & lowm);
+        const uint32_t u0 = (uint32_t)(TL[x0 & (TILE_TL_SIZE - 1)] + TH[x0 >> TILE_TL_BITS]);
+        const uint32_t u1 = u0 + wp;
+        const uint32_t c0 = min(K0, min(u0, K12 - u0));
+        const uint32_t c1 = min(K0, min(u1, K12 - u1));
+        const uint32_t v0 = c0 + Sin[x0 & inmask];
+        const uint32_t v1 = c1 + Sin[(x0 | pbit) & inmask];
+        const uint32_t par = (__popc(hi) + cg0) & 1u;
+        const uint32_t pick1 = par ? (v1 <= v0) : (v1 < v0);
+        Sout[o] = min(v0, v1);
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, (pick1 ^ par) != 0);
+        if ((tid & 31u) == 0) bpw[o >> 5] = ballot;
+    }
+}
+
+// Column in which no read ends (coverage still growing): one cell per output, no back-pointer.
+__device__ __forceinline__ void column_drop0(const TileCol &tc, const int32_t *__restrict__ TL, const int32_t *__restrict__ TH,
+                                             const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, uint32_t tid) {
+    const uint32_t inmask = low_mask(tc.l_in);
+    const uint32_t K0 = tc.K0, K12 = tc.K12;
+    const uint32_t nout = 1u << tc.l_out;
+#pragma unroll 4
+    for (uint32_t o = tid; o < nout; o += NT) {
+        const uint32_t u = (uint32_t)(TL[o & (TILE_TL_SIZE - 1)] + TH[o >> TILE_TL_BITS]);
+        Sout[o] = min(K0, min(u, K12 - u)) + Sin[o & inmask];
+    }
+}
 
 #define CUDA_TRY(expr)                                                    \
     do {                                                                  \
@@ -83,14 +137,10 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
             if (panels[mid].tile_begin <= blockIdx.x) lo = mid;
             else hi = mid;
         }
-        S.a_col = lo;
+        S.panel_index = lo;
     }
     __syncthreads();
-    {
-        const uint32_t pi = S.a_col;
-        __syncthreads();
-        if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[pi])[tid];
-    }
+    if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[S.panel_index])[tid];
     __syncthreads();
     const Panel &P = S.P;
     const uint32_t tile = blockIdx.x - P.tile_begin;
@@ -109,16 +159,24 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
     }
 
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
-        __syncthreads();
-        if (tid < sizeof(TileCol) / 4) ((uint32_t *)&S.tc)[tid] = ((const uint32_t *)&tcols[k])[tid];
-        if (tid == 1023) S.a_col = cols[k].a;
-        __syncthreads();
-        const TileCol &tc = S.tc;
-        if (tid < TILE_TL_SIZE) S.TL[tid] = tile_tl_entry(tc, tid);
-        else if (tid < TILE_TL_SIZE + TILE_TH_SIZE) S.TH[tid - TILE_TL_SIZE] = tile_th_entry(tc, tile, tid - TILE_TL_SIZE);
-        else if (tid == TILE_TL_SIZE + TILE_TH_SIZE) S.cg = tile_cg(tc, tile);
-        __syncthreads();
-        TileCtx c{&tc, tile, S.TL, S.TH, S.cg, S.buf[cur]};
+        const uint32_t j = (k - P.col_begin) % TC_CHUNK;
+        if (j == 0) {
+            // stage the next TC_CHUNK column descriptors (previous chunk is no longer referenced)
+            __syncthreads();
+            const uint32_t ncol = min(TC_CHUNK, P.col_end - k);
+            constexpr uint32_t WORDS = sizeof(TileCol) / 4;
+            for (uint32_t w = tid; w < ncol * WORDS; w += NT)
+                ((uint32_t *)S.tcs)[w] = ((const uint32_t *)(tcols + k))[w];
+            if (tid < ncol) S.a_col[tid] = cols[k + tid].a;
+            __syncthreads();
+            build_tables(S, S.tcs[0], tile, k & 1u, tid);
+        }
+        __syncthreads();  // tables of column k ready; previous column's outputs complete
+        // tables of column k+1 are produced while column k is evaluated (double buffered)
+        if (j + 1 < TC_CHUNK && k + 1 < P.col_end) build_tables(S, S.tcs[j + 1], tile, (k + 1) & 1u, tid);
+        const TileCol &tc = S.tcs[j];
+        const uint32_t tb = k & 1u;
+        TileCtx c{&tc, tile, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur]};
         uint32_t *Sout = S.buf[cur ^ 1];
         const uint32_t m = tc.l_in + tc.n_new;
 
@@ -126,7 +184,7 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
             // chain end: every read ends here -> one global minimum per chain, ordered by the
             // reference's Gray-code visiting rank of the canonical index
             const uint32_t ncell = 1u << m;
-            const uint32_t gpart = pdep32(tile, ~tc.lmask_col & low_mask(S.a_col));
+            const uint32_t gpart = pdep32(tile, ~tc.lmask_col & low_mask(S.a_col[j]));
             const uint32_t per = ncell >= NT ? ncell / NT : 1;
             unsigned long long key = KEY_INF;
             if (tid * per < ncell) key = tile_eval_end(c, gpart, tid * per, tid * per + per);
@@ -141,7 +199,11 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
             const uint32_t nout = 1u << tc.l_out;
             const uint32_t ncand = 1u << tc.d;
             uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
-            if (nout >= NT) {
+            if (nout >= NT && tc.d == 1) {
+                column_drop1(tc, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
+            } else if (nout >= NT && tc.d == 0) {
+                column_drop0(tc, S.TL[tb], S.TH[tb], S.buf[cur], Sout, tid);
+            } else if (nout >= NT) {
                 for (uint32_t o = tid; o < nout; o += NT) {
                     const unsigned long long key = tile_eval(c, o, 0, ncand);
                     Sout[o] = (uint32_t)(key >> 32);
