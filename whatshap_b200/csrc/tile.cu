@@ -28,6 +28,8 @@ struct TileSmem {
     uint32_t buf[2][TILE_ENTRIES];
     int32_t TL[2][TILE_TL_SIZE];
     int32_t TH[2][TILE_TH_SIZE];
+    int32_t T9[2][512];   // fast path: K2 + E(global bits) + weights of output bits 5..13
+    int32_t T5[2][32];    // fast path: weights of output bits 0..4 (the lane)
     unsigned long long keys[NT];
     TileCol tcs[TC_CHUNK];
     Panel P;
@@ -36,8 +38,36 @@ struct TileSmem {
     uint32_t panel_index;
 };
 
+// The steady-state column of a coverage-capped ReadSet: the oldest local read (local bit 0) ends,
+// enough outputs for every thread.  It gets a kernel path whose inner loop has no index arithmetic.
+__device__ __forceinline__ bool is_fast_column(const TileCol &tc) {
+    return tc.kind == 0 && tc.d == 1 && tc.dpos[0] == 0 && tc.l_out >= 10 && tc.l_in >= 1 && tc.l_in + 4 >= tc.l_out;
+}
+
 // Tables of one column (see tile_device.h): threads 0..384 each produce one entry.
 __device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uint32_t tile, uint32_t which, uint32_t tid) {
+    if (is_fast_column(tc)) {
+        // indexed by the OUTPUT index o (= cell index without the dropped bit 0): o bit q <-> local bit q+1
+        if (tid < 512) {
+            int32_t s = tc.K2;
+            for (uint32_t b = 0; b < tc.g; ++b)
+                if ((tile >> b) & 1u) s += tc.w_global[b];
+#pragma unroll
+            for (uint32_t q = 0; q < 9; ++q)
+                if ((tid >> q) & 1u) s += tc.w_local[q + 6];
+            S.T9[which][tid] = s;
+        } else if (tid < 512 + 32) {
+            const uint32_t l = tid - 512;
+            int32_t s = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < 5; ++q)
+                if ((l >> q) & 1u) s += tc.w_local[q + 1];
+            S.T5[which][l] = s;
+        } else if (tid == 512 + 32) {
+            S.cg[which] = tile_cg(tc, tile);
+        }
+        return;
+    }
     if (tid < TILE_TL_SIZE) S.TL[which][tid] = tile_tl_entry(tc, tid);
     else if (tid < TILE_TL_SIZE + TILE_TH_SIZE) S.TH[which][tid - TILE_TL_SIZE] = tile_th_entry(tc, tile, tid - TILE_TL_SIZE);
     else if (tid == TILE_TL_SIZE + TILE_TH_SIZE) S.cg[which] = tile_cg(tc, tile);
@@ -72,6 +102,42 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, (pick1 ^ par) != 0);
         if ((tid & 31u) == 0) bpw[o >> 5] = ballot;
     }
+}
+
+// Fast path of column_drop1 for dropped bit 0 (see is_fast_column).  Warp w owns the 32*ITERS
+// consecutive outputs starting at w*32*ITERS; all shared-memory addresses inside the loop are
+// per-thread bases plus compile-time offsets, the two candidate cells of an output share one 64-bit
+// load, and each warp emits its ITERS back-pointer words with one coalesced store.
+template <int ITERS>
+__device__ __forceinline__ void column_drop1_p0(const TileCol &tc, const int32_t *__restrict__ T9, const int32_t *__restrict__ T5,
+                                                uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout,
+                                                uint32_t *__restrict__ bpw, uint32_t tid) {
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t obase = warp * (ITERS * 32u) + lane;  // o = obase + 32*it
+    const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;   // candidate pairs of the previous projection
+    const uint2 *sin2 = reinterpret_cast<const uint2 *>(Sin) + (obase & pmask);
+    const int32_t *t9 = T9 + warp * ITERS;
+    const uint32_t e_lane = (uint32_t)T5[lane];
+    uint32_t *so = Sout + obase;
+    const uint32_t wp = (uint32_t)tc.w_local[0];
+    const uint32_t K0 = tc.K0, K12 = tc.K12;
+    const uint32_t par0 = (__popc(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
+    uint32_t myword = 0;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+        const uint32_t u0 = e_lane + (uint32_t)t9[it];
+        const uint32_t u1 = u0 + wp;
+        const uint32_t c0 = min(K0, min(u0, K12 - u0));
+        const uint32_t c1 = min(K0, min(u1, K12 - u1));
+        const uint2 s = sin2[it * 32];
+        const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
+        const uint32_t par = par0 ^ (uint32_t)(__builtin_popcount((unsigned)it) & 1);
+        const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
+        so[it * 32] = min(v0, v1);
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (par != 0));
+        if (lane == (uint32_t)it) myword = ballot;
+    }
+    if (lane < (uint32_t)ITERS) bpw[warp * ITERS + lane] = myword;
 }
 
 // Column in which no read ends (coverage still growing): one cell per output, no back-pointer.
@@ -199,7 +265,15 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
             const uint32_t nout = 1u << tc.l_out;
             const uint32_t ncand = 1u << tc.d;
             uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
-            if (nout >= NT && tc.d == 1) {
+            if (is_fast_column(tc)) {
+                switch (tc.l_out) {
+                    case 10: column_drop1_p0<1>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+                    case 11: column_drop1_p0<2>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+                    case 12: column_drop1_p0<4>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+                    case 13: column_drop1_p0<8>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+                    default: column_drop1_p0<16>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+                }
+            } else if (nout >= NT && tc.d == 1) {
                 column_drop1(tc, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
             } else if (nout >= NT && tc.d == 0) {
                 column_drop0(tc, S.TL[tb], S.TH[tb], S.buf[cur], Sout, tid);
