@@ -48,7 +48,13 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
             for (uint32_t t = 0; t < (1u << P.g); ++t) {
                 uint32_t *Sin = bufA.data(), *Sout = bufB.data();
                 if (P.fresh) Sin[0] = 0;
-                else {
+                else if (P.in_layout == 1) {
+                    const uint32_t told = t & low_mask(P.in_gold);
+                    for (uint32_t i = 0; i < (1u << P.s_in); ++i) {
+                        const uint32_t tA = i & low_mask(P.in_gA), ll = i >> P.in_gA;
+                        Sin[i] = state[P.in_off + ((uint64_t)told << P.in_j) + ((uint64_t)tA << P.in_sA) + ll];
+                    }
+                } else {
                     const uint32_t gpart = pdep32(t, P.gmask_in);
                     for (uint32_t l = 0; l < (1u << P.s_in); ++l) Sin[l] = state[P.in_off + (pdep32(l, P.lmask_in) | gpart)];
                 }
@@ -84,7 +90,9 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                         std::swap(Sin, Sout);
                     }
                 }
-                if (!P.ends_chain) {
+                if (!P.ends_chain && P.out_layout == 1) {
+                    for (uint32_t l = 0; l < (1u << P.s_out); ++l) state[P.out_off + ((uint64_t)t << P.s_out) + l] = Sin[l];
+                } else if (!P.ends_chain) {
                     const uint32_t gpart = pdep32(t, P.gmask_out);
                     for (uint32_t l = 0; l < (1u << P.s_out); ++l) state[P.out_off + (pdep32(l, P.lmask_out) | gpart)] = Sin[l];
                 }
@@ -122,5 +130,22 @@ extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {
     out8[5] = ts.bp_words;
     out8[6] = ts.state_traffic_bytes;
     out8[7] = pk.stats.algorithmic_bytes;
+    return 0;
+}
+
+// number of panel hand-offs that use the tile-major state layout / total hand-offs
+extern "C" int whemul_plan_handoffs(const whmec_problem *p, uint64_t *out2) {
+    Packed pk;
+    std::string msg;
+    int rc = pack_problem(p, pk, msg);
+    if (rc != WHMEC_OK) return rc;
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    if (!ts.eligible) return 100;
+    out2[0] = out2[1] = 0;
+    for (const Panel &P : ts.panels) {
+        if (!P.fresh) out2[1]++;
+        if (P.in_layout == 1) out2[0]++;
+    }
     return 0;
 }

@@ -212,9 +212,47 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
     const uint32_t tile = blockIdx.x - P.tile_begin;
     uint32_t cur = 0;
 
-    // ---- load the tile's slice of the incoming projection column (canonical layout in HBM)
+    // ---- load the tile's slice of the incoming projection column
     if (P.fresh) {
         if (tid == 0) S.buf[0][0] = 0;
+    } else if (P.in_layout == 1) {
+        // tile-major hand-off: one contiguous 2^j chunk from each of the 2^gA producer tiles, transposed
+        // through the second buffer (XOR-swizzled so that both passes are bank-conflict free) into
+        // the canonical local order  index = (chunk offset << gA) | producer tile.
+        const uint32_t gA = P.in_gA, jb = P.in_j, nin = 1u << P.s_in;
+        const uint32_t told = tile & low_mask(P.in_gold);
+        const uint32_t *src = state + P.in_off + ((uint64_t)told << jb);
+        const uint32_t jmask = (1u << jb) - 1u, amask = (1u << gA) - 1u;
+        const uint32_t sh = gA <= 5 ? 5 - gA : 0;
+        // staging index of element (producer tile tA, offset ll): a bijection of [0, 2^s_in) chosen so
+        // that 32 consecutive (tA, ll) in either order hit 32 different banks
+        auto sidx = [=](uint32_t tA, uint32_t ll) -> uint32_t {
+            if (jb >= 5) return (tA << jb) + (ll ^ ((tA << sh) & 31u));
+            const uint32_t idx = (tA << jb) + ll;
+            return idx ^ ((idx >> 5) & jmask);
+        };
+        uint32_t *stage = gA ? S.buf[1] : S.buf[0];
+        for (uint32_t e0 = tid; e0 < nin; e0 += 8 * NT) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t e = e0 + u * NT;
+                if (e < nin) v[u] = src[((uint64_t)(e >> jb) << P.in_sA) + (e & jmask)];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t e = e0 + u * NT;
+                const uint32_t tA = e >> jb;
+                if (e < nin) stage[gA ? sidx(tA, e & jmask) : e] = v[u];
+            }
+        }
+        if (gA) {
+            __syncthreads();
+            for (uint32_t i = tid; i < nin; i += NT) {
+                const uint32_t tA = i & amask, ll = i >> gA;
+                S.buf[0][i] = stage[sidx(tA, ll)];
+            }
+        }
     } else {
         const uint32_t nin = 1u << P.s_in;
         const uint32_t gpart = pdep32(tile, P.gmask_in);
@@ -313,7 +351,18 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
     }
 
     // ---- write the tile back in canonical layout for the next panel
-    if (!P.ends_chain) {
+    if (!P.ends_chain && P.out_layout == 1) {
+        __syncthreads();
+        const uint32_t nout = 1u << P.s_out;
+        uint32_t *dst = state + P.out_off + ((uint64_t)tile << P.s_out);
+        if (P.s_out >= 2) {
+            const uint4 *b4 = reinterpret_cast<const uint4 *>(S.buf[cur]);
+            uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+            for (uint32_t v = tid; v < (nout >> 2); v += NT) d4[v] = b4[v];
+        } else {
+            if (tid < nout) dst[tid] = S.buf[cur][tid];
+        }
+    } else if (!P.ends_chain) {
         __syncthreads();
         const uint32_t nout = 1u << P.s_out;
         const uint32_t gpart = pdep32(tile, P.gmask_out);

@@ -39,6 +39,8 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     ts.cols.assign(n, TileCol());
     const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
     std::vector<std::vector<Panel>> per_chain(n_chains);
+    struct PanelSets { std::vector<uint32_t> G, Lout, Lold, Gold; };
+    std::vector<std::vector<PanelSets>> per_chain_sets(n_chains);
     uint64_t state_words = 0, bp_words = 0;
 
     for (uint32_t c = 0; c < n_chains; ++c) {
@@ -232,7 +234,9 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     bp_words += per_tile_words << tc.g;
                     ts.cols[q] = tc;
                 }
+                P.in_gold = (uint32_t)Gold.size();
                 per_chain[c].push_back(P);
+                per_chain_sets[c].push_back(PanelSets{G, Lcur, Lold, Gold});
                 ++pcount;
                 state.swap(kept);
                 k = j;
@@ -244,6 +248,26 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             }
         }
     }
+
+    // hand-off layouts between consecutive panels of a chain (see Panel in tile_plan.h)
+    for (uint32_t c = 0; c < n_chains; ++c)
+        for (size_t q = 0; q + 1 < per_chain[c].size(); ++q) {
+            Panel &A = per_chain[c][q], &B = per_chain[c][q + 1];
+            const PanelSets &sa = per_chain_sets[c][q], &sb = per_chain_sets[c][q + 1];
+            if (A.ends_chain) continue;
+            if (!sa.G.empty() && !sa.Lout.empty() && sa.G.back() > sa.Lout.front()) continue;  // producer's global reads must be the oldest
+            if (sb.Lold.size() < sa.G.size()) continue;
+            const size_t j = sb.Lold.size() - sa.G.size();
+            if (j < 2 || j > sa.Lout.size()) continue;  // chunks of at least 4 entries
+            std::vector<uint32_t> want = sa.G;
+            want.insert(want.end(), sa.Lout.begin(), sa.Lout.begin() + j);
+            if (want != sb.Lold) continue;
+            A.out_layout = 1;
+            B.in_layout = 1;
+            B.in_gA = (uint32_t)sa.G.size();
+            B.in_j = (uint32_t)j;
+            B.in_sA = A.s_out;
+        }
 
     // launch rounds: round r = r-th panel of every chain that has one
     size_t max_panels = 0;

@@ -58,6 +58,15 @@ struct Panel {
     uint32_t ends_chain;           // last column is the chain end: no state is written
     uint32_t fresh;                // first panel of its chain: the input state is the single value 0
     uint32_t tile_begin;           // first CTA of this panel inside its launch
+    // State hand-off layout between consecutive panels of a chain.  0 = canonical (the reference's
+    // forward-projection index).  1 = tile-major: the producer tile t writes its 2^s_out entries
+    // contiguously at (t << s_out); possible when the consumer's local reads are the producer's
+    // global reads plus the LOW j local bits of the producer (the steady state), so that every
+    // consumer tile gathers one contiguous 2^j chunk from each producer tile.
+    uint32_t in_layout, out_layout;
+    uint32_t in_gA, in_j, in_sA;   // tile-major input: producer's global bits, chunk bits, producer's s_out
+    uint32_t in_gold;              // number of consumer tile-id bits that come from the old state
+    uint32_t pad;
     uint64_t in_off, out_off;      // 32-bit word offsets of the chain's state buffers
 };
 
