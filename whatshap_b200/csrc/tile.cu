@@ -38,32 +38,34 @@ struct TileSmem {
     uint32_t panel_index;
 };
 
-// The steady-state column of a coverage-capped ReadSet: the oldest local read (local bit 0) ends,
-// enough outputs for every thread.  It gets a kernel path whose inner loop has no index arithmetic.
-__device__ __forceinline__ bool is_fast_column(const TileCol &tc) {
-    return tc.kind == 0 && tc.d == 1 && tc.dpos[0] == 0 && tc.l_out >= 10 && tc.l_in >= 1 && tc.l_in + 4 >= tc.l_out;
-}
+// The steady-state column of a coverage-capped ReadSet: the oldest local read (local bit 0) ends and
+// there are enough outputs for every thread.  The planner marks such columns (TileCol::pad0):
+//   1  fast:        every thread produces 2^LG outputs
+//   2  fast+share:  exactly one read starts in this column: outputs o and o + nout/2 (new read on side
+//                   0 / 1) use the same two previous values, so one thread produces both from one load
+// TileCol::pad1 = LG.  Output index o = cell index without the dropped bit 0: o bit q <-> local bit q+1.
+__device__ __forceinline__ uint32_t fast_kind(const TileCol &tc) { return tc.pad0; }
 
 // Tables of one column (see tile_device.h): threads 0..384 each produce one entry.
 __device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uint32_t tile, uint32_t which, uint32_t tid) {
-    if (is_fast_column(tc)) {
-        // indexed by the OUTPUT index o (= cell index without the dropped bit 0): o bit q <-> local bit q+1
-        if (tid < 512) {
+    if (fast_kind(tc)) {
+        const uint32_t lg = tc.pad1;
+        if (tid < 32) {  // per-warp part: K2 + E(global reads of this tile) + output bits 5+LG .. 9+LG
             int32_t s = tc.K2;
             for (uint32_t b = 0; b < tc.g; ++b)
                 if ((tile >> b) & 1u) s += tc.w_global[b];
 #pragma unroll
-            for (uint32_t q = 0; q < 9; ++q)
-                if ((tid >> q) & 1u) s += tc.w_local[q + 6];
+            for (uint32_t q = 0; q < 5; ++q)
+                if ((tid >> q) & 1u) s += tc.w_local[6 + lg + q];
             S.T9[which][tid] = s;
-        } else if (tid < 512 + 32) {
-            const uint32_t l = tid - 512;
+        } else if (tid < 64) {  // per-lane part: output bits 0..4
+            const uint32_t l = tid - 32;
             int32_t s = 0;
 #pragma unroll
             for (uint32_t q = 0; q < 5; ++q)
                 if ((l >> q) & 1u) s += tc.w_local[q + 1];
             S.T5[which][l] = s;
-        } else if (tid == 512 + 32) {
+        } else if (tid == 64) {
             S.cg[which] = tile_cg(tc, tile);
         }
         return;
@@ -104,40 +106,61 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
     }
 }
 
-// Fast path of column_drop1 for dropped bit 0 (see is_fast_column).  Warp w owns the 32*ITERS
-// consecutive outputs starting at w*32*ITERS; all shared-memory addresses inside the loop are
-// per-thread bases plus compile-time offsets, the two candidate cells of an output share one 64-bit
-// load, and each warp emits its ITERS back-pointer words with one coalesced store.
-template <int ITERS>
-__device__ __forceinline__ void column_drop1_p0(const TileCol &tc, const int32_t *__restrict__ T9, const int32_t *__restrict__ T5,
-                                                uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout,
-                                                uint32_t *__restrict__ bpw, uint32_t tid) {
+// plain expressions (no recursion, no calls) so that they fold to constants once the loops are unrolled
+#define cx_ctz(x) (((x) & 1) ? 0 : ((x) & 2) ? 1 : ((x) & 4) ? 2 : ((x) & 8) ? 3 : 4)
+#define cx_parity(x) ((((x) >> 0) ^ ((x) >> 1) ^ ((x) >> 2) ^ ((x) >> 3) ^ ((x) >> 4)) & 1)
+
+// Fast path of column_drop1 for dropped bit 0 (see fast_kind).  Warp w owns 32 * 2^LG consecutive
+// outputs; every shared-memory address inside the loop is a per-thread base plus a compile-time
+// offset, the E() of the 2^LG outputs of a thread are subset sums built with one add each, the two
+// candidate cells of an output share one 64-bit load (and with SHARE the two outputs that differ
+// only in the newly started read share it too), back-pointers leave as warp ballots.
+template <int LG, bool HASK0, bool SHARE>
+__device__ __forceinline__ void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
+                                            uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout,
+                                            uint32_t *__restrict__ bpw, uint32_t tid) {
+    constexpr int IT = 1 << LG;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
-    const uint32_t obase = warp * (ITERS * 32u) + lane;  // o = obase + 32*it
-    const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;   // candidate pairs of the previous projection
+    const uint32_t obase = warp * (IT * 32u) + lane;      // o = obase + 32*it  (+ nout/2 for the shared twin)
+    const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;    // candidate pairs of the previous projection
     const uint2 *sin2 = reinterpret_cast<const uint2 *>(Sin) + (obase & pmask);
-    const int32_t *t9 = T9 + warp * ITERS;
-    const uint32_t e_lane = (uint32_t)T5[lane];
     uint32_t *so = Sout + obase;
+    const uint32_t half = 1u << (tc.l_out - 1);
     const uint32_t wp = (uint32_t)tc.w_local[0];
+    const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
     const uint32_t K0 = tc.K0, K12 = tc.K12;
     const uint32_t par0 = (__popc(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
-    uint32_t myword = 0;
+    uint32_t *bp = bpw + warp * IT;
+    uint32_t ue[IT];
+    ue[0] = (uint32_t)(TW[warp] + T5[lane]);
 #pragma unroll
-    for (int it = 0; it < ITERS; ++it) {
-        const uint32_t u0 = e_lane + (uint32_t)t9[it];
-        const uint32_t u1 = u0 + wp;
-        const uint32_t c0 = min(K0, min(u0, K12 - u0));
-        const uint32_t c1 = min(K0, min(u1, K12 - u1));
+    for (int it = 1; it < IT; ++it) ue[it] = ue[it & (it - 1)] + (uint32_t)tc.w_local[6 + cx_ctz(it)];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
         const uint2 s = sin2[it * 32];
-        const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
-        const uint32_t par = par0 ^ (uint32_t)(__builtin_popcount((unsigned)it) & 1);
-        const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
-        so[it * 32] = min(v0, v1);
-        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (par != 0));
-        if (lane == (uint32_t)it) myword = ballot;
+        const uint32_t par = par0 ^ (uint32_t)cx_parity(it);
+        {
+            const uint32_t u0 = ue[it], u1 = u0 + wp;
+            uint32_t c0 = min(u0, K12 - u0), c1 = min(u1, K12 - u1);
+            if (HASK0) { c0 = min(c0, K0); c1 = min(c1, K0); }
+            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
+            const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
+            so[it * 32] = min(v0, v1);
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (par != 0));
+            bp[it] = ballot;  // all lanes store the same word to the same address: one transaction, no divergence
+        }
+        if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
+            const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
+            uint32_t c0 = min(u0, K12 - u0), c1 = min(u1, K12 - u1);
+            if (HASK0) { c0 = min(c0, K0); c1 = min(c1, K0); }
+            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
+            const uint32_t parb = par ^ 1u;
+            const bool pick1 = v1 < v0 + parb;
+            so[half + it * 32] = min(v0, v1);
+            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (parb != 0));
+            bp[(half >> 5) + it] = ballot;
+        }
     }
-    if (lane < (uint32_t)ITERS) bpw[warp * ITERS + lane] = myword;
 }
 
 // Column in which no read ends (coverage still growing): one cell per output, no back-pointer.
@@ -303,14 +326,27 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
             const uint32_t nout = 1u << tc.l_out;
             const uint32_t ncand = 1u << tc.d;
             uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
-            if (is_fast_column(tc)) {
-                switch (tc.l_out) {
-                    case 10: column_drop1_p0<1>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
-                    case 11: column_drop1_p0<2>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
-                    case 12: column_drop1_p0<4>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
-                    case 13: column_drop1_p0<8>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
-                    default: column_drop1_p0<16>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); break;
+            if (fast_kind(tc)) {
+#define WHMEC_FAST(LGV, SH)                                                                                      \
+    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); \
+    else column_fast<LGV, true, SH>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
+                if (fast_kind(tc) == 2) {
+                    switch (tc.pad1) {
+                        case 0: WHMEC_FAST(0, true) break;
+                        case 1: WHMEC_FAST(1, true) break;
+                        case 2: WHMEC_FAST(2, true) break;
+                        default: WHMEC_FAST(3, true) break;
+                    }
+                } else {
+                    switch (tc.pad1) {
+                        case 0: WHMEC_FAST(0, false) break;
+                        case 1: WHMEC_FAST(1, false) break;
+                        case 2: WHMEC_FAST(2, false) break;
+                        case 3: WHMEC_FAST(3, false) break;
+                        default: WHMEC_FAST(4, false) break;
+                    }
                 }
+#undef WHMEC_FAST
             } else if (nout >= NT && tc.d == 1) {
                 column_drop1(tc, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
             } else if (nout >= NT && tc.d == 0) {

@@ -190,6 +190,17 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                             if ((m.keep >> q) & 1) kept.push_back(reads[q]);
                         tc.gmask_out = mask_of(kept, G);
                     }
+                    // kernel path hint (tile.cu: fast_kind): steady-state columns
+                    if (tc.kind == 0 && tc.d == 1 && tc.dpos[0] == 0 && tc.l_out >= 10 && tc.l_in >= 1 && tc.l_in + 4 >= tc.l_out &&
+                        TILE_SMAX == 14) {
+                        if (tc.n_new == 1 && tc.l_out >= 11) {
+                            tc.pad0 = 2;
+                            tc.pad1 = (uint8_t)(tc.l_out - 11);
+                        } else {
+                            tc.pad0 = 1;
+                            tc.pad1 = (uint8_t)(tc.l_out - 10);
+                        }
+                    }
                     accepted.push_back(tc);
                     Lcur.swap(nextL);
                     if (chain_end) {
