@@ -149,3 +149,20 @@ extern "C" int whemul_plan_handoffs(const whmec_problem *p, uint64_t *out2) {
     }
     return 0;
 }
+
+#include <chrono>
+// host-side timing of the packer and the tile planner (milliseconds)
+extern "C" int whemul_time_host(const whmec_problem *p, double *out2) {
+    Packed pk;
+    std::string msg;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = pack_problem(p, pk, msg);
+    auto t1 = std::chrono::steady_clock::now();
+    if (rc != WHMEC_OK) return rc;
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    auto t2 = std::chrono::steady_clock::now();
+    out2[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    out2[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    return 0;
+}

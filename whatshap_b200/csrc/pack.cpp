@@ -12,7 +12,11 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <functional>
+#include <thread>
 
 namespace whmec {
 
@@ -55,6 +59,10 @@ bool build_h2p(const whmec_problem *p, uint32_t tv, int8_t *h2p /* [n_ind][2] */
 }  // namespace
 
 int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t_start = tnow();
     const uint32_t n = p->n_cols;
     pk = Packed();
     pk.n = n;
@@ -142,122 +150,238 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
 
     pk.read_first = first;
     pk.read_last = last;
-
-    // ---- columns
-    pk.cols.resize(n);
-    pk.act_off.assign(n + 1, 0);
-    std::vector<uint32_t> active;  // ascending read index
-    std::vector<uint64_t> cursor(p->n_reads);
-    for (uint32_t r = 0; r < p->n_reads; ++r) cursor[r] = p->read_off[r];
-    uint32_t next_read = 0;
-    std::vector<uint32_t> prev_active;
-    uint32_t max_a = 0;
-    for (uint32_t k = 0; k < n; ++k) {
-        prev_active = active;
-        // retire reads that ended, admit reads that start here
-        active.erase(std::remove_if(active.begin(), active.end(), [&](uint32_t r) { return last[r] < k; }), active.end());
-        while (next_read < p->n_reads && first[next_read] == k) active.push_back(next_read++);
-        if (active.size() > MAX_ACTIVE) {
-            err = "more than 30 reads are active in one column (coverage too high)";
-            return WHMEC_ERR_UNSUPPORTED;
-        }
-        ColMeta &m = pk.cols[k];
-        std::memset(&m, 0, sizeof m);
-        m.a = (uint32_t)active.size();
-        max_a = std::max(max_a, m.a);
-        m.rc = p->recombcost[k];
-        m.first = (k == 0);
-        // backward projection width = |active(k) ∩ active(k-1)|; those are the lowest bits
-        uint32_t w = 0;
-        for (uint32_t r : active)
-            if (std::binary_search(prev_active.begin(), prev_active.end(), r)) ++w;
-        m.bw = (k == 0) ? 0 : w;
-        for (uint32_t j = 0; j < m.a; ++j) {
-            uint32_t r = active[j];
-            while (p->ent_col[cursor[r]] < k) ++cursor[r];
-            pk.act_read.push_back(r);
-            pk.act_ind.push_back((uint8_t)p->read_ind[r]);
-            if (p->ent_col[cursor[r]] == k) {
-                pk.act_allele.push_back(p->ent_allele[cursor[r]]);
-                pk.act_phred.push_back(p->ent_phred[cursor[r]]);
-            } else {  // gap inside the read's span: BLANK entry, phred 0 (columniterator.cpp:131)
-                pk.act_allele.push_back(2);
-                pk.act_phred.push_back(0);
-            }
-            // kept in column k+1 ?
-            if (k + 1 < n && last[r] >= k + 1) m.keep |= 1u << j;
-        }
-        pk.act_off[k + 1] = pk.act_read.size();
-        m.f = popc32(m.keep);
-        m.d = m.a - m.f;
-        uint32_t di = 0;
-        for (uint32_t j = 0; j < m.a; ++j)
-            if (!((m.keep >> j) & 1)) m.dpos[di++] = (uint8_t)j;
-    }
-    if (n > 0 && next_read != p->n_reads) {
+    if (n > 0 && p->n_reads > 0 && first[p->n_reads - 1] >= n) {
         err = "read starts at a column that is not in positions";
         return WHMEC_ERR_INPUT;
     }
 
-    // ---- cost functions per (column, transmission value, allowed assignment)
-    pk.fn_group.assign((size_t)n * (T + 1), 0);
-    uint64_t base_total = 0, rc_total = 0;
-    for (uint32_t k = 0; k < n; ++k) {
-        ColMeta &m = pk.cols[k];
-        m.fn_off = (uint32_t)pk.fn_c0.size();
-        m.grp_off = k * (T + 1);
-        const uint64_t e0 = pk.act_off[k];
-        bool any = false;
-        uint32_t max_base = 0;
-        for (uint32_t t = 0; t < T; ++t) {
-            const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
-            pk.fn_group[m.grp_off + t] = (uint32_t)pk.fn_c0.size() - m.fn_off;
-            for (uint32_t A = 0; A < (1u << P); ++A) {
-                bool ok = true;
-                unsigned int base = 0;
-                for (uint32_t i = 0; i < p->n_ind; ++i) {
-                    uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
-                    if (p->distrust) {
-                        // pedigreecolumncostcomputer.cpp:37  `unsigned += double`
-                        double g = p->gl[((size_t)i * n + k) * 3 + (a0 + a1)];
-                        base = (unsigned int)((double)base + g);
-                    } else if (p->gt[(size_t)i * n + k] != a0 + a1) {
-                        ok = false;
-                        break;
-                    }
-                }
-                if (!ok) continue;
-                any = true;
-                max_base = std::max(max_base, base);
-                uint32_t c0 = base;
-                size_t doff = pk.fn_delta.size();
-                pk.fn_delta.resize(doff + FN_STRIDE, 0);
-                for (uint32_t j = 0; j < m.a; ++j) {
-                    uint8_t al = pk.act_allele[e0 + j];
-                    if (al > 1) continue;  // BLANK contributes nothing
-                    uint32_t w = pk.act_phred[e0 + j];
-                    uint32_t ind = pk.act_ind[e0 + j];
-                    // read on haplotype `bit` of its individual sits in partition h2p[ind][bit]; it costs
-                    // w when the allele assigned to that partition differs (cost computer :59-67)
-                    uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w : 0;
-                    uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w : 0;
-                    c0 += cost0;
-                    pk.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
-                }
-                pk.fn_c0.push_back(c0);
-                pk.fn_asg.push_back(A);
-                pk.fn_base.push_back(base);
+    const auto t_valid = tnow();
+    // ---- split the columns at DP-independent chain boundaries (no read spans the cut) into chunks
+    //      that are packed by independent host threads
+    std::vector<int32_t> span(n + 2, 0);  // span[k] > 0: some read is active in both k-1 and k
+    for (uint32_t r = 0; r < p->n_reads; ++r)
+        if (last[r] > first[r]) {
+            span[first[r] + 1] += 1;
+            span[last[r] + 1] -= 1;
+        }
+    std::vector<uint32_t> cut;  // chunk starts (columns)
+    {
+        const uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        const uint32_t target = std::max<uint32_t>(256, n / (4 * hw) + 1);
+        int32_t run = 0;
+        uint32_t last_cut = 0;
+        cut.push_back(0);
+        for (uint32_t k = 1; k < n; ++k) {
+            run += span[k];
+            if (run == 0 && k - last_cut >= target) {
+                cut.push_back(k);
+                last_cut = k;
             }
         }
-        pk.fn_group[m.grp_off + T] = (uint32_t)pk.fn_c0.size() - m.fn_off;
-        if (!any) {  // no transmission value admits any assignment: pedigreedptable.cpp:301-303
-            err = "Error: Mendelian conflict";
-            return WHMEC_ERR_MENDELIAN;
+        cut.push_back(n);
+    }
+    const uint32_t n_chunks = n ? (uint32_t)cut.size() - 1 : 0;
+    struct Chunk {
+        std::vector<uint32_t> act_read, act_phred, fn_c0, fn_asg, fn_base, fn_group;
+        std::vector<uint8_t> act_allele, act_ind;
+        std::vector<int32_t> fn_delta;
+        uint32_t max_a = 0;
+        uint64_t base_total = 0, rc_total = 0;
+        int rc = WHMEC_OK;
+        uint32_t err_col = 0;
+        std::string err;
+    };
+    std::vector<Chunk> chunks(n_chunks);
+    std::vector<uint32_t> chunk_first_read(n_chunks + 1, p->n_reads);
+    {
+        uint32_t r = 0;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            while (r < p->n_reads && first[r] < cut[c]) ++r;
+            chunk_first_read[c] = r;
         }
-        base_total += max_base;
-        rc_total += (uint64_t)m.rc * pk.tb;
+    }
+    pk.cols.resize(n);
+    pk.act_off.assign(n + 1, 0);
+    pk.fn_group.assign((size_t)n * (T + 1), 0);
+
+    auto build_chunk = [&](uint32_t ci) {
+        Chunk &ch = chunks[ci];
+        const uint32_t kb = cut[ci], ke = cut[ci + 1];
+        std::vector<uint32_t> active, prev_active;
+        uint32_t next_read = chunk_first_read[ci];
+        const uint32_t read_end = chunk_first_read[ci + 1];
+        std::vector<uint64_t> cursor;  // indexed by read - chunk_first_read[ci]
+        cursor.reserve(read_end - next_read);
+        for (uint32_t r = next_read; r < read_end; ++r) cursor.push_back(p->read_off[r]);
+        const uint32_t r0 = chunk_first_read[ci];
+        for (uint32_t k = kb; k < ke; ++k) {
+            prev_active = active;
+            active.erase(std::remove_if(active.begin(), active.end(), [&](uint32_t r) { return last[r] < k; }), active.end());
+            while (next_read < read_end && first[next_read] == k) active.push_back(next_read++);
+            if (active.size() > MAX_ACTIVE) {
+                ch.rc = WHMEC_ERR_UNSUPPORTED;
+                ch.err_col = k;
+                ch.err = "more than 30 reads are active in one column (coverage too high)";
+                return;
+            }
+            ColMeta &m = pk.cols[k];
+            std::memset(&m, 0, sizeof m);
+            m.a = (uint32_t)active.size();
+            ch.max_a = std::max(ch.max_a, m.a);
+            m.rc = p->recombcost[k];
+            m.first = (k == 0);
+            uint32_t w = 0;  // backward projection width = |active(k) ∩ active(k-1)|; those are the lowest bits
+            for (uint32_t r : active)
+                if (std::binary_search(prev_active.begin(), prev_active.end(), r)) ++w;
+            m.bw = (k == 0) ? 0 : w;
+            const size_t e0 = ch.act_read.size();
+            pk.act_off[k] = e0;  // chunk-relative for now
+            for (uint32_t j = 0; j < m.a; ++j) {
+                const uint32_t r = active[j];
+                uint64_t &cur = cursor[r - r0];
+                while (p->ent_col[cur] < k) ++cur;
+                ch.act_read.push_back(r);
+                ch.act_ind.push_back((uint8_t)p->read_ind[r]);
+                if (p->ent_col[cur] == k) {
+                    ch.act_allele.push_back(p->ent_allele[cur]);
+                    ch.act_phred.push_back(p->ent_phred[cur]);
+                } else {  // gap inside the read's span: BLANK entry, phred 0 (columniterator.cpp:131)
+                    ch.act_allele.push_back(2);
+                    ch.act_phred.push_back(0);
+                }
+                if (k + 1 < n && last[r] >= k + 1) m.keep |= 1u << j;
+            }
+            m.f = popc32(m.keep);
+            m.d = m.a - m.f;
+            uint32_t di = 0;
+            for (uint32_t j = 0; j < m.a; ++j)
+                if (!((m.keep >> j) & 1)) m.dpos[di++] = (uint8_t)j;
+
+            // cost functions per (transmission value, allowed assignment)
+            m.fn_off = (uint32_t)ch.fn_c0.size();  // chunk-relative for now
+            m.grp_off = k * (T + 1);
+            bool any = false;
+            uint32_t max_base = 0;
+            for (uint32_t t = 0; t < T; ++t) {
+                const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
+                pk.fn_group[m.grp_off + t] = (uint32_t)ch.fn_c0.size() - m.fn_off;
+                for (uint32_t A = 0; A < (1u << P); ++A) {
+                    bool ok = true;
+                    unsigned int base = 0;
+                    for (uint32_t i = 0; i < p->n_ind; ++i) {
+                        uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
+                        if (p->distrust) {
+                            // pedigreecolumncostcomputer.cpp:37  `unsigned += double`
+                            double g = p->gl[((size_t)i * n + k) * 3 + (a0 + a1)];
+                            base = (unsigned int)((double)base + g);
+                        } else if (p->gt[(size_t)i * n + k] != a0 + a1) {
+                            ok = false;
+                            break;
+                        }
+                    }
+                    if (!ok) continue;
+                    any = true;
+                    max_base = std::max(max_base, base);
+                    uint32_t c0 = base;
+                    const size_t doff = ch.fn_delta.size();
+                    ch.fn_delta.resize(doff + FN_STRIDE, 0);
+                    for (uint32_t j = 0; j < m.a; ++j) {
+                        const uint8_t al = ch.act_allele[e0 + j];
+                        if (al > 1) continue;  // BLANK contributes nothing
+                        const uint32_t w2 = ch.act_phred[e0 + j];
+                        const uint32_t ind = ch.act_ind[e0 + j];
+                        // read on haplotype `bit` of its individual sits in partition h2p[ind][bit]; it costs
+                        // w when the allele assigned to that partition differs (cost computer :59-67)
+                        const uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w2 : 0;
+                        const uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w2 : 0;
+                        c0 += cost0;
+                        ch.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
+                    }
+                    ch.fn_c0.push_back(c0);
+                    ch.fn_asg.push_back(A);
+                    ch.fn_base.push_back(base);
+                }
+            }
+            pk.fn_group[m.grp_off + T] = (uint32_t)ch.fn_c0.size() - m.fn_off;
+            if (!any) {  // no transmission value admits any assignment: pedigreedptable.cpp:301-303
+                ch.rc = WHMEC_ERR_MENDELIAN;
+                ch.err_col = k;
+                ch.err = "Error: Mendelian conflict";
+                return;
+            }
+            ch.base_total += max_base;
+            ch.rc_total += (uint64_t)m.rc * pk.tb;
+        }
+    };
+    {
+        uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
+        const uint32_t nthreads = std::min(hw, n_chunks);
+        std::atomic<uint32_t> next{0};
+        auto worker = [&]() {
+            for (uint32_t ci = next.fetch_add(1); ci < n_chunks; ci = next.fetch_add(1)) build_chunk(ci);
+        };
+        if (nthreads <= 1) {
+            worker();
+        } else {
+            std::vector<std::thread> pool;
+            for (uint32_t t = 0; t + 1 < nthreads; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &th : pool) th.join();
+        }
+    }
+    const auto t_chunks = tnow();
+    // the reference reports the first failing column (columns are visited in order)
+    for (uint32_t ci = 0; ci < n_chunks; ++ci)
+        if (chunks[ci].rc != WHMEC_OK) {
+            err = chunks[ci].err;
+            return chunks[ci].rc;
+        }
+    // ---- merge the chunks
+    uint32_t max_a = 0;
+    uint64_t base_total = 0, rc_total = 0;
+    {
+        size_t act_total = 0, fn_total = 0;
+        std::vector<size_t> act_base(n_chunks), fn_base_off(n_chunks);
+        for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+            act_base[ci] = act_total;
+            fn_base_off[ci] = fn_total;
+            act_total += chunks[ci].act_read.size();
+            fn_total += chunks[ci].fn_c0.size();
+            max_a = std::max(max_a, chunks[ci].max_a);
+            base_total += chunks[ci].base_total;
+            rc_total += chunks[ci].rc_total;
+        }
+        pk.act_read.resize(act_total);
+        pk.act_allele.resize(act_total);
+        pk.act_phred.resize(act_total);
+        pk.act_ind.resize(act_total);
+        pk.fn_c0.resize(fn_total);
+        pk.fn_asg.resize(fn_total);
+        pk.fn_base.resize(fn_total);
+        pk.fn_delta.resize(fn_total * FN_STRIDE);
+        for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+            Chunk &ch = chunks[ci];
+            std::copy(ch.act_read.begin(), ch.act_read.end(), pk.act_read.begin() + act_base[ci]);
+            std::copy(ch.act_allele.begin(), ch.act_allele.end(), pk.act_allele.begin() + act_base[ci]);
+            std::copy(ch.act_phred.begin(), ch.act_phred.end(), pk.act_phred.begin() + act_base[ci]);
+            std::copy(ch.act_ind.begin(), ch.act_ind.end(), pk.act_ind.begin() + act_base[ci]);
+            std::copy(ch.fn_c0.begin(), ch.fn_c0.end(), pk.fn_c0.begin() + fn_base_off[ci]);
+            std::copy(ch.fn_asg.begin(), ch.fn_asg.end(), pk.fn_asg.begin() + fn_base_off[ci]);
+            std::copy(ch.fn_base.begin(), ch.fn_base.end(), pk.fn_base.begin() + fn_base_off[ci]);
+            std::copy(ch.fn_delta.begin(), ch.fn_delta.end(), pk.fn_delta.begin() + fn_base_off[ci] * FN_STRIDE);
+            for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) {
+                pk.act_off[k] += act_base[ci];
+                pk.cols[k].fn_off += (uint32_t)fn_base_off[ci];
+            }
+        }
+        pk.act_off[n] = act_total;
     }
     pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 28);
+    const auto t_merge = tnow();
+    if (timing)
+        std::fprintf(stderr, "[whmec] pack: validate %.2f ms, chunks(%u) %.2f ms, merge %.2f ms\n", tms(t_start, t_valid), n_chunks,
+                     tms(t_valid, t_chunks), tms(t_chunks, t_merge));
 
     // ---- chains, back-pointer layout, accounting
     uint64_t words = 0;

@@ -432,6 +432,20 @@ struct TileImpl {
 
 }  // namespace
 
+size_t device_available_bytes() {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t reserved = 0, used = 0;
+        if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            free_b += (size_t)(reserved - used);
+    }
+    return free_b;
+}
+
 bool TilePlan::plan(const Packed &pk) {
     TileImpl *I = new TileImpl();
     plan_tiles(pk, I->ts);
@@ -449,8 +463,7 @@ bool TilePlan::plan(const Packed &pk) {
 int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::string &msg) {
     TileImpl *I = (TileImpl *)impl;
     const TileSchedule &ts = I->ts;
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t free_b = device_available_bytes();
     const uint64_t need = (ts.state_words + ts.bp_words + 2) * 4 + (uint64_t)pk.n * (sizeof(TileCol) + sizeof(ColMeta)) +
                           ts.panels.size() * sizeof(Panel);
     if (need + (512ull << 20) > free_b) {
@@ -458,13 +471,13 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
         return WHMEC_ERR_UNSUPPORTED;
     }
     I->n_chains = (uint32_t)pk.chain_begin.size() - 1;
-    CUDA_TRY(cudaMalloc((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta)));
-    CUDA_TRY(cudaMalloc((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol)));
-    CUDA_TRY(cudaMalloc((void **)&I->d_panels, ts.panels.size() * sizeof(Panel)));
-    CUDA_TRY(cudaMalloc((void **)&I->d_state, (ts.state_words + 1) * 4));
-    CUDA_TRY(cudaMalloc((void **)&I->d_arena, (ts.bp_words + 1) * 4));
-    CUDA_TRY(cudaMalloc((void **)&I->d_chain_begin, pk.chain_begin.size() * 4));
-    CUDA_TRY(cudaMalloc((void **)&I->d_chain_keys, (size_t)I->n_chains * 8));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta), stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol), stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_panels, ts.panels.size() * sizeof(Panel), stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_state, (ts.state_words + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_arena, (ts.bp_words + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_begin, pk.chain_begin.size() * 4, stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_keys, (size_t)I->n_chains * 8, stream));
     auto up = [&](void *dst, const void *src, size_t bytes) {
         h2d += bytes;
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
@@ -501,11 +514,12 @@ int TilePlan::backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_
     return WHMEC_OK;
 }
 
-void TilePlan::release() {
+void TilePlan::release(cudaStream_t stream) {
     TileImpl *I = (TileImpl *)impl;
     if (!I) return;
-    cudaFree(I->d_cols); cudaFree(I->d_tcols); cudaFree(I->d_panels); cudaFree(I->d_state);
-    cudaFree(I->d_arena); cudaFree(I->d_chain_begin); cudaFree(I->d_chain_keys);
+    for (void *q : {(void *)I->d_cols, (void *)I->d_tcols, (void *)I->d_panels, (void *)I->d_state, (void *)I->d_arena,
+                    (void *)I->d_chain_begin, (void *)I->d_chain_keys})
+        if (q) cudaFreeAsync(q, stream);
     delete I;
     impl = nullptr;
 }

@@ -8,6 +8,9 @@
 
 namespace whmec {
 
+// free device memory plus what the stream-ordered pool holds but does not use
+size_t device_available_bytes();
+
 struct TilePlan {
     uint64_t backptr_bytes = 0;
     uint64_t state_bytes = 0;     // projection state moved through global memory by one sweep
@@ -19,7 +22,7 @@ struct TilePlan {
     int create(const Packed &pk, cudaStream_t stream, uint64_t &h2d_bytes, std::string &msg);
     int sweep(const Packed &pk, cudaStream_t stream, std::string &msg);
     int backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg);
-    void release();
+    void release(cudaStream_t stream);
 };
 
 }  // namespace whmec

@@ -2,7 +2,12 @@
 #include "tile_plan.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 
 namespace whmec {
 
@@ -35,21 +40,29 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         ts.why = "cost range exceeds the exact range of the tile arithmetic";
         return;
     }
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    auto tnow = [] { return std::chrono::steady_clock::now(); };
+    auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = tnow();
     const uint32_t n = pk.n;
     ts.cols.assign(n, TileCol());
     const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
     std::vector<std::vector<Panel>> per_chain(n_chains);
     struct PanelSets { std::vector<uint32_t> G, Lout, Lold, Gold; };
     std::vector<std::vector<PanelSets>> per_chain_sets(n_chains);
-    uint64_t state_words = 0, bp_words = 0;
+    // per-chain results; offsets are chain-relative until all chains are planned (chains are planned by
+    // independent host threads)
+    std::vector<uint64_t> chain_state_words(n_chains, 0), chain_bp_words(n_chains, 0), chain_traffic(n_chains, 0);
+    std::vector<std::string> chain_why(n_chains);
 
-    for (uint32_t c = 0; c < n_chains; ++c) {
+    auto plan_chain = [&](uint32_t c) -> bool {
         const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1] - 1;
         uint32_t fmax = 0;
         for (uint32_t k = k0; k <= k1; ++k) fmax = std::max(fmax, pk.cols[k].f);
         const uint64_t buf_words = (uint64_t)1 << fmax;
-        const uint64_t chain_state = state_words;
-        state_words += 2 * buf_words;
+        const uint64_t chain_state = 0;
+        chain_state_words[c] = 2 * buf_words;
+        uint64_t bp_words = 0;
         uint32_t pcount = 0;
 
         std::vector<uint32_t> state;  // reads kept after column k-1, canonical (ascending) order
@@ -59,8 +72,8 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             const uint32_t fin = (uint32_t)state.size();
             const uint32_t n_new0 = m0.a - m0.bw;
             if (fin != m0.bw && !(k == k0 && m0.bw == 0)) {
-                ts.why = "internal: state/backward width mismatch";
-                return;
+                chain_why[c] = "internal: state/backward width mismatch";
+                return false;
             }
             // Candidates for the tile-local bits: the reads of the incoming state plus the reads
             // that start in this column (at a panel's first column new reads may become global, which
@@ -233,7 +246,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     P.s_out = (uint32_t)Lcur.size();
                     P.lmask_out = mask_of(kept, Lcur);
                     P.gmask_out = mask_of(kept, G);
-                    ts.state_traffic_bytes += 2ull * 4ull * ((uint64_t)1 << kept.size());
+                    chain_traffic[c] += 2ull * 4ull * ((uint64_t)1 << kept.size());
                 }
                 for (uint32_t q = k; q < j; ++q) {
                     TileCol &tc = accepted[q - k];
@@ -254,10 +267,52 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                 placed = true;
             }
             if (!placed) {
-                ts.why = "a column drops more reads at once than a tile can hold";
-                return;
+                chain_why[c] = "a column drops more reads at once than a tile can hold";
+                return false;
             }
         }
+        chain_bp_words[c] = bp_words;
+        return true;
+    };
+    {
+        uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
+        const uint32_t nthreads = std::min(hw, std::max(1u, n_chains / 2));
+        std::atomic<uint32_t> next{0};
+        std::atomic<bool> failed{false};
+        auto worker = [&]() {
+            for (uint32_t c = next.fetch_add(1); c < n_chains && !failed.load(); c = next.fetch_add(1))
+                if (!plan_chain(c)) failed.store(true);
+        };
+        if (nthreads <= 1) {
+            worker();
+        } else {
+            std::vector<std::thread> pool;
+            for (uint32_t t = 0; t + 1 < nthreads; ++t) pool.emplace_back(worker);
+            worker();
+            for (auto &th : pool) th.join();
+        }
+        if (failed.load()) {
+            for (uint32_t c = 0; c < n_chains; ++c)
+                if (!chain_why[c].empty()) {
+                    ts.why = chain_why[c];
+                    break;
+                }
+            return;
+        }
+    }
+    const auto t1 = tnow();
+    // make the chain-relative offsets absolute
+    uint64_t state_words = 0, bp_words = 0;
+    for (uint32_t c = 0; c < n_chains; ++c) {
+        for (Panel &P : per_chain[c]) {
+            P.in_off += state_words;
+            P.out_off += state_words;
+        }
+        for (uint32_t k = pk.chain_begin[c]; k < pk.chain_begin[c + 1]; ++k) ts.cols[k].bp_off += bp_words;
+        state_words += chain_state_words[c];
+        bp_words += chain_bp_words[c];
+        ts.state_traffic_bytes += chain_traffic[c];
     }
 
     // hand-off layouts between consecutive panels of a chain (see Panel in tile_plan.h)
@@ -299,6 +354,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     ts.state_words = state_words;
     ts.bp_words = bp_words;
     ts.eligible = true;
+    if (timing) std::fprintf(stderr, "[whmec] plan: chains %.2f ms, assemble %.2f ms\n", tms(t0, t1), tms(t1, tnow()));
 }
 
 }  // namespace whmec

@@ -7,6 +7,7 @@
 // There is deliberately NO CPU execution path in this library: if CUDA is unavailable every
 // entry point that computes returns WHMEC_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <malloc.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -169,19 +170,34 @@ __global__ void backtrace_kernel(const ColMeta *__restrict__ cols, const uint32_
     }
 }
 
+// Device buffers come from the device's stream-ordered memory pool with an unlimited release
+// threshold: a process that phases many chromosomes pays cudaMalloc for its largest problem once.
 template <class Tp>
 struct DevBuf {
     Tp *p = nullptr;
     size_t count = 0;
-    cudaError_t alloc(size_t n) {
+    cudaStream_t stream = nullptr;
+    cudaError_t alloc(size_t n, cudaStream_t s) {
         count = n;
-        return cudaMalloc((void **)&p, std::max<size_t>(n, 1) * sizeof(Tp));
+        stream = s;
+        return cudaMallocAsync((void **)&p, std::max<size_t>(n, 1) * sizeof(Tp), s);
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
     }
 };
+
+void keep_pool_memory(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done[device] = true;
+}
 
 }  // namespace
 
@@ -207,16 +223,33 @@ struct whmec_plan {
         d_cols.release(); d_fn_c0.release(); d_fn_group.release(); d_val[0].release(); d_val[1].release();
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
-        tiles.release();
+        tiles.release(stream);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            cudaStreamDestroy(stream);
+        }
     }
 };
 
 namespace {
 
+// The packed problem and the tile schedule are tens of MB of freshly touched host memory per call;
+// returning them to the OS on every free (glibc's default for large blocks) makes each call pay the
+// page faults again.  Keep freed blocks in the process heap instead (opt out: WHMEC_KEEP_HOST_MEMORY=0).
+void keep_host_memory() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char *e = std::getenv("WHMEC_KEEP_HOST_MEMORY");
+    if (e && e[0] == '0') return;
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+}
+
 int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::string &msg) {
+    keep_host_memory();
     int rc = pack_problem(p, pl->pk, msg);
     if (rc != WHMEC_OK) return rc;
     Packed &pk = pl->pk;
@@ -229,14 +262,15 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
             return WHMEC_ERR_UNSUPPORTED;
         }
     CUDA_TRY(cudaSetDevice(device));
+    keep_pool_memory(device);
     CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreate(&pl->ev0));
     CUDA_TRY(cudaEventCreate(&pl->ev1));
     const uint32_t n = pk.n;
 
-    CUDA_TRY(pl->d_path_index.alloc(n));
-    CUDA_TRY(pl->d_path_tv.alloc(n));
-    CUDA_TRY(pl->d_result.alloc(4));
+    CUDA_TRY(pl->d_path_index.alloc(n, pl->stream));
+    CUDA_TRY(pl->d_path_tv.alloc(n, pl->stream));
+    CUDA_TRY(pl->d_result.alloc(4, pl->stream));
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     uint64_t h2d = 0;
 
@@ -248,8 +282,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         pl->stats.path_kind = 1;
         pl->stats.backptr_bytes = pl->tiles.backptr_bytes;
     } else {
-        size_t free_b = 0, total_b = 0;
-        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        const size_t free_b = device_available_bytes();
         uint64_t max_ent = 1;
         for (const ColMeta &m : pk.cols) max_ent = std::max<uint64_t>(max_ent, ((uint64_t)1 << m.f) * pk.T);
         uint64_t need = pk.bp_words * 4 + max_ent * (4 * 2 + 8) + pk.fn_delta.size() * 4 + (uint64_t)n * sizeof(ColMeta);
@@ -257,15 +290,15 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
             msg = "back-pointer storage exceeds the free HBM of this device";
             return WHMEC_ERR_UNSUPPORTED;
         }
-        CUDA_TRY(pl->d_cols.alloc(n));
-        CUDA_TRY(pl->d_fn_c0.alloc(pk.fn_c0.size()));
-        CUDA_TRY(pl->d_fn_delta.alloc(pk.fn_delta.size()));
-        CUDA_TRY(pl->d_fn_group.alloc(pk.fn_group.size()));
-        CUDA_TRY(pl->d_chain_begin.alloc(pk.chain_begin.size()));
-        CUDA_TRY(pl->d_val[0].alloc(max_ent));
-        CUDA_TRY(pl->d_val[1].alloc(max_ent));
-        CUDA_TRY(pl->d_keys.alloc(max_ent));
-        CUDA_TRY(pl->d_arena.alloc(pk.bp_words + 1));
+        CUDA_TRY(pl->d_cols.alloc(n, pl->stream));
+        CUDA_TRY(pl->d_fn_c0.alloc(pk.fn_c0.size(), pl->stream));
+        CUDA_TRY(pl->d_fn_delta.alloc(pk.fn_delta.size(), pl->stream));
+        CUDA_TRY(pl->d_fn_group.alloc(pk.fn_group.size(), pl->stream));
+        CUDA_TRY(pl->d_chain_begin.alloc(pk.chain_begin.size(), pl->stream));
+        CUDA_TRY(pl->d_val[0].alloc(max_ent, pl->stream));
+        CUDA_TRY(pl->d_val[1].alloc(max_ent, pl->stream));
+        CUDA_TRY(pl->d_keys.alloc(max_ent, pl->stream));
+        CUDA_TRY(pl->d_arena.alloc(pk.bp_words + 1, pl->stream));
         auto up = [&](void *dst, const void *src, size_t bytes) {
             h2d += bytes;
             return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pl->stream);
