@@ -1,3 +1,12 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 2>&1 | tail -1
-python bench.py --steps 5 --warmup 3 --workload cfg2 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-300
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -2
+python - <<'PY'
+import time, sys, json
+sys.path.insert(0,'.')
+from whatshap_b200 import synth, _lib
+for name, n in [('cfg5',20000)]:
+    p=synth.config(name,n)
+    plan=_lib.Plan(p)
+    for i in range(4): plan.sweep()
+    st=plan.stats(); sol=plan.finish(); plan.close()
+    print(name,n,'sweep %.3f ms'%st['sweep_ms'], 'cols/s=%.0f'%(n/(st['sweep_ms']/1e3)), 'launches',st['kernel_launches'],'cost',sol.cost, flush=True)
+PY

@@ -38,6 +38,22 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
         if (m.d + tb > 32) { msg = "d + tb > 32"; return fail(WHMEC_ERR_UNSUPPORTED); }
         uint64_t nout = (uint64_t)1 << m.f, ncand = (uint64_t)1 << m.d;
         cur.assign(nout * T, UMAX);
+        // per-column lookup tables, as a thread block builds them in shared memory
+        const uint32_t nf_col = pk.fn_group[m.grp_off + T];
+        std::vector<uint32_t> pd_lo(TAB_SIZE), pd_hi(TAB_SIZE);
+        std::vector<int32_t> tlo((size_t)nf_col * TAB_SIZE), thi((size_t)nf_col * TAB_SIZE);
+        const uint32_t keep_lo = lowest_set_bits(m.keep, TAB_BITS), keep_hi = lowest_set_bits(m.keep & ~keep_lo, TAB_BITS);
+        for (uint32_t vv = 0; vv < TAB_SIZE; ++vv) {
+            pd_lo[vv] = pdep32(vv, keep_lo);
+            pd_hi[vv] = pdep32(vv, keep_hi);
+        }
+        for (uint32_t F = 0; F < nf_col; ++F)
+            for (uint32_t half = 0; half < 2; ++half)
+                for (uint32_t hi4 = 0; hi4 < 16; ++hi4)
+                    build_cost_table_run(pk.fn_delta.data() + (size_t)(m.fn_off + F) * FN_STRIDE, half, hi4,
+                                         (half ? thi.data() : tlo.data()) + (size_t)F * TAB_SIZE + 16 * hi4);
+        ColTables tab{pd_lo.data(), pd_hi.data(), m.keep & ~keep_lo & ~keep_hi, tlo.data(), thi.data()};
+        const bool use_tab = (k % 2) == 0;  // exercise both initialisation paths
         for (uint64_t o = 0; o < nout; ++o)
             for (uint32_t i = 0; i < T; ++i) {
                 ColView v;
@@ -47,6 +63,8 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
                 v.fn_delta = pk.fn_delta.data() + (size_t)(m.fn_off + g0) * FN_STRIDE;
                 v.nf = g1 - g0;
                 v.prev = prev.data();
+                v.tab = use_tab ? &tab : nullptr;
+                v.tab_fn0 = g0;
                 uint64_t best = KEY_INF;
                 uint64_t step = chunk ? chunk : ncand;
                 for (uint64_t r0 = 0; r0 < ncand; r0 += step) {  // chunked like the atomic kernel

@@ -14,7 +14,18 @@ namespace whmec {
 // (pedigreedptable.cpp:293-296,320-324).
 constexpr uint64_t KEY_INF = 0xFFFFFFFFFFFFFFFFull;
 
-constexpr int NF_REG = 16;  // cost functions kept incrementally in registers per thread
+constexpr int NF_REG = 16;  // most cost functions kept incrementally in registers per thread
+
+// Optional per-column lookup tables (built once per thread block in shared memory) that replace the
+// bit loops of the initialisation: scatter of the output index into the kept positions, and the
+// value of every cost function on the low / high byte of a cell index.
+constexpr uint32_t TAB_BITS = 8, TAB_SIZE = 1u << TAB_BITS;
+
+struct ColTables {
+    const uint32_t *pd_lo, *pd_hi;   // pdep(v, lowest 8 kept bits), pdep(v, next 8 kept bits)
+    uint32_t keep_rest;              // kept bits beyond the first 16
+    const int32_t *lo, *hi;          // [function][256]: sum of deltas over cell bits 0..7 / 8..15
+};
 
 struct ColView {
     const ColMeta *m;
@@ -23,27 +34,63 @@ struct ColView {
     const int32_t *fn_delta;   // [nf][FN_STRIDE]
     uint32_t nf;
     const uint32_t *prev;      // [2^bw][T] values of the previous projection (ignored if m->first)
+    const ColTables *tab;      // nullptr: use the bit loops
+    uint32_t tab_fn0;          // index of this group's first function inside the tables
 };
+
+WHMEC_HD uint32_t lowest_set_bits(uint32_t mask, uint32_t count) {
+    uint32_t out = 0;
+    for (uint32_t i = 0; i < count && mask; ++i) {
+        uint32_t low = mask & (0u - mask);
+        out |= low;
+        mask ^= low;
+    }
+    return out;
+}
+
+// One run of 16 consecutive table entries of cost function F: entries [16*hi4, 16*hi4+16) of the
+// byte table `half` (0: cell bits 0..7, 1: bits 8..15).  Subset sums with one add per entry.
+WHMEC_HD void build_cost_table_run(const int32_t *delta /* [FN_STRIDE] of F */, uint32_t half, uint32_t hi4, int32_t *out16) {
+    const int32_t *d = delta + half * TAB_BITS;
+    int32_t base = 0;
+    for (uint32_t q = 0; q < 4; ++q)
+        if ((hi4 >> q) & 1u) base += d[4 + q];
+    out16[0] = base;
+    for (uint32_t i = 1; i < 16; ++i) out16[i] = out16[i & (i - 1)] + d[ctz32(i)];
+}
 
 // Best key over candidates r in [r0, r1) of forward-projection entry `o` for transmission value i.
 // Reference: one iteration of the Gray-code loop body (pedigreedptable.cpp:239-327), restricted
 // to the candidates projecting onto `o` and visited in the same relative order.
-WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
+template <int NFR>
+WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
     const ColMeta &m = *v.m;
     const uint32_t drop = ~m.keep & low_mask(m.a);
-    const uint32_t kept = pdep32(o, m.keep);
+    uint32_t kept;
+    if (v.tab) {
+        kept = v.tab->pd_lo[o & (TAB_SIZE - 1)] | v.tab->pd_hi[(o >> TAB_BITS) & (TAB_SIZE - 1)];
+        if (v.tab->keep_rest) kept |= pdep32(o >> (2 * TAB_BITS), v.tab->keep_rest);
+    } else {
+        kept = pdep32(o, m.keep);
+    }
     const uint32_t cg = rank_offset(m, kept);
     uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cg, drop);
     const uint32_t bmask = low_mask(m.bw);
-    const bool incremental = v.nf <= (uint32_t)NF_REG;
+    const bool incremental = v.nf <= (uint32_t)NFR;
 
-    uint32_t cost[NF_REG];
+    uint32_t cost[NFR];
     if (incremental) {
 #pragma unroll
-        for (int F = 0; F < NF_REG; ++F) {
+        for (int F = 0; F < NFR; ++F) {
             if ((uint32_t)F < v.nf) {
                 uint32_t c = v.fn_c0[F];
-                for (uint32_t j = 0; j < m.a; ++j)
+                uint32_t j0 = 0;
+                if (v.tab) {  // bits 0..15 from the byte tables, the rest (a > 16) bit by bit
+                    const size_t t = (size_t)(v.tab_fn0 + F) * TAB_SIZE;
+                    c += (uint32_t)(v.tab->lo[t + (x & (TAB_SIZE - 1))] + v.tab->hi[t + ((x >> TAB_BITS) & (TAB_SIZE - 1))]);
+                    j0 = 2 * TAB_BITS;
+                }
+                for (uint32_t j = j0; j < m.a; ++j)
                     if ((x >> j) & 1u) c += (uint32_t)v.fn_delta[F * FN_STRIDE + j];
                 cost[F] = c;
             } else {
@@ -58,7 +105,7 @@ WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint
         uint32_t cur = UMAX;
         if (incremental) {
 #pragma unroll
-            for (int F = 0; F < NF_REG; ++F)
+            for (int F = 0; F < NFR; ++F)
                 if ((uint32_t)F < v.nf && cost[F] < cur) cur = cost[F];
         } else {
             for (uint32_t F = 0; F < v.nf; ++F) {
@@ -89,7 +136,7 @@ WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint
             if (incremental) {
                 const bool set = (x >> pos) & 1u;
 #pragma unroll
-                for (int F = 0; F < NF_REG; ++F)
+                for (int F = 0; F < NFR; ++F)
                     if ((uint32_t)F < v.nf) {
                         uint32_t dlt = (uint32_t)v.fn_delta[F * FN_STRIDE + pos];
                         cost[F] += set ? dlt : (0u - dlt);
@@ -98,6 +145,13 @@ WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint
         }
     }
     return best;
+}
+
+// Dispatch on the number of cost functions of the transmission group: the common small groups get a
+// small code path (the whole kernel otherwise thrashes the instruction cache).
+WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
+    if (v.nf <= 4) return eval_candidates_t<4>(v, o, i, r0, r1);
+    return eval_candidates_t<NF_REG>(v, o, i, r0, r1);
 }
 
 // One backtrace step (pedigreedptable.cpp:155-160): given the back-pointer word of entry

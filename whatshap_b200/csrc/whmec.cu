@@ -58,55 +58,159 @@ __device__ __forceinline__ void bp_store_warp(uint32_t *arena, uint64_t off_word
     if (sub == 0 && valid) arena[off_words + e / per] = word;
 }
 
-__device__ __forceinline__ ColView make_view(const ColMeta *m, uint32_t T, uint32_t tb, const uint32_t *fn_c0,
-                                             const int32_t *fn_delta, const uint32_t *fn_group, const uint32_t *prev,
-                                             uint32_t i) {
+// The cost functions of one column are read by every thread of the block many times: stage them in
+// shared memory (up to FN_SMEM functions; beyond that the global arrays are used directly).
+constexpr uint32_t FN_SMEM = 48;
+constexpr uint32_t FN_TAB = 12;  // columns with at most this many cost functions get byte tables
+
+struct ColShared {
+    ColMeta m;
+    uint32_t group[MAX_T + 1];
+    uint32_t c0[FN_SMEM];
+    int32_t delta[FN_SMEM * FN_STRIDE];
+    uint32_t pd_lo[TAB_SIZE], pd_hi[TAB_SIZE];
+    int32_t tlo[FN_TAB * TAB_SIZE], thi[FN_TAB * TAB_SIZE];
+    ColTables tab;
+    uint32_t staged, tabled;
+};
+
+// `cm` and `nf` arrive as kernel parameters (constant bank): no dependent global loads before the
+// function arrays can be fetched.
+__device__ __forceinline__ void stage_column(ColShared &S, const ColMeta &cm, uint32_t nf, uint32_t T,
+                                             const uint32_t *fn_c0, const int32_t *fn_delta, const uint32_t *fn_group) {
+    if (threadIdx.x < sizeof(ColMeta) / 4) ((uint32_t *)&S.m)[threadIdx.x] = ((const uint32_t *)&cm)[threadIdx.x];
+    for (uint32_t i = threadIdx.x; i <= T; i += blockDim.x) S.group[i] = fn_group[cm.grp_off + i];
+    if (threadIdx.x == 0) S.staged = nf <= FN_SMEM;
+    if (nf <= FN_SMEM) {
+        for (uint32_t i = threadIdx.x; i < nf; i += blockDim.x) S.c0[i] = fn_c0[cm.fn_off + i];
+        // only the first `a` deltas of a function are ever read
+        const uint32_t a = cm.a;
+        for (uint32_t i = threadIdx.x; i < nf * a; i += blockDim.x) {
+            const uint32_t F = i / a, j = i - F * a;
+            S.delta[F * FN_STRIDE + j] = fn_delta[(size_t)(cm.fn_off + F) * FN_STRIDE + j];
+        }
+        // zero the unused deltas the byte tables may touch
+        for (uint32_t i = threadIdx.x; i < nf * (2 * TAB_BITS); i += blockDim.x) {
+            const uint32_t F = i / (2 * TAB_BITS), j = i - F * (2 * TAB_BITS);
+            if (j >= a) S.delta[F * FN_STRIDE + j] = 0;
+        }
+    }
+    const bool tabled = nf <= FN_TAB;
+    const uint32_t keep_lo = lowest_set_bits(cm.keep, TAB_BITS), keep_hi = lowest_set_bits(cm.keep & ~keep_lo, TAB_BITS);
+    if (tabled)
+        for (uint32_t v = threadIdx.x; v < 2 * TAB_SIZE; v += blockDim.x) {
+            if (v < TAB_SIZE) S.pd_lo[v] = pdep32(v, keep_lo);
+            else S.pd_hi[v - TAB_SIZE] = pdep32(v - TAB_SIZE, keep_hi);
+        }
+    __syncthreads();
+    if (tabled) {
+        for (uint32_t run = threadIdx.x; run < nf * 32; run += blockDim.x) {
+            const uint32_t F = run >> 5, half = (run >> 4) & 1u, hi4 = run & 15u;
+            build_cost_table_run(S.delta + F * FN_STRIDE, half, hi4, (half ? S.thi : S.tlo) + F * TAB_SIZE + 16 * hi4);
+        }
+        if (threadIdx.x == 0) {
+            S.tab.pd_lo = S.pd_lo;
+            S.tab.pd_hi = S.pd_hi;
+            S.tab.keep_rest = cm.keep & ~keep_lo & ~keep_hi;
+            S.tab.lo = S.tlo;
+            S.tab.hi = S.thi;
+        }
+    }
+    if (threadIdx.x == 0) S.tabled = tabled;
+    __syncthreads();
+}
+
+__device__ __forceinline__ ColView make_view(const ColShared &S, uint32_t T, uint32_t tb, const uint32_t *fn_c0,
+                                             const int32_t *fn_delta, const uint32_t *prev, uint32_t i) {
     ColView v;
-    v.m = m;
+    v.m = &S.m;
     v.T = T;
     v.tb = tb;
-    const uint32_t g0 = fn_group[m->grp_off + i], g1 = fn_group[m->grp_off + i + 1];
-    v.fn_c0 = fn_c0 + m->fn_off + g0;
-    v.fn_delta = fn_delta + (size_t)(m->fn_off + g0) * FN_STRIDE;
+    const uint32_t g0 = S.group[i], g1 = S.group[i + 1];
+    if (S.staged) {
+        v.fn_c0 = S.c0 + g0;
+        v.fn_delta = S.delta + (size_t)g0 * FN_STRIDE;
+    } else {
+        v.fn_c0 = fn_c0 + S.m.fn_off + g0;
+        v.fn_delta = fn_delta + (size_t)(S.m.fn_off + g0) * FN_STRIDE;
+    }
     v.nf = g1 - g0;
     v.prev = prev;
+    v.tab = S.tabled ? &S.tab : nullptr;
+    v.tab_fn0 = g0;
     return v;
 }
 
+// lanes per projection entry (log2): one thread per entry when the column has enough entries to fill
+// the GPU, otherwise the 2^d candidates of an entry are spread over up to 32 lanes
+__host__ __device__ inline uint32_t col_lane_bits(uint32_t log_entries, uint32_t d) {
+    if (log_entries >= 14) return 0;
+    const uint32_t want = 14 - log_entries;
+    const uint32_t lc = d < want ? d : want;
+    return lc < 5 ? lc : 5;
+}
+
 // Thread e = o*T + i evaluates all 2^d candidates of its projection entry (d small).
-__global__ void __launch_bounds__(256) col_direct_kernel(const ColMeta *__restrict__ cols, uint32_t k, uint32_t T,
+__global__ void __launch_bounds__(256) col_direct_kernel(const __grid_constant__ ColMeta cm, uint32_t nf, uint32_t T,
                                                          uint32_t tb, const uint32_t *__restrict__ fn_c0,
                                                          const int32_t *__restrict__ fn_delta,
                                                          const uint32_t *__restrict__ fn_group,
                                                          const uint32_t *__restrict__ prev, uint32_t *__restrict__ out,
                                                          uint32_t *__restrict__ arena) {
-    __shared__ ColMeta sm;
-    if (threadIdx.x < sizeof(ColMeta) / 4) ((uint32_t *)&sm)[threadIdx.x] = ((const uint32_t *)&cols[k])[threadIdx.x];
-    __syncthreads();
+    __shared__ ColShared S;
+    __shared__ uint32_t bpvals[256];
+    stage_column(S, cm, nf, T, fn_c0, fn_delta, fn_group);
+    const ColMeta &sm = S.m;
+    // 2^lc lanes share one projection entry (its 2^d candidates in parallel, d <= 6), so that even the
+    // small columns of a pedigree expose enough threads to hide instruction latency
+    const uint32_t lc = col_lane_bits(sm.f + tb, sm.d);
+    const uint32_t per = 1u << (sm.d - lc);
     const uint64_t nent = ((uint64_t)1 << sm.f) * T;
-    const uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t bpv = 0;
+    const uint32_t ent_per_block = blockDim.x >> lc;
+    const uint32_t le = threadIdx.x >> lc;                 // entry within the block
+    const uint64_t e = (uint64_t)blockIdx.x * ent_per_block + le;
+    const uint32_t c = threadIdx.x & ((1u << lc) - 1u);   // candidate chunk of this lane
+    unsigned long long key = KEY_INF;
     if (e < nent) {
         const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
-        ColView v = make_view(&sm, T, tb, fn_c0, fn_delta, fn_group, prev, i);
-        const uint64_t key = eval_candidates(v, o, i, 0u, 1u << sm.d);
-        out[e] = (uint32_t)(key >> 32);
-        bpv = (uint32_t)key & low_mask(sm.d + tb);
+        ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i);
+        key = eval_candidates(v, o, i, c * per, (c + 1) * per);
     }
-    bp_store_warp(arena, sm.bp_off, sm.bp_width, e, bpv, e < nent);
+    for (uint32_t off = 1; off < (1u << lc); off <<= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = other < key ? other : key;
+    }
+    if (c == 0) {
+        if (e < nent) out[e] = (uint32_t)(key >> 32);
+        bpvals[le] = e < nent ? ((uint32_t)key & low_mask(sm.d + tb)) : 0u;
+    }
+    __syncthreads();
+    // pack this block's back-pointers: ent_per_block * width bits, a whole number of 32-bit words
+    const uint32_t w = sm.bp_width;
+    if (w) {
+        const uint32_t per_word = 32u / w;
+        const uint32_t words = (ent_per_block * w) >> 5;
+        const uint64_t first_word = ((uint64_t)blockIdx.x * ent_per_block * w) >> 5;
+        if (threadIdx.x < words) {
+            uint32_t word = 0;
+            for (uint32_t q = 0; q < per_word; ++q) word |= (w == 32 ? bpvals[threadIdx.x] : (bpvals[threadIdx.x * per_word + q] << (q * w)));
+            const uint64_t total_words = (nent * w + 31) >> 5;
+            if (first_word + threadIdx.x < total_words) arena[sm.bp_off + first_word + threadIdx.x] = word;
+        }
+    }
 }
 
 // Many dropped reads (chain ends): the 2^d candidates of an entry are split over 2^log_chunks
 // threads; partial minima meet in a 64-bit atomicMin on the key.
-__global__ void __launch_bounds__(256) col_chunk_kernel(const ColMeta *__restrict__ cols, uint32_t k, uint32_t T,
+__global__ void __launch_bounds__(256) col_chunk_kernel(const __grid_constant__ ColMeta cm, uint32_t nf, uint32_t T,
                                                         uint32_t tb, const uint32_t *__restrict__ fn_c0,
                                                         const int32_t *__restrict__ fn_delta,
                                                         const uint32_t *__restrict__ fn_group,
                                                         const uint32_t *__restrict__ prev, uint32_t log_chunks,
                                                         unsigned long long *__restrict__ keys) {
-    __shared__ ColMeta sm;
-    if (threadIdx.x < sizeof(ColMeta) / 4) ((uint32_t *)&sm)[threadIdx.x] = ((const uint32_t *)&cols[k])[threadIdx.x];
-    __syncthreads();
+    __shared__ ColShared S;
+    stage_column(S, cm, nf, T, fn_c0, fn_delta, fn_group);
+    const ColMeta &sm = S.m;
     const uint64_t nent = ((uint64_t)1 << sm.f) * T;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t e = gid >> log_chunks;
@@ -115,7 +219,7 @@ __global__ void __launch_bounds__(256) col_chunk_kernel(const ColMeta *__restric
     if (e < nent) {
         const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
         const uint32_t per = 1u << (sm.d - log_chunks);
-        ColView v = make_view(&sm, T, tb, fn_c0, fn_delta, fn_group, prev, i);
+        ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i);
         key = eval_candidates(v, o, i, c * per, (c + 1) * per);
     }
     if (log_chunks >= 5) {  // a whole warp works on the same entry: reduce before the atomic
@@ -215,6 +319,8 @@ struct whmec_plan {
     DevBuf<int32_t> d_fn_delta;
     DevBuf<unsigned long long> d_keys;
     uint32_t last_buf = 0;
+    uint32_t sweeps_done = 0;
+    cudaGraphExec_t graph_exec = nullptr;
     // tile path
     TilePlan tiles;
 
@@ -224,6 +330,7 @@ struct whmec_plan {
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
         tiles.release(stream);
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) {
@@ -317,9 +424,17 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     return WHMEC_OK;
 }
 
+// The column path issues one (small) kernel per column; a sweep of the same plan is replayed from a
+// CUDA graph from the second time on (launch-bound inner loop, captured once).
 int column_sweep(whmec_plan *pl, std::string &msg) {
     Packed &pk = pl->pk;
     const uint32_t n = pk.n, T = pk.T, tb = pk.tb;
+    if (pl->graph_exec) {
+        CUDA_TRY(cudaGraphLaunch(pl->graph_exec, pl->stream));
+        return WHMEC_OK;
+    }
+    const bool capture = pl->sweeps_done >= 1 && n >= 64;
+    if (capture) CUDA_TRY(cudaStreamBeginCapture(pl->stream, cudaStreamCaptureModeThreadLocal));
     uint32_t launches = 0;
     uint32_t curb = 0;
     for (uint32_t k = 0; k < n; ++k) {
@@ -328,8 +443,10 @@ int column_sweep(whmec_plan *pl, std::string &msg) {
         const uint32_t *prev = pl->d_val[curb ^ 1].p;
         uint32_t *out = pl->d_val[curb].p;
         if (m.d <= 6) {
-            const unsigned blocks = (unsigned)((nent + 255) / 256);
-            col_direct_kernel<<<blocks, 256, 0, pl->stream>>>(pl->d_cols.p, k, T, tb, pl->d_fn_c0.p, pl->d_fn_delta.p,
+            const uint32_t lc = col_lane_bits(m.f + tb, m.d);
+            const uint64_t ent_per_block = 256u >> lc;
+            const unsigned blocks = (unsigned)((nent + ent_per_block - 1) / ent_per_block);
+            col_direct_kernel<<<blocks, 256, 0, pl->stream>>>(m, pk.fn_group[m.grp_off + T], T, tb, pl->d_fn_c0.p, pl->d_fn_delta.p,
                                                                pl->d_fn_group.p, prev, out, pl->d_arena.p);
             launches += 1;
         } else {
@@ -337,7 +454,7 @@ int column_sweep(whmec_plan *pl, std::string &msg) {
             CUDA_TRY(cudaMemsetAsync(pl->d_keys.p, 0xFF, nent * 8, pl->stream));
             const uint64_t threads = nent << log_chunks;
             const unsigned blocks = (unsigned)((threads + 255) / 256);
-            col_chunk_kernel<<<blocks, 256, 0, pl->stream>>>(pl->d_cols.p, k, T, tb, pl->d_fn_c0.p, pl->d_fn_delta.p,
+            col_chunk_kernel<<<blocks, 256, 0, pl->stream>>>(m, pk.fn_group[m.grp_off + T], T, tb, pl->d_fn_c0.p, pl->d_fn_delta.p,
                                                               pl->d_fn_group.p, prev, log_chunks, pl->d_keys.p);
             col_finalize_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, pl->stream>>>(pl->d_cols.p, k, T, tb, pl->d_keys.p,
                                                                                           out, pl->d_arena.p);
@@ -346,8 +463,16 @@ int column_sweep(whmec_plan *pl, std::string &msg) {
         curb ^= 1;
     }
     pl->last_buf = curb ^ 1;
-    CUDA_TRY(cudaGetLastError());
     pl->stats.kernel_launches = launches;
+    if (capture) {
+        cudaGraph_t graph = nullptr;
+        CUDA_TRY(cudaStreamEndCapture(pl->stream, &graph));
+        CUDA_TRY(cudaGraphInstantiate(&pl->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        CUDA_TRY(cudaGraphLaunch(pl->graph_exec, pl->stream));
+    }
+    CUDA_TRY(cudaGetLastError());
+    pl->sweeps_done++;
     return WHMEC_OK;
 }
 
