@@ -271,3 +271,42 @@ def random_problem(
         gt=gt,
         gl=gl,
     )
+
+
+def het_path_cost(prob: FlatProblem, path_index: np.ndarray) -> int:
+    """MEC cost of a given bipartition path for an all-heterozygous single individual:
+    sum over columns of min(D, W - D), D = weight of the reads whose allele disagrees with the
+    side they are on (closed form of pedigreecolumncostcomputer.cpp:101-114 for genotype 0/1).
+    Used as a size-independent consistency check of large GPU runs: the reported optimal cost
+    must be the cost of the reported path."""
+    assert prob.n_ind == 1 and not prob.distrust and np.all(prob.gt == 1)
+    n = prob.n_cols
+    lens = np.diff(prob.read_off.astype(np.int64))
+    rid = np.repeat(np.arange(prob.n_reads), lens)
+    first = prob.ent_col[prob.read_off[:-1].astype(np.int64)].astype(np.int64)
+    last = prob.ent_col[prob.read_off[1:].astype(np.int64) - 1].astype(np.int64)
+    # bit position of a read in column k = its rank among the active reads (reads are sorted by first position)
+    cols = prob.ent_col.astype(np.int64)
+    active = []
+    nxt = 0
+    bitpos = np.zeros(cols.size, np.int64)
+    off = prob.read_off.astype(np.int64)
+    cursor = off[:-1].copy()
+    for k in range(n):
+        active = [r for r in active if last[r] >= k]
+        while nxt < prob.n_reads and first[nxt] == k:
+            active.append(nxt)
+            nxt += 1
+        for j, r in enumerate(active):
+            c = cursor[r]
+            if c < off[r + 1] and cols[c] == k:
+                bitpos[c] = j
+                cursor[r] += 1
+    side = (path_index.astype(np.int64)[cols] >> bitpos) & 1
+    w = prob.ent_phred.astype(np.int64)
+    al = prob.ent_allele.astype(np.int64)
+    valid = al < 2
+    mismatch = (al != side) & valid  # het assignment (side 0 -> allele 0, side 1 -> allele 1)
+    D = np.bincount(cols, weights=np.where(mismatch, w, 0), minlength=n)
+    W = np.bincount(cols, weights=np.where(valid, w, 0), minlength=n)
+    return int(np.minimum(D, W - D).sum())
