@@ -109,11 +109,14 @@ def hbm_peak():
 
 
 def recorded_traffic(workload):
-    """dram bytes per tile-kernel launch from the committed ncu capture, if one exists."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
+    committed `ncu --set full` capture of this workload (profiles/traffic.json), else None."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
-        return json.load(open(path)).get(workload)
-    return None
+        rec = json.load(open(path)).get(workload)
+        if rec:
+            return rec["bytes_per_launch"], rec["report"]
+    return None, None
 
 
 def make_workload(name, cols, rank):
@@ -318,7 +321,8 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(name), "peak_source": peak_src,
+                "traffic": recorded_traffic(name)[0], "traffic_source": recorded_traffic(name)[1], "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": stats["algorithmic_bytes"] / max(launches, 1),
                 "kernel": "tile_panel_kernel" if int(stats["path_kind"]) == 1 else "col_direct_kernel",
                 "algorithmic_bytes_per_step": int(stats["algorithmic_bytes"]), "launches_per_step": launches,
                 "bytes_moved_per_step": {"backpointers": int(stats["backptr_bytes"]), "state": int(stats["state_bytes"])},

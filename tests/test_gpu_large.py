@@ -50,3 +50,15 @@ def test_trio_replay_is_deterministic(gpu):
     b = plan.finish()
     plan.close()
     assert a.same_as(b)
+
+
+def test_pedigree_batched_sweep_equals_sequential_sweep(gpu, monkeypatch):
+    """Trio with 6 chains: the two-pass transfer-matrix sweep (all chains advance together) must write
+    exactly the back-pointers of the column-by-column sweep."""
+    prob = synth.config("cfg5", 3_000)
+    batched, st1 = gpu.solve(prob)
+    monkeypatch.setenv("WHMEC_PED_SEQUENTIAL", "1")
+    sequential, st2 = gpu.solve(prob)
+    assert (st1["path_kind"], st2["path_kind"]) == (3, 2)
+    assert batched.same_as(sequential), batched.diff(sequential)
+    assert st1["kernel_launches"] < st2["kernel_launches"] / 2

@@ -390,7 +390,9 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
         ColMeta &m = pk.cols[k];
         if (k == 0 || pk.cols[k - 1].f == 0) pk.chain_begin.push_back(k);
         const bool lastcol = (k + 1 == n);
-        m.bp_width = round_bp_width(m.d + pk.tb);  // the last column stores its winner too (f == 0)
+        // the last column stores its winner too (f == 0); columns that drop many reads have few entries and
+        // keep one word per entry (a thread block owns one entry there and writes its word alone)
+        m.bp_width = m.d >= 8 ? 32 : round_bp_width(m.d + pk.tb);
         m.bp_off = words;
         uint64_t entries = ((uint64_t)1 << m.f) * T;
         words += (entries * m.bp_width + 31) / 32;

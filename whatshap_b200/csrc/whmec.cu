@@ -150,19 +150,13 @@ __host__ __device__ inline uint32_t col_lane_bits(uint32_t log_entries, uint32_t
     return lc < 5 ? lc : 5;
 }
 
-// Thread e = o*T + i evaluates all 2^d candidates of its projection entry (d small).
-__global__ void __launch_bounds__(256) col_direct_kernel(const __grid_constant__ ColMeta cm, uint32_t nf, uint32_t T,
-                                                         uint32_t tb, const uint32_t *__restrict__ fn_c0,
-                                                         const int32_t *__restrict__ fn_delta,
-                                                         const uint32_t *__restrict__ fn_group,
-                                                         const uint32_t *__restrict__ prev, uint32_t *__restrict__ out,
-                                                         uint32_t *__restrict__ arena) {
-    __shared__ ColShared S;
-    __shared__ uint32_t bpvals[256];
-    stage_column(S, cm, nf, T, fn_c0, fn_delta, fn_group);
+// Body of the per-column kernels for d <= 7: thread (or lane group) per projection entry.
+__device__ __forceinline__ void direct_body(ColShared &S, uint32_t *bpvals, uint32_t T, uint32_t tb,
+                                            const uint32_t *fn_c0, const int32_t *fn_delta, const uint32_t *prev,
+                                            uint32_t *out, uint32_t *arena, bool write_bp) {
     const ColMeta &sm = S.m;
-    // 2^lc lanes share one projection entry (its 2^d candidates in parallel, d <= 6), so that even the
-    // small columns of a pedigree expose enough threads to hide instruction latency
+    // 2^lc lanes share one projection entry (its 2^d candidates in parallel), so that even the small
+    // columns of a pedigree expose enough threads to hide instruction latency
     const uint32_t lc = col_lane_bits(sm.f + tb, sm.d);
     const uint32_t per = 1u << (sm.d - lc);
     const uint64_t nent = ((uint64_t)1 << sm.f) * T;
@@ -187,7 +181,7 @@ __global__ void __launch_bounds__(256) col_direct_kernel(const __grid_constant__
     __syncthreads();
     // pack this block's back-pointers: ent_per_block * width bits, a whole number of 32-bit words
     const uint32_t w = sm.bp_width;
-    if (w) {
+    if (w && write_bp) {
         const uint32_t per_word = 32u / w;
         const uint32_t words = (ent_per_block * w) >> 5;
         const uint64_t first_word = ((uint64_t)blockIdx.x * ent_per_block * w) >> 5;
@@ -198,6 +192,120 @@ __global__ void __launch_bounds__(256) col_direct_kernel(const __grid_constant__
             if (first_word + threadIdx.x < total_words) arena[sm.bp_off + first_word + threadIdx.x] = word;
         }
     }
+}
+
+// Thread e = o*T + i evaluates all 2^d candidates of its projection entry (d small).
+__global__ void __launch_bounds__(256) col_direct_kernel(const __grid_constant__ ColMeta cm, uint32_t nf, uint32_t T,
+                                                         uint32_t tb, const uint32_t *__restrict__ fn_c0,
+                                                         const int32_t *__restrict__ fn_delta,
+                                                         const uint32_t *__restrict__ fn_group,
+                                                         const uint32_t *__restrict__ prev, uint32_t *__restrict__ out,
+                                                         uint32_t *__restrict__ arena) {
+    __shared__ ColShared S;
+    __shared__ uint32_t bpvals[256];
+    stage_column(S, cm, nf, T, fn_c0, fn_delta, fn_group);
+    direct_body(S, bpvals, T, tb, fn_c0, fn_delta, prev, out, arena, true);
+}
+
+// ------------------------------------------------------------------------------------------
+// Batched pedigree sweep.  Transmission vectors couple the DP-independent chains of a pedigree only
+// through the T values handed from one chain to the next (pedigreedptable.cpp:272-297), and a chain
+// is min-plus linear in that vector.  Pass 1 sweeps every chain once per unit input vector (values
+// only) -> its T x T transfer matrix; a tiny prefix pass turns the matrices into every chain's true
+// input vector; pass 2 re-sweeps every chain with its true input, writing the same back-pointers
+// the sequential sweep would write (verified there against the reference).
+// All chains advance together: one launch = one column step of every (chain, input) instance.
+// ------------------------------------------------------------------------------------------
+struct PedStep {
+    ColMeta cm;
+    uint32_t nf;
+    uint32_t slot;   // state slot of the instance (two value buffers per slot)
+    uint32_t flags;  // bit 0: write back-pointers
+    uint32_t pad;
+};
+
+__global__ void __launch_bounds__(256) col_batched_kernel(const PedStep *__restrict__ steps, uint32_t *__restrict__ vals,
+                                                          uint64_t max_ent, uint32_t T, uint32_t tb,
+                                                          const uint32_t *__restrict__ fn_c0, const int32_t *__restrict__ fn_delta,
+                                                          const uint32_t *__restrict__ fn_group, uint32_t *__restrict__ arena,
+                                                          uint32_t parity) {
+    __shared__ ColShared S;
+    __shared__ uint32_t bpvals[256];
+    __shared__ unsigned long long wkeys[8];
+    const PedStep &st = steps[blockIdx.y];
+    const uint64_t nent = ((uint64_t)1 << st.cm.f) * T;
+    const uint32_t d = st.cm.d;
+    uint64_t blocks_needed;
+    if (d <= 7) {
+        const uint32_t lc = col_lane_bits(st.cm.f + tb, d);
+        const uint64_t epb = 256u >> lc;
+        blocks_needed = (nent + epb - 1) / epb;
+    } else {
+        blocks_needed = nent;
+    }
+    if (blockIdx.x >= blocks_needed) return;
+    const uint32_t *prev = vals + ((uint64_t)st.slot * 2 + (parity ^ 1u)) * max_ent;
+    uint32_t *out = vals + ((uint64_t)st.slot * 2 + parity) * max_ent;
+    stage_column(S, st.cm, st.nf, T, fn_c0, fn_delta, fn_group);
+    if (d <= 7) {
+        direct_body(S, bpvals, T, tb, fn_c0, fn_delta, prev, out, arena, (st.flags & 1u) != 0);
+        return;
+    }
+    // many reads end here (chain end): the block owns one entry and splits its 2^d candidates
+    const uint64_t e = blockIdx.x;
+    const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
+    const uint32_t per = 1u << (d - 8);
+    ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i);
+    unsigned long long key = eval_candidates(v, o, i, threadIdx.x * per, (threadIdx.x + 1) * per);
+    for (int off = 16; off > 0; off >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, off);
+        key = other < key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) wkeys[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) key = wkeys[w] < key ? wkeys[w] : key;
+        out[e] = (uint32_t)(key >> 32);
+        if (st.flags & 1u) arena[S.m.bp_off + e] = (uint32_t)key & low_mask(d + tb);  // bp_width == 32 for d >= 8
+    }
+}
+
+// pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
+// arithmetic, give every chain's true input vector (a few hundred operations: one thread)
+__global__ void ped_prefix_kernel(uint32_t *__restrict__ vals, uint64_t max_ent, uint32_t T, uint32_t n_chains,
+                                  const uint32_t *__restrict__ chain_len) {
+    if (blockIdx.x || threadIdx.x) return;
+    // pass-1 slots: chain 0 -> slot 0 (true input); chain c >= 1, unit vector u -> slot 1 + (c-1)*T + u
+    // pass-2 slots: chain c >= 1 -> slot p2 + (c-1), p2 = 1 + (n_chains-1)*T
+    const uint32_t p2 = 1 + (n_chains - 1) * T;
+    uint32_t in[MAX_T], outv[MAX_T];
+    const uint32_t par0 = (chain_len[0] - 1) & 1u;
+    for (uint32_t i = 0; i < T; ++i) in[i] = vals[((uint64_t)0 * 2 + par0) * max_ent + i];
+    for (uint32_t c = 1; c < n_chains; ++c) {
+        uint32_t *dst = vals + ((uint64_t)(p2 + c - 1) * 2 + 1) * max_ent;  // read by the chain's first column (parity 0 step)
+        for (uint32_t i = 0; i < T; ++i) dst[i] = in[i];
+        const uint32_t par = (chain_len[c] - 1) & 1u;
+        for (uint32_t i = 0; i < T; ++i) outv[i] = UMAX;
+        for (uint32_t u = 0; u < T; ++u) {
+            if (in[u] == UMAX) continue;
+            const uint32_t *M = vals + ((uint64_t)(1 + (c - 1) * T + u) * 2 + par) * max_ent;
+            for (uint32_t i = 0; i < T; ++i) {
+                if (M[i] == UMAX) continue;
+                const uint32_t s = in[u] + M[i];
+                if (s < outv[i]) outv[i] = s;
+            }
+        }
+        for (uint32_t i = 0; i < T; ++i) in[i] = outv[i];
+    }
+}
+
+// unit input vectors of pass 1: slot 1 + (c-1)*T + u gets 0 at u, +inf elsewhere
+__global__ void ped_init_kernel(uint32_t *__restrict__ vals, uint64_t max_ent, uint32_t T, uint32_t n_slots) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_slots * T) return;
+    const uint32_t slot = 1 + idx / T, j = idx % T;
+    const uint32_t u = (slot - 1) % T;
+    vals[((uint64_t)slot * 2 + 1) * max_ent + j] = (j == u) ? 0u : UMAX;
 }
 
 // Many dropped reads (chain ends): the 2^d candidates of an entry are split over 2^log_chunks
@@ -319,6 +427,14 @@ struct whmec_plan {
     DevBuf<int32_t> d_fn_delta;
     DevBuf<unsigned long long> d_keys;
     uint32_t last_buf = 0;
+    // batched pedigree sweep (see col_batched_kernel)
+    bool use_ped_batch = false;
+    DevBuf<PedStep> d_ped_steps;
+    DevBuf<uint32_t> d_ped_vals, d_chain_len;
+    std::vector<uint32_t> ped_begin[2], ped_grid[2];
+    uint64_t ped_max_ent = 0;
+    uint32_t ped_slots = 0;
+    const uint32_t *d_last_vals = nullptr;
     uint32_t sweeps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
     // tile path
@@ -329,6 +445,7 @@ struct whmec_plan {
         d_cols.release(); d_fn_c0.release(); d_fn_group.release(); d_val[0].release(); d_val[1].release();
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
+        d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
@@ -416,11 +533,99 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         CUDA_TRY(up(pl->d_fn_group.p, pk.fn_group.data(), pk.fn_group.size() * 4));
         CUDA_TRY(up(pl->d_chain_begin.p, pk.chain_begin.data(), pk.chain_begin.size() * 4));
         pl->stats.path_kind = 2;
+        // pedigrees with several chains: batched two-pass sweep
+        const char *seq = std::getenv("WHMEC_PED_SEQUENTIAL");
+        const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+        if (pk.T > 1 && C >= 2 && pk.safe31 && !(seq && seq[0] == '1')) {
+            const uint32_t T = pk.T;
+            const uint32_t slots = 1 + (C - 1) * T + (C - 1);
+            if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && 1 + (uint64_t)(C - 1) * T <= 65535) {
+                std::vector<PedStep> steps;
+                std::vector<uint32_t> clen(C);
+                uint32_t maxlen = 0;
+                for (uint32_t c = 0; c < C; ++c) {
+                    clen[c] = pk.chain_begin[c + 1] - pk.chain_begin[c];
+                    maxlen = std::max(maxlen, clen[c]);
+                }
+                auto blocks_for = [&](const ColMeta &m) -> uint32_t {
+                    const uint64_t nent = ((uint64_t)1 << m.f) * T;
+                    if (m.d > 7) return (uint32_t)nent;
+                    const uint64_t epb = 256u >> col_lane_bits(m.f + pk.tb, m.d);
+                    return (uint32_t)((nent + epb - 1) / epb);
+                };
+                for (int pass = 0; pass < 2; ++pass) {
+                    pl->ped_begin[pass].clear();
+                    pl->ped_grid[pass].clear();
+                    for (uint32_t st = 0; st < maxlen; ++st) {
+                        pl->ped_begin[pass].push_back((uint32_t)steps.size());
+                        uint32_t gmax = 0;
+                        for (uint32_t c = (pass == 0 ? 0 : 1); c < C; ++c) {
+                            if (clen[c] <= st) continue;
+                            const ColMeta &m = pk.cols[pk.chain_begin[c] + st];
+                            const uint32_t reps = (pass == 0 && c > 0) ? T : 1;
+                            for (uint32_t u = 0; u < reps; ++u) {
+                                PedStep ps;
+                                ps.cm = m;
+                                ps.nf = pk.fn_group[m.grp_off + T];
+                                ps.slot = pass == 0 ? (c == 0 ? 0 : 1 + (c - 1) * T + u) : (1 + (C - 1) * T + (c - 1));
+                                ps.flags = (pass == 1 || c == 0) ? 1u : 0u;
+                                ps.pad = 0;
+                                steps.push_back(ps);
+                            }
+                            gmax = std::max(gmax, blocks_for(m));
+                        }
+                        pl->ped_grid[pass].push_back(gmax);
+                    }
+                    pl->ped_begin[pass].push_back((uint32_t)steps.size());
+                }
+                CUDA_TRY(pl->d_ped_steps.alloc(steps.size(), pl->stream));
+                CUDA_TRY(pl->d_ped_vals.alloc((uint64_t)slots * 2 * max_ent, pl->stream));
+                CUDA_TRY(pl->d_chain_len.alloc(C, pl->stream));
+                CUDA_TRY(up(pl->d_ped_steps.p, steps.data(), steps.size() * sizeof(PedStep)));
+                CUDA_TRY(up(pl->d_chain_len.p, clen.data(), C * 4));
+                CUDA_TRY(cudaStreamSynchronize(pl->stream));  // `steps` and `clen` are stack-local
+                pl->ped_max_ent = max_ent;
+                pl->ped_slots = slots;
+                pl->use_ped_batch = true;
+                const uint32_t last_slot = 1 + (C - 1) * T + (C - 2);
+                pl->d_last_vals = pl->d_ped_vals.p + ((uint64_t)last_slot * 2 + ((clen[C - 1] - 1) & 1u)) * max_ent;
+                pl->stats.path_kind = 3;
+            }
+        }
     }
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     CUDA_TRY(cudaEventElapsedTime(&pl->stats.h2d_ms, pl->ev0, pl->ev1));
     pl->stats.h2d_bytes = h2d;
+    return WHMEC_OK;
+}
+
+int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
+    Packed &pk = pl->pk;
+    const uint32_t T = pk.T, tb = pk.tb;
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+    uint32_t launches = 0;
+    const uint32_t unit_slots = (C - 1) * T;
+    ped_init_kernel<<<(unit_slots * T + 255) / 256, 256, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, unit_slots);
+    ++launches;
+    for (int pass = 0; pass < 2; ++pass) {
+        const size_t nsteps = pl->ped_grid[pass].size();
+        for (size_t st = 0; st < nsteps; ++st) {
+            const uint32_t b0 = pl->ped_begin[pass][st], b1 = pl->ped_begin[pass][st + 1];
+            if (b1 == b0) continue;
+            dim3 grid(pl->ped_grid[pass][st], b1 - b0);
+            col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
+                                                               pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
+                                                               (uint32_t)(st & 1));
+            ++launches;
+        }
+        if (pass == 0) {
+            ped_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, C, pl->d_chain_len.p);
+            ++launches;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    pl->stats.kernel_launches = launches;
     return WHMEC_OK;
 }
 
@@ -488,6 +693,8 @@ int plan_sweep_impl(whmec_plan *pl, std::string &msg) {
         rc = pl->tiles.sweep(pl->pk, pl->stream, msg);
         pl->stats.kernel_launches = pl->tiles.launches;
         pl->stats.state_bytes = pl->tiles.state_bytes;
+    } else if (pl->use_ped_batch) {
+        rc = ped_batched_sweep(pl, msg);
     } else {
         rc = column_sweep(pl, msg);
     }
@@ -521,7 +728,7 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg) {
         const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
         const uint32_t threads = pk.T == 1 ? n_chains : 1;
         backtrace_kernel<<<(threads + 63) / 64, 64, 0, pl->stream>>>(pl->d_cols.p, pl->d_arena.p, pk.T, pk.tb,
-                                                                      pl->d_chain_begin.p, n_chains, n, pl->d_val[pl->last_buf].p,
+                                                                      pl->d_chain_begin.p, n_chains, n, pl->use_ped_batch ? pl->d_last_vals : pl->d_val[pl->last_buf].p,
                                                                       pl->d_path_index.p, pl->d_path_tv.p, pl->d_result.p);
         CUDA_TRY(cudaGetLastError());
     }
