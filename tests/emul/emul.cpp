@@ -32,7 +32,9 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
         if (s->partition) std::memset(s->partition, 1, p->n_reads);
         return WHMEC_OK;
     }
-    std::vector<uint32_t> arena(pk.bp_words + 1, 0), prev, cur;
+    std::vector<uint32_t> arena(pk.bp_words + 1, 0), prev, cur, prevm;
+    std::vector<uint8_t> prevarg;
+    bool have_xform = false;
     for (uint32_t k = 0; k < n; ++k) {
         const ColMeta &m = pk.cols[k];
         if (m.d + tb > 32) { msg = "d + tb > 32"; return fail(WHMEC_ERR_UNSUPPORTED); }
@@ -65,6 +67,8 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
                 v.prev = prev.data();
                 v.tab = use_tab ? &tab : nullptr;
                 v.tab_fn0 = g0;
+                v.prevm = have_xform ? prevm.data() : nullptr;
+                v.prevarg = have_xform ? prevarg.data() : nullptr;
                 uint64_t best = KEY_INF;
                 uint64_t step = chunk ? chunk : ncand;
                 for (uint64_t r0 = 0; r0 < ncand; r0 += step) {  // chunked like the atomic kernel
@@ -76,6 +80,19 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
                 bp_store_serial(arena.data(), m.bp_off, m.bp_width, o * T + i, (uint32_t)best & low_mask(m.d + tb));
             }
         prev.swap(cur);
+        // every third hand-over keeps raw values, the others pre-apply the transition minimum of the next
+        // column (as the batched pedigree kernels do in their epilogue)
+        have_xform = (k + 1 < n) && (k % 3 != 2);
+        if (have_xform) {
+            prevm.assign(nout * T, UMAX);
+            prevarg.assign(nout * T, 0);
+            for (uint64_t o = 0; o < nout; ++o)
+                for (uint32_t i = 0; i < T; ++i) {
+                    uint32_t arg;
+                    prevm[o * T + i] = transition_min(&prev[o * T], T, i, pk.cols[k + 1].rc, &arg);
+                    prevarg[o * T + i] = (uint8_t)arg;
+                }
+        }
     }
     std::vector<uint32_t> pidx(n), ptv(n);
     BtView bv{pk.cols.data(), arena.data(), T, tb};

@@ -36,7 +36,28 @@ struct ColView {
     const uint32_t *prev;      // [2^bw][T] values of the previous projection (ignored if m->first)
     const ColTables *tab;      // nullptr: use the bit loops
     uint32_t tab_fn0;          // index of this group's first function inside the tables
+    // Optional pre-transformed previous projection: prevm[b*T+i] = min_j(prev[b][j] + popcount(i^j)*rc)
+    // with prevarg the smallest minimising j (transition_min below).  Exact whenever no 32-bit sum
+    // wraps (the batched pedigree path requires that); nullptr: raw values in `prev`.
+    const uint32_t *prevm;
+    const uint8_t *prevarg;
 };
+
+// min over the previous transmission value for target value i (pedigreedptable.cpp:270-297 without the
+// column's own cost): smallest j wins ties, all-infinite rows give (UMAX, 0).
+WHMEC_HD uint32_t transition_min(const uint32_t *row /* [T] */, uint32_t T, uint32_t i, uint32_t rc, uint32_t *arg) {
+    uint32_t mn = UMAX, mj = 0;
+    for (uint32_t j = 0; j < T; ++j) {
+        if (row[j] == UMAX) continue;
+        const uint32_t val = row[j] + popc32(i ^ j) * rc;
+        if (val < mn) {
+            mn = val;
+            mj = j;
+        }
+    }
+    *arg = mj;
+    return mn;
+}
 
 WHMEC_HD uint32_t lowest_set_bits(uint32_t mask, uint32_t count) {
     uint32_t out = 0;
@@ -100,6 +121,7 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
     }
 
     uint64_t best = KEY_INF;
+    uint32_t best_b = 0;
     for (uint32_t r = r0; r < r1; ++r) {
         // get_cost(): min over allowed assignments (pedigreecolumncostcomputer.cpp:101-114)
         uint32_t cur = UMAX;
@@ -118,17 +140,25 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
         // min over previous transmission values (pedigreedptable.cpp:270-297), first j wins
         const uint32_t b = x & bmask;
         uint32_t mn = UMAX, mj = 0;
-        for (uint32_t j = 0; j < v.T; ++j) {
-            uint32_t prev = m.first ? 0u : v.prev[(size_t)b * v.T + j];
-            uint32_t val = (cur < UMAX && prev < UMAX) ? cur + prev : UMAX;
-            if (val < UMAX) val += popc32(i ^ j) * m.rc;
-            if (val < mn) {
-                mn = val;
-                mj = j;
+        if (v.prevm && !m.first) {
+            const uint32_t pm = v.prevm[(size_t)b * v.T + i];
+            if (cur < UMAX && pm < UMAX) mn = cur + pm;
+        } else {
+            for (uint32_t j = 0; j < v.T; ++j) {
+                uint32_t prev = m.first ? 0u : v.prev[(size_t)b * v.T + j];
+                uint32_t val = (cur < UMAX && prev < UMAX) ? cur + prev : UMAX;
+                if (val < UMAX) val += popc32(i ^ j) * m.rc;
+                if (val < mn) {
+                    mn = val;
+                    mj = j;
+                }
             }
         }
         uint64_t key = ((uint64_t)mn << 32) | ((uint64_t)r << v.tb) | mj;
-        if (key < best) best = key;
+        if (key < best) {
+            best = key;
+            best_b = b;
+        }
         // step to the next candidate in Gray-rank order: exactly one dropped bit flips
         if (r + 1 < r1) {
             const uint32_t pos = m.dpos[ctz32(r + 1)];
@@ -144,6 +174,8 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
             }
         }
     }
+    // the argmin j of the winner is looked up once (it never decides between candidates: r is unique)
+    if (v.prevm && !m.first && (uint32_t)(best >> 32) != UMAX) best |= v.prevarg[(size_t)best_b * v.T + i];
     return best;
 }
 

@@ -121,7 +121,8 @@ __device__ __forceinline__ void stage_column(ColShared &S, const ColMeta &cm, ui
 }
 
 __device__ __forceinline__ ColView make_view(const ColShared &S, uint32_t T, uint32_t tb, const uint32_t *fn_c0,
-                                             const int32_t *fn_delta, const uint32_t *prev, uint32_t i) {
+                                             const int32_t *fn_delta, const uint32_t *prev, uint32_t i,
+                                             const uint8_t *prevarg = nullptr) {
     ColView v;
     v.m = &S.m;
     v.T = T;
@@ -138,6 +139,8 @@ __device__ __forceinline__ ColView make_view(const ColShared &S, uint32_t T, uin
     v.prev = prev;
     v.tab = S.tabled ? &S.tab : nullptr;
     v.tab_fn0 = g0;
+    v.prevm = prevarg ? prev : nullptr;  // `prev` holds transition minima when their argmins are given
+    v.prevarg = prevarg;
     return v;
 }
 
@@ -153,7 +156,9 @@ __host__ __device__ inline uint32_t col_lane_bits(uint32_t log_entries, uint32_t
 // Body of the per-column kernels for d <= 7: thread (or lane group) per projection entry.
 __device__ __forceinline__ void direct_body(ColShared &S, uint32_t *bpvals, uint32_t T, uint32_t tb,
                                             const uint32_t *fn_c0, const int32_t *fn_delta, const uint32_t *prev,
-                                            uint32_t *out, uint32_t *arena, bool write_bp) {
+                                            uint32_t *out, uint32_t *arena, bool write_bp, const uint8_t *prevarg = nullptr,
+                                            bool xform_out = false, uint32_t rc_next = 0, uint8_t *outarg = nullptr,
+                                            uint32_t *svals = nullptr) {
     const ColMeta &sm = S.m;
     // 2^lc lanes share one projection entry (its 2^d candidates in parallel), so that even the small
     // columns of a pedigree expose enough threads to hide instruction latency
@@ -167,7 +172,7 @@ __device__ __forceinline__ void direct_body(ColShared &S, uint32_t *bpvals, uint
     unsigned long long key = KEY_INF;
     if (e < nent) {
         const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
-        ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i);
+        ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i, prevarg);
         key = eval_candidates(v, o, i, c * per, (c + 1) * per);
     }
     for (uint32_t off = 1; off < (1u << lc); off <<= 1) {
@@ -175,10 +180,21 @@ __device__ __forceinline__ void direct_body(ColShared &S, uint32_t *bpvals, uint
         key = other < key ? other : key;
     }
     if (c == 0) {
-        if (e < nent) out[e] = (uint32_t)(key >> 32);
+        if (xform_out) svals[le] = (uint32_t)(key >> 32);  // KEY_INF for entries beyond the column
+        else if (e < nent) out[e] = (uint32_t)(key >> 32);
         bpvals[le] = e < nent ? ((uint32_t)key & low_mask(sm.d + tb)) : 0u;
     }
     __syncthreads();
+    if (xform_out && threadIdx.x < ent_per_block) {
+        // hand the NEXT column min_j(value_j + popcount(i^j) * rc_next) instead of the raw values: the T
+        // values of one projection index sit next to each other in this block
+        const uint64_t e2 = (uint64_t)blockIdx.x * ent_per_block + threadIdx.x;
+        if (e2 < nent) {
+            uint32_t arg;
+            out[e2] = transition_min(&svals[threadIdx.x & ~(T - 1)], T, (uint32_t)e2 & (T - 1), rc_next, &arg);
+            outarg[e2] = (uint8_t)arg;
+        }
+    }
     // pack this block's back-pointers: ent_per_block * width bits, a whole number of 32-bit words
     const uint32_t w = sm.bp_width;
     if (w && write_bp) {
@@ -220,17 +236,19 @@ struct PedStep {
     ColMeta cm;
     uint32_t nf;
     uint32_t slot;   // state slot of the instance (two value buffers per slot)
-    uint32_t flags;  // bit 0: write back-pointers
-    uint32_t pad;
+    uint32_t flags;  // bit 0: write back-pointers; bit 1: write transition minima for the next column;
+                     // bit 2: the previous projection holds transition minima
+    uint32_t rc_next;
 };
 
 __global__ void __launch_bounds__(256) col_batched_kernel(const PedStep *__restrict__ steps, uint32_t *__restrict__ vals,
                                                           uint64_t max_ent, uint32_t T, uint32_t tb,
                                                           const uint32_t *__restrict__ fn_c0, const int32_t *__restrict__ fn_delta,
                                                           const uint32_t *__restrict__ fn_group, uint32_t *__restrict__ arena,
-                                                          uint32_t parity) {
+                                                          uint32_t parity, uint8_t *__restrict__ args) {
     __shared__ ColShared S;
     __shared__ uint32_t bpvals[256];
+    __shared__ uint32_t svals[256];
     __shared__ unsigned long long wkeys[8];
     const PedStep &st = steps[blockIdx.y];
     const uint64_t nent = ((uint64_t)1 << st.cm.f) * T;
@@ -246,16 +264,19 @@ __global__ void __launch_bounds__(256) col_batched_kernel(const PedStep *__restr
     if (blockIdx.x >= blocks_needed) return;
     const uint32_t *prev = vals + ((uint64_t)st.slot * 2 + (parity ^ 1u)) * max_ent;
     uint32_t *out = vals + ((uint64_t)st.slot * 2 + parity) * max_ent;
+    const uint8_t *prevarg = (st.flags & 4u) ? args + ((uint64_t)st.slot * 2 + (parity ^ 1u)) * max_ent : nullptr;
+    uint8_t *outarg = args + ((uint64_t)st.slot * 2 + parity) * max_ent;
     stage_column(S, st.cm, st.nf, T, fn_c0, fn_delta, fn_group);
     if (d <= 7) {
-        direct_body(S, bpvals, T, tb, fn_c0, fn_delta, prev, out, arena, (st.flags & 1u) != 0);
+        direct_body(S, bpvals, T, tb, fn_c0, fn_delta, prev, out, arena, (st.flags & 1u) != 0, prevarg, (st.flags & 2u) != 0,
+                    st.rc_next, outarg, svals);
         return;
     }
     // many reads end here (chain end): the block owns one entry and splits its 2^d candidates
     const uint64_t e = blockIdx.x;
     const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
     const uint32_t per = 1u << (d - 8);
-    ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i);
+    ColView v = make_view(S, T, tb, fn_c0, fn_delta, prev, i, prevarg);
     unsigned long long key = eval_candidates(v, o, i, threadIdx.x * per, (threadIdx.x + 1) * per);
     for (int off = 16; off > 0; off >>= 1) {
         const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, off);
@@ -431,6 +452,7 @@ struct whmec_plan {
     bool use_ped_batch = false;
     DevBuf<PedStep> d_ped_steps;
     DevBuf<uint32_t> d_ped_vals, d_chain_len;
+    DevBuf<uint8_t> d_ped_args;
     std::vector<uint32_t> ped_begin[2], ped_grid[2];
     uint64_t ped_max_ent = 0;
     uint32_t ped_slots = 0;
@@ -445,7 +467,7 @@ struct whmec_plan {
         d_cols.release(); d_fn_c0.release(); d_fn_group.release(); d_val[0].release(); d_val[1].release();
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
-        d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release();
+        d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release(); d_ped_args.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
@@ -561,15 +583,24 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                         uint32_t gmax = 0;
                         for (uint32_t c = (pass == 0 ? 0 : 1); c < C; ++c) {
                             if (clen[c] <= st) continue;
-                            const ColMeta &m = pk.cols[pk.chain_begin[c] + st];
+                            const uint32_t kcol = pk.chain_begin[c] + st;
+                            const ColMeta &m = pk.cols[kcol];
                             const uint32_t reps = (pass == 0 && c > 0) ? T : 1;
+                            // a column hands transition minima to the next one of its chain when the T values of a
+                            // projection index are produced inside one thread block
+                            auto xform = [&](uint32_t k) {
+                                const ColMeta &q = pk.cols[k];
+                                return k + 1 < pk.chain_begin[c + 1] && q.d <= 7 && T <= (256u >> col_lane_bits(q.f + pk.tb, q.d));
+                            };
                             for (uint32_t u = 0; u < reps; ++u) {
                                 PedStep ps;
                                 ps.cm = m;
                                 ps.nf = pk.fn_group[m.grp_off + T];
                                 ps.slot = pass == 0 ? (c == 0 ? 0 : 1 + (c - 1) * T + u) : (1 + (C - 1) * T + (c - 1));
                                 ps.flags = (pass == 1 || c == 0) ? 1u : 0u;
-                                ps.pad = 0;
+                                if (xform(kcol)) ps.flags |= 2u;
+                                if (st > 0 && xform(kcol - 1)) ps.flags |= 4u;
+                                ps.rc_next = kcol + 1 < pk.n ? pk.cols[kcol + 1].rc : 0;
                                 steps.push_back(ps);
                             }
                             gmax = std::max(gmax, blocks_for(m));
@@ -580,6 +611,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                 }
                 CUDA_TRY(pl->d_ped_steps.alloc(steps.size(), pl->stream));
                 CUDA_TRY(pl->d_ped_vals.alloc((uint64_t)slots * 2 * max_ent, pl->stream));
+                CUDA_TRY(pl->d_ped_args.alloc((uint64_t)slots * 2 * max_ent, pl->stream));
                 CUDA_TRY(pl->d_chain_len.alloc(C, pl->stream));
                 CUDA_TRY(up(pl->d_ped_steps.p, steps.data(), steps.size() * sizeof(PedStep)));
                 CUDA_TRY(up(pl->d_chain_len.p, clen.data(), C * 4));
@@ -616,7 +648,7 @@ int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
             dim3 grid(pl->ped_grid[pass][st], b1 - b0);
             col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
                                                                pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
-                                                               (uint32_t)(st & 1));
+                                                               (uint32_t)(st & 1), pl->d_ped_args.p);
             ++launches;
         }
         if (pass == 0) {
