@@ -179,6 +179,63 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
     return best;
 }
 
+// Values-only evaluation for several input vectors at once (pass 1 of the batched pedigree sweep):
+// the column costs of a cell are shared by all T right-hand sides, only the previous values differ.
+// No tie-breaking is needed here — pass 2 recomputes the winners with the true inputs.
+//   planes:       previous projection of right-hand side u at planes + u * plane_stride
+//   first_chain:  the chain's first column: right-hand side u is the unit vector e_u, i.e. the
+//                 transition minimum is popcount(i ^ u) * rc without touching memory
+//   transformed:  planes hold transition minima (see ColView::prevm), else raw values
+constexpr uint32_t MULTI_MAX = 8;
+
+WHMEC_HD void eval_values_multi(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1, const uint32_t *planes,
+                                uint64_t plane_stride, bool first_chain, bool transformed, uint32_t *mn /* [T] */) {
+    const ColMeta &m = *v.m;
+    const uint32_t drop = ~m.keep & low_mask(m.a);
+    uint32_t kept;
+    if (v.tab) {
+        kept = v.tab->pd_lo[o & (TAB_SIZE - 1)] | v.tab->pd_hi[(o >> TAB_BITS) & (TAB_SIZE - 1)];
+        if (v.tab->keep_rest) kept |= pdep32(o >> (2 * TAB_BITS), v.tab->keep_rest);
+    } else {
+        kept = pdep32(o, m.keep);
+    }
+    uint32_t x = kept | pdep32(r0 ^ (r0 >> 1), drop);
+    const uint32_t bmask = low_mask(m.bw);
+    for (uint32_t u = 0; u < v.T; ++u) mn[u] = UMAX;
+    for (uint32_t r = r0; r < r1; ++r) {
+        uint32_t cur = UMAX;
+        for (uint32_t F = 0; F < v.nf; ++F) {
+            uint32_t c = v.fn_c0[F];
+            uint32_t j0 = 0;
+            if (v.tab) {
+                const size_t t = (size_t)(v.tab_fn0 + F) * TAB_SIZE;
+                c += (uint32_t)(v.tab->lo[t + (x & (TAB_SIZE - 1))] + v.tab->hi[t + ((x >> TAB_BITS) & (TAB_SIZE - 1))]);
+                j0 = 2 * TAB_BITS;
+            }
+            for (uint32_t j = j0; j < m.a; ++j)
+                if ((x >> j) & 1u) c += (uint32_t)v.fn_delta[F * FN_STRIDE + j];
+            if (c < cur) cur = c;
+        }
+        if (cur != UMAX) {
+            const size_t b = (size_t)(x & bmask) * v.T;
+            for (uint32_t u = 0; u < v.T; ++u) {
+                uint32_t pm;
+                if (first_chain) {
+                    // the very first column of the table ignores its input: min_j popcount(i^j)*rc = 0
+                    pm = m.first ? 0u : popc32(i ^ u) * m.rc;
+                } else if (transformed) {
+                    pm = planes[u * plane_stride + b + i];
+                } else {
+                    uint32_t arg;
+                    pm = transition_min(planes + u * plane_stride + b, v.T, i, m.rc, &arg);
+                }
+                if (pm != UMAX && cur + pm < mn[u]) mn[u] = cur + pm;
+            }
+        }
+        if (r + 1 < r1) x ^= 1u << m.dpos[ctz32(r + 1)];
+    }
+}
+
 // Dispatch on the number of cost functions of the transmission group: the common small groups get a
 // small code path (the whole kernel otherwise thrashes the instruction cache).
 WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {

@@ -291,25 +291,102 @@ __global__ void __launch_bounds__(256) col_batched_kernel(const PedStep *__restr
     }
 }
 
+// Pass 1 for the chains that need a transfer matrix: one instance per chain computes the values for all
+// T unit input vectors at once (slots st.slot .. st.slot+T-1).  flags bit 3: first column of its chain.
+__global__ void __launch_bounds__(256) col_multi_kernel(const PedStep *__restrict__ steps, uint32_t *__restrict__ vals,
+                                                        uint64_t max_ent, uint32_t T, uint32_t tb,
+                                                        const uint32_t *__restrict__ fn_c0, const int32_t *__restrict__ fn_delta,
+                                                        const uint32_t *__restrict__ fn_group, uint32_t parity) {
+    __shared__ ColShared S;
+    __shared__ uint32_t svals[MULTI_MAX * 256];
+    const PedStep &st = steps[blockIdx.y];
+    const uint64_t nent = ((uint64_t)1 << st.cm.f) * T;
+    const uint32_t d = st.cm.d;
+    const uint32_t lc = d <= 7 ? col_lane_bits(st.cm.f + tb, d) : 0;
+    const uint32_t ent_per_block = d <= 7 ? (256u >> lc) : 1u;
+    if ((uint64_t)blockIdx.x * ent_per_block >= nent) return;
+    const uint64_t plane_stride = 2 * max_ent;
+    const uint32_t *planes = vals + ((uint64_t)st.slot * 2 + (parity ^ 1u)) * max_ent;
+    uint32_t *out0 = vals + ((uint64_t)st.slot * 2 + parity) * max_ent;
+    const bool first_chain = (st.flags & 8u) != 0, transformed = (st.flags & 4u) != 0, xform_out = (st.flags & 2u) != 0;
+    stage_column(S, st.cm, st.nf, T, fn_c0, fn_delta, fn_group);
+    uint32_t mn[MULTI_MAX];
+    if (d <= 7) {
+        const uint32_t per = 1u << (d - lc);
+        const uint32_t le = threadIdx.x >> lc;
+        const uint64_t e = (uint64_t)blockIdx.x * ent_per_block + le;
+        const uint32_t c = threadIdx.x & ((1u << lc) - 1u);
+        for (uint32_t u = 0; u < T; ++u) mn[u] = UMAX;
+        if (e < nent) {
+            const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
+            ColView v = make_view(S, T, tb, fn_c0, fn_delta, nullptr, i);
+            eval_values_multi(v, o, i, c * per, (c + 1) * per, planes, plane_stride, first_chain, transformed, mn);
+        }
+        for (uint32_t u = 0; u < T; ++u) {
+            uint32_t val = mn[u];
+            for (uint32_t off = 1; off < (1u << lc); off <<= 1) {
+                const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, val, off);
+                val = other < val ? other : val;
+            }
+            if (c == 0) {
+                if (xform_out) svals[u * 256 + le] = val;
+                else if (e < nent) out0[u * plane_stride + e] = val;
+            }
+        }
+        if (xform_out) {
+            __syncthreads();
+            if (threadIdx.x < ent_per_block) {
+                const uint64_t e2 = (uint64_t)blockIdx.x * ent_per_block + threadIdx.x;
+                if (e2 < nent)
+                    for (uint32_t u = 0; u < T; ++u) {
+                        uint32_t arg;
+                        out0[u * plane_stride + e2] =
+                            transition_min(&svals[u * 256 + (threadIdx.x & ~(T - 1))], T, (uint32_t)e2 & (T - 1), st.rc_next, &arg);
+                    }
+            }
+        }
+        return;
+    }
+    // chain end: the block owns one entry
+    const uint64_t e = blockIdx.x;
+    const uint32_t o = (uint32_t)(e >> tb), i = (uint32_t)e & (T - 1);
+    const uint32_t per = 1u << (d - 8);
+    ColView v = make_view(S, T, tb, fn_c0, fn_delta, nullptr, i);
+    eval_values_multi(v, o, i, threadIdx.x * per, (threadIdx.x + 1) * per, planes, plane_stride, first_chain, transformed, mn);
+    for (uint32_t u = 0; u < T; ++u) {
+        uint32_t val = mn[u];
+        for (int off = 16; off > 0; off >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xFFFFFFFFu, val, off);
+            val = other < val ? other : val;
+        }
+        if ((threadIdx.x & 31) == 0) svals[u * 8 + (threadIdx.x >> 5)] = val;
+    }
+    __syncthreads();
+    if (threadIdx.x < T) {
+        uint32_t val = UMAX;
+        for (int w = 0; w < 8; ++w) val = svals[threadIdx.x * 8 + w] < val ? svals[threadIdx.x * 8 + w] : val;
+        out0[threadIdx.x * plane_stride + e] = val;
+    }
+}
+
 // pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
 // arithmetic, give every chain's true input vector (a few hundred operations: one thread)
 __global__ void ped_prefix_kernel(uint32_t *__restrict__ vals, uint64_t max_ent, uint32_t T, uint32_t n_chains,
                                   const uint32_t *__restrict__ chain_len) {
     if (blockIdx.x || threadIdx.x) return;
-    // pass-1 slots: chain 0 -> slot 0 (true input); chain c >= 1, unit vector u -> slot 1 + (c-1)*T + u
-    // pass-2 slots: chain c >= 1 -> slot p2 + (c-1), p2 = 1 + (n_chains-1)*T
-    const uint32_t p2 = 1 + (n_chains - 1) * T;
+    // pass-1 planes: chain c, unit vector u -> slot c*T + u;  pass-2 slot of chain c: n_chains*T + c.
+    // Chain 0 starts the table: its first column ignores the input (pedigreedptable.cpp:275-278), every
+    // plane of it holds the same, true, output.
     uint32_t in[MAX_T], outv[MAX_T];
-    const uint32_t par0 = (chain_len[0] - 1) & 1u;
-    for (uint32_t i = 0; i < T; ++i) in[i] = vals[((uint64_t)0 * 2 + par0) * max_ent + i];
+    for (uint32_t i = 0; i < T; ++i) in[i] = vals[((uint64_t)0 * 2 + ((chain_len[0] - 1) & 1u)) * max_ent + i];
     for (uint32_t c = 1; c < n_chains; ++c) {
-        uint32_t *dst = vals + ((uint64_t)(p2 + c - 1) * 2 + 1) * max_ent;  // read by the chain's first column (parity 0 step)
+        uint32_t *dst = vals + ((uint64_t)(n_chains * T + c) * 2 + 1) * max_ent;  // read by the chain's first column (step 0)
         for (uint32_t i = 0; i < T; ++i) dst[i] = in[i];
         const uint32_t par = (chain_len[c] - 1) & 1u;
         for (uint32_t i = 0; i < T; ++i) outv[i] = UMAX;
         for (uint32_t u = 0; u < T; ++u) {
             if (in[u] == UMAX) continue;
-            const uint32_t *M = vals + ((uint64_t)(1 + (c - 1) * T + u) * 2 + par) * max_ent;
+            const uint32_t *M = vals + ((uint64_t)(c * T + u) * 2 + par) * max_ent;
             for (uint32_t i = 0; i < T; ++i) {
                 if (M[i] == UMAX) continue;
                 const uint32_t s = in[u] + M[i];
@@ -324,8 +401,8 @@ __global__ void ped_prefix_kernel(uint32_t *__restrict__ vals, uint64_t max_ent,
 __global__ void ped_init_kernel(uint32_t *__restrict__ vals, uint64_t max_ent, uint32_t T, uint32_t n_slots) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_slots * T) return;
-    const uint32_t slot = 1 + idx / T, j = idx % T;
-    const uint32_t u = (slot - 1) % T;
+    const uint32_t slot = idx / T, j = idx % T;
+    const uint32_t u = slot % T;
     vals[((uint64_t)slot * 2 + 1) * max_ent + j] = (j == u) ? 0u : UMAX;
 }
 
@@ -453,7 +530,8 @@ struct whmec_plan {
     DevBuf<PedStep> d_ped_steps;
     DevBuf<uint32_t> d_ped_vals, d_chain_len;
     DevBuf<uint8_t> d_ped_args;
-    std::vector<uint32_t> ped_begin[2], ped_grid[2];
+    std::vector<uint32_t> ped_begin[3], ped_grid[3];  // [0] pass 1 (per-input instances), [1] pass 2, [2] pass 1 multi-RHS
+    bool ped_multi = false;
     uint64_t ped_max_ent = 0;
     uint32_t ped_slots = 0;
     const uint32_t *d_last_vals = nullptr;
@@ -560,8 +638,8 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
         if (pk.T > 1 && C >= 2 && pk.safe31 && !(seq && seq[0] == '1')) {
             const uint32_t T = pk.T;
-            const uint32_t slots = 1 + (C - 1) * T + (C - 1);
-            if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && 1 + (uint64_t)(C - 1) * T <= 65535) {
+            const uint32_t slots = C * T + C;
+            if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && (uint64_t)C * T <= 65535) {
                 std::vector<PedStep> steps;
                 std::vector<uint32_t> clen(C);
                 uint32_t maxlen = 0;
@@ -575,17 +653,25 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                     const uint64_t epb = 256u >> col_lane_bits(m.f + pk.tb, m.d);
                     return (uint32_t)((nent + epb - 1) / epb);
                 };
-                for (int pass = 0; pass < 2; ++pass) {
+                pl->ped_multi = T <= MULTI_MAX;
+                for (int pass = 0; pass < 3; ++pass) {
                     pl->ped_begin[pass].clear();
                     pl->ped_grid[pass].clear();
+                    if (pass == 2 && !pl->ped_multi) continue;
                     for (uint32_t st = 0; st < maxlen; ++st) {
                         pl->ped_begin[pass].push_back((uint32_t)steps.size());
                         uint32_t gmax = 0;
-                        for (uint32_t c = (pass == 0 ? 0 : 1); c < C; ++c) {
+                        // pass 0: chain 0 (true input) and, without the multi-RHS kernel, every (chain, unit vector);
+                        // pass 1: chains >= 1 with their true inputs; pass 2: one multi-RHS instance per chain >= 1
+                        // with the multi-RHS kernel pass 0 is empty: chain 0 (whose input is known: the first column
+                        // of the table ignores it) runs in pass 1 like every other chain
+                        const uint32_t c_begin = (pass == 0 && !pl->ped_multi) ? 0 : (pass == 0 ? C : 0);
+                        const uint32_t c_end = C;
+                        for (uint32_t c = c_begin; c < c_end; ++c) {
                             if (clen[c] <= st) continue;
                             const uint32_t kcol = pk.chain_begin[c] + st;
                             const ColMeta &m = pk.cols[kcol];
-                            const uint32_t reps = (pass == 0 && c > 0) ? T : 1;
+                            const uint32_t reps = pass == 0 ? T : 1;
                             // a column hands transition minima to the next one of its chain when the T values of a
                             // projection index are produced inside one thread block
                             auto xform = [&](uint32_t k) {
@@ -596,10 +682,11 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                                 PedStep ps;
                                 ps.cm = m;
                                 ps.nf = pk.fn_group[m.grp_off + T];
-                                ps.slot = pass == 0 ? (c == 0 ? 0 : 1 + (c - 1) * T + u) : (1 + (C - 1) * T + (c - 1));
-                                ps.flags = (pass == 1 || c == 0) ? 1u : 0u;
+                                ps.slot = pass == 1 ? (C * T + c) : (c * T + u);
+                                ps.flags = pass == 1 ? 1u : 0u;
                                 if (xform(kcol)) ps.flags |= 2u;
                                 if (st > 0 && xform(kcol - 1)) ps.flags |= 4u;
+                                if (pass == 2 && st == 0) ps.flags |= 8u;
                                 ps.rc_next = kcol + 1 < pk.n ? pk.cols[kcol + 1].rc : 0;
                                 steps.push_back(ps);
                             }
@@ -619,7 +706,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                 pl->ped_max_ent = max_ent;
                 pl->ped_slots = slots;
                 pl->use_ped_batch = true;
-                const uint32_t last_slot = 1 + (C - 1) * T + (C - 2);
+                const uint32_t last_slot = C * T + (C - 1);
                 pl->d_last_vals = pl->d_ped_vals.p + ((uint64_t)last_slot * 2 + ((clen[C - 1] - 1) & 1u)) * max_ent;
                 pl->stats.path_kind = 3;
             }
@@ -637,19 +724,30 @@ int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
     const uint32_t T = pk.T, tb = pk.tb;
     const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
     uint32_t launches = 0;
-    const uint32_t unit_slots = (C - 1) * T;
+    const uint32_t unit_slots = C * T;
     ped_init_kernel<<<(unit_slots * T + 255) / 256, 256, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, unit_slots);
     ++launches;
     for (int pass = 0; pass < 2; ++pass) {
         const size_t nsteps = pl->ped_grid[pass].size();
         for (size_t st = 0; st < nsteps; ++st) {
             const uint32_t b0 = pl->ped_begin[pass][st], b1 = pl->ped_begin[pass][st + 1];
-            if (b1 == b0) continue;
-            dim3 grid(pl->ped_grid[pass][st], b1 - b0);
-            col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
-                                                               pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
-                                                               (uint32_t)(st & 1), pl->d_ped_args.p);
-            ++launches;
+            if (b1 > b0) {
+                dim3 grid(pl->ped_grid[pass][st], b1 - b0);
+                col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
+                                                                   pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
+                                                                   (uint32_t)(st & 1), pl->d_ped_args.p);
+                ++launches;
+            }
+            if (pass == 0 && pl->ped_multi && st < pl->ped_grid[2].size()) {
+                const uint32_t m0 = pl->ped_begin[2][st], m1 = pl->ped_begin[2][st + 1];
+                if (m1 > m0) {
+                    dim3 grid(pl->ped_grid[2][st], m1 - m0);
+                    col_multi_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + m0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
+                                                                     pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p,
+                                                                     (uint32_t)(st & 1));
+                    ++launches;
+                }
+            }
         }
         if (pass == 0) {
             ped_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, C, pl->d_chain_len.p);
