@@ -102,3 +102,41 @@ def test_empty(gpu, checker):
     prob = synth.sliding_window(0, 5)
     sol, _ = gpu.solve(prob)
     assert sol.cost == 0
+
+
+def _spans_problem(spans, n_cols, seed):
+    """Single individual, all-het, reads given as (first, last) column spans without gaps."""
+    from whatshap_b200._abi import FlatProblem
+
+    rng = np.random.default_rng(seed)
+    off, cols = [0], []
+    for a, b in spans:
+        cols.extend(range(a, b + 1))
+        off.append(len(cols))
+    nnz = len(cols)
+    return FlatProblem(
+        positions=(np.arange(n_cols) + 1) * 10, read_off=np.array(off, np.uint64), ent_col=np.array(cols, np.uint32),
+        ent_allele=rng.integers(0, 2, nnz).astype(np.uint8), ent_phred=rng.integers(1, 30, nnz).astype(np.uint32),
+        read_ind=np.zeros(len(spans), np.uint32), recombcost=np.zeros(n_cols, np.uint32), n_ind=1, gt=np.ones((1, n_cols), np.uint8),
+    )
+
+
+def test_tile_planner_declines_and_column_kernel_takes_over(gpu, checker):
+    """16 reads end in the same column while 3 others continue: more simultaneous drops than a tile
+    holds, so the whole problem must fall back to the general column kernel — same answer."""
+    spans = [(0, 10)] * 16 + [(5, 20)] * 3
+    prob = _spans_problem(spans, 21, seed=4)
+    want = checker.solve(prob)
+    got, stats = gpu.solve(prob)
+    assert stats["path_kind"] == 2
+    assert got.same_as(want), got.diff(want)
+
+
+def test_many_reads_start_together_and_end_one_by_one(gpu, checker):
+    """18 reads start in column 0 (some become tile-global bits at once) and end staggered."""
+    spans = [(0, 3 + i) for i in range(18)]
+    prob = _spans_problem(spans, 21, seed=5)
+    want = checker.solve(prob)
+    got, stats = gpu.solve(prob)
+    assert stats["path_kind"] == 1
+    assert got.same_as(want), got.diff(want)

@@ -58,13 +58,14 @@ bool build_h2p(const whmec_problem *p, uint32_t tv, int8_t *h2p /* [n_ind][2] */
 
 }  // namespace
 
-int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
+int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want_deltas) {
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t_start = tnow();
     const uint32_t n = p->n_cols;
     pk = Packed();
+    pk.has_deltas = want_deltas;
     pk.n = n;
     pk.n_reads = p->n_reads;
     pk.n_ind = p->n_ind;
@@ -182,8 +183,8 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
     }
     const uint32_t n_chunks = n ? (uint32_t)cut.size() - 1 : 0;
     struct Chunk {
-        std::vector<uint32_t> act_read, act_phred, fn_c0, fn_asg, fn_base, fn_group;
-        std::vector<uint8_t> act_allele, act_ind;
+        std::vector<uint32_t> fn_c0, fn_asg, fn_base, fn_group;
+        size_t act_base = 0, act_count = 0;  // this chunk's slice of the (column, active read) arrays
         std::vector<int32_t> fn_delta;
         uint32_t max_a = 0;
         uint64_t base_total = 0, rc_total = 0;
@@ -203,6 +204,21 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
     pk.cols.resize(n);
     pk.act_off.assign(n + 1, 0);
     pk.fn_group.assign((size_t)n * (T + 1), 0);
+    // a read is active in every column of its span: the (column, active read) arrays have exactly
+    // sum(last - first + 1) entries, and a chunk's slice starts after the reads that precede it
+    {
+        size_t total = 0;
+        uint32_t ci = 0;
+        for (uint32_t r = 0; r < p->n_reads; ++r) {
+            while (ci < n_chunks && chunk_first_read[ci] == r) chunks[ci++].act_base = total;
+            total += (size_t)last[r] - first[r] + 1;
+        }
+        while (ci < n_chunks) chunks[ci++].act_base = total;
+        pk.act_read.resize(total);
+        pk.act_allele.resize(total);
+        pk.act_phred.resize(total);
+        pk.act_ind.resize(total);
+    }
 
     auto build_chunk = [&](uint32_t ci) {
         Chunk &ch = chunks[ci];
@@ -234,23 +250,25 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
             for (uint32_t r : active)
                 if (std::binary_search(prev_active.begin(), prev_active.end(), r)) ++w;
             m.bw = (k == 0) ? 0 : w;
-            const size_t e0 = ch.act_read.size();
-            pk.act_off[k] = e0;  // chunk-relative for now
+            const size_t e0 = ch.act_base + ch.act_count;
+            pk.act_off[k] = e0;
             for (uint32_t j = 0; j < m.a; ++j) {
                 const uint32_t r = active[j];
                 uint64_t &cur = cursor[r - r0];
                 while (p->ent_col[cur] < k) ++cur;
-                ch.act_read.push_back(r);
-                ch.act_ind.push_back((uint8_t)p->read_ind[r]);
+                const size_t q = e0 + j;
+                pk.act_read[q] = r;
+                pk.act_ind[q] = (uint8_t)p->read_ind[r];
                 if (p->ent_col[cur] == k) {
-                    ch.act_allele.push_back(p->ent_allele[cur]);
-                    ch.act_phred.push_back(p->ent_phred[cur]);
+                    pk.act_allele[q] = p->ent_allele[cur];
+                    pk.act_phred[q] = p->ent_phred[cur];
                 } else {  // gap inside the read's span: BLANK entry, phred 0 (columniterator.cpp:131)
-                    ch.act_allele.push_back(2);
-                    ch.act_phred.push_back(0);
+                    pk.act_allele[q] = 2;
+                    pk.act_phred[q] = 0;
                 }
                 if (k + 1 < n && last[r] >= k + 1) m.keep |= 1u << j;
             }
+            ch.act_count += m.a;
             m.f = popc32(m.keep);
             m.d = m.a - m.f;
             uint32_t di = 0;
@@ -284,18 +302,18 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
                     max_base = std::max(max_base, base);
                     uint32_t c0 = base;
                     const size_t doff = ch.fn_delta.size();
-                    ch.fn_delta.resize(doff + FN_STRIDE, 0);
+                    if (want_deltas) ch.fn_delta.resize(doff + FN_STRIDE, 0);
                     for (uint32_t j = 0; j < m.a; ++j) {
-                        const uint8_t al = ch.act_allele[e0 + j];
+                        const uint8_t al = pk.act_allele[e0 + j];
                         if (al > 1) continue;  // BLANK contributes nothing
-                        const uint32_t w2 = ch.act_phred[e0 + j];
-                        const uint32_t ind = ch.act_ind[e0 + j];
+                        const uint32_t w2 = pk.act_phred[e0 + j];
+                        const uint32_t ind = pk.act_ind[e0 + j];
                         // read on haplotype `bit` of its individual sits in partition h2p[ind][bit]; it costs
                         // w when the allele assigned to that partition differs (cost computer :59-67)
                         const uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w2 : 0;
                         const uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w2 : 0;
                         c0 += cost0;
-                        ch.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
+                        if (want_deltas) ch.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
                     }
                     ch.fn_c0.push_back(c0);
                     ch.fn_asg.push_back(A);
@@ -341,41 +359,28 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err) {
     uint32_t max_a = 0;
     uint64_t base_total = 0, rc_total = 0;
     {
-        size_t act_total = 0, fn_total = 0;
-        std::vector<size_t> act_base(n_chunks), fn_base_off(n_chunks);
+        size_t fn_total = 0;
+        std::vector<size_t> fn_base_off(n_chunks);
         for (uint32_t ci = 0; ci < n_chunks; ++ci) {
-            act_base[ci] = act_total;
             fn_base_off[ci] = fn_total;
-            act_total += chunks[ci].act_read.size();
             fn_total += chunks[ci].fn_c0.size();
             max_a = std::max(max_a, chunks[ci].max_a);
             base_total += chunks[ci].base_total;
             rc_total += chunks[ci].rc_total;
         }
-        pk.act_read.resize(act_total);
-        pk.act_allele.resize(act_total);
-        pk.act_phred.resize(act_total);
-        pk.act_ind.resize(act_total);
         pk.fn_c0.resize(fn_total);
         pk.fn_asg.resize(fn_total);
         pk.fn_base.resize(fn_total);
-        pk.fn_delta.resize(fn_total * FN_STRIDE);
+        pk.fn_delta.resize(want_deltas ? fn_total * FN_STRIDE : 0);
         for (uint32_t ci = 0; ci < n_chunks; ++ci) {
             Chunk &ch = chunks[ci];
-            std::copy(ch.act_read.begin(), ch.act_read.end(), pk.act_read.begin() + act_base[ci]);
-            std::copy(ch.act_allele.begin(), ch.act_allele.end(), pk.act_allele.begin() + act_base[ci]);
-            std::copy(ch.act_phred.begin(), ch.act_phred.end(), pk.act_phred.begin() + act_base[ci]);
-            std::copy(ch.act_ind.begin(), ch.act_ind.end(), pk.act_ind.begin() + act_base[ci]);
             std::copy(ch.fn_c0.begin(), ch.fn_c0.end(), pk.fn_c0.begin() + fn_base_off[ci]);
             std::copy(ch.fn_asg.begin(), ch.fn_asg.end(), pk.fn_asg.begin() + fn_base_off[ci]);
             std::copy(ch.fn_base.begin(), ch.fn_base.end(), pk.fn_base.begin() + fn_base_off[ci]);
             std::copy(ch.fn_delta.begin(), ch.fn_delta.end(), pk.fn_delta.begin() + fn_base_off[ci] * FN_STRIDE);
-            for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) {
-                pk.act_off[k] += act_base[ci];
-                pk.cols[k].fn_off += (uint32_t)fn_base_off[ci];
-            }
+            for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) pk.cols[k].fn_off += (uint32_t)fn_base_off[ci];
         }
-        pk.act_off[n] = act_total;
+        pk.act_off[n] = pk.act_read.size();
     }
     pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 28);
     const auto t_merge = tnow();

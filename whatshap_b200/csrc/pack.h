@@ -12,6 +12,7 @@ namespace whmec {
 struct Packed {
     uint32_t n = 0, n_reads = 0, n_ind = 0, n_trios = 0;
     uint32_t T = 1, tb = 0, P = 2;
+    bool has_deltas = true;              // fn_delta filled
     bool safe31 = false;                 // every reachable cost value < 2^30 (tile-kernel arithmetic is exact)
     std::vector<ColMeta> cols;           // [n]
     // active reads per column, CSR aligned with cols[k].a
@@ -35,7 +36,8 @@ struct Packed {
 };
 
 // Returns WHMEC_OK or an error code with a reference-compatible message in `err`.
-int pack_problem(const whmec_problem *p, Packed &out, std::string &err);
+// `want_deltas == false` skips the per-read deltas of the cost functions (the tile kernel does not use them).
+int pack_problem(const whmec_problem *p, Packed &out, std::string &err, bool want_deltas = true);
 
 // get_optimal_partitioning + get_super_reads from the optimal path (pedigreedptable.cpp:344-406).
 int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *path_tv,

@@ -574,9 +574,18 @@ void keep_host_memory() {
 
 int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::string &msg) {
     keep_host_memory();
-    int rc = pack_problem(p, pl->pk, msg);
+    // single-individual problems normally run on the tile kernel, which needs no per-read cost deltas
+    const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
+    const bool forced_column = force && force[0] == '1';
+    const bool tile_candidate = p->n_ind == 1 && p->n_trios == 0 && !forced_column;
+    int rc = pack_problem(p, pl->pk, msg, !tile_candidate);
     if (rc != WHMEC_OK) return rc;
     Packed &pk = pl->pk;
+    pl->use_tiles = tile_candidate && pk.n > 0 && pl->tiles.plan(pk);
+    if (tile_candidate && !pl->use_tiles && pk.n > 0) {  // planner declined: the column kernel needs the deltas
+        rc = pack_problem(p, pl->pk, msg, true);
+        if (rc != WHMEC_OK) return rc;
+    }
     pl->device = device;
     pl->stats = pk.stats;
     if (pk.n == 0) return WHMEC_OK;
@@ -598,8 +607,6 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     uint64_t h2d = 0;
 
-    const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
-    pl->use_tiles = !(force && force[0] == '1') && pl->tiles.plan(pk);
     if (pl->use_tiles) {
         rc = pl->tiles.create(pk, pl->stream, h2d, msg);
         if (rc != WHMEC_OK) return rc;
