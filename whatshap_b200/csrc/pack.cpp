@@ -432,7 +432,9 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
     }
     if (!s->sr_allele && !s->sr_quality) return WHMEC_OK;
     // get_super_reads -> get_alleles (pedigreecolumncostcomputer.cpp:117-175)
-    for (uint32_t k = 0; k < n; ++k) {
+    std::atomic<int> failed{0};
+    auto do_range = [&](uint32_t kb, uint32_t ke) {
+    for (uint32_t k = kb; k < ke; ++k) {
         const ColMeta &m = pk.cols[k];
         const uint32_t t = path_tv[k], x = path_index[k];
         const int8_t *h2p = &pk.h2p[(size_t)t * pk.n_ind * 2];
@@ -473,8 +475,8 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
             }
         }
         if (best == UMAX) {
-            err = "Error: Mendelian conflict";
-            return WHMEC_ERR_MENDELIAN;
+            failed.store(1);
+            return;
         }
         for (uint32_t i = 0; i < pk.n_ind; ++i) {
             uint32_t quality = 0;
@@ -489,6 +491,24 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
             }
             if (s->sr_quality) s->sr_quality[(size_t)i * n + k] = quality;
         }
+    }
+    };
+    {
+        uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
+        const uint32_t nthreads = std::min<uint32_t>(hw, n / 4096 + 1);
+        if (nthreads <= 1) {
+            do_range(0, n);
+        } else {
+            std::vector<std::thread> pool;
+            const uint32_t step = (n + nthreads - 1) / nthreads;
+            for (uint32_t t = 0; t < nthreads; ++t) pool.emplace_back(do_range, std::min(n, t * step), std::min(n, (t + 1) * step));
+            for (auto &th : pool) th.join();
+        }
+    }
+    if (failed.load()) {
+        err = "Error: Mendelian conflict";
+        return WHMEC_ERR_MENDELIAN;
     }
     return WHMEC_OK;
 }
