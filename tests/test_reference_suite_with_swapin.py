@@ -1,0 +1,29 @@
+"""The reference's OWN unit tests for this path (tests/test_phasing.py, tests/test_pedigreephasing.py,
+tests/test_verification.py — SURVEY.md §4) run unmodified from /root/reference with
+`whatshap.core.PedigreeDPTable` replaced by this repository's swap-in class operating on the real
+Cython ReadSet / Pedigree objects.  Authoring container only (needs /root/reference)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get("WHATSHAP_REF", "/root/reference")
+
+
+def test_reference_tests_pass_with_swapped_dp_table():
+    from oracle import build_pyref
+
+    pyref = build_pyref.build()
+    if not pyref:
+        pytest.skip("reference tree not available")
+    env = dict(os.environ, WHMEC_PYREF=pyref, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), pyref, ROOT]))
+    cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "swapin_plugin",
+           "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py"]
+    res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=900)
+    tail = (res.stdout + res.stderr)[-2000:]
+    assert res.returncode == 0, tail
+    assert " passed" in tail and "failed" not in tail, tail
+    # make sure the swap really happened: the plugin module must have been imported by that run
+    assert "swapin_plugin" not in res.stderr or "No module" not in res.stderr
