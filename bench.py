@@ -326,6 +326,11 @@ def main():
                 "kernel": "tile_panel_kernel" if int(stats["path_kind"]) == 1 else "col_direct_kernel",
                 "algorithmic_bytes_per_step": int(stats["algorithmic_bytes"]), "launches_per_step": launches,
                 "bytes_moved_per_step": {"backpointers": int(stats["backptr_bytes"]), "state": int(stats["state_bytes"])},
+                "note": ("algorithmic bytes follow the reference's data layout (u32 projection read + u32 value and u32 back-pointer "
+                         "written per entry and column, SURVEY.md 8(d)); the tile kernel keeps the projection in shared memory for a "
+                         "whole panel of columns and stores 1-bit back-pointers, so its real DRAM traffic (`traffic`, ncu) is far below "
+                         "that and frac can exceed 1: the kernel is bound by integer issue, see dp_cells_per_s"),
+                "dp_cells_per_s": stats["cells"] / (statistics.mean(sweep_ms) / 1e3),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
