@@ -140,3 +140,15 @@ def test_many_reads_start_together_and_end_one_by_one(gpu, checker):
     got, stats = gpu.solve(prob)
     assert stats["path_kind"] == 1
     assert got.same_as(want), got.diff(want)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fuzz_high_coverage_irregular_single_individual(gpu, checker, kernel_path, seed):
+    """Irregular spans at coverage up to 13: columns with >= 2^10 outputs take the tile kernel's fast
+    paths (one read ends, zero / one / several reads start) as well as its generic loops."""
+    rng = np.random.default_rng(900 + seed)
+    for it in range(12):
+        prob = synth.random_problem(rng, int(rng.integers(20, 45)), 13, "single", distrust=bool(rng.integers(0, 2)),
+                                    conflict_free=True, max_phred=int(rng.integers(1, 30)), mean_len=float(rng.choice([8, 14])),
+                                    gap=0.05)
+        assert_same(gpu, checker, prob, f"seed={seed} it={it}", want_path=kernel_path)
