@@ -152,3 +152,29 @@ def test_fuzz_high_coverage_irregular_single_individual(gpu, checker, kernel_pat
                                     conflict_free=True, max_phred=int(rng.integers(1, 30)), mean_len=float(rng.choice([8, 14])),
                                     gap=0.05)
         assert_same(gpu, checker, prob, f"seed={seed} it={it}", want_path=kernel_path)
+
+
+def test_pedigree_many_reads_end_mid_chain(gpu, checker):
+    """Trio, two chains; inside the first chain 9 reads end in one column while others continue
+    (d = 9: one thread block per projection entry, raw hand-over to the next column) — the batched
+    two-pass sweep must still equal the reference."""
+    from whatshap_b200._abi import FlatProblem
+
+    rng = np.random.default_rng(12)
+    spans = [(0, 6)] * 9 + [(3, 12)] * 3 + [(8, 12)] * 2 + [(13, 20)] * 4 + [(15, 20)] * 3
+    n_cols = 21
+    off, cols = [0], []
+    for a, b in spans:
+        cols.extend(range(a, b + 1))
+        off.append(len(cols))
+    nnz = len(cols)
+    prob = FlatProblem(
+        positions=(np.arange(n_cols) + 1) * 10, read_off=np.array(off, np.uint64), ent_col=np.array(cols, np.uint32),
+        ent_allele=rng.integers(0, 2, nnz).astype(np.uint8), ent_phred=rng.integers(1, 9, nnz).astype(np.uint32),
+        read_ind=(np.arange(len(spans)) % 3).astype(np.uint32), recombcost=np.full(n_cols, 3, np.uint32), n_ind=3,
+        trios=np.array([0, 1, 2], np.uint32), gt=np.ones((3, n_cols), np.uint8),
+    )
+    want = checker.solve(prob)
+    got, stats = gpu.solve(prob)
+    assert stats["path_kind"] == 3
+    assert got.same_as(want), got.diff(want)

@@ -83,7 +83,7 @@ WHMEC_HD void build_cost_table_run(const int32_t *delta /* [FN_STRIDE] of F */, 
 // Best key over candidates r in [r0, r1) of forward-projection entry `o` for transmission value i.
 // Reference: one iteration of the Gray-code loop body (pedigreedptable.cpp:239-327), restricted
 // to the candidates projecting onto `o` and visited in the same relative order.
-template <int NFR>
+template <int NFR, bool EXACT = false>
 WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
     const ColMeta &m = *v.m;
     const uint32_t drop = ~m.keep & low_mask(m.a);
@@ -97,13 +97,13 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
     const uint32_t cg = rank_offset(m, kept);
     uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cg, drop);
     const uint32_t bmask = low_mask(m.bw);
-    const bool incremental = v.nf <= (uint32_t)NFR;
+    const bool incremental = EXACT || v.nf <= (uint32_t)NFR;
 
     uint32_t cost[NFR];
     if (incremental) {
 #pragma unroll
         for (int F = 0; F < NFR; ++F) {
-            if ((uint32_t)F < v.nf) {
+            if (EXACT || (uint32_t)F < v.nf) {
                 uint32_t c = v.fn_c0[F];
                 uint32_t j0 = 0;
                 if (v.tab) {  // bits 0..15 from the byte tables, the rest (a > 16) bit by bit
@@ -128,7 +128,7 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
         if (incremental) {
 #pragma unroll
             for (int F = 0; F < NFR; ++F)
-                if ((uint32_t)F < v.nf && cost[F] < cur) cur = cost[F];
+                if ((EXACT || (uint32_t)F < v.nf) && cost[F] < cur) cur = cost[F];
         } else {
             for (uint32_t F = 0; F < v.nf; ++F) {
                 uint32_t c = v.fn_c0[F];
@@ -167,7 +167,7 @@ WHMEC_HD uint64_t eval_candidates_t(const ColView &v, uint32_t o, uint32_t i, ui
                 const bool set = (x >> pos) & 1u;
 #pragma unroll
                 for (int F = 0; F < NFR; ++F)
-                    if ((uint32_t)F < v.nf) {
+                    if (EXACT || (uint32_t)F < v.nf) {
                         uint32_t dlt = (uint32_t)v.fn_delta[F * FN_STRIDE + pos];
                         cost[F] += set ? dlt : (0u - dlt);
                     }
@@ -239,7 +239,13 @@ WHMEC_HD void eval_values_multi(const ColView &v, uint32_t o, uint32_t i, uint32
 // Dispatch on the number of cost functions of the transmission group: the common small groups get a
 // small code path (the whole kernel otherwise thrashes the instruction cache).
 WHMEC_HD uint64_t eval_candidates(const ColView &v, uint32_t o, uint32_t i, uint32_t r0, uint32_t r1) {
-    if (v.nf <= 4) return eval_candidates_t<4>(v, o, i, r0, r1);
+    switch (v.nf) {  // exact small counts: no per-function predicates in the candidate loop
+        case 1: return eval_candidates_t<1, true>(v, o, i, r0, r1);
+        case 2: return eval_candidates_t<2, true>(v, o, i, r0, r1);
+        case 3: return eval_candidates_t<3, true>(v, o, i, r0, r1);
+        case 4: return eval_candidates_t<4, true>(v, o, i, r0, r1);
+        default: break;
+    }
     return eval_candidates_t<NF_REG>(v, o, i, r0, r1);
 }
 
