@@ -70,6 +70,18 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
     pk.n_reads = p->n_reads;
     pk.n_ind = p->n_ind;
     pk.n_trios = p->n_trios;
+    if (n > 0 && (!p->recombcost || (!p->distrust && !p->gt))) {
+        err = "recombcost and genotypes must be given for every column";
+        return WHMEC_ERR_INPUT;
+    }
+    if (p->n_reads > 0 && (!p->read_off || !p->ent_col || !p->ent_allele || !p->ent_phred || !p->read_ind)) {
+        err = "read arrays must not be null";
+        return WHMEC_ERR_INPUT;
+    }
+    if (p->n_trios > 0 && !p->trios) {
+        err = "trios must not be null";
+        return WHMEC_ERR_INPUT;
+    }
     if (p->n_ind == 0 || p->n_ind > MAX_IND) {
         err = "pedigree must have between 1 and 16 individuals";
         return WHMEC_ERR_UNSUPPORTED;

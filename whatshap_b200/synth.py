@@ -1,9 +1,9 @@
 """Deterministic synthetic ReadSets for the BASELINE.json configurations.
 
 There is no reference generator: the reference ships no benchmark for this path.  These
-generators emit the *flat* problem (`FlatProblem`) directly; `to_objects()` turns a flat problem
-into the Python-level `ReadSet` / `Pedigree` the way `whatshap phase` would hand them to
-`PedigreeDPTable` (whatshap/cli/phase.py:542-610).
+generators emit the *flat* problem (`FlatProblem`, the arrays of the C ABI) directly, in the read
+order `ReadSet.sort()` would produce (sorted by first position), which is what `whatshap phase` hands
+to `PedigreeDPTable` (whatshap/cli/phase.py:542-610).
 """
 from __future__ import annotations
 
@@ -233,10 +233,8 @@ def random_problem(
     haps = rng.integers(0, 2, (n_ind, 2, n_cols))
     hom = rng.random((n_ind, n_cols)) < hom_rate
     haps[:, 1, :] = np.where(hom, haps[:, 0, :], haps[:, 1, :])
-    for (f, m, c) in T:  # parents always precede children in these pedigrees or are fixed up in order
-        pass
-    order = list(range(n_ind))
-    done = set(i for i in range(n_ind) if i not in T[:, 2].tolist()) if T.size else set(order)
+    # children inherit one haplotype per parent (parents are resolved before their children)
+    done = set(i for i in range(n_ind) if i not in T[:, 2].tolist()) if T.size else set(range(n_ind))
     while len(done) < n_ind:
         for (f, m, c) in T:
             if c not in done and f in done and m in done:
