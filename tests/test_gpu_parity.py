@@ -178,3 +178,19 @@ def test_pedigree_many_reads_end_mid_chain(gpu, checker):
     got, stats = gpu.solve(prob)
     assert stats["path_kind"] == 3
     assert got.same_as(want), got.diff(want)
+
+
+def test_tiny_chain_before_a_multi_tile_chain(gpu, checker):
+    """Regression: a one-read chain (2 state words) used to leave the next chain's state buffers off a
+    16-byte boundary, which the vectorised tile-major hand-off needs (irregular data only)."""
+    spans = [(0, 1)]
+    for s in range(-15, 38):
+        a, b = max(2, 2 + s), min(2 + s + 16, 41)
+        if b - a >= 1:
+            spans.append((a, b))
+    spans.sort(key=lambda ab: ab[0])
+    prob = _spans_problem(spans, 42, seed=8)
+    want = checker.solve(prob)
+    got, stats = gpu.solve(prob)
+    assert stats["path_kind"] == 1 and stats["max_active"] == 17
+    assert got.same_as(want), got.diff(want)

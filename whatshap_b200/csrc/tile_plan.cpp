@@ -59,7 +59,8 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1] - 1;
         uint32_t fmax = 0;
         for (uint32_t k = k0; k <= k1; ++k) fmax = std::max(fmax, pk.cols[k].f);
-        const uint64_t buf_words = (uint64_t)1 << fmax;
+        // at least 4 words so that every chain's buffers stay 16-byte aligned (vector stores of whole tiles)
+        const uint64_t buf_words = std::max<uint64_t>(4, (uint64_t)1 << fmax);
         const uint64_t chain_state = 0;
         chain_state_words[c] = 2 * buf_words;
         uint64_t bp_words = 0;

@@ -190,6 +190,7 @@ def random_problem(
     mean_len: float = 4.0,
     conflict_free: bool = True,
     hom_rate: float = 0.2,
+    burst: int = 3,
 ) -> FlatProblem:
     """Irregular instance for fuzzing: random spans, interior gaps, tie-heavy small weights,
     blank (allele 2) entries, columns without reads, coverage capped at `max_cov`."""
@@ -198,8 +199,7 @@ def random_problem(
     reads = []
     start = 0
     while start < n_cols:
-        burst = int(rng.integers(0, 3))
-        for _ in range(burst):
+        for _ in range(int(rng.integers(0, burst))):
             L = 1 + int(rng.geometric(1.0 / mean_len))
             end = min(n_cols - 1, start + L)
             if end == start:
