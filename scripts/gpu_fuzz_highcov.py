@@ -1,6 +1,6 @@
 """Parity fuzz of the multi-tile paths (coverage 15-18, irregular spans): tile kernel with global bits,
 canonical and tile-major hand-offs, vs the compiled reference and vs the column kernel.
-    python scripts/gpu_fuzz_highcov.py [seconds]"""
+    python scripts/gpu_fuzz_highcov.py [seconds [min_coverage max_coverage]]"""
 import os
 import sys
 import time
@@ -12,12 +12,13 @@ from oracle import checker  # noqa: E402
 from whatshap_b200 import _lib, synth  # noqa: E402
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+cov_lo, cov_hi = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (15, 18)
 ck = checker.best()
 rng = np.random.default_rng(int(time.time()) & 0xFFFF)
 t0 = time.time()
 n = errs = multi = 0
 while time.time() - t0 < budget:
-    cov = int(rng.integers(15, 19))
+    cov = int(rng.integers(cov_lo, cov_hi + 1))
     prob = synth.random_problem(rng, int(rng.integers(12, 40)), cov, "single", distrust=bool(rng.integers(0, 3) == 0),
                                 conflict_free=True, max_phred=int(rng.integers(1, 40)), mean_len=float(rng.choice([10, 16, 24])),
                                 gap=float(rng.choice([0.0, 0.1])), burst=6)
