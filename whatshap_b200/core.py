@@ -11,6 +11,7 @@ fallback: constructing a `PedigreeDPTable` without the CUDA library or a GPU rai
 from __future__ import annotations
 
 import copy
+from itertools import chain
 from math import comb
 from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
 
@@ -535,38 +536,56 @@ def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, di
         pos_list = readset.get_positions()
     else:
         pos_list = [int(p) for p in positions]
-    col_of = {p: i for i, p in enumerate(pos_list)}
     n = len(pos_list)
-    read_off = [0]
-    ent_col: List[int] = []
-    ent_allele: List[int] = []
-    ent_phred: List[int] = []
-    read_ind = []
-    prev_first = None
-    for r in readset:
-        read_ind.append(pedigree.id_to_index(r.sample_id))  # raises like Pedigree::id_to_index
-        if not r._pos:
-            raise RuntimeError("No variants present")
-        if prev_first is not None and r._pos[0] < prev_first:
+    reads = readset._reads
+    m = len(reads)
+    # -- reads: one vectorised pass over all variants (the containers keep plain Python lists) ------------
+    read_ind = np.fromiter((pedigree.id_to_index(r._sample_id) for r in reads), np.uint32, count=m)  # raises like id_to_index
+    lens = np.fromiter((len(r._pos) for r in reads), np.int64, count=m)
+    if m and int(lens.min()) == 0:
+        raise RuntimeError("No variants present")
+    total = int(lens.sum())
+    pos = np.fromiter(chain.from_iterable(r._pos for r in reads), np.int64, count=total)
+    allele = np.fromiter(chain.from_iterable(r._allele for r in reads), np.int64, count=total)
+    quality = np.fromiter(chain.from_iterable(r._quality for r in reads), np.int64, count=total)
+    off = np.zeros(m + 1, np.int64)
+    np.cumsum(lens, out=off[1:])
+    if m:
+        first, last_i = off[:-1], off[1:] - 1
+        if m > 1 and bool((np.diff(pos[first]) < 0).any()):
             raise RuntimeError("ColumnIterator: reads in ReadSet are not sorted.")
-        if not r.is_sorted():
+        step = np.diff(pos)
+        step[last_i[:-1]] = 1  # differences across read boundaries do not count
+        if bool((step <= 0).any()):
             raise RuntimeError("ColumnIterator: encountered read with unsorted variants.")
-        prev_first = r._pos[0]
-        if r._pos[0] not in col_of or r._pos[-1] not in col_of:
+    pos_arr = np.array(pos_list, np.int64)
+    if n and bool((np.diff(pos_arr) <= 0).any()):
+        # unsorted / repeated explicit positions: the last occurrence defines the column, as in a dict
+        col_of = {p: i for i, p in enumerate(pos_list)}
+        col = np.fromiter((col_of.get(int(p), -1) for p in pos), np.int64, count=total)
+    elif n:
+        col = np.searchsorted(pos_arr, pos)
+        col = np.where((col < n) & (pos_arr[np.minimum(col, n - 1)] == pos), col, -1)
+    else:
+        col = np.full(total, -1, np.int64)
+    valid = col >= 0
+    if m:
+        bad = np.nonzero(~(valid[first] & valid[last_i]))[0]
+        if bad.size:
             # the reference asserts here (columniterator.cpp:36-39) and aborts the process
-            raise RuntimeError("read {!r}: first/last variant position is not among the given positions".format(r.name))
-        for p, a, q in zip(r._pos, r._allele, r._quality):
-            c = col_of.get(p)
-            if c is None:
-                continue  # interior variants outside `positions` are skipped (columniterator.cpp:101-104)
-            if a not in (0, 1, 2):
-                raise RuntimeError("read {!r}: allele {} is not 0 (REF), 1 (ALT) or 2 (BLANK)".format(r.name, a))
-            if q < 0:
-                raise OverflowError("negative quality")
-            ent_col.append(c)
-            ent_allele.append(a)
-            ent_phred.append(q)
-        read_off.append(len(ent_col))
+            raise RuntimeError("read {!r}: first/last variant position is not among the given positions".format(reads[int(bad[0])].name))
+    # interior variants outside `positions` are skipped (columniterator.cpp:101-104)
+    wrong = np.nonzero(valid & ((allele < 0) | (allele > 2)))[0]
+    if wrong.size:
+        r_idx = int(np.searchsorted(off, wrong[0], side="right") - 1)
+        raise RuntimeError("read {!r}: allele {} is not 0 (REF), 1 (ALT) or 2 (BLANK)".format(reads[r_idx].name, int(allele[wrong[0]])))
+    if bool((valid & (quality < 0)).any()):
+        raise OverflowError("negative quality")
+    kept = np.add.reduceat(valid.astype(np.int64), off[:-1]) if m else np.zeros(0, np.int64)
+    read_off = np.zeros(m + 1, np.uint64)
+    np.cumsum(kept, out=read_off[1:])
+    ent_col, ent_allele, ent_phred = col[valid], allele[valid], quality[valid]
+    # -- pedigree --------------------------------------------------------------------------------------
     n_ind = len(pedigree)
     if n_ind == 0:
         raise RuntimeError("pedigree without individuals")
@@ -578,21 +597,20 @@ def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, di
         # its own tests pass lists that are one short (tests/test_pedigreephasing.py:247,266); reading
         # past the end is undefined there, here the last given cost is repeated.
         rc = rc + [rc[-1] if rc else 0] * (n - len(rc))
+    code = {(0, 0): 0, (0, 1): 1, (1, 1): 2}  # canonical index of diploid biallelic genotypes (genotype.cpp:82-93)
     gt = np.full((n_ind, n), GT_OTHER, np.uint8)
     gl = np.zeros((n_ind, n, 3), np.float64) if distrust_genotypes else None
     for i in range(n_ind):
-        for k in range(n):
-            g = pedigree._genotypes[i][k]
-            if g.is_diploid_and_biallelic():
-                gt[i, k] = g.get_index()
-            if distrust_genotypes:
+        gt[i, :] = np.fromiter((code.get(g._alleles, GT_OTHER) for g in pedigree._genotypes[i][:n]), np.uint8, count=n)
+        if distrust_genotypes:
+            for k in range(n):
                 lk = pedigree._gls[i][k]
                 if lk is None:
                     # assert(gls != nullptr) in the reference (pedigreecolumncostcomputer.cpp:36)
                     raise RuntimeError("distrust_genotypes requires genotype likelihoods for every variant")
                 if lk.get_ploidy() != 2:
                     raise RuntimeError("genotype likelihoods must be diploid")
-                gl[i, k, :] = lk.as_vector()[:3]
+                gl[i, k, :] = lk._gl[:3]
     trios = [x for t in pedigree._triples for x in t]
     return FlatProblem(
         positions=np.array(pos_list, np.uint32),
