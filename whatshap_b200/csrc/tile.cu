@@ -25,7 +25,7 @@ constexpr uint32_t TILE_ENTRIES = 1u << TILE_SMAX;
 constexpr uint32_t TC_CHUNK = 16;  // column descriptors staged in shared memory at a time
 
 struct TileSmem {
-    uint32_t buf[2][TILE_ENTRIES];
+    uint32_t buf[3][TILE_ENTRIES];  // [0],[1]: ping-pong projection; [2]: staging / prefetch of the next tile's input
     int32_t TL[2][TILE_TL_SIZE];
     int32_t TH[2][TILE_TH_SIZE];
     int32_t T9[2][512];   // fast path: K2 + E(global bits) + weights of output bits 5..13
@@ -210,72 +210,71 @@ __device__ __forceinline__ uint32_t mask_without_low_bits(uint32_t mask, uint32_
     return mask;
 }
 
+// Staging index of element (producer tile tA, offset ll) of a tile-major hand-off: a bijection of
+// [0, 2^s_in) chosen so that 32 consecutive (tA, ll) in either order hit 32 different banks.
+__device__ __forceinline__ uint32_t stage_index(uint32_t gA, uint32_t jb, uint32_t tA, uint32_t ll) {
+    if (gA == 0) return ll;
+    if (jb >= 5) return (tA << jb) + (ll ^ ((tA << (gA <= 5 ? 5 - gA : 0)) & 31u));
+    const uint32_t idx = (tA << jb) + ll;
+    return idx ^ ((idx >> 5) & ((1u << jb) - 1u));
+}
+
+__device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Asynchronous gather of one tile's input (tile-major hand-off) into the staging buffer: one contiguous
+// 2^j chunk from each of the 2^gA producer tiles.  `pp` points to the panel in global memory.
+__device__ __forceinline__ void stage_tile_async(uint32_t *stage, const Panel *pp, uint32_t ptile, const uint32_t *state) {
+    const uint32_t gA = __ldg(&pp->in_gA), jb = __ldg(&pp->in_j), sA = __ldg(&pp->in_sA);
+    const uint32_t nin = 1u << __ldg(&pp->s_in);
+    const uint32_t told = ptile & low_mask(__ldg(&pp->in_gold));
+    const uint32_t *src = state + __ldg(&pp->in_off) + ((uint64_t)told << jb);
+    const uint32_t jmask = (1u << jb) - 1u;
+    for (uint32_t e = threadIdx.x; e < nin; e += NT) {
+        const uint32_t tA = e >> jb, ll = e & jmask;
+        cp_async4(&stage[stage_index(gA, jb, tA, ll)], src + ((uint64_t)tA << sA) + ll);
+    }
+    cp_async_commit();
+}
+
 __global__ void __launch_bounds__(NT, 1)
-tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const TileCol *__restrict__ tcols,
+tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t total_tiles, const TileCol *__restrict__ tcols,
                   const ColMeta *__restrict__ cols, uint32_t *__restrict__ state, uint32_t *__restrict__ arena,
                   unsigned long long *__restrict__ chain_keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
     const uint32_t tid = threadIdx.x;
 
-    // which panel does this CTA belong to?  panels[] is sorted by tile_begin within the launch
-    if (tid == 0) {
-        uint32_t lo = 0, hi = n_panels;
-        while (hi - lo > 1) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (panels[mid].tile_begin <= blockIdx.x) lo = mid;
-            else hi = mid;
-        }
-        S.panel_index = lo;
-    }
-    __syncthreads();
-    if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[S.panel_index])[tid];
+    // Persistent CTAs: each walks the launch's tiles with stride gridDim.x and, while it sweeps one
+    // tile's panel, the input of its next tile is already streaming into the third buffer (cp.async).
+    uint32_t pi = 0;            // panel of the current work item; panels[] is sorted by tile_begin
+    bool staged = false;        // the staging buffer holds (or is receiving) the current tile's input
+    for (uint32_t work = blockIdx.x; work < total_tiles; work += gridDim.x) {
+    while (pi + 1 < n_panels && __ldg(&panels[pi + 1].tile_begin) <= work) ++pi;
+    __syncthreads();  // previous work item completely done (its stores read the buffers, S.P is reused)
+    if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[pi])[tid];
     __syncthreads();
     const Panel &P = S.P;
-    const uint32_t tile = blockIdx.x - P.tile_begin;
+    const uint32_t tile = work - P.tile_begin;
     uint32_t cur = 0;
 
-    // ---- load the tile's slice of the incoming projection column
+    // ---- the tile's slice of the incoming projection column
     if (P.fresh) {
         if (tid == 0) S.buf[0][0] = 0;
     } else if (P.in_layout == 1) {
-        // tile-major hand-off: one contiguous 2^j chunk from each of the 2^gA producer tiles, transposed
-        // through the second buffer (XOR-swizzled so that both passes are bank-conflict free) into
-        // the canonical local order  index = (chunk offset << gA) | producer tile.
+        // tile-major hand-off: gathered into the staging buffer (XOR-swizzled so that both passes are
+        // bank-conflict free), then transposed into the canonical local order
+        //   index = (chunk offset << gA) | producer tile.
+        if (!staged) stage_tile_async(S.buf[2], &panels[pi], tile, state);
+        cp_async_wait_all();
+        __syncthreads();
         const uint32_t gA = P.in_gA, jb = P.in_j, nin = 1u << P.s_in;
-        const uint32_t told = tile & low_mask(P.in_gold);
-        const uint32_t *src = state + P.in_off + ((uint64_t)told << jb);
-        const uint32_t jmask = (1u << jb) - 1u, amask = (1u << gA) - 1u;
-        const uint32_t sh = gA <= 5 ? 5 - gA : 0;
-        // staging index of element (producer tile tA, offset ll): a bijection of [0, 2^s_in) chosen so
-        // that 32 consecutive (tA, ll) in either order hit 32 different banks
-        auto sidx = [=](uint32_t tA, uint32_t ll) -> uint32_t {
-            if (jb >= 5) return (tA << jb) + (ll ^ ((tA << sh) & 31u));
-            const uint32_t idx = (tA << jb) + ll;
-            return idx ^ ((idx >> 5) & jmask);
-        };
-        uint32_t *stage = gA ? S.buf[1] : S.buf[0];
-        for (uint32_t e0 = tid; e0 < nin; e0 += 8 * NT) {
-            uint32_t v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t e = e0 + u * NT;
-                if (e < nin) v[u] = src[((uint64_t)(e >> jb) << P.in_sA) + (e & jmask)];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t e = e0 + u * NT;
-                const uint32_t tA = e >> jb;
-                if (e < nin) stage[gA ? sidx(tA, e & jmask) : e] = v[u];
-            }
-        }
-        if (gA) {
-            __syncthreads();
-            for (uint32_t i = tid; i < nin; i += NT) {
-                const uint32_t tA = i & amask, ll = i >> gA;
-                S.buf[0][i] = stage[sidx(tA, ll)];
-            }
-        }
+        const uint32_t amask = (1u << gA) - 1u;
+        for (uint32_t i = tid; i < nin; i += NT) S.buf[0][i] = S.buf[2][stage_index(gA, jb, i & amask, i >> gA)];
     } else {
         const uint32_t nin = 1u << P.s_in;
         const uint32_t gpart = pdep32(tile, P.gmask_in);
@@ -283,6 +282,20 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
         const uint32_t himask = mask_without_low_bits(P.lmask_in, 10);
         const uint32_t *src = state + P.in_off;
         for (uint32_t l = tid, it = 0; l < nin; l += NT, ++it) S.buf[0][l] = src[lo | pdep32(it, himask) | gpart];
+    }
+    __syncthreads();  // staging buffer free again
+    // ---- prefetch the input of this CTA's next tile
+    staged = false;
+    {
+        const uint32_t nwork = work + gridDim.x;
+        if (nwork < total_tiles) {
+            uint32_t pn = pi;
+            while (pn + 1 < n_panels && __ldg(&panels[pn + 1].tile_begin) <= nwork) ++pn;
+            if (__ldg(&panels[pn].in_layout) == 1 && !__ldg(&panels[pn].fresh)) {
+                stage_tile_async(S.buf[2], &panels[pn], nwork - __ldg(&panels[pn].tile_begin), state);
+                staged = true;
+            }
+        }
     }
 
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
@@ -407,6 +420,7 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, const Til
         uint32_t *dst = state + P.out_off;
         for (uint32_t l = tid, it = 0; l < nout; l += NT, ++it) dst[lo | pdep32(it, himask) | gpart] = S.buf[cur][l];
     }
+    }  // work loop
 }
 
 __global__ void tile_backtrace_kernel(const ColMeta *__restrict__ cols, const TileCol *__restrict__ tcols,
@@ -428,6 +442,7 @@ struct TileImpl {
     uint32_t *d_state = nullptr, *d_arena = nullptr, *d_chain_begin = nullptr;
     unsigned long long *d_chain_keys = nullptr;
     uint32_t n_chains = 0;
+    uint32_t n_sm = 148;
 };
 
 }  // namespace
@@ -486,6 +501,12 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     CUDA_TRY(up(I->d_tcols, ts.cols.data(), (size_t)pk.n * sizeof(TileCol)));
     CUDA_TRY(up(I->d_panels, ts.panels.data(), ts.panels.size() * sizeof(Panel)));
     CUDA_TRY(up(I->d_chain_begin, pk.chain_begin.data(), pk.chain_begin.size() * 4));
+    {
+        int dev = 0, sms = 148;
+        CUDA_TRY(cudaGetDevice(&dev));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        I->n_sm = (uint32_t)sms;
+    }
     CUDA_TRY(cudaFuncSetAttribute(tile_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     return WHMEC_OK;
 }
@@ -497,7 +518,8 @@ int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
     launches = 0;
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r) {
         const uint32_t p0 = ts.round_begin[r], p1 = ts.round_begin[r + 1];
-        tile_panel_kernel<<<ts.round_tiles[r], NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, I->d_tcols, I->d_cols,
+        const uint32_t grid = std::min<uint32_t>(ts.round_tiles[r], I->n_sm);
+        tile_panel_kernel<<<grid, NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, ts.round_tiles[r], I->d_tcols, I->d_cols,
                                                                                 I->d_state, I->d_arena, I->d_chain_keys);
         ++launches;
     }
