@@ -28,8 +28,8 @@ struct TileSmem {
     uint32_t buf[3][TILE_ENTRIES];  // [0],[1]: ping-pong projection; [2]: staging / prefetch of the next tile's input
     int32_t TL[2][TILE_TL_SIZE];
     int32_t TH[2][TILE_TH_SIZE];
-    int32_t T9[2][512];   // fast path: K2 + E(global bits) + weights of output bits 5..13
-    int32_t T5[2][32];    // fast path: weights of output bits 0..4 (the lane)
+    int32_t TW[2][32];    // fast path, per warp: K2 + E(global bits of the tile) + weights of the warp's output bits
+    int32_t T5[2][32];    // fast path, per lane: weights of output bits 0..4
     unsigned long long keys[NT];
     TileCol tcs[TC_CHUNK];
     Panel P;
@@ -46,7 +46,8 @@ struct TileSmem {
 // TileCol::pad1 = LG.  Output index o = cell index without the dropped bit 0: o bit q <-> local bit q+1.
 __device__ __forceinline__ uint32_t fast_kind(const TileCol &tc) { return tc.pad0; }
 
-// Tables of one column (see tile_device.h): threads 0..384 each produce one entry.
+// Tables of one column: the x-indexed TL/TH pair of tile_device.h (threads 0..384, one entry each) or, for
+// fast columns, the two 32-entry tables of column_fast.
 __device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uint32_t tile, uint32_t which, uint32_t tid) {
     if (fast_kind(tc)) {
         const uint32_t lg = tc.pad1;
@@ -57,7 +58,7 @@ __device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uin
 #pragma unroll
             for (uint32_t q = 0; q < 5; ++q)
                 if ((tid >> q) & 1u) s += tc.w_local[6 + lg + q];
-            S.T9[which][tid] = s;
+            S.TW[which][tid] = s;
         } else if (tid < 64) {  // per-lane part: output bits 0..4
             const uint32_t l = tid - 32;
             int32_t s = 0;
@@ -341,8 +342,8 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
             uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
             if (fast_kind(tc)) {
 #define WHMEC_FAST(LGV, SH)                                                                                      \
-    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); \
-    else column_fast<LGV, true, SH>(tc, S.T9[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
+    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); \
+    else column_fast<LGV, true, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
                 if (fast_kind(tc) == 2) {
                     switch (tc.pad1) {
                         case 0: WHMEC_FAST(0, true) break;

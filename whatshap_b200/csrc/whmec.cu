@@ -10,6 +10,7 @@
 #include <malloc.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -932,13 +933,24 @@ int whmec_plan_stats(const whmec_plan *plan, whmec_stats *st) {
 void whmec_plan_destroy(whmec_plan *plan) { delete plan; }
 
 int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st, char *err, size_t errlen) {
+    using clk = std::chrono::steady_clock;
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = clk::now();
     whmec_plan *pl = nullptr;
     int rc = whmec_plan_create(p, device, &pl, err, errlen);
     if (rc != WHMEC_OK) return rc;
+    const auto t1 = clk::now();
     rc = whmec_plan_sweep(pl, err, errlen);
+    const auto t2 = clk::now();
     if (rc == WHMEC_OK) rc = whmec_plan_finish(pl, s, err, errlen);
-    if (st) *st = pl->stats;
+    const auto t3 = clk::now();
+    const whmec_stats stats = pl->stats;
+    if (st) *st = stats;
     whmec_plan_destroy(pl);
+    if (timing)
+        std::fprintf(stderr, "[whmec] solve: create %.2f ms (h2d %.2f), sweep %.2f ms (device %.2f), finish %.2f ms (device %.2f), destroy %.2f ms\n",
+                     ms(t0, t1), (double)stats.h2d_ms, ms(t1, t2), (double)stats.sweep_ms, ms(t2, t3), (double)stats.d2h_ms, ms(t3, clk::now()));
     return rc;
 }
 
