@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WHMEC_ABI_VERSION 1
+#define WHMEC_ABI_VERSION 2
 
 /* return codes */
 #define WHMEC_OK 0
@@ -123,6 +123,35 @@ void whmec_plan_destroy(whmec_plan *plan);
 /* One-shot: create + sweep + finish + destroy, host buffers in, host buffers out. */
 int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st_or_null,
                 char *err, size_t errlen);
+
+/* ---- A pedigree table (T = 4^trios > 1) shared by several GPUs --------------------------------
+ * The reference sweeps a family's table on one thread (src/pedigreedptable.cpp:84-174).  Columns that no
+ * read spans cut it into chains that exchange only the T projection values of the cut
+ * (pedigreedptable.cpp:272-297), and a chain is min-plus linear in them.  A SEGMENT is a run of whole
+ * chains given as a problem of its own (its columns, its reads, recombcost of exactly these columns);
+ * one process per GPU holds one segment, and the caller (whatshap_b200/multigpu.py) moves T x T u32
+ * matrices and T-vectors between the processes:
+ *   1. whmec_segment_create   pack + upload; `continues` != 0 unless the segment starts the table
+ *   2. whmec_segment_transfer matrix[u*T + i] = value at transmission value i behind the segment when the
+ *                             vector handed to it is 0 at u and +inf (0xFFFFFFFF) elsewhere; the first
+ *                             segment ignores its input (pedigreedptable.cpp:275-278): all rows equal
+ *   3. (caller) all-gather the matrices, fold them left to right -> every segment's true input vector
+ *   4. whmec_segment_sweep    sweep with the true input (NULL for the first segment), writing the same
+ *                             back-pointers the single sweep would; out_vec = the T values behind it
+ *   5. whmec_segment_exits    exits[u] = transmission value the backtrace hands to the preceding segment
+ *                             when it enters this one with u; is_last: entered at the optimum of the
+ *                             table's last column instead (all T answers equal)
+ *   6. (caller) all-gather, follow the realised entries right to left
+ *   7. whmec_segment_finish   backtrace from `entry` (< 0: this segment ends the table) + outputs for the
+ *                             segment's columns and reads; s->cost is the table's optimum iff entry < 0
+ * Results are bit-identical to whmec_solve on the whole table.  WHMEC_ERR_UNSUPPORTED: single-individual
+ * problems (their chains are independent, shard them with whmec_solve), costs beyond 2^28. */
+int whmec_segment_create(const whmec_problem *p, int device, int continues, whmec_plan **out, char *err, size_t errlen);
+int whmec_segment_transfer(whmec_plan *plan, uint32_t *matrix /* [T*T] */, char *err, size_t errlen);
+int whmec_segment_sweep(whmec_plan *plan, const uint32_t *in_vec /* [T] or NULL */, uint32_t *out_vec /* [T] */,
+                        char *err, size_t errlen);
+int whmec_segment_exits(whmec_plan *plan, int is_last, uint32_t *exits /* [T] */, char *err, size_t errlen);
+int whmec_segment_finish(whmec_plan *plan, int entry, whmec_solution *s, char *err, size_t errlen);
 
 /* Sort key of ReadSet::sort() ties: std::hash<std::string>(name) ^ std::hash<int>(source_id)
  * as computed by libstdc++ (64-bit murmur, seed 0xc70f6907); src/readset.h:68-72. */

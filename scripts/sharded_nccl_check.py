@@ -25,4 +25,18 @@ if rank == 0:
     whole, _ = _lib.solve(prob, device=local)
     print("sharded == single-GPU:", sol.same_as(whole), "cost", sol.cost, "world", dist.get_world_size(), "%.1f ms" % (dt * 1e3))
     assert sol.same_as(whole)
+# pedigree (T = 4): the ranks hold segments of ONE table and exchange transfer matrices / exit tables
+ped = synth.config("cfg5") if rank == 0 else None
+multigpu.solve_sharded(synth.config("cfg5", 2000) if rank == 0 else None)  # warm-up
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+sol = multigpu.solve_sharded(ped)
+dt = time.perf_counter() - t0
+if rank == 0:
+    t1 = time.perf_counter()
+    whole, _ = _lib.solve(ped, device=local)
+    one = time.perf_counter() - t1
+    print("pedigree segments == single-GPU:", sol.same_as(whole), "cost", sol.cost, "world", dist.get_world_size(),
+          "%.1f ms (single GPU, host in/out: %.1f ms)" % (dt * 1e3, one * 1e3))
+    assert sol.same_as(whole)
 dist.destroy_process_group()

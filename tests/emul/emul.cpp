@@ -14,30 +14,27 @@
 
 using namespace whmec;
 
-extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t chunk, char *err, size_t errlen) {
-    Packed pk;
-    std::string msg;
-    int rc = pack_problem(p, pk, msg);
-    auto fail = [&](int code) {
-        if (err && errlen) {
-            std::strncpy(err, msg.c_str(), errlen - 1);
-            err[errlen - 1] = 0;
-        }
-        return code;
-    };
-    if (rc != WHMEC_OK) return fail(rc);
-    const uint32_t n = pk.n, T = pk.T, tb = pk.tb;
-    if (n == 0) {
-        s->cost = 0;
-        if (s->partition) std::memset(s->partition, 1, p->n_reads);
-        return WHMEC_OK;
+namespace {
+
+int fail_with(const std::string &msg, char *err, size_t errlen, int code) {
+    if (err && errlen) {
+        std::strncpy(err, msg.c_str(), errlen - 1);
+        err[errlen - 1] = 0;
     }
-    std::vector<uint32_t> arena(pk.bp_words + 1, 0), prev, cur, prevm;
+    return code;
+}
+
+// Columns [k0, k1) swept one after the other, every thread's work done serially.  `prev` holds the
+// projection handed to column k0 (ignored by a column with m.first) and ends as column k1-1's.
+int sweep_columns(const Packed &pk, uint32_t k0, uint32_t k1, uint32_t chunk, std::vector<uint32_t> &prev,
+                  std::vector<uint32_t> &arena, std::string &msg) {
+    const uint32_t T = pk.T, tb = pk.tb;
+    std::vector<uint32_t> cur, prevm;
     std::vector<uint8_t> prevarg;
     bool have_xform = false;
-    for (uint32_t k = 0; k < n; ++k) {
+    for (uint32_t k = k0; k < k1; ++k) {
         const ColMeta &m = pk.cols[k];
-        if (m.d + tb > 32) { msg = "d + tb > 32"; return fail(WHMEC_ERR_UNSUPPORTED); }
+        if (m.d + tb > 32) { msg = "d + tb > 32"; return WHMEC_ERR_UNSUPPORTED; }
         uint64_t nout = (uint64_t)1 << m.f, ncand = (uint64_t)1 << m.d;
         cur.assign(nout * T, UMAX);
         // per-column lookup tables, as a thread block builds them in shared memory
@@ -82,7 +79,7 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
         prev.swap(cur);
         // every third hand-over keeps raw values, the others pre-apply the transition minimum of the next
         // column (as the batched pedigree kernels do in their epilogue)
-        have_xform = (k + 1 < n) && (k % 3 != 2);
+        have_xform = (k + 1 < k1) && (k % 3 != 2);
         if (have_xform) {
             prevm.assign(nout * T, UMAX);
             prevarg.assign(nout * T, 0);
@@ -94,6 +91,25 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
                 }
         }
     }
+    return WHMEC_OK;
+}
+
+}  // namespace
+
+extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t chunk, char *err, size_t errlen) {
+    Packed pk;
+    std::string msg;
+    int rc = pack_problem(p, pk, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+    const uint32_t n = pk.n, T = pk.T, tb = pk.tb;
+    if (n == 0) {
+        s->cost = 0;
+        if (s->partition) std::memset(s->partition, 1, p->n_reads);
+        return WHMEC_OK;
+    }
+    std::vector<uint32_t> arena(pk.bp_words + 1, 0), prev;
+    rc = sweep_columns(pk, 0, n, chunk, prev, arena, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
     std::vector<uint32_t> pidx(n), ptv(n);
     BtView bv{pk.cols.data(), arena.data(), T, tb};
     uint32_t cost, x, tv, ptvv;
@@ -101,6 +117,149 @@ extern "C" int whemul_solve(const whmec_problem *p, whmec_solution *s, uint32_t 
     backtrace_range(bv, n - 1, 0, x, tv, ptvv, pidx.data(), ptv.data());
     s->cost = cost;
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
-    if (rc != WHMEC_OK) return fail(rc);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+    return WHMEC_OK;
+}
+
+// ---- segments of a pedigree table: same entry points and semantics as whmec_segment_* (include/whmec.h),
+// ---- built from the same __host__ __device__ functions the CUDA kernels call
+struct whemul_segment {
+    Packed pk;
+    bool continues = false;
+    std::vector<uint32_t> arena, last_vals, exits;
+    bool swept = false;
+};
+
+extern "C" int whemul_segment_create(const whmec_problem *p, int continues, whemul_segment **out, char *err, size_t errlen) {
+    std::string msg;
+    whemul_segment *sg = new whemul_segment();
+    *out = nullptr;
+    int rc = pack_problem(p, sg->pk, msg);
+    if (rc == WHMEC_OK && (sg->pk.T == 1 || sg->pk.n == 0 || !sg->pk.safe31)) {
+        msg = "unsupported segment";
+        rc = WHMEC_ERR_UNSUPPORTED;
+    }
+    if (rc != WHMEC_OK) {
+        delete sg;
+        return fail_with(msg, err, errlen, rc);
+    }
+    sg->continues = continues != 0;
+    if (sg->continues) sg->pk.cols[0].first = 0;
+    sg->arena.assign(sg->pk.bp_words + 1, 0);
+    *out = sg;
+    return WHMEC_OK;
+}
+
+extern "C" void whemul_segment_destroy(whemul_segment *sg) { delete sg; }
+
+extern "C" int whemul_segment_transfer(whemul_segment *sg, uint32_t *matrix, char *err, size_t errlen) {
+    const Packed &pk = sg->pk;
+    const uint32_t T = pk.T, C = (uint32_t)pk.chain_begin.size() - 1;
+    std::string msg;
+    // per-chain matrices from unit inputs (what pass 1 of the batched sweep leaves in its planes) ...
+    std::vector<uint32_t> M((size_t)C * T * T);
+    for (uint32_t c = 0; c < C; ++c)
+        for (uint32_t u = 0; u < T; ++u) {
+            std::vector<uint32_t> prev(T, UMAX);
+            prev[u] = 0;
+            int rc = sweep_columns(pk, pk.chain_begin[c], pk.chain_begin[c + 1], 0, prev, sg->arena, msg);
+            if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+            std::memcpy(&M[((size_t)c * T + u) * T], prev.data(), (size_t)T * 4);
+        }
+    // ... folded like ped_prefix_kernel does with `matrix` given
+    for (uint32_t u0 = 0; u0 < T; ++u0) {
+        uint32_t in[MAX_T];
+        uint32_t c_first = 0;
+        if (sg->continues) {
+            for (uint32_t i = 0; i < T; ++i) in[i] = i == u0 ? 0u : UMAX;
+        } else {
+            for (uint32_t i = 0; i < T; ++i) in[i] = M[(size_t)u0 * T + i];  // every plane of chain 0 holds its true output
+            c_first = 1;
+        }
+        fold_chains(T, c_first, C, in, [&](uint32_t c, uint32_t u) { return &M[((size_t)c * T + u) * T]; },
+                    [](uint32_t, const uint32_t *) {});
+        std::memcpy(matrix + (size_t)u0 * T, in, (size_t)T * 4);
+    }
+    return WHMEC_OK;
+}
+
+extern "C" int whemul_segment_sweep(whemul_segment *sg, const uint32_t *in_vec, uint32_t *out_vec, char *err, size_t errlen) {
+    const Packed &pk = sg->pk;
+    std::string msg;
+    if (sg->continues != (in_vec != nullptr)) return fail_with("input vector / continues mismatch", err, errlen, WHMEC_ERR_INPUT);
+    std::vector<uint32_t> prev;
+    if (in_vec) prev.assign(in_vec, in_vec + pk.T);
+    int rc = sweep_columns(pk, 0, pk.n, 0, prev, sg->arena, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+    sg->last_vals = prev;
+    std::memcpy(out_vec, prev.data(), (size_t)pk.T * 4);
+    sg->swept = true;
+    return WHMEC_OK;
+}
+
+namespace {
+// bt_chain_start of whmec.cu
+void chain_start(const whemul_segment *sg, const BtView &bv, uint32_t c, uint32_t u, int entry, uint32_t *x, uint32_t *tv,
+                 uint32_t *ptv, uint32_t *cost) {
+    const Packed &pk = sg->pk;
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1, k_last = pk.chain_begin[c + 1] - 1;
+    if (c + 1 == C && entry < 0) {
+        pick_optimum(pk.cols[k_last], sg->last_vals.data(), sg->arena.data(), pk.T, pk.tb, cost, x, tv, ptv);
+    } else {
+        *tv = u;
+        chain_entry(bv, k_last, u, x, ptv);
+    }
+}
+
+void chain_exits(whemul_segment *sg, int entry) {
+    const Packed &pk = sg->pk;
+    const uint32_t T = pk.T, C = (uint32_t)pk.chain_begin.size() - 1;
+    BtView bv{pk.cols.data(), sg->arena.data(), T, pk.tb};
+    sg->exits.assign((size_t)C * T, 0);
+    for (uint32_t c = 0; c < C; ++c)
+        for (uint32_t u = 0; u < T; ++u) {
+            uint32_t x, tv, ptv, cost;
+            chain_start(sg, bv, c, u, entry, &x, &tv, &ptv, &cost);
+            sg->exits[(size_t)c * T + u] = backtrace_range(bv, pk.chain_begin[c + 1] - 1, pk.chain_begin[c], x, tv, ptv, nullptr, nullptr);
+        }
+}
+}  // namespace
+
+extern "C" int whemul_segment_exits(whemul_segment *sg, int is_last, uint32_t *exits, char *err, size_t errlen) {
+    const Packed &pk = sg->pk;
+    const uint32_t T = pk.T, C = (uint32_t)pk.chain_begin.size() - 1;
+    if (!sg->swept) return fail_with("exits before sweep", err, errlen, WHMEC_ERR_INPUT);
+    chain_exits(sg, is_last ? -1 : 0);
+    for (uint32_t t = 0; t < T; ++t) {
+        uint32_t e = t;
+        for (uint32_t c = C; c-- > 0;) e = sg->exits[(size_t)c * T + e];
+        exits[t] = e;
+    }
+    return WHMEC_OK;
+}
+
+extern "C" int whemul_segment_finish(whemul_segment *sg, int entry, whmec_solution *s, char *err, size_t errlen) {
+    const Packed &pk = sg->pk;
+    const uint32_t T = pk.T, C = (uint32_t)pk.chain_begin.size() - 1, n = pk.n;
+    std::string msg;
+    if (!sg->swept) return fail_with("finish before sweep", err, errlen, WHMEC_ERR_INPUT);
+    chain_exits(sg, entry);
+    std::vector<uint32_t> entries(C), pidx(n), ptv(n);
+    uint32_t e = entry < 0 ? 0u : (uint32_t)entry;
+    for (uint32_t c = C; c-- > 0;) {
+        entries[c] = e;
+        e = sg->exits[(size_t)c * T + e];
+    }
+    BtView bv{pk.cols.data(), sg->arena.data(), T, pk.tb};
+    uint32_t total = 0;
+    for (uint32_t c = 0; c < C; ++c) {
+        uint32_t x, tv, ptvv, cost = 0;
+        chain_start(sg, bv, c, entries[c], entry, &x, &tv, &ptvv, &cost);
+        backtrace_range(bv, pk.chain_begin[c + 1] - 1, pk.chain_begin[c], x, tv, ptvv, pidx.data(), ptv.data());
+        if (c + 1 == C) total = cost;
+    }
+    s->cost = total;
+    int rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
     return WHMEC_OK;
 }

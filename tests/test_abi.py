@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.lib()
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.whmec_abi_version() == 1
+    assert lib.whmec_abi_version() == 2
     assert b"sm_100a" in lib.whmec_build_info()
 
 

@@ -93,3 +93,81 @@ def test_tile_planner_on_benchmark_shapes(emul):
             assert traffic * 10 < alg
         else:
             assert traffic == 0 and rounds == 1
+
+
+# ---- segments of a pedigree table (multi-GPU scheme for T > 1) ----
+def _segmented(prob, n_segments):
+    from emul_segment import EmulSegment
+    from whatshap_b200 import multigpu
+
+    return multigpu.solve_pedigree_segments(prob, n_segments, EmulSegment)
+
+
+def test_pedigree_segments_on_golden_vectors():
+    """Every golden pedigree case that has at least two chains, cut into 2 and 3 segments: transfer
+    matrices, folded input vectors, pass-2 back-pointers, exit tables and the stitched backtrace must
+    reproduce the reference's whole-table answer (cost, path, transmission vector, super-reads)."""
+    from whatshap_b200 import multigpu
+
+    n = 0
+    for group in golden_io.GROUPS:
+        for label, prob, want, error in golden_io.load(group):
+            if prob.n_trios == 0 or want is None or len(multigpu.independent_blocks(prob)) < 2:
+                continue
+            for n_segments in (2, 3):
+                got = _segmented(prob, n_segments)
+                assert got.same_as(want), (label, n_segments, got.diff(want))
+            n += 1
+    assert n >= 10
+
+
+@pytest.mark.parametrize("pedigree", ["trio", "trio_child_first", "quartet", "three_generations"])
+def test_pedigree_segments_random(pedigree):
+    """Irregular pedigrees (T = 4 and 16, trusted and distrusted genotypes, Mendelian conflicts) against
+    the checker; a conflict must surface as the same error."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import checker
+    from whatshap_b200 import multigpu
+
+    ck = checker.best()
+    rng = np.random.default_rng(abs(hash(pedigree)) % 1000 + 3)
+    done = 0
+    for it in range(60):
+        prob = synth.random_problem(rng, int(rng.integers(4, 24)), int(rng.integers(2, 5)), pedigree=pedigree,
+                                    distrust=it % 3 == 0, conflict_free=it % 5 != 0, mean_len=float(rng.choice([1.5, 3.0])))
+        if len(multigpu.independent_blocks(prob)) < 2:
+            continue
+        try:
+            want, werr = ck.solve(prob), ""
+        except RuntimeError as e:
+            want, werr = None, str(e)
+        for n_segments in (2, 4):
+            try:
+                got, gerr = _segmented(prob, n_segments), ""
+            except RuntimeError as e:
+                got, gerr = None, str(e)
+            assert gerr == werr, (it, n_segments, gerr, werr)
+            if want is not None:
+                assert got.same_as(want), (it, n_segments, got.diff(want))
+        done += 1
+    assert done >= 25
+
+
+def test_segment_helpers():
+    from whatshap_b200 import multigpu
+
+    inf = multigpu.UMAX
+    m = np.array([[1, inf], [5, 2]], np.uint32)
+    assert multigpu.minplus(np.array([3, inf], np.uint32), m).tolist() == [4, inf]
+    assert multigpu.minplus(np.array([3, 0], np.uint32), m).tolist() == [4, 2]
+    first = np.array([[7, 9], [7, 9]], np.uint32)  # the first segment ignores its input: equal rows
+    ins = multigpu.segment_inputs([None, first, None, m])
+    assert ins[0] is None and ins[1] is None and ins[2] is None and ins[3].tolist() == [7, 9]
+    # right to left: the last segment starts at the optimum (-1) and hands exits[0] on
+    assert multigpu.segment_entries([np.array([1, 0]), None, np.array([0, 1]), np.array([1, 1])]) == [1, None, 1, -1]
+    assert multigpu.contiguous_shares(np.array([1.0, 1, 1, 1]), 2) == [(0, 2), (2, 4)]
+    assert sorted(multigpu.contiguous_shares(np.array([5.0]), 3)) == [(0, 0), (0, 1), (1, 1)]  # one block: one rank has it
+    shares = multigpu.contiguous_shares(np.array([8.0, 1, 1, 1, 1, 4]), 3)
+    assert shares[0][0] == 0 and shares[-1][1] == 6 and all(a[1] == b[0] for a, b in zip(shares, shares[1:]))

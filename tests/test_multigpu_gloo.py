@@ -30,8 +30,29 @@ def _worker(rank, world, port, kind, out_queue):
     ck = checker.best()
     prob = None
     if rank == 0:
-        prob = synth.sliding_window(120, 6, block_len=20, seed=5, gap=0.1) if kind == "single" else synth.trio(40, 2, block_len=20, seed=6)
-    sol = multigpu.solve_sharded(prob, solver=ck.solve)
+        if kind == "single":
+            prob = synth.sliding_window(120, 6, block_len=20, seed=5, gap=0.1)
+        elif kind == "trio":
+            prob = synth.trio(40, 2, block_len=10, seed=6)
+        elif kind == "trio_two_blocks":  # fewer blocks than ranks: one rank holds no segment
+            prob = synth.trio(24, 2, block_len=12, seed=8)
+        else:  # "conflict": the error of one rank's segment is raised on every rank
+            prob = synth.trio(40, 2, block_len=10, seed=6)
+            prob.gt = prob.gt.copy()
+            prob.gt[:, 33] = [0, 0, 2]
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from emul_segment import EmulSegment
+
+    # pedigrees: every rank holds a segment of the table (host emulation of the per-rank CUDA calls)
+    try:
+        sol = multigpu.solve_sharded(prob, solver=ck.solve, segment_factory=EmulSegment)
+    except RuntimeError as e:
+        assert kind == "conflict" and "Mendelian conflict" in str(e), (kind, str(e))
+        if rank == 0:
+            out_queue.put((True, "", 1))
+        dist.destroy_process_group()
+        return
+    assert kind != "conflict"
     if rank == 0:
         want = ck.solve(prob)
         out_queue.put((sol.same_as(want), sol.diff(want), int(sol.cost)))
@@ -40,12 +61,12 @@ def _worker(rank, world, port, kind, out_queue):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind", ["single", "trio"])
-def test_two_rank_block_sharding_matches_unsharded(kind):
+@pytest.mark.parametrize("kind,world", [("single", 2), ("trio", 2), ("trio", 3), ("trio_two_blocks", 3), ("conflict", 2)])
+def test_block_sharding_matches_unsharded(kind, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, kind, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, kind, q)) for r in range(world)]
     for p in procs:
         p.start()
     ok, diff, cost = q.get(timeout=120)

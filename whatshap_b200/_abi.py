@@ -246,6 +246,10 @@ class MendelianConflict(RuntimeError):
     """RuntimeError('Error: Mendelian conflict') — same text as pedigreedptable.cpp:302."""
 
 
+class Unsupported(RuntimeError):
+    """WHMEC_ERR_UNSUPPORTED: the problem is outside what this build handles (include/whmec.h)."""
+
+
 def raise_for(rc: int, msg: str):
     """Map a C-ABI return code to the exception the reference would raise (cpp.pxd `except +`)."""
     if rc == WHMEC_OK:
@@ -257,5 +261,5 @@ def raise_for(rc: int, msg: str):
     if rc == WHMEC_ERR_CUDA:
         raise RuntimeError(f"CUDA failure: {msg}")
     if rc == WHMEC_ERR_UNSUPPORTED:
-        raise RuntimeError(f"unsupported problem: {msg}")
+        raise Unsupported(f"unsupported problem: {msg}")
     raise RuntimeError(f"whmec error {rc}: {msg}")

@@ -27,6 +27,11 @@ EXPORTS = (
     "whmec_plan_stats",
     "whmec_plan_destroy",
     "whmec_solve",
+    "whmec_segment_create",
+    "whmec_segment_transfer",
+    "whmec_segment_sweep",
+    "whmec_segment_exits",
+    "whmec_segment_finish",
     "whmec_read_sort_key",
 )
 
@@ -59,7 +64,15 @@ def lib() -> C.CDLL:
     L.whmec_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
     L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
     L.whmec_read_sort_key.restype = C.c_uint64
-    for name in ("whmec_plan_create", "whmec_plan_sweep", "whmec_plan_finish", "whmec_plan_stats", "whmec_solve"):
+    u32p = C.POINTER(C.c_uint32)
+    L.whmec_segment_create.argtypes = [C.POINTER(CProblem), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
+    L.whmec_segment_transfer.argtypes = [C.c_void_p, u32p, C.c_char_p, C.c_size_t]
+    L.whmec_segment_sweep.argtypes = [C.c_void_p, u32p, u32p, C.c_char_p, C.c_size_t]
+    L.whmec_segment_exits.argtypes = [C.c_void_p, C.c_int, u32p, C.c_char_p, C.c_size_t]
+    L.whmec_segment_finish.argtypes = [C.c_void_p, C.c_int, C.POINTER(CSolution), C.c_char_p, C.c_size_t]
+    for name in ("whmec_plan_create", "whmec_plan_sweep", "whmec_plan_finish", "whmec_plan_stats", "whmec_solve",
+                 "whmec_segment_create", "whmec_segment_transfer", "whmec_segment_sweep", "whmec_segment_exits",
+                 "whmec_segment_finish"):
         getattr(L, name).restype = C.c_int
     return L
 
@@ -117,6 +130,74 @@ class Plan:
 
     def __exit__(self, *exc):
         self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Segment:
+    """A run of whole chains of a pedigree table on one GPU (`whmec_segment_*`, include/whmec.h):
+    the unit `multigpu.solve_sharded` spreads over the ranks when T > 1."""
+
+    def __init__(self, prob: FlatProblem, continues: bool, device: int = 0):
+        self.prob = prob
+        self.T = 4 ** prob.n_trios
+        self._h = C.c_void_p()
+        cp = prob.as_c()
+        err = C.create_string_buffer(512)
+        rc = lib().whmec_segment_create(C.byref(cp), device, int(bool(continues)), C.byref(self._h), err, len(err))
+        raise_for(rc, err.value.decode())
+
+    @staticmethod
+    def _ptr(a):
+        return a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+    def transfer(self):
+        import numpy as np
+
+        m = np.zeros((self.T, self.T), np.uint32)
+        err = C.create_string_buffer(512)
+        raise_for(lib().whmec_segment_transfer(self._h, self._ptr(m), err, len(err)), err.value.decode())
+        return m
+
+    def sweep(self, in_vec=None):
+        import numpy as np
+
+        out = np.zeros(self.T, np.uint32)
+        vec = None if in_vec is None else np.ascontiguousarray(in_vec, np.uint32)
+        err = C.create_string_buffer(512)
+        rc = lib().whmec_segment_sweep(self._h, None if vec is None else self._ptr(vec), self._ptr(out), err, len(err))
+        raise_for(rc, err.value.decode())
+        return out
+
+    def exits(self, is_last: bool):
+        import numpy as np
+
+        out = np.zeros(self.T, np.uint32)
+        err = C.create_string_buffer(512)
+        raise_for(lib().whmec_segment_exits(self._h, int(bool(is_last)), self._ptr(out), err, len(err)), err.value.decode())
+        return out
+
+    def finish(self, entry: int) -> FlatSolution:
+        sol = FlatSolution(self.prob.n_cols, self.prob.n_reads, self.prob.n_ind)
+        cs = sol.as_c()
+        err = C.create_string_buffer(512)
+        raise_for(lib().whmec_segment_finish(self._h, int(entry), C.byref(cs), err, len(err)), err.value.decode())
+        sol.cost = int(cs.cost)
+        return sol
+
+    def stats(self) -> dict:
+        st = CStats()
+        lib().whmec_plan_stats(self._h, C.byref(st))
+        return st.as_dict()
+
+    def close(self) -> None:
+        if self._h:
+            lib().whmec_plan_destroy(self._h)
+            self._h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -284,11 +284,15 @@ struct BtView {
 };
 
 // Backtrace from column k_last down to k_first (pedigreedptable.cpp:144-160).  (x, tv) is the
-// cell chosen in k_last and prev_tv the argmin transmission value it was reached from.
-WHMEC_HD void backtrace_range(const BtView &v, uint32_t k_last, uint32_t k_first, uint32_t x, uint32_t tv,
-                              uint32_t prev_tv, uint32_t *path_index, uint32_t *path_tv) {
-    path_index[k_last] = x;
-    path_tv[k_last] = tv;
+// cell chosen in k_last and prev_tv the argmin transmission value it was reached from.  Returns the
+// transmission value the walk hands to column k_first - 1; with path_index == nullptr nothing is
+// written (the walk only determines that value).
+WHMEC_HD uint32_t backtrace_range(const BtView &v, uint32_t k_last, uint32_t k_first, uint32_t x, uint32_t tv,
+                                  uint32_t prev_tv, uint32_t *path_index, uint32_t *path_tv) {
+    if (path_index) {
+        path_index[k_last] = x;
+        path_tv[k_last] = tv;
+    }
     for (uint32_t k = k_last; k > k_first; --k) {
         const uint32_t b = x & low_mask(v.cols[k].bw);
         const ColMeta &pm = v.cols[k - 1];
@@ -297,8 +301,41 @@ WHMEC_HD void backtrace_range(const BtView &v, uint32_t k_last, uint32_t k_first
         x = backpointer_to_index(pm, v.tb, b, bp, &j);
         tv = prev_tv;
         prev_tv = j;
-        path_index[k - 1] = x;
-        path_tv[k - 1] = tv;
+        if (path_index) {
+            path_index[k - 1] = x;
+            path_tv[k - 1] = tv;
+        }
+    }
+    return prev_tv;
+}
+
+// A chain (maximal run of columns connected by reads) is entered from its successor through the single
+// projection index 0 of its last column: the successor's first column has bw == 0, so the step of
+// backtrace_range that crosses the boundary reads entry (0, prev_tv).  `u` is that prev_tv.
+WHMEC_HD void chain_entry(const BtView &v, uint32_t k_last, uint32_t u, uint32_t *x, uint32_t *prev_tv) {
+    const ColMeta &m = v.cols[k_last];
+    const uint32_t bp = bp_load(v.arena, m.bp_off, m.bp_width, u);
+    *x = backpointer_to_index(m, v.tb, 0, bp, prev_tv);
+}
+
+// Min-plus fold of per-chain T x T transfer matrices over chains [c_first, n_chains): in <- in (x) M_c.
+// Matrix row u of chain c is the T-vector `row(c, u)`; `each(c, in)` sees the input of chain c.
+template <class Row, class Each>
+WHMEC_HD void fold_chains(uint32_t T, uint32_t c_first, uint32_t n_chains, uint32_t *in, Row row, Each each) {
+    uint32_t outv[MAX_T];
+    for (uint32_t c = c_first; c < n_chains; ++c) {
+        each(c, in);
+        for (uint32_t i = 0; i < T; ++i) outv[i] = UMAX;
+        for (uint32_t u = 0; u < T; ++u) {
+            if (in[u] == UMAX) continue;
+            const uint32_t *M = row(c, u);
+            for (uint32_t i = 0; i < T; ++i) {
+                if (M[i] == UMAX) continue;
+                const uint32_t s = in[u] + M[i];
+                if (s < outv[i]) outv[i] = s;
+            }
+        }
+        for (uint32_t i = 0; i < T; ++i) in[i] = outv[i];
     }
 }
 

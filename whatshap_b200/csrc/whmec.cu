@@ -371,31 +371,40 @@ __global__ void __launch_bounds__(256) col_multi_kernel(const PedStep *__restric
 }
 
 // pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
-// arithmetic, give every chain's true input vector (a few hundred operations: one thread)
+// arithmetic (a few hundred operations per row).
+//   pass-1 planes: chain c, unit vector u -> slot c*T + u;  pass-2 slot of chain c: n_chains*T + c.
+//   in_vec == nullptr: the plan starts the DP table; chain 0's first column ignores its input
+//     (pedigreedptable.cpp:275-278), every pass-1 plane of it holds the same, true, output.
+//   in_vec != nullptr: the plan is a segment continuing a table and in_vec the T values handed over
+//     by the columns before it (whmec_segment_sweep).
+//   matrix == nullptr (one thread): store every chain's true input vector where its first column reads it.
+//   matrix != nullptr (T threads): thread u folds the unit vector e_u through all chains -> row u of the
+//     segment's own transfer matrix (whmec_segment_transfer); nothing else is written.
 __global__ void ped_prefix_kernel(uint32_t *__restrict__ vals, uint64_t max_ent, uint32_t T, uint32_t n_chains,
-                                  const uint32_t *__restrict__ chain_len) {
-    if (blockIdx.x || threadIdx.x) return;
-    // pass-1 planes: chain c, unit vector u -> slot c*T + u;  pass-2 slot of chain c: n_chains*T + c.
-    // Chain 0 starts the table: its first column ignores the input (pedigreedptable.cpp:275-278), every
-    // plane of it holds the same, true, output.
-    uint32_t in[MAX_T], outv[MAX_T];
-    for (uint32_t i = 0; i < T; ++i) in[i] = vals[((uint64_t)0 * 2 + ((chain_len[0] - 1) & 1u)) * max_ent + i];
-    for (uint32_t c = 1; c < n_chains; ++c) {
-        uint32_t *dst = vals + ((uint64_t)(n_chains * T + c) * 2 + 1) * max_ent;  // read by the chain's first column (step 0)
-        for (uint32_t i = 0; i < T; ++i) dst[i] = in[i];
-        const uint32_t par = (chain_len[c] - 1) & 1u;
-        for (uint32_t i = 0; i < T; ++i) outv[i] = UMAX;
-        for (uint32_t u = 0; u < T; ++u) {
-            if (in[u] == UMAX) continue;
-            const uint32_t *M = vals + ((uint64_t)(c * T + u) * 2 + par) * max_ent;
-            for (uint32_t i = 0; i < T; ++i) {
-                if (M[i] == UMAX) continue;
-                const uint32_t s = in[u] + M[i];
-                if (s < outv[i]) outv[i] = s;
-            }
-        }
-        for (uint32_t i = 0; i < T; ++i) in[i] = outv[i];
+                                  const uint32_t *__restrict__ chain_len, const uint32_t *__restrict__ in_vec,
+                                  uint32_t continues, uint32_t *__restrict__ matrix) {
+    const uint32_t u0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u0 >= (matrix ? T : 1u)) return;
+    uint32_t in[MAX_T];
+    uint32_t c_first = 0;
+    if (matrix && continues) {
+        for (uint32_t i = 0; i < T; ++i) in[i] = i == u0 ? 0u : UMAX;
+    } else if (!matrix && in_vec) {
+        for (uint32_t i = 0; i < T; ++i) in[i] = in_vec[i];
+    } else {
+        for (uint32_t i = 0; i < T; ++i) in[i] = vals[((uint64_t)0 * 2 + ((chain_len[0] - 1) & 1u)) * max_ent + i];
+        c_first = 1;
     }
+    fold_chains(
+        T, c_first, n_chains, in,
+        [&](uint32_t c, uint32_t u) { return vals + ((uint64_t)(c * T + u) * 2 + ((chain_len[c] - 1) & 1u)) * max_ent; },
+        [&](uint32_t c, const uint32_t *cur) {
+            if (matrix) return;
+            uint32_t *dst = vals + ((uint64_t)(n_chains * T + c) * 2 + 1) * max_ent;  // read by the chain's first column (step 0)
+            for (uint32_t i = 0; i < T; ++i) dst[i] = cur[i];
+        });
+    if (matrix)
+        for (uint32_t i = 0; i < T; ++i) matrix[(uint64_t)u0 * T + i] = in[i];
 }
 
 // unit input vectors of pass 1: slot 1 + (c-1)*T + u gets 0 at u, +inf elsewhere
@@ -456,29 +465,87 @@ __global__ void __launch_bounds__(256) col_finalize_kernel(const ColMeta *__rest
 }
 
 // Backtrace on the device: the packed back-pointers stay in HBM, only the path comes back.
-// T == 1: DP-independent chains are traced by independent threads.  T > 1: one thread walks the
-// whole table (transmission values couple the chains, pedigreedptable.cpp:272-297).
-__global__ void backtrace_kernel(const ColMeta *__restrict__ cols, const uint32_t *__restrict__ arena, uint32_t T,
-                                 uint32_t tb, const uint32_t *__restrict__ chain_begin, uint32_t n_chains, uint32_t n,
+// T == 1: DP-independent chains are traced by independent threads.
+__global__ void backtrace_kernel(const ColMeta *__restrict__ cols, const uint32_t *__restrict__ arena,
+                                 const uint32_t *__restrict__ chain_begin, uint32_t n_chains, uint32_t n,
                                  const uint32_t *__restrict__ last_vals, uint32_t *__restrict__ path_index,
                                  uint32_t *__restrict__ path_tv, uint32_t *__restrict__ result) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    BtView bv{cols, arena, T, tb};
-    if (T == 1) {
-        if (c >= n_chains) return;
-        const uint32_t k_first = chain_begin[c], k_last = chain_begin[c + 1] - 1;
-        const ColMeta &m = cols[k_last];
-        const uint32_t bp = bp_load(arena, m.bp_off, m.bp_width, 0);
-        const uint32_t x = candidate_index(m, 0, bp);
-        backtrace_range(bv, k_last, k_first, x, 0, 0, path_index, path_tv);
-        if (k_last == n - 1) result[0] = last_vals[0];
+    BtView bv{cols, arena, 1, 0};
+    if (c >= n_chains) return;
+    const uint32_t k_first = chain_begin[c], k_last = chain_begin[c + 1] - 1;
+    const ColMeta &m = cols[k_last];
+    const uint32_t bp = bp_load(arena, m.bp_off, m.bp_width, 0);
+    const uint32_t x = candidate_index(m, 0, bp);
+    backtrace_range(bv, k_last, k_first, x, 0, 0, path_index, path_tv);
+    if (k_last == n - 1) result[0] = last_vals[0];
+}
+
+// T > 1: transmission values couple the chains (pedigreedptable.cpp:272-297), but only through the one
+// value `prev_tv` that the walk carries across a chain boundary (chain_entry).  Three small kernels
+// instead of one thread walking the whole table:
+//   exits:   thread (c, u) walks chain c as if entered with prev_tv = u and records the value it would
+//            hand to chain c-1 (no path written).  The last chain of a plan that ends the table is entered
+//            at the optimum of its last column instead (entry < 0), for every u alike.
+//   entries: one thread follows the realised entry values right to left over the n_chains boundaries
+//            (or, with seg_exits, thread u composes the exits of all chains: what the plan as a whole hands
+//            to its predecessor when entered with u -- whmec_segment_exits).
+//   paths:   thread c walks chain c again from its realised entry and writes the path.
+struct BtArgs {
+    const ColMeta *cols;
+    const uint32_t *arena, *chain_begin, *last_vals;
+    uint32_t T, tb, n_chains;
+    int entry;  // prev_tv handed to the last chain by the columns after the plan; < 0: the plan ends the table
+};
+
+__device__ __forceinline__ void bt_chain_start(const BtArgs &a, const BtView &bv, uint32_t c, uint32_t u, uint32_t *x,
+                                               uint32_t *tv, uint32_t *ptv, uint32_t *cost) {
+    const uint32_t k_last = a.chain_begin[c + 1] - 1;
+    if (c + 1 == a.n_chains && a.entry < 0) {
+        pick_optimum(a.cols[k_last], a.last_vals, a.arena, a.T, a.tb, cost, x, tv, ptv);
     } else {
-        if (c != 0) return;
-        uint32_t cost, x, tv, ptv;
-        pick_optimum(cols[n - 1], last_vals, arena, T, tb, &cost, &x, &tv, &ptv);
-        backtrace_range(bv, n - 1, 0, x, tv, ptv, path_index, path_tv);
-        result[0] = cost;
+        *tv = u;
+        chain_entry(bv, k_last, u, x, ptv);
     }
+}
+
+__global__ void bt_exits_kernel(const BtArgs a, uint32_t *__restrict__ exits) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.n_chains * a.T) return;
+    const uint32_t c = idx / a.T, u = idx % a.T;
+    BtView bv{a.cols, a.arena, a.T, a.tb};
+    uint32_t x, tv, ptv, cost;
+    bt_chain_start(a, bv, c, u, &x, &tv, &ptv, &cost);
+    exits[idx] = backtrace_range(bv, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, nullptr, nullptr);
+}
+
+__global__ void bt_entries_kernel(const BtArgs a, const uint32_t *__restrict__ exits, uint32_t *__restrict__ entries,
+                                  uint32_t *__restrict__ seg_exits) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (seg_exits) {
+        if (t >= a.T) return;
+        uint32_t e = t;
+        for (uint32_t c = a.n_chains; c-- > 0;) e = exits[c * a.T + e];
+        seg_exits[t] = e;
+        return;
+    }
+    if (t) return;
+    uint32_t e = a.entry < 0 ? 0u : (uint32_t)a.entry;  // the optimum's exit is stored for every u alike
+    for (uint32_t c = a.n_chains; c-- > 0;) {
+        entries[c] = e;
+        e = exits[c * a.T + e];
+    }
+}
+
+__global__ void bt_paths_kernel(const BtArgs a, const uint32_t *__restrict__ entries, uint32_t *__restrict__ path_index,
+                                uint32_t *__restrict__ path_tv, uint32_t *__restrict__ result) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    BtView bv{a.cols, a.arena, a.T, a.tb};
+    uint32_t x, tv, ptv, cost = 0;
+    bt_chain_start(a, bv, c, entries[c], &x, &tv, &ptv, &cost);
+    backtrace_range(bv, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, path_index, path_tv);
+    if (c + 1 == a.n_chains) result[0] = cost;
 }
 
 // Device buffers come from the device's stream-ordered memory pool with an unlimited release
@@ -536,6 +603,12 @@ struct whmec_plan {
     uint64_t ped_max_ent = 0;
     uint32_t ped_slots = 0;
     const uint32_t *d_last_vals = nullptr;
+    // segment of a pedigree table shared by several GPUs (whmec_segment_*): 0 = whole table,
+    // 1 = first segment, 2 = segment continuing a table (its first column receives an input vector)
+    int segment = 0;
+    bool transferred = false;
+    int exits_mode = 0;  // 0: not computed since the last sweep; 1: last chain entered at the optimum; 2: like any chain
+    DevBuf<uint32_t> d_in_vec, d_matrix, d_bt_exits, d_bt_entries;
     uint32_t sweeps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
     // tile path
@@ -547,6 +620,7 @@ struct whmec_plan {
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
         d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release(); d_ped_args.release();
+        d_in_vec.release(); d_matrix.release(); d_bt_exits.release(); d_bt_entries.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
@@ -573,12 +647,13 @@ void keep_host_memory() {
     mallopt(M_TRIM_THRESHOLD, 1 << 30);
 }
 
-int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::string &msg) {
+int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::string &msg, int segment = 0) {
     keep_host_memory();
+    pl->segment = segment;
     // single-individual problems normally run on the tile kernel, which needs no per-read cost deltas
     const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
     const bool forced_column = force && force[0] == '1';
-    const bool tile_candidate = p->n_ind == 1 && p->n_trios == 0 && !forced_column;
+    const bool tile_candidate = p->n_ind == 1 && p->n_trios == 0 && !forced_column && !segment;
     int rc = pack_problem(p, pl->pk, msg, !tile_candidate);
     if (rc != WHMEC_OK) return rc;
     Packed &pk = pl->pk;
@@ -589,6 +664,13 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     }
     pl->device = device;
     pl->stats = pk.stats;
+    if (segment) {
+        if (pk.T == 1 || pk.n == 0) {
+            msg = "unsupported: table segments are for pedigrees (T > 1) and need at least one column; single-individual chains are independent problems";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
+        if (segment == 2) pk.cols[0].first = 0;  // column 0 reads the vector handed over by the preceding segment
+    }
     if (pk.n == 0) return WHMEC_OK;
     for (const ColMeta &m : pk.cols)
         if (m.d + pk.tb > 32) {
@@ -644,7 +726,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         // pedigrees with several chains: batched two-pass sweep
         const char *seq = std::getenv("WHMEC_PED_SEQUENTIAL");
         const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
-        if (pk.T > 1 && C >= 2 && pk.safe31 && !(seq && seq[0] == '1')) {
+        if (pk.T > 1 && (C >= 2 || segment) && pk.safe31 && !(seq && seq[0] == '1' && !segment)) {
             const uint32_t T = pk.T;
             const uint32_t slots = C * T + C;
             if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && (uint64_t)C * T <= 65535) {
@@ -719,6 +801,18 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                 pl->stats.path_kind = 3;
             }
         }
+        if (segment && !pl->use_ped_batch) {
+            msg = "unsupported: this segment cannot run the two-pass pedigree sweep (costs beyond 2^28 or state beyond the budget)";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
+        if (pk.T > 1) {
+            CUDA_TRY(pl->d_bt_exits.alloc((size_t)C * pk.T, pl->stream));
+            CUDA_TRY(pl->d_bt_entries.alloc(C, pl->stream));
+        }
+        if (segment) {
+            CUDA_TRY(pl->d_in_vec.alloc(pk.T, pl->stream));
+            CUDA_TRY(pl->d_matrix.alloc((size_t)pk.T * pk.T, pl->stream));
+        }
     }
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
@@ -727,44 +821,57 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     return WHMEC_OK;
 }
 
-int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
+// One pass of the batched pedigree sweep.  pass 0: unit input vectors, values only (transfer matrices);
+// pass 1: true input vectors, back-pointers written.
+int ped_pass(whmec_plan *pl, int pass, uint32_t &launches, std::string &msg) {
     Packed &pk = pl->pk;
     const uint32_t T = pk.T, tb = pk.tb;
-    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
-    uint32_t launches = 0;
-    const uint32_t unit_slots = C * T;
-    ped_init_kernel<<<(unit_slots * T + 255) / 256, 256, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, unit_slots);
-    ++launches;
-    for (int pass = 0; pass < 2; ++pass) {
-        const size_t nsteps = pl->ped_grid[pass].size();
-        for (size_t st = 0; st < nsteps; ++st) {
-            const uint32_t b0 = pl->ped_begin[pass][st], b1 = pl->ped_begin[pass][st + 1];
-            if (b1 > b0) {
-                dim3 grid(pl->ped_grid[pass][st], b1 - b0);
-                col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
-                                                                   pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
-                                                                   (uint32_t)(st & 1), pl->d_ped_args.p);
+    if (pass == 0) {
+        const uint32_t unit_slots = ((uint32_t)pk.chain_begin.size() - 1) * T;
+        ped_init_kernel<<<(unit_slots * T + 255) / 256, 256, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, unit_slots);
+        ++launches;
+    }
+    const size_t nsteps = pl->ped_grid[pass].size();
+    for (size_t st = 0; st < nsteps; ++st) {
+        const uint32_t b0 = pl->ped_begin[pass][st], b1 = pl->ped_begin[pass][st + 1];
+        if (b1 > b0) {
+            dim3 grid(pl->ped_grid[pass][st], b1 - b0);
+            col_batched_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + b0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
+                                                               pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, pl->d_arena.p,
+                                                               (uint32_t)(st & 1), pl->d_ped_args.p);
+            ++launches;
+        }
+        if (pass == 0 && pl->ped_multi && st < pl->ped_grid[2].size()) {
+            const uint32_t m0 = pl->ped_begin[2][st], m1 = pl->ped_begin[2][st + 1];
+            if (m1 > m0) {
+                dim3 grid(pl->ped_grid[2][st], m1 - m0);
+                col_multi_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + m0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
+                                                                 pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p, (uint32_t)(st & 1));
                 ++launches;
             }
-            if (pass == 0 && pl->ped_multi && st < pl->ped_grid[2].size()) {
-                const uint32_t m0 = pl->ped_begin[2][st], m1 = pl->ped_begin[2][st + 1];
-                if (m1 > m0) {
-                    dim3 grid(pl->ped_grid[2][st], m1 - m0);
-                    col_multi_kernel<<<grid, 256, 0, pl->stream>>>(pl->d_ped_steps.p + m0, pl->d_ped_vals.p, pl->ped_max_ent, T, tb,
-                                                                     pl->d_fn_c0.p, pl->d_fn_delta.p, pl->d_fn_group.p,
-                                                                     (uint32_t)(st & 1));
-                    ++launches;
-                }
-            }
-        }
-        if (pass == 0) {
-            ped_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, T, C, pl->d_chain_len.p);
-            ++launches;
         }
     }
     CUDA_TRY(cudaGetLastError());
-    pl->stats.kernel_launches = launches;
     return WHMEC_OK;
+}
+
+// every chain's true input vector from the transfer matrices (in_vec: see ped_prefix_kernel)
+int ped_prefix(whmec_plan *pl, const uint32_t *d_in_vec, uint32_t &launches, std::string &msg) {
+    const uint32_t C = (uint32_t)pl->pk.chain_begin.size() - 1;
+    ped_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, pl->pk.T, C, pl->d_chain_len.p, d_in_vec,
+                                                 pl->segment == 2, nullptr);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    return WHMEC_OK;
+}
+
+int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
+    uint32_t launches = 0;
+    int rc = ped_pass(pl, 0, launches, msg);
+    if (rc == WHMEC_OK) rc = ped_prefix(pl, nullptr, launches, msg);
+    if (rc == WHMEC_OK) rc = ped_pass(pl, 1, launches, msg);
+    pl->stats.kernel_launches = launches;
+    return rc;
 }
 
 // The column path issues one (small) kernel per column; a sweep of the same plan is replayed from a
@@ -841,10 +948,42 @@ int plan_sweep_impl(whmec_plan *pl, std::string &msg) {
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
     pl->swept = true;
+    pl->exits_mode = 0;
     return WHMEC_OK;
 }
 
-int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg) {
+BtArgs bt_args(const whmec_plan *pl, int entry) {
+    const Packed &pk = pl->pk;
+    return BtArgs{pl->d_cols.p, pl->d_arena.p, pl->d_chain_begin.p, pl->use_ped_batch ? pl->d_last_vals : pl->d_val[pl->last_buf].p,
+                  pk.T, pk.tb, (uint32_t)pk.chain_begin.size() - 1, entry};
+}
+
+// exits of every (chain, entry value): the first of the three backtrace kernels for T > 1
+int pedigree_exits(whmec_plan *pl, int entry, std::string &msg) {
+    const BtArgs a = bt_args(pl, entry);
+    const uint32_t threads = a.n_chains * a.T;
+    bt_exits_kernel<<<(threads + 63) / 64, 64, 0, pl->stream>>>(a, pl->d_bt_exits.p);
+    CUDA_TRY(cudaGetLastError());
+    pl->exits_mode = entry < 0 ? 1 : 2;
+    return WHMEC_OK;
+}
+
+// entry < 0: the plan ends the table (start from the optimum of the last column); otherwise the
+// transmission value handed over by the segment that follows.
+int pedigree_backtrace(whmec_plan *pl, int entry, std::string &msg) {
+    if (pl->exits_mode != (entry < 0 ? 1 : 2)) {  // the table of exits depends only on how the last chain is entered
+        int rc = pedigree_exits(pl, entry, msg);
+        if (rc != WHMEC_OK) return rc;
+    }
+    const BtArgs a = bt_args(pl, entry);
+    bt_entries_kernel<<<1, 32, 0, pl->stream>>>(a, pl->d_bt_exits.p, pl->d_bt_entries.p, nullptr);
+    bt_paths_kernel<<<(a.n_chains + 63) / 64, 64, 0, pl->stream>>>(a, pl->d_bt_entries.p, pl->d_path_index.p, pl->d_path_tv.p,
+                                                                    pl->d_result.p);
+    CUDA_TRY(cudaGetLastError());
+    return WHMEC_OK;
+}
+
+int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int entry = -1) {
     Packed &pk = pl->pk;
     const uint32_t n = pk.n;
     if (n == 0) {  // pedigreedptable.cpp:88-92
@@ -864,10 +1003,14 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg) {
         CUDA_TRY(cudaMemsetAsync(pl->d_path_tv.p, 0, (size_t)n * 4, pl->stream));
     } else {
         const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
-        const uint32_t threads = pk.T == 1 ? n_chains : 1;
-        backtrace_kernel<<<(threads + 63) / 64, 64, 0, pl->stream>>>(pl->d_cols.p, pl->d_arena.p, pk.T, pk.tb,
-                                                                      pl->d_chain_begin.p, n_chains, n, pl->use_ped_batch ? pl->d_last_vals : pl->d_val[pl->last_buf].p,
-                                                                      pl->d_path_index.p, pl->d_path_tv.p, pl->d_result.p);
+        const uint32_t *last_vals = pl->use_ped_batch ? pl->d_last_vals : pl->d_val[pl->last_buf].p;
+        if (pk.T == 1) {
+            backtrace_kernel<<<(n_chains + 63) / 64, 64, 0, pl->stream>>>(pl->d_cols.p, pl->d_arena.p, pl->d_chain_begin.p, n_chains, n,
+                                                                           last_vals, pl->d_path_index.p, pl->d_path_tv.p, pl->d_result.p);
+        } else {
+            int rc = pedigree_backtrace(pl, entry, msg);
+            if (rc != WHMEC_OK) return rc;
+        }
         CUDA_TRY(cudaGetLastError());
     }
     std::vector<uint32_t> pidx(n), ptv(n);
@@ -881,6 +1024,87 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg) {
     pl->stats.d2h_bytes = (uint64_t)n * 8 + 16;
     s->cost = result[0];
     return build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+}
+
+// ---- segments of a pedigree table (include/whmec.h) ----
+int segment_check(const whmec_plan *pl, std::string &msg) {
+    if (!pl || !pl->segment || !pl->use_ped_batch) {
+        msg = "not a segment plan (use whmec_segment_create)";
+        return WHMEC_ERR_INPUT;
+    }
+    return WHMEC_OK;
+}
+
+int segment_transfer_impl(whmec_plan *pl, uint32_t *matrix, std::string &msg) {
+    int rc = segment_check(pl, msg);
+    if (rc != WHMEC_OK) return rc;
+    const Packed &pk = pl->pk;
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+    CUDA_TRY(cudaSetDevice(pl->device));
+    CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
+    uint32_t launches = 0;
+    rc = ped_pass(pl, 0, launches, msg);
+    if (rc != WHMEC_OK) return rc;
+    ped_prefix_kernel<<<(pk.T + 31) / 32, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, pk.T, C, pl->d_chain_len.p, nullptr,
+                                                                pl->segment == 2, pl->d_matrix.p);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(matrix, pl->d_matrix.p, (size_t)pk.T * pk.T * 4, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
+    pl->stats.kernel_launches = launches;
+    pl->transferred = true;
+    return WHMEC_OK;
+}
+
+int segment_sweep_impl(whmec_plan *pl, const uint32_t *in_vec, uint32_t *out_vec, std::string &msg) {
+    int rc = segment_check(pl, msg);
+    if (rc != WHMEC_OK) return rc;
+    if (!pl->transferred) {
+        msg = "whmec_segment_sweep called before whmec_segment_transfer";
+        return WHMEC_ERR_INPUT;
+    }
+    if ((pl->segment == 2) != (in_vec != nullptr)) {
+        msg = "a continuing segment needs an input vector, the first segment of a table takes none";
+        return WHMEC_ERR_INPUT;
+    }
+    const uint32_t T = pl->pk.T;
+    CUDA_TRY(cudaSetDevice(pl->device));
+    CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
+    if (in_vec) CUDA_TRY(cudaMemcpyAsync(pl->d_in_vec.p, in_vec, (size_t)T * 4, cudaMemcpyHostToDevice, pl->stream));
+    uint32_t launches = 0;
+    rc = ped_prefix(pl, in_vec ? pl->d_in_vec.p : nullptr, launches, msg);
+    if (rc == WHMEC_OK) rc = ped_pass(pl, 1, launches, msg);
+    if (rc != WHMEC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out_vec, pl->d_last_vals, (size_t)T * 4, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, pl->ev0, pl->ev1));
+    pl->stats.sweep_ms += ms;
+    pl->stats.kernel_launches += launches;
+    pl->swept = true;
+    pl->exits_mode = 0;
+    return WHMEC_OK;
+}
+
+int segment_exits_impl(whmec_plan *pl, int is_last, uint32_t *exits, std::string &msg) {
+    int rc = segment_check(pl, msg);
+    if (rc != WHMEC_OK) return rc;
+    if (!pl->swept) {
+        msg = "whmec_segment_exits called before whmec_segment_sweep";
+        return WHMEC_ERR_INPUT;
+    }
+    CUDA_TRY(cudaSetDevice(pl->device));
+    rc = pedigree_exits(pl, is_last ? -1 : 0, msg);
+    if (rc != WHMEC_OK) return rc;
+    const BtArgs a = bt_args(pl, is_last ? -1 : 0);
+    bt_entries_kernel<<<(a.T + 31) / 32, 32, 0, pl->stream>>>(a, pl->d_bt_exits.p, nullptr, pl->d_in_vec.p);  // d_in_vec is free again
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(exits, pl->d_in_vec.p, (size_t)a.T * 4, cudaMemcpyDeviceToHost, pl->stream));
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    return WHMEC_OK;
 }
 
 }  // namespace
@@ -931,6 +1155,53 @@ int whmec_plan_stats(const whmec_plan *plan, whmec_stats *st) {
 }
 
 void whmec_plan_destroy(whmec_plan *plan) { delete plan; }
+
+int whmec_segment_create(const whmec_problem *p, int device, int continues, whmec_plan **out, char *err, size_t errlen) {
+    std::string msg;
+    whmec_plan *pl = new whmec_plan();
+    int rc = plan_create_impl(p, device, pl, msg, continues ? 2 : 1);
+    if (rc != WHMEC_OK) {
+        set_err(err, errlen, msg);
+        delete pl;
+        *out = nullptr;
+        return rc;
+    }
+    *out = pl;
+    return WHMEC_OK;
+}
+
+int whmec_segment_transfer(whmec_plan *plan, uint32_t *matrix, char *err, size_t errlen) {
+    std::string msg;
+    int rc = segment_transfer_impl(plan, matrix, msg);
+    if (rc != WHMEC_OK) set_err(err, errlen, msg);
+    return rc;
+}
+
+int whmec_segment_sweep(whmec_plan *plan, const uint32_t *in_vec, uint32_t *out_vec, char *err, size_t errlen) {
+    std::string msg;
+    int rc = segment_sweep_impl(plan, in_vec, out_vec, msg);
+    if (rc != WHMEC_OK) set_err(err, errlen, msg);
+    return rc;
+}
+
+int whmec_segment_exits(whmec_plan *plan, int is_last, uint32_t *exits, char *err, size_t errlen) {
+    std::string msg;
+    int rc = segment_exits_impl(plan, is_last, exits, msg);
+    if (rc != WHMEC_OK) set_err(err, errlen, msg);
+    return rc;
+}
+
+int whmec_segment_finish(whmec_plan *plan, int entry, whmec_solution *s, char *err, size_t errlen) {
+    std::string msg;
+    int rc = segment_check(plan, msg);
+    if (rc == WHMEC_OK && entry >= (int)plan->pk.T) {
+        msg = "entry transmission value out of range";
+        rc = WHMEC_ERR_INPUT;
+    }
+    if (rc == WHMEC_OK) rc = plan_finish_impl(plan, s, msg, entry);
+    if (rc != WHMEC_OK) set_err(err, errlen, msg);
+    return rc;
+}
 
 int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st, char *err, size_t errlen) {
     using clk = std::chrono::steady_clock;

@@ -65,29 +65,178 @@ def assign_blocks(work: np.ndarray, world: int) -> List[List[int]]:
     return shares
 
 
-def merge_block_solutions(prob: FlatProblem, blocks, solutions) -> FlatSolution:
-    """Concatenate per-block results in column order; costs add (T = 1)."""
+def merge_block_solutions(prob: FlatProblem, blocks, solutions, cost: Optional[int] = None) -> FlatSolution:
+    """Concatenate per-block results in column order; costs add (T = 1) unless `cost` is given."""
     out = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
     first = prob.ent_col[prob.read_off[:-1].astype(np.int64)] if prob.n_reads else np.zeros(0, np.uint32)
-    cost = 0
+    total = 0
     for (lo, hi), sol in zip(blocks, solutions):
-        cost += int(sol.cost)
+        total += int(sol.cost)
         out.path_index[lo:hi] = sol.path_index
         out.path_tv[lo:hi] = sol.path_tv
         out.sr_allele[:, :, lo:hi] = sol.sr_allele
         out.sr_quality[:, lo:hi] = sol.sr_quality
         reads = np.nonzero((first >= lo) & (first < hi))[0]
         out.partition[reads] = sol.partition
-    out.cost = cost & 0xFFFFFFFF
+    out.cost = (total if cost is None else cost) & 0xFFFFFFFF
     return out
 
 
+UMAX = 0xFFFFFFFF
+
+
+def contiguous_shares(work: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """Cut the block sequence into `world` contiguous runs [b0, b1) of about equal work (a run may be
+    empty when there are fewer blocks than ranks)."""
+    n = len(work)
+    cum = np.concatenate([[0.0], np.cumsum(work, dtype=np.float64)])
+    cuts = [0]
+    for r in range(1, world):
+        want = cum[-1] * r / world
+        b = int(np.searchsorted(cum, want, side="left"))
+        if b > 0 and want - cum[b - 1] < cum[min(b, n)] - want:
+            b -= 1
+        cuts.append(min(max(b, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def minplus(vec: np.ndarray, matrix: np.ndarray) -> np.ndarray:
+    """out[i] = min_u vec[u] + matrix[u, i] over u32 with 0xFFFFFFFF as +inf (the fold of
+    `ped_prefix_kernel`, whatshap_b200/csrc/whmec.cu)."""
+    v = vec.astype(np.uint64)[:, None]
+    m = matrix.astype(np.uint64)
+    s = v + m
+    s[(v == UMAX) | (m == UMAX)] = UMAX
+    return s.min(axis=0).astype(np.uint32)
+
+
+def segment_inputs(matrices: Sequence[Optional[np.ndarray]]) -> List[Optional[np.ndarray]]:
+    """True input vector of every segment from the segments' transfer matrices (None: rank without
+    columns).  The first segment ignores its input: all rows of its matrix are its output."""
+    inputs: List[Optional[np.ndarray]] = []
+    vec = None
+    for m in matrices:
+        if m is None:
+            inputs.append(None)
+            continue
+        inputs.append(vec)
+        vec = m[0].copy() if vec is None else minplus(vec, m)
+    return inputs
+
+
+def segment_entries(exits: Sequence[Optional[np.ndarray]]) -> List[Optional[int]]:
+    """Transmission value the backtrace enters every segment with, right to left; -1 for the segment
+    that ends the table (it starts at the optimum and reports the same exit for every value)."""
+    entries: List[Optional[int]] = [None] * len(exits)
+    entry = -1
+    for s in range(len(exits) - 1, -1, -1):
+        if exits[s] is None:
+            continue
+        entries[s] = entry
+        entry = int(exits[s][max(entry, 0)])
+    return entries
+
+
+def _default_segment_factory():
+    import torch
+
+    from . import _lib
+
+    device = torch.cuda.current_device()
+    return lambda p, continues: _lib.Segment(p, continues, device=device)
+
+
+def segment_ranges(prob: FlatProblem, world: int) -> List[Optional[Tuple[int, int]]]:
+    """Column range [lo, hi) of every rank's segment (None: no columns for that rank)."""
+    blocks = independent_blocks(prob)
+    shares = contiguous_shares(block_work(prob, blocks), world)
+    return [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in shares]
+
+
+def solve_pedigree_segments(prob: FlatProblem, n_segments: int, segment_factory=None) -> FlatSolution:
+    """The multi-GPU pedigree scheme with all `n_segments` segments driven by ONE process on one
+    device, in the order the ranks would run them -- the single-GPU check of `whmec_segment_*`
+    (tests/test_gpu_sharded.py) and of this module's folding logic."""
+    if segment_factory is None:
+        segment_factory = _default_segment_factory()
+    ranges = segment_ranges(prob, n_segments)
+    segs = [None if r is None else segment_factory(prob.slice_columns(*r), r[0] > 0) for r in ranges]
+    try:
+        last_active = max(i for i, sg in enumerate(segs) if sg is not None)
+        inputs = segment_inputs([sg.transfer() if sg else None for sg in segs])
+        for sg, vec in zip(segs, inputs):
+            if sg:
+                sg.sweep(vec)
+        entries = segment_entries([sg.exits(i == last_active) if sg else None for i, sg in enumerate(segs)])
+        parts = [(ranges[i], sg.finish(entries[i])) for i, sg in enumerate(segs) if sg]
+    finally:
+        for sg in segs:
+            if sg:
+                sg.close()
+    return merge_block_solutions(prob, [r for r, _ in parts], [sol for _, sol in parts], cost=int(parts[-1][1].cost))
+
+
+def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) -> Tuple[bool, Optional[FlatSolution]]:
+    """T > 1: `prob` is known on every rank.  Returns (True, solution) on rank 0 and (True, None)
+    elsewhere, or (False, None) on every rank if some segment is outside what the two-pass scheme
+    handles (the caller then solves on one GPU).  Input errors (Mendelian conflict, unsorted reads) are
+    raised on every rank."""
+    import torch.distributed as dist
+
+    from ._abi import Unsupported
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if segment_factory is None:
+        segment_factory = _default_segment_factory()
+    ranges = segment_ranges(prob, world)
+    last_active = max(r for r in range(world) if ranges[r] is not None)
+
+    def everyone(value):
+        box = [None] * world
+        dist.all_gather_object(box, value, group=group)
+        return box
+
+    seg, status = None, ("ok", "")
+    mine = ranges[rank]
+    if mine is not None:
+        try:
+            seg = segment_factory(prob.slice_columns(*mine), mine[0] > 0)
+        except Unsupported as e:
+            status = ("unsupported", str(e))
+        except RuntimeError as e:
+            status = ("error", e)
+    try:
+        states = everyone(status)
+        for kind, payload in states:
+            if kind == "error":
+                raise payload
+        if any(kind == "unsupported" for kind, _ in states):
+            return False, None
+        matrices = everyone(seg.transfer() if seg else None)
+        out_vec = seg.sweep(segment_inputs(matrices)[rank]) if seg else None
+        exits = everyone(seg.exits(rank == last_active) if seg else None)
+        entry = segment_entries(exits)[rank]
+        part = (rank, seg.finish(entry), out_vec) if seg else None
+    finally:
+        if seg is not None:
+            seg.close()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(part, gathered, dst=0, group=group)
+    if rank != 0:
+        return True, None
+    parts = sorted((p for p in gathered if p is not None), key=lambda p: p[0])
+    return True, merge_block_solutions(prob, [ranges[r] for r, _, _ in parts], [sol for _, sol, _ in parts],
+                                       cost=int(parts[-1][1].cost))
+
+
 def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatProblem], FlatSolution]] = None,
-                  group=None) -> Optional[FlatSolution]:
+                  group=None, segment_factory=None) -> Optional[FlatSolution]:
     """Solve `prob` (given on rank 0; other ranks pass None) on all ranks of `group`.
 
-    Returns the merged solution on rank 0 and None elsewhere.  `solver` defaults to the CUDA path on
-    this rank's current device; tests inject a CPU checker to exercise the sharding logic with gloo."""
+    Returns the merged solution on rank 0 and None elsewhere.  `solver` / `segment_factory` default to
+    the CUDA path on this rank's current device; tests inject CPU stand-ins to exercise the sharding
+    logic with gloo."""
     import torch.distributed as dist
 
     if solver is None:
@@ -101,7 +250,11 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
     box = [prob]
     dist.broadcast_object_list(box, src=0, group=group)  # "trivial broadcast of the block list"
     prob = box[0]
-    if prob.n_trios > 0 or prob.n_cols == 0:  # transmission vectors couple the blocks: one GPU
+    if prob.n_trios > 0 and world > 1 and len(independent_blocks(prob)) > 1:  # transmission vectors couple the blocks
+        handled, sol = solve_pedigree_sharded(prob, segment_factory, group)
+        if handled:
+            return sol
+    if prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or outside the two-pass scheme: one GPU
         sol = solver(prob) if rank == 0 else None
         dist.barrier(group)
         return sol
