@@ -29,9 +29,11 @@ if rank == 0:
 ped = synth.config("cfg5") if rank == 0 else None
 multigpu.solve_sharded(synth.config("cfg5", 2000) if rank == 0 else None)  # warm-up
 torch.cuda.synchronize()
+os.environ["WHMEC_TIMING"] = "1"
 t0 = time.perf_counter()
 sol = multigpu.solve_sharded(ped)
 dt = time.perf_counter() - t0
+os.environ.pop("WHMEC_TIMING")
 if rank == 0:
     t1 = time.perf_counter()
     whole, _ = _lib.solve(ped, device=local)

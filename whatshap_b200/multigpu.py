@@ -197,6 +197,11 @@ def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) 
         dist.all_gather_object(box, value, group=group)
         return box
 
+    import os
+    import time
+
+    marks = [("start", time.perf_counter())]
+    mark = lambda name: marks.append((name, time.perf_counter()))
     seg, status = None, ("ok", "")
     mine = ranges[rank]
     if mine is not None:
@@ -213,16 +218,27 @@ def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) 
                 raise payload
         if any(kind == "unsupported" for kind, _ in states):
             return False, None
-        matrices = everyone(seg.transfer() if seg else None)
+        mark("create")
+        matrix = seg.transfer() if seg else None
+        mark("transfer")
+        matrices = everyone(matrix)
+        mark("gather matrices")
         out_vec = seg.sweep(segment_inputs(matrices)[rank]) if seg else None
+        mark("sweep")
         exits = everyone(seg.exits(rank == last_active) if seg else None)
+        mark("exits + gather")
         entry = segment_entries(exits)[rank]
         part = (rank, seg.finish(entry), out_vec) if seg else None
+        mark("finish")
     finally:
         if seg is not None:
             seg.close()
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(part, gathered, dst=0, group=group)
+    mark("gather results")
+    if rank == 0 and os.environ.get("WHMEC_TIMING"):
+        print("[whmec] pedigree segments, rank 0: " + ", ".join(
+            "%s %.1f ms" % (name, (t - t0) * 1e3) for (name, t), (_, t0) in zip(marks[1:], marks[:-1])), flush=True)
     if rank != 0:
         return True, None
     parts = sorted((p for p in gathered if p is not None), key=lambda p: p[0])
