@@ -153,6 +153,36 @@ int whmec_segment_sweep(whmec_plan *plan, const uint32_t *in_vec /* [T] or NULL 
 int whmec_segment_exits(whmec_plan *plan, int is_last, uint32_t *exits /* [T] */, char *err, size_t errlen);
 int whmec_segment_finish(whmec_plan *plan, int entry, whmec_solution *s, char *err, size_t errlen);
 
+/* ---- Coverage-capping read selection (host only; the step before the DP) -------------------------
+ * whatshap/readselect.pyx:240-272 picks reads greedily by score until every variant is covered or max_cov
+ * is reached.  Which read wins a tie is decided by the sift rules of the reference's positional max-heap
+ * (whatshap/priorityqueue.pyx; scores are int triples compared lexicographically), by the iteration order
+ * of a std::unordered_set<int> of freshly covered positions (readselect.pyx:117,135) and by the iteration
+ * order of CPython sets of read indices.  The first two are reproduced here (the second by using the very
+ * same container); the sets stay in Python (whatshap_b200/readselect.py), which hands their iteration
+ * orders in as arrays.  Reads are CSR over entries in ReadSet order; the arrays given to _create must
+ * outlive the selector.  Output arrays must hold n_reads (resp. the longest read's) elements. */
+typedef struct whmec_selector whmec_selector;
+whmec_selector *whmec_selector_create(uint32_t n_reads, uint32_t n_variants, const uint64_t *read_off, const int32_t *ent_pos,
+                                      const uint32_t *ent_rank /* rank of ent_pos among `positions` */,
+                                      const int32_t *positions /* sorted, distinct */, uint32_t max_cov);
+void whmec_selector_destroy(whmec_selector *sel);
+/* A slice (readselect.pyx:108-166) starts: queue items[0..n) in this order with scores[3*item .. 3*item+2]. */
+void whmec_selector_begin_slice(whmec_selector *sel, const uint32_t *items, const int32_t *scores, uint32_t n);
+/* Pop until a read is taken (returns 1: *read, the variant ranks it covers first in fresh_ranks[0..*n_fresh), in the
+ * order the caller must process them) or the queue is empty (returns 0).  Reads popped on the way whose span is
+ * already at max_cov are appended to over[0..*n_over). */
+int whmec_selector_next(whmec_selector *sel, uint32_t *read, uint32_t *fresh_ranks, uint32_t *n_fresh, uint32_t *over,
+                        uint32_t *n_over);
+/* Score update after a read was taken (readselect.pyx:38-52,160-164) for items[0..n) in this order: if still queued,
+ * the first component drops by the number of the item's variants that are not among the last fresh ones. */
+void whmec_selector_rescore(whmec_selector *sel, const uint32_t *items, uint32_t n);
+/* Bridging pass after a slice (readselect.pyx:199-228): queue items in order; a popped read whose span is full is
+ * removed (taken 0), one that connects two blocks of the reads taken so far is taken (taken 1), others stay.
+ * slice_reads: the reads the slice took.  Returns the number of removed[] / taken[] entries. */
+uint32_t whmec_selector_bridge(whmec_selector *sel, const uint32_t *items, const int32_t *scores, uint32_t n,
+                               const uint32_t *slice_reads, uint32_t n_slice, uint32_t *removed, uint8_t *taken);
+
 /* Sort key of ReadSet::sort() ties: std::hash<std::string>(name) ^ std::hash<int>(source_id)
  * as computed by libstdc++ (64-bit murmur, seed 0xc70f6907); src/readset.h:68-72. */
 uint64_t whmec_read_sort_key(const char *name, size_t len, int32_t source_id);

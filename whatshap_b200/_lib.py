@@ -32,6 +32,12 @@ EXPORTS = (
     "whmec_segment_sweep",
     "whmec_segment_exits",
     "whmec_segment_finish",
+    "whmec_selector_create",
+    "whmec_selector_destroy",
+    "whmec_selector_begin_slice",
+    "whmec_selector_next",
+    "whmec_selector_rescore",
+    "whmec_selector_bridge",
     "whmec_read_sort_key",
 )
 
@@ -65,6 +71,20 @@ def lib() -> C.CDLL:
     L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
     L.whmec_read_sort_key.restype = C.c_uint64
     u32p = C.POINTER(C.c_uint32)
+    i32p = C.POINTER(C.c_int32)
+    u64p, u8p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint8)
+    L.whmec_selector_create.argtypes = [C.c_uint32, C.c_uint32, u64p, i32p, u32p, i32p, C.c_uint32]
+    L.whmec_selector_create.restype = C.c_void_p
+    L.whmec_selector_destroy.argtypes = [C.c_void_p]
+    L.whmec_selector_destroy.restype = None
+    L.whmec_selector_begin_slice.argtypes = [C.c_void_p, u32p, i32p, C.c_uint32]
+    L.whmec_selector_begin_slice.restype = None
+    L.whmec_selector_next.argtypes = [C.c_void_p, u32p, u32p, u32p, u32p, u32p]
+    L.whmec_selector_next.restype = C.c_int
+    L.whmec_selector_rescore.argtypes = [C.c_void_p, u32p, C.c_uint32]
+    L.whmec_selector_rescore.restype = None
+    L.whmec_selector_bridge.argtypes = [C.c_void_p, u32p, i32p, C.c_uint32, u32p, C.c_uint32, u32p, u8p]
+    L.whmec_selector_bridge.restype = C.c_uint32
     L.whmec_segment_create.argtypes = [C.POINTER(CProblem), C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
     L.whmec_segment_transfer.argtypes = [C.c_void_p, u32p, C.c_char_p, C.c_size_t]
     L.whmec_segment_sweep.argtypes = [C.c_void_p, u32p, u32p, C.c_char_p, C.c_size_t]
