@@ -171,3 +171,41 @@ def test_segment_helpers():
     assert sorted(multigpu.contiguous_shares(np.array([5.0]), 3)) == [(0, 0), (0, 1), (1, 1)]  # one block: one rank has it
     shares = multigpu.contiguous_shares(np.array([8.0, 1, 1, 1, 1, 4]), 3)
     assert shares[0][0] == 0 and shares[-1][1] == 6 and all(a[1] == b[0] for a, b in zip(shares, shares[1:]))
+
+
+# ---- group-wise driver of whmec_solve (csrc/grouped.h): slicing and merging, emulated kernels as backend ----
+def _grouped(lib, prob, groups, tiles):
+    lib.whemul_grouped_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    sol = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+    cp, cs, handled, n_groups = prob.as_c(), sol.as_c(), C.c_int(0), C.c_uint32(0)
+    assert lib.whemul_grouped_solve(C.byref(cp), C.byref(cs), groups, tiles, C.byref(handled), C.byref(n_groups)) == 0
+    sol.cost = int(cs.cost)
+    return (sol if handled.value else None), n_groups.value
+
+
+def test_groups_of_chains_reproduce_the_whole_solve(emul, checker):
+    """A single-individual problem cut into groups of whole chains, every group solved on its own slice of the
+    input arrays, results written back at their offsets: identical to the reference on the whole problem.
+    Problems the driver must decline (pedigrees, few chains, unsorted input, Mendelian conflicts) fall through."""
+    lib = emul["libwhemul.so"]
+    rng = np.random.default_rng(4)
+    handled = 0
+    for it in range(120):
+        prob = synth.random_problem(rng, int(rng.integers(10, 80)), int(rng.integers(2, 7)), pedigree="single", distrust=it % 4 == 0,
+                                    conflict_free=it % 7 != 0, mean_len=float(rng.choice([1.5, 3.0])))
+        try:
+            want = checker.solve(prob)
+        except RuntimeError:
+            want = None
+        for groups in (2, 4):
+            got, _ = _grouped(lib, prob, groups, it % 2)
+            if got is None:
+                continue
+            assert want is not None and got.same_as(want), (it, groups, got.diff(want) if want is not None else "error expected")
+            handled += 1
+    assert handled > 100
+    prob = synth.sliding_window(600, 12, block_len=50, seed=3)
+    got, n_groups = _grouped(lib, prob, 4, 1)
+    assert n_groups == 4 and got.same_as(checker.solve(prob))
+    assert _grouped(lib, synth.trio(60, 2, block_len=10, seed=1), 2, 0)[0] is None      # transmission values couple the chains
+    assert _grouped(lib, synth.sliding_window(60, 5, block_len=30, seed=1), 2, 1)[0] is None  # two chains: not worth cutting

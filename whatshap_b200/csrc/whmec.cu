@@ -20,6 +20,7 @@
 #include "../../include/whmec.h"
 #include "common.h"
 #include "dp_device.h"
+#include "grouped.h"
 #include "pack.h"
 #include "tile.cuh"
 
@@ -586,6 +587,7 @@ struct whmec_plan {
     Packed pk;
     whmec_stats stats{};
     bool swept = false;
+    bool sweep_pending = false;  // a sweep is enqueued but has not been waited for
     bool use_tiles = false;
     // column-kernel buffers
     DevBuf<ColMeta> d_cols;
@@ -926,7 +928,8 @@ int column_sweep(whmec_plan *pl, std::string &msg) {
     return WHMEC_OK;
 }
 
-int plan_sweep_impl(whmec_plan *pl, std::string &msg) {
+// wait == false: the sweep is only enqueued on the plan's stream; plan_finish_impl (same stream) collects it
+int plan_sweep_impl(whmec_plan *pl, std::string &msg, bool wait = true) {
     if (pl->pk.n == 0) {
         pl->swept = true;
         return WHMEC_OK;
@@ -945,10 +948,12 @@ int plan_sweep_impl(whmec_plan *pl, std::string &msg) {
     }
     if (rc != WHMEC_OK) return rc;
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
-    CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
     pl->swept = true;
     pl->exits_mode = 0;
+    pl->sweep_pending = !wait;
+    if (!wait) return WHMEC_OK;
+    CUDA_TRY(cudaStreamSynchronize(pl->stream));
+    CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
     return WHMEC_OK;
 }
 
@@ -996,6 +1001,11 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int en
         return WHMEC_ERR_INPUT;
     }
     CUDA_TRY(cudaSetDevice(pl->device));
+    if (pl->sweep_pending) {  // enqueued by plan_sweep_impl(wait = false): its events are reused below
+        CUDA_TRY(cudaEventSynchronize(pl->ev1));
+        CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
+        pl->sweep_pending = false;
+    }
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     if (pl->use_tiles) {
         int rc = pl->tiles.backtrace(pk, pl->stream, pl->d_path_index.p, pl->d_result.p, msg);
@@ -1107,6 +1117,46 @@ int segment_exits_impl(whmec_plan *pl, int is_last, uint32_t *exits, std::string
     return WHMEC_OK;
 }
 
+// Backend of solve_in_groups (grouped.h): one plan per group of chains, sweeps enqueued without waiting
+struct CudaGroups {
+    using Handle = whmec_plan;
+    int device;
+    whmec_stats total{};
+    uint32_t groups = 0;
+    int start(const whmec_problem &q, whmec_plan *&h, std::string &msg) {
+        h = new whmec_plan();
+        int rc = plan_create_impl(&q, device, h, msg);
+        if (rc == WHMEC_OK) rc = plan_sweep_impl(h, msg, false);
+        if (rc != WHMEC_OK) {
+            delete h;
+            h = nullptr;
+        }
+        return rc;
+    }
+    int finish(whmec_plan *h, whmec_solution *sub, std::string &msg) {
+        const int rc = plan_finish_impl(h, sub, msg);
+        if (rc != WHMEC_OK) return rc;
+        const whmec_stats &st = h->stats;
+        total.cells += st.cells;
+        total.algorithmic_bytes += st.algorithmic_bytes;
+        total.backptr_bytes += st.backptr_bytes;
+        total.state_bytes += st.state_bytes;
+        total.kernel_launches += st.kernel_launches;
+        total.n_chains += st.n_chains;
+        total.max_active = std::max(total.max_active, st.max_active);
+        total.transmissions = st.transmissions;
+        total.sweep_ms += st.sweep_ms;
+        total.h2d_ms += st.h2d_ms;
+        total.d2h_ms += st.d2h_ms;
+        total.h2d_bytes += st.h2d_bytes;
+        total.d2h_bytes += st.d2h_bytes;
+        total.path_kind = (groups == 0 || total.path_kind == st.path_kind) ? st.path_kind : 3;
+        ++groups;
+        return WHMEC_OK;
+    }
+    void destroy(whmec_plan *h) { delete h; }
+};
+
 }  // namespace
 
 extern "C" {
@@ -1208,6 +1258,23 @@ int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_sta
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = clk::now();
+    // WHMEC_SOLVE_GROUPS=G (G >= 2): single-individual problems with many chains are cut into G groups of chains;
+    // the host packs / plans / uploads group g+1 while the GPU sweeps group g (grouped.h).  Off by default.
+    if (const char *e = std::getenv("WHMEC_SOLVE_GROUPS")) {
+        const int G = std::atoi(e);
+        if (G >= 2 && G <= 64) {
+            keep_host_memory();
+            CudaGroups be{device};
+            std::string msg;
+            bool handled = false;
+            solve_in_groups(p, s, (uint32_t)G, be, msg, &handled);
+            if (handled) {
+                if (st) *st = be.total;
+                if (timing) std::fprintf(stderr, "[whmec] solve: %u groups, %.2f ms (device sweeps %.2f ms)\n", be.groups, ms(t0, clk::now()), (double)be.total.sweep_ms);
+                return WHMEC_OK;
+            }
+        }
+    }
     whmec_plan *pl = nullptr;
     int rc = whmec_plan_create(p, device, &pl, err, errlen);
     if (rc != WHMEC_OK) return rc;
