@@ -10,6 +10,11 @@ sys.path.insert(0, os.environ["WHMEC_PYREF"])
 
 import whatshap.core as core  # noqa: E402
 
+try:  # the compiled reference-side binding, if it was built (integration/build_bridge.py): before core is patched
+    import whatshap_bridge  # noqa: E402,F401
+except ImportError:
+    pass
+
 from oracle import checker  # noqa: E402
 from whatshap_b200 import adapters  # noqa: E402
 

@@ -101,3 +101,87 @@ def test_single_individual_matrices_through_real_objects(ref_core, checker):
             assert a.get_optimal_partitioning() == b.get_optimal_partitioning()
             (sa, _), (sb, _) = a.get_super_reads(), b.get_super_reads()
             assert [[(v.position, v.allele, v.quality) for v in r] for r in sa[0]] == [[(v.position, v.allele, v.quality) for v in r] for r in sb[0]]
+
+
+def _one_individual_pedigree(n):
+    ped = mine.Pedigree(mine.NumericSampleIds())
+    ped.add_individual("sample", [mine.Genotype([0, 1])] * n)
+    return ped
+
+
+def test_flatten_errors_follow_the_reference_order():
+    """The first offending read decides, and within a read the order in which the reference's constructor path
+    would stumble: unknown sample, no variants, unsorted reads, unsorted variants, uncovered ends, bad allele."""
+    rs = string_to_readset("""
+      111
+       101
+    """)
+    ped = _one_individual_pedigree(4)
+    prob, ids = adapters.flatten_objects(rs, [1] * 4, ped)
+    assert ids == [0] and prob.n_cols == 4 and prob.read_off.tolist() == [0, 3, 6] and prob.ent_col.tolist() == [0, 1, 2, 1, 2, 3]
+
+    def with_read(build, **kw):
+        out = mine.ReadSet()
+        for r in rs:
+            out.add(r)
+        read = mine.Read("extra", 50, 0, kw.get("sample", 0))
+        build(read)
+        out.add(read)
+        return out
+
+    cases = [
+        (lambda r: [r.add_variant(20, 0, 1), r.add_variant(30, 1, 1)], dict(sample=7), "Individual with ID 7 not present"),
+        (lambda r: None, {}, "No variants present"),
+        (lambda r: [r.add_variant(10, 0, 1), r.add_variant(30, 1, 1)], {}, "reads in ReadSet are not sorted"),
+        (lambda r: [r.add_variant(30, 0, 1), r.add_variant(20, 1, 1), r.add_variant(40, 1, 1)], {}, "read with unsorted variants"),
+        (lambda r: [r.add_variant(30, 0, 1), r.add_variant(40, 7, 1)], {}, "allele 7 is not 0, 1 or 2"),
+    ]
+    for build, kw, text in cases:
+        with pytest.raises(RuntimeError, match=text):
+            adapters.flatten_objects(with_read(build, **kw), [1] * 4, ped)
+    with pytest.raises(RuntimeError, match="first/last variant position is not among the given positions"):
+        adapters.flatten_objects(rs, [1] * 3, _one_individual_pedigree(3), positions=[10, 20, 30])
+    # interior positions that are not DP columns are dropped (ColumnIterator skips them)
+    rs2 = string_to_readset("""
+      1111
+      1 11
+    """)
+    prob, _ = adapters.flatten_objects(rs2, [1] * 3, _one_individual_pedigree(3), positions=[10, 30, 40])
+    assert prob.read_off.tolist() == [0, 3, 6] and prob.ent_col.tolist() == [0, 1, 2, 0, 1, 2]
+
+
+def test_compiled_bridge_reads_the_same_arrays_as_the_python_api(ref_core, monkeypatch):
+    """integration/whatshap_bridge.pyx (built against the reference tree) against the public-API walk."""
+    import os
+    import time
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "integration"))
+    import build_bridge
+
+    build_bridge.build(os.path.dirname(os.path.dirname(ref_core.__file__)), os.path.dirname(os.path.dirname(ref_core.__file__)))
+    rng = np.random.default_rng(8)
+    rs = ref_core.ReadSet()
+    n_var = 3000
+    for i in range(4000):
+        read = ref_core.Read("r%d" % i, 60, int(rng.integers(0, 2)), 0)
+        start = int(rng.integers(0, n_var - 2))
+        for v in range(start, min(n_var, start + 2 + int(rng.geometric(0.1)))):
+            if v == start or rng.random() > 0.1:
+                read.add_variant(50 + 11 * v, int(rng.integers(0, 3)), int(rng.integers(0, 90)))
+        if len(read) >= 1:
+            rs.add(read)
+    rs.sort()
+    n = len(rs.get_positions())
+    ped = ref_core.Pedigree(ref_core.NumericSampleIds())
+    ped.add_individual("sample", [ref_core.Genotype([0, 1])] * n)
+    assert adapters._bridge_for(rs) is not None, "the bridge was built but cannot be imported"
+    t = time.perf_counter()
+    fast, _ = adapters.flatten_objects(rs, [3] * n, ped)
+    t_fast = time.perf_counter() - t
+    monkeypatch.setattr(adapters, "_bridge_for", lambda readset: None)
+    t = time.perf_counter()
+    slow, _ = adapters.flatten_objects(rs, [3] * n, ped)
+    t_slow = time.perf_counter() - t
+    for field in ("positions", "read_off", "ent_col", "ent_allele", "ent_phred", "read_ind", "recombcost", "gt"):
+        assert np.array_equal(getattr(fast, field), getattr(slow, field)), field
+    print("flatten_objects: compiled bridge %.3f s, public Python API %.3f s" % (t_fast, t_slow))

@@ -92,44 +92,95 @@ def _pedigree_from_str(pedigree):
     return ids, trios, gts, gls
 
 
+def _bridge_for(readset):
+    """The compiled reference-side binding (integration/whatshap_bridge.pyx), if it is importable and
+    `readset` is a genuine `whatshap.core.ReadSet`; else None."""
+    if type(readset).__module__ != "whatshap.core":
+        return None
+    try:  # Cython re-checks every extension type of whatshap.core at import: a patched attribute there makes it refuse
+        import whatshap_bridge
+    except (ImportError, ValueError, TypeError):
+        return None
+    return whatshap_bridge
+
+
+def _readset_to_csr(readset):
+    """(read_off, ent_pos, ent_allele, ent_quality, sample_id, names or None) of any ReadSet-like object."""
+    bridge = _bridge_for(readset)
+    if bridge is not None:  # straight from the C++ objects, no Python object per entry
+        off, pos, allele, quality, sample, _ = bridge.readset_to_csr(readset)
+        return off.astype(np.int64), pos.astype(np.int64), allele.astype(np.int64), quality.astype(np.int64), sample.astype(np.int64), None
+    off, pos, allele, quality, sample, names = [0], [], [], [], [], []
+    for read in readset:
+        for v in read:
+            pos.append(v.position)
+            allele.append(v.allele)
+            quality.append(v.quality)
+        off.append(len(pos))
+        sample.append(read.sample_id)
+        names.append(read.name)
+    as_int = lambda xs: np.array(xs, np.int64)
+    return as_int(off), as_int(pos), as_int(allele), as_int(quality), as_int(sample), names
+
+
 def flatten_objects(readset, recombcost, pedigree, distrust_genotypes: bool = False, positions=None) -> Tuple[FlatProblem, List[int]]:
     """ReadSet / Pedigree objects of `whatshap.core` (or of this package) -> (`whmec_problem` arrays,
-    numeric sample id of every pedigree index)."""
+    numeric sample id of every pedigree index).  Errors of the reference's constructor path are raised with its
+    texts (src/pedigreedptable.cpp:32-34, src/columniterator.cpp:29,32), the first offending read deciding."""
     if hasattr(pedigree, "_rec_individuals"):
         ids, trios, gts, gls = _pedigree_from_recording(pedigree)
     else:
         ids, trios, gts, gls = _pedigree_from_str(pedigree)
-    index_of = {numeric: i for i, numeric in enumerate(ids)}
-    pos_list = list(readset.get_positions()) if positions is None else [int(p) for p in positions]
-    col_of = {p: i for i, p in enumerate(pos_list)}
+    pos_list = np.array(list(readset.get_positions()) if positions is None else [int(p) for p in positions], np.int64)
     n = len(pos_list)
-    read_off, ent_col, ent_allele, ent_phred, read_ind = [0], [], [], [], []
-    prev_first = None
-    for read in readset:
-        if read.sample_id not in index_of:
-            raise RuntimeError("Individual with ID {} not present in pedigree.".format(read.sample_id))
-        read_ind.append(index_of[read.sample_id])
-        variants = list(read)
-        if not variants:
-            raise RuntimeError("No variants present")
-        pos = [v.position for v in variants]
-        if prev_first is not None and pos[0] < prev_first:
-            raise RuntimeError("ColumnIterator: reads in ReadSet are not sorted.")
-        if any(b <= a for a, b in zip(pos, pos[1:])):
-            raise RuntimeError("ColumnIterator: encountered read with unsorted variants.")
-        prev_first = pos[0]
-        if pos[0] not in col_of or pos[-1] not in col_of:
-            raise RuntimeError("read {!r}: first/last variant position is not among the given positions".format(read.name))
-        for v in variants:
-            c = col_of.get(v.position)
-            if c is None:
-                continue
-            if v.allele not in (0, 1, 2):
-                raise RuntimeError("read {!r}: allele {} is not 0, 1 or 2".format(read.name, v.allele))
-            ent_col.append(c)
-            ent_allele.append(v.allele)
-            ent_phred.append(v.quality)
-        read_off.append(len(ent_col))
+    off, ent_pos, ent_allele, ent_quality, sample, names = _readset_to_csr(readset)
+    n_reads = len(off) - 1
+    name_of = lambda r: names[r] if names is not None else readset[int(r)].name
+    lens = np.diff(off)
+    id_arr = np.array(ids, np.int64)
+    id_order = np.argsort(id_arr, kind="stable")
+    slot = np.searchsorted(id_arr[id_order], sample)
+    known = (slot < len(ids)) & (id_arr[id_order][np.minimum(slot, max(len(ids) - 1, 0))] == sample) if len(ids) else np.zeros(n_reads, bool)
+    read_ind = id_order[np.minimum(slot, max(len(ids) - 1, 0))] if len(ids) else np.zeros(n_reads, np.int64)
+    # per-read checks, in the order the reference meets them while walking the reads
+    nonempty = lens > 0
+    first = np.where(nonempty, ent_pos[np.minimum(off[:-1], max(len(ent_pos) - 1, 0))] if len(ent_pos) else 0, 0)
+    last = np.where(nonempty, ent_pos[np.maximum(off[1:] - 1, 0)] if len(ent_pos) else 0, 0)
+    prev_first = np.concatenate([[np.iinfo(np.int64).min], np.maximum.accumulate(first)[:-1]]) if n_reads else first
+    inner_unsorted = np.zeros(n_reads, bool)
+    if len(ent_pos) > 1:
+        step_bad = np.diff(ent_pos) <= 0
+        step_bad[off[1:-1][(off[1:-1] > 0) & (off[1:-1] < len(ent_pos))] - 1] = False  # steps across read boundaries
+        read_of_step = np.repeat(np.arange(n_reads), lens)[:-1]
+        inner_unsorted[np.unique(read_of_step[step_bad])] = True
+    in_positions = lambda p: (np.searchsorted(pos_list, p) < n) & (pos_list[np.minimum(np.searchsorted(pos_list, p), max(n - 1, 0))] == p) if n else np.zeros(len(p), bool)
+    ends_known = in_positions(first) & in_positions(last)
+    bad_allele_entry = (ent_allele < 0) | (ent_allele > 2)
+    ent_in_positions = in_positions(ent_pos)
+    read_of_entry = np.repeat(np.arange(n_reads), lens)
+    bad_allele = np.zeros(n_reads, bool)
+    bad_allele[np.unique(read_of_entry[bad_allele_entry & ent_in_positions])] = True
+    problems = [
+        (~known, lambda r: "Individual with ID {} not present in pedigree.".format(int(sample[r]))),
+        (~nonempty, lambda r: "No variants present"),
+        (first < prev_first, lambda r: "ColumnIterator: reads in ReadSet are not sorted."),
+        (inner_unsorted, lambda r: "ColumnIterator: encountered read with unsorted variants."),
+        (~ends_known, lambda r: "read {!r}: first/last variant position is not among the given positions".format(name_of(r))),
+        (bad_allele, lambda r: "read {!r}: allele {} is not 0, 1 or 2".format(
+            name_of(r), int(ent_allele[off[r]:off[r + 1]][(bad_allele_entry & ent_in_positions)[off[r]:off[r + 1]]][0]))),
+    ]
+    any_bad = np.zeros(n_reads, bool)
+    for mask, _ in problems:
+        any_bad |= mask
+    if any_bad.any():
+        r = int(np.argmax(any_bad))
+        for mask, message in problems:
+            if mask[r]:
+                raise RuntimeError(message(r))
+    keep = ent_in_positions
+    kept_per_read = np.add.reduceat(keep.astype(np.int64), off[:-1]) if n_reads else np.zeros(0, np.int64)
+    read_off = np.concatenate([[0], np.cumsum(kept_per_read)]).astype(np.uint64)
+    ent_col = np.searchsorted(pos_list, ent_pos[keep]).astype(np.uint32)
     n_ind = len(ids)
     rc = [int(x) for x in recombcost]
     if len(rc) < n:
@@ -146,8 +197,8 @@ def flatten_objects(readset, recombcost, pedigree, distrust_genotypes: bool = Fa
                     raise RuntimeError("distrust_genotypes requires genotype likelihoods for every variant")
                 gl[i, k, :] = gls[i][k]
     return FlatProblem(
-        positions=np.array(pos_list, np.uint32), read_off=np.array(read_off, np.uint64), ent_col=np.array(ent_col, np.uint32),
-        ent_allele=np.array(ent_allele, np.uint8), ent_phred=np.array(ent_phred, np.uint32), read_ind=np.array(read_ind, np.uint32),
+        positions=pos_list.astype(np.uint32), read_off=read_off, ent_col=ent_col,
+        ent_allele=ent_allele[keep].astype(np.uint8), ent_phred=ent_quality[keep].astype(np.uint32), read_ind=read_ind.astype(np.uint32),
         recombcost=np.array(rc[:n], np.uint32), n_ind=n_ind, trios=np.array([x for t in trios for x in t], np.uint32),
         distrust=bool(distrust_genotypes), gt=gt, gl=gl,
     ), ids
