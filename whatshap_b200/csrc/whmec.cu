@@ -10,6 +10,7 @@
 #include <malloc.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -568,14 +569,14 @@ struct DevBuf {
 };
 
 void keep_pool_memory(int device) {
-    static bool done[64] = {false};
-    if (device < 0 || device >= 64 || done[device]) return;
+    static std::atomic<bool> done[64];  // zero-initialised; a second thread repeating the call is harmless
+    if (device < 0 || device >= 64 || done[device].load()) return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t threshold = UINT64_MAX;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
-    done[device] = true;
+    done[device].store(true);
 }
 
 }  // namespace
@@ -640,9 +641,8 @@ namespace {
 // returning them to the OS on every free (glibc's default for large blocks) makes each call pay the
 // page faults again.  Keep freed blocks in the process heap instead (opt out: WHMEC_KEEP_HOST_MEMORY=0).
 void keep_host_memory() {
-    static bool done = false;
-    if (done) return;
-    done = true;
+    static std::atomic<bool> done{false};
+    if (done.exchange(true)) return;
     const char *e = std::getenv("WHMEC_KEEP_HOST_MEMORY");
     if (e && e[0] == '0') return;
     mallopt(M_MMAP_THRESHOLD, 1 << 30);
@@ -1157,6 +1157,28 @@ struct CudaGroups {
     void destroy(whmec_plan *h) { delete h; }
 };
 
+// Same driver, one group at a time: nothing of group g stays on the device when group g+1 is created.
+// Used when a whole problem does not fit the HBM budget but its groups of chains do.
+struct SequentialGroups {
+    struct Handle {
+        const whmec_problem *prob;
+    };
+    CudaGroups inner{0};
+    int start(const whmec_problem &q, Handle *&h, std::string &) {
+        h = new Handle{&q};
+        return WHMEC_OK;
+    }
+    int finish(Handle *h, whmec_solution *sub, std::string &msg) {
+        whmec_plan *pl = nullptr;
+        int rc = inner.start(*h->prob, pl, msg);
+        if (rc != WHMEC_OK) return rc;
+        rc = inner.finish(pl, sub, msg);
+        inner.destroy(pl);
+        return rc;
+    }
+    void destroy(Handle *h) { delete h; }
+};
+
 }  // namespace
 
 extern "C" {
@@ -1277,6 +1299,22 @@ int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_sta
     }
     whmec_plan *pl = nullptr;
     int rc = whmec_plan_create(p, device, &pl, err, errlen);
+    if (rc == WHMEC_ERR_UNSUPPORTED && err && std::strstr(err, "exceeds the free HBM")) {
+        // the back-pointers of the whole table do not fit: chains of a single individual are independent problems,
+        // solve them group after group (2, 4, ... groups until a group fits)
+        for (uint32_t G = 2; G <= 1024; G *= 2) {
+            SequentialGroups be;
+            be.inner.device = device;
+            std::string msg;
+            bool handled = false;
+            solve_in_groups(p, s, G, be, msg, &handled);
+            if (handled) {
+                if (st) *st = be.inner.total;
+                if (errlen) err[0] = 0;
+                return WHMEC_OK;
+            }
+        }
+    }
     if (rc != WHMEC_OK) return rc;
     const auto t1 = clk::now();
     rc = whmec_plan_sweep(pl, err, errlen);
