@@ -40,6 +40,7 @@ WORKLOADS = {
     # name: (description, columns, coverage, T)
     "cfg2": ("synthetic diploid ReadSet: 10k variants, max-coverage 15, single individual", 10_000, 15, 1),
     "cfg3": ("synthetic diploid ReadSet: 50k variants, max-coverage 20, 100 independent blocks", 50_000, 20, 1),
+    "cfg3g": ("cfg3 with block lengths ~ Geometric(mean 500) instead of 100 equal blocks (load balance)", 50_000, 20, 1),
     "cfg4": ("synthetic diploid ReadSet: 50k variants, max-coverage 25, one block (2^25 bipartitions)", 50_000, 25, 1),
     "cfg5": ("synthetic trio Pedigree (3 individuals, recombination cost on): 20k variants, coverage 15", 20_000, 15, 4),
 }
@@ -129,6 +130,8 @@ def make_workload(name, cols, rank):
         n = prob.n_cols
         if name == "cfg5":
             prob = trio(n, 5, block_len=500, seed=SEEDS[name] + rank)
+        elif name == "cfg3g":
+            prob = sliding_window(n, 20, block_len=synth.geometric_blocks(n, 500.0, SEEDS[name] + rank), seed=SEEDS[name] + rank)
         else:
             cov = WORKLOADS[name][2]
             prob = sliding_window(n, cov, block_len=(n if name == "cfg4" else 500), seed=SEEDS[name] + rank)
@@ -146,7 +149,7 @@ def cpu_sample(name, prob, target_cols):
     return synth.sliding_window(target_cols, cov, block_len=target_cols, seed=SEEDS[name])
 
 
-CPU_SAMPLE_COLS = {"cfg2": 4000, "cfg3": 160, "cfg4": 6, "cfg5": 1500}
+CPU_SAMPLE_COLS = {"cfg2": 4000, "cfg3": 160, "cfg3g": 160, "cfg4": 6, "cfg5": 1500}
 
 
 def run_cpu_baseline(name, prob):

@@ -77,6 +77,16 @@ def test_tile_kernel_logic_on_golden_vectors(emul, libname):
     assert n_tiled > 40
 
 
+def test_tile_logic_on_ragged_chains(emul, checker):
+    """Chains of very different lengths (block lengths ~ Geometric, the cfg3g shape at small scale): some end
+    after two columns, some span many panels; both tile sizes."""
+    for libname, cov, mean in (("libwhemul.so", 6, 20.0), ("libwhemul_small.so", 7, 12.0), ("libwhemul_small.so", 9, 30.0)):
+        for seed in (1, 2):
+            prob = synth.sliding_window(300, cov, block_len=synth.geometric_blocks(300, mean, seed), seed=seed, gap=0.1 * (seed - 1))
+            got = run_tile(emul[libname], prob, 0)
+            assert got is not None and got.same_as(checker.solve(prob)), (libname, cov, seed)
+
+
 def test_tile_planner_on_benchmark_shapes(emul):
     """Panels per chain and state traffic for the BASELINE.json shapes (planner only, no DP)."""
     lib = emul["libwhemul.so"]
@@ -168,7 +178,7 @@ def test_segment_helpers():
     # right to left: the last segment starts at the optimum (-1) and hands exits[0] on
     assert multigpu.segment_entries([np.array([1, 0]), None, np.array([0, 1]), np.array([1, 1])]) == [1, None, 1, -1]
     assert multigpu.contiguous_shares(np.array([1.0, 1, 1, 1]), 2) == [(0, 2), (2, 4)]
-    assert sorted(multigpu.contiguous_shares(np.array([5.0]), 3)) == [(0, 0), (0, 1), (1, 1)]  # one block: one rank has it
+    assert sorted(multigpu.contiguous_shares(np.array([5.0]), 3)) == [(0, 1), (1, 1), (1, 1)]  # one block: one rank has it
     shares = multigpu.contiguous_shares(np.array([8.0, 1, 1, 1, 1, 4]), 3)
     assert shares[0][0] == 0 and shares[-1][1] == 6 and all(a[1] == b[0] for a, b in zip(shares, shares[1:]))
 

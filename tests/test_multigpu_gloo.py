@@ -88,3 +88,18 @@ def test_block_partition_and_lpt():
     # a read that bridges two blocks fuses them
     prob2 = synth.sliding_window(60, 4, block_len=60, seed=3)
     assert multigpu.independent_blocks(prob2) == [(0, 60)]
+
+
+def test_ragged_blocks_balance_over_ranks():
+    """cfg3g (block lengths ~ Geometric(500)): LPT by DP cells keeps 8 ranks within 1 % of each other,
+    and the best contiguous runs (pedigree segments) are as balanced as ~40 ragged blocks allow."""
+    prob = synth.config("cfg3g", 20000)
+    blocks = multigpu.independent_blocks(prob)
+    lengths = np.array([hi - lo for lo, hi in blocks])
+    assert lengths.sum() == 20000 and lengths.min() >= 2 and lengths.max() > 3 * lengths.mean()
+    work = multigpu.block_work(prob, blocks)
+    for world in (2, 4, 8):
+        loads = np.array([work[s].sum() for s in multigpu.assign_blocks(work, world)])
+        assert loads.max() / loads.mean() < 1.01, (world, loads)
+        runs = np.array([work[a:b].sum() for a, b in multigpu.contiguous_shares(work, world)])
+        assert runs.max() / runs.mean() < (1.05, 1.15, 1.3)[(2, 4, 8).index(world)], (world, runs)

@@ -86,18 +86,30 @@ UMAX = 0xFFFFFFFF
 
 
 def contiguous_shares(work: np.ndarray, world: int) -> List[Tuple[int, int]]:
-    """Cut the block sequence into `world` contiguous runs [b0, b1) of about equal work (a run may be
-    empty when there are fewer blocks than ranks)."""
+    """Cut the block sequence into `world` contiguous runs [b0, b1) minimising the largest run's work
+    (a run may be empty when there are fewer blocks than ranks)."""
+    work = np.asarray(work, np.float64)
     n = len(work)
-    cum = np.concatenate([[0.0], np.cumsum(work, dtype=np.float64)])
-    cuts = [0]
-    for r in range(1, world):
-        want = cum[-1] * r / world
-        b = int(np.searchsorted(cum, want, side="left"))
-        if b > 0 and want - cum[b - 1] < cum[min(b, n)] - want:
-            b -= 1
-        cuts.append(min(max(b, cuts[-1]), n))
-    cuts.append(n)
+
+    def runs_for(limit):  # greedy: fewest runs with no run above `limit`
+        cuts, acc = [0], 0.0
+        for i, w in enumerate(work):
+            if acc > 0 and acc + w > limit:
+                cuts.append(i)
+                acc = 0.0
+            acc += w
+        cuts.append(n)
+        return cuts
+
+    lo, hi = (float(work.max()) if n else 0.0), float(work.sum())
+    for _ in range(60):  # bisection on the largest run (the classic linear-partition bound)
+        mid = (lo + hi) / 2
+        if len(runs_for(mid)) - 1 <= world:
+            hi = mid
+        else:
+            lo = mid
+    cuts = runs_for(hi)
+    cuts += [n] * (world + 1 - len(cuts))  # ranks beyond the last cut hold nothing
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 

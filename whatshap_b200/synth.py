@@ -14,7 +14,7 @@ import numpy as np
 from ._abi import FlatProblem, GT_OTHER
 
 #: seeds fixed by SURVEY.md §8(d)
-SEEDS = {"cfg2": 20250915, "cfg3": 20250920, "cfg4": 20250925, "cfg5": 20250935}
+SEEDS = {"cfg2": 20250915, "cfg3": 20250920, "cfg3g": 20250921, "cfg4": 20250925, "cfg5": 20250935}
 
 
 def _csr_from_spans(first: np.ndarray, last: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
@@ -29,13 +29,34 @@ def _csr_from_spans(first: np.ndarray, last: np.ndarray) -> Tuple[np.ndarray, np
     return off, cols
 
 
-def _window_spans(n: int, c: int, stride: int, block_len: int) -> Tuple[np.ndarray, np.ndarray]:
+def geometric_blocks(n: int, mean: float, seed: int, minimum: int = 2) -> np.ndarray:
+    """Block lengths ~ Geometric(mean) summing to n (the load-balance variant of cfg3)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    lens, total = [], 0
+    while total < n:
+        b = max(minimum, int(rng.geometric(1.0 / mean)))
+        b = min(b, n - total)
+        if n - total - b in range(1, minimum):  # do not leave a stub shorter than `minimum`
+            b = n - total
+        lens.append(b)
+        total += b
+    return np.array(lens, np.int64)
+
+
+def _window_spans(n: int, c: int, stride: int, block_len) -> Tuple[np.ndarray, np.ndarray]:
     """Read spans so that every column has exactly `c` active reads and no read crosses a
-    block boundary.  Reads are ordered by (first column, start), i.e. ReadSet order."""
+    block boundary.  Reads are ordered by (first column, start), i.e. ReadSet order.
+    `block_len`: one length for all blocks, or the sequence of block lengths (summing to n)."""
     L = c * stride
     firsts, lasts = [], []
-    for b0 in range(0, n, block_len):
-        B = min(block_len, n - b0)
+    if np.ndim(block_len) == 0:
+        starts = list(range(0, n, int(block_len)))
+        lengths = [min(int(block_len), n - b0) for b0 in starts]
+    else:
+        lengths = [int(b) for b in block_len]
+        assert sum(lengths) == n, "block lengths must sum to the number of columns"
+        starts = np.concatenate([[0], np.cumsum(lengths)[:-1]]).astype(int).tolist()
+    for b0, B in zip(starts, lengths):
         s = np.arange(-(L - stride), B, stride)
         f = np.maximum(s, 0)
         l = np.minimum(s + L - 1, B - 1)
@@ -51,13 +72,14 @@ def sliding_window(
     n: int,
     c: int,
     stride: int = 1,
-    block_len: int = 500,
+    block_len=500,
     err: float = 0.05,
     seed: int = 0,
     gap: float = 0.0,
     max_phred: int = 40,
 ) -> FlatProblem:
-    """Single diploid individual, all sites heterozygous (trusted), coverage exactly `c`."""
+    """Single diploid individual, all sites heterozygous (trusted), coverage exactly `c` (fewer where a
+    block is shorter than a read)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     first, last = _window_spans(n, c, stride, block_len)
     off, cols = _csr_from_spans(first, last)
@@ -155,11 +177,14 @@ def trio(
 
 
 def config(name: str, n: Optional[int] = None) -> FlatProblem:
-    """The four GPU configurations of BASELINE.json (cfg2..cfg5); `n` overrides the column count."""
+    """The four GPU configurations of BASELINE.json (cfg2..cfg5) and the ragged variant of cfg3; `n` overrides the column count."""
     if name == "cfg2":
         return sliding_window(n or 10_000, 15, block_len=500, seed=SEEDS[name])
     if name == "cfg3":
         return sliding_window(n or 50_000, 20, block_len=500, seed=SEEDS[name])
+    if name == "cfg3g":  # cfg3 with block lengths ~ Geometric(mean 500): load balance over SMs and GPUs (SURVEY.md 8(d))
+        nn = n or 50_000
+        return sliding_window(nn, 20, block_len=geometric_blocks(nn, 500.0, SEEDS[name]), seed=SEEDS[name])
     if name == "cfg4":
         nn = n or 50_000
         return sliding_window(nn, 25, block_len=nn, seed=SEEDS[name])
