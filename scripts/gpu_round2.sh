@@ -1,0 +1,21 @@
+#!/bin/bash
+# First GPU call of the next round (single B200, ~4 min): everything that was written in round 1 after the
+# GPU minutes ran out, plus the usual gates.  Run:  gpurun --timeout 900 -- 'bash scripts/gpu_round2.sh'
+set -x
+mkdir -p gpurun_out
+timeout 700 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
+# group-wise pipeline of whmec_solve (csrc/grouped.h): bit-equality with the ordinary solve + end-to-end times
+timeout 300 python scripts/gpu_grouped_check.py 2>&1 | tail -12 | tee gpurun_out/grouped_check.log
+# headline bench with and without the pipeline (look at "e2e")
+timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
+WHMEC_SOLVE_GROUPS=4 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_groups4.json 2> gpurun_out/bench_cfg3_groups4.err
+# ragged blocks (load balance over the persistent tile grid)
+timeout 300 python bench.py --workload cfg3g --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3g.json 2> gpurun_out/bench_cfg3g.err
+for f in gpurun_out/bench_cfg3.json gpurun_out/bench_cfg3_groups4.json gpurun_out/bench_cfg3g.json; do
+  python - "$f" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print(sys.argv[1], "value %.0f" % d["value"], "ms/step %.2f" % d["ms_per_step"], "e2e %.0f (%.1f ms)" % (d["e2e"]["value"], d["e2e"]["ms_per_step"]))
+PY
+done
