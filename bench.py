@@ -120,6 +120,18 @@ def recorded_traffic(workload):
     return None, None
 
 
+def recorded_issue(workload, cells_per_launch):
+    """Instruction-issue view of the same ncu capture: the DP kernels are bound by integer issue, not by HBM."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        rec = json.load(open(path)).get(workload)
+        if rec and "warp_inst_executed" in rec:
+            return {"issue_active_pct_of_peak": rec["issue_active_pct"], "warp_instructions_per_launch": rec["warp_inst_executed"],
+                    "thread_instructions_per_dp_cell": 32.0 * rec["warp_inst_executed"] / max(cells_per_launch, 1.0),
+                    "source": rec["report"], "note": "ncu capture of one launch of the dominant kernel; 100 % = one warp instruction per scheduler per cycle"}
+    return None
+
+
 def make_workload(name, cols, rank):
     from whatshap_b200 import synth
 
@@ -318,7 +330,7 @@ def main():
             "config": {
                 "workload": name, "description": WORKLOADS[name][0], "columns_per_gpu": n_cols,
                 "coverage": WORKLOADS[name][2], "transmission_vectors": WORKLOADS[name][3],
-                "chains": int(stats["n_chains"]), "kernel_path": {1: "tile", 2: "column"}.get(int(stats["path_kind"]), "mixed"),
+                "chains": int(stats["n_chains"]), "kernel_path": {1: "tile", 2: "column", 3: "column (batched pedigree sweep)"}.get(int(stats["path_kind"]), "mixed"),
                 "l2": "512 MiB buffer rewritten between timed steps (L2 flush)", "sharding": "one full-size workload per GPU, no collective on the data path",
                 "optimal_cost_rank0": int(sol.cost), "wall_s_timed_region": wall,
             },
@@ -326,7 +338,8 @@ def main():
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(name)[0], "traffic_source": recorded_traffic(name)[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stats["algorithmic_bytes"] / max(launches, 1),
-                "kernel": "tile_panel_kernel" if int(stats["path_kind"]) == 1 else "col_direct_kernel",
+                "kernel": {1: "tile_panel_kernel", 2: "col_direct_kernel", 3: "col_batched_kernel"}.get(int(stats["path_kind"]), "col_direct_kernel"),
+                "issue": recorded_issue(name, stats["cells"] / max(launches, 1)),
                 "algorithmic_bytes_per_step": int(stats["algorithmic_bytes"]), "launches_per_step": launches,
                 "bytes_moved_per_step": {"backpointers": int(stats["backptr_bytes"]), "state": int(stats["state_bytes"])},
                 "note": ("algorithmic bytes follow the reference's data layout (u32 projection read + u32 value and u32 back-pointer "

@@ -53,8 +53,12 @@ def main(prefix):
             total = float(r[rd]) * UNIT[units[rd]] + float(r[wr]) * UNIT[units[wr]]
             lines.append(f"dram bytes per launch (read+write): {total:.0f}")
             wl = name[len(prefix):].split(".")[0].split("_")[-1]
-            traffic[wl] = {"bytes_per_launch": total, "kernel": "tile_panel_kernel", "report": name,
-                           "grid": int(r[hdr.index('launch__grid_size')]), "duration_us": float(r[hdr.index('gpu__time_duration.sum')])}
+            kernel = r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].strip()
+            num = lambda key: float(r[hdr.index(key)])
+            traffic[wl] = {"bytes_per_launch": total, "kernel": kernel, "report": name,
+                           "grid": int(num("launch__grid_size")), "duration_us": num("gpu__time_duration.sum"),
+                           "warp_inst_executed": num("smsp__inst_executed.sum"), "sm_cycles_elapsed": num("sm__cycles_elapsed.max"),
+                           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active")}
         open(os.path.join(ROOT, "profiles", name.replace(".ncu-rep", ".txt")), "w").write("\n".join(lines) + "\n")
         print("\n".join(lines))
     json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)
