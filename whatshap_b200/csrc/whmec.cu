@@ -372,6 +372,111 @@ __global__ void __launch_bounds__(256) col_multi_kernel(const PedStep *__restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused pedigree sweep, one thread block per chain (EXPERIMENTAL, WHMEC_PED_CHAIN=1).
+// The batched sweep above issues one launch per column step and keeps the projection in global memory; at
+// pedigree sizes (cfg5: 16 K entries per column) that is bound by launch latency and by every block
+// re-staging the column.  Here a block of 1024 threads owns one (chain, input) instance and walks all its
+// columns: the projection (raw values R, transition minima M + their argmins A) lives in shared memory,
+// the column is staged once, only back-pointers and the chain's final T values go to HBM.  Same per-entry
+// code (eval_candidates, transition_min) and same back-pointer layout as the other column kernels, so the
+// backtrace kernels are unchanged.
+//   unit == 1: instance (chain c, unit vector u) = block c*T + u, values only, row u of the chain's transfer
+//              matrix -> out_vecs[(c*T + u)*T ..];   unit == 0: block c, true input in_vecs[c*T ..], back-pointers.
+// ------------------------------------------------------------------------------------------
+struct PedChainArgs {
+    const ColMeta *cols;
+    const uint32_t *chain_begin, *fn_c0, *fn_group;
+    const int32_t *fn_delta;
+    uint32_t *arena;
+    const uint32_t *in_vecs;
+    uint32_t *out_vecs;
+    uint32_t T, tb, max_ent, unit;
+};
+
+constexpr uint32_t PED_CHAIN_THREADS = 1024;
+
+__global__ void __launch_bounds__(PED_CHAIN_THREADS) ped_chain_kernel(const PedChainArgs a) {
+    extern __shared__ __align__(16) uint32_t ped_dyn[];
+    __shared__ ColShared S;
+    const uint32_t T = a.T, tb = a.tb, tid = threadIdx.x;
+    uint32_t *R = ped_dyn;                                              // raw values of the current column
+    uint32_t *M = R + a.max_ent;                                        // transition minima handed to the next column
+    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(M + a.max_ent);  // partial minima of small columns
+    uint32_t *invec = reinterpret_cast<uint32_t *>(skeys + PED_CHAIN_THREADS);          // the chain's input vector
+    uint8_t *A = reinterpret_cast<uint8_t *>(invec + MAX_T);            // argmins of M
+    const uint32_t c = a.unit ? blockIdx.x / T : blockIdx.x, u = blockIdx.x % T;
+    const uint32_t k0 = a.chain_begin[c], k1 = a.chain_begin[c + 1];
+    if (tid < T) invec[tid] = a.unit ? (tid == u ? 0u : UMAX) : a.in_vecs[(size_t)c * T + tid];
+    bool have_m = false;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const ColMeta &cm = a.cols[k];
+        __syncthreads();  // the previous column is complete (R, M, A) and S may be overwritten
+        stage_column(S, cm, a.fn_group[cm.grp_off + T], T, a.fn_c0, a.fn_delta, a.fn_group);
+        const uint32_t d = S.m.d;
+        const uint32_t nent = (1u << S.m.f) * T;
+        uint32_t lc = 0;  // lanes per entry: small columns (chain ends) spread an entry's 2^d candidates over threads
+        while ((nent << lc) < PED_CHAIN_THREADS && lc < d) ++lc;
+        const uint32_t total = nent << lc, per = 1u << (d - lc);
+        if (lc) {
+            for (uint32_t e = tid; e < nent; e += PED_CHAIN_THREADS) skeys[e] = KEY_INF;
+            __syncthreads();
+        }
+        const bool write_bp = !a.unit;
+        const uint32_t *prev = have_m ? M : invec;
+        const uint8_t *prevarg = have_m ? A : nullptr;
+        for (uint32_t base = 0; base < total; base += PED_CHAIN_THREADS) {
+            const uint32_t g = base + tid, e = g >> lc, chunk = g & ((1u << lc) - 1u);
+            unsigned long long key = KEY_INF;
+            if (g < total) {
+                const uint32_t o = e >> tb, i = e & (T - 1);
+                ColView v = make_view(S, T, tb, a.fn_c0, a.fn_delta, prev, i, prevarg);
+                key = eval_candidates(v, o, i, chunk * per, (chunk + 1) * per);
+            }
+            if (lc) {
+                if (g < total) atomicMin(&skeys[e], key);
+            } else {
+                if (g < total) R[e] = (uint32_t)(key >> 32);
+                if (write_bp) bp_store_warp(a.arena, S.m.bp_off, S.m.bp_width, e, (uint32_t)key & low_mask(d + tb), g < total);
+            }
+        }
+        if (lc) {
+            __syncthreads();
+            for (uint32_t base = 0; base < nent; base += PED_CHAIN_THREADS) {
+                const uint32_t e = base + tid;
+                const unsigned long long key = e < nent ? skeys[e] : KEY_INF;
+                if (e < nent) R[e] = (uint32_t)(key >> 32);
+                if (write_bp) bp_store_warp(a.arena, S.m.bp_off, S.m.bp_width, e, (uint32_t)key & low_mask(d + tb), e < nent);
+            }
+        }
+        __syncthreads();
+        if (k + 1 < k1) {  // hand the next column min_j(value_j + popcount(i^j) * rc) and its argmin
+            const uint32_t rc_next = a.cols[k + 1].rc;
+            for (uint32_t e = tid; e < nent; e += PED_CHAIN_THREADS) {
+                uint32_t arg;
+                M[e] = transition_min(&R[e & ~(T - 1)], T, e & (T - 1), rc_next, &arg);
+                A[e] = (uint8_t)arg;
+            }
+            have_m = true;
+        }
+    }
+    __syncthreads();
+    if (tid < T) a.out_vecs[(size_t)blockIdx.x * T + tid] = R[tid];  // a chain ends with f == 0: T raw values
+}
+
+// true input vector of every chain from the chains' transfer matrices (compact form of ped_prefix_kernel)
+__global__ void ped_chain_prefix_kernel(const uint32_t *__restrict__ matrices, uint32_t T, uint32_t n_chains,
+                                        uint32_t *__restrict__ in_vecs) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t in[MAX_T];
+    for (uint32_t i = 0; i < T; ++i) in[i] = matrices[i];  // chain 0 starts the table: every row is its true output
+    fold_chains(
+        T, 1, n_chains, in, [&](uint32_t c, uint32_t u) { return matrices + ((size_t)c * T + u) * T; },
+        [&](uint32_t c, const uint32_t *cur) {
+            for (uint32_t i = 0; i < T; ++i) in_vecs[(size_t)c * T + i] = cur[i];
+        });
+}
+
 // pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
 // arithmetic (a few hundred operations per row).
 //   pass-1 planes: chain c, unit vector u -> slot c*T + u;  pass-2 slot of chain c: n_chains*T + c.
@@ -612,6 +717,10 @@ struct whmec_plan {
     bool transferred = false;
     int exits_mode = 0;  // 0: not computed since the last sweep; 1: last chain entered at the optimum; 2: like any chain
     DevBuf<uint32_t> d_in_vec, d_matrix, d_bt_exits, d_bt_entries;
+    // fused per-chain pedigree sweep (ped_chain_kernel, experimental)
+    bool use_ped_chain = false;
+    DevBuf<uint32_t> d_chain_matrices, d_chain_in, d_chain_out;
+    size_t ped_chain_smem = 0;
     uint32_t sweeps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
     // tile path
@@ -624,6 +733,7 @@ struct whmec_plan {
         d_result.release(); d_fn_delta.release(); d_keys.release();
         d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release(); d_ped_args.release();
         d_in_vec.release(); d_matrix.release(); d_bt_exits.release(); d_bt_entries.release();
+        d_chain_matrices.release(); d_chain_in.release(); d_chain_out.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
@@ -803,6 +913,20 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                 pl->stats.path_kind = 3;
             }
         }
+        if (const char *pc = std::getenv("WHMEC_PED_CHAIN")) {
+            // experimental: one block per chain with the projection in shared memory (ped_chain_kernel)
+            const size_t smem = (size_t)max_ent * 9 + PED_CHAIN_THREADS * 8 + MAX_T * 4;
+            if (pc[0] == '1' && pl->use_ped_batch && !segment && max_ent <= 16384 && pk.T <= 16) {
+                CUDA_TRY(pl->d_chain_matrices.alloc((size_t)C * pk.T * pk.T, pl->stream));
+                CUDA_TRY(pl->d_chain_in.alloc((size_t)C * pk.T, pl->stream));
+                CUDA_TRY(pl->d_chain_out.alloc((size_t)C * pk.T, pl->stream));
+                CUDA_TRY(cudaFuncSetAttribute(ped_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pl->ped_chain_smem = smem;
+                pl->ped_max_ent = max_ent;
+                pl->use_ped_chain = true;
+                pl->d_last_vals = pl->d_chain_out.p + (size_t)(C - 1) * pk.T;
+            }
+        }
         if (segment && !pl->use_ped_batch) {
             msg = "unsupported: this segment cannot run the two-pass pedigree sweep (costs beyond 2^28 or state beyond the budget)";
             return WHMEC_ERR_UNSUPPORTED;
@@ -867,7 +991,29 @@ int ped_prefix(whmec_plan *pl, const uint32_t *d_in_vec, uint32_t &launches, std
     return WHMEC_OK;
 }
 
+// three launches for the whole table: unit inputs of every chain, prefix, true inputs
+int ped_chain_sweep(whmec_plan *pl, std::string &msg) {
+    const Packed &pk = pl->pk;
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1, T = pk.T;
+    PedChainArgs a{pl->d_cols.p, pl->d_chain_begin.p, pl->d_fn_c0.p, pl->d_fn_group.p, pl->d_fn_delta.p, pl->d_arena.p,
+                   pl->d_chain_in.p, pl->d_chain_matrices.p, T, pk.tb, (uint32_t)pl->ped_max_ent, 1u};
+    uint32_t launches = 0;
+    if (C > 1) {
+        ped_chain_kernel<<<C * T, PED_CHAIN_THREADS, pl->ped_chain_smem, pl->stream>>>(a);
+        ped_chain_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_chain_matrices.p, T, C, pl->d_chain_in.p);
+        launches += 2;
+    }
+    a.unit = 0;
+    a.out_vecs = pl->d_chain_out.p;
+    ped_chain_kernel<<<C, PED_CHAIN_THREADS, pl->ped_chain_smem, pl->stream>>>(a);
+    ++launches;
+    CUDA_TRY(cudaGetLastError());
+    pl->stats.kernel_launches = launches;
+    return WHMEC_OK;
+}
+
 int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
+    if (pl->use_ped_chain) return ped_chain_sweep(pl, msg);
     uint32_t launches = 0;
     int rc = ped_pass(pl, 0, launches, msg);
     if (rc == WHMEC_OK) rc = ped_prefix(pl, nullptr, launches, msg);
