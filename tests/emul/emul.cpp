@@ -5,6 +5,7 @@
 // oracle in the GPU-less authoring container.  It is built into tests/emul/libwhemul.so by
 // tests/emul/Makefile, loaded only by tests/test_emulation.py, and is NOT a fallback: the product
 // library (whatshap_b200/csrc) contains no CPU execution path.
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -260,6 +261,103 @@ extern "C" int whemul_segment_finish(whemul_segment *sg, int entry, whmec_soluti
     }
     s->cost = total;
     int rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+    return WHMEC_OK;
+}
+
+// ---- host mirror of ped_chain_kernel (csrc/whmec.cu, WHMEC_PED_CHAIN): the same phases in the same order, every
+// ---- phase run for all 1024 "threads" one after the other; checks the scheme (lanes per entry, merge of partial
+// ---- keys, buffers R / M / A, unit instances + prefix + true instances), not the CUDA glue itself
+namespace {
+constexpr uint32_t CHAIN_THREADS = 1024;
+
+void chain_instance(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool write_bp, std::vector<uint32_t> &arena, uint32_t *out_vec) {
+    const uint32_t T = pk.T, tb = pk.tb;
+    const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1];
+    uint64_t max_ent = 1;
+    for (uint32_t k = k0; k < k1; ++k) max_ent = std::max<uint64_t>(max_ent, ((uint64_t)1 << pk.cols[k].f) * T);
+    std::vector<uint32_t> R(max_ent), M(max_ent), invec(in_vec, in_vec + T);
+    std::vector<uint8_t> A(max_ent);
+    std::vector<uint64_t> skeys(CHAIN_THREADS);
+    bool have_m = false;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const ColMeta &m = pk.cols[k];
+        const uint32_t d = m.d, nent = (1u << m.f) * T;
+        uint32_t lc = 0;
+        while ((nent << lc) < CHAIN_THREADS && lc < d) ++lc;
+        const uint32_t total = nent << lc, per = 1u << (d - lc);
+        if (lc) std::fill(skeys.begin(), skeys.begin() + nent, KEY_INF);
+        const uint32_t *prev = have_m ? M.data() : invec.data();
+        for (uint32_t base = 0; base < total; base += CHAIN_THREADS)
+            for (uint32_t tid = 0; tid < CHAIN_THREADS; ++tid) {
+                const uint32_t g = base + tid, e = g >> lc, chunk = g & ((1u << lc) - 1u);
+                if (g >= total) continue;
+                ColView v;
+                const uint32_t i = e & (T - 1), o = e >> tb;
+                const uint32_t g0 = pk.fn_group[m.grp_off + i], g1 = pk.fn_group[m.grp_off + i + 1];
+                v.m = &m; v.T = T; v.tb = tb;
+                v.fn_c0 = pk.fn_c0.data() + m.fn_off + g0;
+                v.fn_delta = pk.fn_delta.data() + (size_t)(m.fn_off + g0) * FN_STRIDE;
+                v.nf = g1 - g0;
+                v.prev = prev;
+                v.tab = nullptr; v.tab_fn0 = g0;
+                v.prevm = have_m ? M.data() : nullptr;
+                v.prevarg = have_m ? A.data() : nullptr;
+                const uint64_t key = eval_candidates(v, o, i, chunk * per, (chunk + 1) * per);
+                if (lc) {
+                    skeys[e] = std::min(skeys[e], key);
+                } else {
+                    R[e] = (uint32_t)(key >> 32);
+                    if (write_bp) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e, (uint32_t)key & low_mask(d + tb));
+                }
+            }
+        if (lc)
+            for (uint32_t e = 0; e < nent; ++e) {
+                R[e] = (uint32_t)(skeys[e] >> 32);
+                if (write_bp) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e, (uint32_t)skeys[e] & low_mask(d + tb));
+            }
+        if (k + 1 < k1) {
+            for (uint32_t e = 0; e < nent; ++e) {
+                uint32_t arg;
+                M[e] = transition_min(&R[e & ~(T - 1)], T, e & (T - 1), pk.cols[k + 1].rc, &arg);
+                A[e] = (uint8_t)arg;
+            }
+            have_m = true;
+        }
+    }
+    std::memcpy(out_vec, R.data(), (size_t)T * 4);
+}
+}  // namespace
+
+extern "C" int whemul_ped_chain_solve(const whmec_problem *p, whmec_solution *s, char *err, size_t errlen) {
+    Packed pk;
+    std::string msg;
+    int rc = pack_problem(p, pk, msg);
+    if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
+    const uint32_t n = pk.n, T = pk.T;
+    if (n == 0 || T == 1 || !pk.safe31) return fail_with("not a pedigree problem for the chain kernel", err, errlen, 100);
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+    std::vector<uint32_t> arena(pk.bp_words + 1, 0), matrices((size_t)C * T * T), in_vecs((size_t)C * T, 0), out_vecs((size_t)C * T);
+    if (C > 1) {
+        for (uint32_t c = 0; c < C; ++c)
+            for (uint32_t u = 0; u < T; ++u) {
+                std::vector<uint32_t> unit(T, UMAX);
+                unit[u] = 0;
+                chain_instance(pk, c, unit.data(), false, arena, &matrices[((size_t)c * T + u) * T]);
+            }
+        uint32_t in[MAX_T];
+        for (uint32_t i = 0; i < T; ++i) in[i] = matrices[i];
+        fold_chains(T, 1, C, in, [&](uint32_t c, uint32_t u) { return &matrices[((size_t)c * T + u) * T]; },
+                    [&](uint32_t c, const uint32_t *cur) { std::memcpy(&in_vecs[(size_t)c * T], cur, (size_t)T * 4); });
+    }
+    for (uint32_t c = 0; c < C; ++c) chain_instance(pk, c, &in_vecs[(size_t)c * T], true, arena, &out_vecs[(size_t)c * T]);
+    std::vector<uint32_t> pidx(n), ptv(n);
+    BtView bv{pk.cols.data(), arena.data(), T, pk.tb};
+    uint32_t cost, x, tv, ptvv;
+    pick_optimum(pk.cols[n - 1], &out_vecs[(size_t)(C - 1) * T], arena.data(), T, pk.tb, &cost, &x, &tv, &ptvv);
+    backtrace_range(bv, n - 1, 0, x, tv, ptvv, pidx.data(), ptv.data());
+    s->cost = cost;
+    rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
     return WHMEC_OK;
 }

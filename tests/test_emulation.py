@@ -219,3 +219,42 @@ def test_groups_of_chains_reproduce_the_whole_solve(emul, checker):
     assert n_groups == 4 and got.same_as(checker.solve(prob))
     assert _grouped(lib, synth.trio(60, 2, block_len=10, seed=1), 2, 0)[0] is None      # transmission values couple the chains
     assert _grouped(lib, synth.sliding_window(60, 5, block_len=30, seed=1), 2, 1)[0] is None  # two chains: not worth cutting
+
+
+def test_per_chain_pedigree_scheme(emul, checker):
+    """Host mirror of the experimental fused pedigree sweep (ped_chain_kernel, WHMEC_PED_CHAIN): unit instances per chain
+    -> transfer matrices -> prefix -> true instances, lanes-per-entry splitting with key merging on small columns,
+    transition minima handed over inside a chain; must equal the reference on golden and random pedigrees."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_ped_chain_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_char_p, C.c_size_t]
+
+    def run(prob):
+        sol = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+        cp, cs, err = prob.as_c(), sol.as_c(), C.create_string_buffer(256)
+        rc = lib.whemul_ped_chain_solve(C.byref(cp), C.byref(cs), err, len(err))
+        if rc == 100:
+            return None
+        raise_for(rc, err.value.decode())
+        sol.cost = int(cs.cost)
+        return sol
+
+    n = 0
+    for group in golden_io.GROUPS:
+        for label, prob, want, error in golden_io.load(group):
+            if prob.n_trios == 0 or want is None:
+                continue
+            got = run(prob)
+            if got is not None:
+                assert got.same_as(want), (label, got.diff(want))
+                n += 1
+    assert n >= 40
+    rng = np.random.default_rng(23)
+    for it in range(60):
+        prob = synth.random_problem(rng, int(rng.integers(4, 30)), int(rng.integers(2, 8)), pedigree=["trio", "quartet", "three_generations"][it % 3],
+                                    distrust=it % 3 == 0, mean_len=float(rng.choice([1.5, 4.0, 8.0])))
+        try:
+            want = checker.solve(prob)
+        except RuntimeError:
+            continue
+        got = run(prob)
+        assert got is None or got.same_as(want), (it, got.diff(want))
