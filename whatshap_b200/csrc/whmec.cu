@@ -15,6 +15,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -1270,13 +1273,11 @@ struct CudaGroups {
     whmec_stats total{};
     uint32_t groups = 0;
     int start(const whmec_problem &q, whmec_plan *&h, std::string &msg) {
-        h = new whmec_plan();
-        int rc = plan_create_impl(&q, device, h, msg);
-        if (rc == WHMEC_OK) rc = plan_sweep_impl(h, msg, false);
-        if (rc != WHMEC_OK) {
-            delete h;
-            h = nullptr;
-        }
+        h = nullptr;
+        std::unique_ptr<whmec_plan> pl(new whmec_plan());
+        int rc = plan_create_impl(&q, device, pl.get(), msg);
+        if (rc == WHMEC_OK) rc = plan_sweep_impl(pl.get(), msg, false);
+        if (rc == WHMEC_OK) h = pl.release();
         return rc;
     }
     int finish(whmec_plan *h, whmec_solution *sub, std::string &msg) {
@@ -1327,6 +1328,21 @@ struct SequentialGroups {
 
 }  // namespace
 
+// No C++ exception may cross the C ABI (a failed host allocation inside the packer or planner would otherwise
+// unwind into the caller's C / ctypes frame): entry points that allocate run their body through this.
+template <class Body>
+int guarded(char *err, size_t errlen, Body body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc &) {
+        set_err(err, errlen, "out of host memory");
+        return WHMEC_ERR_UNSUPPORTED;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, std::string("internal error: ") + e.what());
+        return WHMEC_ERR_INPUT;
+    }
+}
+
 extern "C" {
 
 int whmec_abi_version(void) { return WHMEC_ABI_VERSION; }
@@ -1340,31 +1356,36 @@ int whmec_device_count(void) {
 }
 
 int whmec_plan_create(const whmec_problem *p, int device, whmec_plan **out, char *err, size_t errlen) {
-    std::string msg;
-    whmec_plan *pl = new whmec_plan();
-    int rc = plan_create_impl(p, device, pl, msg);
-    if (rc != WHMEC_OK) {
-        set_err(err, errlen, msg);
-        delete pl;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
         *out = nullptr;
-        return rc;
-    }
-    *out = pl;
-    return WHMEC_OK;
+        std::unique_ptr<whmec_plan> pl(new whmec_plan());  // released (device buffers too) if anything below throws
+        const int rc = plan_create_impl(p, device, pl.get(), msg);
+        if (rc != WHMEC_OK) {
+            set_err(err, errlen, msg);
+            return rc;
+        }
+        *out = pl.release();
+        return WHMEC_OK;
+    });
 }
 
 int whmec_plan_sweep(whmec_plan *plan, char *err, size_t errlen) {
-    std::string msg;
-    int rc = plan_sweep_impl(plan, msg);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = plan_sweep_impl(plan, msg);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
 int whmec_plan_finish(whmec_plan *plan, whmec_solution *s, char *err, size_t errlen) {
-    std::string msg;
-    int rc = plan_finish_impl(plan, s, msg);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = plan_finish_impl(plan, s, msg);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
 int whmec_plan_stats(const whmec_plan *plan, whmec_stats *st) {
@@ -1375,53 +1396,62 @@ int whmec_plan_stats(const whmec_plan *plan, whmec_stats *st) {
 void whmec_plan_destroy(whmec_plan *plan) { delete plan; }
 
 int whmec_segment_create(const whmec_problem *p, int device, int continues, whmec_plan **out, char *err, size_t errlen) {
-    std::string msg;
-    whmec_plan *pl = new whmec_plan();
-    int rc = plan_create_impl(p, device, pl, msg, continues ? 2 : 1);
-    if (rc != WHMEC_OK) {
-        set_err(err, errlen, msg);
-        delete pl;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
         *out = nullptr;
-        return rc;
-    }
-    *out = pl;
-    return WHMEC_OK;
+        std::unique_ptr<whmec_plan> pl(new whmec_plan());
+        const int rc = plan_create_impl(p, device, pl.get(), msg, continues ? 2 : 1);
+        if (rc != WHMEC_OK) {
+            set_err(err, errlen, msg);
+            return rc;
+        }
+        *out = pl.release();
+        return WHMEC_OK;
+    });
 }
 
 int whmec_segment_transfer(whmec_plan *plan, uint32_t *matrix, char *err, size_t errlen) {
-    std::string msg;
-    int rc = segment_transfer_impl(plan, matrix, msg);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = segment_transfer_impl(plan, matrix, msg);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
 int whmec_segment_sweep(whmec_plan *plan, const uint32_t *in_vec, uint32_t *out_vec, char *err, size_t errlen) {
-    std::string msg;
-    int rc = segment_sweep_impl(plan, in_vec, out_vec, msg);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = segment_sweep_impl(plan, in_vec, out_vec, msg);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
 int whmec_segment_exits(whmec_plan *plan, int is_last, uint32_t *exits, char *err, size_t errlen) {
-    std::string msg;
-    int rc = segment_exits_impl(plan, is_last, exits, msg);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = segment_exits_impl(plan, is_last, exits, msg);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
 int whmec_segment_finish(whmec_plan *plan, int entry, whmec_solution *s, char *err, size_t errlen) {
-    std::string msg;
-    int rc = segment_check(plan, msg);
-    if (rc == WHMEC_OK && entry >= (int)plan->pk.T) {
-        msg = "entry transmission value out of range";
-        rc = WHMEC_ERR_INPUT;
-    }
-    if (rc == WHMEC_OK) rc = plan_finish_impl(plan, s, msg, entry);
-    if (rc != WHMEC_OK) set_err(err, errlen, msg);
-    return rc;
+    return guarded(err, errlen, [&]() -> int {
+        std::string msg;
+        int rc = segment_check(plan, msg);
+        if (rc == WHMEC_OK && entry >= (int)plan->pk.T) {
+            msg = "entry transmission value out of range";
+            rc = WHMEC_ERR_INPUT;
+        }
+        if (rc == WHMEC_OK) rc = plan_finish_impl(plan, s, msg, entry);
+        if (rc != WHMEC_OK) set_err(err, errlen, msg);
+        return rc;
+    });
 }
 
-int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st, char *err, size_t errlen) {
+static int solve_impl(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st, char *err, size_t errlen) {
     using clk = std::chrono::steady_clock;
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     auto ms = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -1474,6 +1504,10 @@ int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_sta
         std::fprintf(stderr, "[whmec] solve: create %.2f ms (h2d %.2f), sweep %.2f ms (device %.2f), finish %.2f ms (device %.2f), destroy %.2f ms\n",
                      ms(t0, t1), (double)stats.h2d_ms, ms(t1, t2), (double)stats.sweep_ms, ms(t2, t3), (double)stats.d2h_ms, ms(t3, clk::now()));
     return rc;
+}
+
+int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st, char *err, size_t errlen) {
+    return guarded(err, errlen, [&]() -> int { return solve_impl(p, s, device, st, err, errlen); });
 }
 
 }  // extern "C"
