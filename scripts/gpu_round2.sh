@@ -9,6 +9,8 @@ timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 timeout 300 python scripts/gpu_grouped_check.py 2>&1 | tail -12 | tee gpurun_out/grouped_check.log
 # fused per-chain pedigree sweep (ped_chain_kernel): bit-equality + sweep time against the batched sweep
 timeout 300 python scripts/gpu_ped_chain_check.py 2>&1 | tail -8 | tee gpurun_out/ped_chain_check.log
+# extremes of the value range / pedigree size on the CUDA path
+timeout 300 python scripts/gpu_extremes_check.py 2>&1 | tail -20 | tee gpurun_out/extremes_check.log
 # headline bench with and without the pipeline (look at "e2e")
 timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
 WHMEC_SOLVE_GROUPS=4 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_groups4.json 2> gpurun_out/bench_cfg3_groups4.err

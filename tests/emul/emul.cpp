@@ -80,7 +80,8 @@ int sweep_columns(const Packed &pk, uint32_t k0, uint32_t k1, uint32_t chunk, st
         prev.swap(cur);
         // every third hand-over keeps raw values, the others pre-apply the transition minimum of the next
         // column (as the batched pedigree kernels do in their epilogue)
-        have_xform = (k + 1 < k1) && (k % 3 != 2);
+        // (only when sums cannot wrap: the product uses transition minima on the batched path, which requires pk.safe31)
+        have_xform = pk.safe31 && (k + 1 < k1) && (k % 3 != 2);
         if (have_xform) {
             prevm.assign(nout * T, UMAX);
             prevarg.assign(nout * T, 0);

@@ -258,3 +258,43 @@ def test_per_chain_pedigree_scheme(emul, checker):
             continue
         got = run(prob)
         assert got is None or got.same_as(want), (it, got.diff(want))
+
+
+# ---- extremes of the value range and of the pedigree size (column path; SURVEY.md Appendix A: u32 arithmetic wraps) ----
+def _extreme_problems():
+    rng = np.random.default_rng(3)
+    for max_phred in (10**6, 2**26, 2**30, 2**31 + 5):  # totals beyond 2^28 switch off every shortcut that assumes no wrap-around
+        yield f"single max_phred={max_phred}", synth.random_problem(rng, 14, 5, pedigree="single", max_phred=max_phred)
+        yield f"trio max_phred={max_phred}", synth.random_problem(rng, 10, 4, pedigree="trio", max_phred=max_phred)
+    for rc in (2**31 - 1, 2**32 - 1):  # popcount * recombcost wraps
+        prob = synth.random_problem(rng, 12, 4, pedigree="trio")
+        prob.recombcost = np.full(prob.n_cols, rc, np.uint32)
+        yield f"trio recombcost={rc}", prob
+    prob = synth.random_problem(rng, 10, 4, pedigree="trio", distrust=True)
+    prob.gl = prob.gl * 1e8  # `unsigned += double` on large likelihoods
+    yield "trio gl*1e8", prob
+    prob = synth.random_problem(rng, 10, 4, pedigree="single", distrust=True)
+    prob.gl = prob.gl * 4e8
+    yield "single gl*4e8", prob
+    for pedigree in ("three_children", "four_children"):  # T = 64 and T = 256 (the supported maximum)
+        for it in range(2):
+            yield f"{pedigree} #{it}", synth.random_problem(rng, int(rng.integers(3, 6)), 3, pedigree=pedigree, distrust=it == 1, mean_len=2.0)
+
+
+def test_extreme_values_and_pedigree_sizes(emul, checker):
+    lib = emul["libwhemul.so"]
+    n = 0
+    for label, prob in _extreme_problems():
+        want, got = checker.solve(prob), run_column(lib, prob, 0)
+        assert got.same_as(want), (label, got.diff(want))
+        tiled = run_tile(lib, prob, 0) if prob.n_ind == 1 else None
+        assert tiled is None or tiled.same_as(want), (label, "tile", tiled.diff(want))  # the planner declines what it cannot do exactly
+        n += 1
+    assert n == 16
+
+
+def test_more_than_thirty_active_reads_is_refused(emul):
+    from whatshap_b200._abi import Unsupported
+
+    with pytest.raises(Unsupported, match="more than 30 reads are active"):
+        run_column(emul["libwhemul.so"], synth.sliding_window(40, 31, block_len=40, seed=1), 0)
