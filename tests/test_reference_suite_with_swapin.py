@@ -1,7 +1,9 @@
 """The reference's OWN unit tests for this path (tests/test_phasing.py, tests/test_pedigreephasing.py,
 tests/test_verification.py — SURVEY.md §4) run unmodified from /root/reference with
 `whatshap.core.PedigreeDPTable` replaced by this repository's swap-in class operating on the real
-Cython ReadSet / Pedigree objects.  Authoring container only (needs /root/reference)."""
+Cython ReadSet / Pedigree objects, and with the host steps around the DP (read selection, its priority queue,
+recombination events) replaced too: tests/test_readselect.py, tests/test_priorityqueue.py, tests/test_pedigree.py.
+Authoring container only (needs /root/reference)."""
 import os
 import subprocess
 import sys
@@ -20,7 +22,8 @@ def test_reference_tests_pass_with_swapped_dp_table():
         pytest.skip("reference tree not available")
     env = dict(os.environ, WHMEC_PYREF=pyref, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), pyref, ROOT]))
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "swapin_plugin",
-           "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py"]
+           "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py",
+           "tests/test_readselect.py", "tests/test_priorityqueue.py", "tests/test_pedigree.py"]
     res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=900)
     tail = (res.stdout + res.stderr)[-2000:]
     assert res.returncode == 0, tail
