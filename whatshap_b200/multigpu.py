@@ -108,9 +108,23 @@ def contiguous_shares(work: np.ndarray, world: int) -> List[Tuple[int, int]]:
             hi = mid
         else:
             lo = mid
-    cuts = runs_for(hi)
-    cuts += [n] * (world + 1 - len(cuts))  # ranks beyond the last cut hold nothing
-    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+    cuts = runs_for(hi * (1 + 1e-9))  # the bisection ends a rounding error below a feasible limit at worst
+    if len(cuts) - 1 > world:
+        cuts = cuts[:world] + [n]
+    runs = [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1) if cuts[i + 1] > cuts[i]]
+    prefix = np.concatenate([[0.0], np.cumsum(work)])
+    load = lambda run: prefix[run[1]] - prefix[run[0]]
+    while len(runs) < world:  # idle ranks left: halve the heaviest run that still has two blocks
+        candidates = [r for r in runs if r[1] - r[0] >= 2]
+        if not candidates:
+            break
+        a, b = max(candidates, key=load)
+        mid = min(range(a + 1, b), key=lambda m: max(prefix[m] - prefix[a], prefix[b] - prefix[m]))
+        runs[runs.index((a, b))] = (a, mid)
+        runs.append((mid, b))
+        runs.sort()
+    runs += [(n, n)] * (world - len(runs))  # more ranks than blocks: the rest hold nothing
+    return runs
 
 
 def minplus(vec: np.ndarray, matrix: np.ndarray) -> np.ndarray:
