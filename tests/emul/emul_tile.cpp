@@ -166,3 +166,72 @@ extern "C" int whemul_time_host(const whmec_problem *p, double *out2) {
     out2[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
     return 0;
 }
+
+#include <malloc.h>
+// host-side timing as whmec_solve sees it for a single individual: packer without deltas, tile planner,
+// super-read construction on an arbitrary path (milliseconds); heap retention as in the library
+extern "C" int whemul_time_host_product(const whmec_problem *p, double *out3) {
+    static bool once = false;
+    if (!once) {
+        once = true;
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    }
+    Packed pk;
+    std::string msg;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = pack_problem(p, pk, msg, false);
+    auto t1 = std::chrono::steady_clock::now();
+    if (rc != WHMEC_OK) return rc;
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    auto t2 = std::chrono::steady_clock::now();
+    std::vector<uint32_t> pidx(pk.n), ptv(pk.n, 0);
+    for (uint32_t k = 0; k < pk.n; ++k) pidx[k] = (k * 2654435761u) & low_mask(pk.cols[k].a);
+    std::vector<uint8_t> part(p->n_reads), sra((size_t)p->n_ind * 2 * pk.n);
+    std::vector<uint32_t> srq((size_t)p->n_ind * pk.n);
+    whmec_solution s{};
+    s.partition = part.data();
+    s.sr_allele = sra.data();
+    s.sr_quality = srq.data();
+    auto t3 = std::chrono::steady_clock::now();
+    build_outputs(pk, pidx.data(), ptv.data(), &s, msg);
+    auto t4 = std::chrono::steady_clock::now();
+    out3[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    out3[1] = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    out3[2] = std::chrono::duration<double, std::milli>(t4 - t3).count();
+    return 0;
+}
+
+// FNV-1a digest of everything the planner produces (to hold planner rewrites to byte-identical schedules)
+extern "C" int whemul_plan_digest(const whmec_problem *p, uint64_t *digest) {
+    Packed pk;
+    std::string msg;
+    int rc = pack_problem(p, pk, msg, false);
+    if (rc != WHMEC_OK) return rc;
+    TileSchedule ts;
+    plan_tiles(pk, ts);
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](const void *ptr, size_t bytes) {
+        const unsigned char *b = (const unsigned char *)ptr;
+        for (size_t i = 0; i < bytes; ++i) h = (h ^ b[i]) * 1099511628211ull;
+    };
+    const uint64_t head[5] = {ts.eligible, ts.state_words, ts.bp_words, ts.state_traffic_bytes, ts.panels.size()};
+    mix(head, sizeof head);
+    mix(ts.why.data(), ts.why.size());
+    if (ts.eligible) {
+        mix(ts.cols.data(), ts.cols.size() * sizeof(TileCol));
+        mix(ts.panels.data(), ts.panels.size() * sizeof(Panel));
+        mix(ts.round_begin.data(), ts.round_begin.size() * 4);
+        mix(ts.round_tiles.data(), ts.round_tiles.size() * 4);
+    }
+    mix(pk.cols.data(), pk.cols.size() * sizeof(ColMeta));
+    mix(pk.act_read.data(), pk.act_read.size() * 4);
+    mix(pk.act_phred.data(), pk.act_phred.size() * 4);
+    mix(pk.act_allele.data(), pk.act_allele.size());
+    mix(pk.fn_c0.data(), pk.fn_c0.size() * 4);
+    mix(pk.fn_asg.data(), pk.fn_asg.size() * 4);
+    mix(pk.fn_group.data(), pk.fn_group.size() * 4);
+    *digest = h;
+    return 0;
+}

@@ -1,0 +1,133 @@
+// Persistent host worker pool (see hostpool.h).
+#include "hostpool.h"
+
+#include <pthread.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
+
+namespace whmec {
+
+uint32_t host_threads(uint32_t cap) {
+    uint32_t hw = std::max(1u, std::min(cap, std::thread::hardware_concurrency()));
+    if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = (uint32_t)std::max(1, std::atoi(e));
+    return hw;
+}
+
+namespace {
+
+constexpr uint32_t MAX_WORKERS = 63;
+
+struct Job {
+    const std::function<void(uint32_t)> *fn;
+    uint32_t n;
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> slots{0};  // workers that may still join this job
+};
+
+void drain(Job &j) {
+    for (uint32_t t = j.next.fetch_add(1, std::memory_order_relaxed); t < j.n; t = j.next.fetch_add(1, std::memory_order_relaxed)) (*j.fn)(t);
+}
+
+struct Pool {
+    std::mutex entry;  // one job at a time
+    std::mutex m;
+    std::condition_variable cv, done_cv;
+    uint32_t n_workers = 0;
+    Job *job = nullptr;
+    std::atomic<uint64_t> gen{0};
+    uint32_t running = 0;  // workers that have not yet checked out of the current job
+
+    void worker(uint64_t seen) {
+        for (;;) {
+            Job *j;
+            {
+                // the host phases of one solve follow each other within microseconds: poll briefly before sleeping
+                const auto t0 = std::chrono::steady_clock::now();
+                while (gen.load(std::memory_order_acquire) == seen &&
+                       std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150)) {
+#if defined(__x86_64__)
+                    __builtin_ia32_pause();
+#endif
+                }
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return gen.load() != seen; });
+                seen = gen.load();
+                j = job;
+            }
+            if (j->slots.fetch_sub(1, std::memory_order_relaxed) > 0) drain(*j);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--running == 0) done_cv.notify_one();
+            }
+        }
+    }
+};
+
+std::atomic<Pool *> g_pool{nullptr};
+std::once_flag g_atfork;
+
+// The workers do not exist in a forked child: start over with an empty pool there (the old one is leaked).
+void after_fork_in_child() { g_pool.store(nullptr); }
+
+Pool *pool() {
+    Pool *p = g_pool.load(std::memory_order_acquire);
+    if (p) return p;
+    std::call_once(g_atfork, [] { pthread_atfork(nullptr, nullptr, after_fork_in_child); });
+    Pool *fresh = new Pool();
+    if (g_pool.compare_exchange_strong(p, fresh)) return fresh;
+    delete fresh;
+    return p;
+}
+
+void run_on_temporary_threads(uint32_t n_threads, Job &j) {
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t + 1 < n_threads; ++t) th.emplace_back([&j] { drain(j); });
+    drain(j);
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+void parallel_tasks(uint32_t n_tasks, uint32_t n_threads, const std::function<void(uint32_t)> &fn) {
+    if (n_tasks == 0) return;
+    n_threads = std::min(std::min(n_threads, n_tasks), MAX_WORKERS + 1);
+    if (n_threads <= 1) {
+        for (uint32_t t = 0; t < n_tasks; ++t) fn(t);
+        return;
+    }
+    Job j;
+    j.fn = &fn;
+    j.n = n_tasks;
+    Pool *P = pool();
+    std::unique_lock<std::mutex> entry(P->entry, std::try_to_lock);
+    if (!entry.owns_lock()) {
+        run_on_temporary_threads(n_threads, j);
+        return;
+    }
+    j.slots.store((int)n_threads - 1);
+    {
+        std::lock_guard<std::mutex> lk(P->m);
+        while (P->n_workers < n_threads - 1) {
+            std::thread(&Pool::worker, P, P->gen.load()).detach();
+            ++P->n_workers;
+        }
+        P->job = &j;
+        P->running = P->n_workers;
+        ++P->gen;
+    }
+    P->cv.notify_all();
+    drain(j);
+    {
+        std::unique_lock<std::mutex> lk(P->m);
+        P->done_cv.wait(lk, [&] { return P->running == 0; });
+        P->job = nullptr;
+    }
+}
+
+}  // namespace whmec

@@ -123,41 +123,51 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         return WHMEC_ERR_INPUT;
     }
 
-    // ---- read spans and the checks of the ColumnIterator constructor (columniterator.cpp:25-33)
+    // ---- read spans and the checks of the ColumnIterator constructor (columniterator.cpp:25-33); ranges of
+    //      reads are checked by independent host threads, the reference's error is that of the first failing read
     std::vector<uint32_t> first(p->n_reads), last(p->n_reads);
-    uint32_t prev_first = 0;
     uint64_t phred_total = 0;
-    for (uint32_t r = 0; r < p->n_reads; ++r) {
-        uint64_t b = p->read_off[r], e = p->read_off[r + 1];
-        if (e <= b) {
-            err = "No variants present";
-            return WHMEC_ERR_INPUT;
-        }
-        for (uint64_t q = b; q < e; ++q) {
-            if (q > b && p->ent_col[q] <= p->ent_col[q - 1]) {
-                err = "ColumnIterator: encountered read with unsorted variants.";
-                return WHMEC_ERR_INPUT;
+    {
+        constexpr uint32_t READS_PER_TASK = 4096;
+        const uint32_t n_tasks = (p->n_reads + READS_PER_TASK - 1) / READS_PER_TASK;
+        struct Range {
+            const char *err = nullptr;
+            int rc = WHMEC_OK;
+            uint64_t phred = 0;
+        };
+        std::vector<Range> ranges(n_tasks);
+        parallel_tasks(n_tasks, host_threads(32), [&](uint32_t task) {
+            Range &rg = ranges[task];
+            const uint32_t r_begin = task * READS_PER_TASK, r_end = std::min(p->n_reads, r_begin + READS_PER_TASK);
+            uint64_t phred = 0;
+            auto fail = [&](const char *msg) {
+                rg.err = msg;
+                rg.rc = WHMEC_ERR_INPUT;
+            };
+            for (uint32_t r = r_begin; r < r_end; ++r) {
+                const uint64_t b = p->read_off[r], e = p->read_off[r + 1];
+                if (e <= b) return fail("No variants present");
+                for (uint64_t q = b; q < e; ++q) {
+                    if (q > b && p->ent_col[q] <= p->ent_col[q - 1]) return fail("ColumnIterator: encountered read with unsorted variants.");
+                    if (p->ent_allele[q] > 2) return fail("allele of a read entry must be 0 (REF), 1 (ALT) or 2 (BLANK)");
+                    phred += p->ent_phred[q];
+                }
+                first[r] = p->ent_col[b];
+                last[r] = p->ent_col[e - 1];
+                if (last[r] >= n) return fail("read entry refers to a column outside positions");
+                // the preceding read (an empty one fails in its own right, before this read is looked at)
+                const uint32_t prev_first = (r > 0 && p->read_off[r] > p->read_off[r - 1]) ? p->ent_col[p->read_off[r - 1]] : 0;
+                if (first[r] < prev_first) return fail("ColumnIterator: reads in ReadSet are not sorted.");
+                if (p->read_ind[r] >= p->n_ind) return fail("read refers to an individual outside the pedigree");
             }
-            if (p->ent_allele[q] > 2) {
-                err = "allele of a read entry must be 0 (REF), 1 (ALT) or 2 (BLANK)";
-                return WHMEC_ERR_INPUT;
+            rg.phred = phred;
+        });
+        for (const Range &rg : ranges) {
+            if (rg.rc != WHMEC_OK) {
+                err = rg.err;
+                return rg.rc;
             }
-            phred_total += p->ent_phred[q];
-        }
-        first[r] = p->ent_col[b];
-        last[r] = p->ent_col[e - 1];
-        if (last[r] >= n) {
-            err = "read entry refers to a column outside positions";
-            return WHMEC_ERR_INPUT;
-        }
-        if (first[r] < prev_first) {
-            err = "ColumnIterator: reads in ReadSet are not sorted.";
-            return WHMEC_ERR_INPUT;
-        }
-        prev_first = first[r];
-        if (p->read_ind[r] >= p->n_ind) {
-            err = "read refers to an individual outside the pedigree";
-            return WHMEC_ERR_INPUT;
+            phred_total += rg.phred;
         }
     }
 
@@ -179,7 +189,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         }
     std::vector<uint32_t> cut;  // chunk starts (columns)
     {
-        const uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        const uint32_t hw = host_threads(32);
         const uint32_t target = std::max<uint32_t>(256, n / (4 * hw) + 1);
         int32_t run = 0;
         uint32_t last_cut = 0;
@@ -214,8 +224,8 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         }
     }
     pk.cols.resize(n);
-    pk.act_off.assign(n + 1, 0);
-    pk.fn_group.assign((size_t)n * (T + 1), 0);
+    pk.act_off.resize(n + 1);
+    pk.fn_group.resize((size_t)n * (T + 1));
     // a read is active in every column of its span: the (column, active read) arrays have exactly
     // sum(last - first + 1) entries, and a chunk's slice starts after the reads that precede it
     {
@@ -235,57 +245,77 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
     auto build_chunk = [&](uint32_t ci) {
         Chunk &ch = chunks[ci];
         const uint32_t kb = cut[ci], ke = cut[ci + 1];
-        std::vector<uint32_t> active, prev_active;
+        // active reads of the current column (ascending read index = bit order) and their entry cursors
+        uint32_t active[MAX_ACTIVE];
+        uint64_t cursor[MAX_ACTIVE];
+        uint32_t na = 0;
         uint32_t next_read = chunk_first_read[ci];
         const uint32_t read_end = chunk_first_read[ci + 1];
-        std::vector<uint64_t> cursor;  // indexed by read - chunk_first_read[ci]
-        cursor.reserve(read_end - next_read);
-        for (uint32_t r = next_read; r < read_end; ++r) cursor.push_back(p->read_off[r]);
-        const uint32_t r0 = chunk_first_read[ci];
+        const size_t fn_hint = (size_t)(ke - kb) * 2 * T;
+        ch.fn_c0.reserve(fn_hint);
+        ch.fn_asg.reserve(fn_hint);
+        ch.fn_base.reserve(fn_hint);
+        if (want_deltas) ch.fn_delta.reserve(fn_hint * FN_STRIDE);
+        const uint32_t n_asg = 1u << P;
         for (uint32_t k = kb; k < ke; ++k) {
-            prev_active = active;
-            active.erase(std::remove_if(active.begin(), active.end(), [&](uint32_t r) { return last[r] < k; }), active.end());
-            while (next_read < read_end && first[next_read] == k) active.push_back(next_read++);
-            if (active.size() > MAX_ACTIVE) {
-                ch.rc = WHMEC_ERR_UNSUPPORTED;
-                ch.err_col = k;
-                ch.err = "more than 30 reads are active in one column (coverage too high)";
-                return;
+            // reads that ended before k leave; the survivors are the reads shared with column k-1, which are
+            // therefore the lowest bits (backward projection width, columnindexingscheme.cpp:62-85)
+            uint32_t w = 0;
+            for (uint32_t j = 0; j < na; ++j)
+                if (last[active[j]] >= k) {
+                    active[w] = active[j];
+                    cursor[w] = cursor[j];
+                    ++w;
+                }
+            na = w;
+            while (next_read < read_end && first[next_read] == k) {
+                if (na == MAX_ACTIVE) {
+                    ch.rc = WHMEC_ERR_UNSUPPORTED;
+                    ch.err_col = k;
+                    ch.err = "more than 30 reads are active in one column (coverage too high)";
+                    return;
+                }
+                active[na] = next_read;
+                cursor[na] = p->read_off[next_read];
+                ++na;
+                ++next_read;
             }
             ColMeta &m = pk.cols[k];
             std::memset(&m, 0, sizeof m);
-            m.a = (uint32_t)active.size();
+            m.a = na;
             ch.max_a = std::max(ch.max_a, m.a);
             m.rc = p->recombcost[k];
             m.first = (k == 0);
-            uint32_t w = 0;  // backward projection width = |active(k) ∩ active(k-1)|; those are the lowest bits
-            for (uint32_t r : active)
-                if (std::binary_search(prev_active.begin(), prev_active.end(), r)) ++w;
             m.bw = (k == 0) ? 0 : w;
             const size_t e0 = ch.act_base + ch.act_count;
             pk.act_off[k] = e0;
-            for (uint32_t j = 0; j < m.a; ++j) {
+            uint32_t *a_read = pk.act_read.data() + e0, *a_phred = pk.act_phred.data() + e0;
+            uint8_t *a_allele = pk.act_allele.data() + e0, *a_ind = pk.act_ind.data() + e0;
+            uint32_t keep = 0;
+            for (uint32_t j = 0; j < na; ++j) {
                 const uint32_t r = active[j];
-                uint64_t &cur = cursor[r - r0];
+                uint64_t cur = cursor[j];
                 while (p->ent_col[cur] < k) ++cur;
-                const size_t q = e0 + j;
-                pk.act_read[q] = r;
-                pk.act_ind[q] = (uint8_t)p->read_ind[r];
+                cursor[j] = cur;
+                a_read[j] = r;
+                a_ind[j] = (uint8_t)p->read_ind[r];
                 if (p->ent_col[cur] == k) {
-                    pk.act_allele[q] = p->ent_allele[cur];
-                    pk.act_phred[q] = p->ent_phred[cur];
+                    a_allele[j] = p->ent_allele[cur];
+                    a_phred[j] = p->ent_phred[cur];
                 } else {  // gap inside the read's span: BLANK entry, phred 0 (columniterator.cpp:131)
-                    pk.act_allele[q] = 2;
-                    pk.act_phred[q] = 0;
+                    a_allele[j] = 2;
+                    a_phred[j] = 0;
                 }
-                if (k + 1 < n && last[r] >= k + 1) m.keep |= 1u << j;
+                if (k + 1 < n && last[r] >= k + 1) keep |= 1u << j;
             }
-            ch.act_count += m.a;
-            m.f = popc32(m.keep);
+            ch.act_count += na;
+            m.keep = keep;
+            m.f = popc32(keep);
             m.d = m.a - m.f;
-            uint32_t di = 0;
-            for (uint32_t j = 0; j < m.a; ++j)
-                if (!((m.keep >> j) & 1)) m.dpos[di++] = (uint8_t)j;
+            {
+                uint32_t di = 0;
+                for (uint32_t drop = ~keep & low_mask(na); drop; drop &= drop - 1) m.dpos[di++] = (uint8_t)ctz32(drop);
+            }
 
             // cost functions per (transmission value, allowed assignment)
             m.fn_off = (uint32_t)ch.fn_c0.size();  // chunk-relative for now
@@ -295,7 +325,14 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
             for (uint32_t t = 0; t < T; ++t) {
                 const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
                 pk.fn_group[m.grp_off + t] = (uint32_t)ch.fn_c0.size() - m.fn_off;
-                for (uint32_t A = 0; A < (1u << P); ++A) {
+                // A read on haplotype 0 of its individual sits in partition h2p[ind][0] and costs its phred when
+                // the allele assigned to that partition differs from the read's (cost computer :59-67): at x = 0
+                // the cost of an assignment is a sum over partitions of S[partition][allele that differs].
+                uint32_t S[MAX_P][2];
+                for (uint32_t q = 0; q < P; ++q) S[q][0] = S[q][1] = 0;
+                for (uint32_t j = 0; j < na; ++j)
+                    if (a_allele[j] <= 1) S[h2p[2 * a_ind[j]]][a_allele[j] ^ 1] += a_phred[j];
+                for (uint32_t A = 0; A < n_asg; ++A) {
                     bool ok = true;
                     unsigned int base = 0;
                     for (uint32_t i = 0; i < p->n_ind; ++i) {
@@ -313,19 +350,21 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
                     any = true;
                     max_base = std::max(max_base, base);
                     uint32_t c0 = base;
-                    const size_t doff = ch.fn_delta.size();
-                    if (want_deltas) ch.fn_delta.resize(doff + FN_STRIDE, 0);
-                    for (uint32_t j = 0; j < m.a; ++j) {
-                        const uint8_t al = pk.act_allele[e0 + j];
-                        if (al > 1) continue;  // BLANK contributes nothing
-                        const uint32_t w2 = pk.act_phred[e0 + j];
-                        const uint32_t ind = pk.act_ind[e0 + j];
-                        // read on haplotype `bit` of its individual sits in partition h2p[ind][bit]; it costs
-                        // w when the allele assigned to that partition differs (cost computer :59-67)
-                        const uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w2 : 0;
-                        const uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w2 : 0;
-                        c0 += cost0;
-                        if (want_deltas) ch.fn_delta[doff + j] = (int32_t)(cost1 - cost0);
+                    for (uint32_t q = 0; q < P; ++q) c0 += S[q][(A >> q) & 1];
+                    if (want_deltas) {
+                        // moving read j to haplotype 1 changes the cost by (cost on partition h2p[ind][1]) - (cost on h2p[ind][0])
+                        const size_t doff = ch.fn_delta.size();
+                        ch.fn_delta.resize(doff + FN_STRIDE, 0);
+                        int32_t *delta = &ch.fn_delta[doff];
+                        for (uint32_t j = 0; j < na; ++j) {
+                            const uint8_t al = a_allele[j];
+                            if (al > 1) continue;  // BLANK contributes nothing
+                            const uint32_t w2 = a_phred[j];
+                            const uint32_t ind = a_ind[j];
+                            const uint32_t cost0 = (((A >> h2p[2 * ind]) & 1) != al) ? w2 : 0;
+                            const uint32_t cost1 = (((A >> h2p[2 * ind + 1]) & 1) != al) ? w2 : 0;
+                            delta[j] = (int32_t)(cost1 - cost0);
+                        }
                     }
                     ch.fn_c0.push_back(c0);
                     ch.fn_asg.push_back(A);
@@ -343,23 +382,8 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
             ch.rc_total += (uint64_t)m.rc * pk.tb;
         }
     };
-    {
-        uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
-        const uint32_t nthreads = std::min(hw, n_chunks);
-        std::atomic<uint32_t> next{0};
-        auto worker = [&]() {
-            for (uint32_t ci = next.fetch_add(1); ci < n_chunks; ci = next.fetch_add(1)) build_chunk(ci);
-        };
-        if (nthreads <= 1) {
-            worker();
-        } else {
-            std::vector<std::thread> pool;
-            for (uint32_t t = 0; t + 1 < nthreads; ++t) pool.emplace_back(worker);
-            worker();
-            for (auto &th : pool) th.join();
-        }
-    }
+    const uint32_t pack_threads = host_threads(32);
+    parallel_tasks(n_chunks, pack_threads, build_chunk);
     const auto t_chunks = tnow();
     // the reference reports the first failing column (columns are visited in order)
     for (uint32_t ci = 0; ci < n_chunks; ++ci)
@@ -384,14 +408,14 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         pk.fn_asg.resize(fn_total);
         pk.fn_base.resize(fn_total);
         pk.fn_delta.resize(want_deltas ? fn_total * FN_STRIDE : 0);
-        for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+        parallel_tasks(n_chunks, pack_threads, [&](uint32_t ci) {
             Chunk &ch = chunks[ci];
             std::copy(ch.fn_c0.begin(), ch.fn_c0.end(), pk.fn_c0.begin() + fn_base_off[ci]);
             std::copy(ch.fn_asg.begin(), ch.fn_asg.end(), pk.fn_asg.begin() + fn_base_off[ci]);
             std::copy(ch.fn_base.begin(), ch.fn_base.end(), pk.fn_base.begin() + fn_base_off[ci]);
             std::copy(ch.fn_delta.begin(), ch.fn_delta.end(), pk.fn_delta.begin() + fn_base_off[ci] * FN_STRIDE);
             for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) pk.cols[k].fn_off += (uint32_t)fn_base_off[ci];
-        }
+        });
         pk.act_off[n] = pk.act_read.size();
     }
     pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 28);
@@ -434,21 +458,23 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
     if (s->path_tv && path_tv != s->path_tv) std::memcpy(s->path_tv, path_tv, sizeof(uint32_t) * n);
     // get_optimal_partitioning (pedigreedptable.cpp:391-406) + core.pyx:414: a read is reported in
     // partition 0 iff its bit is 0 in some column it is active in.
-    if (s->partition) {
-        std::memset(s->partition, 1, pk.n_reads);
-        for (uint32_t k = 0; k < n; ++k) {
-            const uint64_t e0 = pk.act_off[k];
-            for (uint32_t j = 0; j < pk.cols[k].a; ++j)
-                if (((path_index[k] >> j) & 1) == 0) s->partition[pk.act_read[e0 + j]] = 0;
-        }
-    }
-    if (!s->sr_allele && !s->sr_quality) return WHMEC_OK;
+    // Column ranges are handled by independent host threads; a read that spans two ranges may be cleared by both
+    // (same value, relaxed atomic byte stores).
+    if (s->partition) std::memset(s->partition, 1, pk.n_reads);
+    const bool want_superreads = s->sr_allele || s->sr_quality;
+    if (!s->partition && !want_superreads) return WHMEC_OK;
     // get_super_reads -> get_alleles (pedigreecolumncostcomputer.cpp:117-175)
     std::atomic<int> failed{0};
     auto do_range = [&](uint32_t kb, uint32_t ke) {
     for (uint32_t k = kb; k < ke; ++k) {
         const ColMeta &m = pk.cols[k];
         const uint32_t t = path_tv[k], x = path_index[k];
+        if (s->partition) {
+            const uint32_t *reads = pk.act_read.data() + pk.act_off[k];
+            for (uint32_t zero = ~x & low_mask(m.a); zero; zero &= zero - 1)
+                __atomic_store_n(&s->partition[reads[ctz32(zero)]], (uint8_t)0, __ATOMIC_RELAXED);
+        }
+        if (!want_superreads) continue;
         const int8_t *h2p = &pk.h2p[(size_t)t * pk.n_ind * 2];
         uint32_t cp[MAX_P][2];
         for (uint32_t q = 0; q < P; ++q) cp[q][0] = cp[q][1] = 0;
@@ -506,17 +532,9 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
     }
     };
     {
-        uint32_t hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
-        const uint32_t nthreads = std::min<uint32_t>(hw, n / 4096 + 1);
-        if (nthreads <= 1) {
-            do_range(0, n);
-        } else {
-            std::vector<std::thread> pool;
-            const uint32_t step = (n + nthreads - 1) / nthreads;
-            for (uint32_t t = 0; t < nthreads; ++t) pool.emplace_back(do_range, std::min(n, t * step), std::min(n, (t + 1) * step));
-            for (auto &th : pool) th.join();
-        }
+        const uint32_t n_ranges = std::min<uint32_t>(n / 1024 + 1, 64);
+        const uint32_t step = (n + n_ranges - 1) / n_ranges;
+        parallel_tasks(n_ranges, host_threads(16), [&](uint32_t t) { do_range(std::min(n, t * step), std::min(n, (t + 1) * step)); });
     }
     if (failed.load()) {
         err = "Error: Mendelian conflict";

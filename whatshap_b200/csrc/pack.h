@@ -6,6 +6,7 @@
 
 #include "../../include/whmec.h"
 #include "common.h"
+#include "hostpool.h"
 
 namespace whmec {
 
@@ -14,19 +15,20 @@ struct Packed {
     uint32_t T = 1, tb = 0, P = 2;
     bool has_deltas = true;              // fn_delta filled
     bool safe31 = false;                 // every reachable cost value < 2^30 (tile-kernel arithmetic is exact)
-    std::vector<ColMeta> cols;           // [n]
+    // (RawVec: resize() does not zero-fill; every element is written by the packer)
+    RawVec<ColMeta> cols;                // [n]
     // active reads per column, CSR aligned with cols[k].a
-    std::vector<uint64_t> act_off;       // [n+1]
-    std::vector<uint32_t> act_read;      // read index of bit j
-    std::vector<uint8_t> act_allele;     // 0/1/2
-    std::vector<uint32_t> act_phred;
-    std::vector<uint8_t> act_ind;
+    RawVec<uint64_t> act_off;            // [n+1]
+    RawVec<uint32_t> act_read;           // read index of bit j
+    RawVec<uint8_t> act_allele;          // 0/1/2
+    RawVec<uint32_t> act_phred;
+    RawVec<uint8_t> act_ind;
     // cost functions (see common.h), grouped per column and transmission value
-    std::vector<uint32_t> fn_c0;
-    std::vector<int32_t> fn_delta;       // [nf][FN_STRIDE]
-    std::vector<uint32_t> fn_asg;        // allele assignment A of the function
-    std::vector<uint32_t> fn_base;       // genotype-likelihood base cost of A
-    std::vector<uint32_t> fn_group;      // per column T+1 offsets relative to cols[k].fn_off
+    RawVec<uint32_t> fn_c0;
+    RawVec<int32_t> fn_delta;            // [nf][FN_STRIDE]
+    RawVec<uint32_t> fn_asg;             // allele assignment A of the function
+    RawVec<uint32_t> fn_base;            // genotype-likelihood base cost of A
+    RawVec<uint32_t> fn_group;           // per column T+1 offsets relative to cols[k].fn_off
     std::vector<int8_t> h2p;             // [T][n_ind][2]
     std::vector<uint32_t> read_first, read_last;  // column span of every read
     // chains: maximal runs of columns with f > 0 between them (T == 1 only uses them)

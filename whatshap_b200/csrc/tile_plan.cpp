@@ -7,26 +7,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <thread>
 
 namespace whmec {
 
 namespace {
 
-struct ChainCtx {
-    const Packed *pk;
-    uint32_t chain, k0, k1;  // columns [k0, k1], k1 is the chain end (f == 0)
-};
-
 // reads of column k in canonical order
-inline const uint32_t *col_reads(const Packed &pk, uint32_t k) { return &pk.act_read[pk.act_off[k]]; }
-
-uint32_t mask_of(const std::vector<uint32_t> &all, const std::vector<uint32_t> &subset_sorted) {
-    uint32_t m = 0;
-    for (size_t i = 0; i < all.size(); ++i)
-        if (std::binary_search(subset_sorted.begin(), subset_sorted.end(), all[i])) m |= 1u << i;
-    return m;
-}
+inline const uint32_t *col_reads(const Packed &pk, uint32_t k) { return pk.act_read.data() + pk.act_off[k]; }
 
 }  // namespace
 
@@ -45,7 +32,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = tnow();
     const uint32_t n = pk.n;
-    ts.cols.assign(n, TileCol());
+    ts.cols.resize(n);  // every column is written by exactly one committed panel
     const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
     std::vector<std::vector<Panel>> per_chain(n_chains);
     struct PanelSets { std::vector<uint32_t> G, Lout, Lold, Gold; };
@@ -55,10 +42,33 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     std::vector<uint64_t> chain_state_words(n_chains, 0), chain_bp_words(n_chains, 0), chain_traffic(n_chains, 0);
     std::vector<std::string> chain_why(n_chains);
 
+    // Sets of reads are small (at most 30 reads are active in a column) and are kept as ascending arrays;
+    // "where does read r sit in the current column / in the tile's local order" are O(1) look-ups in
+    // per-chain tables indexed by (read - first read of the chain) and validated by a stamp.
+    struct Small {
+        uint32_t v[32];
+        uint32_t n = 0;
+        void push(uint32_t x) { v[n++] = x; }
+        std::vector<uint32_t> vec() const { return std::vector<uint32_t>(v, v + n); }
+    };
     auto plan_chain = [&](uint32_t c) -> bool {
         const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1] - 1;
-        uint32_t fmax = 0;
-        for (uint32_t k = k0; k <= k1; ++k) fmax = std::max(fmax, pk.cols[k].f);
+        uint32_t fmax = 0, rbase = 0xFFFFFFFFu, rtop = 0;
+        for (uint32_t k = k0; k <= k1; ++k) {
+            const ColMeta &m = pk.cols[k];
+            fmax = std::max(fmax, m.f);
+            if (m.a) {
+                const uint32_t *reads = col_reads(pk, k);
+                rbase = std::min(rbase, reads[0]);
+                rtop = std::max(rtop, reads[m.a - 1]);
+            }
+        }
+        const uint32_t nr = rbase == 0xFFFFFFFFu ? 0 : rtop - rbase + 1;
+        // stamped tables: column position, position in the tile's local order, membership in L / G / Lold / Gold
+        std::vector<uint32_t> col_stamp(nr, 0), cur_stamp(nr, 0), l_stamp(nr, 0), g_stamp(nr, 0), lold_stamp(nr, 0), gold_stamp(nr, 0);
+        std::vector<uint8_t> col_pos(nr, 0), cur_pos(nr, 0);
+        uint32_t tick = 0;     // one per visited column
+        uint32_t attempt = 0;  // one per tried tile size
         // at least 4 words so that every chain's buffers stay 16-byte aligned (vector stores of whole tiles)
         const uint64_t buf_words = std::max<uint64_t>(4, (uint64_t)1 << fmax);
         const uint64_t chain_state = 0;
@@ -66,11 +76,11 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         uint64_t bp_words = 0;
         uint32_t pcount = 0;
 
-        std::vector<uint32_t> state;  // reads kept after column k-1, canonical (ascending) order
+        Small state;  // reads kept after column k-1, canonical (ascending) order
         uint32_t k = k0;
         while (k <= k1) {
             const ColMeta &m0 = pk.cols[k];
-            const uint32_t fin = (uint32_t)state.size();
+            const uint32_t fin = state.n;
             const uint32_t n_new0 = m0.a - m0.bw;
             if (fin != m0.bw && !(k == k0 && m0.bw == 0)) {
                 chain_why[c] = "internal: state/backward width mismatch";
@@ -80,69 +90,80 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             // that start in this column (at a panel's first column new reads may become global, which
             // is how a chain that starts with more reads than one tile holds is cut).
             const uint32_t *reads0 = col_reads(pk, k);
-            std::vector<uint32_t> cand = state;
-            for (uint32_t q = m0.bw; q < m0.a; ++q) cand.push_back(reads0[q]);
+            const uint32_t n_cand = state.n + n_new0;
             auto by_last = [&](uint32_t a, uint32_t b) { return pk.read_last[a] < pk.read_last[b]; };
-            std::vector<uint32_t> old_by_end = state, new_by_end(cand.begin() + state.size(), cand.end());
-            std::stable_sort(old_by_end.begin(), old_by_end.end(), by_last);
-            std::stable_sort(new_by_end.begin(), new_by_end.end(), by_last);
+            Small old_by_end = state, new_by_end;
+            for (uint32_t q = m0.bw; q < m0.a; ++q) new_by_end.push(reads0[q]);
+            std::stable_sort(old_by_end.v, old_by_end.v + old_by_end.n, by_last);
+            std::stable_sort(new_by_end.v, new_by_end.v + new_by_end.n, by_last);
             // Local bits: the soonest-ending old reads (as many as the input buffer holds) and then the
             // soonest-ending new reads; everything else is global for this panel.
-            int s_try = (int)std::min<uint32_t>((uint32_t)cand.size(), TILE_MMAX);
+            int s_try = (int)std::min<uint32_t>(n_cand, TILE_MMAX);
             bool placed = false;
             uint32_t last_size = 0xFFFFFFFFu;
             for (; s_try >= 0 && !placed; --s_try) {
-                const uint32_t l_old = std::min<uint32_t>({(uint32_t)state.size(), TILE_SMAX, (uint32_t)s_try});
+                const uint32_t l_old = std::min<uint32_t>({state.n, TILE_SMAX, (uint32_t)s_try});
                 const uint32_t l_new = std::min<uint32_t>(n_new0, (uint32_t)s_try - l_old);
                 const uint32_t s0 = l_old + l_new;
                 if (s0 == last_size) continue;
                 last_size = s0;
-                if (cand.size() - s0 > TILE_GMAX) break;
-                std::vector<uint32_t> Lold(old_by_end.begin(), old_by_end.begin() + l_old);
-                std::vector<uint32_t> Gold(old_by_end.begin() + l_old, old_by_end.end());
-                std::vector<uint32_t> L = Lold, G = Gold;
-                L.insert(L.end(), new_by_end.begin(), new_by_end.begin() + l_new);
-                G.insert(G.end(), new_by_end.begin() + l_new, new_by_end.end());
-                std::sort(L.begin(), L.end());
-                std::sort(G.begin(), G.end());
-                std::sort(Lold.begin(), Lold.end());
-                std::sort(Gold.begin(), Gold.end());
-                const uint32_t n_new_local0 = (uint32_t)(L.size() - Lold.size());
-                std::vector<uint32_t> Lcur = Lold;
-                std::vector<TileCol> accepted;
+                if (n_cand - s0 > TILE_GMAX) break;
+                ++attempt;
+                Small Lold, Gold, G;
+                for (uint32_t q = 0; q < l_old; ++q) Lold.push(old_by_end.v[q]);
+                for (uint32_t q = l_old; q < old_by_end.n; ++q) Gold.push(old_by_end.v[q]);
+                G = Gold;
+                for (uint32_t q = l_new; q < new_by_end.n; ++q) G.push(new_by_end.v[q]);
+                std::sort(G.v, G.v + G.n);
+                std::sort(Lold.v, Lold.v + Lold.n);
+                std::sort(Gold.v, Gold.v + Gold.n);
+                for (uint32_t q = 0; q < Lold.n; ++q) l_stamp[Lold.v[q] - rbase] = attempt;
+                for (uint32_t q = 0; q < l_new; ++q) l_stamp[new_by_end.v[q] - rbase] = attempt;
+                for (uint32_t q = 0; q < G.n; ++q) g_stamp[G.v[q] - rbase] = attempt;
+                const uint32_t n_new_local0 = l_new;
+                Small Lcur = Lold;
+                uint32_t n_accepted = 0;
                 uint32_t j = k;
                 bool ends_chain = false;
                 for (; j <= k1; ++j) {
                     const ColMeta &m = pk.cols[j];
                     const uint32_t *reads = col_reads(pk, j);
                     const uint32_t n_new = (j == k) ? n_new_local0 : (m.a - m.bw);
-                    const uint32_t l_in = (uint32_t)Lcur.size();
+                    const uint32_t l_in = Lcur.n;
                     const uint32_t mm = l_in + n_new;
                     if (mm > TILE_MMAX) break;
-                    std::vector<uint32_t> cur = Lcur;
+                    ++tick;
+                    Small cur = Lcur;
                     for (uint32_t q = m.bw; q < m.a; ++q)  // new reads are the top bits (global ones excluded)
-                        if (j != k || std::binary_search(L.begin(), L.end(), reads[q])) cur.push_back(reads[q]);
+                        if (j != k || l_stamp[reads[q] - rbase] == attempt) cur.push(reads[q]);
+                    for (uint32_t q = 0; q < cur.n; ++q) {
+                        cur_stamp[cur.v[q] - rbase] = tick;
+                        cur_pos[cur.v[q] - rbase] = (uint8_t)q;
+                    }
+                    for (uint32_t q = 0; q < m.a; ++q) {
+                        col_stamp[reads[q] - rbase] = tick;
+                        col_pos[reads[q] - rbase] = (uint8_t)q;
+                    }
                     const bool chain_end = (m.f == 0);
                     uint32_t dropmask = 0, d = 0;
                     bool drops_global = false;
-                    for (uint32_t q = 0; q < m.a; ++q)
-                        if (!((m.keep >> q) & 1)) {
-                            auto it = std::find(cur.begin(), cur.end(), reads[q]);
-                            if (it == cur.end()) drops_global = true;
-                            else {
-                                dropmask |= 1u << (uint32_t)(it - cur.begin());
-                                ++d;
-                            }
+                    for (uint32_t drop = ~m.keep & low_mask(m.a); drop; drop &= drop - 1) {
+                        const uint32_t r = reads[ctz32(drop)] - rbase;
+                        if (cur_stamp[r] != tick) drops_global = true;
+                        else {
+                            dropmask |= 1u << cur_pos[r];
+                            ++d;
                         }
+                    }
                     if (!chain_end && drops_global) break;
                     const uint32_t l_out = mm - d;
                     if (!chain_end && l_out > TILE_SMAX) break;
-                    TileCol tc;
+                    TileCol &tc = ts.cols[j];  // a non-empty attempt is always committed, so this is final
                     std::memset(&tc, 0, sizeof tc);
                     tc.l_in = (uint8_t)l_in;
                     tc.n_new = (uint8_t)n_new;
                     tc.kind = chain_end ? 1 : 0;
-                    tc.g = (uint8_t)G.size();
+                    tc.g = (uint8_t)G.n;
                     if (chain_end) {
                         tc.d = (uint8_t)mm;
                         tc.l_out = 0;
@@ -164,45 +185,43 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     tc.K0 = K0;
                     tc.K2 = (int32_t)K2;
                     tc.K12 = K1 + K2;
-                    const uint64_t e0 = pk.act_off[j];
+                    const uint8_t *alleles = pk.act_allele.data() + pk.act_off[j];
+                    const uint32_t *phreds = pk.act_phred.data() + pk.act_off[j];
                     auto weight_of = [&](uint32_t read) -> int32_t {
-                        for (uint32_t q = 0; q < m.a; ++q)
-                            if (reads[q] == read) {
-                                uint8_t al = pk.act_allele[e0 + q];
-                                int32_t w = (int32_t)pk.act_phred[e0 + q];
-                                return al == 0 ? w : (al == 1 ? -w : 0);
-                            }
-                        return 0;
+                        const uint32_t r = read - rbase;
+                        if (col_stamp[r] != tick) return 0;
+                        const uint8_t al = alleles[col_pos[r]];
+                        const int32_t w = (int32_t)phreds[col_pos[r]];
+                        return al == 0 ? w : (al == 1 ? -w : 0);
                     };
                     uint32_t lmask_col = 0;
                     for (uint32_t q = 0; q < mm; ++q) {
-                        tc.w_local[q] = weight_of(cur[q]);
-                        for (uint32_t z = 0; z < m.a; ++z)
-                            if (reads[z] == cur[q]) lmask_col |= 1u << z;
+                        tc.w_local[q] = weight_of(cur.v[q]);
+                        if (col_stamp[cur.v[q] - rbase] == tick) lmask_col |= 1u << col_pos[cur.v[q] - rbase];
                     }
                     tc.lmask_col = lmask_col;
-                    for (uint32_t b = 0; b < G.size(); ++b) tc.w_global[b] = weight_of(G[b]);
+                    for (uint32_t b = 0; b < G.n; ++b) tc.w_global[b] = weight_of(G.v[b]);
                     uint32_t di = 0;
-                    for (uint32_t q = 0; q < mm; ++q)
-                        if ((tc.dropmask >> q) & 1) {
-                            if (di < 16) {
-                                tc.dpos[di] = (uint8_t)q;
-                                uint32_t ga = 0;
-                                for (uint32_t b = 0; b < G.size(); ++b)
-                                    if (G[b] > cur[q]) ga |= 1u << b;
-                                tc.gabove[di] = ga;
-                            }
-                            ++di;
+                    Small nextL;  // state after this column
+                    for (uint32_t q = 0; q < mm; ++q) {
+                        if (!((tc.dropmask >> q) & 1)) {
+                            nextL.push(cur.v[q]);
+                            continue;
                         }
-                    // state after this column
-                    std::vector<uint32_t> nextL;
-                    for (uint32_t q = 0; q < mm; ++q)
-                        if (!((tc.dropmask >> q) & 1)) nextL.push_back(cur[q]);
+                        if (di < 16) {
+                            tc.dpos[di] = (uint8_t)q;
+                            // tile-id bits of the global reads canonically above this read (G is ascending)
+                            uint32_t below = 0;
+                            while (below < G.n && G.v[below] <= cur.v[q]) ++below;
+                            tc.gabove[di] = low_mask(G.n) & ~low_mask(below);
+                        }
+                        ++di;
+                    }
                     if (!chain_end) {
-                        std::vector<uint32_t> kept;
-                        for (uint32_t q = 0; q < m.a; ++q)
-                            if ((m.keep >> q) & 1) kept.push_back(reads[q]);
-                        tc.gmask_out = mask_of(kept, G);
+                        uint32_t gm = 0, rank = 0;
+                        for (uint32_t keep = m.keep; keep; keep &= keep - 1, ++rank)
+                            if (g_stamp[reads[ctz32(keep)] - rbase] == attempt) gm |= 1u << rank;
+                        tc.gmask_out = gm;
                     }
                     // kernel path hint (tile.cu: fast_kind): steady-state columns
                     if (tc.kind == 0 && tc.d == 1 && tc.dpos[0] == 0 && tc.l_out >= 10 && tc.l_in >= 1 && tc.l_in + 4 >= tc.l_out &&
@@ -215,55 +234,62 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                             tc.pad1 = (uint8_t)(tc.l_out - 10);
                         }
                     }
-                    accepted.push_back(tc);
-                    Lcur.swap(nextL);
+                    ++n_accepted;
+                    Lcur = nextL;
                     if (chain_end) {
                         ends_chain = true;
                         ++j;
                         break;
                     }
                 }
-                if (accepted.empty()) continue;  // try a smaller tile
+                if (n_accepted == 0) continue;  // try a smaller tile
                 // commit the panel [k, j)
+                for (uint32_t q = 0; q < Lold.n; ++q) lold_stamp[Lold.v[q] - rbase] = attempt;
+                for (uint32_t q = 0; q < Gold.n; ++q) gold_stamp[Gold.v[q] - rbase] = attempt;
                 Panel P;
                 std::memset(&P, 0, sizeof P);
                 P.chain = c;
                 P.col_begin = k;
                 P.col_end = j;
-                P.g = (uint32_t)G.size();
-                P.s_in = (uint32_t)Lold.size();
-                P.lmask_in = mask_of(state, Lold);
-                P.gmask_in = mask_of(state, Gold);
+                P.g = G.n;
+                P.s_in = Lold.n;
+                for (uint32_t q = 0; q < state.n; ++q) {
+                    if (lold_stamp[state.v[q] - rbase] == attempt) P.lmask_in |= 1u << q;
+                    if (gold_stamp[state.v[q] - rbase] == attempt) P.gmask_in |= 1u << q;
+                }
                 P.ends_chain = ends_chain ? 1 : 0;
                 P.fresh = (k == k0) ? 1 : 0;
                 P.in_off = chain_state + (uint64_t)(pcount & 1) * buf_words;
                 P.out_off = chain_state + (uint64_t)((pcount + 1) & 1) * buf_words;
-                std::vector<uint32_t> kept;
+                Small kept;
                 if (!ends_chain) {
                     const ColMeta &ml = pk.cols[j - 1];
                     const uint32_t *reads = col_reads(pk, j - 1);
-                    for (uint32_t q = 0; q < ml.a; ++q)
-                        if ((ml.keep >> q) & 1) kept.push_back(reads[q]);
-                    P.s_out = (uint32_t)Lcur.size();
-                    P.lmask_out = mask_of(kept, Lcur);
-                    P.gmask_out = mask_of(kept, G);
-                    chain_traffic[c] += 2ull * 4ull * ((uint64_t)1 << kept.size());
+                    for (uint32_t keep = ml.keep; keep; keep &= keep - 1) kept.push(reads[ctz32(keep)]);
+                    P.s_out = Lcur.n;
+                    // Lcur is the local order after column j-1, whose tick is still current
+                    for (uint32_t q = 0; q < kept.n; ++q) {
+                        bool in_lcur = false;
+                        for (uint32_t z = 0; z < Lcur.n; ++z) in_lcur |= (Lcur.v[z] == kept.v[q]);
+                        if (in_lcur) P.lmask_out |= 1u << q;
+                        if (g_stamp[kept.v[q] - rbase] == attempt) P.gmask_out |= 1u << q;
+                    }
+                    chain_traffic[c] += 2ull * 4ull * ((uint64_t)1 << kept.n);
                 }
                 for (uint32_t q = k; q < j; ++q) {
-                    TileCol &tc = accepted[q - k];
+                    TileCol &tc = ts.cols[q];
                     tc.bp_width = tc.kind == 1 ? 0 : round_bp_width(tc.d);
                     tc.bp_off = bp_words;
                     // every tile's slice starts on a word boundary
                     uint64_t per_tile_words = ((((uint64_t)1 << tc.l_out) * tc.bp_width) + 31) / 32;
                     tc.bp_tile_words = (uint32_t)per_tile_words;
                     bp_words += per_tile_words << tc.g;
-                    ts.cols[q] = tc;
                 }
-                P.in_gold = (uint32_t)Gold.size();
+                P.in_gold = Gold.n;
                 per_chain[c].push_back(P);
-                per_chain_sets[c].push_back(PanelSets{G, Lcur, Lold, Gold});
+                per_chain_sets[c].push_back(PanelSets{G.vec(), Lcur.vec(), Lold.vec(), Gold.vec()});
                 ++pcount;
-                state.swap(kept);
+                state = kept;
                 k = j;
                 placed = true;
             }
@@ -276,23 +302,11 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         return true;
     };
     {
-        uint32_t hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-        if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = std::max(1, std::atoi(e));
-        const uint32_t nthreads = std::min(hw, std::max(1u, n_chains / 2));
-        std::atomic<uint32_t> next{0};
+        const uint32_t nthreads = std::min(host_threads(32), std::max(1u, n_chains / 2));
         std::atomic<bool> failed{false};
-        auto worker = [&]() {
-            for (uint32_t c = next.fetch_add(1); c < n_chains && !failed.load(); c = next.fetch_add(1))
-                if (!plan_chain(c)) failed.store(true);
-        };
-        if (nthreads <= 1) {
-            worker();
-        } else {
-            std::vector<std::thread> pool;
-            for (uint32_t t = 0; t + 1 < nthreads; ++t) pool.emplace_back(worker);
-            worker();
-            for (auto &th : pool) th.join();
-        }
+        parallel_tasks(n_chains, nthreads, [&](uint32_t c) {
+            if (!failed.load() && !plan_chain(c)) failed.store(true);
+        });
         if (failed.load()) {
             for (uint32_t c = 0; c < n_chains; ++c)
                 if (!chain_why[c].empty()) {

@@ -73,7 +73,7 @@ struct Panel {
 struct TileSchedule {
     bool eligible = false;
     std::string why;                      // reason when not eligible
-    std::vector<TileCol> cols;            // [n] indexed by global column
+    RawVec<TileCol> cols;                 // [n] indexed by global column
     std::vector<Panel> panels;            // grouped by launch round
     std::vector<uint32_t> round_begin;    // panels of round r: [round_begin[r], round_begin[r+1])
     std::vector<uint32_t> round_tiles;    // CTAs per round
