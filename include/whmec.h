@@ -14,6 +14,9 @@
  *   whmec_plan_*           <- same path, split into upload / forward sweep / backtrace so that
  *                             a caller (bench.py) can keep the packed ReadSet resident in HBM
  *   whmec_read_sort_key    <- ReadSet::read_comparator_t tie-break hash  src/readset.h:39-81
+ *   whmec_genotype         <- GenotypeDPTable::GenotypeDPTable  src/genotypedptable.cpp:17-48 (ctor runs the
+ *                             backward and the forward pass :118-215) + get_genotype_likelihoods :445-451,
+ *                             bound at whatshap/core.pyx:581-600  (sibling DP)
  *
  * Plain pointers and sizes only.  All input pointers are caller-owned host
  * memory, read-only, and need to stay valid only for the duration of the call.
@@ -98,7 +101,7 @@ typedef struct whmec_stats {
     float sweep_ms;              /* device time of the last forward sweep (CUDA events) */
     float h2d_ms, d2h_ms;        /* device-timed copies of the last solve */
     uint64_t h2d_bytes, d2h_bytes;
-    uint32_t path_kind;          /* 1 = tile kernel, 2 = column kernel, 3 = mixed */
+    uint32_t path_kind;          /* 1 = tile kernel, 2 = column kernel, 3 = batched pedigree sweep, 4 = genotyping (forward-backward) */
     uint32_t reserved;
 } whmec_stats;
 
@@ -123,6 +126,20 @@ void whmec_plan_destroy(whmec_plan *plan);
 /* One-shot: create + sweep + finish + destroy, host buffers in, host buffers out. */
 int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_stats *st_or_null,
                 char *err, size_t errlen);
+
+/* ---- Genotype likelihoods by the forward-backward algorithm (the reference's GenotypeDPTable) ----------
+ * Same inputs as whmec_solve, read differently where the reference does: p->gl holds, per individual and
+ * column, the PRIOR probabilities of the genotypes 0/0, 0/1, 1/1 (required; the reference asserts on missing
+ * ones, src/transitionprobabilitycomputer.cpp:66), recombcost[k] is the phred-scaled recombination
+ * probability between columns k-1 and k, phred scores are error probabilities 10^(-q/10) (0 -> 0.9999,
+ * src/genotypecolumncostcomputer.cpp:26-33); p->gt and p->distrust are ignored.  Every read must cover at
+ * least two columns (the reference asserts, src/backwardcolumniterator.cpp:41): WHMEC_ERR_INPUT otherwise.
+ * likelihoods (caller-allocated, [n_ind][n_cols][3] doubles) receives get_genotype_likelihoods(individual, column)
+ * for every individual (pedigree index order) and column.  Floating point: the reference computes in 80-bit long
+ * double with running-sum scaling, the device in double with max scaling; the normalised likelihoods agree to
+ * ~1e-13 (the reference's own tests compare with 1e-9, whatshap/testhelpers.py:11-15).  st->backptr_bytes reports
+ * the bytes of backward tables kept in HBM, st->sweep_ms the device time of both passes. */
+int whmec_genotype(const whmec_problem *p, double *likelihoods, int device, whmec_stats *st_or_null, char *err, size_t errlen);
 
 /* ---- A pedigree table (T = 4^trios > 1) shared by several GPUs --------------------------------
  * The reference sweeps a family's table on one thread (src/pedigreedptable.cpp:84-174).  Columns that no

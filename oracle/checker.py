@@ -42,6 +42,13 @@ class _Checker:
             self._solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_char_p, C.c_size_t]
         self._solve.restype = C.c_int
         self.last_seconds: Optional[float] = None
+        # forward-backward genotyping DP (GenotypeDPTable): whref_genotype / whoracle_genotype
+        self._genotype = getattr(self.lib, prefix + "_genotype", None)
+        if self._genotype is not None:
+            dp = C.POINTER(C.c_double)
+            self._genotype.argtypes = ([C.POINTER(CProblem), dp, dp, C.c_char_p, C.c_size_t] if has_time
+                                       else [C.POINTER(CProblem), dp, C.c_char_p, C.c_size_t])
+            self._genotype.restype = C.c_int
 
     def solve(self, prob: FlatProblem) -> FlatSolution:
         sol = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
@@ -56,6 +63,22 @@ class _Checker:
         raise_for(rc, err.value.decode())
         sol.cost = int(cs.cost)
         return sol
+
+    def genotype(self, prob: FlatProblem):
+        """Genotype likelihoods [n_ind, n_cols, 3] of the reference's GenotypeDPTable (`prob.gl` = priors)."""
+        import numpy as np
+
+        out = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
+        cp, err = prob.as_c(), C.create_string_buffer(512)
+        dp = out.ctypes.data_as(C.POINTER(C.c_double))
+        if self._has_time:
+            secs = C.c_double(0.0)
+            rc = self._genotype(C.byref(cp), dp, C.byref(secs), err, len(err))
+            self.last_seconds = secs.value
+        else:
+            rc = self._genotype(C.byref(cp), dp, err, len(err))
+        raise_for(rc, err.value.decode())
+        return out
 
     def solve_many_timed(self, probs: Sequence[FlatProblem], threads: int) -> float:
         """Wall seconds for solving all `probs` on `threads` host threads (reference only)."""

@@ -13,6 +13,7 @@
 //   get_super_reads                 src/pedigreedptable.cpp:344-388
 //   get_optimal_partitioning        src/pedigreedptable.cpp:391-406  (+ core.pyx:414 true->0 mapping)
 //   get_optimal_score               src/pedigreedptable.cpp:338-341
+//   GenotypeDPTable ctor / get_genotype_likelihoods   src/genotypedptable.cpp:17-48,445-451  (sibling DP)
 
 #include <chrono>
 #include <cstring>
@@ -32,6 +33,7 @@
 #include "readset.h"
 #include "genotype.h"
 #include "phredgenotypelikelihoods.h"
+#include "genotypedptable.h"
 
 #include "../include/whmec.h"
 
@@ -166,6 +168,34 @@ int whref_solve_many(const whmec_problem *const *ps, uint32_t n, uint32_t n_thre
             return rc[i];
         }
     return WHMEC_OK;
+}
+
+// Run the reference's forward-backward genotyping DP (GenotypeDPTable) once: out[(i * n_cols + k) * 3 + g] = likelihood of
+// genotype index g (0/0, 0/1, 1/1) of individual i at column k, rounded from long double to double.  p->gl holds the
+// genotype priors (the reference asserts on missing ones); p->gt is ignored by this DP.
+int whref_genotype(const whmec_problem *p, double *out, double *ctor_seconds, char *err, size_t errlen) {
+    try {
+        if (p->n_cols > 0 && !p->gl) {
+            set_err(err, errlen, "genotype priors (gl) are required");
+            return WHMEC_ERR_INPUT;
+        }
+        Built b;
+        build(p, b);
+        auto t0 = std::chrono::steady_clock::now();
+        GenotypeDPTable dp(b.rs.get(), b.recomb, b.ped.get(), &b.positions);
+        auto t1 = std::chrono::steady_clock::now();
+        if (ctor_seconds) *ctor_seconds = std::chrono::duration<double>(t1 - t0).count();
+        for (uint32_t i = 0; i < p->n_ind; ++i)
+            for (uint32_t k = 0; k < p->n_cols; ++k) {
+                double *q = out + ((size_t)i * p->n_cols + k) * 3;
+                std::vector<long double> l = dp.get_genotype_likelihoods(i, k);
+                for (int g = 0; g < 3; ++g) q[g] = (double)l[g];
+            }
+        return WHMEC_OK;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return WHMEC_ERR_INPUT;
+    }
 }
 
 const char *whref_info(void) { return "whatshap reference C++ (PedigreeDPTable), compiled in place by oracle/Makefile"; }

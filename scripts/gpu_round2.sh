@@ -11,6 +11,8 @@ timeout 300 python scripts/gpu_grouped_check.py 2>&1 | tail -12 | tee gpurun_out
 timeout 300 python scripts/gpu_ped_chain_check.py 2>&1 | tail -8 | tee gpurun_out/ped_chain_check.log
 # extremes of the value range / pedigree size on the CUDA path
 timeout 300 python scripts/gpu_extremes_check.py 2>&1 | tail -20 | tee gpurun_out/extremes_check.log
+# forward-backward genotyping DP (whmec_genotype): first run on a device; parity first, then timings
+timeout 500 python scripts/gpu_genotype_check.py 2>&1 | tail -12 | tee gpurun_out/genotype_check.log
 # headline bench with and without the pipeline (look at "e2e")
 timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
 WHMEC_SOLVE_GROUPS=4 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_groups4.json 2> gpurun_out/bench_cfg3_groups4.err

@@ -1,0 +1,28 @@
+"""TEST-ONLY: the genotyping kernels' per-cell code (whatshap_b200/csrc/gl_device.h) and host packer (gl_pack.cpp)
+executed serially on the host by tests/emul/libwhemul.so — a stand-in for `whmec_genotype` where there is no GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from whatshap_b200._abi import CProblem, raise_for
+
+EMUL_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emul")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", EMUL_DIR, "all"], check=True, capture_output=True)
+        _lib = C.CDLL(os.path.join(EMUL_DIR, "libwhemul.so"))
+        _lib.whemul_genotype.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.c_char_p, C.c_size_t]
+    return _lib
+
+
+def genotype(prob, device: int = 0):
+    out = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
+    cp, err = prob.as_c(), C.create_string_buffer(512)
+    raise_for(lib().whemul_genotype(C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), err, len(err)), err.value.decode())
+    return out, {}

@@ -1,7 +1,7 @@
 """pytest plugin used by test_reference_suite_with_swapin.py (second run): the reference's test modules import
 `whatshap.core`; before they do, EVERY class of this path in that module is replaced by this repository's Python
 mirror (`whatshap_b200.core`), `whatshap.graph.ComponentFinder` by `whatshap_b200.components.ComponentFinder`, and the
-CUDA solve behind `PedigreeDPTable` by the CPU checker (no GPU in the authoring container; the CUDA solve is held to the
+CUDA solves behind `PedigreeDPTable` / `GenotypeDPTable` by the CPU checker (no GPU in the authoring container; the CUDA solve is held to the
 same checker by the GPU tests).  The reference's tests then exercise this package's containers unmodified."""
 import os
 import sys
@@ -26,7 +26,10 @@ from whatshap_b200 import readselect as my_select  # noqa: E402
 
 _checker = checker.port()
 _lib.solve = lambda prob, device=0: (_checker.solve(prob), {})
-for name in ("NumericSampleIds", "Read", "ReadSet", "Pedigree", "Genotype", "PhredGenotypeLikelihoods", "PedigreeDPTable",
+import emul_genotype  # noqa: E402
+
+_lib.genotype = emul_genotype.genotype  # the kernels' per-cell code + host packer, stepped on the host
+for name in ("NumericSampleIds", "Read", "ReadSet", "Pedigree", "Genotype", "PhredGenotypeLikelihoods", "PedigreeDPTable", "GenotypeDPTable",
              "binomial_coefficient", "get_max_genotype_ploidy", "get_max_genotype_alleles"):
     setattr(core, name, getattr(mine, name) if hasattr(mine, name) else getattr(mine.core, name))
 whatshap.graph.ComponentFinder = components.ComponentFinder

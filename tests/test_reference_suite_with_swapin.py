@@ -35,7 +35,8 @@ def test_reference_tests_pass_with_swapped_dp_table():
 def test_reference_tests_pass_on_this_packages_containers():
     """Second run: every class of the path in `whatshap.core` replaced by this package's Python mirror
     (tests/swapin_all_plugin.py), so the reference's data-model tests (tests/test_reads.py, tests/test_pedigree.py,
-    tests/test_graph.py), its read-selection / priority-queue tests and the three DP test files exercise THIS
+    tests/test_graph.py), its read-selection / priority-queue tests, the three phasing-DP test files and the two genotyping-DP
+    test files (tests/test_genotyping.py, tests/test_pedigreegenotyping.py; `GenotypeDPTable` backed by the emulated kernels) exercise THIS
     package's containers and host steps unmodified.  HapCHAT-parametrised cases are another algorithm (deselected)."""
     from oracle import build_pyref
 
@@ -45,7 +46,8 @@ def test_reference_tests_pass_on_this_packages_containers():
     env = dict(os.environ, WHMEC_PYREF=pyref, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), pyref, ROOT]))
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "swapin_all_plugin", "-k", "not hapchat",
            "tests/test_reads.py", "tests/test_pedigree.py", "tests/test_graph.py", "tests/test_readselect.py", "tests/test_priorityqueue.py",
-           "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py"]
+           "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py",
+           "tests/test_genotyping.py", "tests/test_pedigreegenotyping.py"]
     res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=900)
     tail = (res.stdout + res.stderr)[-2000:]
     assert res.returncode == 0, tail

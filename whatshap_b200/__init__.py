@@ -2,6 +2,7 @@
 `PedigreeDPTable` interface.  See DESIGN.md; the compute path is CUDA only (libwhmec.so)."""
 from .core import (  # noqa: F401
     Genotype,
+    GenotypeDPTable,
     NumericSampleIds,
     Pedigree,
     PedigreeDPTable,
@@ -18,6 +19,6 @@ from .variant import Variant  # noqa: F401
 PhasingAlgorithm.register(PedigreeDPTable)
 
 __all__ = [
-    "Genotype", "NumericSampleIds", "Pedigree", "PedigreeDPTable", "PhredGenotypeLikelihoods", "Read", "ReadSet",
+    "Genotype", "GenotypeDPTable", "NumericSampleIds", "Pedigree", "PedigreeDPTable", "PhredGenotypeLikelihoods", "Read", "ReadSet",
     "Variant", "PhasingAlgorithm",
 ]

@@ -11,6 +11,8 @@ import subprocess
 from functools import lru_cache
 from typing import Optional, Tuple
 
+import numpy as np
+
 from ._abi import CProblem, CSolution, CStats, FlatProblem, FlatSolution, raise_for
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -39,6 +41,7 @@ EXPORTS = (
     "whmec_selector_rescore",
     "whmec_selector_bridge",
     "whmec_read_sort_key",
+    "whmec_genotype",
 )
 
 
@@ -68,6 +71,8 @@ def lib() -> C.CDLL:
     L.whmec_plan_destroy.argtypes = [C.c_void_p]
     L.whmec_plan_destroy.restype = None
     L.whmec_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
+    L.whmec_genotype.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
+    L.whmec_genotype.restype = C.c_int
     L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
     L.whmec_read_sort_key.restype = C.c_uint64
     u32p = C.POINTER(C.c_uint32)
@@ -110,6 +115,16 @@ def solve(prob: FlatProblem, device: int = 0) -> Tuple[FlatSolution, dict]:
     raise_for(rc, err.value.decode())
     sol.cost = int(cs.cost)
     return sol, st.as_dict()
+
+
+def genotype(prob: FlatProblem, device: int = 0) -> Tuple[np.ndarray, dict]:
+    """Genotype likelihoods [n_ind, n_cols, 3] by the forward-backward DP (`whmec_genotype`); `prob.gl` holds the priors."""
+    out = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
+    cp, st = prob.as_c(), CStats()
+    err = C.create_string_buffer(512)
+    rc = lib().whmec_genotype(C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), device, C.byref(st), err, len(err))
+    raise_for(rc, err.value.decode())
+    return out, st.as_dict()
 
 
 class Plan:

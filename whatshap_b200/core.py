@@ -667,3 +667,28 @@ class PedigreeDPTable:
 
     def get_optimal_partitioning(self) -> List[int]:
         return self._solution.partition.tolist()
+
+
+class GenotypeDPTable:
+    """Genotype likelihoods by the forward-backward algorithm over the same bipartition DP; the constructor
+    does all the work (core.pyx:581-600, src/genotypedptable.cpp:17-48).  `pedigree` must carry genotype
+    likelihoods (priors) for every variant; `recombcost` are phred-scaled recombination probabilities."""
+
+    def __init__(self, numeric_sample_ids: NumericSampleIds, readset: ReadSet, recombcost, pedigree: Pedigree,
+                 positions=None, device: int = 0):
+        if not isinstance(readset, ReadSet):
+            raise TypeError("Argument 'readset' has incorrect type")
+        if not isinstance(pedigree, Pedigree):
+            raise TypeError("Argument 'pedigree' has incorrect type")
+        self.pedigree = pedigree
+        self.numeric_sample_ids = numeric_sample_ids
+        # the priors travel in the `gl` array of the flat problem (as they do for distrusted genotypes)
+        self._problem = _flatten(readset, recombcost, pedigree, True, positions)
+        self._likelihoods, self.stats = _lib.genotype(self._problem, device=device)
+
+    def get_genotype_likelihoods(self, sample_id, pos: int) -> PhredGenotypeLikelihoods:
+        """Likelihoods of 0/0, 0/1, 1/1 of `sample_id` at column `pos` (src/genotypedptable.cpp:445-451)."""
+        index = self.pedigree.id_to_index(self.numeric_sample_ids[sample_id])
+        if not 0 <= pos < self._problem.n_cols:
+            raise IndexError("position index out of range")  # assert in the reference
+        return PhredGenotypeLikelihoods(self._likelihoods[index, pos].tolist())

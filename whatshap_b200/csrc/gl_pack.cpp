@@ -1,0 +1,124 @@
+// Host packing of the genotyping DP (gl_pack.h).  Restates, once per problem:
+//   phred -> error probability          src/genotypecolumncostcomputer.cpp:24-45
+//   transmission transition matrix      src/transitionprobabilitycomputer.cpp:18-44
+//   allele-assignment priors            src/transitionprobabilitycomputer.cpp:46-89
+// in the reference's long double arithmetic, rounded to double for the device.
+#include "gl_pack.h"
+
+#include <cmath>
+#include <map>
+
+namespace whmec {
+
+namespace {
+
+long double phred_probability(uint32_t phred) {  // genotypecolumncostcomputer.cpp:24-45
+    if (phred == 0) return 0.9999L;
+    return powl(10.0L, -(long double)(int)phred / 10.0L);
+}
+
+}  // namespace
+
+int gl_pack(const whmec_problem *p, Packed &pk, GlPacked &g, std::string &err) {
+    g = GlPacked();
+    if (p->n_cols > 0 && !p->gl) {
+        // assert(gls != nullptr), transitionprobabilitycomputer.cpp:66
+        err = "genotyping needs genotype likelihoods (priors) for every individual and column";
+        return WHMEC_ERR_INPUT;
+    }
+    whmec_problem q = *p;
+    q.distrust = 1;  // the column structure does not depend on genotypes; no genotype constraint applies here
+    int rc = pack_problem(&q, pk, err, false);
+    if (rc != WHMEC_OK) return rc;
+    for (uint32_t r = 0; r < pk.n_reads; ++r)
+        if (pk.read_first[r] == pk.read_last[r]) {
+            // the reference asserts first column < last column (backwardcolumniterator.cpp:41) and aborts
+            err = "genotyping: a read covers a single variant (reads need at least two)";
+            return WHMEC_ERR_INPUT;
+        }
+    const uint32_t n = pk.n, T = pk.T, P = pk.P, nA = 1u << P, n_ind = pk.n_ind;
+    if (n_ind > GL_MAX_IND || P > GL_MAX_P) {
+        err = "unsupported pedigree size for genotyping";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
+    g.cols.resize(n);
+    g.eps.resize(pk.act_phred.size());
+    for (size_t e = 0; e < pk.act_phred.size(); ++e) g.eps[e] = (double)phred_probability(pk.act_phred[e]);
+    g.trans.resize((size_t)n * T * T);
+    g.q.resize((size_t)n * T * nA);
+    const uint32_t trio_bits = pk.tb;
+    for (uint32_t k = 0; k < n; ++k) {
+        const ColMeta &m = pk.cols[k];
+        GlCol &c = g.cols[k];
+        c.a = m.a;
+        c.bw = m.bw;
+        c.keep = m.keep;
+        c.f = m.f;
+        // Without transmission values (T == 1) a chain boundary hands over a single number, which cancels in the
+        // per-column normalisation: every DP-independent chain is then a table of its own (and they can be
+        // processed group by group when the backward tables of all columns do not fit the device).
+        c.first = (k == 0) || (T == 1 && pk.cols[k - 1].f == 0);
+        c.last = (k + 1 == n) || (T == 1 && m.f == 0);
+        c.act_off = pk.act_off[k];
+        c.beta_off = g.beta_doubles;
+        const uint64_t proj = ((uint64_t)1 << m.f) * T;
+        if (!c.last) g.beta_doubles += proj;
+        g.max_proj = std::max(g.max_proj, proj);
+        c.trans_off = (uint64_t)k * T * T;
+        c.q_off = (uint64_t)k * T * nA;
+        // transmission transitions
+        const long double r = powl(10.0L, -(long double)p->recombcost[k] / 10.0L);
+        std::vector<long double> bern(trio_bits + 1);
+        for (uint32_t i = 0; i <= trio_bits; ++i) bern[i] = powl(r, (long double)i) * powl(1.0L - r, (long double)(trio_bits - i));
+        for (uint32_t i = 0; i < T; ++i) {
+            long double norm = 0.0L;
+            for (uint32_t j = 0; j < T; ++j) norm += bern[popc32(i ^ j)];
+            for (uint32_t j = 0; j < T; ++j) g.trans[c.trans_off + (size_t)i * T + j] = (double)(bern[popc32(i ^ j)] / norm);
+        }
+        // allele-assignment priors
+        for (uint32_t i = 0; i < T; ++i) {
+            const int8_t *h = &pk.h2p[(size_t)i * n_ind * 2];
+            std::map<std::vector<uint8_t>, size_t> count;
+            std::vector<std::vector<uint8_t>> geno(nA);
+            std::vector<long double> prob(nA);
+            for (uint32_t A = 0; A < nA; ++A) {
+                long double pr = 1.0L;
+                std::vector<uint8_t> gv(n_ind);
+                for (uint32_t ind = 0; ind < n_ind; ++ind) {
+                    const uint32_t gi = ((A >> h[2 * ind]) & 1u) + ((A >> h[2 * ind + 1]) & 1u);
+                    pr *= p->gl[((size_t)ind * n + k) * 3 + gi];
+                    gv[ind] = (uint8_t)gi;
+                }
+                count[gv] += 1;
+                prob[A] = pr;
+                geno[A] = gv;
+            }
+            long double norm = 0.0L;
+            for (uint32_t A = 0; A < nA; ++A) {
+                prob[A] /= count[geno[A]];
+                norm += prob[A];
+            }
+            for (uint32_t A = 0; A < nA; ++A) g.q[c.q_off + (size_t)i * nA + A] = (double)(prob[A] / norm);
+        }
+    }
+    return WHMEC_OK;
+}
+
+void gl_scale_host(double *v, uint64_t n) {
+    double mx = 0.0;
+    for (uint64_t i = 0; i < n; ++i) mx = v[i] > mx ? v[i] : mx;
+    if (!(mx > 0.0)) return;
+    const double inv = 1.0 / mx;
+    for (uint64_t i = 0; i < n; ++i) v[i] *= inv;
+}
+
+void gl_normalise(const double *acc, uint32_t n, uint32_t n_ind, double *likelihoods) {
+    for (uint32_t k = 0; k < n; ++k) {
+        const double *a0 = acc + (size_t)k * n_ind * 3;
+        const double total = a0[0] + a0[1] + a0[2];  // every (x, i, A) lands in exactly one genotype of each individual
+        for (uint32_t ind = 0; ind < n_ind; ++ind)
+            for (uint32_t gi = 0; gi < 3; ++gi) likelihoods[((size_t)ind * n + k) * 3 + gi] = a0[ind * 3 + gi] / total;
+    }
+}
+
+}  // namespace whmec

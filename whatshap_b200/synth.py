@@ -335,3 +335,51 @@ def het_path_cost(prob: FlatProblem, path_index: np.ndarray) -> int:
     D = np.bincount(cols, weights=np.where(mismatch, w, 0), minlength=n)
     W = np.bincount(cols, weights=np.where(valid, w, 0), minlength=n)
     return int(np.minimum(D, W - D).sum())
+
+
+def genotyping_problem(
+    rng: np.random.Generator,
+    n_cols: int,
+    max_cov: int,
+    pedigree: str = "single",
+    max_phred: int = 40,
+    recomb_max: int = 30,
+    prior: str = "random",
+    **kw,
+) -> FlatProblem:
+    """Irregular instance for the forward-backward genotyping DP (GenotypeDPTable): as `random_problem`, but every
+    read covers at least two variants (the reference asserts that, src/backwardcolumniterator.cpp:41), `gl` holds
+    genotype PRIORS (probabilities; `uniform`, `random`, or `sparse` = with exact zeros) and recombination costs
+    are phred-scaled probabilities."""
+    base = random_problem(rng, n_cols, max_cov, pedigree, distrust=False, max_phred=max_phred, **kw)
+    off = base.read_off.astype(np.int64)
+    first = base.ent_col[off[:-1]] if base.n_reads else np.zeros(0, np.uint32)
+    last = base.ent_col[off[1:] - 1] if base.n_reads else np.zeros(0, np.uint32)
+    keep = np.nonzero(last > first)[0]
+    sel = np.concatenate([np.arange(off[r], off[r + 1]) for r in keep]) if keep.size else np.zeros(0, np.int64)
+    lens = (off[1:] - off[:-1])[keep]
+    new_off = np.zeros(keep.size + 1, np.uint64)
+    np.cumsum(lens, out=new_off[1:])
+    n_ind = base.n_ind
+    if prior == "uniform":
+        gl = np.full((n_ind, n_cols, 3), 1.0 / 3.0)
+    else:
+        gl = rng.random((n_ind, n_cols, 3)) + 0.05
+        if prior == "sparse":
+            gl[rng.random((n_ind, n_cols, 3)) < 0.15] = 0.0
+            gl[..., 1] = np.maximum(gl[..., 1], 0.05)  # keep every column feasible for every individual
+        gl /= gl.sum(axis=2, keepdims=True)
+    return FlatProblem(
+        positions=base.positions,
+        read_off=new_off,
+        ent_col=base.ent_col[sel],
+        ent_allele=base.ent_allele[sel],
+        ent_phred=base.ent_phred[sel],
+        read_ind=base.read_ind[keep],
+        recombcost=rng.integers(0, recomb_max + 1, n_cols).astype(np.uint32),
+        n_ind=n_ind,
+        trios=base.trios,
+        distrust=True,
+        gt=None,
+        gl=gl,
+    )
