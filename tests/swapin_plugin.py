@@ -1,5 +1,5 @@
 """pytest plugin used by test_reference_suite_with_swapin.py: before the reference's test modules are
-imported, replace `whatshap.core.PedigreeDPTable` by this repository's swap-in class (the CPU checker
+imported, replace `whatshap.core.PedigreeDPTable` / `GenotypeDPTable` by this repository's swap-in classes (the CPU checker
 stands in for the per-call CUDA solve; the CUDA path itself is held to the same checker by the GPU tests)
 and the host steps around the DP by this repository's: `whatshap.readselect.readselection`,
 `whatshap.priorityqueue.PriorityQueue`, `whatshap.pedigree.find_recombination` / `centimorgen_to_phred`."""
@@ -24,6 +24,12 @@ from oracle import checker  # noqa: E402
 from whatshap_b200 import adapters  # noqa: E402
 
 core.PedigreeDPTable = adapters.make_dp_table_class(core, solver=checker.port().solve)
+# the genotyping DP: the kernels' per-cell code + host packer stepped on the host (tests/emul); the exact genotype
+# priors reach the adapter through a recording Pedigree subclass (the real class has no getters)
+import emul_genotype  # noqa: E402
+
+core.Pedigree = adapters.recording_pedigree(core.Pedigree)
+core.GenotypeDPTable = adapters.make_genotype_table_class(core, solver=lambda p: emul_genotype.genotype(p)[0])
 
 from whatshap_b200 import pedigree as my_pedigree  # noqa: E402
 from whatshap_b200 import priorityqueue as my_queue  # noqa: E402

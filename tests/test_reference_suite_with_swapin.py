@@ -2,7 +2,8 @@
 tests/test_verification.py — SURVEY.md §4) run unmodified from /root/reference with
 `whatshap.core.PedigreeDPTable` replaced by this repository's swap-in class operating on the real
 Cython ReadSet / Pedigree objects, and with the host steps around the DP (read selection, its priority queue,
-recombination events) replaced too: tests/test_readselect.py, tests/test_priorityqueue.py, tests/test_pedigree.py.
+recombination events) replaced too: tests/test_readselect.py, tests/test_priorityqueue.py, tests/test_pedigree.py; and the
+reference's genotyping tests (tests/test_genotyping.py, tests/test_pedigreegenotyping.py) with `GenotypeDPTable` replaced.
 Authoring container only (needs /root/reference)."""
 import os
 import subprocess
@@ -23,7 +24,8 @@ def test_reference_tests_pass_with_swapped_dp_table():
     env = dict(os.environ, WHMEC_PYREF=pyref, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), pyref, ROOT]))
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "swapin_plugin",
            "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py",
-           "tests/test_readselect.py", "tests/test_priorityqueue.py", "tests/test_pedigree.py"]
+           "tests/test_readselect.py", "tests/test_priorityqueue.py", "tests/test_pedigree.py",
+           "tests/test_genotyping.py", "tests/test_pedigreegenotyping.py"]
     res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=900)
     tail = (res.stdout + res.stderr)[-2000:]
     assert res.returncode == 0, tail

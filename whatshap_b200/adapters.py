@@ -239,3 +239,28 @@ def make_dp_table_class(core_module, solver=None):
             return self._solution.partition.tolist()
 
     return PedigreeDPTable
+
+
+def make_genotype_table_class(core_module, solver=None):
+    """A `GenotypeDPTable` look-alike (constructor and `get_genotype_likelihoods` of whatshap/core.pyx:581-600) that
+    runs the forward-backward DP on the GPU from `core_module`'s own objects and answers with its
+    `PhredGenotypeLikelihoods`.  The pedigree should be a `recording_pedigree` (exact genotype priors; the `str()`
+    fallback keeps 6 significant digits).  `solver(problem) -> ndarray [n_ind, n_cols, 3]` defaults to the CUDA path."""
+    Likelihoods = core_module.PhredGenotypeLikelihoods
+
+    class GenotypeDPTable:
+        def __init__(self, numeric_sample_ids, readset, recombcost, pedigree, positions=None):
+            self.pedigree = pedigree
+            self.numeric_sample_ids = numeric_sample_ids
+            # the priors travel where distrusted genotypes carry their likelihoods
+            self._problem, self._ids = flatten_objects(readset, recombcost, pedigree, True, positions)
+            run = solver or (lambda p: _lib.genotype(p)[0])
+            self._likelihoods = run(self._problem)
+
+        def get_genotype_likelihoods(self, sample_id, pos):
+            index = self._ids.index(self.numeric_sample_ids[sample_id])
+            if not 0 <= pos < self._problem.n_cols:
+                raise IndexError("position index out of range")
+            return Likelihoods(self._likelihoods[index, pos].tolist())
+
+    return GenotypeDPTable
