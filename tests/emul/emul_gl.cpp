@@ -8,7 +8,7 @@
 
 using namespace whmec;
 
-extern "C" int whemul_genotype(const whmec_problem *p, double *likelihoods, char *err, size_t errlen) {
+extern "C" int whemul_genotype_grouped(const whmec_problem *p, double *likelihoods, uint32_t group_tables, char *err, size_t errlen) {
     Packed pk;
     GlPacked g;
     std::string msg;
@@ -24,22 +24,47 @@ extern "C" int whemul_genotype(const whmec_problem *p, double *likelihoods, char
     if (n == 0) return WHMEC_OK;
     const GlView v = g.view(pk);
     auto add = [](double *addr, double val) { *addr += val; };
-    std::vector<double> beta(g.beta_doubles + 1, 0.0), F[2], acc((size_t)n * n_ind * 3, 0.0);
-    F[0].assign(g.max_proj, 0.0);
-    F[1].assign(g.max_proj, 0.0);
-    for (uint32_t k = n - 1; k >= 1; --k) {
-        if (g.cols[k].first) continue;  // nothing enters the first column of a table from the left
-        double *out = beta.data() + g.cols[k - 1].beta_off;
-        for (uint64_t x = 0; x < ((uint64_t)1 << g.cols[k].a); ++x) gl_backward_cell(v, k, (uint32_t)x, beta.data() + g.cols[k].beta_off, out, add);
-        gl_scale_host(out, ((uint64_t)1 << g.cols[k - 1].f) * T);
+    std::vector<double> acc((size_t)n * n_ind * 3, 0.0);
+    // groups of whole tables, as whmec_genotype forms them when the backward tables do not fit the device together
+    // (`group_tables` tables per group; 0 = everything in one group); each group runs its launch schedule (gl_schedule)
+    std::vector<uint32_t> group_begin{0};
+    {
+        uint32_t tables = 0;
+        for (uint32_t k = 0; k < n; ++k)
+            if (g.cols[k].last && k + 1 < n && group_tables && ++tables % group_tables == 0) group_begin.push_back(k + 1);
+        group_begin.push_back(n);
     }
-    for (uint32_t k = 0; k < n; ++k) {
-        std::vector<double> &cur = F[k & 1], &prev = F[(k + 1) & 1];
-        for (uint64_t x = 0; x < ((uint64_t)1 << g.cols[k].a); ++x)
-            gl_forward_cell(v, k, (uint32_t)x, prev.data(), cur.data(), beta.data() + g.cols[k].beta_off, acc.data() + (size_t)k * n_ind * 3, add);
-        if (!g.cols[k].last) gl_scale_host(cur.data(), ((uint64_t)1 << g.cols[k].f) * T);
-        std::fill(prev.begin(), prev.end(), 0.0);
+    for (size_t q = 0; q + 1 < group_begin.size(); ++q) {
+        GlSchedule sc;
+        gl_schedule(g, T, group_begin[q], group_begin[q + 1], sc);
+        std::vector<double> beta(sc.beta_doubles + 1, 0.0), F(sc.f_pool_doubles, 0.0);
+        auto table_of = [&](uint32_t k) { return beta.data() + (g.cols[k].beta_off - sc.beta_base); };
+        for (size_t l = 0; l + 1 < sc.bwd_begin.size(); ++l) {
+            for (uint32_t e = sc.bwd_begin[l]; e < sc.bwd_begin[l + 1]; ++e) {  // the cells of one launch
+                const GlStep &st = sc.steps[e];
+                for (uint64_t x = 0; x < ((uint64_t)1 << st.cells_log2); ++x)
+                    gl_backward_cell(v, st.k, (uint32_t)x, table_of(st.k), beta.data() + st.cur_off, add);
+            }
+            for (uint32_t e = sc.bwd_begin[l]; e < sc.bwd_begin[l + 1]; ++e) gl_scale_host(beta.data() + sc.steps[e].cur_off, sc.steps[e].n_scale);
+        }
+        for (size_t l = 0; l + 1 < sc.fwd_begin.size(); ++l) {
+            for (uint32_t e = sc.fwd_begin[l]; e < sc.fwd_begin[l + 1]; ++e) {
+                const GlStep &st = sc.steps[e];
+                for (uint64_t x = 0; x < ((uint64_t)1 << st.cells_log2); ++x)
+                    gl_forward_cell(v, st.k, (uint32_t)x, F.data() + st.prev_off, F.data() + st.cur_off, table_of(st.k),
+                                    acc.data() + (size_t)st.k * n_ind * 3, add);
+            }
+            for (uint32_t e = sc.fwd_begin[l]; e < sc.fwd_begin[l + 1]; ++e) {
+                const GlStep &st = sc.steps[e];
+                gl_scale_host(F.data() + st.cur_off, st.n_scale);
+                std::fill(F.begin() + st.prev_off, F.begin() + st.prev_off + st.n_clear, 0.0);
+            }
+        }
     }
     gl_normalise(acc.data(), n, n_ind, likelihoods);
     return WHMEC_OK;
+}
+
+extern "C" int whemul_genotype(const whmec_problem *p, double *likelihoods, char *err, size_t errlen) {
+    return whemul_genotype_grouped(p, likelihoods, 0, err, errlen);
 }

@@ -79,6 +79,17 @@ def test_kernel_code_on_many_chains_and_wide_columns():
         assert np.allclose(got.sum(axis=2), 1.0, atol=1e-12)
 
 
+def test_groups_of_tables_give_the_same_likelihoods():
+    """The launch schedule (one launch = one column of every table of a group, gl_schedule) with 1, 2, 3 tables per group."""
+    rng = np.random.default_rng(13)
+    prob = synth.genotyping_problem(rng, 150, 5, "single", prior="random", burst=3, mean_len=3.0)
+    whole, _ = emul_genotype.genotype(prob)
+    assert close(whole, checker.port().genotype(prob), TOL_DEVICE)
+    for per_group in (1, 2, 3):
+        got, _ = emul_genotype.genotype(prob, group_tables=per_group)
+        assert np.array_equal(got, whole, equal_nan=True), per_group
+
+
 @pytest.fixture
 def emulated_backend(monkeypatch):
     monkeypatch.setattr(_lib, "genotype", emul_genotype.genotype)

@@ -4,10 +4,11 @@
 //
 // One thread per DP cell (bipartition x of a column); a cell adds its contribution to the projection entry it
 // maps to with a double-precision atomicAdd (several cells share an entry when reads end / start in the column).
-// Per column: backward pass  gl_backward_kernel + gl_scale_kernel,  forward pass  gl_forward_kernel + gl_scale_kernel.
+// Per step: backward pass  gl_backward_kernel + gl_scale_kernel,  forward pass  gl_forward_kernel + gl_scale_kernel;
+// one launch advances every table of a group by one column (gl_schedule, gl_pack.cpp): for a single individual the
+// DP-independent chains are tables of their own, so the launch count is 4 x (longest chain), not 4 x (columns).
 // The backward tables of all columns of a group stay in HBM (the reference keeps every sqrt(n)-th and recomputes,
-// genotypedptable.cpp:139-166,326-343).  First correct version: launch-bound (4 small launches per column);
-// batching the chains of a single individual into one launch per step is the next cut.
+// genotypedptable.cpp:139-166,326-343).
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -38,36 +39,44 @@ struct AtomicAdd {
     __device__ void operator()(double *addr, double v) const { atomicAdd(addr, v); }
 };
 
-__global__ void __launch_bounds__(GL_THREADS) gl_backward_kernel(GlView v, uint32_t k, const double *beta_k, double *out) {
+// grid.y = the tables advanced by this launch (GlStep each); grid.x covers the widest column among them
+__global__ void __launch_bounds__(GL_THREADS) gl_backward_kernel(GlView v, const GlStep *steps, double *beta, uint64_t beta_base) {
+    const GlStep st = steps[blockIdx.y];
     const uint64_t x = (uint64_t)blockIdx.x * GL_THREADS + threadIdx.x;
-    if (x >= ((uint64_t)1 << v.cols[k].a)) return;
-    gl_backward_cell(v, k, (uint32_t)x, beta_k, out, AtomicAdd());
+    if (x >= ((uint64_t)1 << st.cells_log2)) return;
+    gl_backward_cell(v, st.k, (uint32_t)x, beta + (v.cols[st.k].beta_off - beta_base), beta + st.cur_off, AtomicAdd());
 }
 
-// lacc_out: [n_ind * 3] posterior accumulators of column k
-__global__ void __launch_bounds__(GL_THREADS) gl_forward_kernel(GlView v, uint32_t k, const double *prev, double *cur, const double *beta_k,
+// lacc: [n_cols][n_ind * 3] posterior accumulators
+__global__ void __launch_bounds__(GL_THREADS) gl_forward_kernel(GlView v, const GlStep *steps, double *F, const double *beta, uint64_t beta_base,
                                                                 double *lacc_out) {
     __shared__ double s_acc[GL_MAX_IND * 3];
+    const GlStep st = steps[blockIdx.y];
+    if ((uint64_t)blockIdx.x * GL_THREADS >= ((uint64_t)1 << st.cells_log2)) return;  // whole block beyond this column (uniform)
     const uint32_t n_acc = v.n_ind * 3;
     if (threadIdx.x < n_acc) s_acc[threadIdx.x] = 0.0;
     __syncthreads();
     double lacc[GL_MAX_IND * 3];
     for (uint32_t e = 0; e < n_acc; ++e) lacc[e] = 0.0;
     const uint64_t x = (uint64_t)blockIdx.x * GL_THREADS + threadIdx.x;
-    if (x < ((uint64_t)1 << v.cols[k].a)) gl_forward_cell(v, k, (uint32_t)x, prev, cur, beta_k, lacc, AtomicAdd());
+    if (x < ((uint64_t)1 << st.cells_log2))
+        gl_forward_cell(v, st.k, (uint32_t)x, F + st.prev_off, F + st.cur_off, beta + (v.cols[st.k].beta_off - beta_base), lacc, AtomicAdd());
     for (uint32_t e = 0; e < n_acc; ++e) {
         double s = lacc[e];
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, off);
         if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(&s_acc[e], s);
     }
     __syncthreads();
-    if (threadIdx.x < n_acc && s_acc[threadIdx.x] != 0.0) atomicAdd(&lacc_out[threadIdx.x], s_acc[threadIdx.x]);
+    if (threadIdx.x < n_acc && s_acc[threadIdx.x] != 0.0) atomicAdd(&lacc_out[(size_t)st.k * n_acc + threadIdx.x], s_acc[threadIdx.x]);
 }
 
-// One block: divides the finished projection column v[0..n) by its largest entry (gl_scale_host) and clears the
-// buffer the next column accumulates into.
-__global__ void __launch_bounds__(1024) gl_scale_kernel(double *v, uint64_t n, double *clear, uint64_t n_clear) {
+// One block per table of the launch: divides the finished projection column (pool + cur_off, n_scale entries) by its
+// largest entry (gl_scale_host) and clears the buffer the table's next column accumulates into (pool + prev_off).
+__global__ void __launch_bounds__(1024) gl_scale_kernel(const GlStep *steps, double *pool) {
     __shared__ double s_max[32];
+    const GlStep st = steps[blockIdx.x];
+    double *v = pool + st.cur_off;
+    const uint64_t n = st.n_scale;
     double mx = 0.0;
     for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, v[i]);
     for (int off = 16; off > 0; off >>= 1) mx = fmax(mx, __shfl_down_sync(0xFFFFFFFFu, mx, off));
@@ -84,7 +93,8 @@ __global__ void __launch_bounds__(1024) gl_scale_kernel(double *v, uint64_t n, d
         const double inv = 1.0 / mx;
         for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) v[i] *= inv;
     }
-    for (uint64_t i = threadIdx.x; i < n_clear; i += blockDim.x) clear[i] = 0.0;
+    double *c = pool + st.prev_off;
+    for (uint64_t i = threadIdx.x; i < st.n_clear; i += blockDim.x) c[i] = 0.0;
 }
 
 struct Buffers {  // freed on every exit path
@@ -129,45 +139,57 @@ int genotype_impl(const whmec_problem *p, double *likelihoods, int device, whmec
 
     // groups of whole tables (T == 1: chains; otherwise the one table) whose backward tables fit the device together
     const size_t free_b = device_available_bytes();
-    const uint64_t fixed = (uint64_t)n * sizeof(GlCol) + g.eps.size() * 10 + (g.trans.size() + g.q.size()) * 8 + 2 * g.max_proj * 8 +
+    const uint64_t fixed = (uint64_t)n * sizeof(GlCol) + g.eps.size() * 10 + (g.trans.size() + g.q.size()) * 8 + (uint64_t)n * sizeof(GlStep) * 2 +
                            (uint64_t)n * n_ind * 3 * 8 + (512ull << 20);
     if (fixed > free_b) {
         msg = "genotyping: problem exceeds the free HBM of this device";
         return WHMEC_ERR_UNSUPPORTED;
     }
-    const uint64_t budget = (free_b - fixed) / 8;  // doubles available for backward tables
+    const uint64_t budget = (free_b - fixed) / 8;  // doubles available for backward tables + projection buffers
     std::vector<uint32_t> group_begin{0};
     {
-        uint64_t run = 0;
+        uint64_t run = 0, table = 0, widest = 1;
         uint32_t table_begin = 0;
         for (uint32_t k = 0; k < n; ++k) {
-            const uint64_t cost = g.cols[k].last ? 0 : ((uint64_t)1 << g.cols[k].f) * T;
-            run += cost;
-            if (g.cols[k].last) {  // a table ends here
-                uint64_t table = 0;
-                for (uint32_t q = table_begin; q <= k; ++q) table += g.cols[q].last ? 0 : ((uint64_t)1 << g.cols[q].f) * T;
-                if (table > budget) {
-                    msg = "genotyping: the backward tables of one chain exceed the free HBM of this device";
-                    return WHMEC_ERR_UNSUPPORTED;
-                }
-                if (run > budget) {  // close the group before this table
-                    group_begin.push_back(table_begin);
-                    run = table;
-                }
-                table_begin = k + 1;
+            if (!g.cols[k].last) {
+                const uint64_t proj = ((uint64_t)1 << g.cols[k].f) * T;
+                table += proj;
+                widest = std::max(widest, proj);
+                continue;
             }
+            // a table ends here: its backward tables and its two projection buffers
+            const uint64_t cost = table + 2 * widest;
+            if (cost > budget) {
+                msg = "genotyping: the backward tables of one chain exceed the free HBM of this device";
+                return WHMEC_ERR_UNSUPPORTED;
+            }
+            if (run + cost > budget) {  // close the group before this table
+                group_begin.push_back(table_begin);
+                run = 0;
+            }
+            run += cost;
+            table_begin = k + 1;
+            table = 0;
+            widest = 1;
         }
         group_begin.push_back(n);
     }
-    uint64_t max_group = 0;
+    // launch schedules of the groups (one launch advances every table of a group by one column)
+    std::vector<GlSchedule> schedules(group_begin.size() - 1);
+    uint64_t max_group = 0, max_pool = 1, max_steps = 1;
     for (size_t q = 0; q + 1 < group_begin.size(); ++q) {
-        const uint32_t lo = group_begin[q], hi = group_begin[q + 1];
-        const uint64_t end = g.cols[hi - 1].beta_off;  // the last column of a group ends a table: it owns no entries
-        max_group = std::max(max_group, end - g.cols[lo].beta_off);
+        gl_schedule(g, T, group_begin[q], group_begin[q + 1], schedules[q]);
+        max_group = std::max(max_group, schedules[q].beta_doubles);
+        max_pool = std::max(max_pool, schedules[q].f_pool_doubles);
+        max_steps = std::max<uint64_t>(max_steps, schedules[q].steps.size());
     }
-
+    if ((max_group + max_pool) > budget) {  // the two projection buffers per table count too
+        msg = "genotyping: backward tables and projection buffers exceed the free HBM of this device";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
     GlCol *d_cols = nullptr;
-    double *d_eps = nullptr, *d_trans = nullptr, *d_q = nullptr, *d_beta = nullptr, *d_F[2] = {nullptr, nullptr}, *d_acc = nullptr;
+    double *d_eps = nullptr, *d_trans = nullptr, *d_q = nullptr, *d_beta = nullptr, *d_F = nullptr, *d_acc = nullptr;
+    GlStep *d_steps = nullptr;
     uint8_t *d_allele = nullptr, *d_ind = nullptr;
     int8_t *d_h2p = nullptr;
     CUDA_TRY(B.alloc(&d_cols, n));
@@ -178,8 +200,8 @@ int genotype_impl(const whmec_problem *p, double *likelihoods, int device, whmec
     CUDA_TRY(B.alloc(&d_trans, g.trans.size()));
     CUDA_TRY(B.alloc(&d_q, g.q.size()));
     CUDA_TRY(B.alloc(&d_beta, max_group + 1));
-    CUDA_TRY(B.alloc(&d_F[0], g.max_proj));
-    CUDA_TRY(B.alloc(&d_F[1], g.max_proj));
+    CUDA_TRY(B.alloc(&d_F, max_pool));
+    CUDA_TRY(B.alloc(&d_steps, max_steps));
     CUDA_TRY(B.alloc(&d_acc, (size_t)n * n_ind * 3));
     uint64_t h2d = 0;
     auto up = [&](void *dst, const void *src, size_t bytes) {
@@ -194,8 +216,6 @@ int genotype_impl(const whmec_problem *p, double *likelihoods, int device, whmec
     CUDA_TRY(up(d_trans, g.trans.data(), g.trans.size() * 8));
     CUDA_TRY(up(d_q, g.q.data(), g.q.size() * 8));
     CUDA_TRY(cudaMemsetAsync(d_acc, 0, (size_t)n * n_ind * 3 * 8, s));
-    CUDA_TRY(cudaMemsetAsync(d_F[0], 0, g.max_proj * 8, s));
-    CUDA_TRY(cudaMemsetAsync(d_F[1], 0, g.max_proj * 8, s));
     const GlView v{d_cols, d_eps, d_allele, d_ind, d_h2p, d_trans, d_q, T, pk.P, n_ind};
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -203,27 +223,32 @@ int genotype_impl(const whmec_problem *p, double *likelihoods, int device, whmec
     CUDA_TRY(cudaEventCreate(&ev1));
     CUDA_TRY(cudaEventRecord(ev0, s));
     uint32_t launches = 0;
-    auto blocks_of = [&](uint32_t k) { return (unsigned)((((uint64_t)1 << g.cols[k].a) + GL_THREADS - 1) / GL_THREADS); };
+    constexpr uint32_t MAX_GRID_Y = 65535;
     for (size_t q = 0; q + 1 < group_begin.size(); ++q) {
-        const uint32_t lo = group_begin[q], hi = group_begin[q + 1];
-        const uint64_t base = g.cols[lo].beta_off;
-        // column records hold offsets into the layout of ALL backward tables; the device holds this group's, from `base` on
-        auto table_of = [&](uint32_t k) { return d_beta + (g.cols[k].beta_off - base); };
-        CUDA_TRY(cudaMemsetAsync(d_beta, 0, (g.cols[hi - 1].beta_off - base + 1) * 8, s));
-        for (uint32_t k = hi - 1; k > lo; --k) {
-            if (g.cols[k].first) continue;  // nothing enters the first column of a table from the left
-            double *out = table_of(k - 1);
-            gl_backward_kernel<<<blocks_of(k), GL_THREADS, 0, s>>>(v, k, table_of(k), out);
-            gl_scale_kernel<<<1, 1024, 0, s>>>(out, ((uint64_t)1 << g.cols[k - 1].f) * T, nullptr, 0);
-            launches += 2;
-        }
-        for (uint32_t k = lo; k < hi; ++k) {
-            double *cur = d_F[k & 1], *prev = d_F[(k + 1) & 1];
-            gl_forward_kernel<<<blocks_of(k), GL_THREADS, 0, s>>>(v, k, prev, cur, table_of(k), d_acc + (size_t)k * n_ind * 3);
-            // scale F_k (the last column of a table writes none) and clear the buffer column k+1 accumulates into
-            gl_scale_kernel<<<1, 1024, 0, s>>>(cur, g.cols[k].last ? 0 : ((uint64_t)1 << g.cols[k].f) * T, prev, g.max_proj);
-            launches += 2;
-        }
+        const GlSchedule &sc = schedules[q];
+        if (q > 0) CUDA_TRY(cudaStreamSynchronize(s));  // the step list of the previous group is still being read
+        CUDA_TRY(up(d_steps, sc.steps.data(), sc.steps.size() * sizeof(GlStep)));
+        CUDA_TRY(cudaMemsetAsync(d_beta, 0, (sc.beta_doubles + 1) * 8, s));
+        CUDA_TRY(cudaMemsetAsync(d_F, 0, sc.f_pool_doubles * 8, s));
+        auto widest = [&](uint32_t e0, uint32_t e1) {
+            uint32_t a_max = 0;
+            for (uint32_t e = e0; e < e1; ++e) a_max = std::max(a_max, sc.steps[e].cells_log2);
+            return (unsigned)((((uint64_t)1 << a_max) + GL_THREADS - 1) / GL_THREADS);
+        };
+        for (size_t l = 0; l + 1 < sc.bwd_begin.size(); ++l)
+            for (uint32_t e0 = sc.bwd_begin[l]; e0 < sc.bwd_begin[l + 1]; e0 += MAX_GRID_Y) {
+                const uint32_t e1 = std::min(sc.bwd_begin[l + 1], e0 + MAX_GRID_Y);
+                gl_backward_kernel<<<dim3(widest(e0, e1), e1 - e0), GL_THREADS, 0, s>>>(v, d_steps + e0, d_beta, sc.beta_base);
+                gl_scale_kernel<<<e1 - e0, 1024, 0, s>>>(d_steps + e0, d_beta);
+                launches += 2;
+            }
+        for (size_t l = 0; l + 1 < sc.fwd_begin.size(); ++l)
+            for (uint32_t e0 = sc.fwd_begin[l]; e0 < sc.fwd_begin[l + 1]; e0 += MAX_GRID_Y) {
+                const uint32_t e1 = std::min(sc.fwd_begin[l + 1], e0 + MAX_GRID_Y);
+                gl_forward_kernel<<<dim3(widest(e0, e1), e1 - e0), GL_THREADS, 0, s>>>(v, d_steps + e0, d_F, d_beta, sc.beta_base, d_acc);
+                gl_scale_kernel<<<e1 - e0, 1024, 0, s>>>(d_steps + e0, d_F);
+                launches += 2;
+            }
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(ev1, s));

@@ -5,6 +5,7 @@
 // in the reference's long double arithmetic, rounded to double for the device.
 #include "gl_pack.h"
 
+#include <algorithm>
 #include <cmath>
 #include <map>
 
@@ -102,6 +103,59 @@ int gl_pack(const whmec_problem *p, Packed &pk, GlPacked &g, std::string &err) {
         }
     }
     return WHMEC_OK;
+}
+
+void gl_schedule(const GlPacked &g, uint32_t T, uint32_t lo, uint32_t hi, GlSchedule &out) {
+    out = GlSchedule();
+    out.beta_base = g.cols[lo].beta_off;
+    out.beta_doubles = g.cols[hi - 1].beta_off - out.beta_base;  // the group ends a table: its last column owns no entries
+    struct Table {
+        uint32_t begin, end;  // columns [begin, end)
+        uint64_t f_off, f_size;
+    };
+    std::vector<Table> tables;
+    uint32_t longest = 0;
+    for (uint32_t k = lo, begin = lo; k < hi; ++k)
+        if (g.cols[k].last) {
+            uint64_t size = 1;
+            for (uint32_t q = begin; q <= k; ++q)
+                if (!g.cols[q].last) size = std::max(size, ((uint64_t)1 << g.cols[q].f) * T);
+            tables.push_back(Table{begin, k + 1, out.f_pool_doubles, size});
+            out.f_pool_doubles += 2 * size;
+            longest = std::max(longest, k + 1 - begin);
+            begin = k + 1;
+        }
+    // backward: step s handles the s-th column from the right of every table that still has a column to its left
+    for (uint32_t s = 0; s + 1 < longest; ++s) {
+        out.bwd_begin.push_back((uint32_t)out.steps.size());
+        for (const Table &t : tables) {
+            if (t.end - t.begin < s + 2) continue;
+            const uint32_t k = t.end - 1 - s;
+            GlStep st{};
+            st.k = k;
+            st.cells_log2 = g.cols[k].a;
+            st.cur_off = g.cols[k - 1].beta_off - out.beta_base;
+            st.n_scale = ((uint64_t)1 << g.cols[k - 1].f) * T;
+            out.steps.push_back(st);
+        }
+    }
+    out.bwd_begin.push_back((uint32_t)out.steps.size());
+    for (uint32_t s = 0; s < longest; ++s) {
+        out.fwd_begin.push_back((uint32_t)out.steps.size());
+        for (const Table &t : tables) {
+            if (t.end - t.begin <= s) continue;
+            const uint32_t k = t.begin + s;
+            GlStep st{};
+            st.k = k;
+            st.cells_log2 = g.cols[k].a;
+            st.cur_off = t.f_off + (uint64_t)(s & 1) * t.f_size;
+            st.prev_off = t.f_off + (uint64_t)((s + 1) & 1) * t.f_size;
+            st.n_scale = g.cols[k].last ? 0 : ((uint64_t)1 << g.cols[k].f) * T;
+            st.n_clear = t.f_size;
+            out.steps.push_back(st);
+        }
+    }
+    out.fwd_begin.push_back((uint32_t)out.steps.size());
 }
 
 void gl_scale_host(double *v, uint64_t n) {

@@ -21,6 +21,25 @@ struct GlPacked {
     }
 };
 
+// Launch schedule of a group of tables (columns [lo, hi), whole tables): one launch advances EVERY table of the group
+// by one column, so the launch count is 4 x (longest table) instead of 4 x (columns).  Shared by genotype.cu and the
+// test-only emulation, which executes the same steps with the same buffer offsets.
+struct GlStep {           // one column of one table inside a launch (grid.y)
+    uint32_t k;           // column
+    uint32_t cells_log2;  // a_k
+    uint64_t cur_off;     // forward: F_k in the F pool; backward: B_{k-1} in the group's backward store (doubles)
+    uint64_t prev_off;    // forward: F_{k-1} in the F pool (cleared after the step); backward: unused
+    uint64_t n_scale;     // entries of the finished column at cur_off to rescale (0: none)
+    uint64_t n_clear;     // forward: entries at prev_off to clear for the next column
+};
+struct GlSchedule {
+    std::vector<GlStep> steps;
+    std::vector<uint32_t> bwd_begin, fwd_begin;  // launch s covers steps [begin[s], begin[s + 1])
+    uint64_t beta_base = 0, beta_doubles = 0;    // the group's slice of the backward tables
+    uint64_t f_pool_doubles = 0;                 // two projection buffers per table
+};
+void gl_schedule(const GlPacked &g, uint32_t T, uint32_t lo, uint32_t hi, GlSchedule &out);
+
 // Packs `p` (whose gl holds the genotype priors; gt and distrust are ignored) for the genotyping DP.
 int gl_pack(const whmec_problem *p, Packed &pk, GlPacked &g, std::string &err);
 
