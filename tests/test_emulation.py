@@ -298,3 +298,34 @@ def test_more_than_thirty_active_reads_is_refused(emul):
 
     with pytest.raises(Unsupported, match="more than 30 reads are active"):
         run_column(emul["libwhemul.so"], synth.sliding_window(40, 31, block_len=40, seed=1), 0)
+
+
+def test_host_worker_pool_serves_concurrent_callers(emul):
+    """Packer / planner calls from several Python threads at once (ctypes releases the GIL): one caller owns the persistent
+    pool, the others fall back to short-lived threads (hostpool.cpp); every call returns the same schedule digest."""
+    import threading
+
+    lib = emul["libwhemul.so"]
+    lib.whemul_plan_digest.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_uint64)]
+    prob = synth.config("cfg3", 3000)
+    cp = prob.as_c()
+    want = C.c_uint64(0)
+    assert lib.whemul_plan_digest(C.byref(cp), C.byref(want)) == 0
+    results, errors = [], []
+
+    def work():
+        try:
+            for _ in range(6):
+                d = C.c_uint64(0)
+                rc = lib.whemul_plan_digest(C.byref(cp), C.byref(d))
+                results.append((rc, d.value))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert not errors and all(not t.is_alive() for t in threads)
+    assert len(results) == 24 and all(r == (0, want.value) for r in results)

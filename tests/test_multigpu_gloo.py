@@ -103,3 +103,41 @@ def test_ragged_blocks_balance_over_ranks():
         assert loads.max() / loads.mean() < 1.01, (world, loads)
         runs = np.array([work[a:b].sum() for a, b in multigpu.contiguous_shares(work, world)])
         assert runs.max() / runs.mean() < (1.05, 1.15, 1.3)[(2, 4, 8).index(world)], (world, runs)
+
+
+def _genotype_worker(rank, world, port, out_queue):
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    import emul_genotype
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    prob = synth.genotyping_problem(np.random.default_rng(21), 160, 5, "single", prior="random", burst=3, mean_len=3.0) if rank == 0 else None
+    got = multigpu.genotype_sharded(prob, solver=lambda p: emul_genotype.genotype(p)[0])
+    if rank == 0:
+        whole, _ = emul_genotype.genotype(prob)
+        out_queue.put((bool(np.array_equal(got, whole, equal_nan=True)), len(multigpu.independent_blocks(prob))))
+    else:
+        assert got is None
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_genotyping_shards_by_chains(world):
+    """Single individual: every rank runs the forward-backward DP on its run of chains (emulated kernels stand in for the
+    per-rank CUDA call); the gathered likelihoods equal the unsharded ones exactly."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_genotype_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    same, n_blocks = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same and n_blocks > world

@@ -309,3 +309,48 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         return None
     by_block = dict(pair for part in gathered for pair in part)
     return merge_block_solutions(prob, blocks, [by_block[b] for b in range(len(blocks))])
+
+
+def genotype_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatProblem], np.ndarray]] = None,
+                     group=None) -> Optional[np.ndarray]:
+    """Genotype likelihoods (`whmec_genotype`, the reference's GenotypeDPTable) of `prob` (given on rank 0; other ranks
+    pass None) on all ranks of `group`; returns [n_ind, n_cols, 3] on rank 0, None elsewhere.
+
+    Without transmission values every DP-independent chain is a forward-backward table of its own (a chain boundary hands
+    over one number, which cancels in each column's normalisation), so a single individual shards like the phasing DP:
+    every rank takes a contiguous run of whole chains balanced by DP cells, no collective on the data path, likelihoods
+    gathered on rank 0.  A pedigree is one table and runs on one GPU (replicas only)."""
+    import torch.distributed as dist
+
+    if solver is None:
+        import torch
+
+        from . import _lib
+
+        device = torch.cuda.current_device()
+        solver = lambda p: _lib.genotype(p, device=device)[0]
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [prob]
+    dist.broadcast_object_list(box, src=0, group=group)
+    prob = box[0]
+    if prob.n_trios > 0 or prob.n_cols == 0 or world == 1:
+        out = solver(prob) if rank == 0 else None
+        dist.barrier(group)
+        return out
+    blocks = independent_blocks(prob)
+    runs = contiguous_shares(block_work(prob, blocks), world)
+    b0, b1 = runs[rank]
+    mine = None
+    if b1 > b0:
+        lo, hi = blocks[b0][0], blocks[b1 - 1][1]
+        mine = (lo, hi, solver(prob.slice_columns(lo, hi)))
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    out = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
+    for part in gathered:
+        if part is not None:
+            lo, hi, lk = part
+            out[:, lo:hi, :] = lk
+    return out
