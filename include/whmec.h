@@ -14,6 +14,7 @@
  *   whmec_plan_*           <- same path, split into upload / forward sweep / backtrace so that
  *                             a caller (bench.py) can keep the packed ReadSet resident in HBM
  *   whmec_read_sort_key    <- ReadSet::read_comparator_t tie-break hash  src/readset.h:39-81
+ *   whmec_compute_genotypes <- compute_genotypes  src/genotyper.cpp:12-54 (priors for the genotyping DP)
  *   whmec_genotype         <- GenotypeDPTable::GenotypeDPTable  src/genotypedptable.cpp:17-48 (ctor runs the
  *                             backward and the forward pass :118-215) + get_genotype_likelihoods :445-451,
  *                             bound at whatshap/core.pyx:581-600  (sibling DP)
@@ -140,6 +141,14 @@ int whmec_solve(const whmec_problem *p, whmec_solution *s, int device, whmec_sta
  * ~1e-13 (the reference's own tests compare with 1e-9, whatshap/testhelpers.py:11-15).  st->backptr_bytes reports
  * the bytes of backward tables kept in HBM, st->sweep_ms the device time of both passes. */
 int whmec_genotype(const whmec_problem *p, double *likelihoods, int device, whmec_stats *st_or_null, char *err, size_t errlen);
+
+/* Per-column genotype priors of one sample's reads, the step `whatshap genotype` runs before the DP above
+ * (compute_genotypes, src/genotyper.cpp:12-54, bound at whatshap/core.pyx:602-617): every read entry multiplies a
+ * (hom-ref, het, hom-alt) distribution by the likelihood of its allele with error max(0.05, 10^(-phred/10)), renormalising
+ * after every factor (src/genotypedistribution.cpp:56-66).  Host only, bit-identical doubles (same operation order).
+ * Uses positions / reads of `p` (pedigree fields ignored).  gl: [n_cols][3]; gt: [n_cols], the likeliest genotype index
+ * if the probability of the others is < 0.1, else -1 (the reference's empty Genotype). */
+int whmec_compute_genotypes(const whmec_problem *p, double *gl, int8_t *gt, char *err, size_t errlen);
 
 /* ---- A pedigree table (T = 4^trios > 1) shared by several GPUs --------------------------------
  * The reference sweeps a family's table on one thread (src/pedigreedptable.cpp:84-174).  Columns that no

@@ -34,6 +34,9 @@
 #include "genotype.h"
 #include "phredgenotypelikelihoods.h"
 #include "genotypedptable.h"
+#include <cassert>
+#include "genotypedistribution.h"
+#include "genotyper.h"
 
 #include "../include/whmec.h"
 
@@ -191,6 +194,26 @@ int whref_genotype(const whmec_problem *p, double *out, double *ctor_seconds, ch
                 std::vector<long double> l = dp.get_genotype_likelihoods(i, k);
                 for (int g = 0; g < 3; ++g) q[g] = (double)l[g];
             }
+        return WHMEC_OK;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return WHMEC_ERR_INPUT;
+    }
+}
+
+// compute_genotypes (src/genotyper.cpp:12-54) on the reads of `p`: gl[k*3 + g], gt[k] in {0,1,2} or -1 (empty Genotype).
+int whref_compute_genotypes(const whmec_problem *p, double *gl, int8_t *gt, char *err, size_t errlen) {
+    try {
+        Built b;
+        build(p, b);
+        std::vector<Genotype> genotypes;
+        std::vector<GenotypeDistribution> dists;
+        std::vector<unsigned int> *positions = new std::vector<unsigned int>(b.positions);  // the callee deletes it
+        compute_genotypes(*b.rs, &genotypes, &dists, positions);
+        for (uint32_t k = 0; k < p->n_cols; ++k) {
+            for (int g = 0; g < 3; ++g) gl[(size_t)k * 3 + g] = dists[k].probabilityOf(g);
+            gt[k] = genotypes[k].is_none() ? (int8_t)-1 : (int8_t)genotypes[k].get_index();
+        }
         return WHMEC_OK;
     } catch (const std::exception &e) {
         set_err(err, errlen, e.what());

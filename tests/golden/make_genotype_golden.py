@@ -7,6 +7,8 @@ Cases
   kat.*    the read matrices of the reference's own known-answer tests (tests/test_genotyping.py:113-190 of the
            reference: uniform and non-uniform priors, phred 10), built through this package's containers; the
            likelihoods the reference's test file states are stored beside the ones the compiled reference returns
+  prior.*  24 seeded single-sample read sets with the per-column priors of the reference's compute_genotypes
+           (src/genotyper.cpp:12-54; whref_compute_genotypes), doubles stored exactly
   fuzz.*   seeded irregular instances over six pedigree shapes (gaps, blanks, phred 0..60, uniform / random / sparse
            priors, recombination costs 0..30)
 """
@@ -77,6 +79,25 @@ def main():
         if stated is not None:
             out[f"{i}.stated"] = stated
             assert np.allclose(out[f"{i}.likelihoods"][0], stated, rtol=0, atol=1e-9), label
+    # compute_genotypes (src/genotyper.cpp:12-54): per-column priors of one sample's reads, bit-exact doubles
+    import ctypes as C
+
+    from whatshap_b200._abi import CProblem
+
+    lib = ref.lib
+    lib.whref_compute_genotypes.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.POINTER(C.c_int8), C.c_char_p, C.c_size_t]
+    n_prior = 24
+    out["n_prior"] = np.array(n_prior)
+    for i in range(n_prior):
+        prob = synth.random_problem(rng, int(rng.integers(1, 80)), int(rng.integers(1, 25)), "single", max_phred=int(rng.choice([3, 20, 60])), gap=0.2)
+        gl, gt = np.zeros((prob.n_cols, 3)), np.zeros(prob.n_cols, np.int8)
+        cp, err = prob.as_c(), C.create_string_buffer(256)
+        rc = lib.whref_compute_genotypes(C.byref(cp), gl.ctypes.data_as(C.POINTER(C.c_double)), gt.ctypes.data_as(C.POINTER(C.c_int8)), err, 256)
+        assert rc == 0, err.value
+        for f in ("positions", "read_off", "ent_col", "ent_allele", "ent_phred", "read_ind", "recombcost"):
+            out[f"prior.{i}.{f}"] = getattr(prob, f)
+        out[f"prior.{i}.gl"] = gl
+        out[f"prior.{i}.gt"] = gt
     np.savez_compressed(os.path.join(HERE, "genotype.npz"), **out)
     print("wrote", len(cases), "cases")
 

@@ -185,3 +185,25 @@ def test_compiled_bridge_reads_the_same_arrays_as_the_python_api(ref_core, monke
     for field in ("positions", "read_off", "ent_col", "ent_allele", "ent_phred", "read_ind", "recombcost", "gt"):
         assert np.array_equal(getattr(fast, field), getattr(slow, field)), field
     print("flatten_objects: compiled bridge %.3f s, public Python API %.3f s" % (t_fast, t_slow))
+
+
+def test_prior_genotyper_equals_the_real_binding(ref_core):
+    """`compute_genotypes` (core.pyx:602-617) of this package and of the real extension on the same reads: same
+    Genotype objects (by alleles), same likelihood tuples, bit for bit."""
+    rng = np.random.default_rng(17)
+    for _ in range(20):
+        rows = []
+        n_cols = int(rng.integers(3, 12))
+        for _r in range(int(rng.integers(2, 14))):
+            start = int(rng.integers(0, n_cols - 1))
+            length = int(rng.integers(2, n_cols - start + 1))
+            rows.append(" " * start + "".join(rng.choice(list("01"), length)))
+        weights = "\n".join("".join(str(int(rng.integers(1, 10))) if ch != " " else " " for ch in row) for row in rows)
+        rs = string_to_readset("\n".join(rows), weights, scale_quality=int(rng.choice([1, 5, 10])))
+        rs.sort()
+        real = to_real(ref_core, rs)
+        real.sort()
+        mine_gt, mine_gl = mine.compute_genotypes(rs)
+        real_gt, real_gl = ref_core.compute_genotypes(real)
+        assert [g.as_vector() for g in mine_gt] == [g.as_vector() for g in real_gt]
+        assert [tuple(x) for x in mine_gl] == [tuple(x) for x in real_gl]

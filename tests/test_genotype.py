@@ -152,3 +152,30 @@ def test_c_abi_errors_need_no_gpu():
     if _lib.device_count() == 0:
         with pytest.raises(RuntimeError, match="CUDA"):
             _lib.genotype(prob)
+
+
+def test_prior_genotyper_is_bit_exact():
+    """compute_genotypes (src/genotyper.cpp:12-54): host code on both sides, same operation order -> identical doubles."""
+    z = np.load(os.path.join(HERE, "golden", "genotype.npz"))
+    for i in range(int(z["n_prior"])):
+        g = lambda f: z[f"prior.{i}.{f}"]
+        prob = FlatProblem(positions=g("positions"), read_off=g("read_off"), ent_col=g("ent_col"), ent_allele=g("ent_allele"),
+                           ent_phred=g("ent_phred"), read_ind=g("read_ind"), recombcost=g("recombcost"), n_ind=1)
+        gl, gt = _lib.compute_genotypes(prob)
+        assert np.array_equal(gl, g("gl")) and np.array_equal(gt, g("gt")), i
+
+
+def test_prior_genotyper_python_surface():
+    from whatshap_b200.core import Genotype, compute_genotypes
+
+    rs = string_to_readset("\n".join(["11"] * 9 + ["01"]), "\n".join(["99"] * 9 + ["11"]))  # ten reads; error floor 0.05 per read
+    genotypes, likelihoods = compute_genotypes(rs)
+    assert len(genotypes) == len(likelihoods) == 2
+    assert genotypes[1] == Genotype([1, 1]) and abs(sum(likelihoods[1]) - 1.0) < 1e-12
+    assert all(isinstance(x, tuple) and len(x) == 3 for x in likelihoods)
+    # a column with conflicting evidence stays uncalled (error probability >= 0.1 -> empty genotype)
+    mixed, _ = compute_genotypes(string_to_readset("""
+      11
+      00
+    """))
+    assert all(g.is_none() for g in mixed)

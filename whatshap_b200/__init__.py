@@ -10,6 +10,7 @@ from .core import (  # noqa: F401
     Read,
     ReadSet,
     binomial_coefficient,
+    compute_genotypes,
     get_max_genotype_alleles,
     get_max_genotype_ploidy,
 )
@@ -20,5 +21,5 @@ PhasingAlgorithm.register(PedigreeDPTable)
 
 __all__ = [
     "Genotype", "GenotypeDPTable", "NumericSampleIds", "Pedigree", "PedigreeDPTable", "PhredGenotypeLikelihoods", "Read", "ReadSet",
-    "Variant", "PhasingAlgorithm",
+    "Variant", "PhasingAlgorithm", "compute_genotypes",
 ]

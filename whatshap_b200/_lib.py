@@ -42,6 +42,7 @@ EXPORTS = (
     "whmec_selector_bridge",
     "whmec_read_sort_key",
     "whmec_genotype",
+    "whmec_compute_genotypes",
 )
 
 
@@ -73,6 +74,8 @@ def lib() -> C.CDLL:
     L.whmec_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
     L.whmec_genotype.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.c_int, C.POINTER(CStats), C.c_char_p, C.c_size_t]
     L.whmec_genotype.restype = C.c_int
+    L.whmec_compute_genotypes.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.POINTER(C.c_int8), C.c_char_p, C.c_size_t]
+    L.whmec_compute_genotypes.restype = C.c_int
     L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
     L.whmec_read_sort_key.restype = C.c_uint64
     u32p = C.POINTER(C.c_uint32)
@@ -125,6 +128,16 @@ def genotype(prob: FlatProblem, device: int = 0) -> Tuple[np.ndarray, dict]:
     rc = lib().whmec_genotype(C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), device, C.byref(st), err, len(err))
     raise_for(rc, err.value.decode())
     return out, st.as_dict()
+
+
+def compute_genotypes(prob: FlatProblem) -> Tuple[np.ndarray, np.ndarray]:
+    """Per-column genotype priors of the reads of `prob` (`whmec_compute_genotypes`, host only): (gl [n_cols, 3], gt [n_cols], -1 = none)."""
+    gl = np.zeros((prob.n_cols, 3), np.float64)
+    gt = np.zeros(prob.n_cols, np.int8)
+    cp, err = prob.as_c(), C.create_string_buffer(512)
+    rc = lib().whmec_compute_genotypes(C.byref(cp), gl.ctypes.data_as(C.POINTER(C.c_double)), gt.ctypes.data_as(C.POINTER(C.c_int8)), err, len(err))
+    raise_for(rc, err.value.decode())
+    return gl, gt
 
 
 class Plan:

@@ -525,13 +525,9 @@ class Pedigree:
         return "\n".join(out) + "\n"
 
 
-def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, distrust_genotypes: bool,
-             positions: Optional[Sequence[int]]) -> FlatProblem:
-    """ReadSet / Pedigree / recombcost -> the CSR arrays of `whmec_problem` (include/whmec.h).
-
-    Restates the input side of the reference constructor: `reassignReadIds`, the sample-id to
-    pedigree-index translation (src/pedigreedptable.cpp:24-34) and ColumnIterator's mapping of
-    positions to columns (src/columniterator.cpp:12-22)."""
+def _flatten_reads(readset: ReadSet, positions: Optional[Sequence[int]], index_of_sample):
+    """The read side of `_flatten`: (pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind).
+    `index_of_sample(sample_id)` gives the pedigree index of a read's sample."""
     if positions is None:
         pos_list = readset.get_positions()
     else:
@@ -540,7 +536,7 @@ def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, di
     reads = readset._reads
     m = len(reads)
     # -- reads: one vectorised pass over all variants (the containers keep plain Python lists) ------------
-    read_ind = np.fromiter((pedigree.id_to_index(r._sample_id) for r in reads), np.uint32, count=m)  # raises like id_to_index
+    read_ind = np.fromiter((index_of_sample(r._sample_id) for r in reads), np.uint32, count=m)  # raises like id_to_index
     lens = np.fromiter((len(r._pos) for r in reads), np.int64, count=m)
     if m and int(lens.min()) == 0:
         raise RuntimeError("No variants present")
@@ -584,7 +580,18 @@ def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, di
     kept = np.add.reduceat(valid.astype(np.int64), off[:-1]) if m else np.zeros(0, np.int64)
     read_off = np.zeros(m + 1, np.uint64)
     np.cumsum(kept, out=read_off[1:])
-    ent_col, ent_allele, ent_phred = col[valid], allele[valid], quality[valid]
+    return pos_list, read_off, col[valid], allele[valid], quality[valid], read_ind
+
+
+def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, distrust_genotypes: bool,
+             positions: Optional[Sequence[int]]) -> FlatProblem:
+    """ReadSet / Pedigree / recombcost -> the CSR arrays of `whmec_problem` (include/whmec.h).
+
+    Restates the input side of the reference constructor: `reassignReadIds`, the sample-id to
+    pedigree-index translation (src/pedigreedptable.cpp:24-34) and ColumnIterator's mapping of
+    positions to columns (src/columniterator.cpp:12-22)."""
+    pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind = _flatten_reads(readset, positions, pedigree.id_to_index)
+    n = len(pos_list)
     # -- pedigree --------------------------------------------------------------------------------------
     n_ind = len(pedigree)
     if n_ind == 0:
@@ -692,3 +699,20 @@ class GenotypeDPTable:
         if not 0 <= pos < self._problem.n_cols:
             raise IndexError("position index out of range")  # assert in the reference
         return PhredGenotypeLikelihoods(self._likelihoods[index, pos].tolist())
+
+
+def compute_genotypes(readset: ReadSet, positions=None):
+    """Per-variant genotype priors from one sample's reads, the step `whatshap genotype` runs before `GenotypeDPTable`
+    (core.pyx:602-617, src/genotyper.cpp:12-54): returns (genotypes, likelihoods) with `Genotype([])` where no genotype
+    reaches an error probability below 0.1, and likelihoods as (hom-ref, het, hom-alt) tuples.  Host only; the doubles
+    equal the reference's bit for bit."""
+    if not isinstance(readset, ReadSet):
+        raise TypeError("Argument 'readset' has incorrect type")
+    pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind = _flatten_reads(readset, positions, lambda sample: 0)
+    n = len(pos_list)
+    prob = FlatProblem(positions=np.array(pos_list, np.uint32), read_off=np.array(read_off, np.uint64), ent_col=np.array(ent_col, np.uint32),
+                       ent_allele=np.array(ent_allele, np.uint8), ent_phred=np.array(ent_phred, np.uint32),
+                       read_ind=np.array(read_ind, np.uint32), recombcost=np.zeros(n, np.uint32), n_ind=1)
+    gl, gt = _lib.compute_genotypes(prob)
+    genotypes = [Genotype(_index_to_alleles(int(g), 2)) if g >= 0 else Genotype([]) for g in gt.tolist()]
+    return genotypes, [tuple(row) for row in gl.tolist()]

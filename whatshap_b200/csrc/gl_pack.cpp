@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <map>
 
 namespace whmec {
@@ -176,3 +177,79 @@ void gl_normalise(const double *acc, uint32_t n, uint32_t n_ind, double *likelih
 }
 
 }  // namespace whmec
+
+// compute_genotypes (src/genotyper.cpp:12-54): columns are independent; within a column the factors are applied in
+// the order of the column iterator (ascending read index) so that every double equals the reference's.
+extern "C" int whmec_compute_genotypes(const whmec_problem *p, double *gl, int8_t *gt, char *err, size_t errlen) {
+    using namespace whmec;
+    std::string msg;
+    int rc = WHMEC_OK;
+    try {
+        if (!p || !gl || !gt) {
+            msg = "null argument";
+            rc = WHMEC_ERR_INPUT;
+        } else {
+            whmec_problem q = *p;
+            q.n_ind = 1;  // one sample's reads; no pedigree, no genotype constraint
+            q.n_trios = 0;
+            q.trios = nullptr;
+            q.distrust = 0;
+            std::vector<uint8_t> het(p->n_cols, 1);
+            std::vector<uint32_t> zero_ind(p->n_reads, 0), no_cost(p->n_cols, 0);
+            q.gt = het.data();
+            q.gl = nullptr;
+            q.read_ind = zero_ind.data();
+            if (!q.recombcost) q.recombcost = no_cost.data();
+            Packed pk;
+            rc = pack_problem(&q, pk, msg, false);
+            if (rc == WHMEC_OK) {
+                const uint32_t n = pk.n;
+                const uint32_t n_tasks = n / 2048 + 1, step = (n + n_tasks - 1) / n_tasks;
+                parallel_tasks(n_tasks, host_threads(16), [&](uint32_t task) {
+                    for (uint32_t k = task * step; k < std::min(n, (task + 1) * step); ++k) {
+                        double d[3] = {1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0};
+                        const uint64_t e0 = pk.act_off[k];
+                        for (uint32_t j = 0; j < pk.cols[k].a; ++j) {
+                            const uint8_t al = pk.act_allele[e0 + j];
+                            if (al > 1) continue;
+                            const double p_wrong = std::max(0.05, std::pow(10.0, -((double)pk.act_phred[e0 + j]) / 10.0));
+                            const double f_same = 2.0 / 3.0 - 1.0 / 3.0 * p_wrong, f_het = 1.0 / 3.0, f_other = 1.0 / 3.0 * p_wrong;
+                            const double f[3] = {al == 0 ? f_same : f_other, f_het, al == 0 ? f_other : f_same};
+                            double sum = 0.0;  // operator* (genotypedistribution.cpp:56-66)
+                            for (int i = 0; i < 3; ++i) {
+                                d[i] *= f[i];
+                                sum += d[i];
+                            }
+                            for (int i = 0; i < 3; ++i) d[i] /= sum;
+                        }
+                        double p_sum = 0.0;  // normalize (:24-36)
+                        for (int i = 0; i < 3; ++i) p_sum += d[i];
+                        if (p_sum <= 0.0) d[0] = d[1] = d[2] = 1.0 / 3.0;
+                        else
+                            for (int i = 0; i < 3; ++i) d[i] /= p_sum;
+                        int best_index = 0;  // likeliestGenotype / errorProbability (:12-22,37-55)
+                        double best = 0.0;
+                        for (int i = 0; i < 3; ++i)
+                            if (d[i] > best) {
+                                best = d[i];
+                                best_index = i;
+                            }
+                        double p_err = 0.0;
+                        for (int i = 0; i < 3; ++i)
+                            if (i != best_index) p_err += d[i];
+                        gt[k] = p_err < 0.1 ? (int8_t)best_index : (int8_t)-1;
+                        for (int i = 0; i < 3; ++i) gl[(size_t)k * 3 + i] = d[i];
+                    }
+                });
+            }
+        }
+    } catch (const std::exception &e) {
+        msg = e.what();
+        rc = WHMEC_ERR_INPUT;
+    }
+    if (rc != WHMEC_OK && err && errlen) {
+        std::strncpy(err, msg.c_str(), errlen - 1);
+        err[errlen - 1] = 0;
+    }
+    return rc;
+}
