@@ -73,11 +73,11 @@ WHMEC_HD uint32_t lowest_set_bits(uint32_t mask, uint32_t count) {
 // byte table `half` (0: cell bits 0..7, 1: bits 8..15).  Subset sums with one add per entry.
 WHMEC_HD void build_cost_table_run(const int32_t *delta /* [FN_STRIDE] of F */, uint32_t half, uint32_t hi4, int32_t *out16) {
     const int32_t *d = delta + half * TAB_BITS;
-    int32_t base = 0;
+    uint32_t base = 0;  // sums wrap like the reference's unsigned costs (no signed overflow)
     for (uint32_t q = 0; q < 4; ++q)
-        if ((hi4 >> q) & 1u) base += d[4 + q];
-    out16[0] = base;
-    for (uint32_t i = 1; i < 16; ++i) out16[i] = out16[i & (i - 1)] + d[ctz32(i)];
+        if ((hi4 >> q) & 1u) base += (uint32_t)d[4 + q];
+    out16[0] = (int32_t)base;
+    for (uint32_t i = 1; i < 16; ++i) out16[i] = (int32_t)((uint32_t)out16[i & (i - 1)] + (uint32_t)d[ctz32(i)]);
 }
 
 // Best key over candidates r in [r0, r1) of forward-projection entry `o` for transmission value i.

@@ -519,9 +519,10 @@ int build_outputs(const Packed &pk, const uint32_t *path_index, const uint32_t *
         for (uint32_t i = 0; i < pk.n_ind; ++i) {
             uint32_t quality = 0;
             for (uint32_t h = 0; h < 2; ++h) {
-                int q = std::abs((int)bfa[i][h][0] - (int)bfa[i][h][1]);  // (:162) int casts: UMAX -> -1
-                quality = (uint32_t)q;
-                if (q == 0) call[i][h] = WHMEC_ALLELE_EQUAL_SCORES;
+                // (:162) abs((int)c0 - (int)c1): int casts (UMAX -> -1), two's-complement difference, magnitude
+                const int32_t diff = (int32_t)(bfa[i][h][0] - bfa[i][h][1]);
+                quality = diff < 0 ? 0u - (uint32_t)diff : (uint32_t)diff;
+                if (quality == 0) call[i][h] = WHMEC_ALLELE_EQUAL_SCORES;
             }
             if (s->sr_allele) {
                 s->sr_allele[((size_t)i * 2 + 0) * n + k] = (uint8_t)call[i][0];
