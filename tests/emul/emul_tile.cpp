@@ -150,9 +150,20 @@ extern "C" int whemul_plan_handoffs(const whmec_problem *p, uint64_t *out2) {
     return 0;
 }
 
+#include <malloc.h>
+
 #include <chrono>
 // host-side timing of the packer and the tile planner (milliseconds)
+static void keep_heap_like_the_library() {
+    static bool once = false;
+    if (once) return;
+    once = true;
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+}
+
 extern "C" int whemul_time_host(const whmec_problem *p, double *out2) {
+    keep_heap_like_the_library();
     Packed pk;
     std::string msg;
     auto t0 = std::chrono::steady_clock::now();
@@ -167,16 +178,10 @@ extern "C" int whemul_time_host(const whmec_problem *p, double *out2) {
     return 0;
 }
 
-#include <malloc.h>
 // host-side timing as whmec_solve sees it for a single individual: packer without deltas, tile planner,
 // super-read construction on an arbitrary path (milliseconds); heap retention as in the library
 extern "C" int whemul_time_host_product(const whmec_problem *p, double *out3) {
-    static bool once = false;
-    if (!once) {
-        once = true;
-        mallopt(M_MMAP_THRESHOLD, 1 << 30);
-        mallopt(M_TRIM_THRESHOLD, 1 << 30);
-    }
+    keep_heap_like_the_library();
     Packed pk;
     std::string msg;
     auto t0 = std::chrono::steady_clock::now();

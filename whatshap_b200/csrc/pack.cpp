@@ -205,9 +205,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
     }
     const uint32_t n_chunks = n ? (uint32_t)cut.size() - 1 : 0;
     struct Chunk {
-        std::vector<uint32_t> fn_c0, fn_asg, fn_base, fn_group;
         size_t act_base = 0, act_count = 0;  // this chunk's slice of the (column, active read) arrays
-        std::vector<int32_t> fn_delta;
         uint32_t max_a = 0;
         uint64_t base_total = 0, rc_total = 0;
         int rc = WHMEC_OK;
@@ -242,6 +240,58 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         pk.act_ind.resize(total);
     }
 
+    // ---- pass 1: the allowed allele assignments of every (column, transmission value) depend on the genotypes only
+    //      (pedigreecolumncostcomputer.cpp:14-50); counting them first gives every column its slice of the function
+    //      arrays, so that the chunk workers write their results in place (no per-chunk buffers, no merge copy)
+    const uint32_t n_asg = 1u << P;
+    const uint32_t pack_threads = host_threads(32);
+    std::vector<uint32_t> fn_off_of(n + 1, 0);
+    // allow[t][i][g]: bit set over the assignments A under which individual i has genotype index g (columns only select)
+    const uint32_t W = (n_asg + 63) / 64;
+    std::vector<uint64_t> allow((size_t)T * p->n_ind * 3 * W, 0);
+    for (uint32_t t = 0; t < T; ++t) {
+        const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
+        for (uint32_t i = 0; i < p->n_ind; ++i)
+            for (uint32_t A = 0; A < n_asg; ++A) {
+                const uint32_t g = ((A >> h2p[2 * i]) & 1) + ((A >> h2p[2 * i + 1]) & 1);
+                allow[(((size_t)t * p->n_ind + i) * 3 + g) * W + A / 64] |= 1ull << (A % 64);
+            }
+    }
+    // allowed assignments of (column k, transmission value t) as a bit set in `out` (W words); returns their number
+    auto allowed = [&](uint32_t k, uint32_t t, uint64_t *out) -> uint32_t {
+        for (uint32_t w = 0; w < W; ++w) out[w] = ~0ull;
+        if (n_asg < 64) out[0] = (1ull << n_asg) - 1;
+        if (!p->distrust)
+            for (uint32_t i = 0; i < p->n_ind; ++i) {
+                const uint8_t g = p->gt[(size_t)i * n + k];
+                for (uint32_t w = 0; w < W; ++w) out[w] &= g <= 2 ? allow[(((size_t)t * p->n_ind + i) * 3 + g) * W + w] : 0ull;
+            }
+        uint32_t count = 0;
+        for (uint32_t w = 0; w < W; ++w) count += (uint32_t)__builtin_popcountll(out[w]);
+        return count;
+    };
+    {
+        const uint32_t n_tasks = n / 1024 + 1, step = (n + n_tasks - 1) / n_tasks;
+        parallel_tasks(n_tasks, pack_threads, [&](uint32_t task) {
+            uint64_t set[16];
+            for (uint32_t k = task * step; k < std::min(n, (task + 1) * step); ++k) {
+                uint32_t count = 0;
+                for (uint32_t t = 0; t < T; ++t) {
+                    pk.fn_group[(size_t)k * (T + 1) + t] = count;
+                    count += allowed(k, t, set);
+                }
+                pk.fn_group[(size_t)k * (T + 1) + T] = count;
+                fn_off_of[k + 1] = count;  // 0: Mendelian conflict, reported by the chunk worker in column order
+            }
+        });
+        for (uint32_t k = 0; k < n; ++k) fn_off_of[k + 1] += fn_off_of[k];
+        const size_t fn_total = fn_off_of[n];
+        pk.fn_c0.resize(fn_total);
+        pk.fn_asg.resize(fn_total);
+        pk.fn_base.resize(fn_total);
+        pk.fn_delta.resize(want_deltas ? fn_total * FN_STRIDE : 0);
+    }
+
     auto build_chunk = [&](uint32_t ci) {
         Chunk &ch = chunks[ci];
         const uint32_t kb = cut[ci], ke = cut[ci + 1];
@@ -251,12 +301,6 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         uint32_t na = 0;
         uint32_t next_read = chunk_first_read[ci];
         const uint32_t read_end = chunk_first_read[ci + 1];
-        const size_t fn_hint = (size_t)(ke - kb) * 2 * T;
-        ch.fn_c0.reserve(fn_hint);
-        ch.fn_asg.reserve(fn_hint);
-        ch.fn_base.reserve(fn_hint);
-        if (want_deltas) ch.fn_delta.reserve(fn_hint * FN_STRIDE);
-        const uint32_t n_asg = 1u << P;
         for (uint32_t k = kb; k < ke; ++k) {
             // reads that ended before k leave; the survivors are the reads shared with column k-1, which are
             // therefore the lowest bits (backward projection width, columnindexingscheme.cpp:62-85)
@@ -317,14 +361,19 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
                 for (uint32_t drop = ~keep & low_mask(na); drop; drop &= drop - 1) m.dpos[di++] = (uint8_t)ctz32(drop);
             }
 
-            // cost functions per (transmission value, allowed assignment)
-            m.fn_off = (uint32_t)ch.fn_c0.size();  // chunk-relative for now
+            // cost functions per (transmission value, allowed assignment), written to this column's slice
+            m.fn_off = fn_off_of[k];
             m.grp_off = k * (T + 1);
-            bool any = false;
+            if (fn_off_of[k + 1] == fn_off_of[k]) {  // no transmission value admits any assignment: pedigreedptable.cpp:301-303
+                ch.rc = WHMEC_ERR_MENDELIAN;
+                ch.err_col = k;
+                ch.err = "Error: Mendelian conflict";
+                return;
+            }
+            uint32_t F = m.fn_off;
             uint32_t max_base = 0;
             for (uint32_t t = 0; t < T; ++t) {
                 const int8_t *h2p = &pk.h2p[(size_t)t * p->n_ind * 2];
-                pk.fn_group[m.grp_off + t] = (uint32_t)ch.fn_c0.size() - m.fn_off;
                 // A read on haplotype 0 of its individual sits in partition h2p[ind][0] and costs its phred when
                 // the allele assigned to that partition differs from the read's (cost computer :59-67): at x = 0
                 // the cost of an assignment is a sum over partitions of S[partition][allele that differs].
@@ -332,30 +381,25 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
                 for (uint32_t q = 0; q < P; ++q) S[q][0] = S[q][1] = 0;
                 for (uint32_t j = 0; j < na; ++j)
                     if (a_allele[j] <= 1) S[h2p[2 * a_ind[j]]][a_allele[j] ^ 1] += a_phred[j];
+                uint64_t set[16];
+                allowed(k, t, set);
                 for (uint32_t A = 0; A < n_asg; ++A) {
-                    bool ok = true;
+                    if (!((set[A / 64] >> (A % 64)) & 1)) continue;
                     unsigned int base = 0;
-                    for (uint32_t i = 0; i < p->n_ind; ++i) {
-                        uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
-                        if (p->distrust) {
+                    if (p->distrust)
+                        for (uint32_t i = 0; i < p->n_ind; ++i) {
+                            const uint32_t a0 = (A >> h2p[2 * i]) & 1, a1 = (A >> h2p[2 * i + 1]) & 1;
                             // pedigreecolumncostcomputer.cpp:37  `unsigned += double`
-                            double g = p->gl[((size_t)i * n + k) * 3 + (a0 + a1)];
+                            const double g = p->gl[((size_t)i * n + k) * 3 + (a0 + a1)];
                             base = (unsigned int)((double)base + g);
-                        } else if (p->gt[(size_t)i * n + k] != a0 + a1) {
-                            ok = false;
-                            break;
                         }
-                    }
-                    if (!ok) continue;
-                    any = true;
                     max_base = std::max(max_base, base);
                     uint32_t c0 = base;
                     for (uint32_t q = 0; q < P; ++q) c0 += S[q][(A >> q) & 1];
                     if (want_deltas) {
                         // moving read j to haplotype 1 changes the cost by (cost on partition h2p[ind][1]) - (cost on h2p[ind][0])
-                        const size_t doff = ch.fn_delta.size();
-                        ch.fn_delta.resize(doff + FN_STRIDE, 0);
-                        int32_t *delta = &ch.fn_delta[doff];
+                        int32_t *delta = &pk.fn_delta[(size_t)F * FN_STRIDE];
+                        std::memset(delta, 0, sizeof(int32_t) * FN_STRIDE);
                         for (uint32_t j = 0; j < na; ++j) {
                             const uint8_t al = a_allele[j];
                             if (al > 1) continue;  // BLANK contributes nothing
@@ -366,23 +410,16 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
                             delta[j] = (int32_t)(cost1 - cost0);
                         }
                     }
-                    ch.fn_c0.push_back(c0);
-                    ch.fn_asg.push_back(A);
-                    ch.fn_base.push_back(base);
+                    pk.fn_c0[F] = c0;
+                    pk.fn_asg[F] = A;
+                    pk.fn_base[F] = base;
+                    ++F;
                 }
-            }
-            pk.fn_group[m.grp_off + T] = (uint32_t)ch.fn_c0.size() - m.fn_off;
-            if (!any) {  // no transmission value admits any assignment: pedigreedptable.cpp:301-303
-                ch.rc = WHMEC_ERR_MENDELIAN;
-                ch.err_col = k;
-                ch.err = "Error: Mendelian conflict";
-                return;
             }
             ch.base_total += max_base;
             ch.rc_total += (uint64_t)m.rc * pk.tb;
         }
     };
-    const uint32_t pack_threads = host_threads(32);
     parallel_tasks(n_chunks, pack_threads, build_chunk);
     const auto t_chunks = tnow();
     // the reference reports the first failing column (columns are visited in order)
@@ -391,37 +428,18 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
             err = chunks[ci].err;
             return chunks[ci].rc;
         }
-    // ---- merge the chunks
     uint32_t max_a = 0;
     uint64_t base_total = 0, rc_total = 0;
-    {
-        size_t fn_total = 0;
-        std::vector<size_t> fn_base_off(n_chunks);
-        for (uint32_t ci = 0; ci < n_chunks; ++ci) {
-            fn_base_off[ci] = fn_total;
-            fn_total += chunks[ci].fn_c0.size();
-            max_a = std::max(max_a, chunks[ci].max_a);
-            base_total += chunks[ci].base_total;
-            rc_total += chunks[ci].rc_total;
-        }
-        pk.fn_c0.resize(fn_total);
-        pk.fn_asg.resize(fn_total);
-        pk.fn_base.resize(fn_total);
-        pk.fn_delta.resize(want_deltas ? fn_total * FN_STRIDE : 0);
-        parallel_tasks(n_chunks, pack_threads, [&](uint32_t ci) {
-            Chunk &ch = chunks[ci];
-            std::copy(ch.fn_c0.begin(), ch.fn_c0.end(), pk.fn_c0.begin() + fn_base_off[ci]);
-            std::copy(ch.fn_asg.begin(), ch.fn_asg.end(), pk.fn_asg.begin() + fn_base_off[ci]);
-            std::copy(ch.fn_base.begin(), ch.fn_base.end(), pk.fn_base.begin() + fn_base_off[ci]);
-            std::copy(ch.fn_delta.begin(), ch.fn_delta.end(), pk.fn_delta.begin() + fn_base_off[ci] * FN_STRIDE);
-            for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) pk.cols[k].fn_off += (uint32_t)fn_base_off[ci];
-        });
-        pk.act_off[n] = pk.act_read.size();
+    for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+        max_a = std::max(max_a, chunks[ci].max_a);
+        base_total += chunks[ci].base_total;
+        rc_total += chunks[ci].rc_total;
     }
+    pk.act_off[n] = pk.act_read.size();
     pk.safe31 = (phred_total + base_total + rc_total) < (1ull << 28);
     const auto t_merge = tnow();
     if (timing)
-        std::fprintf(stderr, "[whmec] pack: validate %.2f ms, chunks(%u) %.2f ms, merge %.2f ms\n", tms(t_start, t_valid), n_chunks,
+        std::fprintf(stderr, "[whmec] pack: validate %.2f ms, count + chunks(%u) %.2f ms, totals %.2f ms\n", tms(t_start, t_valid), n_chunks,
                      tms(t_valid, t_chunks), tms(t_chunks, t_merge));
 
     // ---- chains, back-pointer layout, accounting
