@@ -2,10 +2,13 @@
 
 For a single individual (T = 1) the DP decomposes exactly at columns that no read spans: cost adds,
 partitioning / super-reads concatenate, tie-breaks are unaffected (a constant offset changes no `<`).
-Those blocks are the unit of work: rank 0 broadcasts the flat problem, every rank (one process per
-GPU, `torch.distributed` over NCCL) solves its share through the C ABI with no collective on the data
-path, and the per-block results are gathered on rank 0.  Pedigrees (T > 1) couple the blocks through
-the transmission vector and run on one GPU ("replicas only" this round).
+Those blocks are the unit of work: rank 0 scatters to every rank (one process per GPU,
+`torch.distributed` over NCCL) the blocks of its share, each rank solves them through the C ABI with
+no collective on the data path, and the per-block results are gathered on rank 0.  Pedigrees (T > 1)
+couple the blocks through the transmission vector: every rank holds a SEGMENT of the table
+(`whmec_segment_*`) and the ranks exchange T x T transfer matrices and exit tables (two all-gathers of a
+few hundred bytes), bit-identical to the single-GPU solve.  `genotype_sharded` does the same by chains for the
+forward-backward genotyping DP of a single individual.
 
 The reference has no counterpart (single process, `whatshap/cli/phase.py:604-610` runs one
 PedigreeDPTable per chromosome x family).
@@ -203,11 +206,13 @@ def solve_pedigree_segments(prob: FlatProblem, n_segments: int, segment_factory=
     return merge_block_solutions(prob, [r for r, _ in parts], [sol for _, sol in parts], cost=int(parts[-1][1].cost))
 
 
-def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) -> Tuple[bool, Optional[FlatSolution]]:
-    """T > 1: `prob` is known on every rank.  Returns (True, solution) on rank 0 and (True, None)
-    elsewhere, or (False, None) on every rank if some segment is outside what the two-pass scheme
-    handles (the caller then solves on one GPU).  Input errors (Mendelian conflict, unsorted reads) are
-    raised on every rank."""
+def solve_pedigree_sharded(prob: Optional[FlatProblem], segment_factory=None, group=None, ranges=None,
+                           my_slice: Optional[FlatProblem] = None) -> Tuple[bool, Optional[FlatSolution]]:
+    """T > 1.  Every rank holds its segment of the table: either `prob` is known on every rank (each slices its own
+    range), or `ranges` (all ranks' column ranges) and `my_slice` (this rank's columns, None for a rank without columns)
+    are given and only rank 0 needs `prob` (for merging).  Returns (True, solution) on rank 0 and (True, None)
+    elsewhere, or (False, None) on every rank if some segment is outside what the two-pass scheme handles (the
+    caller then solves on one GPU).  Input errors (Mendelian conflict, unsorted reads) are raised on every rank."""
     import torch.distributed as dist
 
     from ._abi import Unsupported
@@ -215,7 +220,9 @@ def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if segment_factory is None:
         segment_factory = _default_segment_factory()
-    ranges = segment_ranges(prob, world)
+    if ranges is None:
+        ranges = segment_ranges(prob, world)
+        my_slice = prob.slice_columns(*ranges[rank]) if ranges[rank] is not None else None
     last_active = max(r for r in range(world) if ranges[r] is not None)
 
     def everyone(value):
@@ -232,7 +239,7 @@ def solve_pedigree_sharded(prob: FlatProblem, segment_factory=None, group=None) 
     mine = ranges[rank]
     if mine is not None:
         try:
-            seg = segment_factory(prob.slice_columns(*mine), mine[0] > 0)
+            seg = segment_factory(my_slice, mine[0] > 0)
         except Unsupported as e:
             status = ("unsupported", str(e))
         except RuntimeError as e:
@@ -276,9 +283,11 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
                   group=None, segment_factory=None) -> Optional[FlatSolution]:
     """Solve `prob` (given on rank 0; other ranks pass None) on all ranks of `group`.
 
-    Returns the merged solution on rank 0 and None elsewhere.  `solver` / `segment_factory` default to
-    the CUDA path on this rank's current device; tests inject CPU stand-ins to exercise the sharding
-    logic with gloo."""
+    Rank 0 cuts the problem and SCATTERS the pieces — a rank receives only the columns and reads it works on (the
+    "trivial broadcast of the block list" of the north_star, without shipping every rank the whole ReadSet): the blocks of
+    its share for a single individual, its segment of the table for a pedigree.  Returns the merged solution on rank 0
+    and None elsewhere.  `solver` / `segment_factory` default to the CUDA path on this rank's current device; tests
+    inject CPU stand-ins to exercise the sharding logic with gloo."""
     import torch.distributed as dist
 
     if solver is None:
@@ -289,20 +298,31 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         device = torch.cuda.current_device()
         solver = lambda p: _lib.solve(p, device=device)[0]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    box = [prob]
-    dist.broadcast_object_list(box, src=0, group=group)  # "trivial broadcast of the block list"
-    prob = box[0]
-    if prob.n_trios > 0 and world > 1 and len(independent_blocks(prob)) > 1:  # transmission vectors couple the blocks
-        handled, sol = solve_pedigree_sharded(prob, segment_factory, group)
+    payloads = None
+    blocks = None
+    if rank == 0:
+        blocks = independent_blocks(prob)
+        if prob.n_trios > 0 and world > 1 and len(blocks) > 1:  # transmission vectors couple the blocks: segments of the table
+            ranges = segment_ranges(prob, world)
+            payloads = [("segments", ranges, prob.slice_columns(*r) if r is not None else None) for r in ranges]
+        elif prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or no columns: one GPU
+            payloads = [("single", None, None)] * world
+        else:
+            shares = assign_blocks(block_work(prob, blocks), world)
+            payloads = [("blocks", None, [(b, prob.slice_columns(*blocks[b])) for b in share]) for share in shares]
+    box = [None]
+    dist.scatter_object_list(box, payloads, src=0, group=group)
+    mode, ranges, piece = box[0]
+    if mode == "segments":
+        handled, sol = solve_pedigree_sharded(prob, segment_factory, group, ranges=ranges, my_slice=piece)
         if handled:
             return sol
-    if prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or outside the two-pass scheme: one GPU
+        mode = "single"  # some segment is outside the two-pass scheme: the whole table on rank 0's GPU
+    if mode == "single":
         sol = solver(prob) if rank == 0 else None
         dist.barrier(group)
         return sol
-    blocks = independent_blocks(prob)
-    shares = assign_blocks(block_work(prob, blocks), world)
-    mine = [(b, solver(prob.slice_columns(*blocks[b]))) for b in shares[rank]]
+    mine = [(b, solver(sub)) for b, sub in piece]
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(mine, gathered, dst=0, group=group)  # per-block super-reads back to rank 0
     if rank != 0:
@@ -330,20 +350,24 @@ def genotype_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[Fla
         device = torch.cuda.current_device()
         solver = lambda p: _lib.genotype(p, device=device)[0]
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    box = [prob]
-    dist.broadcast_object_list(box, src=0, group=group)
-    prob = box[0]
-    if prob.n_trios > 0 or prob.n_cols == 0 or world == 1:
+    payloads = None
+    if rank == 0:
+        if prob.n_trios > 0 or prob.n_cols == 0 or world == 1:
+            payloads = [("single", 0, 0, None)] * world
+        else:  # every rank receives only its run of chains
+            blocks = independent_blocks(prob)
+            payloads = []
+            for b0, b1 in contiguous_shares(block_work(prob, blocks), world):
+                lo, hi = (blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else (0, 0)
+                payloads.append(("chains", lo, hi, prob.slice_columns(lo, hi) if hi > lo else None))
+    box = [None]
+    dist.scatter_object_list(box, payloads, src=0, group=group)
+    mode, lo, hi, piece = box[0]
+    if mode == "single":
         out = solver(prob) if rank == 0 else None
         dist.barrier(group)
         return out
-    blocks = independent_blocks(prob)
-    runs = contiguous_shares(block_work(prob, blocks), world)
-    b0, b1 = runs[rank]
-    mine = None
-    if b1 > b0:
-        lo, hi = blocks[b0][0], blocks[b1 - 1][1]
-        mine = (lo, hi, solver(prob.slice_columns(lo, hi)))
+    mine = (lo, hi, solver(piece)) if piece is not None else None
     gathered = [None] * world if rank == 0 else None
     dist.gather_object(mine, gathered, dst=0, group=group)
     if rank != 0:
