@@ -41,3 +41,8 @@ whatshap.priorityqueue.PriorityQueue = my_queue.PriorityQueue
 whatshap.pedigree.find_recombination = my_pedigree.find_recombination
 whatshap.pedigree.centimorgen_to_phred = my_pedigree.centimorgen_to_phred
 whatshap.pedigree.RecombinationEvent = my_pedigree.RecombinationEvent
+# recombination costs fed to the pedigree / genotyping DP (tests/test_geneticmap.py of the reference)
+for name in ("GeneticMapRecombinationCostComputer", "UniformRecombinationCostComputer", "ParseError", "recombination_cost_map", "mendelian_conflict"):
+    if hasattr(my_pedigree, name) and hasattr(whatshap.pedigree, name):
+        setattr(whatshap.pedigree, name, getattr(my_pedigree, name))
+core.compute_genotypes = mine.compute_genotypes

@@ -47,7 +47,7 @@ def test_reference_tests_pass_on_this_packages_containers():
         pytest.skip("reference tree not available")
     env = dict(os.environ, WHMEC_PYREF=pyref, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "tests"), pyref, ROOT]))
     cmd = [sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-p", "swapin_all_plugin", "-k", "not hapchat",
-           "tests/test_reads.py", "tests/test_pedigree.py", "tests/test_graph.py", "tests/test_readselect.py", "tests/test_priorityqueue.py",
+           "tests/test_reads.py", "tests/test_pedigree.py", "tests/test_geneticmap.py", "tests/test_graph.py", "tests/test_readselect.py", "tests/test_priorityqueue.py",
            "tests/test_phasing.py", "tests/test_pedigreephasing.py", "tests/test_verification.py",
            "tests/test_genotyping.py", "tests/test_pedigreegenotyping.py"]
     res = subprocess.run(cmd, cwd=REF, env=env, capture_output=True, text=True, timeout=900)
