@@ -13,6 +13,17 @@ timeout 300 python scripts/gpu_ped_chain_check.py 2>&1 | tail -8 | tee gpurun_ou
 timeout 300 python scripts/gpu_extremes_check.py 2>&1 | tail -20 | tee gpurun_out/extremes_check.log
 # forward-backward genotyping DP (whmec_genotype): first run on a device; parity first, then timings
 timeout 500 python scripts/gpu_genotype_check.py 2>&1 | tail -12 | tee gpurun_out/genotype_check.log
+# ncu: launch list of the genotyping DP + one full capture of its forward kernel (only if the parity run above was green)
+if grep -q " passed" gpurun_out/genotype_check.log && ! grep -q "failed" gpurun_out/genotype_check.log; then
+  cat > gpurun_out/_gl_run.py <<'PY'
+import numpy as np
+from whatshap_b200 import _lib, synth
+prob = synth.genotyping_problem(np.random.default_rng(2), 1000, 15, "single", prior="random", burst=8, mean_len=10.0)
+_lib.genotype(prob); out, st = _lib.genotype(prob); print(st)
+PY
+  timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_genotype.csv python gpurun_out/_gl_run.py > /dev/null 2>&1
+  timeout 400 ncu --set full --clock-control none --import-source on -k regex:gl_forward_kernel -s 40 -c 1 -o gpurun_out/r02_gl_forward python gpurun_out/_gl_run.py > /dev/null 2>&1
+fi
 # headline bench with and without the pipeline (look at "e2e")
 timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_cfg3.json 2> gpurun_out/bench_cfg3.err
 WHMEC_SOLVE_GROUPS=4 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_groups4.json 2> gpurun_out/bench_cfg3_groups4.err
