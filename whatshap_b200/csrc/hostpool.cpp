@@ -14,7 +14,13 @@
 namespace whmec {
 
 uint32_t host_threads(uint32_t cap) {
-    uint32_t hw = std::max(1u, std::min(cap, std::thread::hardware_concurrency()));
+    uint32_t cores = std::max(1u, std::thread::hardware_concurrency());
+    // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): the ranks of a box share its cores
+    if (const char *e = std::getenv("LOCAL_WORLD_SIZE")) {
+        const int ranks = std::atoi(e);
+        if (ranks > 1) cores = std::max(1u, cores / (uint32_t)ranks);
+    }
+    uint32_t hw = std::min(cap, cores);
     if (const char *e = std::getenv("WHMEC_HOST_THREADS")) hw = (uint32_t)std::max(1, std::atoi(e));
     return hw;
 }
