@@ -8,7 +8,8 @@
 
 using namespace whmec;
 
-extern "C" int whemul_genotype_grouped(const whmec_problem *p, double *likelihoods, uint32_t group_tables, char *err, size_t errlen) {
+extern "C" int whemul_genotype_grouped(const whmec_problem *p, double *likelihoods, uint64_t budget_doubles, uint32_t *n_groups,
+                                       char *err, size_t errlen) {
     Packed pk;
     GlPacked g;
     std::string msg;
@@ -26,14 +27,10 @@ extern "C" int whemul_genotype_grouped(const whmec_problem *p, double *likelihoo
     auto add = [](double *addr, double val) { *addr += val; };
     std::vector<double> acc((size_t)n * n_ind * 3, 0.0);
     // groups of whole tables, as whmec_genotype forms them when the backward tables do not fit the device together
-    // (`group_tables` tables per group; 0 = everything in one group); each group runs its launch schedule (gl_schedule)
-    std::vector<uint32_t> group_begin{0};
-    {
-        uint32_t tables = 0;
-        for (uint32_t k = 0; k < n; ++k)
-            if (g.cols[k].last && k + 1 < n && group_tables && ++tables % group_tables == 0) group_begin.push_back(k + 1);
-        group_begin.push_back(n);
-    }
+    // (gl_groups with `budget_doubles`; 0 = no limit); each group runs its launch schedule (gl_schedule)
+    std::vector<uint32_t> group_begin;
+    if (!gl_groups(g, T, budget_doubles ? budget_doubles : ~0ull, group_begin)) return WHMEC_ERR_UNSUPPORTED;
+    if (n_groups) *n_groups = (uint32_t)group_begin.size() - 1;
     for (size_t q = 0; q + 1 < group_begin.size(); ++q) {
         GlSchedule sc;
         gl_schedule(g, T, group_begin[q], group_begin[q + 1], sc);
@@ -66,5 +63,5 @@ extern "C" int whemul_genotype_grouped(const whmec_problem *p, double *likelihoo
 }
 
 extern "C" int whemul_genotype(const whmec_problem *p, double *likelihoods, char *err, size_t errlen) {
-    return whemul_genotype_grouped(p, likelihoods, 0, err, errlen);
+    return whemul_genotype_grouped(p, likelihoods, 0, nullptr, err, errlen);
 }

@@ -80,14 +80,27 @@ def test_kernel_code_on_many_chains_and_wide_columns():
 
 
 def test_groups_of_tables_give_the_same_likelihoods():
-    """The launch schedule (one launch = one column of every table of a group, gl_schedule) with 1, 2, 3 tables per group."""
+    """The launch schedule (one launch = one column of every table of a group, gl_schedule) under shrinking memory budgets
+    (gl_groups): more and more groups, the same likelihoods; a budget below one table is refused."""
+    from whatshap_b200._abi import Unsupported
+
     rng = np.random.default_rng(13)
-    prob = synth.genotyping_problem(rng, 150, 5, "single", prior="random", burst=3, mean_len=3.0)
-    whole, _ = emul_genotype.genotype(prob)
-    assert close(whole, checker.port().genotype(prob), TOL_DEVICE)
-    for per_group in (1, 2, 3):
-        got, _ = emul_genotype.genotype(prob, group_tables=per_group)
-        assert np.array_equal(got, whole, equal_nan=True), per_group
+    prob = synth.sliding_window(144, 5, block_len=12, seed=13, gap=0.1)  # 12 chains of 12 columns
+    prob.gl = rng.random((1, prob.n_cols, 3)) + 0.05
+    prob.recombcost = rng.integers(0, 30, prob.n_cols).astype(np.uint32)
+    whole, info = emul_genotype.genotype(prob)
+    assert info["groups"] == 1 and close(whole, checker.port().genotype(prob), TOL_DEVICE)
+    seen, refused = set(), False
+    for budget in (20000, 2000, 1000, 600, 400, 250, 8):  # doubles; the last one is below any table
+        try:
+            got, info = emul_genotype.genotype(prob, budget_doubles=budget)
+        except Unsupported:
+            refused = True
+            continue
+        assert not refused, "a smaller budget cannot be feasible after a larger one was refused"
+        assert np.array_equal(got, whole, equal_nan=True), budget
+        seen.add(info["groups"])
+    assert refused and max(seen) > 3 and len(seen) >= 3, seen
 
 
 @pytest.fixture

@@ -146,33 +146,10 @@ int genotype_impl(const whmec_problem *p, double *likelihoods, int device, whmec
         return WHMEC_ERR_UNSUPPORTED;
     }
     const uint64_t budget = (free_b - fixed) / 8;  // doubles available for backward tables + projection buffers
-    std::vector<uint32_t> group_begin{0};
-    {
-        uint64_t run = 0, table = 0, widest = 1;
-        uint32_t table_begin = 0;
-        for (uint32_t k = 0; k < n; ++k) {
-            if (!g.cols[k].last) {
-                const uint64_t proj = ((uint64_t)1 << g.cols[k].f) * T;
-                table += proj;
-                widest = std::max(widest, proj);
-                continue;
-            }
-            // a table ends here: its backward tables and its two projection buffers
-            const uint64_t cost = table + 2 * widest;
-            if (cost > budget) {
-                msg = "genotyping: the backward tables of one chain exceed the free HBM of this device";
-                return WHMEC_ERR_UNSUPPORTED;
-            }
-            if (run + cost > budget) {  // close the group before this table
-                group_begin.push_back(table_begin);
-                run = 0;
-            }
-            run += cost;
-            table_begin = k + 1;
-            table = 0;
-            widest = 1;
-        }
-        group_begin.push_back(n);
+    std::vector<uint32_t> group_begin;
+    if (!gl_groups(g, T, budget, group_begin)) {
+        msg = "genotyping: the backward tables of one chain exceed the free HBM of this device";
+        return WHMEC_ERR_UNSUPPORTED;
     }
     // launch schedules of the groups (one launch advances every table of a group by one column)
     std::vector<GlSchedule> schedules(group_begin.size() - 1);

@@ -159,6 +159,33 @@ void gl_schedule(const GlPacked &g, uint32_t T, uint32_t lo, uint32_t hi, GlSche
     out.fwd_begin.push_back((uint32_t)out.steps.size());
 }
 
+bool gl_groups(const GlPacked &g, uint32_t T, uint64_t budget, std::vector<uint32_t> &begin) {
+    begin.assign(1, 0);
+    const uint32_t n = (uint32_t)g.cols.size();
+    uint64_t run = 0, table = 0, widest = 1;
+    uint32_t table_begin = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+        if (!g.cols[k].last) {
+            const uint64_t proj = ((uint64_t)1 << g.cols[k].f) * T;
+            table += proj;
+            widest = std::max(widest, proj);
+            continue;
+        }
+        const uint64_t cost = table + 2 * widest;  // a table ends here: its backward tables and its two projection buffers
+        if (cost > budget) return false;
+        if (run + cost > budget) {  // close the group before this table
+            begin.push_back(table_begin);
+            run = 0;
+        }
+        run += cost;
+        table_begin = k + 1;
+        table = 0;
+        widest = 1;
+    }
+    begin.push_back(n);
+    return true;
+}
+
 void gl_scale_host(double *v, uint64_t n) {
     double mx = 0.0;
     for (uint64_t i = 0; i < n; ++i) mx = v[i] > mx ? v[i] : mx;

@@ -40,6 +40,10 @@ struct GlSchedule {
 };
 void gl_schedule(const GlPacked &g, uint32_t T, uint32_t lo, uint32_t hi, GlSchedule &out);
 
+// Cuts the columns into groups of whole tables whose backward tables + two projection buffers per table stay within
+// `budget` doubles: group q = columns [begin[q], begin[q + 1]).  False if a single table exceeds the budget.
+bool gl_groups(const GlPacked &g, uint32_t T, uint64_t budget, std::vector<uint32_t> &begin);
+
 // Packs `p` (whose gl holds the genotype priors; gt and distrust are ignored) for the genotyping DP.
 int gl_pack(const whmec_problem *p, Packed &pk, GlPacked &g, std::string &err);
 
