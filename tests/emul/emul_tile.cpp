@@ -7,8 +7,64 @@
 #include "../../whatshap_b200/csrc/pack.h"
 #include "../../whatshap_b200/csrc/tile_plan.h"
 #include "../../whatshap_b200/csrc/tile_device.h"
+#include "../../whatshap_b200/csrc/tile_fast.h"
+
+#include <cstdlib>
 
 using namespace whmec;
+
+// Steady-state columns (TileCol::pad0 != 0) run the kernel's column_fast code thread by thread, as tile_panel_kernel
+// dispatches it; the warp ballots that carry the back-pointer bits are assembled from the lanes' recorded predicates.
+// WHEMUL_TILE_FAST=0 sends these columns through the generic tile_eval loop instead (the two must agree).
+namespace {
+
+uint64_t g_last_fast_columns = 0;
+
+struct RecordEmit {
+    uint32_t *words;  // back-pointer words of this warp
+    uint32_t lane;
+    void operator()(uint32_t word, bool bit) const {
+        if (bit) words[word] |= 1u << lane;
+    }
+};
+
+template <int LG, bool SHARE>
+void fast_column(const TileCol &tc, const int32_t *TW, const int32_t *T5, uint32_t cg, const uint32_t *Sin, uint32_t *Sout, uint32_t *bpw) {
+    constexpr uint32_t IT = 1u << LG;
+    for (uint32_t w = 0; w < ((1u << tc.l_out) + 31) / 32; ++w) bpw[w] = 0;
+    for (uint32_t tid = 0; tid < 1024; ++tid) {
+        RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u};
+        if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+        else column_fast<LG, true, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+    }
+}
+
+void run_fast_column(const TileCol &tc, uint32_t tile, const uint32_t *Sin, uint32_t *Sout, uint32_t *bpw) {
+    int32_t TW[32], T5[32];
+    for (uint32_t i = 0; i < 32; ++i) {
+        TW[i] = tile_fast_warp_entry(tc, tile, i);
+        T5[i] = tile_fast_lane_entry(tc, i);
+    }
+    const uint32_t cg = tile_cg(tc, tile);
+    if (tc.pad0 == 2) {
+        switch (tc.pad1) {
+            case 0: fast_column<0, true>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            case 1: fast_column<1, true>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            case 2: fast_column<2, true>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            default: fast_column<3, true>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+        }
+    } else {
+        switch (tc.pad1) {
+            case 0: fast_column<0, false>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            case 1: fast_column<1, false>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            case 2: fast_column<2, false>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            case 3: fast_column<3, false>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+            default: fast_column<4, false>(tc, TW, T5, cg, Sin, Sout, bpw); break;
+        }
+    }
+}
+
+}  // namespace
 
 // returns 100 when the planner declares the problem not eligible for the tile path
 extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint32_t chunk, uint32_t *n_panels,
@@ -42,6 +98,9 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     std::vector<uint64_t> chain_key(n_chains, KEY_INF);
     std::vector<uint32_t> bufA(1u << TILE_SMAX), bufB(1u << TILE_SMAX);
     std::vector<int32_t> TL(TILE_TL_SIZE), TH(TILE_TH_SIZE);
+    const char *fast_env = std::getenv("WHEMUL_TILE_FAST");
+    const bool use_fast = !(fast_env && fast_env[0] == '0');
+    uint64_t fast_columns = 0;
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
         for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
             const Panel &P = ts.panels[pi];
@@ -74,6 +133,10 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                             if (key < best) best = key;
                         }
                         if (best < chain_key[P.chain]) chain_key[P.chain] = best;
+                    } else if (tc.pad0 && use_fast) {
+                        run_fast_column(tc, t, Sin, Sout, arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words);
+                        ++fast_columns;
+                        std::swap(Sin, Sout);
                     } else {
                         const uint32_t ncand = 1u << tc.d;
                         for (uint32_t o = 0; o < (1u << tc.l_out); ++o) {
@@ -106,10 +169,14 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                              chain_key[c], pidx.data());
     }
     s->cost = (uint32_t)total;
+    g_last_fast_columns = fast_columns;
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail(rc);
     return WHMEC_OK;
 }
+
+// (tile, column) pairs the last whemul_tile_solve ran through column_fast
+extern "C" uint64_t whemul_last_fast_columns(void) { return g_last_fast_columns; }
 
 // planner statistics only (no DP): panels, rounds, total tiles, max tiles per round, state/bp words
 extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {

@@ -329,3 +329,31 @@ def test_host_worker_pool_serves_concurrent_callers(emul):
         t.join(timeout=120)
     assert not errors and all(not t.is_alive() for t in threads)
     assert len(results) == 24 and all(r == (0, want.value) for r in results)
+
+
+def test_steady_state_column_code_of_the_tile_kernel(emul, checker, monkeypatch):
+    """`column_fast` (whatshap_b200/csrc/tile_fast.h) — the code that executes 60 % of the tile kernel's instructions — run
+    thread by thread with its warp ballots assembled from the lanes' predicates: same cost, path and super-reads as the
+    reference, and as the generic per-output loop (WHEMUL_TILE_FAST=0), tie-heavy weights and homozygous / distrusted
+    columns (K0 active) included."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_last_fast_columns.restype = C.c_uint64
+    total_fast = 0
+    for cov, n in ((11, 30), (12, 36), (15, 34), (16, 30), (17, 26)):
+        for seed, max_phred in ((1, 40), (2, 2)):
+            prob = synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.06 * seed, max_phred=max_phred)
+            if seed == 2:  # homozygous sites make K0 finite (HASK0 variants)
+                prob.gt = prob.gt.copy()
+                prob.gt[0, ::3] = 0
+            want = checker.solve(prob)
+            monkeypatch.delenv("WHEMUL_TILE_FAST", raising=False)
+            fast = run_tile(lib, prob, 0)
+            n_fast = int(lib.whemul_last_fast_columns())
+            monkeypatch.setenv("WHEMUL_TILE_FAST", "0")
+            generic = run_tile(lib, prob, 0)
+            assert int(lib.whemul_last_fast_columns()) == 0
+            assert fast is not None and fast.same_as(want), (cov, seed, fast.diff(want))
+            assert generic.same_as(want), (cov, seed)
+            assert n_fast > 0 or cov < 12, (cov, n_fast)
+            total_fast += n_fast
+    assert total_fast > 300

@@ -16,6 +16,7 @@
 
 #include "../../include/whmec.h"
 #include "tile_device.h"
+#include "tile_fast.h"
 #include "tile_plan.h"
 
 namespace whmec {
@@ -53,22 +54,10 @@ __device__ __forceinline__ uint32_t fast_kind(const TileCol &tc) { return tc.pad
 // fast columns, the two 32-entry tables of column_fast.
 __device__ __forceinline__ void build_tables(TileSmem &S, const TileCol &tc, uint32_t tile, uint32_t which, uint32_t tid) {
     if (fast_kind(tc)) {
-        const uint32_t lg = tc.pad1;
-        if (tid < 32) {  // per-warp part: K2 + E(global reads of this tile) + output bits 5+LG .. 9+LG
-            int32_t s = tc.K2;
-            for (uint32_t b = 0; b < tc.g; ++b)
-                if ((tile >> b) & 1u) s += tc.w_global[b];
-#pragma unroll
-            for (uint32_t q = 0; q < 5; ++q)
-                if ((tid >> q) & 1u) s += tc.w_local[6 + lg + q];
-            S.TW[which][tid] = s;
-        } else if (tid < 64) {  // per-lane part: output bits 0..4
-            const uint32_t l = tid - 32;
-            int32_t s = 0;
-#pragma unroll
-            for (uint32_t q = 0; q < 5; ++q)
-                if ((l >> q) & 1u) s += tc.w_local[q + 1];
-            S.T5[which][l] = s;
+        if (tid < 32) {
+            S.TW[which][tid] = tile_fast_warp_entry(tc, tile, tid);
+        } else if (tid < 64) {
+            S.T5[which][tid - 32] = tile_fast_lane_entry(tc, tid - 32);
         } else if (tid == 64) {
             S.cg[which] = tile_cg(tc, tile);
         }
@@ -110,62 +99,12 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
     }
 }
 
-// plain expressions (no recursion, no calls) so that they fold to constants once the loops are unrolled
-#define cx_ctz(x) (((x) & 1) ? 0 : ((x) & 2) ? 1 : ((x) & 4) ? 2 : ((x) & 8) ? 3 : 4)
-#define cx_parity(x) ((((x) >> 0) ^ ((x) >> 1) ^ ((x) >> 2) ^ ((x) >> 3) ^ ((x) >> 4)) & 1)
-
-// Fast path of column_drop1 for dropped bit 0 (see fast_kind).  Warp w owns 32 * 2^LG consecutive
-// outputs; every shared-memory address inside the loop is a per-thread base plus a compile-time
-// offset, the E() of the 2^LG outputs of a thread are subset sums built with one add each, the two
-// candidate cells of an output share one 64-bit load (and with SHARE the two outputs that differ
-// only in the newly started read share it too), back-pointers leave as warp ballots.
-template <int LG, bool HASK0, bool SHARE>
-__device__ __forceinline__ void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
-                                            uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout,
-                                            uint32_t *__restrict__ bpw, uint32_t tid) {
-    constexpr int IT = 1 << LG;
-    const uint32_t lane = tid & 31u, warp = tid >> 5;
-    const uint32_t obase = warp * (IT * 32u) + lane;      // o = obase + 32*it  (+ nout/2 for the shared twin)
-    const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;    // candidate pairs of the previous projection
-    const uint2 *sin2 = reinterpret_cast<const uint2 *>(Sin) + (obase & pmask);
-    uint32_t *so = Sout + obase;
-    const uint32_t half = 1u << (tc.l_out - 1);
-    const uint32_t wp = (uint32_t)tc.w_local[0];
-    const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
-    const uint32_t K0 = tc.K0, K12 = tc.K12;
-    const uint32_t par0 = (__popc(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
-    uint32_t *bp = bpw + warp * IT;
-    uint32_t ue[IT];
-    ue[0] = (uint32_t)(TW[warp] + T5[lane]);
-#pragma unroll
-    for (int it = 1; it < IT; ++it) ue[it] = ue[it & (it - 1)] + (uint32_t)tc.w_local[6 + cx_ctz(it)];
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const uint2 s = sin2[it * 32];
-        const uint32_t par = par0 ^ (uint32_t)cx_parity(it);
-        {
-            const uint32_t u0 = ue[it], u1 = u0 + wp;
-            uint32_t c0 = min(u0, K12 - u0), c1 = min(u1, K12 - u1);
-            if (HASK0) { c0 = min(c0, K0); c1 = min(c1, K0); }
-            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
-            const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
-            so[it * 32] = min(v0, v1);
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (par != 0));
-            bp[it] = ballot;  // all lanes store the same word to the same address: one transaction, no divergence
-        }
-        if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
-            const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
-            uint32_t c0 = min(u0, K12 - u0), c1 = min(u1, K12 - u1);
-            if (HASK0) { c0 = min(c0, K0); c1 = min(c1, K0); }
-            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
-            const uint32_t parb = par ^ 1u;
-            const bool pick1 = v1 < v0 + parb;
-            so[half + it * 32] = min(v0, v1);
-            const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, pick1 != (parb != 0));
-            bp[(half >> 5) + it] = ballot;
-        }
-    }
-}
+// Back-pointer words of the fast path leave as warp ballots: all lanes store the same word to the same address (one
+// transaction, no divergence).
+struct BallotEmit {
+    uint32_t *bp;
+    __device__ __forceinline__ void operator()(uint32_t word, bool bit) const { bp[word] = __ballot_sync(0xFFFFFFFFu, bit); }
+};
 
 // Column in which no read ends (coverage still growing): one cell per output, no back-pointer.
 __device__ __forceinline__ void column_drop0(const TileCol &tc, const int32_t *__restrict__ TL, const int32_t *__restrict__ TH,
@@ -345,8 +284,8 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
             uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
             if (fast_kind(tc)) {
 #define WHMEC_FAST(LGV, SH)                                                                                      \
-    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid); \
-    else column_fast<LGV, true, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
+    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid); \
+    else column_fast<LGV, true, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid);
                 if (fast_kind(tc) == 2) {
                     switch (tc.pad1) {
                         case 0: WHMEC_FAST(0, true) break;

@@ -1,0 +1,96 @@
+// Steady-state column of the tile kernel (see tile.cu: fast_kind), as host/device code: the CUDA kernel emits the
+// back-pointer bits as warp ballots, the test-only emulation (tests/emul) records them lane by lane.
+#pragma once
+#include "tile_device.h"
+
+namespace whmec {
+
+#if defined(__CUDACC__)
+using TilePair = uint2;
+#define WHMEC_UMIN(a, b) min(a, b)
+#define WHMEC_POPC(x) popc32(x)
+#else
+struct alignas(8) TilePair {
+    uint32_t x, y;
+};
+#define WHMEC_UMIN(a, b) ((a) < (b) ? (a) : (b))
+#define WHMEC_POPC(x) popc32(x)
+#endif
+
+// The two 32-entry tables of a fast column: per warp  K2 + E(global reads of this tile) + output bits 5+LG .. 9+LG,
+// per lane the weights of output bits 0..4  (output bit q <-> local bit q + 1: local bit 0 is the read that ends).
+WHMEC_HD int32_t tile_fast_warp_entry(const TileCol &tc, uint32_t tile, uint32_t warp) {
+    const uint32_t lg = tc.pad1;
+    int32_t s = tc.K2;
+    for (uint32_t b = 0; b < tc.g; ++b)
+        if ((tile >> b) & 1u) s += tc.w_global[b];
+#pragma unroll
+    for (uint32_t q = 0; q < 5; ++q)
+        if ((warp >> q) & 1u) s += tc.w_local[6 + lg + q];
+    return s;
+}
+
+WHMEC_HD int32_t tile_fast_lane_entry(const TileCol &tc, uint32_t lane) {
+    int32_t s = 0;
+#pragma unroll
+    for (uint32_t q = 0; q < 5; ++q)
+        if ((lane >> q) & 1u) s += tc.w_local[q + 1];
+    return s;
+}
+
+// plain expressions (no recursion, no calls) so that they fold to constants once the loops are unrolled
+#define cx_ctz(x) (((x) & 1) ? 0 : ((x) & 2) ? 1 : ((x) & 4) ? 2 : ((x) & 8) ? 3 : 4)
+#define cx_parity(x) ((((x) >> 0) ^ ((x) >> 1) ^ ((x) >> 2) ^ ((x) >> 3) ^ ((x) >> 4)) & 1)
+
+// Fast path of column_drop1 for dropped bit 0 (see fast_kind).  Warp w owns 32 * 2^LG consecutive
+// outputs; every shared-memory address inside the loop is a per-thread base plus a compile-time
+// offset, the E() of the 2^LG outputs of a thread are subset sums built with one add each, the two
+// candidate cells of an output share one 64-bit load (and with SHARE the two outputs that differ
+// only in the newly started read share it too), back-pointers leave as warp ballots.
+// `emit(word, bit)`: this thread's bit of back-pointer word `word` of its warp (words are numbered from the warp's first).
+template <int LG, bool HASK0, bool SHARE, class Emit>
+WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
+                          uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
+    constexpr int IT = 1 << LG;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t obase = warp * (IT * 32u) + lane;      // o = obase + 32*it  (+ nout/2 for the shared twin)
+    const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;    // candidate pairs of the previous projection
+    const TilePair *sin2 = reinterpret_cast<const TilePair *>(Sin) + (obase & pmask);
+    uint32_t *so = Sout + obase;
+    const uint32_t half = 1u << (tc.l_out - 1);
+    const uint32_t wp = (uint32_t)tc.w_local[0];
+    const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
+    const uint32_t K0 = tc.K0, K12 = tc.K12;
+    const uint32_t par0 = (WHMEC_POPC(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
+    uint32_t ue[IT];
+    ue[0] = (uint32_t)(TW[warp] + T5[lane]);
+#pragma unroll
+    for (int it = 1; it < IT; ++it) ue[it] = ue[it & (it - 1)] + (uint32_t)tc.w_local[6 + cx_ctz(it)];
+#pragma unroll
+    for (int it = 0; it < IT; ++it) {
+        const TilePair s = sin2[it * 32];
+        const uint32_t par = par0 ^ (uint32_t)cx_parity(it);
+        {
+            const uint32_t u0 = ue[it], u1 = u0 + wp;
+            uint32_t c0 = WHMEC_UMIN(u0, K12 - u0), c1 = WHMEC_UMIN(u1, K12 - u1);
+            if (HASK0) { c0 = WHMEC_UMIN(c0, K0); c1 = WHMEC_UMIN(c1, K0); }
+            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
+            const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
+            so[it * 32] = WHMEC_UMIN(v0, v1);
+            emit((uint32_t)it, pick1 != (par != 0));
+        }
+        if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
+            const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
+            uint32_t c0 = WHMEC_UMIN(u0, K12 - u0), c1 = WHMEC_UMIN(u1, K12 - u1);
+            if (HASK0) { c0 = WHMEC_UMIN(c0, K0); c1 = WHMEC_UMIN(c1, K0); }
+            const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
+            const uint32_t parb = par ^ 1u;
+            const bool pick1 = v1 < v0 + parb;
+            so[half + it * 32] = WHMEC_UMIN(v0, v1);
+            emit((half >> 5) + (uint32_t)it, pick1 != (parb != 0));
+        }
+    }
+}
+
+
+}  // namespace whmec
