@@ -357,3 +357,15 @@ def test_steady_state_column_code_of_the_tile_kernel(emul, checker, monkeypatch)
             assert n_fast > 0 or cov < 12, (cov, n_fast)
             total_fast += n_fast
     assert total_fast > 300
+
+
+@pytest.mark.parametrize("cov,n,seed", [(18, 44, 1), (20, 48, 3)])
+def test_tile_kernel_code_at_benchmark_coverage(emul, checker, cov, n, seed):
+    """Coverage of the BASELINE.json workloads (2^18 .. 2^20 cells per column): several tiles per panel, several panels with
+    tile-major hand-offs, the steady-state column code on every tile — against the reference on a chain the CPU finishes in seconds."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_last_fast_columns.restype = C.c_uint64
+    prob = synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.05, max_phred=40 if seed % 4 == 1 else 2)
+    got = run_tile(lib, prob, 0)
+    assert got is not None and int(lib.whemul_last_fast_columns()) > 300
+    assert got.same_as(checker.solve(prob)), got.diff(checker.solve(prob))
