@@ -207,3 +207,29 @@ def test_prior_genotyper_equals_the_real_binding(ref_core):
         real_gt, real_gl = ref_core.compute_genotypes(real)
         assert [g.as_vector() for g in mine_gt] == [g.as_vector() for g in real_gt]
         assert [tuple(x) for x in mine_gl] == [tuple(x) for x in real_gl]
+
+
+def test_prior_genotyper_adapter_on_real_objects(ref_core):
+    """`adapters.make_compute_genotypes` fed the reference's real ReadSet returns what the real binding returns."""
+    rs = string_to_readset("""
+      1  11010
+      00 00101
+      001 01110
+       1    111
+       111 0101
+    """, """
+      5  92341
+      11 13452
+      334 98765
+       2    121
+       999 1111
+    """)
+    real = to_real(ref_core, rs)
+    real.sort()
+    compute = adapters.make_compute_genotypes(ref_core)
+    for positions in (None, list(real.get_positions())):
+        got_gt, got_gl = compute(real, positions)
+        want_gt, want_gl = ref_core.compute_genotypes(real, positions)
+        assert [g.as_vector() for g in got_gt] == [g.as_vector() for g in want_gt]
+        assert [tuple(x) for x in got_gl] == [tuple(x) for x in want_gl]
+        assert all(isinstance(g, ref_core.Genotype) for g in got_gt)

@@ -264,3 +264,32 @@ def make_genotype_table_class(core_module, solver=None):
             return Likelihoods(self._likelihoods[index, pos].tolist())
 
     return GenotypeDPTable
+
+
+def make_compute_genotypes(core_module):
+    """`compute_genotypes(readset, positions=None)` (whatshap/core.pyx:602-617) for `core_module`'s own ReadSet objects:
+    per-variant genotype priors through `whmec_compute_genotypes` (host; identical doubles), answered with
+    `core_module.Genotype` objects and likelihood tuples."""
+    Genotype = core_module.Genotype
+
+    class _Het:  # any genotype will do: the prior genotyper looks at the reads only
+        @staticmethod
+        def is_diploid_and_biallelic():
+            return True
+
+        @staticmethod
+        def get_index():
+            return 1
+
+    def compute_genotypes(readset, positions=None):
+        n = len(readset.get_positions()) if positions is None else len(positions)
+        samples = sorted({int(read.sample_id) for read in readset}) or [0]
+        stub = type("ReadsOnly", (), {})()
+        stub._rec_individuals = [(sid, [_Het] * n, None) for sid in samples]
+        stub._rec_trios = []
+        prob, _ = flatten_objects(readset, [0] * n, stub, False, positions)
+        gl, gt = _lib.compute_genotypes(prob)
+        alleles = ([0, 0], [0, 1], [1, 1])
+        return [Genotype(alleles[g]) if g >= 0 else Genotype([]) for g in gt.tolist()], [tuple(row) for row in gl.tolist()]
+
+    return compute_genotypes
