@@ -18,13 +18,19 @@ using namespace whmec;
 // WHEMUL_TILE_FAST=0 sends these columns through the generic tile_eval loop instead (the two must agree).
 namespace {
 
-uint64_t g_last_fast_columns = 0;
+uint64_t g_last_fast_columns = 0, g_last_packed_columns = 0;
 
 struct RecordEmit {
-    uint32_t *words;  // back-pointer words of this warp
+    uint32_t *words;  // back-pointer words of this warp (ballot order) ...
     uint32_t lane;
+    uint32_t *tile_words;  // ... or of the whole tile (thread-packed layout)
+    uint32_t tid, bits_per_thread;
     void operator()(uint32_t word, bool bit) const {
         if (bit) words[word] |= 1u << lane;
+    }
+    void store(uint32_t bits) const {  // element `tid` of `bits_per_thread` bits, little endian like the kernel's u8 / u16 stores
+        const uint32_t at = tid * bits_per_thread;
+        tile_words[at >> 5] |= (bits & low_mask(bits_per_thread)) << (at & 31u);
     }
 };
 
@@ -33,8 +39,11 @@ void fast_column(const TileCol &tc, const int32_t *TW, const int32_t *T5, uint32
     constexpr uint32_t IT = 1u << LG;
     for (uint32_t w = 0; w < ((1u << tc.l_out) + 31) / 32; ++w) bpw[w] = 0;
     for (uint32_t tid = 0; tid < 1024; ++tid) {
-        RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u};
-        if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+        RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u, bpw, tid, tile_fast_bits_per_thread(tc)};
+        if (tc.pad2) {
+            if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+            else column_fast<LG, true, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+        } else if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
         else column_fast<LG, true, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
     }
 }
@@ -100,7 +109,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     std::vector<int32_t> TL(TILE_TL_SIZE), TH(TILE_TH_SIZE);
     const char *fast_env = std::getenv("WHEMUL_TILE_FAST");
     const bool use_fast = !(fast_env && fast_env[0] == '0');
-    uint64_t fast_columns = 0;
+    uint64_t fast_columns = 0, packed_columns = 0;
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
         for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
             const Panel &P = ts.panels[pi];
@@ -136,6 +145,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                     } else if (tc.pad0 && use_fast) {
                         run_fast_column(tc, t, Sin, Sout, arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words);
                         ++fast_columns;
+                        packed_columns += tc.pad2 != 0;
                         std::swap(Sin, Sout);
                     } else {
                         const uint32_t ncand = 1u << tc.d;
@@ -170,6 +180,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     }
     s->cost = (uint32_t)total;
     g_last_fast_columns = fast_columns;
+    g_last_packed_columns = packed_columns;
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail(rc);
     return WHMEC_OK;
@@ -177,6 +188,8 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
 
 // (tile, column) pairs the last whemul_tile_solve ran through column_fast
 extern "C" uint64_t whemul_last_fast_columns(void) { return g_last_fast_columns; }
+// ... of which with thread-packed back-pointer bits (WHMEC_TILE_PACKED_BP=1)
+extern "C" uint64_t whemul_last_packed_columns(void) { return g_last_packed_columns; }
 
 // planner statistics only (no DP): panels, rounds, total tiles, max tiles per round, state/bp words
 extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {

@@ -369,3 +369,27 @@ def test_tile_kernel_code_at_benchmark_coverage(emul, checker, cov, n, seed):
     got = run_tile(lib, prob, 0)
     assert got is not None and int(lib.whemul_last_fast_columns()) > 300
     assert got.same_as(checker.solve(prob)), got.diff(checker.solve(prob))
+
+
+def test_thread_packed_back_pointers(emul, checker, monkeypatch):
+    """WHMEC_TILE_PACKED_BP=1 (experimental layout of the fast columns' back-pointer bits: each thread keeps the bits of its own
+    outputs, formed from the sign of v1 - v0 - par by a funnel shift; tile_packed_bit_index decodes them in the backtrace):
+    same results as the reference with both layouts, sliding windows (twin outputs) and irregular starts, K0 active or not."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_last_fast_columns.restype = C.c_uint64
+    lib.whemul_last_packed_columns.restype = C.c_uint64
+    monkeypatch.setenv("WHMEC_TILE_PACKED_BP", "1")
+    rng = np.random.default_rng(23)
+    n_fast = n_packed = 0
+    cases = [synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.05 * (seed % 3), max_phred=2 if seed % 2 == 0 else 40)
+             for cov, n, seed in ((13, 30, 1), (14, 30, 2), (15, 34, 3), (16, 30, 4), (17, 28, 5), (19, 40, 6))]
+    for prob in cases[1::2]:
+        prob.gt = prob.gt.copy()
+        prob.gt[0, ::4] = 2  # homozygous sites: K0 finite
+    cases += [synth.random_problem(rng, 30, cov, "single", gap=0.1, mean_len=14.0, burst=5, max_phred=3) for cov in (13, 14, 15)]
+    for prob in cases:
+        got = run_tile(lib, prob, 0)
+        assert got is not None and got.same_as(checker.solve(prob)), got.diff(checker.solve(prob))
+        n_fast += int(lib.whemul_last_fast_columns())
+        n_packed += int(lib.whemul_last_packed_columns())
+    assert n_fast > 800 and n_packed > 600  # 8 or 16 outputs per thread: coverage >= 14

@@ -104,6 +104,20 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
 struct BallotEmit {
     uint32_t *bp;
     __device__ __forceinline__ void operator()(uint32_t word, bool bit) const { bp[word] = __ballot_sync(0xFFFFFFFFu, bit); }
+    __device__ __forceinline__ void store(uint32_t) const {}
+};
+
+// Thread-packed layout (TileCol::pad2 == 1, experimental): thread `tid` owns element `tid` of BITS bits; a warp's 32
+// elements are contiguous (one 32- or 64-byte transaction).
+template <int BITS>
+struct PackedEmit {
+    uint32_t *bpw;  // the tile's slice of the arena
+    uint32_t tid;
+    __device__ __forceinline__ void operator()(uint32_t, bool) const {}
+    __device__ __forceinline__ void store(uint32_t bits) const {
+        if (BITS == 8) reinterpret_cast<uint8_t *>(bpw)[tid] = (uint8_t)bits;
+        else reinterpret_cast<uint16_t *>(bpw)[tid] = (uint16_t)bits;
+    }
 };
 
 // Column in which no read ends (coverage still growing): one cell per output, no back-pointer.
@@ -286,7 +300,16 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
 #define WHMEC_FAST(LGV, SH)                                                                                      \
     if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid); \
     else column_fast<LGV, true, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid);
-                if (fast_kind(tc) == 2) {
+#define WHMEC_FAST_PACKED(LGV, SH, BITS)                                                                          \
+    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH, true>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, PackedEmit<BITS>{bpw, tid}, tid); \
+    else column_fast<LGV, true, SH, true>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, PackedEmit<BITS>{bpw, tid}, tid);
+                if (tc.pad2) {  // thread-packed back-pointer bits (planner: 8 or 16 outputs per thread only)
+                    if (fast_kind(tc) == 2) {
+                        if (tc.pad1 == 2) { WHMEC_FAST_PACKED(2, true, 8) } else { WHMEC_FAST_PACKED(3, true, 16) }
+                    } else {
+                        if (tc.pad1 == 3) { WHMEC_FAST_PACKED(3, false, 8) } else { WHMEC_FAST_PACKED(4, false, 16) }
+                    }
+                } else if (fast_kind(tc) == 2) {
                     switch (tc.pad1) {
                         case 0: WHMEC_FAST(0, true) break;
                         case 1: WHMEC_FAST(1, true) break;
@@ -302,6 +325,7 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
                         default: WHMEC_FAST(4, false) break;
                     }
                 }
+#undef WHMEC_FAST_PACKED
 #undef WHMEC_FAST
             } else if (nout >= NT && tc.d == 1) {
                 column_drop1(tc, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);

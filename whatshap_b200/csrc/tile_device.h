@@ -94,6 +94,27 @@ WHMEC_HD uint64_t tile_eval_end(const TileCtx &c, uint32_t gpart, uint32_t x0, u
     return best;
 }
 
+// Bits per thread of a fast column (the width of one element of the thread-packed layout).
+WHMEC_HD uint32_t tile_fast_bits_per_thread(const TileCol &tc) { return (1u << tc.pad1) << (tc.pad0 == 2 ? 1 : 0); }
+
+// Thread-packed layout: index of the back-pointer bit of local output `lo` inside the tile's slice of the arena
+// (output o = warp * 2^LG * 32 + it * 32 + lane, + nout / 2 for the twin; element = thread; a thread shifts its bits in
+// in the order (it = 0, twin of 0, it = 1, ...), so the j-th one sits at bit N - 1 - j of the element).
+WHMEC_HD uint32_t tile_packed_bit_index(const TileCol &tc, uint32_t lo) {
+    const uint32_t lg = tc.pad1, it_count = 1u << lg;
+    const uint32_t half = 1u << (tc.l_out - 1);
+    uint32_t twin = 0;
+    if (tc.pad0 == 2 && lo >= half) {
+        twin = 1;
+        lo -= half;
+    }
+    const uint32_t warp = lo >> (lg + 5), it = (lo >> 5) & (it_count - 1), lane = lo & 31u;
+    const uint32_t n = tile_fast_bits_per_thread(tc);
+    const uint32_t j = tc.pad0 == 2 ? 2 * it + twin : it;
+    return (warp * 32 + lane) * n + (n - 1 - j);
+}
+
+
 // Backtrace of one chain through the tile-layout back-pointers (pedigreedptable.cpp:144-160).
 WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, const uint32_t *arena, uint32_t k_first,
                                    uint32_t k_last, uint64_t end_key, uint32_t *path_index) {
@@ -107,7 +128,8 @@ WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, co
         const uint32_t fmask = low_mask(pm.f);
         const uint32_t tile = pext32(o, pt.gmask_out);
         const uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
-        const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_words, pt.bp_width, lo);
+        const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_words, pt.bp_width,
+                                    pt.pad2 ? tile_packed_bit_index(pt, lo) : lo);
         x = candidate_index(pm, o, bp);
         path_index[k - 1] = x;
     }

@@ -38,6 +38,15 @@ WHMEC_HD int32_t tile_fast_lane_entry(const TileCol &tc, uint32_t lane) {
     return s;
 }
 
+// (bits << 1) | (t >> 31): one SHF.L.W on the device
+WHMEC_HD uint32_t tile_shift_in_sign(uint32_t bits, uint32_t t) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(t, bits, 1);
+#else
+    return (bits << 1) | (t >> 31);
+#endif
+}
+
 // plain expressions (no recursion, no calls) so that they fold to constants once the loops are unrolled
 #define cx_ctz(x) (((x) & 1) ? 0 : ((x) & 2) ? 1 : ((x) & 4) ? 2 : ((x) & 8) ? 3 : 4)
 #define cx_parity(x) ((((x) >> 0) ^ ((x) >> 1) ^ ((x) >> 2) ^ ((x) >> 3) ^ ((x) >> 4)) & 1)
@@ -48,7 +57,12 @@ WHMEC_HD int32_t tile_fast_lane_entry(const TileCol &tc, uint32_t lane) {
 // candidate cells of an output share one 64-bit load (and with SHARE the two outputs that differ
 // only in the newly started read share it too), back-pointers leave as warp ballots.
 // `emit(word, bit)`: this thread's bit of back-pointer word `word` of its warp (words are numbered from the warp's first).
-template <int LG, bool HASK0, bool SHARE, class Emit>
+// PACKED (TileCol::pad2 == 1, experimental): the thread keeps the bits of its own 2^LG (x 2 with SHARE) outputs in a
+// register and hands them to `emit.store(bits)` once per column.  No predicate is formed: with all values below 2^28
+// (the tile path's precondition) "candidate 1 wins" is the sign of v1 - v0 - par, and one funnel shift moves that sign
+// bit into the register — IADD3 + SHF per output instead of IADD + ISETP + VOTE + STG.  The outputs arrive in the order
+// (it = 0, twin of 0, it = 1, ...), so the first one ends up in the highest of the thread's bits (tile_packed_bit_index).
+template <int LG, bool HASK0, bool SHARE, bool PACKED = false, class Emit>
 WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
                           uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
     constexpr int IT = 1 << LG;
@@ -62,6 +76,7 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
     const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
     const uint32_t K0 = tc.K0, K12 = tc.K12;
     const uint32_t par0 = (WHMEC_POPC(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
+    uint32_t bits = 0;
     uint32_t ue[IT];
     ue[0] = (uint32_t)(TW[warp] + T5[lane]);
 #pragma unroll
@@ -77,7 +92,8 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
             const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
             const bool pick1 = v1 < v0 + par;  // par == 0: candidate 0 is visited first and keeps ties
             so[it * 32] = WHMEC_UMIN(v0, v1);
-            emit((uint32_t)it, pick1 != (par != 0));
+            if (PACKED) bits = tile_shift_in_sign(bits, v1 - v0 - par);  // sign set <=> pick1
+            else emit((uint32_t)it, pick1 != (par != 0));
         }
         if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
             const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
@@ -87,10 +103,22 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
             const uint32_t parb = par ^ 1u;
             const bool pick1 = v1 < v0 + parb;
             so[half + it * 32] = WHMEC_UMIN(v0, v1);
-            emit((half >> 5) + (uint32_t)it, pick1 != (parb != 0));
+            if (PACKED) bits = tile_shift_in_sign(bits, v1 - v0 - parb);
+            else emit((half >> 5) + (uint32_t)it, pick1 != (parb != 0));
         }
     }
+    if (PACKED) {
+        // stored bit = pick1 ^ par, par = par0 ^ parity(it) ^ twin: fold the compile-time part and the thread's par0 in at once
+        constexpr uint32_t N = SHARE ? 2 * IT : IT;
+        uint32_t cm = 0;
+#pragma unroll
+        for (int it = 0; it < IT; ++it) {
+            if (SHARE) cm |= ((uint32_t)cx_parity(it) << (N - 1 - 2 * it)) | (((uint32_t)cx_parity(it) ^ 1u) << (N - 2 - 2 * it));
+            else cm |= (uint32_t)cx_parity(it) << (N - 1 - it);
+        }
+        const uint32_t all = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
+        emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
+    }
 }
-
 
 }  // namespace whmec

@@ -28,6 +28,8 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         return;
     }
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    const char *packed_env = std::getenv("WHMEC_TILE_PACKED_BP");
+    const bool packed_bp = packed_env && packed_env[0] == '1';
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = tnow();
@@ -233,6 +235,11 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                             tc.pad0 = 1;
                             tc.pad1 = (uint8_t)(tc.l_out - 10);
                         }
+                    }
+                    // experimental (WHMEC_TILE_PACKED_BP=1): thread-packed back-pointer bits where a thread owns 8 or 16 outputs
+                    if (packed_bp && tc.pad0) {
+                        const uint32_t per_thread = (1u << tc.pad1) << (tc.pad0 == 2 ? 1 : 0);
+                        if (per_thread == 8 || per_thread == 16) tc.pad2 = 1;
                     }
                     ++n_accepted;
                     Lcur = nextL;

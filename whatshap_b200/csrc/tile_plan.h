@@ -40,7 +40,7 @@ struct TileCol {            // one column as seen by a tile (device + host)
     uint32_t bp_width;      // 0,1,2,4,8,16 bits per entry
     uint64_t bp_off;        // 32-bit words into the arena; tile t owns words [bp_off + t*bp_tile_words, +bp_tile_words)
     uint32_t bp_tile_words; // ceil(2^l_out * bp_width / 32)
-    uint32_t pad2;
+    uint32_t pad2;          // fast columns: 1 = back-pointer bits packed per thread (tile_packed_bit_index), 0 = warp-ballot order
     uint32_t gmask_out;     // canonical mask (over f_k bits) of the global reads after this column
     uint32_t lmask_col;     // canonical mask (over a_k bits) of the local reads of this column
     int32_t w_local[16];    // signed weight of local bit q:  +phred if allele 0, -phred if allele 1
