@@ -1,6 +1,6 @@
 #!/bin/bash
-# First GPU call of the next round (single B200, ~4 min): everything that was written in round 1 after the
-# GPU minutes ran out, plus the usual gates.  Run:  gpurun --timeout 900 -- 'bash scripts/gpu_round2.sh'
+# First GPU call of the next round (single B200, ~15-25 min): everything that was written in round 1 after the
+# GPU minutes ran out, plus the usual gates.  Run:  gpurun --timeout 2400 -- 'bash scripts/gpu_round2.sh'
 set -x
 mkdir -p gpurun_out
 timeout 700 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
