@@ -320,3 +320,119 @@ extern "C" int whemul_plan_digest(const whmec_problem *p, uint64_t *digest) {
     *digest = h;
     return 0;
 }
+
+// ---- the experimental packed 16-bit column (column_fast16, tile_fast.h) against column_fast on one random column:
+// same tile state (canonical u32 layout vs the rotated u16 layout), same costs, same tie-breaking.  Returns the number of
+// outputs compared, or a negative code on the first difference.
+namespace {
+
+struct StoreEmit {
+    uint32_t *slot;
+    void operator()(uint32_t, bool) const {}
+    void store(uint32_t bits) const { *slot = bits; }
+};
+
+template <int LG16>
+long fast16_check(uint32_t seed, uint32_t cg, uint32_t pX) {
+    constexpr uint32_t IT = 1u << LG16, l_out = 12 + LG16, l_in = l_out, m = l_in + 1;
+    uint64_t rs = seed * 0x9E3779B97F4A7C15ull + 12345;
+    auto rnd = [&](uint32_t n) { rs = rs * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)((rs >> 33) % n); };
+    if (pX < 1 || pX >= l_in) return -100;
+    // reads of the column: phred and allele per canonical cell bit (bit 0 ends here, bit l_in starts here)
+    int32_t w[16];
+    uint32_t K1 = 0, K2 = 0;
+    const uint32_t max_phred = 1 + rnd(40);
+    for (uint32_t q = 0; q < m; ++q) {
+        const uint32_t ph = rnd(max_phred + 1), al = rnd(2);
+        w[q] = al == 0 ? (int32_t)ph : -(int32_t)ph;
+        (al == 0 ? K1 : K2) += ph;
+    }
+    TileCol tc;
+    std::memset(&tc, 0, sizeof tc);
+    tc.l_in = l_in; tc.n_new = 1; tc.d = 1; tc.l_out = l_out; tc.kind = 0; tc.g = 0;
+    tc.dropmask = 1; tc.K0 = TILE_KINF; tc.K12 = K1 + K2; tc.K2 = (int32_t)K2; tc.dpos[0] = 0;
+    tc.pad0 = 2; tc.pad1 = (uint8_t)(l_out - 11);
+    for (uint32_t q = 0; q < m; ++q) tc.w_local[q] = w[q];
+    // previous projection values of the tile (tie-heavy: small range)
+    const uint32_t base = 1000000 + rnd(1000), range = 1 + rnd(rnd(2) ? 6 : 3000);
+    std::vector<uint32_t> S32(1u << l_in), out32(1u << l_out), bp32((1u << l_out) / 32, 0);
+    for (auto &v : S32) v = base + rnd(range);
+    {
+        int32_t TW[32], T5[32];
+        for (uint32_t i = 0; i < 32; ++i) {
+            TW[i] = tile_fast_warp_entry(tc, 0, i);
+            T5[i] = tile_fast_lane_entry(tc, i);
+        }
+        constexpr int LG32 = LG16 + 1;
+        for (uint32_t tid = 0; tid < 1024; ++tid) {
+            RecordEmit emit{bp32.data() + (tid >> 5) * (1u << LG32), tid & 31u, bp32.data(), tid, 0};
+            column_fast<LG32, false, true>(tc, TW, T5, cg, S32.data(), out32.data(), emit, tid);
+        }
+    }
+    // the rotated u16 tile: X first, the ending read second, the others in order
+    auto others_of = [&](uint32_t x, uint32_t bits) {  // canonical index without bit 0 and bit pX, compacted
+        uint32_t o = 0, k = 0;
+        for (uint32_t q = 1; q < bits; ++q)
+            if (q != pX) o |= ((x >> q) & 1u) << k++;
+        return o;
+    };
+    std::vector<uint32_t> Win(1u << (l_in - 1), 0), Wout(1u << (l_out - 1), 0), tbits(1024, 0);
+    for (uint32_t x = 0; x < (1u << l_in); ++x) {
+        const uint32_t xr = ((x >> pX) & 1u) | ((x & 1u) << 1) | (others_of(x, l_in) << 2);
+        const uint32_t v = S32[x] - base + 7;  // tile-relative, a small positive offset
+        Win[xr >> 1] |= v << (16 * (xr & 1u));
+    }
+    TileCol16 t16;
+    std::memset(&t16, 0, sizeof t16);
+    auto both = [](int32_t v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; };
+    t16.k12x2 = both((int32_t)(K1 + K2)); t16.k2x2 = both((int32_t)K2);
+    t16.wp2 = both(w[0]); t16.nwp2 = both(-w[0]);
+    t16.wn2 = both(w[l_in]); t16.nwn2 = both(-w[l_in]);
+    t16.wx_hi = ((uint32_t)w[pX] & 0xFFFFu) << 16; t16.nwx_hi = ((uint32_t)(-w[pX]) & 0xFFFFu) << 16;
+    t16.l_out = l_out;
+    {
+        uint32_t k = 0;
+        for (uint32_t q = 1; q < l_in; ++q)
+            if (q != pX) { t16.w2[k] = both(w[q]); t16.nw2[k] = both(-w[q]); ++k; }
+    }
+    uint32_t TW2[32], T52[32];
+    for (uint32_t i = 0; i < 32; ++i) {
+        uint32_t a = 0, b = 0;
+        for (uint32_t bit = 0; bit < 5; ++bit) {
+            if ((i >> bit) & 1u) {
+                a = whmec_vadd2_host(a, t16.w2[5 + LG16 + bit]);
+                b = whmec_vadd2_host(b, t16.w2[bit]);
+            }
+        }
+        TW2[i] = a;
+        T52[i] = b;
+    }
+    for (uint32_t tid = 0; tid < 1024; ++tid)
+        column_fast16<LG16>(t16, TW2, T52, cg, Win.data(), Wout.data(), StoreEmit{&tbits[tid]}, tid);
+    // compare every output
+    const uint32_t halfq = 1u << (l_out - 2), N = 4 * IT;
+    for (uint32_t o = 0; o < (1u << l_out); ++o) {  // canonical output index: cell index without bit 0
+        const uint32_t cell = o << 1;
+        const uint32_t X = (cell >> pX) & 1u, nw = (cell >> l_in) & 1u, oth = others_of(cell & ((1u << l_in) - 1u), l_in);
+        const uint32_t q = oth | (nw ? halfq : 0), qm = oth;
+        const uint32_t got = (Wout[q] >> (16 * X)) & 0xFFFFu;
+        if (got != out32[o] - base + 7) return -(long)(1 + o);
+        const uint32_t warp = qm >> (LG16 + 5), it = (qm >> 5) & (IT - 1), lane = qm & 31u, tid = warp * 32 + lane;
+        const uint32_t j = it * 4 + nw * 2 + (X ? 0 : 1);
+        const uint32_t dbit = (tbits[tid] >> (N - 1 - j)) & 1u;
+        const uint32_t par = (popc32(o) + cg) & 1u;
+        const uint32_t pick1_32 = ((bp32[o >> 5] >> (o & 31u)) & 1u) ^ par;  // the ballot layout stores pick1 ^ par
+        if ((dbit ^ 1u) != pick1_32) return -(long)(1000000 + o);
+    }
+    return (long)(1u << l_out);
+}
+
+}  // namespace
+
+extern "C" long whemul_fast16_column_check(uint32_t seed, uint32_t lg16, uint32_t cg, uint32_t pX) {
+    switch (lg16) {
+        case 0: return fast16_check<0>(seed, cg, pX);
+        case 1: return fast16_check<1>(seed, cg, pX);
+        default: return fast16_check<2>(seed, cg, pX);
+    }
+}

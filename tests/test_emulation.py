@@ -393,3 +393,21 @@ def test_thread_packed_back_pointers(emul, checker, monkeypatch):
         n_fast += int(lib.whemul_last_fast_columns())
         n_packed += int(lib.whemul_last_packed_columns())
     assert n_fast > 800 and n_packed > 600  # 8 or 16 outputs per thread: coverage >= 14
+
+
+def test_packed_16_bit_column_building_block(emul):
+    """`column_fast16` (csrc/tile_fast.h; not used by the kernel yet): the steady-state column on packed u16
+    values in the rotated tile layout gives, output by output, the values and the tie-breaking decisions of `column_fast` on the
+    same tile state — random weights / alleles, tie-heavy and wide value ranges, every position of the long-lived read X,
+    tiles of 2^12, 2^13 and 2^14 entries."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_fast16_column_check.restype = C.c_long
+    lib.whemul_fast16_column_check.argtypes = [C.c_uint32] * 4
+    compared = 0
+    for seed in range(24):
+        for lg in (0, 1, 2):
+            l_in = 12 + lg
+            got = lib.whemul_fast16_column_check(seed, lg, seed & 1, 1 + (seed * 5) % (l_in - 1))
+            assert got == 1 << l_in, (seed, lg, got)
+            compared += got
+    assert compared == 24 * (4096 + 8192 + 16384)
