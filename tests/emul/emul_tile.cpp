@@ -417,12 +417,12 @@ long fast16_check(uint32_t seed, uint32_t cg, uint32_t pX) {
         const uint32_t q = oth | (nw ? halfq : 0), qm = oth;
         const uint32_t got = (Wout[q] >> (16 * X)) & 0xFFFFu;
         if (got != out32[o] - base + 7) return -(long)(1 + o);
-        const uint32_t warp = qm >> (LG16 + 5), it = (qm >> 5) & (IT - 1), lane = qm & 31u, tid = warp * 32 + lane;
-        const uint32_t j = it * 4 + nw * 2 + (X ? 0 : 1);
-        const uint32_t dbit = (tbits[tid] >> (N - 1 - j)) & 1u;
-        const uint32_t par = (popc32(o) + cg) & 1u;
-        const uint32_t pick1_32 = ((bp32[o >> 5] >> (o & 31u)) & 1u) ^ par;  // the ballot layout stores pick1 ^ par
-        if ((dbit ^ 1u) != pick1_32) return -(long)(1000000 + o);
+        // the bit the backtrace would read (tile_u16_bit_index) against the ballot layout's bit of the same output
+        const uint32_t idx = tile_u16_bit_index(l_out, pX - 1, o);
+        const uint32_t r16 = (tbits[idx / N] >> (idx % N)) & 1u;
+        const uint32_t r32 = (bp32[o >> 5] >> (o & 31u)) & 1u;
+        if (r16 != r32) return -(long)(1000000 + o);
+        (void)qm;
     }
     return (long)(1u << l_out);
 }

@@ -202,7 +202,34 @@ WHMEC_HD void column_fast16(const TileCol16 &tc, const uint32_t *__restrict__ TW
             bits = tile_shift_in_sign(bits, d << 16);  // low half (output A)
         }
     }
-    emit.store(bits);
+    // the raw bit says "v1 >= v0 + par"; the back-pointer is the rank of the winner in visiting order, pick1 ^ par with
+    // pick1 = !raw: flip output A's bit unless its parity is set, output B's bit if it is (B has one more bit set: X)
+    constexpr uint32_t N = 4 * IT;
+    uint32_t cm = 0;  // par0 == 0
+#pragma unroll
+    for (int it = 0; it < IT; ++it)
+#pragma unroll
+        for (int twin = 0; twin < 2; ++twin) {
+            const uint32_t pa = (uint32_t)cx_parity(it) ^ (uint32_t)twin;
+            const int j = it * 4 + twin * 2;
+            cm |= pa << (N - 1 - j);               // output B: raw ^ par_A
+            cm |= (pa ^ 1u) << (N - 1 - (j + 1));  // output A: raw ^ 1 ^ par_A
+        }
+    const uint32_t all = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
+    emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
+}
+
+// Index of the back-pointer bit of canonical local output `lo` of a column swept by column_fast16 inside the tile's slice
+// of the arena: `xpos_out` = canonical position of X among the output bits, the starting read is the top bit, pair index =
+// the remaining bits; element = thread (N = 2^(l_out - 10) bits), j-th shifted-in bit at N - 1 - j.
+WHMEC_HD uint32_t tile_u16_bit_index(uint32_t l_out, uint32_t xpos_out, uint32_t lo) {
+    const uint32_t lg = l_out - 12, it_count = 1u << lg, n = 4u << lg;
+    const uint32_t X = (lo >> xpos_out) & 1u, nw = (lo >> (l_out - 1)) & 1u;
+    const uint32_t low = lo & ((1u << xpos_out) - 1u), high = (lo & ((1u << (l_out - 1)) - 1u)) >> (xpos_out + 1);
+    const uint32_t qm = low | (high << xpos_out);
+    const uint32_t warp = qm >> (lg + 5), it = (qm >> 5) & (it_count - 1), lane = qm & 31u;
+    const uint32_t j = it * 4 + nw * 2 + (X ? 0 : 1);
+    return (warp * 32 + lane) * n + (n - 1 - j);
 }
 
 }  // namespace whmec
