@@ -30,10 +30,13 @@ WHMEC_SOLVE_GROUPS=4 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-b
 # thread-packed back-pointers: parity fuzz first, then the bench
 WHMEC_TILE_PACKED_BP=1 timeout 200 python scripts/gpu_fuzz_highcov.py 90 14 18 2>&1 | tail -3 | tee gpurun_out/fuzz_packed_bp.log
 WHMEC_TILE_PACKED_BP=1 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_packedbp.json 2> gpurun_out/bench_cfg3_packedbp.err
+# packed 16-bit steady-state panels: parity fuzz at coverage 16-19 first, then the bench
+WHMEC_TILE_U16=1 timeout 200 python scripts/gpu_fuzz_highcov.py 90 16 19 2>&1 | tail -3 | tee gpurun_out/fuzz_u16.log
+WHMEC_TILE_U16=1 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_u16.json 2> gpurun_out/bench_cfg3_u16.err
 WHMEC_PINNED_STAGING=1 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3_pinned.json 2> gpurun_out/bench_cfg3_pinned.err
 # ragged blocks (load balance over the persistent tile grid)
 timeout 300 python bench.py --workload cfg3g --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cfg3g.json 2> gpurun_out/bench_cfg3g.err
-for f in gpurun_out/bench_cfg3.json gpurun_out/bench_cfg3_groups4.json gpurun_out/bench_cfg3_packedbp.json gpurun_out/bench_cfg3_pinned.json gpurun_out/bench_cfg3g.json; do
+for f in gpurun_out/bench_cfg3.json gpurun_out/bench_cfg3_groups4.json gpurun_out/bench_cfg3_packedbp.json gpurun_out/bench_cfg3_u16.json gpurun_out/bench_cfg3_pinned.json gpurun_out/bench_cfg3g.json; do
   python - "$f" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])

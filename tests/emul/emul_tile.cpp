@@ -18,7 +18,13 @@ using namespace whmec;
 // WHEMUL_TILE_FAST=0 sends these columns through the generic tile_eval loop instead (the two must agree).
 namespace {
 
-uint64_t g_last_fast_columns = 0, g_last_packed_columns = 0;
+uint64_t g_last_fast_columns = 0, g_last_packed_columns = 0, g_last_u16_columns = 0;
+
+struct StoreEmit {
+    uint32_t *slot;
+    void operator()(uint32_t, bool) const {}
+    void store(uint32_t bits) const { *slot = bits; }
+};
 
 struct RecordEmit {
     uint32_t *words;  // back-pointer words of this warp (ballot order) ...
@@ -40,7 +46,7 @@ void fast_column(const TileCol &tc, const int32_t *TW, const int32_t *T5, uint32
     for (uint32_t w = 0; w < ((1u << tc.l_out) + 31) / 32; ++w) bpw[w] = 0;
     for (uint32_t tid = 0; tid < 1024; ++tid) {
         RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u, bpw, tid, tile_fast_bits_per_thread(tc)};
-        if (tc.pad2) {
+        if (tc.pad2 & 1u) {
             if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
             else column_fast<LG, true, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
         } else if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
@@ -109,7 +115,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     std::vector<int32_t> TL(TILE_TL_SIZE), TH(TILE_TH_SIZE);
     const char *fast_env = std::getenv("WHEMUL_TILE_FAST");
     const bool use_fast = !(fast_env && fast_env[0] == '0');
-    uint64_t fast_columns = 0, packed_columns = 0;
+    uint64_t fast_columns = 0, packed_columns = 0, u16_columns = 0;
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
         for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
             const Panel &P = ts.panels[pi];
@@ -126,6 +132,52 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                     const uint32_t gpart = pdep32(t, P.gmask_in);
                     for (uint32_t l = 0; l < (1u << P.s_in); ++l) Sin[l] = state[P.in_off + (pdep32(l, P.lmask_in) | gpart)];
                 }
+                if (P.pad >> 31) {
+                    // ---- packed 16-bit panel (experimental): rotate + convert the tile, sweep every column with
+                    //      column_fast16, convert back into the canonical u32 order the write-back below expects
+                    const uint32_t s_in = P.s_in, xp0 = s_in - 1, spread = P.pad & 0x7FFFFFFFu;
+                    const uint32_t base = Sin[0] - spread;
+                    std::vector<uint32_t> W0(1u << (s_in - 1), 0), W1(1u << (s_in - 1), 0);
+                    for (uint32_t i = 0; i < (1u << s_in); ++i) {
+                        const uint32_t rel = Sin[i] - base;
+                        if (rel >= 32768u) { msg = "u16 panel: input beyond the planner's range bound"; return fail(101); }
+                        const uint32_t xr = tile_u16_rotate(i, xp0);
+                        W0[xr >> 1] |= rel << (16 * (xr & 1u));
+                    }
+                    uint32_t *Win = W0.data(), *Wout = W1.data();
+                    for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
+                        const TileCol &tc = ts.cols[k];
+                        if (!tile_is_u16(tc) || tile_u16_xpos(tc) != xp0 - (k - P.col_begin)) { msg = "u16 panel: column not marked"; return fail(103); }
+                        TileCol16 c16;
+                        tile_col16_from(tc, t, c16);
+                        uint32_t TW2[32], T52[32];
+                        for (uint32_t i = 0; i < 32; ++i) {
+                            TW2[i] = tile_fast16_warp_entry(c16, i);
+                            T52[i] = tile_fast16_lane_entry(c16, i);
+                        }
+                        const uint32_t cg = tile_cg(tc, t), nbits = 4u << (tc.l_out - 12);
+                        uint32_t *bpw = arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words;
+                        for (uint32_t w = 0; w < tc.bp_tile_words; ++w) bpw[w] = 0;
+                        for (uint32_t tid = 0; tid < 1024; ++tid) {
+                            uint32_t bits = 0;
+                            StoreEmit emit{&bits};
+                            if (tc.l_out == 14) column_fast16<2>(c16, TW2, T52, cg, Win, Wout, emit, tid);
+                            else column_fast16<1>(c16, TW2, T52, cg, Win, Wout, emit, tid);
+                            const uint32_t at = tid * nbits;  // element tid, as the kernel's u8 / u16 store
+                            bpw[at >> 5] |= bits << (at & 31u);
+                        }
+                        for (uint32_t w = 0; w < (1u << (tc.l_out - 1)); ++w)
+                            if ((Wout[w] & 0x8000u) || (Wout[w] & 0x80000000u)) { msg = "u16 panel: value beyond 2^15"; return fail(102); }
+                        std::swap(Win, Wout);
+                        ++fast_columns;
+                        ++u16_columns;
+                    }
+                    const uint32_t xpo = xp0 - (P.col_end - P.col_begin);  // canonical position of X after the panel
+                    for (uint32_t i = 0; i < (1u << P.s_out); ++i) {
+                        const uint32_t xr = tile_u16_rotate(i, xpo);
+                        Sin[i] = ((Win[xr >> 1] >> (16 * (xr & 1u))) & 0xFFFFu) + base;
+                    }
+                } else
                 for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
                     const TileCol &tc = ts.cols[k];
                     for (uint32_t i = 0; i < TILE_TL_SIZE; ++i) TL[i] = tile_tl_entry(tc, i);
@@ -145,7 +197,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                     } else if (tc.pad0 && use_fast) {
                         run_fast_column(tc, t, Sin, Sout, arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words);
                         ++fast_columns;
-                        packed_columns += tc.pad2 != 0;
+                        packed_columns += (tc.pad2 & 1u) != 0;
                         std::swap(Sin, Sout);
                     } else {
                         const uint32_t ncand = 1u << tc.d;
@@ -181,6 +233,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     s->cost = (uint32_t)total;
     g_last_fast_columns = fast_columns;
     g_last_packed_columns = packed_columns;
+    g_last_u16_columns = u16_columns;
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail(rc);
     return WHMEC_OK;
@@ -190,6 +243,8 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
 extern "C" uint64_t whemul_last_fast_columns(void) { return g_last_fast_columns; }
 // ... of which with thread-packed back-pointer bits (WHMEC_TILE_PACKED_BP=1)
 extern "C" uint64_t whemul_last_packed_columns(void) { return g_last_packed_columns; }
+// ... and (tile, column) pairs swept by column_fast16 inside packed 16-bit panels (WHMEC_TILE_U16=1)
+extern "C" uint64_t whemul_last_u16_columns(void) { return g_last_u16_columns; }
 
 // planner statistics only (no DP): panels, rounds, total tiles, max tiles per round, state/bp words
 extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {
@@ -326,11 +381,6 @@ extern "C" int whemul_plan_digest(const whmec_problem *p, uint64_t *digest) {
 // outputs compared, or a negative code on the first difference.
 namespace {
 
-struct StoreEmit {
-    uint32_t *slot;
-    void operator()(uint32_t, bool) const {}
-    void store(uint32_t bits) const { *slot = bits; }
-};
 
 template <int LG16>
 long fast16_check(uint32_t seed, uint32_t cg, uint32_t pX) {

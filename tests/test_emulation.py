@@ -411,3 +411,24 @@ def test_packed_16_bit_column_building_block(emul):
             assert got == 1 << l_in, (seed, lg, got)
             compared += got
     assert compared == 24 * (4096 + 8192 + 16384)
+
+
+def test_packed_16_bit_panels_end_to_end(emul, checker, monkeypatch):
+    """WHMEC_TILE_U16=1 (experimental): the planner marks steady-state panels, cuts them before the long-lived
+    read X ends and states a range bound; a marked panel is rotated + converted to tile-relative u16 where it is loaded, swept by
+    `column_fast16`, converted back where it is written; the backtrace reads the thread-packed bits (tile_u16_bit_index).
+    Same cost, path and super-reads as the reference; the emulation fails loudly if a value leaves the stated range."""
+    lib = emul["libwhemul.so"]
+    lib.whemul_last_u16_columns.restype = C.c_uint64
+    monkeypatch.setenv("WHMEC_TILE_U16", "1")
+    swept = 0
+    for cov, n, seed in ((16, 44, 2), (17, 44, 3), (19, 44, 5), (20, 40, 6)):
+        prob = synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.04 * (seed % 3), max_phred=2 if seed % 2 == 0 else 40)
+        got = run_tile(lib, prob, 0)
+        assert got is not None and got.same_as(checker.solve(prob)), (cov, got.diff(checker.solve(prob)))
+        swept += int(lib.whemul_last_u16_columns())
+    assert swept > 800
+    # without the switch no panel is marked
+    monkeypatch.delenv("WHMEC_TILE_U16")
+    run_tile(lib, synth.sliding_window(40, 17, block_len=40, seed=3), 0)
+    assert int(lib.whemul_last_u16_columns()) == 0

@@ -219,17 +219,58 @@ WHMEC_HD void column_fast16(const TileCol16 &tc, const uint32_t *__restrict__ TW
     emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
 }
 
-// Index of the back-pointer bit of canonical local output `lo` of a column swept by column_fast16 inside the tile's slice
-// of the arena: `xpos_out` = canonical position of X among the output bits, the starting read is the top bit, pair index =
-// the remaining bits; element = thread (N = 2^(l_out - 10) bits), j-th shifted-in bit at N - 1 - j.
-WHMEC_HD uint32_t tile_u16_bit_index(uint32_t l_out, uint32_t xpos_out, uint32_t lo) {
-    const uint32_t lg = l_out - 12, it_count = 1u << lg, n = 4u << lg;
-    const uint32_t X = (lo >> xpos_out) & 1u, nw = (lo >> (l_out - 1)) & 1u;
-    const uint32_t low = lo & ((1u << xpos_out) - 1u), high = (lo & ((1u << (l_out - 1)) - 1u)) >> (xpos_out + 1);
-    const uint32_t qm = low | (high << xpos_out);
-    const uint32_t warp = qm >> (lg + 5), it = (qm >> 5) & (it_count - 1), lane = qm & 31u;
-    const uint32_t j = it * 4 + nw * 2 + (X ? 0 : 1);
-    return (warp * 32 + lane) * n + (n - 1 - j);
+// TileCol::pad2 of a column inside a packed 16-bit panel: bit 8 set, bits 16..23 = position of X among the column's
+// canonical cell bits.
+WHMEC_HD bool tile_is_u16(const TileCol &tc) { return (tc.pad2 & 0x100u) != 0; }
+WHMEC_HD uint32_t tile_u16_xpos(const TileCol &tc) { return (tc.pad2 >> 16) & 0xFFu; }
+
+WHMEC_HD uint32_t tile_both_halves(int32_t v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; }
+
+// The packed constants of one column of tile `tile` from its TileCol (canonical cell order: bit 0 ends here, bit l_in
+// starts here, X at tile_u16_xpos) -- everything column_fast16 needs except the two 32-entry tables.
+WHMEC_HD void tile_col16_from(const TileCol &tc, uint32_t tile, TileCol16 &out) {
+    const uint32_t xpos = tile_u16_xpos(tc), l_in = tc.l_in;
+    int32_t k2 = tc.K2;
+    for (uint32_t b = 0; b < tc.g; ++b)
+        if ((tile >> b) & 1u) k2 += tc.w_global[b];
+    out.k12x2 = tile_both_halves((int32_t)tc.K12);
+    out.k2x2 = tile_both_halves(k2);
+    out.wp2 = tile_both_halves(tc.w_local[0]);
+    out.nwp2 = tile_both_halves(-tc.w_local[0]);
+    out.wn2 = tile_both_halves(tc.w_local[l_in]);
+    out.nwn2 = tile_both_halves(-tc.w_local[l_in]);
+    out.wx_hi = ((uint32_t)tc.w_local[xpos] & 0xFFFFu) << 16;
+    out.nwx_hi = ((uint32_t)(-tc.w_local[xpos]) & 0xFFFFu) << 16;
+    out.l_out = tc.l_out;
+    uint32_t k = 0;
+    for (uint32_t q = 1; q < l_in; ++q)
+        if (q != xpos) {
+            out.w2[k] = tile_both_halves(tc.w_local[q]);
+            out.nw2[k] = tile_both_halves(-tc.w_local[q]);
+            ++k;
+        }
+    for (; k < 16; ++k) out.w2[k] = out.nw2[k] = 0;
+}
+
+// The two 32-entry tables of column_fast16: sums of the packed weights selected by the warp / lane bits of the pair index.
+WHMEC_HD uint32_t tile_fast16_warp_entry(const TileCol16 &c, uint32_t warp) {
+    const uint32_t lg = c.l_out - 12;
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < 5; ++b)
+        if ((warp >> b) & 1u) s = WHMEC_VADD2(s, c.w2[5 + lg + b]);
+    return s;
+}
+WHMEC_HD uint32_t tile_fast16_lane_entry(const TileCol16 &c, uint32_t lane) {
+    uint32_t s = 0;
+    for (uint32_t b = 0; b < 5; ++b)
+        if ((lane >> b) & 1u) s = WHMEC_VADD2(s, c.w2[b]);
+    return s;
+}
+
+// Rotated index of canonical local index i of `bits` bits with X at canonical position xp: X first, the rest in order.
+WHMEC_HD uint32_t tile_u16_rotate(uint32_t i, uint32_t xp) {
+    const uint32_t low = i & ((1u << xp) - 1u), high = i >> (xp + 1);
+    return ((i >> xp) & 1u) | (low << 1) | (high << (xp + 1));
 }
 
 }  // namespace whmec
