@@ -270,12 +270,17 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
             uint16_t *h = reinterpret_cast<uint16_t *>(W[0]);
             for (uint32_t i = tid; i < nin; i += NT) h[tile_u16_rotate(i, xp0)] = (uint16_t)(S.buf[0][i] - base);
         }
-        if (tid == 64) tile_col16_from(tcols[kb], tile, S.c16[kb % 3]);
-        if (tid == 96 && kb + 1 < ke) tile_col16_from(tcols[kb + 1], tile, S.c16[(kb + 1) % 3]);
+        {  // the panel's column descriptors (at most 13 < TC_CHUNK) into shared memory
+            constexpr uint32_t WORDS = sizeof(TileCol) / 4;
+            for (uint32_t w = tid; w < (ke - kb) * WORDS; w += NT) ((uint32_t *)S.tcs)[w] = ((const uint32_t *)(tcols + kb))[w];
+        }
+        __syncthreads();
+        if (tid == 64) tile_col16_from(S.tcs[0], tile, S.c16[kb % 3]);
+        if (tid == 96 && kb + 1 < ke) tile_col16_from(S.tcs[1], tile, S.c16[(kb + 1) % 3]);
         __syncthreads();
         if (tid < 32) S.TW[kb & 1u][tid] = (int32_t)tile_fast16_warp_entry(S.c16[kb % 3], tid);
         else if (tid < 64) S.T5[kb & 1u][tid - 32] = (int32_t)tile_fast16_lane_entry(S.c16[kb % 3], tid - 32);
-        else if (tid == 64) S.cg[kb & 1u] = tile_cg(tcols[kb], tile);
+        else if (tid == 64) S.cg[kb & 1u] = tile_cg(S.tcs[0], tile);
         uint32_t wcur = 0;
         for (uint32_t k = kb; k < ke; ++k) {
             __syncthreads();  // constants and tables of column k ready; column k - 1 complete
@@ -283,12 +288,12 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
                 const uint32_t nb = (k + 1) & 1u;
                 if (tid < 32) S.TW[nb][tid] = (int32_t)tile_fast16_warp_entry(S.c16[(k + 1) % 3], tid);
                 else if (tid < 64) S.T5[nb][tid - 32] = (int32_t)tile_fast16_lane_entry(S.c16[(k + 1) % 3], tid - 32);
-                else if (tid == 64) S.cg[nb] = tile_cg(tcols[k + 1], tile);
-                else if (tid == 96 && k + 2 < ke) tile_col16_from(tcols[k + 2], tile, S.c16[(k + 2) % 3]);
+                else if (tid == 64) S.cg[nb] = tile_cg(S.tcs[k + 1 - kb], tile);
+                else if (tid == 96 && k + 2 < ke) tile_col16_from(S.tcs[k + 2 - kb], tile, S.c16[(k + 2) % 3]);
             }
             const TileCol16 &c = S.c16[k % 3];
             const uint32_t tb = k & 1u;
-            uint32_t *bpw = arena + __ldg(&tcols[k].bp_off) + (uint64_t)tile * __ldg(&tcols[k].bp_tile_words);
+            uint32_t *bpw = arena + S.tcs[k - kb].bp_off + (uint64_t)tile * S.tcs[k - kb].bp_tile_words;
             if (c.l_out == 14)
                 column_fast16<2>(c, reinterpret_cast<const uint32_t *>(S.TW[tb]), reinterpret_cast<const uint32_t *>(S.T5[tb]), S.cg[tb],
                                  W[wcur], W[wcur ^ 1u], PackedEmit<16>{bpw, tid}, tid);
