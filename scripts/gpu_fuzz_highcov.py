@@ -19,9 +19,17 @@ t0 = time.time()
 n = errs = multi = 0
 while time.time() - t0 < budget:
     cov = int(rng.integers(cov_lo, cov_hi + 1))
-    prob = synth.random_problem(rng, int(rng.integers(12, 40)), cov, "single", distrust=bool(rng.integers(0, 3) == 0),
-                                conflict_free=True, max_phred=int(rng.integers(1, 40)), mean_len=float(rng.choice([10, 16, 24])),
-                                gap=float(rng.choice([0.0, 0.1])), burst=6)
+    if n % 2:  # irregular spans
+        prob = synth.random_problem(rng, int(rng.integers(12, 40)), cov, "single", distrust=bool(rng.integers(0, 3) == 0),
+                                    conflict_free=True, max_phred=int(rng.integers(1, 40)), mean_len=float(rng.choice([10, 16, 24])),
+                                    gap=float(rng.choice([0.0, 0.1])), burst=6)
+    else:      # sliding windows: long runs of steady-state columns (the fast / thread-packed / packed 16-bit column code)
+        length = int(rng.integers(cov + 6, 56))
+        prob = synth.sliding_window(length, cov, block_len=int(rng.integers(cov + 4, length + 1)), seed=int(rng.integers(1 << 30)),
+                                    gap=float(rng.random() * 0.12), max_phred=int(rng.choice([1, 2, 40, 90])))
+        if rng.random() < 0.3:  # some homozygous sites
+            prob.gt = prob.gt.copy()
+            prob.gt[0, rng.random(prob.n_cols) < 0.1] = int(rng.integers(0, 3))
     os.environ.pop("WHMEC_FORCE_COLUMN_KERNEL", None)
     got, st = _lib.solve(prob)
     want = ck.solve(prob)
