@@ -3,7 +3,7 @@
 # GPU minutes ran out, plus the usual gates.  Run:  gpurun --timeout 2400 -- 'bash scripts/gpu_round2.sh'
 set -x
 mkdir -p gpurun_out
-timeout 700 python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+timeout 1500 python -m pytest tests -q -m gpu --timeout 400 -p no:cacheprovider 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 # group-wise pipeline of whmec_solve (csrc/grouped.h): bit-equality with the ordinary solve + end-to-end times
 timeout 300 python scripts/gpu_grouped_check.py 2>&1 | tail -12 | tee gpurun_out/grouped_check.log

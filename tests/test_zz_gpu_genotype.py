@@ -1,18 +1,12 @@
 """GPU parity of whmec_genotype (forward-backward genotyping DP) against the reference-generated golden vectors and
-the CPU checker, through the C ABI.  The kernels were written after this round's GPU minutes were spent: the
-device path has only been held to the reference through the host emulation of its per-cell code (tests/test_genotype.py),
-so these tests are opt-in until they have run on a B200 once (WHMEC_GPU_GENOTYPE=1; scripts/gpu_genotype_check.py runs
-them first thing next round).  Tolerance as in tests/test_genotype.py: 1e-9 absolute on the normalised likelihoods."""
-import os
-
+the CPU checker, through the C ABI.  Tolerance as in tests/test_genotype.py: 1e-9 absolute on the normalised likelihoods."""
 import numpy as np
 import pytest
 
 from oracle import checker
 from whatshap_b200 import _lib, synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("WHMEC_GPU_GENOTYPE") != "1", reason="device path not yet run on a GPU (opt in: WHMEC_GPU_GENOTYPE=1)")]
+pytestmark = pytest.mark.gpu
 
 TOL = 1e-9
 
