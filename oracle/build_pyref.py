@@ -46,3 +46,46 @@ def build() -> str:
 
 if __name__ == "__main__":
     print(build() or "reference tree not found")
+
+
+SHIP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyref")
+
+
+def ship() -> str:
+    """Puts the COMPILED reference binding where it travels to the GPU box (oracle/_ref is git-ignored, not
+    gpurun-ignored, exactly like oracle/_ref/libwhref.so): oracle/_ref/pyref/whatshap/core.*.so plus two stub modules
+    of our own (`__init__`, `variant` — core.pyx imports `.variant.Variant`, a three-field dataclass).  No reference
+    source is copied.  Returns the directory to put on sys.path ('' when neither a build nor a prebuilt copy exists)."""
+    pkg = os.path.join(SHIP, "whatshap")
+    have = os.path.isdir(pkg) and any(f.startswith("core.") and f.endswith(".so") for f in os.listdir(pkg))
+    built = build()
+    if built:
+        os.makedirs(pkg, exist_ok=True)
+        for f in os.listdir(os.path.join(built, "whatshap")):
+            if f.startswith("core.") and f.endswith(".so"):
+                src, dst = os.path.join(built, "whatshap", f), os.path.join(pkg, f)
+                if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(src):
+                    shutil.copy(src, dst)
+                have = True
+    if have:
+        with open(os.path.join(pkg, "__init__.py"), "w") as f:
+            f.write('"""Stub package (test infrastructure): only the compiled reference binding whatshap.core lives here."""\n')
+        with open(os.path.join(pkg, "variant.py"), "w") as f:
+            f.write('"""Stub: the dataclass whatshap.core imports as `.variant.Variant` (same three fields)."""\n'
+                    "from whatshap_b200.variant import Variant  # noqa: F401\n")
+        return SHIP
+    return ""
+
+
+def shipped_core():
+    """The compiled reference binding `whatshap.core` (authoring container or prebuilt copy on the GPU box), or None."""
+    if "whatshap.core" in sys.modules:  # already imported (e.g. from the full out-of-tree build): the same binding
+        return sys.modules["whatshap.core"]
+    path = ship()
+    if not path:
+        return None
+    import importlib
+
+    if path not in sys.path:
+        sys.path.insert(0, path)
+    return importlib.import_module("whatshap.core")

@@ -64,3 +64,62 @@ def find_components(
         for position in master_block[1:]:
             finder.merge(master_block[0], position)
     return {position: finder.find(position) for position in phased}
+
+
+def compute_overall_components(
+    accessible_positions: Sequence[int],
+    all_reads,
+    distrust_genotypes: bool,
+    family: Sequence[str],
+    genetic_haplotyping: bool,
+    homozygous_positions: Sequence[int],
+    numeric_sample_ids,
+    superreads_list,
+) -> Dict[int, int]:
+    """The step `whatshap phase` runs on the DP's super-reads (whatshap/cli/phase.py:676-714): which positions are
+    heterozygous is re-read from the super-reads when genotypes were distrusted (a site the DP called homozygous no
+    longer connects anything), and with genetic haplotyping of a family the homozygous sites form one master block."""
+    master_block = None
+    het_by_sample: Optional[Dict[int, Set[int]]] = None
+    accessible = set(accessible_positions)
+    if distrust_genotypes:
+        hom_anywhere: Set[int] = set()
+        het_by_sample = {}
+        for sample, (hap0, hap1) in zip(family, superreads_list):
+            hets: Set[int] = set()
+            for v0, v1 in zip(hap0, hap1):
+                assert v0.position == v1.position
+                if v0.position not in accessible:
+                    continue
+                call = (v0.allele, v1.allele)
+                if call in ((0, 1), (1, 0)):
+                    hets.add(v0.position)
+                elif call in ((0, 0), (1, 1)):
+                    hom_anywhere.add(v0.position)  # EQUAL_SCORES (3) calls are neither
+            het_by_sample[numeric_sample_ids[sample]] = hets
+        if len(family) > 1 and genetic_haplotyping:
+            master_block = sorted(hom_anywhere)
+    elif len(family) > 1 and genetic_haplotyping:
+        master_block = sorted(set(homozygous_positions) & accessible)
+    return find_components(accessible_positions, all_reads, master_block, het_by_sample)
+
+
+def phase_calls(family: Sequence[str], superreads_list, overall_components: Mapping[int, int], numeric_sample_ids=None):
+    """Hand-off to `PhasedVcfWriter.write(chromosome, sample_superreads, sample_components)`
+    (whatshap/cli/phase.py:640-652, whatshap/vcf.py:1147-1188): returns the two dictionaries the writer takes —
+    sample -> its two super-reads, sample -> the (shared) component map — and, per sample, the table the writer
+    derives from them first: position -> (allele of haplotype 0, allele of haplotype 1) for every site whose two
+    calls are 0 / 1 (sites called EQUAL_SCORES = 3 stay unphased), i.e. the GT it writes with PS = component + 1."""
+    superreads, components, phases = {}, {}, {}
+    for sample, pair in zip(family, superreads_list):
+        assert len(pair) == 2
+        if numeric_sample_ids is not None:
+            assert pair[0].sample_id == pair[1].sample_id == numeric_sample_ids[sample]
+        superreads[sample] = pair
+        components[sample] = overall_components  # identical for all samples of a family
+        table = {}
+        for v0, v1 in zip(pair[0], pair[1]):
+            if v0.allele in (0, 1) and v1.allele in (0, 1):
+                table[v0.position] = (v0.allele, v1.allele)
+        phases[sample] = table
+    return superreads, components, phases
