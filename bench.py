@@ -162,6 +162,9 @@ def cpu_sample(name, prob, target_cols):
 
 
 CPU_SAMPLE_COLS = {"cfg2": 4000, "cfg3": 160, "cfg3g": 160, "cfg4": 6, "cfg5": 1500}
+# reference arm (--impl reference): columns per instance and step, one instance per host thread (a step takes seconds)
+REF_SAMPLE_COLS = {"cfg2": 400, "cfg3": 16, "cfg3g": 16, "cfg4": 4, "cfg5": 150}
+REF_MAX_THREADS = {"cfg4": 32}  # 3 x 128 MiB per stored column and instance in the reference's layout
 
 
 def run_cpu_baseline(name, prob):
@@ -204,12 +207,10 @@ def bench_reference(args, rank, world):
                 out.append(synth.sliding_window(cols, cov, block_len=cols, seed=SEEDS[name] + 1000 + i))
         return out
 
-    # size a step to ~4 s of wall time on this host: calibrate with a tiny batch first (all host
-    # threads contend for memory bandwidth, so per-thread speed is far below the single-thread figure)
-    cols = 4
-    if ref is not None:
-        t_cal = ref.solve_many_timed(make(cols, threads), threads)
-        cols = int(min(max(4, cols * 4.0 / max(t_cal, 1e-3)), CPU_SAMPLE_COLS[name]))
+    # FIXED sample (no time-based calibration: the ratio against this arm must be reproducible): one independent
+    # block prefix of REF_SAMPLE_COLS columns per host thread, every instance single-threaded like the reference.
+    cols = REF_SAMPLE_COLS[name]
+    threads = min(threads, REF_MAX_THREADS.get(name, threads))
     probs = make(cols, threads)
     if ref is not None:
         kind = "reference"
@@ -224,11 +225,16 @@ def bench_reference(args, rank, world):
                 port.solve(p)
             return (time.perf_counter() - t0)
         probs = probs[:1]
+    step()  # one discarded call (page faults, allocator growth) on top of the requested warm-up
     for _ in range(args.warmup):
         step()
     times = [step() for _ in range(args.steps)]
     total_cols = cols * len(probs)
     value = total_cols * len(times) / sum(times)
+    single = None
+    if ref is not None:  # the reference is single-threaded: one instance alone on the box
+        ref.solve_many_timed(probs[:1], 1)
+        single = cols / ref.solve_many_timed(probs[:1], 1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
@@ -236,7 +242,8 @@ def bench_reference(args, rank, world):
         "config": {"workload": name, "description": WORKLOADS[name][0],
                    "sample": f"{len(probs)} independent {cols}-column block prefixes per step, one per host thread"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind == "reference" else 1, "kind": kind,
-                         "sample": f"{len(probs)} x {cols} columns per step"},
+                         "sample": f"{len(probs)} x {cols} columns per step (fixed sample)",
+                         "single_thread_value": single},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -30,7 +30,7 @@ def _worker(rank, world, port, kind, out_queue):
     ck = checker.best()
     prob = None
     if rank == 0:
-        if kind == "single":
+        if kind in ("single", "rank1_fails"):
             prob = synth.sliding_window(120, 6, block_len=20, seed=5, gap=0.1)
         elif kind == "trio":
             prob = synth.trio(40, 2, block_len=10, seed=6)
@@ -43,16 +43,23 @@ def _worker(rank, world, port, kind, out_queue):
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
     from emul_segment import EmulSegment
 
+    solver = ck.solve
+    if kind == "rank1_fails" and rank == 1:  # a rank-local failure (e.g. CUDA out of memory) must not leave the others in a collective
+        def solver(p):
+            raise RuntimeError("CUDA failure: out of memory (injected)")
     # pedigrees: every rank holds a segment of the table (host emulation of the per-rank CUDA calls)
     try:
-        sol = multigpu.solve_sharded(prob, solver=ck.solve, segment_factory=EmulSegment)
+        sol = multigpu.solve_sharded(prob, solver=solver, segment_factory=EmulSegment)
     except RuntimeError as e:
-        assert kind == "conflict" and "Mendelian conflict" in str(e), (kind, str(e))
+        if kind == "rank1_fails":
+            assert "out of memory (injected)" in str(e), str(e)
+        else:
+            assert kind == "conflict" and "Mendelian conflict" in str(e), (kind, str(e))
         if rank == 0:
             out_queue.put((True, "", 1))
         dist.destroy_process_group()
         return
-    assert kind != "conflict"
+    assert kind not in ("conflict", "rank1_fails")
     if rank == 0:
         want = ck.solve(prob)
         out_queue.put((sol.same_as(want), sol.diff(want), int(sol.cost)))
@@ -61,7 +68,7 @@ def _worker(rank, world, port, kind, out_queue):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,world", [("single", 2), ("trio", 2), ("trio", 3), ("trio_two_blocks", 3), ("conflict", 2)])
+@pytest.mark.parametrize("kind,world", [("single", 2), ("trio", 2), ("trio", 3), ("trio_two_blocks", 3), ("conflict", 2), ("rank1_fails", 3)])
 def test_block_sharding_matches_unsharded(kind, world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -141,3 +148,22 @@ def test_genotyping_shards_by_chains(world):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert same and n_blocks > world
+
+
+def test_wire_encoding_round_trips():
+    from whatshap_b200 import _wire
+
+    for prob in (synth.trio(30, 2, block_len=10, seed=1), synth.sliding_window(0, 3), synth.random_problem(np.random.default_rng(3), 20, 4, "quartet", distrust=True)):
+        back, tag, lo = _wire.decode_problem(_wire.encode_problem(prob, tag=7, lo=11))
+        assert (tag, lo) == (7, 11) and back.n_ind == prob.n_ind and back.distrust == prob.distrust
+        for f in ("positions", "read_off", "ent_col", "ent_allele", "ent_phred", "read_ind", "recombcost", "trios", "gt"):
+            assert np.array_equal(getattr(back, f), getattr(prob, f)), f
+        assert (back.gl is None) == (prob.gl is None) and (prob.gl is None or np.array_equal(back.gl, prob.gl))
+    from oracle import checker
+
+    prob = synth.trio(30, 2, block_len=10, seed=1)
+    sol = checker.best().solve(prob)
+    back, tag, extra = _wire.decode_solution(_wire.encode_solution(sol, tag=3, extra=np.arange(4)))
+    assert back.same_as(sol) and tag == 3 and extra.tolist() == [0, 1, 2, 3]
+    rows = _wire.separate(_wire.join([np.arange(5, dtype=np.uint8), np.zeros(0, np.uint8), np.arange(40, dtype=np.uint8)]))
+    assert [r.tolist() for r in rows] == [list(range(5)), [], list(range(40))]

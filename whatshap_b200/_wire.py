@@ -1,0 +1,237 @@
+"""Flat byte encoding of problems / solutions and the tensor collectives that move them between the ranks of one box.
+
+`torch.distributed`'s object collectives pickle every payload and, on NCCL, run a size exchange plus two host<->device
+copies per object: for a 9 MB problem cut eight ways that was the whole cost of the sharded solve (round 1: 352 ms on
+8 ranks against a 40 ms single-GPU solve).  Here every payload is ONE contiguous uint8 buffer (a small header followed by
+the raw arrays of `whmec_problem` / `whmec_solution`, include/whmec.h) and travels through tensor collectives only:
+`scatter` / `gather` of equal-size padded rows after one exchange of the row lengths, and `all_gather` for the few hundred
+bytes the pedigree scheme shares (T x T transfer matrices, exit tables, per-rank status).  On NCCL the rows go pinned host
+-> device -> NVLink -> device -> host; on gloo (CPU tests) they stay on the host.
+
+Every rank-local phase reports (ok | error, text) through `all_status` before the next collective, so that a failure on one
+rank is raised on every rank instead of leaving the others in a collective until the communicator times out."""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._abi import FlatProblem, FlatSolution
+
+_MAGIC_PROBLEM = 0x50484D57   # "WMHP"
+_MAGIC_SOLUTION = 0x53484D57  # "WMHS"
+_ALIGN = 16
+
+
+def _pad(n: int) -> int:
+    return (n + _ALIGN - 1) // _ALIGN * _ALIGN
+
+
+def _concat(header: Sequence[int], arrays: Sequence[np.ndarray]) -> np.ndarray:
+    head = np.array(list(header) + [a.nbytes for a in arrays], np.uint64)
+    total = _pad(head.nbytes) + sum(_pad(a.nbytes) for a in arrays)
+    out = np.zeros(total, np.uint8)
+    out[: head.nbytes] = head.view(np.uint8)
+    off = _pad(head.nbytes)
+    for a in arrays:
+        out[off : off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+        off += _pad(a.nbytes)
+    return out
+
+
+def _split(buf: np.ndarray, n_header: int, dtypes: Sequence) -> Tuple[List[int], List[np.ndarray]]:
+    head = buf[: 8 * (n_header + len(dtypes))].view(np.uint64)
+    header = [int(x) for x in head[:n_header]]
+    off = _pad(8 * (n_header + len(dtypes)))
+    arrays = []
+    for i, dt in enumerate(dtypes):
+        nbytes = int(head[n_header + i])
+        arrays.append(buf[off : off + nbytes].view(dt).copy())
+        off += _pad(nbytes)
+    return header, arrays
+
+
+def encode_problem(p: FlatProblem, tag: int = 0, lo: int = 0) -> np.ndarray:
+    """`tag` and `lo` are free header words (block id / first column of the slice)."""
+    gl = p.gl if p.gl is not None else np.zeros(0, np.float64)
+    return _concat(
+        [_MAGIC_PROBLEM, p.n_cols, p.n_reads, p.n_ind, 1 if p.distrust else 0, 1 if p.gl is not None else 0, tag, lo],
+        [p.positions, p.read_off, p.ent_col, p.ent_allele, p.ent_phred, p.read_ind, p.recombcost, p.trios, p.gt, gl],
+    )
+
+
+def decode_problem(buf: np.ndarray) -> Tuple[FlatProblem, int, int]:
+    h, a = _split(buf, 8, [np.uint32, np.uint64, np.uint32, np.uint8, np.uint32, np.uint32, np.uint32, np.uint32, np.uint8, np.float64])
+    assert h[0] == _MAGIC_PROBLEM, "not an encoded problem"
+    n_cols, n_ind = h[1], h[3]
+    prob = FlatProblem(positions=a[0], read_off=a[1], ent_col=a[2], ent_allele=a[3], ent_phred=a[4], read_ind=a[5], recombcost=a[6],
+                       n_ind=n_ind, trios=a[7], distrust=bool(h[4]), gt=a[8].reshape(n_ind, n_cols), gl=a[9] if h[5] else None)
+    return prob, h[6], h[7]
+
+
+def encode_solution(s: FlatSolution, tag: int = 0, extra: Optional[np.ndarray] = None) -> np.ndarray:
+    extra = np.zeros(0, np.uint32) if extra is None else np.asarray(extra, np.uint32)
+    return _concat([_MAGIC_SOLUTION, s.n_cols, s.n_reads, s.n_ind, int(s.cost), tag],
+                   [s.path_index, s.path_tv, s.partition, s.sr_allele, s.sr_quality, extra])
+
+
+def decode_solution(buf: np.ndarray) -> Tuple[FlatSolution, int, np.ndarray]:
+    h, a = _split(buf, 6, [np.uint32, np.uint32, np.uint8, np.uint8, np.uint32, np.uint32])
+    assert h[0] == _MAGIC_SOLUTION, "not an encoded solution"
+    s = FlatSolution(h[1], h[2], h[3])
+    s.cost = h[4]
+    s.path_index, s.path_tv, s.partition = a[0], a[1], a[2]
+    s.sr_allele, s.sr_quality = a[3].reshape(h[3], 2, h[1]), a[4].reshape(h[3], h[1])
+    return s, h[5], a[5]
+
+
+def join(buffers: Sequence[np.ndarray]) -> np.ndarray:
+    """Several encoded payloads in one row: [count, len_0, len_1, ...] then the payloads (each already 16-byte padded)."""
+    head = np.array([len(buffers)] + [b.nbytes for b in buffers], np.uint64)
+    out = np.zeros(_pad(head.nbytes) + sum(_pad(b.nbytes) for b in buffers), np.uint8)
+    out[: head.nbytes] = head.view(np.uint8)
+    off = _pad(head.nbytes)
+    for b in buffers:
+        out[off : off + b.nbytes] = b
+        off += _pad(b.nbytes)
+    return out
+
+
+def separate(row: np.ndarray) -> List[np.ndarray]:
+    if row.size == 0:
+        return []
+    count = int(row[:8].view(np.uint64)[0])
+    lens = row[8 : 8 * (count + 1)].view(np.uint64)
+    off = _pad(8 * (count + 1))
+    out = []
+    for n in lens:
+        out.append(row[off : off + int(n)])
+        off += _pad(int(n))
+    return out
+
+
+# ---- collectives ------------------------------------------------------------------------------------------------
+
+
+class Comm:
+    """The ranks of one process group with byte-row collectives.  Tensors live on this rank's CUDA device for NCCL and on
+    the host for gloo."""
+
+    def __init__(self, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist, self.group = torch, dist, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.cuda = dist.get_backend(group) == "nccl"
+        self.device = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
+        self.root = dist.get_global_rank(group, 0) if group is not None else 0
+
+    def _to_device(self, a: np.ndarray):
+        t = self.torch.from_numpy(a)
+        if self.cuda:
+            t = t.pin_memory().to(self.device, non_blocking=True)
+        return t
+
+    def _to_host(self, t) -> np.ndarray:
+        return t.cpu().numpy() if self.cuda else t.numpy()
+
+    def lengths(self, mine: int) -> List[int]:
+        t = self.torch.tensor([mine], dtype=self.torch.int64, device=self.device)
+        box = [self.torch.zeros(1, dtype=self.torch.int64, device=self.device) for _ in range(self.world)]
+        self.dist.all_gather(box, t, group=self.group)
+        return [int(x.item()) for x in box]
+
+    def scatter_rows(self, rows: Optional[Sequence[np.ndarray]]) -> np.ndarray:
+        """Rank 0 passes one uint8 row per rank; every rank returns its row."""
+        torch, dist = self.torch, self.dist
+        sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        if self.rank == 0:
+            sizes = self._to_device(np.array([r.nbytes for r in rows], np.int64))
+        dist.broadcast(sizes, src=self.root, group=self.group)
+        sizes = [int(x) for x in self._to_host(sizes)]
+        width = max(_pad(max(sizes)), _ALIGN)
+        recv = torch.empty(width, dtype=torch.uint8, device=self.device)
+        parts = None
+        if self.rank == 0:
+            big = np.zeros((self.world, width), np.uint8)
+            for i, r in enumerate(rows):
+                big[i, : r.nbytes] = r
+            parts = list(self._to_device(big).unbind(0))
+        dist.scatter(recv, parts, src=self.root, group=self.group)
+        return self._to_host(recv)[: sizes[self.rank]].copy()
+
+    def gather_rows(self, row: np.ndarray) -> Optional[List[np.ndarray]]:
+        """Every rank passes one uint8 row; rank 0 returns all of them (others None)."""
+        torch, dist = self.torch, self.dist
+        sizes = self.lengths(row.nbytes)
+        width = max(_pad(max(sizes)), _ALIGN)
+        mine = np.zeros(width, np.uint8)
+        mine[: row.nbytes] = row
+        send = self._to_device(mine)
+        parts = [torch.empty(width, dtype=torch.uint8, device=self.device) for _ in range(self.world)] if self.rank == 0 else None
+        dist.gather(send, parts, dst=self.root, group=self.group)
+        if self.rank != 0:
+            return None
+        return [self._to_host(parts[i])[: sizes[i]].copy() for i in range(self.world)]
+
+    def all_rows(self, row: np.ndarray, width: int) -> List[np.ndarray]:
+        """all_gather of one fixed-width uint8 row per rank (a few hundred bytes: matrices, exit tables, status)."""
+        torch, dist = self.torch, self.dist
+        mine = np.zeros(width, np.uint8)
+        mine[: row.nbytes] = row
+        send = self._to_device(mine)
+        box = [torch.empty(width, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+        dist.all_gather(box, send, group=self.group)
+        return [self._to_host(b).copy() for b in box]
+
+    STATUS_WIDTH = 512
+
+    def all_status(self, kind: int, text: str = "", payload: Optional[np.ndarray] = None, payload_width: int = 0):
+        """Every rank reports (kind, text[, payload]); returns the list of all ranks' reports.  kind: 0 ok, 1 unsupported,
+        2 error (RuntimeError), 3 Mendelian conflict.  One all_gather."""
+        width = self.STATUS_WIDTH + _pad(payload_width)
+        row = np.zeros(width, np.uint8)
+        msg = text.encode("utf-8", "replace")[: self.STATUS_WIDTH - 16]
+        row[:8] = np.array([kind], np.uint32).view(np.uint8).tolist() + np.array([len(msg)], np.uint32).view(np.uint8).tolist()
+        row[8:16] = np.array([0 if payload is None else payload.nbytes], np.uint64).view(np.uint8)
+        row[16 : 16 + len(msg)] = np.frombuffer(msg, np.uint8)
+        if payload is not None:
+            row[self.STATUS_WIDTH : self.STATUS_WIDTH + payload.nbytes] = np.ascontiguousarray(payload).reshape(-1).view(np.uint8)
+        out = []
+        for r in self.all_rows(row, width):
+            k, n = (int(x) for x in r[:8].view(np.uint32))
+            nb = int(r[8:16].view(np.uint64)[0])
+            out.append((k, bytes(r[16 : 16 + n]).decode("utf-8", "replace"), r[self.STATUS_WIDTH : self.STATUS_WIDTH + nb] if nb else None))
+        return out
+
+    def warm_up(self) -> None:
+        """First use of a communicator builds its rings / trees (tens to hundreds of ms on NCCL): do it outside any timed region."""
+        self.scatter_rows([np.zeros(16, np.uint8)] * self.world if self.rank == 0 else None)
+        self.gather_rows(np.zeros(16, np.uint8))
+        self.all_status(0)
+
+
+def status_of(exc: Optional[BaseException]) -> Tuple[int, str]:
+    from ._abi import MendelianConflict, Unsupported
+
+    if exc is None:
+        return 0, ""
+    if isinstance(exc, Unsupported):
+        return 1, str(exc)
+    if isinstance(exc, MendelianConflict):
+        return 3, str(exc)
+    return 2, "%s: %s" % (type(exc).__name__, exc) if not isinstance(exc, RuntimeError) else str(exc)
+
+
+def raise_first_error(states, where: str) -> bool:
+    """Raises on EVERY rank the first error any rank reported (same exception type as the single-GPU call would raise);
+    returns True if some rank reported 'unsupported' (the caller falls back to one GPU)."""
+    from ._abi import MendelianConflict
+
+    for rank, (kind, text, _) in enumerate(states):
+        if kind == 3:
+            raise MendelianConflict(text or "Error: Mendelian conflict")
+        if kind == 2:
+            raise RuntimeError(text if text else "rank %d failed during %s" % (rank, where))
+    return any(kind == 1 for kind, _, _ in states)

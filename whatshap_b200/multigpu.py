@@ -207,88 +207,94 @@ def solve_pedigree_segments(prob: FlatProblem, n_segments: int, segment_factory=
 
 
 def solve_pedigree_sharded(prob: Optional[FlatProblem], segment_factory=None, group=None, ranges=None,
-                           my_slice: Optional[FlatProblem] = None) -> Tuple[bool, Optional[FlatSolution]]:
+                           my_slice: Optional[FlatProblem] = None, comm=None, timings: Optional[dict] = None
+                           ) -> Tuple[bool, Optional[FlatSolution]]:
     """T > 1.  Every rank holds its segment of the table: either `prob` is known on every rank (each slices its own
     range), or `ranges` (all ranks' column ranges) and `my_slice` (this rank's columns, None for a rank without columns)
     are given and only rank 0 needs `prob` (for merging).  Returns (True, solution) on rank 0 and (True, None)
     elsewhere, or (False, None) on every rank if some segment is outside what the two-pass scheme handles (the
-    caller then solves on one GPU).  Input errors (Mendelian conflict, unsorted reads) are raised on every rank."""
-    import torch.distributed as dist
+    caller then solves on one GPU).  Every rank-local phase reports its status in the all-gather that follows it, so an
+    error on one rank (Mendelian conflict, unsorted reads, a CUDA failure) is raised on EVERY rank."""
+    import os
+    import time
 
-    from ._abi import Unsupported
+    from . import _wire
 
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    comm = comm or _wire.Comm(group)
+    rank, world = comm.rank, comm.world
     if segment_factory is None:
         segment_factory = _default_segment_factory()
     if ranges is None:
         ranges = segment_ranges(prob, world)
         my_slice = prob.slice_columns(*ranges[rank]) if ranges[rank] is not None else None
     last_active = max(r for r in range(world) if ranges[r] is not None)
-
-    def everyone(value):
-        box = [None] * world
-        dist.all_gather_object(box, value, group=group)
-        return box
-
-    import os
-    import time
-
+    T = 1 << (2 * (my_slice.n_trios if my_slice is not None else 0))
     marks = [("start", time.perf_counter())]
     mark = lambda name: marks.append((name, time.perf_counter()))
-    seg, status = None, ("ok", "")
-    mine = ranges[rank]
-    if mine is not None:
+    seg, mine = None, ranges[rank]
+
+    def phase(fn):
+        """Run a rank-local step; returns (status, result)."""
         try:
-            seg = segment_factory(my_slice, mine[0] > 0)
-        except Unsupported as e:
-            status = ("unsupported", str(e))
-        except RuntimeError as e:
-            status = ("error", e)
+            return (0, ""), fn()
+        except Exception as e:  # noqa: BLE001 - reported to every rank below
+            return _wire.status_of(e), None
+
     try:
-        states = everyone(status)
-        for kind, payload in states:
-            if kind == "error":
-                raise payload
-        if any(kind == "unsupported" for kind, _ in states):
+        status, seg = phase(lambda: segment_factory(my_slice, mine[0] > 0) if mine is not None else None)
+        if _wire.raise_first_error(comm.all_status(*status), "create"):
             return False, None
         mark("create")
-        matrix = seg.transfer() if seg else None
+        status, matrix = phase(lambda: seg.transfer() if seg else None)
         mark("transfer")
-        matrices = everyone(matrix)
+        T_all = max(comm.lengths(T))  # ranks without columns do not know T
+        width = 4 * T_all * T_all
+        states = comm.all_status(*status, payload=None if matrix is None else np.ascontiguousarray(matrix, np.uint32), payload_width=width)
+        _wire.raise_first_error(states, "transfer")
+        matrices = [None if pl is None else pl.view(np.uint32).reshape(T_all, T_all).copy() for _, _, pl in states]
         mark("gather matrices")
-        out_vec = seg.sweep(segment_inputs(matrices)[rank]) if seg else None
+        status, out_vec = phase(lambda: seg.sweep(segment_inputs(matrices)[rank]) if seg else None)
+        _wire.raise_first_error(comm.all_status(*status), "sweep")
         mark("sweep")
-        exits = everyone(seg.exits(rank == last_active) if seg else None)
+        status, ex = phase(lambda: seg.exits(rank == last_active) if seg else None)
+        states = comm.all_status(*status, payload=None if ex is None else np.ascontiguousarray(ex, np.uint32), payload_width=4 * T_all)
+        _wire.raise_first_error(states, "exits")
+        exits = [None if pl is None else pl.view(np.uint32).copy() for _, _, pl in states]
         mark("exits + gather")
         entry = segment_entries(exits)[rank]
-        part = (rank, seg.finish(entry), out_vec) if seg else None
+        status, part = phase(lambda: seg.finish(entry) if seg else None)
+        _wire.raise_first_error(comm.all_status(*status), "finish")
         mark("finish")
     finally:
         if seg is not None:
             seg.close()
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(part, gathered, dst=0, group=group)
+    rows = comm.gather_rows(_wire.encode_solution(part, tag=rank) if part is not None else np.zeros(0, np.uint8))
     mark("gather results")
+    if timings is not None:
+        timings.update({name: (t - t0) * 1e3 for (name, t), (_, t0) in zip(marks[1:], marks[:-1])})
     if rank == 0 and os.environ.get("WHMEC_TIMING"):
         print("[whmec] pedigree segments, rank 0: " + ", ".join(
             "%s %.1f ms" % (name, (t - t0) * 1e3) for (name, t), (_, t0) in zip(marks[1:], marks[:-1])), flush=True)
     if rank != 0:
         return True, None
-    parts = sorted((p for p in gathered if p is not None), key=lambda p: p[0])
-    return True, merge_block_solutions(prob, [ranges[r] for r, _, _ in parts], [sol for _, sol, _ in parts],
-                                       cost=int(parts[-1][1].cost))
+    parts = [(r, _wire.decode_solution(row)[0]) for r, row in enumerate(rows) if row.size]
+    return True, merge_block_solutions(prob, [ranges[r] for r, _ in parts], [sol for _, sol in parts], cost=int(parts[-1][1].cost))
 
 
 def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatProblem], FlatSolution]] = None,
-                  group=None, segment_factory=None) -> Optional[FlatSolution]:
+                  group=None, segment_factory=None, comm=None, timings: Optional[dict] = None) -> Optional[FlatSolution]:
     """Solve `prob` (given on rank 0; other ranks pass None) on all ranks of `group`.
 
     Rank 0 cuts the problem and SCATTERS the pieces — a rank receives only the columns and reads it works on (the
     "trivial broadcast of the block list" of the north_star, without shipping every rank the whole ReadSet): the blocks of
-    its share for a single individual, its segment of the table for a pedigree.  Returns the merged solution on rank 0
-    and None elsewhere.  `solver` / `segment_factory` default to the CUDA path on this rank's current device; tests
-    inject CPU stand-ins to exercise the sharding logic with gloo."""
-    import torch.distributed as dist
+    its share for a single individual, its segment of the table for a pedigree.  The pieces travel as flat byte rows through
+    tensor collectives (`_wire`), the per-block results come back the same way.  Returns the merged solution on rank 0 and
+    None elsewhere; an error on any rank is raised on every rank.  `solver` / `segment_factory` default to the CUDA path on
+    this rank's current device; tests inject CPU stand-ins to exercise the sharding logic with gloo.  `timings` (optional
+    dict) receives this rank's per-phase wall times in ms."""
+    import time
+
+    from . import _wire
 
     if solver is None:
         import torch
@@ -297,50 +303,85 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
 
         device = torch.cuda.current_device()
         solver = lambda p: _lib.solve(p, device=device)[0]
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    payloads = None
+    comm = comm or _wire.Comm(group)
+    rank, world = comm.rank, comm.world
+    t0 = time.perf_counter()
+    rows = None
     blocks = None
+    MODE = {"single": 0, "blocks": 1, "segments": 2}
     if rank == 0:
         blocks = independent_blocks(prob)
         if prob.n_trios > 0 and world > 1 and len(blocks) > 1:  # transmission vectors couple the blocks: segments of the table
             ranges = segment_ranges(prob, world)
-            payloads = [("segments", ranges, prob.slice_columns(*r) if r is not None else None) for r in ranges]
+            flat = np.array([MODE["segments"]] + [x for r in ranges for x in (r if r is not None else (0, 0))], np.int64)
+            rows = [_wire.join([flat.view(np.uint8)] + ([_wire.encode_problem(prob.slice_columns(*r), lo=r[0])] if r is not None else []))
+                    for r in ranges]
         elif prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or no columns: one GPU
-            payloads = [("single", None, None)] * world
+            rows = [_wire.join([np.array([MODE["single"]], np.int64).view(np.uint8)])] * world
         else:
             shares = assign_blocks(block_work(prob, blocks), world)
-            payloads = [("blocks", None, [(b, prob.slice_columns(*blocks[b])) for b in share]) for share in shares]
-    box = [None]
-    dist.scatter_object_list(box, payloads, src=0, group=group)
-    mode, ranges, piece = box[0]
-    if mode == "segments":
-        handled, sol = solve_pedigree_sharded(prob, segment_factory, group, ranges=ranges, my_slice=piece)
+            rows = [_wire.join([np.array([MODE["blocks"]], np.int64).view(np.uint8)] +
+                               [_wire.encode_problem(prob.slice_columns(*blocks[b]), tag=b, lo=blocks[b][0]) for b in share])
+                    for share in shares]
+    t1 = time.perf_counter()
+    pieces = _wire.separate(comm.scatter_rows(rows))
+    head = pieces[0].view(np.int64)
+    mode = int(head[0])
+    t2 = time.perf_counter()
+    if timings is not None:
+        timings.update({"cut + encode": (t1 - t0) * 1e3, "scatter": (t2 - t1) * 1e3})
+    if mode == MODE["segments"]:
+        ranges = [None if head[1 + 2 * r] == head[2 + 2 * r] else (int(head[1 + 2 * r]), int(head[2 + 2 * r])) for r in range(world)]
+        piece = _wire.decode_problem(pieces[1])[0] if len(pieces) > 1 else None
+        handled, sol = solve_pedigree_sharded(prob, segment_factory, group, ranges=ranges, my_slice=piece, comm=comm, timings=timings)
         if handled:
             return sol
-        mode = "single"  # some segment is outside the two-pass scheme: the whole table on rank 0's GPU
-    if mode == "single":
-        sol = solver(prob) if rank == 0 else None
-        dist.barrier(group)
+        mode = MODE["single"]  # some segment is outside the two-pass scheme: the whole table on rank 0's GPU
+    if mode == MODE["single"]:
+        sol, err = None, None
+        if rank == 0:
+            try:
+                sol = solver(prob)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        _wire.raise_first_error(comm.all_status(*_wire.status_of(err)), "solve")
         return sol
-    mine = [(b, solver(sub)) for b, sub in piece]
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(mine, gathered, dst=0, group=group)  # per-block super-reads back to rank 0
+    mine, err = [], None
+    try:
+        for row in pieces[1:]:
+            sub, b, _ = _wire.decode_problem(row)
+            mine.append(_wire.encode_solution(solver(sub), tag=b))
+    except Exception as e:  # noqa: BLE001 - e.g. more active reads than supported, CUDA out of memory
+        err = e
+    t3 = time.perf_counter()
+    _wire.raise_first_error(comm.all_status(*_wire.status_of(err)), "solve")
+    gathered = comm.gather_rows(_wire.join(mine))  # per-block super-reads back to rank 0
+    t4 = time.perf_counter()
+    if timings is not None:
+        timings.update({"solve": (t3 - t2) * 1e3, "gather": (t4 - t3) * 1e3})
     if rank != 0:
         return None
-    by_block = dict(pair for part in gathered for pair in part)
-    return merge_block_solutions(prob, blocks, [by_block[b] for b in range(len(blocks))])
+    by_block = {}
+    for row in gathered:
+        for enc in _wire.separate(row):
+            sol, b, _ = _wire.decode_solution(enc)
+            by_block[b] = sol
+    out = merge_block_solutions(prob, blocks, [by_block[b] for b in range(len(blocks))])
+    if timings is not None:
+        timings["merge"] = (time.perf_counter() - t4) * 1e3
+    return out
 
 
 def genotype_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatProblem], np.ndarray]] = None,
-                     group=None) -> Optional[np.ndarray]:
+                     group=None, comm=None) -> Optional[np.ndarray]:
     """Genotype likelihoods (`whmec_genotype`, the reference's GenotypeDPTable) of `prob` (given on rank 0; other ranks
     pass None) on all ranks of `group`; returns [n_ind, n_cols, 3] on rank 0, None elsewhere.
 
     Without transmission values every DP-independent chain is a forward-backward table of its own (a chain boundary hands
     over one number, which cancels in each column's normalisation), so a single individual shards like the phasing DP:
     every rank takes a contiguous run of whole chains balanced by DP cells, no collective on the data path, likelihoods
-    gathered on rank 0.  A pedigree is one table and runs on one GPU (replicas only)."""
-    import torch.distributed as dist
+    gathered on rank 0.  A pedigree is one table and runs on one GPU (replicas only).  Errors are raised on every rank."""
+    from . import _wire
 
     if solver is None:
         import torch
@@ -349,32 +390,40 @@ def genotype_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[Fla
 
         device = torch.cuda.current_device()
         solver = lambda p: _lib.genotype(p, device=device)[0]
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
-    payloads = None
+    comm = comm or _wire.Comm(group)
+    rank, world = comm.rank, comm.world
+    rows = None
     if rank == 0:
         if prob.n_trios > 0 or prob.n_cols == 0 or world == 1:
-            payloads = [("single", 0, 0, None)] * world
+            rows = [_wire.join([np.array([0, 0, 0], np.int64).view(np.uint8)])] * world
         else:  # every rank receives only its run of chains
             blocks = independent_blocks(prob)
-            payloads = []
+            rows = []
             for b0, b1 in contiguous_shares(block_work(prob, blocks), world):
                 lo, hi = (blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else (0, 0)
-                payloads.append(("chains", lo, hi, prob.slice_columns(lo, hi) if hi > lo else None))
-    box = [None]
-    dist.scatter_object_list(box, payloads, src=0, group=group)
-    mode, lo, hi, piece = box[0]
-    if mode == "single":
-        out = solver(prob) if rank == 0 else None
-        dist.barrier(group)
+                rows.append(_wire.join([np.array([1, lo, hi], np.int64).view(np.uint8)] +
+                                       ([_wire.encode_problem(prob.slice_columns(lo, hi), lo=lo)] if hi > lo else [])))
+    pieces = _wire.separate(comm.scatter_rows(rows))
+    mode, lo, hi = (int(x) for x in pieces[0].view(np.int64))
+    out, err = None, None
+    try:
+        if mode == 0:
+            out = solver(prob) if rank == 0 else None
+        elif len(pieces) > 1:
+            out = np.ascontiguousarray(solver(_wire.decode_problem(pieces[1])[0]), np.float64)
+    except Exception as e:  # noqa: BLE001
+        err = e
+    _wire.raise_first_error(comm.all_status(*_wire.status_of(err)), "genotype")
+    if mode == 0:
         return out
-    mine = (lo, hi, solver(piece)) if piece is not None else None
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(mine, gathered, dst=0, group=group)
+    head = np.array([lo, hi], np.int64).view(np.uint8)
+    gathered = comm.gather_rows(_wire.join([head, out.reshape(-1).view(np.uint8)]) if out is not None else np.zeros(0, np.uint8))
     if rank != 0:
         return None
-    out = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
-    for part in gathered:
-        if part is not None:
-            lo, hi, lk = part
-            out[:, lo:hi, :] = lk
-    return out
+    full = np.zeros((prob.n_ind, prob.n_cols, 3), np.float64)
+    for row in gathered:
+        parts = _wire.separate(row)
+        if parts:
+            lo, hi = (int(x) for x in parts[0].view(np.int64))
+            full[:, lo:hi, :] = parts[1].view(np.float64).reshape(prob.n_ind, hi - lo, 3)
+    return full
