@@ -326,6 +326,33 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = all_cols * e2e_steps / float(e2e_t.item())
 
+    # ---- strong scaling: ONE problem (rank 0's) sharded over all ranks, end to end from rank 0's host arrays --------
+    sharded = None
+    if world > 1:
+        from whatshap_b200 import _wire, multigpu
+
+        comm = _wire.Comm()
+        comm.warm_up()  # communicator set-up is not part of a solve
+        shared = prob if rank == 0 else None
+        multigpu.solve_sharded(shared, comm=comm)  # warm-up (contexts, allocators on every rank)
+        barrier()
+        sh_t0 = time.perf_counter()
+        phases = {}
+        for _ in range(e2e_steps):
+            phases = {}
+            sol_sh = multigpu.solve_sharded(shared, comm=comm, timings=phases)
+        barrier()
+        sh_dt = time.perf_counter() - sh_t0
+        sh_t = torch.tensor([sh_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sh_t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            assert sol_sh.same_as(sol), "sharded and single-GPU solves disagree: " + sol_sh.diff(sol)
+            sharded = {"value": n_cols * e2e_steps / float(sh_t.item()), "unit": UNIT, "ms_per_step": 1e3 * float(sh_t.item()) / e2e_steps,
+                       "scaling": "strong", "columns": n_cols, "ranks": world, "phases_ms_rank0": {k: round(v, 2) for k, v in phases.items()},
+                       "note": "multigpu.solve_sharded: rank 0's host arrays -> cut into blocks (T = 1) or table segments (T > 1) -> tensor "
+                               "scatter -> per-rank whmec_solve / whmec_segment_* -> tensor gather -> merged result on rank 0; bit-identical "
+                               "to the single-GPU solve (asserted)"}
+
     if rank == 0:
         peak, peak_src = hbm_peak()
         launches = int(stats["kernel_launches"])
@@ -361,6 +388,8 @@ def main():
                     "note": "whmec_solve: host CSR arrays in, host result arrays out (pack + alloc + H2D + sweep + backtrace + D2H)"},
             "gpu_launches": launches * args.steps,
         }
+        if sharded is not None:
+            line["e2e_sharded"] = sharded
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = run_cpu_baseline(name, prob)
         print(json.dumps(line), flush=True)

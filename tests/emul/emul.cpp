@@ -6,10 +6,13 @@
 // tests/emul/Makefile, loaded only by tests/test_emulation.py, and is NOT a fallback: the product
 // library (whatshap_b200/csrc) contains no CPU execution path.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
+#include "../../whatshap_b200/csrc/hostpool.h"
 #include "../../whatshap_b200/csrc/pack.h"
 #include "../../whatshap_b200/csrc/dp_device.h"
 
@@ -361,4 +364,27 @@ extern "C" int whemul_ped_chain_solve(const whmec_problem *p, whmec_solution *s,
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
     return WHMEC_OK;
+}
+
+// A task that throws on a pool worker / on the caller: parallel_tasks must rethrow the first exception on the caller after
+// every worker has let go of the job, and the pool must stay usable.  Returns 0 when all of that holds.
+extern "C" int whemul_pool_throw_check(uint32_t n_threads) {
+    using namespace whmec;
+    for (int round = 0; round < 4; ++round) {
+        std::atomic<uint32_t> ran{0};
+        bool caught = false;
+        try {
+            parallel_tasks(256, n_threads, [&](uint32_t t) {
+                ran.fetch_add(1);
+                if (t == (uint32_t)(17 + 60 * round)) throw std::runtime_error("task failed");
+            });
+        } catch (const std::runtime_error &e) {
+            caught = std::string(e.what()) == "task failed";
+        }
+        if (!caught || ran.load() == 0) return 1 + round;
+        std::atomic<uint64_t> sum{0};
+        parallel_tasks(1000, n_threads, [&](uint32_t t) { sum.fetch_add(t); });
+        if (sum.load() != 999ull * 1000 / 2) return 10 + round;
+    }
+    return 0;
 }

@@ -210,7 +210,9 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                                 if (key < best) best = key;
                             }
                             Sout[o] = (uint32_t)(best >> 32);
-                            bp_store_serial(arena.data(), tc.bp_off + (uint64_t)t * tc.bp_tile_words, tc.bp_width, o, (uint32_t)best);
+                            // WHEMUL_TILE_FAST=0 on a column the planner marked thread-packed: same bit positions as the fast code
+                            const uint32_t at = (tc.pad0 && (tc.pad2 & 1u)) ? tile_packed_bit_index(tc, o) : o;
+                            bp_store_serial(arena.data(), tc.bp_off + (uint64_t)t * tc.bp_tile_words, tc.bp_width, at, (uint32_t)best);
                         }
                         std::swap(Sin, Sout);
                     }

@@ -432,3 +432,11 @@ def test_packed_16_bit_panels_end_to_end(emul, checker, monkeypatch):
     monkeypatch.delenv("WHMEC_TILE_U16")
     run_tile(lib, synth.sliding_window(40, 17, block_len=40, seed=3), 0)
     assert int(lib.whemul_last_u16_columns()) == 0
+
+
+def test_host_worker_pool_rethrows_a_task_exception_on_the_caller(emul):
+    """A throwing task (std::bad_alloc in a packer chunk ...) neither terminates a pool worker nor leaves workers with a dangling
+    job: the first exception reaches the caller (and from there the guarded C-ABI wrapper), the pool keeps working."""
+    lib = emul["libwhemul.so"]
+    for n_threads in (1, 2, 8):
+        assert lib.whemul_pool_throw_check(n_threads) == 0

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdlib>
+#include <exception>
 #include <mutex>
 #include <thread>
 
@@ -34,10 +35,28 @@ struct Job {
     uint32_t n;
     std::atomic<uint32_t> next{0};
     std::atomic<int> slots{0};  // workers that may still join this job
+    std::atomic<bool> failed{false};
+    std::mutex err_m;
+    std::exception_ptr err;  // first exception thrown by a task (rethrown on the caller once every worker has checked out)
 };
 
+// A task that throws (std::bad_alloc from a packer chunk, ...) must neither terminate a pool worker nor unwind the caller
+// while workers still hold the stack-allocated Job: the first exception is kept, the remaining tasks are skipped.
 void drain(Job &j) {
-    for (uint32_t t = j.next.fetch_add(1, std::memory_order_relaxed); t < j.n; t = j.next.fetch_add(1, std::memory_order_relaxed)) (*j.fn)(t);
+    for (uint32_t t = j.next.fetch_add(1, std::memory_order_relaxed); t < j.n; t = j.next.fetch_add(1, std::memory_order_relaxed)) {
+        if (j.failed.load(std::memory_order_relaxed)) continue;
+        try {
+            (*j.fn)(t);
+        } catch (...) {
+            std::lock_guard<std::mutex> lk(j.err_m);
+            if (!j.err) j.err = std::current_exception();
+            j.failed.store(true, std::memory_order_relaxed);
+        }
+    }
+}
+
+void rethrow(Job &j) {
+    if (j.err) std::rethrow_exception(j.err);
 }
 
 struct Pool {
@@ -96,6 +115,7 @@ void run_on_temporary_threads(uint32_t n_threads, Job &j) {
     for (uint32_t t = 0; t + 1 < n_threads; ++t) th.emplace_back([&j] { drain(j); });
     drain(j);
     for (auto &t : th) t.join();
+    rethrow(j);
 }
 
 }  // namespace
@@ -134,6 +154,8 @@ void parallel_tasks(uint32_t n_tasks, uint32_t n_threads, const std::function<vo
         P->done_cv.wait(lk, [&] { return P->running == 0; });
         P->job = nullptr;
     }
+    entry.unlock();
+    rethrow(j);
 }
 
 }  // namespace whmec

@@ -17,7 +17,8 @@ uint32_t host_threads(uint32_t cap);
 
 // Runs fn(task) for task = 0 .. n_tasks-1 on up to n_threads threads (the caller is one of them), tasks
 // handed out dynamically.  Returns when all tasks are done.  Re-entrant: a second caller that finds the
-// pool busy runs on short-lived threads of its own.  fn must not throw.
+// pool busy runs on short-lived threads of its own.  If a task throws, the remaining tasks are skipped and the first
+// exception is rethrown on the caller after every worker has let go of the job.
 void parallel_tasks(uint32_t n_tasks, uint32_t n_threads, const std::function<void(uint32_t)> &fn);
 
 // std::allocator whose value-initialisation is default-initialisation: resize() leaves trivial

@@ -29,7 +29,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     }
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     const char *packed_env = std::getenv("WHMEC_TILE_PACKED_BP");
-    const bool packed_bp = packed_env && packed_env[0] == '1';
+    const bool packed_bp = !(packed_env && packed_env[0] == '0');  // default since round 2 (B200: 29.97 -> 25.42 ms on cfg3); "0" keeps the warp-ballot layout
     // experimental (WHMEC_TILE_U16=1): steady-state panels on packed 16-bit values; needs every read's
     // total weight for the range bound
     const char *u16_env = std::getenv("WHMEC_TILE_U16");

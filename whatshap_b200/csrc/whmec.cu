@@ -1052,7 +1052,15 @@ int column_sweep(whmec_plan *pl, std::string &msg) {
             launches += 1;
         } else {
             const uint32_t log_chunks = m.d - 6;
-            CUDA_TRY(cudaMemsetAsync(pl->d_keys.p, 0xFF, nent * 8, pl->stream));
+            if (cudaError_t e = cudaMemsetAsync(pl->d_keys.p, 0xFF, nent * 8, pl->stream); e != cudaSuccess) {
+                if (capture) {  // do not leave the stream in capture mode
+                    cudaGraph_t dead = nullptr;
+                    cudaStreamEndCapture(pl->stream, &dead);
+                    if (dead) cudaGraphDestroy(dead);
+                }
+                msg = std::string("cudaMemsetAsync (column sweep): ") + cudaGetErrorString(e);
+                return WHMEC_ERR_CUDA;
+            }
             const uint64_t threads = nent << log_chunks;
             const unsigned blocks = (unsigned)((threads + 255) / 256);
             col_chunk_kernel<<<blocks, 256, 0, pl->stream>>>(m, pk.fn_group[m.grp_off + T], T, tb, pl->d_fn_c0.p, pl->d_fn_delta.p,
