@@ -18,13 +18,7 @@ using namespace whmec;
 // WHEMUL_TILE_FAST=0 sends these columns through the generic tile_eval loop instead (the two must agree).
 namespace {
 
-uint64_t g_last_fast_columns = 0, g_last_packed_columns = 0, g_last_u16_columns = 0;
-
-struct StoreEmit {
-    uint32_t *slot;
-    void operator()(uint32_t, bool) const {}
-    void store(uint32_t bits) const { *slot = bits; }
-};
+uint64_t g_last_fast_columns = 0, g_last_packed_columns = 0;
 
 struct RecordEmit {
     uint32_t *words;  // back-pointer words of this warp (ballot order) ...
@@ -115,7 +109,7 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     std::vector<int32_t> TL(TILE_TL_SIZE), TH(TILE_TH_SIZE);
     const char *fast_env = std::getenv("WHEMUL_TILE_FAST");
     const bool use_fast = !(fast_env && fast_env[0] == '0');
-    uint64_t fast_columns = 0, packed_columns = 0, u16_columns = 0;
+    uint64_t fast_columns = 0, packed_columns = 0;
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
         for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
             const Panel &P = ts.panels[pi];
@@ -132,52 +126,6 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                     const uint32_t gpart = pdep32(t, P.gmask_in);
                     for (uint32_t l = 0; l < (1u << P.s_in); ++l) Sin[l] = state[P.in_off + (pdep32(l, P.lmask_in) | gpart)];
                 }
-                if (P.pad >> 31) {
-                    // ---- packed 16-bit panel (experimental): rotate + convert the tile, sweep every column with
-                    //      column_fast16, convert back into the canonical u32 order the write-back below expects
-                    const uint32_t s_in = P.s_in, xp0 = s_in - 1, spread = P.pad & 0x7FFFFFFFu;
-                    const uint32_t base = Sin[0] - spread;
-                    std::vector<uint32_t> W0(1u << (s_in - 1), 0), W1(1u << (s_in - 1), 0);
-                    for (uint32_t i = 0; i < (1u << s_in); ++i) {
-                        const uint32_t rel = Sin[i] - base;
-                        if (rel >= 32768u) { msg = "u16 panel: input beyond the planner's range bound"; return fail(101); }
-                        const uint32_t xr = tile_u16_rotate(i, xp0);
-                        W0[xr >> 1] |= rel << (16 * (xr & 1u));
-                    }
-                    uint32_t *Win = W0.data(), *Wout = W1.data();
-                    for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
-                        const TileCol &tc = ts.cols[k];
-                        if (!tile_is_u16(tc) || tile_u16_xpos(tc) != xp0 - (k - P.col_begin)) { msg = "u16 panel: column not marked"; return fail(103); }
-                        TileCol16 c16;
-                        tile_col16_from(tc, t, c16);
-                        uint32_t TW2[32], T52[32];
-                        for (uint32_t i = 0; i < 32; ++i) {
-                            TW2[i] = tile_fast16_warp_entry(c16, i);
-                            T52[i] = tile_fast16_lane_entry(c16, i);
-                        }
-                        const uint32_t cg = tile_cg(tc, t), nbits = 4u << (tc.l_out - 12);
-                        uint32_t *bpw = arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words;
-                        for (uint32_t w = 0; w < tc.bp_tile_words; ++w) bpw[w] = 0;
-                        for (uint32_t tid = 0; tid < 1024; ++tid) {
-                            uint32_t bits = 0;
-                            StoreEmit emit{&bits};
-                            if (tc.l_out == 14) column_fast16<2>(c16, TW2, T52, cg, Win, Wout, emit, tid);
-                            else column_fast16<1>(c16, TW2, T52, cg, Win, Wout, emit, tid);
-                            const uint32_t at = tid * nbits;  // element tid, as the kernel's u8 / u16 store
-                            bpw[at >> 5] |= bits << (at & 31u);
-                        }
-                        for (uint32_t w = 0; w < (1u << (tc.l_out - 1)); ++w)
-                            if ((Wout[w] & 0x8000u) || (Wout[w] & 0x80000000u)) { msg = "u16 panel: value beyond 2^15"; return fail(102); }
-                        std::swap(Win, Wout);
-                        ++fast_columns;
-                        ++u16_columns;
-                    }
-                    const uint32_t xpo = xp0 - (P.col_end - P.col_begin);  // canonical position of X after the panel
-                    for (uint32_t i = 0; i < (1u << P.s_out); ++i) {
-                        const uint32_t xr = tile_u16_rotate(i, xpo);
-                        Sin[i] = ((Win[xr >> 1] >> (16 * (xr & 1u))) & 0xFFFFu) + base;
-                    }
-                } else
                 for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
                     const TileCol &tc = ts.cols[k];
                     for (uint32_t i = 0; i < TILE_TL_SIZE; ++i) TL[i] = tile_tl_entry(tc, i);
@@ -235,7 +183,6 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     s->cost = (uint32_t)total;
     g_last_fast_columns = fast_columns;
     g_last_packed_columns = packed_columns;
-    g_last_u16_columns = u16_columns;
     rc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
     if (rc != WHMEC_OK) return fail(rc);
     return WHMEC_OK;
@@ -245,8 +192,6 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
 extern "C" uint64_t whemul_last_fast_columns(void) { return g_last_fast_columns; }
 // ... of which with thread-packed back-pointer bits (WHMEC_TILE_PACKED_BP=1)
 extern "C" uint64_t whemul_last_packed_columns(void) { return g_last_packed_columns; }
-// ... and (tile, column) pairs swept by column_fast16 inside packed 16-bit panels (WHMEC_TILE_U16=1)
-extern "C" uint64_t whemul_last_u16_columns(void) { return g_last_u16_columns; }
 
 // planner statistics only (no DP): panels, rounds, total tiles, max tiles per round, state/bp words
 extern "C" int whemul_plan_info(const whmec_problem *p, uint64_t *out8) {
@@ -376,115 +321,4 @@ extern "C" int whemul_plan_digest(const whmec_problem *p, uint64_t *digest) {
     mix(pk.fn_group.data(), pk.fn_group.size() * 4);
     *digest = h;
     return 0;
-}
-
-// ---- the experimental packed 16-bit column (column_fast16, tile_fast.h) against column_fast on one random column:
-// same tile state (canonical u32 layout vs the rotated u16 layout), same costs, same tie-breaking.  Returns the number of
-// outputs compared, or a negative code on the first difference.
-namespace {
-
-
-template <int LG16>
-long fast16_check(uint32_t seed, uint32_t cg, uint32_t pX) {
-    constexpr uint32_t IT = 1u << LG16, l_out = 12 + LG16, l_in = l_out, m = l_in + 1;
-    uint64_t rs = seed * 0x9E3779B97F4A7C15ull + 12345;
-    auto rnd = [&](uint32_t n) { rs = rs * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)((rs >> 33) % n); };
-    if (pX < 1 || pX >= l_in) return -100;
-    // reads of the column: phred and allele per canonical cell bit (bit 0 ends here, bit l_in starts here)
-    int32_t w[16];
-    uint32_t K1 = 0, K2 = 0;
-    const uint32_t max_phred = 1 + rnd(40);
-    for (uint32_t q = 0; q < m; ++q) {
-        const uint32_t ph = rnd(max_phred + 1), al = rnd(2);
-        w[q] = al == 0 ? (int32_t)ph : -(int32_t)ph;
-        (al == 0 ? K1 : K2) += ph;
-    }
-    TileCol tc;
-    std::memset(&tc, 0, sizeof tc);
-    tc.l_in = l_in; tc.n_new = 1; tc.d = 1; tc.l_out = l_out; tc.kind = 0; tc.g = 0;
-    tc.dropmask = 1; tc.K0 = TILE_KINF; tc.K12 = K1 + K2; tc.K2 = (int32_t)K2; tc.dpos[0] = 0;
-    tc.pad0 = 2; tc.pad1 = (uint8_t)(l_out - 11);
-    for (uint32_t q = 0; q < m; ++q) tc.w_local[q] = w[q];
-    // previous projection values of the tile (tie-heavy: small range)
-    const uint32_t base = 1000000 + rnd(1000), range = 1 + rnd(rnd(2) ? 6 : 3000);
-    std::vector<uint32_t> S32(1u << l_in), out32(1u << l_out), bp32((1u << l_out) / 32, 0);
-    for (auto &v : S32) v = base + rnd(range);
-    {
-        int32_t TW[32], T5[32];
-        for (uint32_t i = 0; i < 32; ++i) {
-            TW[i] = tile_fast_warp_entry(tc, 0, i);
-            T5[i] = tile_fast_lane_entry(tc, i);
-        }
-        constexpr int LG32 = LG16 + 1;
-        for (uint32_t tid = 0; tid < 1024; ++tid) {
-            RecordEmit emit{bp32.data() + (tid >> 5) * (1u << LG32), tid & 31u, bp32.data(), tid, 0};
-            column_fast<LG32, false, true>(tc, TW, T5, cg, S32.data(), out32.data(), emit, tid);
-        }
-    }
-    // the rotated u16 tile: X first, the ending read second, the others in order
-    auto others_of = [&](uint32_t x, uint32_t bits) {  // canonical index without bit 0 and bit pX, compacted
-        uint32_t o = 0, k = 0;
-        for (uint32_t q = 1; q < bits; ++q)
-            if (q != pX) o |= ((x >> q) & 1u) << k++;
-        return o;
-    };
-    std::vector<uint32_t> Win(1u << (l_in - 1), 0), Wout(1u << (l_out - 1), 0), tbits(1024, 0);
-    for (uint32_t x = 0; x < (1u << l_in); ++x) {
-        const uint32_t xr = ((x >> pX) & 1u) | ((x & 1u) << 1) | (others_of(x, l_in) << 2);
-        const uint32_t v = S32[x] - base + 7;  // tile-relative, a small positive offset
-        Win[xr >> 1] |= v << (16 * (xr & 1u));
-    }
-    TileCol16 t16;
-    std::memset(&t16, 0, sizeof t16);
-    auto both = [](int32_t v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; };
-    t16.k12x2 = both((int32_t)(K1 + K2)); t16.k2x2 = both((int32_t)K2);
-    t16.wp2 = both(w[0]); t16.nwp2 = both(-w[0]);
-    t16.wn2 = both(w[l_in]); t16.nwn2 = both(-w[l_in]);
-    t16.wx_hi = ((uint32_t)w[pX] & 0xFFFFu) << 16; t16.nwx_hi = ((uint32_t)(-w[pX]) & 0xFFFFu) << 16;
-    t16.l_out = l_out;
-    {
-        uint32_t k = 0;
-        for (uint32_t q = 1; q < l_in; ++q)
-            if (q != pX) { t16.w2[k] = both(w[q]); t16.nw2[k] = both(-w[q]); ++k; }
-    }
-    uint32_t TW2[32], T52[32];
-    for (uint32_t i = 0; i < 32; ++i) {
-        uint32_t a = 0, b = 0;
-        for (uint32_t bit = 0; bit < 5; ++bit) {
-            if ((i >> bit) & 1u) {
-                a = whmec_vadd2_host(a, t16.w2[5 + LG16 + bit]);
-                b = whmec_vadd2_host(b, t16.w2[bit]);
-            }
-        }
-        TW2[i] = a;
-        T52[i] = b;
-    }
-    for (uint32_t tid = 0; tid < 1024; ++tid)
-        column_fast16<LG16>(t16, TW2, T52, cg, Win.data(), Wout.data(), StoreEmit{&tbits[tid]}, tid);
-    // compare every output
-    const uint32_t halfq = 1u << (l_out - 2), N = 4 * IT;
-    for (uint32_t o = 0; o < (1u << l_out); ++o) {  // canonical output index: cell index without bit 0
-        const uint32_t cell = o << 1;
-        const uint32_t X = (cell >> pX) & 1u, nw = (cell >> l_in) & 1u, oth = others_of(cell & ((1u << l_in) - 1u), l_in);
-        const uint32_t q = oth | (nw ? halfq : 0), qm = oth;
-        const uint32_t got = (Wout[q] >> (16 * X)) & 0xFFFFu;
-        if (got != out32[o] - base + 7) return -(long)(1 + o);
-        // the bit the backtrace would read (tile_u16_bit_index) against the ballot layout's bit of the same output
-        const uint32_t idx = tile_u16_bit_index(l_out, pX - 1, o);
-        const uint32_t r16 = (tbits[idx / N] >> (idx % N)) & 1u;
-        const uint32_t r32 = (bp32[o >> 5] >> (o & 31u)) & 1u;
-        if (r16 != r32) return -(long)(1000000 + o);
-        (void)qm;
-    }
-    return (long)(1u << l_out);
-}
-
-}  // namespace
-
-extern "C" long whemul_fast16_column_check(uint32_t seed, uint32_t lg16, uint32_t cg, uint32_t pX) {
-    switch (lg16) {
-        case 0: return fast16_check<0>(seed, cg, pX);
-        case 1: return fast16_check<1>(seed, cg, pX);
-        default: return fast16_check<2>(seed, cg, pX);
-    }
 }

@@ -372,7 +372,7 @@ def test_tile_kernel_code_at_benchmark_coverage(emul, checker, cov, n, seed):
 
 
 def test_thread_packed_back_pointers(emul, checker, monkeypatch):
-    """WHMEC_TILE_PACKED_BP=1 (experimental layout of the fast columns' back-pointer bits: each thread keeps the bits of its own
+    """Thread-packed back-pointer bits of the fast columns (the default; WHMEC_TILE_PACKED_BP=0 keeps warp ballots): each thread keeps the bits of its own
     outputs, formed from the sign of v1 - v0 - par by a funnel shift; tile_packed_bit_index decodes them in the backtrace):
     same results as the reference with both layouts, sliding windows (twin outputs) and irregular starts, K0 active or not."""
     lib = emul["libwhemul.so"]
@@ -393,45 +393,6 @@ def test_thread_packed_back_pointers(emul, checker, monkeypatch):
         n_fast += int(lib.whemul_last_fast_columns())
         n_packed += int(lib.whemul_last_packed_columns())
     assert n_fast > 800 and n_packed > 600  # 8 or 16 outputs per thread: coverage >= 14
-
-
-def test_packed_16_bit_column_building_block(emul):
-    """`column_fast16` (csrc/tile_fast.h; not used by the kernel yet): the steady-state column on packed u16
-    values in the rotated tile layout gives, output by output, the values and the tie-breaking decisions of `column_fast` on the
-    same tile state — random weights / alleles, tie-heavy and wide value ranges, every position of the long-lived read X,
-    tiles of 2^12, 2^13 and 2^14 entries."""
-    lib = emul["libwhemul.so"]
-    lib.whemul_fast16_column_check.restype = C.c_long
-    lib.whemul_fast16_column_check.argtypes = [C.c_uint32] * 4
-    compared = 0
-    for seed in range(24):
-        for lg in (0, 1, 2):
-            l_in = 12 + lg
-            got = lib.whemul_fast16_column_check(seed, lg, seed & 1, 1 + (seed * 5) % (l_in - 1))
-            assert got == 1 << l_in, (seed, lg, got)
-            compared += got
-    assert compared == 24 * (4096 + 8192 + 16384)
-
-
-def test_packed_16_bit_panels_end_to_end(emul, checker, monkeypatch):
-    """WHMEC_TILE_U16=1 (experimental): the planner marks steady-state panels, cuts them before the long-lived
-    read X ends and states a range bound; a marked panel is rotated + converted to tile-relative u16 where it is loaded, swept by
-    `column_fast16`, converted back where it is written; the backtrace reads the thread-packed bits (tile_u16_bit_index).
-    Same cost, path and super-reads as the reference; the emulation fails loudly if a value leaves the stated range."""
-    lib = emul["libwhemul.so"]
-    lib.whemul_last_u16_columns.restype = C.c_uint64
-    monkeypatch.setenv("WHMEC_TILE_U16", "1")
-    swept = 0
-    for cov, n, seed in ((16, 44, 2), (17, 44, 3), (19, 44, 5), (20, 40, 6)):
-        prob = synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.04 * (seed % 3), max_phred=2 if seed % 2 == 0 else 40)
-        got = run_tile(lib, prob, 0)
-        assert got is not None and got.same_as(checker.solve(prob)), (cov, got.diff(checker.solve(prob)))
-        swept += int(lib.whemul_last_u16_columns())
-    assert swept > 800
-    # without the switch no panel is marked
-    monkeypatch.delenv("WHMEC_TILE_U16")
-    run_tile(lib, synth.sliding_window(40, 17, block_len=40, seed=3), 0)
-    assert int(lib.whemul_last_u16_columns()) == 0
 
 
 def test_host_worker_pool_rethrows_a_task_exception_on_the_caller(emul):

@@ -20,9 +20,7 @@ pytestmark = pytest.mark.gpu
 
 SWITCHES = {
     "default": {},
-    "ballot_bp": {"WHMEC_TILE_PACKED_BP": "0", "WHMEC_TILE_U16": "0"},
-    "packed_bp": {"WHMEC_TILE_PACKED_BP": "1", "WHMEC_TILE_U16": "0"},
-    "u16": {"WHMEC_TILE_U16": "1"},
+    "ballot_bp": {"WHMEC_TILE_PACKED_BP": "0"},
     "groups4": {"WHMEC_SOLVE_GROUPS": "4"},
     "pinned": {"WHMEC_PINNED_STAGING": "1"},
     "column": {"WHMEC_FORCE_COLUMN_KERNEL": "1"},
@@ -129,10 +127,10 @@ def test_golden_vectors_under_every_pedigree_switch(gpu, monkeypatch, switch):
         assert golden_io.check(lambda p: gpu.solve(p)[0], group) > 0
 
 
-@pytest.mark.parametrize("switch", ["default", "packed_bp", "u16", "groups4"])
+@pytest.mark.parametrize("switch", ["default", "ballot_bp", "groups4"])
 def test_fuzz_high_coverage_under_switches(gpu, checker, monkeypatch, switch):
     """Sliding windows and irregular spans at coverage 14-19 (long runs of steady-state columns, homozygous sites, gaps,
-    tie-heavy and wide weights): the thread-packed and packed 16-bit column code against the reference."""
+    tie-heavy and wide weights): the thread-packed and the ballot column code against the reference."""
     set_switch(monkeypatch, SWITCHES[switch])
     rng = np.random.default_rng(4242)
     for it in range(24):
@@ -156,15 +154,3 @@ def test_fuzz_high_coverage_under_switches(gpu, checker, monkeypatch, switch):
         assert gerr == werr, (it, gerr, werr)
         if want is not None:
             assert got.same_as(want), (switch, it, cov, got.diff(want))
-
-
-def test_packed_16_bit_panels_fall_back_when_the_range_bound_is_exceeded(gpu, checker, monkeypatch):
-    """Phred values so large that a panel's value spread crosses 2^15: the planner must not mark it for the packed 16-bit body
-    (DESIGN.md 7f), and the u32 body must still equal the reference; just below the bound the packed body runs."""
-    set_switch(monkeypatch, {"WHMEC_TILE_U16": "1"})
-    for max_phred in (40, 300, 3000):
-        prob = synth.sliding_window(60, 17, block_len=60, seed=99, max_phred=max_phred)
-        want = checker.solve(prob)
-        got, stats = gpu.solve(prob)
-        assert stats["path_kind"] == 1
-        assert got.same_as(want), (max_phred, got.diff(want))

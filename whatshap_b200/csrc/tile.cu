@@ -40,7 +40,6 @@ struct TileSmem {
     uint32_t cg[2];
     uint32_t a_col[TC_CHUNK];
     uint32_t panel_index;
-    TileCol16 c16[3];  // packed 16-bit panels (experimental): constants of columns k, k + 1, k + 2
 };
 static_assert(sizeof(TileSmem) <= 227 * 1024, "TileSmem exceeds the shared memory of one CTA on sm_100");
 
@@ -257,59 +256,6 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
         }
     }
 
-    if (P.pad >> 31) {
-        // ---- packed 16-bit panel (experimental, WHMEC_TILE_U16=1).  S.buf[0] holds the tile's input in
-        // canonical u32 order; it becomes tile-relative u16 in the rotated order (X first) in the lower half of S.buf[1],
-        // every column is swept by column_fast16 between the two halves of S.buf[1], and the result goes back to
-        // S.buf[0] as canonical u32 for the write-back below.  The constants of column k + 2 and the tables of column
-        // k + 1 are built by four warps' worth of threads while column k is evaluated (one barrier per column).
-        const uint32_t kb = P.col_begin, ke = P.col_end, xp0 = P.s_in - 1, nin = 1u << P.s_in;
-        const uint32_t base = S.buf[0][0] - (P.pad & 0x7FFFFFFFu);
-        uint32_t *W[2] = {S.buf[1], S.buf[1] + TILE_ENTRIES / 2};
-        {
-            uint16_t *h = reinterpret_cast<uint16_t *>(W[0]);
-            for (uint32_t i = tid; i < nin; i += NT) h[tile_u16_rotate(i, xp0)] = (uint16_t)(S.buf[0][i] - base);
-        }
-        {  // the panel's column descriptors (at most 13 < TC_CHUNK) into shared memory
-            constexpr uint32_t WORDS = sizeof(TileCol) / 4;
-            for (uint32_t w = tid; w < (ke - kb) * WORDS; w += NT) ((uint32_t *)S.tcs)[w] = ((const uint32_t *)(tcols + kb))[w];
-        }
-        __syncthreads();
-        if (tid == 64) tile_col16_from(S.tcs[0], tile, S.c16[kb % 3]);
-        if (tid == 96 && kb + 1 < ke) tile_col16_from(S.tcs[1], tile, S.c16[(kb + 1) % 3]);
-        __syncthreads();
-        if (tid < 32) S.TW[kb & 1u][tid] = (int32_t)tile_fast16_warp_entry(S.c16[kb % 3], tid);
-        else if (tid < 64) S.T5[kb & 1u][tid - 32] = (int32_t)tile_fast16_lane_entry(S.c16[kb % 3], tid - 32);
-        else if (tid == 64) S.cg[kb & 1u] = tile_cg(S.tcs[0], tile);
-        uint32_t wcur = 0;
-        for (uint32_t k = kb; k < ke; ++k) {
-            __syncthreads();  // constants and tables of column k ready; column k - 1 complete
-            if (k + 1 < ke) {
-                const uint32_t nb = (k + 1) & 1u;
-                if (tid < 32) S.TW[nb][tid] = (int32_t)tile_fast16_warp_entry(S.c16[(k + 1) % 3], tid);
-                else if (tid < 64) S.T5[nb][tid - 32] = (int32_t)tile_fast16_lane_entry(S.c16[(k + 1) % 3], tid - 32);
-                else if (tid == 64) S.cg[nb] = tile_cg(S.tcs[k + 1 - kb], tile);
-                else if (tid == 96 && k + 2 < ke) tile_col16_from(S.tcs[k + 2 - kb], tile, S.c16[(k + 2) % 3]);
-            }
-            const TileCol16 &c = S.c16[k % 3];
-            const uint32_t tb = k & 1u;
-            uint32_t *bpw = arena + S.tcs[k - kb].bp_off + (uint64_t)tile * S.tcs[k - kb].bp_tile_words;
-            if (c.l_out == 14)
-                column_fast16<2>(c, reinterpret_cast<const uint32_t *>(S.TW[tb]), reinterpret_cast<const uint32_t *>(S.T5[tb]), S.cg[tb],
-                                 W[wcur], W[wcur ^ 1u], PackedEmit<16>{bpw, tid}, tid);
-            else
-                column_fast16<1>(c, reinterpret_cast<const uint32_t *>(S.TW[tb]), reinterpret_cast<const uint32_t *>(S.T5[tb]), S.cg[tb],
-                                 W[wcur], W[wcur ^ 1u], PackedEmit<8>{bpw, tid}, tid);
-            wcur ^= 1u;
-        }
-        __syncthreads();
-        {
-            const uint32_t xpo = xp0 - (ke - kb), nout = 1u << P.s_out;
-            const uint16_t *h = reinterpret_cast<const uint16_t *>(W[wcur]);
-            for (uint32_t i = tid; i < nout; i += NT) S.buf[0][i] = (uint32_t)h[tile_u16_rotate(i, xpo)] + base;
-        }
-        cur = 0;
-    } else
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
         const uint32_t j = (k - P.col_begin) % TC_CHUNK;
         if (j == 0) {

@@ -115,19 +115,6 @@ WHMEC_HD uint32_t tile_packed_bit_index(const TileCol &tc, uint32_t lo) {
 }
 
 
-// Index of the back-pointer bit of canonical local output `lo` of a column swept by column_fast16 inside the tile's slice
-// of the arena: `xpos_out` = canonical position of X among the output bits, the starting read is the top bit, pair index =
-// the remaining bits; element = thread (N = 2^(l_out - 10) bits), j-th shifted-in bit at N - 1 - j.
-WHMEC_HD uint32_t tile_u16_bit_index(uint32_t l_out, uint32_t xpos_out, uint32_t lo) {
-    const uint32_t lg = l_out - 12, it_count = 1u << lg, n = 4u << lg;
-    const uint32_t X = (lo >> xpos_out) & 1u, nw = (lo >> (l_out - 1)) & 1u;
-    const uint32_t low = lo & ((1u << xpos_out) - 1u), high = (lo & ((1u << (l_out - 1)) - 1u)) >> (xpos_out + 1);
-    const uint32_t qm = low | (high << xpos_out);
-    const uint32_t warp = qm >> (lg + 5), it = (qm >> 5) & (it_count - 1), lane = qm & 31u;
-    const uint32_t j = it * 4 + nw * 2 + (X ? 0 : 1);
-    return (warp * 32 + lane) * n + (n - 1 - j);
-}
-
 // Backtrace of one chain through the tile-layout back-pointers (pedigreedptable.cpp:144-160).
 WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, const uint32_t *arena, uint32_t k_first,
                                    uint32_t k_last, uint64_t end_key, uint32_t *path_index) {
@@ -142,8 +129,7 @@ WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, co
         const uint32_t tile = pext32(o, pt.gmask_out);
         const uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
         uint32_t at = lo;
-        if (pt.pad2 & 0x100u) at = tile_u16_bit_index(pt.l_out, ((pt.pad2 >> 16) & 0xFFu) - 1u, lo);  // packed 16-bit panel
-        else if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);                                     // thread-packed bits
+        if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);  // thread-packed bits
         const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_words, pt.bp_width, at);
         x = candidate_index(pm, o, bp);
         path_index[k - 1] = x;

@@ -122,155 +122,3 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
 }
 
 }  // namespace whmec
-
-// ---- experimental building block (not used by the kernel yet): the steady-state column on packed 16-bit
-// values.  Layout of a u16 tile: local bit 0 = a read X that outlives the panel, bit 1 = the read that ends in this
-// column, then the other local reads in canonical order, the read that starts in this column on top.  One 32-bit word
-// holds the same candidate of the two outputs that differ in X; the next word the other candidate of the same outputs.
-// Values are tile-relative and every value (costs included) stays below 2^15.  Exercised against column_fast by
-// tests/emul (whemul_fast16_column_check).
-namespace whmec {
-
-struct TileCol16 {
-    uint32_t k12x2;    // K1 + K2 in both halves
-    uint32_t k2x2;     // K2 (+ E of the tile's global reads) in both halves
-    uint32_t wp2;      // weight of the ending read (bit 1) in both halves, and its negation mod 2^16
-    uint32_t nwp2;
-    uint32_t wn2;      // weight of the starting read (top bit) in both halves, and its negation
-    uint32_t nwn2;
-    uint32_t wx_hi;    // weight of X in the high half only (output B = output A + X)
-    uint32_t nwx_hi;
-    uint32_t w2[16];   // (w, w) of pair-index bit q (rotated output bit q + 1)
-    uint32_t nw2[16];
-    uint32_t l_out;    // log2 outputs (twins included)
-};
-
-#if defined(__CUDA_ARCH__)
-#define WHMEC_VADD2(a, b) __vadd2(a, b)
-#define WHMEC_VMINU2(a, b) __vminu2(a, b)
-#else
-WHMEC_HD uint32_t whmec_vadd2_host(uint32_t a, uint32_t b) { return ((a + b) & 0xFFFFu) | (((a >> 16) + (b >> 16)) << 16); }
-WHMEC_HD uint32_t whmec_vminu2_host(uint32_t a, uint32_t b) {
-    const uint32_t lo = (a & 0xFFFFu) < (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
-    const uint32_t hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
-    return lo | (hi << 16);
-}
-#define WHMEC_VADD2(a, b) whmec_vadd2_host(a, b)
-#define WHMEC_VMINU2(a, b) whmec_vminu2_host(a, b)
-#endif
-
-// Thread `tid` produces the 2^LG pair-iterations x 2 twins x 2 halves outputs of pair indices
-// qm = warp * 2^LG * 32 + it * 32 + lane (and qm + 2^(l_out - 2) for the twin).  TW2 / T52: packed (value, value) sums of
-// the weights selected by the warp / lane bits of qm.  Returns nothing; bits go to emit.store: for iteration `it` the order
-// is (main pair: high half, low half; twin pair: high half, low half), first shifted in = highest.
-template <int LG, class Emit>
-WHMEC_HD void column_fast16(const TileCol16 &tc, const uint32_t *__restrict__ TW2, const uint32_t *__restrict__ T52, uint32_t cg,
-                            const uint32_t *__restrict__ Win, uint32_t *__restrict__ Wout, Emit emit, uint32_t tid) {
-    constexpr int IT = 1 << LG;
-    const uint32_t lane = tid & 31u, warp = tid >> 5;
-    const uint32_t qbase = warp * (IT * 32u) + lane;
-    const TilePair *win2 = reinterpret_cast<const TilePair *>(Win) + qbase;
-    uint32_t *wo = Wout + qbase;
-    const uint32_t halfq = 1u << (tc.l_out - 2);  // pairs without the starting read
-    // parity of the other bits of output A (X = 0) above the ending read; output B has one more bit set (X)
-    const uint32_t par0 = (WHMEC_POPC(qbase) + (cg & 1u)) & 1u;
-    uint32_t ue[IT], nue[IT];
-    ue[0] = WHMEC_VADD2(WHMEC_VADD2(tc.k2x2, WHMEC_VADD2(TW2[warp], T52[lane])), tc.wx_hi);
-    nue[0] = tc.k12x2 - ue[0];  // both halves are true costs: K1 - E >= 0, no borrow
-#pragma unroll
-    for (int it = 1; it < IT; ++it) {
-        ue[it] = WHMEC_VADD2(ue[it & (it - 1)], tc.w2[5 + cx_ctz(it)]);
-        nue[it] = WHMEC_VADD2(nue[it & (it - 1)], tc.nw2[5 + cx_ctz(it)]);
-    }
-    uint32_t bits = 0;
-#pragma unroll
-    for (int it = 0; it < IT; ++it) {
-        const TilePair s = win2[it * 32];
-        const uint32_t parA = par0 ^ (uint32_t)cx_parity(it);
-#pragma unroll
-        for (int twin = 0; twin < 2; ++twin) {
-            const uint32_t u0 = twin ? WHMEC_VADD2(ue[it], tc.wn2) : ue[it];
-            const uint32_t n0 = twin ? WHMEC_VADD2(nue[it], tc.nwn2) : nue[it];
-            const uint32_t c0 = WHMEC_VMINU2(u0, n0);
-            const uint32_t c1 = WHMEC_VMINU2(WHMEC_VADD2(u0, tc.wp2), WHMEC_VADD2(n0, tc.nwp2));
-            const uint32_t v0 = WHMEC_VADD2(c0, s.x), v1 = WHMEC_VADD2(c1, s.y);
-            wo[twin * halfq + it * 32] = WHMEC_VMINU2(v0, v1);
-            // per half: bit 15 of (v1 | 0x8000) - v0 - par is set iff v1 >= v0 + par; the halves have opposite parity (X)
-            const uint32_t pa = parA ^ (uint32_t)twin;  // parity of output A of this pair
-            const uint32_t d = (v1 | 0x80008000u) - v0 - (pa ? 0x00000001u : 0x00010000u);
-            bits = tile_shift_in_sign(bits, d);        // high half (output B)
-            bits = tile_shift_in_sign(bits, d << 16);  // low half (output A)
-        }
-    }
-    // the raw bit says "v1 >= v0 + par"; the back-pointer is the rank of the winner in visiting order, pick1 ^ par with
-    // pick1 = !raw: flip output A's bit unless its parity is set, output B's bit if it is (B has one more bit set: X)
-    constexpr uint32_t N = 4 * IT;
-    uint32_t cm = 0;  // par0 == 0
-#pragma unroll
-    for (int it = 0; it < IT; ++it)
-#pragma unroll
-        for (int twin = 0; twin < 2; ++twin) {
-            const uint32_t pa = (uint32_t)cx_parity(it) ^ (uint32_t)twin;
-            const int j = it * 4 + twin * 2;
-            cm |= pa << (N - 1 - j);               // output B: raw ^ par_A
-            cm |= (pa ^ 1u) << (N - 1 - (j + 1));  // output A: raw ^ 1 ^ par_A
-        }
-    const uint32_t all = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
-    emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
-}
-
-// TileCol::pad2 of a column inside a packed 16-bit panel: bit 8 set, bits 16..23 = position of X among the column's
-// canonical cell bits.
-WHMEC_HD bool tile_is_u16(const TileCol &tc) { return (tc.pad2 & 0x100u) != 0; }
-WHMEC_HD uint32_t tile_u16_xpos(const TileCol &tc) { return (tc.pad2 >> 16) & 0xFFu; }
-
-WHMEC_HD uint32_t tile_both_halves(int32_t v) { return ((uint32_t)v & 0xFFFFu) * 0x00010001u; }
-
-// The packed constants of one column of tile `tile` from its TileCol (canonical cell order: bit 0 ends here, bit l_in
-// starts here, X at tile_u16_xpos) -- everything column_fast16 needs except the two 32-entry tables.
-WHMEC_HD void tile_col16_from(const TileCol &tc, uint32_t tile, TileCol16 &out) {
-    const uint32_t xpos = tile_u16_xpos(tc), l_in = tc.l_in;
-    int32_t k2 = tc.K2;
-    for (uint32_t b = 0; b < tc.g; ++b)
-        if ((tile >> b) & 1u) k2 += tc.w_global[b];
-    out.k12x2 = tile_both_halves((int32_t)tc.K12);
-    out.k2x2 = tile_both_halves(k2);
-    out.wp2 = tile_both_halves(tc.w_local[0]);
-    out.nwp2 = tile_both_halves(-tc.w_local[0]);
-    out.wn2 = tile_both_halves(tc.w_local[l_in]);
-    out.nwn2 = tile_both_halves(-tc.w_local[l_in]);
-    out.wx_hi = ((uint32_t)tc.w_local[xpos] & 0xFFFFu) << 16;
-    out.nwx_hi = ((uint32_t)(-tc.w_local[xpos]) & 0xFFFFu) << 16;
-    out.l_out = tc.l_out;
-    uint32_t k = 0;
-    for (uint32_t q = 1; q < l_in; ++q)
-        if (q != xpos) {
-            out.w2[k] = tile_both_halves(tc.w_local[q]);
-            out.nw2[k] = tile_both_halves(-tc.w_local[q]);
-            ++k;
-        }
-    for (; k < 16; ++k) out.w2[k] = out.nw2[k] = 0;
-}
-
-// The two 32-entry tables of column_fast16: sums of the packed weights selected by the warp / lane bits of the pair index.
-WHMEC_HD uint32_t tile_fast16_warp_entry(const TileCol16 &c, uint32_t warp) {
-    const uint32_t lg = c.l_out - 12;
-    uint32_t s = 0;
-    for (uint32_t b = 0; b < 5; ++b)
-        if ((warp >> b) & 1u) s = WHMEC_VADD2(s, c.w2[5 + lg + b]);
-    return s;
-}
-WHMEC_HD uint32_t tile_fast16_lane_entry(const TileCol16 &c, uint32_t lane) {
-    uint32_t s = 0;
-    for (uint32_t b = 0; b < 5; ++b)
-        if ((lane >> b) & 1u) s = WHMEC_VADD2(s, c.w2[b]);
-    return s;
-}
-
-// Rotated index of canonical local index i of `bits` bits with X at canonical position xp: X first, the rest in order.
-WHMEC_HD uint32_t tile_u16_rotate(uint32_t i, uint32_t xp) {
-    const uint32_t low = i & ((1u << xp) - 1u), high = i >> (xp + 1);
-    return ((i >> xp) & 1u) | (low << 1) | (high << (xp + 1));
-}
-
-}  // namespace whmec

@@ -30,15 +30,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     const char *packed_env = std::getenv("WHMEC_TILE_PACKED_BP");
     const bool packed_bp = !(packed_env && packed_env[0] == '0');  // default since round 2 (B200: 29.97 -> 25.42 ms on cfg3); "0" keeps the warp-ballot layout
-    // experimental (WHMEC_TILE_U16=1): steady-state panels on packed 16-bit values; needs every read's
-    // total weight for the range bound
-    const char *u16_env = std::getenv("WHMEC_TILE_U16");
-    const bool u16_mode = u16_env && u16_env[0] == '1' && TILE_SMAX == 14;
-    std::vector<uint64_t> read_weight;
-    if (u16_mode) {
-        read_weight.assign(pk.n_reads, 0);
-        for (size_t e = 0; e < pk.act_read.size(); ++e) read_weight[pk.act_read[e]] += pk.act_phred[e];
-    }
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = tnow();
@@ -133,7 +124,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                 for (uint32_t q = 0; q < G.n; ++q) g_stamp[G.v[q] - rbase] = attempt;
                 const uint32_t n_new_local0 = l_new;
                 Small Lcur = Lold;
-                Small Lhist[16];  // local order after each of the first 16 accepted columns (packed 16-bit panels are cut short)
                 uint32_t n_accepted = 0;
                 uint32_t j = k;
                 bool ends_chain = false;
@@ -251,7 +241,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                         const uint32_t per_thread = (1u << tc.pad1) << (tc.pad0 == 2 ? 1 : 0);
                         if (per_thread == 8 || per_thread == 16) tc.pad2 = 1;
                     }
-                    if (n_accepted < 16) Lhist[n_accepted] = nextL;
                     ++n_accepted;
                     Lcur = nextL;
                     if (chain_end) {
@@ -261,28 +250,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     }
                 }
                 if (n_accepted == 0) continue;  // try a smaller tile
-                // Packed 16-bit panel?  Every column must be a twin steady-state column (one read ends, one starts, no
-                // homozygous assignment) of one tile size; X = the youngest initial local read must outlive the panel,
-                // so the panel is cut before the column in which X ends; and all values must stay below 2^15.
-                uint32_t u16_spread = 0;
-                if (u16_mode && G.n >= 1 && (Lold.n == 13 || Lold.n == 14)) {
-                    const uint32_t L0 = Lold.n, len16 = std::min<uint32_t>(j - k, L0 - 1);
-                    bool ok = len16 >= 2;
-                    uint64_t spread = 0, growth = 0;
-                    for (uint32_t q = 0; q < L0; ++q) spread += read_weight[Lold.v[q]];
-                    for (uint32_t q = k; q < k + len16 && ok; ++q) {
-                        const TileCol &tc = ts.cols[q];
-                        ok = tc.kind == 0 && tc.pad0 == 2 && tc.l_in == L0 && tc.l_out == L0 && tc.K0 >= TILE_KINF && tc.K12 < 32768;
-                        growth += tc.K12;
-                    }
-                    if (ok && 2 * spread + growth + 16 < 32768) {
-                        j = k + len16;
-                        ends_chain = false;
-                        Lcur = Lhist[len16 - 1];
-                        for (uint32_t q = k; q < j; ++q) ts.cols[q].pad2 = 0x100u | (((L0 - 1) - (q - k)) << 16);
-                        u16_spread = (uint32_t)spread;
-                    }
-                }
                 // commit the panel [k, j)
                 for (uint32_t q = 0; q < Lold.n; ++q) lold_stamp[Lold.v[q] - rbase] = attempt;
                 for (uint32_t q = 0; q < Gold.n; ++q) gold_stamp[Gold.v[q] - rbase] = attempt;
@@ -326,7 +293,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     bp_words += per_tile_words << tc.g;
                 }
                 P.in_gold = Gold.n;
-                if (u16_spread || (ts.cols[k].pad2 & 0x100u)) P.pad = 0x80000000u | u16_spread;  // packed 16-bit panel + its range bound
                 per_chain[c].push_back(P);
                 per_chain_sets[c].push_back(PanelSets{G.vec(), Lcur.vec(), Lold.vec(), Gold.vec()});
                 ++pcount;

@@ -40,8 +40,7 @@ struct TileCol {            // one column as seen by a tile (device + host)
     uint32_t bp_width;      // 0,1,2,4,8,16 bits per entry
     uint64_t bp_off;        // 32-bit words into the arena; tile t owns words [bp_off + t*bp_tile_words, +bp_tile_words)
     uint32_t bp_tile_words; // ceil(2^l_out * bp_width / 32)
-    uint32_t pad2;          // fast columns: bit 0 = back-pointer bits packed per thread (tile_packed_bit_index), else warp-ballot order;
-                            // bit 8 = column of a packed 16-bit panel, bits 16..23 = position of X (tile_fast.h)
+    uint32_t pad2;          // fast columns: bit 0 = back-pointer bits packed per thread (tile_packed_bit_index), else warp-ballot order
     uint32_t gmask_out;     // canonical mask (over f_k bits) of the global reads after this column
     uint32_t lmask_col;     // canonical mask (over a_k bits) of the local reads of this column
     int32_t w_local[16];    // signed weight of local bit q:  +phred if allele 0, -phred if allele 1
@@ -67,7 +66,7 @@ struct Panel {
     uint32_t in_layout, out_layout;
     uint32_t in_gA, in_j, in_sA;   // tile-major input: producer's global bits, chunk bits, producer's s_out
     uint32_t in_gold;              // number of consumer tile-id bits that come from the old state
-    uint32_t pad;                  // bit 31: packed 16-bit panel (experimental), bits 0..30: bound on |S(x) - S(0)| of its input
+    uint32_t pad;
     uint64_t in_off, out_off;      // 32-bit word offsets of the chain's state buffers
 };
 
