@@ -2,6 +2,7 @@
 incl. the steady-state column `column_fast`) against the compiled reference (oracle/_ref).  No GPU.  Authoring container only.
     python scripts/cpu_fuzz_emul.py <seed> <seconds>          # six pedigree shapes + single individuals, coverage <= 12
     python scripts/cpu_fuzz_emul.py <seed> <seconds> fast     # single individuals, coverage 11-15: every tile runs column_fast
+    python scripts/cpu_fuzz_emul.py <seed> <seconds> mirror   # single individuals, coverage 15-19: mirrored multi-tile panels
 Set WHMEC_TILE_PACKED_BP=1 to fuzz the thread-packed back-pointer layout."""
 import ctypes as C
 import os
@@ -40,7 +41,8 @@ def run(lib, prob, tile, chunk):
 
 
 seed, budget = int(sys.argv[1]), float(sys.argv[2])
-fast_mode = len(sys.argv) > 3 and sys.argv[3] == "fast"
+fast_mode = len(sys.argv) > 3 and sys.argv[3] in ("fast", "mirror")
+mirror_mode = len(sys.argv) > 3 and sys.argv[3] == "mirror"  # coverage 15-19: several tiles per panel, mirrored panels, both parities of km
 rng = np.random.default_rng(seed)
 ref = checker.reference()
 assert ref is not None, "needs the compiled reference (oracle/_ref)"
@@ -49,7 +51,7 @@ t0 = time.time()
 n = tiles = fast_cols = 0
 while time.time() - t0 < budget:
     if fast_mode:
-        cov = int(rng.integers(11, 16))
+        cov = int(rng.integers(15, 20)) if mirror_mode else int(rng.integers(11, 16))
         if n % 2:
             prob = synth.random_problem(rng, int(rng.integers(8, 40)), cov, "single", distrust=bool(rng.integers(0, 2)), gap=float(rng.random() * 0.2),
                                         mean_len=float(rng.uniform(8, 20)), burst=int(rng.integers(3, 7)), conflict_free=True, max_phred=int(rng.choice([1, 3, 40])))

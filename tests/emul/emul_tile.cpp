@@ -32,19 +32,33 @@ struct RecordEmit {
         const uint32_t at = tid * bits_per_thread;
         tile_words[at >> 5] |= (bits & low_mask(bits_per_thread)) << (at & 31u);
     }
+    uint32_t section;  // words from the tile's own section to its mirror section (mirrored panels with km != 0)
+    void mirror(uint32_t word, bool bit) const {
+        if (bit) words[section + word] |= 1u << lane;
+    }
+    void store_mirror(uint32_t bits) const {
+        const uint32_t at = tid * bits_per_thread;
+        tile_words[section + (at >> 5)] |= (bits & low_mask(bits_per_thread)) << (at & 31u);
+    }
 };
 
 template <int LG, bool SHARE>
 void fast_column(const TileCol &tc, const int32_t *TW, const int32_t *T5, uint32_t cg, const uint32_t *Sin, uint32_t *Sout, uint32_t *bpw) {
     constexpr uint32_t IT = 1u << LG;
-    for (uint32_t w = 0; w < ((1u << tc.l_out) + 31) / 32; ++w) bpw[w] = 0;
+    const bool mirror = tc.half && tc.km != 0;
+    for (uint32_t w = 0; w < tc.bp_tile_stride; ++w) bpw[w] = 0;
     for (uint32_t tid = 0; tid < 1024; ++tid) {
-        RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u, bpw, tid, tile_fast_bits_per_thread(tc)};
-        if (tc.pad2 & 1u) {
-            if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
-            else column_fast<LG, true, SHARE, true>(tc, TW, T5, cg, Sin, Sout, emit, tid);
-        } else if (tc.K0 >= TILE_KINF) column_fast<LG, false, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
-        else column_fast<LG, true, SHARE>(tc, TW, T5, cg, Sin, Sout, emit, tid);
+        RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u, bpw, tid, tile_fast_bits_per_thread(tc), tc.bp_tile_words};
+        const bool k0 = tc.K0 < TILE_KINF, packed = (tc.pad2 & 1u) != 0;
+#define EMUL_FAST(HK, PK, MR) column_fast<LG, HK, SHARE, PK, MR>(tc, TW, T5, cg, Sin, Sout, emit, tid)
+        if (mirror) {
+            if (packed) { if (k0) EMUL_FAST(true, true, true); else EMUL_FAST(false, true, true); }
+            else { if (k0) EMUL_FAST(true, false, true); else EMUL_FAST(false, false, true); }
+        } else {
+            if (packed) { if (k0) EMUL_FAST(true, true, false); else EMUL_FAST(false, true, false); }
+            else { if (k0) EMUL_FAST(true, false, false); else EMUL_FAST(false, false, false); }
+        }
+#undef EMUL_FAST
     }
 }
 
@@ -113,18 +127,27 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r)
         for (uint32_t pi = ts.round_begin[r]; pi < ts.round_begin[r + 1]; ++pi) {
             const Panel &P = ts.panels[pi];
-            for (uint32_t t = 0; t < (1u << P.g); ++t) {
+            for (uint32_t t = 0; t < (1u << (P.g - P.half)); ++t) {  // mirrored panel: tiles with top tile-id bit 0 only
                 uint32_t *Sin = bufA.data(), *Sout = bufB.data();
                 if (P.fresh) Sin[0] = 0;
                 else if (P.in_layout == 1) {
                     const uint32_t told = t & low_mask(P.in_gold);
                     for (uint32_t i = 0; i < (1u << P.s_in); ++i) {
-                        const uint32_t tA = i & low_mask(P.in_gA), ll = i >> P.in_gA;
-                        Sin[i] = state[P.in_off + ((uint64_t)told << P.in_j) + ((uint64_t)tA << P.in_sA) + ll];
+                        uint32_t tA = i & low_mask(P.in_gA), at = (told << P.in_j) + (i >> P.in_gA);  // producer tile, its local index
+                        if (P.in_half && ((tA >> (P.in_gA - 1)) & 1u)) {  // not computed: complemented index of the mirror tile
+                            tA = ~tA & low_mask(P.in_gA);
+                            at = ~at & low_mask(P.in_sA);
+                        }
+                        Sin[i] = state[P.in_off + ((uint64_t)tA << P.in_sA) + at];
                     }
                 } else {
                     const uint32_t gpart = pdep32(t, P.gmask_in);
-                    for (uint32_t l = 0; l < (1u << P.s_in); ++l) Sin[l] = state[P.in_off + (pdep32(l, P.lmask_in) | gpart)];
+                    const uint32_t fmask_in = P.lmask_in | P.gmask_in;
+                    for (uint32_t l = 0; l < (1u << P.s_in); ++l) {
+                        uint32_t e = pdep32(l, P.lmask_in) | gpart;
+                        if (P.in_half && (e & P.in_top)) e = ~e & fmask_in;
+                        Sin[l] = state[P.in_off + e];
+                    }
                 }
                 for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
                     const TileCol &tc = ts.cols[k];
@@ -143,24 +166,28 @@ extern "C" int whemul_tile_solve(const whmec_problem *p, whmec_solution *s, uint
                         }
                         if (best < chain_key[P.chain]) chain_key[P.chain] = best;
                     } else if (tc.pad0 && use_fast) {
-                        run_fast_column(tc, t, Sin, Sout, arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_words);
+                        run_fast_column(tc, t, Sin, Sout, arena.data() + tc.bp_off + (uint64_t)t * tc.bp_tile_stride);
                         ++fast_columns;
                         packed_columns += (tc.pad2 & 1u) != 0;
                         std::swap(Sin, Sout);
                     } else {
                         const uint32_t ncand = 1u << tc.d;
                         for (uint32_t o = 0; o < (1u << tc.l_out); ++o) {
-                            uint64_t best = KEY_INF;
+                            uint64_t best = KEY_INF, mbest = KEY_INF;
                             uint32_t step = chunk ? chunk : ncand;
                             for (uint32_t r0 = 0; r0 < ncand; r0 += step) {
                                 uint32_t r1 = r0 + step < ncand ? r0 + step : ncand;
-                                uint64_t key = tile_eval(c, o, r0, r1);
+                                uint64_t mkey;
+                                uint64_t key = tile_eval(c, o, r0, r1, &mkey);
                                 if (key < best) best = key;
+                                if (mkey < mbest) mbest = mkey;
                             }
                             Sout[o] = (uint32_t)(best >> 32);
                             // WHEMUL_TILE_FAST=0 on a column the planner marked thread-packed: same bit positions as the fast code
                             const uint32_t at = (tc.pad0 && (tc.pad2 & 1u)) ? tile_packed_bit_index(tc, o) : o;
-                            bp_store_serial(arena.data(), tc.bp_off + (uint64_t)t * tc.bp_tile_words, tc.bp_width, at, (uint32_t)best);
+                            const uint64_t slice = tc.bp_off + (uint64_t)t * tc.bp_tile_stride;
+                            bp_store_serial(arena.data(), slice, tc.bp_width, at, (uint32_t)best);
+                            if (tc.half && tc.km != 0) bp_store_serial(arena.data(), slice + tc.bp_tile_words, tc.bp_width, at, (uint32_t)mbest);
                         }
                         std::swap(Sin, Sout);
                     }

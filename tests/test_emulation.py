@@ -91,7 +91,8 @@ def test_tile_planner_on_benchmark_shapes(emul):
     """Panels per chain and state traffic for the BASELINE.json shapes (planner only, no DP)."""
     lib = emul["libwhemul.so"]
     out = (C.c_uint64 * 8)()
-    for name, n, chains, tiles_per_panel in (("cfg2", 2000, 4, 1), ("cfg3", 1000, 2, 32), ("cfg4", 200, 1, 1024)):
+    # tiles per panel: 2^g / 2 -- of every pair of mirror-image tiles only one is computed (Panel::half)
+    for name, n, chains, tiles_per_panel in (("cfg2", 2000, 4, 1), ("cfg3", 1000, 2, 16), ("cfg4", 200, 1, 512)):
         prob = synth.config(name, n)
         cp = prob.as_c()
         assert lib.whemul_plan_info(C.byref(cp), out) == 0
@@ -367,7 +368,7 @@ def test_tile_kernel_code_at_benchmark_coverage(emul, checker, cov, n, seed):
     lib.whemul_last_fast_columns.restype = C.c_uint64
     prob = synth.sliding_window(n, cov, block_len=n, seed=seed, gap=0.05, max_phred=40 if seed % 4 == 1 else 2)
     got = run_tile(lib, prob, 0)
-    assert got is not None and int(lib.whemul_last_fast_columns()) > 300
+    assert got is not None and int(lib.whemul_last_fast_columns()) > 150
     assert got.same_as(checker.solve(prob)), got.diff(checker.solve(prob))
 
 
@@ -392,7 +393,7 @@ def test_thread_packed_back_pointers(emul, checker, monkeypatch):
         assert got is not None and got.same_as(checker.solve(prob)), got.diff(checker.solve(prob))
         n_fast += int(lib.whemul_last_fast_columns())
         n_packed += int(lib.whemul_last_packed_columns())
-    assert n_fast > 800 and n_packed > 600  # 8 or 16 outputs per thread: coverage >= 14
+    assert n_fast > 400 and n_packed > 300  # 8 or 16 outputs per thread: coverage >= 14
 
 
 def test_host_worker_pool_rethrows_a_task_exception_on_the_caller(emul):

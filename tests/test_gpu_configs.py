@@ -21,6 +21,7 @@ pytestmark = pytest.mark.gpu
 SWITCHES = {
     "default": {},
     "ballot_bp": {"WHMEC_TILE_PACKED_BP": "0"},
+    "mirror_off": {"WHMEC_TILE_MIRROR": "0"},
     "groups4": {"WHMEC_SOLVE_GROUPS": "4"},
     "pinned": {"WHMEC_PINNED_STAGING": "1"},
     "column": {"WHMEC_FORCE_COLUMN_KERNEL": "1"},
@@ -127,7 +128,7 @@ def test_golden_vectors_under_every_pedigree_switch(gpu, monkeypatch, switch):
         assert golden_io.check(lambda p: gpu.solve(p)[0], group) > 0
 
 
-@pytest.mark.parametrize("switch", ["default", "ballot_bp", "groups4"])
+@pytest.mark.parametrize("switch", ["default", "ballot_bp", "mirror_off", "groups4"])
 def test_fuzz_high_coverage_under_switches(gpu, checker, monkeypatch, switch):
     """Sliding windows and irregular spans at coverage 14-19 (long runs of steady-state columns, homozygous sites, gaps,
     tie-heavy and wide weights): the thread-packed and the ballot column code against the reference."""

@@ -35,6 +35,7 @@ struct TileSmem {
     int32_t TW[2][32];    // fast path, per warp: K2 + E(global bits of the tile) + weights of the warp's output bits
     int32_t T5[2][32];    // fast path, per lane: weights of output bits 0..4
     unsigned long long keys[NT];
+    unsigned long long keys2[NT];  // mirrored panels: keys of the mirror outputs (few-output columns)
     TileCol tcs[TC_CHUNK];
     Panel P;
     uint32_t cg[2];
@@ -82,6 +83,7 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
     const uint32_t wp = (uint32_t)tc.w_local[p];
     const uint32_t K0 = tc.K0, K12 = tc.K12, cg0 = cg & 1u;
     const uint32_t nout = 1u << tc.l_out;
+    const bool mirror = tc.half && tc.km != 0;
 #pragma unroll 4
     for (uint32_t o = tid; o < nout; o += NT) {
         const uint32_t hi = o >> p;
@@ -97,6 +99,12 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
         Sout[o] = min(v0, v1);
         const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, (pick1 ^ par) != 0);
         if ((tid & 31u) == 0) bpw[o >> 5] = ballot;
+        if (mirror) {  // the mirror output's winner: same comparison, tie-break parity par ^ km (tile_device.h)
+            const uint32_t q = par ^ 1u;
+            const uint32_t pickm = q ? (v1 <= v0) : (v1 < v0);
+            const uint32_t mballot = __ballot_sync(0xFFFFFFFFu, (pickm ^ q) != 0);
+            if ((tid & 31u) == 0) bpw[tc.bp_tile_words + (o >> 5)] = mballot;
+        }
     }
 }
 
@@ -104,8 +112,11 @@ __device__ __forceinline__ void column_drop1(const TileCol &tc, const int32_t *_
 // transaction, no divergence).
 struct BallotEmit {
     uint32_t *bp;
+    uint32_t section;  // words from the tile's own section to its mirror section (mirrored panels, tile_device.h)
     __device__ __forceinline__ void operator()(uint32_t word, bool bit) const { bp[word] = __ballot_sync(0xFFFFFFFFu, bit); }
+    __device__ __forceinline__ void mirror(uint32_t word, bool bit) const { bp[section + word] = __ballot_sync(0xFFFFFFFFu, bit); }
     __device__ __forceinline__ void store(uint32_t) const {}
+    __device__ __forceinline__ void store_mirror(uint32_t) const {}
 };
 
 // Thread-packed layout (TileCol::pad2 == 1, experimental): thread `tid` owns element `tid` of BITS bits; a warp's 32
@@ -114,10 +125,16 @@ template <int BITS>
 struct PackedEmit {
     uint32_t *bpw;  // the tile's slice of the arena
     uint32_t tid;
+    uint32_t section;
     __device__ __forceinline__ void operator()(uint32_t, bool) const {}
+    __device__ __forceinline__ void mirror(uint32_t, bool) const {}
     __device__ __forceinline__ void store(uint32_t bits) const {
         if (BITS == 8) reinterpret_cast<uint8_t *>(bpw)[tid] = (uint8_t)bits;
         else reinterpret_cast<uint16_t *>(bpw)[tid] = (uint16_t)bits;
+    }
+    __device__ __forceinline__ void store_mirror(uint32_t bits) const {
+        if (BITS == 8) reinterpret_cast<uint8_t *>(bpw + section)[tid] = (uint8_t)bits;
+        else reinterpret_cast<uint16_t *>(bpw + section)[tid] = (uint16_t)bits;
     }
 };
 
@@ -192,9 +209,17 @@ __device__ __forceinline__ void stage_tile_async(uint32_t *stage, const Panel *p
     const uint32_t told = ptile & low_mask(__ldg(&pp->in_gold));
     const uint32_t *src = state + __ldg(&pp->in_off) + ((uint64_t)told << jb);
     const uint32_t jmask = (1u << jb) - 1u;
+    // mirrored producer (Panel::half): its tiles with top tile-id bit 1 were not computed; their entries are the
+    // complemented index of the mirror tile (descending inside the chunk)
+    const uint32_t top = __ldg(&pp->in_half) ? (1u << (gA - 1)) : 0u;
+    const uint32_t amask = (1u << gA) - 1u, smask = (1u << sA) - 1u;
+    const uint32_t *base = state + __ldg(&pp->in_off);
+    const uint32_t chunk0 = told << jb;
     for (uint32_t e = threadIdx.x; e < nin; e += NT) {
         const uint32_t tA = e >> jb, ll = e & jmask;
-        cp_async4(&stage[stage_index(gA, jb, tA, ll)], src + ((uint64_t)tA << sA) + ll);
+        const uint32_t *from = (tA & top) ? base + ((uint64_t)(~tA & amask) << sA) + (~(chunk0 + ll) & smask)
+                                          : src + ((uint64_t)tA << sA) + ll;
+        cp_async4(&stage[stage_index(gA, jb, tA, ll)], from);
     }
     cp_async_commit();
 }
@@ -239,7 +264,12 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
         const uint32_t lo = pdep32(tid, P.lmask_in);
         const uint32_t himask = mask_without_low_bits(P.lmask_in, 10);
         const uint32_t *src = state + P.in_off;
-        for (uint32_t l = tid, it = 0; l < nin; l += NT, ++it) S.buf[0][l] = src[lo | pdep32(it, himask) | gpart];
+        const uint32_t top = P.in_half ? P.in_top : 0u, fmask_in = P.lmask_in | P.gmask_in;
+        for (uint32_t l = tid, it = 0; l < nin; l += NT, ++it) {
+            uint32_t e = lo | pdep32(it, himask) | gpart;
+            if (e & top) e = ~e & fmask_in;  // entry of an uncomputed tile of a mirrored producer
+            S.buf[0][l] = src[e];
+        }
     }
     __syncthreads();  // staging buffer free again
     // ---- prefetch the input of this CTA's next tile
@@ -296,14 +326,28 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
         } else {
             const uint32_t nout = 1u << tc.l_out;
             const uint32_t ncand = 1u << tc.d;
-            uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_words;
+            uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_stride;
+            const bool mirror = tc.half && tc.km != 0;  // the mirror outputs' back-pointers differ: second section
             if (fast_kind(tc)) {
+#define WHMEC_FAST_ARGS tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout
 #define WHMEC_FAST(LGV, SH)                                                                                      \
-    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid); \
-    else column_fast<LGV, true, SH>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, BallotEmit{bpw + (tid >> 5) * (1u << LGV)}, tid);
+    {                                                                                                            \
+        const BallotEmit em{bpw + (tid >> 5) * (1u << LGV), tc.bp_tile_words};                                   \
+        if (mirror) {                                                                                            \
+            if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH, false, true>(WHMEC_FAST_ARGS, em, tid);           \
+            else column_fast<LGV, true, SH, false, true>(WHMEC_FAST_ARGS, em, tid);                               \
+        } else if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH>(WHMEC_FAST_ARGS, em, tid);                     \
+        else column_fast<LGV, true, SH>(WHMEC_FAST_ARGS, em, tid);                                                \
+    }
 #define WHMEC_FAST_PACKED(LGV, SH, BITS)                                                                          \
-    if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH, true>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, PackedEmit<BITS>{bpw, tid}, tid); \
-    else column_fast<LGV, true, SH, true>(tc, S.TW[tb], S.T5[tb], S.cg[tb], S.buf[cur], Sout, PackedEmit<BITS>{bpw, tid}, tid);
+    {                                                                                                            \
+        const PackedEmit<BITS> em{bpw, tid, tc.bp_tile_words};                                                   \
+        if (mirror) {                                                                                            \
+            if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH, true, true>(WHMEC_FAST_ARGS, em, tid);            \
+            else column_fast<LGV, true, SH, true, true>(WHMEC_FAST_ARGS, em, tid);                                \
+        } else if (tc.K0 >= TILE_KINF) column_fast<LGV, false, SH, true>(WHMEC_FAST_ARGS, em, tid);               \
+        else column_fast<LGV, true, SH, true>(WHMEC_FAST_ARGS, em, tid);                                          \
+    }
                 if (tc.pad2 & 1u) {  // thread-packed back-pointer bits (planner: 8 or 16 outputs per thread only)
                     if (fast_kind(tc) == 2) {
                         if (tc.pad1 == 2) { WHMEC_FAST_PACKED(2, true, 8) } else { WHMEC_FAST_PACKED(3, true, 16) }
@@ -328,40 +372,51 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
                 }
 #undef WHMEC_FAST_PACKED
 #undef WHMEC_FAST
+#undef WHMEC_FAST_ARGS
             } else if (nout >= NT && tc.d == 1) {
                 column_drop1(tc, S.TL[tb], S.TH[tb], S.cg[tb], S.buf[cur], Sout, bpw, tid);
             } else if (nout >= NT && tc.d == 0) {
                 column_drop0(tc, S.TL[tb], S.TH[tb], S.buf[cur], Sout, tid);
             } else if (nout >= NT) {
                 for (uint32_t o = tid; o < nout; o += NT) {
-                    const unsigned long long key = tile_eval(c, o, 0, ncand);
+                    uint64_t mkey;
+                    const unsigned long long key = tile_eval(c, o, 0, ncand, &mkey);
                     Sout[o] = (uint32_t)(key >> 32);
                     bp_store_warp_tile(bpw, tc.bp_width, o, (uint32_t)key, true);
+                    if (mirror) bp_store_warp_tile(bpw + tc.bp_tile_words, tc.bp_width, o, (uint32_t)mkey, true);
                 }
             } else {
                 // few outputs: split every output's candidates over several threads
                 const uint32_t spare = 10u - tc.l_out;
                 const uint32_t log_chunks = spare < tc.d ? spare : tc.d;
                 const uint32_t items = nout << log_chunks;
-                if (tid < nout) S.keys[tid] = KEY_INF;
+                if (tid < nout) S.keys[tid] = S.keys2[tid] = KEY_INF;
                 __syncthreads();
-                unsigned long long key = KEY_INF;
+                unsigned long long key = KEY_INF, mkey = KEY_INF;
                 const uint32_t o = tid >> log_chunks;
                 if (tid < items) {
                     const uint32_t ch = tid & ((1u << log_chunks) - 1);
                     const uint32_t per = ncand >> log_chunks;
-                    key = tile_eval(c, o, ch * per, (ch + 1) * per);
+                    uint64_t mk;
+                    key = tile_eval(c, o, ch * per, (ch + 1) * per, &mk);
+                    mkey = mk;
                 }
                 if (log_chunks >= 5) {
                     key = warp_min_u64(key);
-                    if ((tid & 31) == 0 && tid < items) atomicMin(&S.keys[o], key);
+                    if (mirror) mkey = warp_min_u64(mkey);
+                    if ((tid & 31) == 0 && tid < items) {
+                        atomicMin(&S.keys[o], key);
+                        if (mirror) atomicMin(&S.keys2[o], mkey);
+                    }
                 } else if (tid < items) {
                     atomicMin(&S.keys[o], key);
+                    if (mirror) atomicMin(&S.keys2[o], mkey);
                 }
                 __syncthreads();
                 key = tid < nout ? S.keys[tid] : 0ull;
                 if (tid < nout) Sout[tid] = (uint32_t)(key >> 32);
                 bp_store_warp_tile(bpw, tc.bp_width, tid, (uint32_t)key, tid < nout);
+                if (mirror) bp_store_warp_tile(bpw + tc.bp_tile_words, tc.bp_width, tid, tid < nout ? (uint32_t)S.keys2[tid] : 0u, tid < nout);
             }
             cur ^= 1;
         }

@@ -56,9 +56,21 @@ WHMEC_HD uint32_t tile_cell_cost(const TileCtx &c, uint32_t x) {
     return m < c.tc->K0 ? m : c.tc->K0;
 }
 
+// Mirrored panels (Panel::half).  With one individual cost(x) == cost(~x) (~ = all reads of the column change sides), so
+// every projection is symmetric, S(f) == S(~f), and the tile that fixes the global reads to ~t is the mirror image of
+// tile t: only tiles with top tile-id bit 0 are computed.  The VALUES of the mirror tile are the same numbers; its
+// back-pointers are not, because the reference breaks ties by visiting order.  For output f the candidate with dropped-bit
+// pattern delta has rank r = inv_gray(delta ^ gray(c)), c_i = parity of the kept bits above the i-th dropped bit
+// (common.h: rank_offset).  The mirror output ~f has candidates ~x with patterns ~delta and parities c_i ^ NKA_i
+// (NKA_i = number of kept bits above the i-th dropped bit, mod 2), hence rank r' = r ^ km with the per-column constant
+//     km = inv_gray(ones_d) ^ NKA          (TileCol::km, planner).
+// The winner of ~f is therefore the candidate minimising (value, r ^ km): one more key per candidate.  km == 0: both
+// outputs store the same number.  Chain end: rank = inv_gray(canonical index), km = inv_gray(ones_a).
+
 // Regular column: best (value << 32 | r) over candidates r in [r0, r1) of local output entry o,
-// visited in the reference's Gray-rank order (common.h: rank_offset).
-WHMEC_HD uint64_t tile_eval(const TileCtx &c, uint32_t o, uint32_t r0, uint32_t r1) {
+// visited in the reference's Gray-rank order (common.h: rank_offset).  `mirror` (optional): best (value << 32 | r ^ km),
+// the key of the mirror output.
+WHMEC_HD uint64_t tile_eval(const TileCtx &c, uint32_t o, uint32_t r0, uint32_t r1, uint64_t *mirror = nullptr) {
     const TileCol &tc = *c.tc;
     const uint32_t m = tc.l_in + tc.n_new;
     const uint32_t keepmask = ~tc.dropmask & low_mask(m);
@@ -68,13 +80,17 @@ WHMEC_HD uint64_t tile_eval(const TileCtx &c, uint32_t o, uint32_t r0, uint32_t 
     const uint32_t cgray = cpar ^ (cpar >> 1);
     uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cgray, tc.dropmask);
     const uint32_t inmask = low_mask(tc.l_in);
-    uint64_t best = KEY_INF;
+    uint64_t best = KEY_INF, best2 = KEY_INF;
+    const uint32_t km = tc.km;
     for (uint32_t r = r0; r < r1; ++r) {
         const uint32_t val = tile_cell_cost(c, x) + c.Sin[x & inmask];
         const uint64_t key = ((uint64_t)val << 32) | r;
         if (key < best) best = key;
+        const uint64_t key2 = ((uint64_t)val << 32) | (r ^ km);
+        if (key2 < best2) best2 = key2;
         if (r + 1 < r1) x ^= 1u << tc.dpos[ctz32(r + 1)];
     }
+    if (mirror) *mirror = best2;
     return best;
 }
 
@@ -90,6 +106,10 @@ WHMEC_HD uint64_t tile_eval_end(const TileCtx &c, uint32_t gpart, uint32_t x0, u
         g ^= g >> 1; g ^= g >> 2; g ^= g >> 4; g ^= g >> 8; g ^= g >> 16;  // inverse Gray code = visiting rank
         const uint64_t key = ((uint64_t)val << 32) | g;
         if (key < best) best = key;
+        if (tc.half) {  // the same cell of the mirror tile: same value, visiting rank g ^ inv_gray(ones_a)
+            const uint64_t key2 = ((uint64_t)val << 32) | (g ^ tc.km);
+            if (key2 < best) best = key2;
+        }
     }
     return best;
 }
@@ -126,11 +146,17 @@ WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, co
         const ColMeta &pm = cols[k - 1];
         const TileCol &pt = tcols[k - 1];
         const uint32_t fmask = low_mask(pm.f);
-        const uint32_t tile = pext32(o, pt.gmask_out);
-        const uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
+        uint32_t tile = pext32(o, pt.gmask_out);
+        uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
+        uint64_t section = 0;
+        if (pt.half && ((tile >> (pt.g - 1)) & 1u)) {  // output of an uncomputed tile: stored by its mirror image
+            tile = ~tile & low_mask(pt.g);
+            lo = ~lo & low_mask(pt.l_out);
+            if (pt.km != 0) section = pt.bp_tile_words;
+        }
         uint32_t at = lo;
         if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);  // thread-packed bits
-        const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_words, pt.bp_width, at);
+        const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_stride + section, pt.bp_width, at);
         x = candidate_index(pm, o, bp);
         path_index[k - 1] = x;
     }

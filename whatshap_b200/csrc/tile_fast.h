@@ -62,7 +62,10 @@ WHMEC_HD uint32_t tile_shift_in_sign(uint32_t bits, uint32_t t) {
 // (the tile path's precondition) "candidate 1 wins" is the sign of v1 - v0 - par, and one funnel shift moves that sign
 // bit into the register — IADD3 + SHF per output instead of IADD + ISETP + VOTE + STG.  The outputs arrive in the order
 // (it = 0, twin of 0, it = 1, ...), so the first one ends up in the highest of the thread's bits (tile_packed_bit_index).
-template <int LG, bool HASK0, bool SHARE, bool PACKED = false, class Emit>
+// MIRROR (column of a mirrored panel with TileCol::km == 1, see tile_device.h): the back-pointer of the mirror output ~o,
+// which no tile computes, is the same comparison with the opposite tie-break parity: sign(v1 - v0 - !par) ^ !par.  It goes to
+// `emit.mirror(word, bit)` / `emit.store_mirror(bits)` (the second section of the tile's slice).
+template <int LG, bool HASK0, bool SHARE, bool PACKED = false, bool MIRROR = false, class Emit>
 WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
                           uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
     constexpr int IT = 1 << LG;
@@ -76,7 +79,7 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
     const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
     const uint32_t K0 = tc.K0, K12 = tc.K12;
     const uint32_t par0 = (WHMEC_POPC(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
-    uint32_t bits = 0;
+    uint32_t bits = 0, mbits = 0;
     uint32_t ue[IT];
     ue[0] = (uint32_t)(TW[warp] + T5[lane]);
 #pragma unroll
@@ -94,6 +97,11 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
             so[it * 32] = WHMEC_UMIN(v0, v1);
             if (PACKED) bits = tile_shift_in_sign(bits, v1 - v0 - par);  // sign set <=> pick1
             else emit((uint32_t)it, pick1 != (par != 0));
+            if (MIRROR) {
+                const uint32_t q = par ^ 1u;
+                if (PACKED) mbits = tile_shift_in_sign(mbits, v1 - v0 - q);
+                else emit.mirror((uint32_t)it, (v1 < v0 + q) != (q != 0));
+            }
         }
         if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
             const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
@@ -105,6 +113,11 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
             so[half + it * 32] = WHMEC_UMIN(v0, v1);
             if (PACKED) bits = tile_shift_in_sign(bits, v1 - v0 - parb);
             else emit((half >> 5) + (uint32_t)it, pick1 != (parb != 0));
+            if (MIRROR) {
+                const uint32_t q = parb ^ 1u;
+                if (PACKED) mbits = tile_shift_in_sign(mbits, v1 - v0 - q);
+                else emit.mirror((half >> 5) + (uint32_t)it, (v1 < v0 + q) != (q != 0));
+            }
         }
     }
     if (PACKED) {
@@ -118,6 +131,7 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
         }
         const uint32_t all = N >= 32 ? 0xFFFFFFFFu : ((1u << N) - 1u);
         emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
+        if (MIRROR) emit.store_mirror((mbits ^ cm ^ all ^ (par0 ? all : 0u)) & all);  // q = !par throughout
     }
 }
 

@@ -30,6 +30,8 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
     const char *packed_env = std::getenv("WHMEC_TILE_PACKED_BP");
     const bool packed_bp = !(packed_env && packed_env[0] == '0');  // default since round 2 (B200: 29.97 -> 25.42 ms on cfg3); "0" keeps the warp-ballot layout
+    const char *mirror_env = std::getenv("WHMEC_TILE_MIRROR");
+    const bool mirror_on = !(mirror_env && mirror_env[0] == '0');  // "0": every tile of every panel is computed (test hook)
     auto tnow = [] { return std::chrono::steady_clock::now(); };
     auto tms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     const auto t0 = tnow();
@@ -69,6 +71,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         // stamped tables: column position, position in the tile's local order, membership in L / G / Lold / Gold
         std::vector<uint32_t> col_stamp(nr, 0), cur_stamp(nr, 0), l_stamp(nr, 0), g_stamp(nr, 0), lold_stamp(nr, 0), gold_stamp(nr, 0);
         std::vector<uint8_t> col_pos(nr, 0), cur_pos(nr, 0);
+        std::vector<uint8_t> sym_ok(k1 - k0 + 1, 0);
         uint32_t tick = 0;     // one per visited column
         uint32_t attempt = 0;  // one per tried tile size
         // at least 4 words so that every chain's buffers stay 16-byte aligned (vector stores of whole tiles)
@@ -219,6 +222,27 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                         }
                         ++di;
                     }
+                    // mirror rank constant (tile_device.h): rank of the complemented candidate among the candidates of the
+                    // complemented output = rank ^ km,  km = inv_gray(ones_d) ^ NKA,  NKA bit i = parity of the KEPT bits
+                    // (local and global) canonically above the i-th dropped bit;  chain end: km = inv_gray(ones_a)
+                    {
+                        uint32_t km = 0;
+                        if (chain_end) {
+                            for (uint32_t i = 0; i < m.a; ++i) km |= ((m.a - i) & 1u) << i;
+                        } else {
+                            for (uint32_t i = 0; i < d && i < 16; ++i) {
+                                const uint32_t kept_above = (mm - 1 - tc.dpos[i]) - (d - 1 - i) + popc32(tc.gabove[i]);
+                                km |= ((kept_above ^ (d - i)) & 1u) << i;
+                            }
+                        }
+                        tc.km = km;
+                        // symmetry of the column cost under complementing every read
+                        int64_t etot = 0;
+                        for (uint32_t q = 0; q < mm; ++q) etot += tc.w_local[q];
+                        for (uint32_t b = 0; b < G.n; ++b) etot += tc.w_global[b];
+                        const bool both_inf = K1 >= TILE_KINF && K2 >= TILE_KINF;
+                        sym_ok[j - k0] = (both_inf || (K1 < TILE_KINF && K2 < TILE_KINF && (int64_t)K1 - (int64_t)K2 == etot)) ? 1 : 0;
+                    }
                     if (!chain_end) {
                         uint32_t gm = 0, rank = 0;
                         for (uint32_t keep = m.keep; keep; keep &= keep - 1, ++rank)
@@ -283,6 +307,11 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     }
                     chain_traffic[c] += 2ull * 4ull * ((uint64_t)1 << kept.n);
                 }
+                // Mirrored panel (Panel::half): needs cost(x) == cost(~x) in every column, i.e. K1 == K2 + (sum of all signed
+                // weights) or no heterozygous assignment at all -- always true for the reference's cost form; checked anyway.
+                bool half = mirror_on && G.n >= 1;
+                for (uint32_t q = k; q < j && half; ++q) half = sym_ok[q - k0] != 0;
+                P.half = half ? 1 : 0;
                 for (uint32_t q = k; q < j; ++q) {
                     TileCol &tc = ts.cols[q];
                     tc.bp_width = tc.kind == 1 ? 0 : round_bp_width(tc.d);
@@ -290,7 +319,11 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     // every tile's slice starts on a word boundary
                     uint64_t per_tile_words = ((((uint64_t)1 << tc.l_out) * tc.bp_width) + 31) / 32;
                     tc.bp_tile_words = (uint32_t)per_tile_words;
-                    bp_words += per_tile_words << tc.g;
+                    tc.half = half ? 1 : 0;
+                    if (!half) tc.km = 0;  // (computed per column below; only meaningful for mirrored panels)
+                    const uint32_t sections = (half && tc.km != 0 && tc.kind == 0) ? 2 : 1;
+                    tc.bp_tile_stride = (uint32_t)(per_tile_words * sections);
+                    bp_words += (per_tile_words * sections) << (tc.g - (half ? 1 : 0));
                 }
                 P.in_gold = Gold.n;
                 per_chain[c].push_back(P);
@@ -343,6 +376,9 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             Panel &A = per_chain[c][q], &B = per_chain[c][q + 1];
             const PanelSets &sa = per_chain_sets[c][q], &sb = per_chain_sets[c][q + 1];
             if (A.ends_chain) continue;
+            B.in_half = A.half;
+            B.in_top = 0;
+            for (uint32_t gmk = A.gmask_out; gmk; gmk &= gmk - 1) B.in_top = gmk & (0u - gmk);  // highest set bit = top global read
             if (!sa.G.empty() && !sa.Lout.empty() && sa.G.back() > sa.Lout.front()) continue;  // producer's global reads must be the oldest
             if (sb.Lold.size() < sa.G.size()) continue;
             const size_t j = sb.Lold.size() - sa.G.size();
@@ -367,7 +403,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             if (r < per_chain[c].size()) {
                 Panel P = per_chain[c][r];
                 P.tile_begin = tiles;
-                tiles += 1u << P.g;
+                tiles += 1u << (P.g - P.half);
                 ts.panels.push_back(P);
             }
         ts.round_tiles.push_back(tiles);

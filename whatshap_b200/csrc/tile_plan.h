@@ -41,6 +41,10 @@ struct TileCol {            // one column as seen by a tile (device + host)
     uint64_t bp_off;        // 32-bit words into the arena; tile t owns words [bp_off + t*bp_tile_words, +bp_tile_words)
     uint32_t bp_tile_words; // ceil(2^l_out * bp_width / 32)
     uint32_t pad2;          // fast columns: bit 0 = back-pointer bits packed per thread (tile_packed_bit_index), else warp-ballot order
+    uint32_t half;          // 1: column of a mirrored panel (only the tiles whose top tile-id bit is 0 are computed, see Panel::half)
+    uint32_t km;            // mirrored panels: rank of the mirror candidate = rank ^ km (d bits; chain end: a bits), see tile_device.h
+    uint32_t bp_tile_stride;  // words between the slices of consecutive tiles: bp_tile_words, or twice that when the mirror
+                            // outputs' back-pointers differ from the tile's own (half && km != 0): [own | mirror]
     uint32_t gmask_out;     // canonical mask (over f_k bits) of the global reads after this column
     uint32_t lmask_col;     // canonical mask (over a_k bits) of the local reads of this column
     int32_t w_local[16];    // signed weight of local bit q:  +phred if allele 0, -phred if allele 1
@@ -66,6 +70,14 @@ struct Panel {
     uint32_t in_layout, out_layout;
     uint32_t in_gA, in_j, in_sA;   // tile-major input: producer's global bits, chunk bits, producer's s_out
     uint32_t in_gold;              // number of consumer tile-id bits that come from the old state
+    // Complement symmetry (single individual): cost(x) = cost(~x) in every column, hence S(f) = S(~f) for every projection:
+    // tile t of a panel with g >= 1 global reads holds exactly the mirror image of tile ~t.  `half` = 1: only the 2^(g-1)
+    // tiles whose top tile-id bit (the youngest global read) is 0 are computed; a consumer that needs an entry of an
+    // uncomputed tile reads the complemented index of the mirror tile, the back-pointers of the mirror outputs are
+    // derived in the same pass (tile_device.h).
+    uint32_t half;
+    uint32_t in_half;              // the producer of the input state was a mirrored panel
+    uint32_t in_top;               // canonical layout: bit (over the input state's index) of the producer's top global read
     uint32_t pad;
     uint64_t in_off, out_off;      // 32-bit word offsets of the chain's state buffers
 };
