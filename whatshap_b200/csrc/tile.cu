@@ -27,9 +27,15 @@ constexpr int NT = 1024;  // threads per tile
 constexpr uint32_t TILE_ENTRIES = 1u << TILE_SMAX;
 
 constexpr uint32_t TC_CHUNK = 16;  // column descriptors staged in shared memory at a time
+constexpr uint32_t BULK_MAX_GA = 6;     // bulk-copy hand-off: at most 2^6 chunks ...
+constexpr uint32_t BULK_MIN_J = 5;      // ... of at least 2^5 entries (128 bytes)
+constexpr uint32_t BULK_SKEW = 4;       // words of skew between consecutive chunks in the staging buffer (keeps 16-byte alignment)
+constexpr uint32_t STAGE_PAD_WORDS = BULK_SKEW << BULK_MAX_GA;
 
 struct TileSmem {
     uint32_t buf[3][TILE_ENTRIES];  // [0],[1]: ping-pong projection; [2]: staging / prefetch of the next tile's input
+    uint32_t stage_pad[STAGE_PAD_WORDS];  // directly behind buf[2]: bulk-copied chunks are laid out with a 16-byte skew each
+    unsigned long long stage_bar;   // mbarrier of the bulk copies into the staging buffer
     int32_t TL[2][TILE_TL_SIZE];
     int32_t TH[2][TILE_TH_SIZE];
     int32_t TW[2][32];    // fast path, per warp: K2 + E(global bits of the tile) + weights of the warp's output bits
@@ -37,6 +43,9 @@ struct TileSmem {
     unsigned long long keys[NT];
     unsigned long long keys2[NT];  // mirrored panels: keys of the mirror outputs (few-output columns)
     TileCol tcs[TC_CHUNK];
+    int32_t TWs[TC_CHUNK][32];  // steady-state panels: the tables of every column of the panel, built once
+    int32_t T5s[TC_CHUNK][32];
+    uint32_t cgs[TC_CHUNK];
     Panel P;
     uint32_t cg[2];
     uint32_t a_col[TC_CHUNK];
@@ -201,6 +210,52 @@ __device__ __forceinline__ void cp_async4(uint32_t *smem_dst, const uint32_t *gs
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+
+// Tile-major hand-offs whose chunks are at least 128 bytes travel as one bulk copy per producer tile.
+__device__ __forceinline__ bool bulk_handoff(uint32_t gA, uint32_t jb) { return gA <= BULK_MAX_GA && jb >= BULK_MIN_J; }
+
+// Bulk version of stage_tile_async (called by warp 0 only): chunk tA lands at stage + tA * (2^j + BULK_SKEW), in the
+// producer's order -- ascending for a computed producer tile, for an uncomputed one (mirrored producer) the chunk of the
+// mirror tile, which holds the wanted entries in DESCENDING order (the reader flips the offset).
+__device__ __forceinline__ void stage_tile_bulk(uint32_t *stage, unsigned long long *bar, const Panel *pp, uint32_t ptile, const uint32_t *state) {
+    const uint32_t gA = __ldg(&pp->in_gA), jb = __ldg(&pp->in_j), sA = __ldg(&pp->in_sA);
+    const uint32_t told = ptile & low_mask(__ldg(&pp->in_gold));
+    const uint32_t top = __ldg(&pp->in_half) ? (1u << (gA - 1)) : 0u;
+    const uint32_t amask = (1u << gA) - 1u, tmask = (1u << (sA - jb)) - 1u;
+    const uint32_t *base = state + __ldg(&pp->in_off);
+    const uint32_t lane = threadIdx.x & 31u, bytes = 4u << jb;
+    if (lane == 0) mbar_expect_tx(bar, bytes << gA);
+    __syncwarp();
+    for (uint32_t tA = lane; tA <= amask; tA += 32) {
+        const uint32_t *from = (tA & top) ? base + ((uint64_t)(~tA & amask) << sA) + ((uint64_t)(~told & tmask) << jb)
+                                          : base + ((uint64_t)tA << sA) + ((uint64_t)told << jb);
+        bulk_copy_g2s(stage + tA * ((1u << jb) + BULK_SKEW), from, bytes, bar);
+    }
+}
+
 // Asynchronous gather of one tile's input (tile-major hand-off) into the staging buffer: one contiguous
 // 2^j chunk from each of the 2^gA producer tiles.  `pp` points to the panel in global memory.
 __device__ __forceinline__ void stage_tile_async(uint32_t *stage, const Panel *pp, uint32_t ptile, const uint32_t *state) {
@@ -225,7 +280,7 @@ __device__ __forceinline__ void stage_tile_async(uint32_t *stage, const Panel *p
 }
 
 __global__ void __launch_bounds__(NT, 1)
-tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t total_tiles, const TileCol *__restrict__ tcols,
+tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t total_tiles, int32_t tile_log, const TileCol *__restrict__ tcols,
                   const ColMeta *__restrict__ cols, uint32_t *__restrict__ state, uint32_t *__restrict__ arena,
                   unsigned long long *__restrict__ chain_keys) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -235,9 +290,13 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     // Persistent CTAs: each walks the launch's tiles with stride gridDim.x and, while it sweeps one
     // tile's panel, the input of its next tile is already streaming into the third buffer (cp.async).
     uint32_t pi = 0;            // panel of the current work item; panels[] is sorted by tile_begin
-    bool staged = false;        // the staging buffer holds (or is receiving) the current tile's input
+    uint32_t staged = 0;        // the staging buffer holds (or is receiving) the current tile's input: 1 = cp.async, 2 = bulk copies
+    uint32_t bar_phase = 0;     // parity of the staging mbarrier's current phase
+    if (tid == 0) mbar_init(&S.stage_bar, 1);
+    __syncthreads();
     for (uint32_t work = blockIdx.x; work < total_tiles; work += gridDim.x) {
-    while (pi + 1 < n_panels && __ldg(&panels[pi + 1].tile_begin) <= work) ++pi;
+    if (tile_log >= 0) pi = work >> tile_log;  // every panel of this launch has 2^tile_log tiles
+    else while (pi + 1 < n_panels && __ldg(&panels[pi + 1].tile_begin) <= work) ++pi;
     __syncthreads();  // previous work item completely done (its stores read the buffers, S.P is reused)
     if (tid < sizeof(Panel) / 4) ((uint32_t *)&S.P)[tid] = ((const uint32_t *)&panels[pi])[tid];
     __syncthreads();
@@ -248,10 +307,41 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     // ---- the tile's slice of the incoming projection column
     if (P.fresh) {
         if (tid == 0) S.buf[0][0] = 0;
-    } else if (P.in_layout == 1) {
-        // tile-major hand-off: gathered into the staging buffer (XOR-swizzled so that both passes are
-        // bank-conflict free), then transposed into the canonical local order
+    } else if (P.in_layout == 1 && bulk_handoff(P.in_gA, P.in_j)) {
+        // tile-major hand-off, one bulk copy per producer tile (issued by warp 0, normally already while the previous tile
+        // was swept); every thread waits on the mbarrier, then the chunks are transposed into the canonical local order
         //   index = (chunk offset << gA) | producer tile.
+        if (!staged && tid < 32) stage_tile_bulk(S.buf[2], &S.stage_bar, &panels[pi], tile, state);
+        mbar_wait(&S.stage_bar, bar_phase);
+        bar_phase ^= 1u;
+        const uint32_t gA = P.in_gA, jb = P.in_j, nin = 1u << P.s_in;
+        const uint32_t cs = (1u << jb) + BULK_SKEW, jmask = (1u << jb) - 1u;
+        const uint32_t top = P.in_half ? (1u << (gA - 1)) : 0u;  // chunks of uncomputed producer tiles arrive reversed
+        const uint32_t *stage = S.buf[2];
+        if (gA >= 5) {
+            // a warp moves 32 producer tiles x 4 offsets per step; lane L takes offset (L / 8 + r) % 4 in rotation r, so that
+            // the 32 reads (chunk stride = 4 banks) and the 32 writes (consecutive words) of a rotation hit 32 different banks
+            const uint32_t lane = tid & 31u, warp = tid >> 5;
+            for (uint32_t blk = warp; blk < (nin >> 7); blk += NT / 32) {
+                const uint32_t tA = ((blk & ((1u << (gA - 5)) - 1u)) << 5) + lane;
+                const uint32_t ll0 = (blk >> (gA - 5)) << 2;
+                const uint32_t *row = stage + tA * cs;
+#pragma unroll
+                for (uint32_t r = 0; r < 4; ++r) {
+                    const uint32_t ll = ll0 + (((lane >> 3) + r) & 3u);
+                    S.buf[0][(ll << gA) | tA] = row[(tA & top) ? (jmask - ll) : ll];
+                }
+            }
+        } else {
+            const uint32_t amask = (1u << gA) - 1u;
+            for (uint32_t i = tid; i < nin; i += NT) {
+                const uint32_t tA = i & amask, ll = i >> gA;
+                S.buf[0][i] = stage[tA * cs + ((tA & top) ? (jmask - ll) : ll)];
+            }
+        }
+    } else if (P.in_layout == 1) {
+        // tile-major hand-off with small chunks: gathered element by element into the staging buffer (XOR-swizzled so that
+        // both passes are bank-conflict free), then transposed into the canonical local order
         if (!staged) stage_tile_async(S.buf[2], &panels[pi], tile, state);
         cp_async_wait_all();
         __syncthreads();
@@ -273,19 +363,63 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     }
     __syncthreads();  // staging buffer free again
     // ---- prefetch the input of this CTA's next tile
-    staged = false;
+    staged = 0;
     {
         const uint32_t nwork = work + gridDim.x;
         if (nwork < total_tiles) {
             uint32_t pn = pi;
-            while (pn + 1 < n_panels && __ldg(&panels[pn + 1].tile_begin) <= nwork) ++pn;
+            if (tile_log >= 0) pn = nwork >> tile_log;
+            else while (pn + 1 < n_panels && __ldg(&panels[pn + 1].tile_begin) <= nwork) ++pn;
             if (__ldg(&panels[pn].in_layout) == 1 && !__ldg(&panels[pn].fresh)) {
-                stage_tile_async(S.buf[2], &panels[pn], nwork - __ldg(&panels[pn].tile_begin), state);
-                staged = true;
+                const uint32_t ntile = nwork - __ldg(&panels[pn].tile_begin);
+                if (bulk_handoff(__ldg(&panels[pn].in_gA), __ldg(&panels[pn].in_j))) {
+                    if (tid < 32) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads of the buffer above -> async writes
+                        stage_tile_bulk(S.buf[2], &S.stage_bar, &panels[pn], ntile, state);
+                    }
+                    staged = 2;
+                } else {
+                    stage_tile_async(S.buf[2], &panels[pn], ntile, state);
+                    staged = 1;
+                }
             }
         }
     }
 
+    if (P.steady) {
+        // ---- steady-state panel: every column is the twin fast column of one tile size.  Descriptors and ALL tables of
+        // the panel are built once, in parallel (thread (column, entry)); then one barrier and one call per column.
+        const uint32_t kb = P.col_begin, ncol = P.col_end - kb;
+        {
+            constexpr uint32_t WORDS = sizeof(TileCol) / 4;
+            for (uint32_t w = tid; w < ncol * WORDS; w += NT) ((uint32_t *)S.tcs)[w] = ((const uint32_t *)(tcols + kb))[w];
+        }
+        __syncthreads();
+        {
+            const uint32_t j = tid >> 6, idx = tid & 63u;
+            if (j < ncol) {
+                if (idx < 32) S.TWs[j][idx] = tile_fast_warp_entry(S.tcs[j], tile, idx);
+                else S.T5s[j][idx - 32] = tile_fast_lane_entry(S.tcs[j], idx - 32);
+                if (idx == 63) S.cgs[j] = tile_cg(S.tcs[j], tile);
+            }
+        }
+        const bool mirror = S.tcs[0].half && S.tcs[0].km != 0;
+        const uint32_t lg = P.steady - 1u;
+        for (uint32_t j = 0; j < ncol; ++j) {
+            __syncthreads();  // tables ready (j == 0); column j - 1 complete
+            const TileCol &tc = S.tcs[j];
+            uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_stride;
+#define WHMEC_STEADY(LGV, BITS, MR) \
+    column_fast<LGV, false, true, true, MR>(tc, S.TWs[j], S.T5s[j], S.cgs[j], S.buf[cur], S.buf[cur ^ 1], PackedEmit<BITS>{bpw, tid, tc.bp_tile_words}, tid)
+            if (lg == 3) {
+                if (mirror) WHMEC_STEADY(3, 16, true); else WHMEC_STEADY(3, 16, false);
+            } else {
+                if (mirror) WHMEC_STEADY(2, 8, true); else WHMEC_STEADY(2, 8, false);
+            }
+#undef WHMEC_STEADY
+            cur ^= 1;
+        }
+    } else
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
         const uint32_t j = (k - P.col_begin) % TC_CHUNK;
         if (j == 0) {
@@ -615,7 +749,7 @@ int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
     for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r) {
         const uint32_t p0 = ts.round_begin[r], p1 = ts.round_begin[r + 1];
         const uint32_t grid = std::min<uint32_t>(ts.round_tiles[r], I->n_sm);
-        tile_panel_kernel<<<grid, NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, ts.round_tiles[r], I->d_tcols, I->d_cols,
+        tile_panel_kernel<<<grid, NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, ts.round_tiles[r], ts.round_tile_log[r], I->d_tcols, I->d_cols,
                                                                                 I->d_state, I->d_arena, I->d_chain_keys);
         ++launches;
     }

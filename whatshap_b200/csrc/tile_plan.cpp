@@ -326,6 +326,16 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     bp_words += (per_tile_words * sections) << (tc.g - (half ? 1 : 0));
                 }
                 P.in_gold = Gold.n;
+                {  // steady-state panel?
+                    const TileCol &t0 = ts.cols[k];
+                    bool steady = !ends_chain && j - k <= 16 && t0.pad0 == 2 && (t0.pad2 & 1u) && (t0.pad1 == 2 || t0.pad1 == 3);
+                    for (uint32_t q = k; q < j && steady; ++q) {
+                        const TileCol &tc = ts.cols[q];
+                        steady = tc.kind == 0 && tc.pad0 == 2 && tc.pad1 == t0.pad1 && (tc.pad2 & 1u) && tc.K0 >= TILE_KINF &&
+                                 tc.l_in == t0.l_in && tc.l_out == t0.l_out && (tc.half && tc.km != 0) == (t0.half && t0.km != 0);
+                    }
+                    P.steady = steady ? 1u + t0.pad1 : 0u;
+                }
                 per_chain[c].push_back(P);
                 per_chain_sets[c].push_back(PanelSets{G.vec(), Lcur.vec(), Lold.vec(), Gold.vec()});
                 ++pcount;
@@ -407,6 +417,13 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                 ts.panels.push_back(P);
             }
         ts.round_tiles.push_back(tiles);
+        int32_t tlog = -1;
+        for (uint32_t q = ts.round_begin.back(); q < ts.panels.size(); ++q) {
+            const int32_t mine = (int32_t)(ts.panels[q].g - ts.panels[q].half);
+            tlog = (q == ts.round_begin.back() || tlog == mine) ? mine : -2;
+            if (tlog == -2) break;
+        }
+        ts.round_tile_log.push_back(tlog < 0 ? -1 : tlog);
     }
     ts.round_begin.push_back((uint32_t)ts.panels.size());
     ts.state_words = state_words;

@@ -78,7 +78,11 @@ struct Panel {
     uint32_t half;
     uint32_t in_half;              // the producer of the input state was a mirrored panel
     uint32_t in_top;               // canonical layout: bit (over the input state's index) of the producer's top global read
-    uint32_t pad;
+    // Steady-state panel (the bulk of a coverage-capped ReadSet): at most 16 columns, in every one exactly one read ends
+    // (local bit 0) and one starts, the tile keeps 2^13 or 2^14 entries, no homozygous assignment, thread-packed
+    // back-pointers, one mirror mode.  The kernel sweeps such a panel with all per-column tables built once, in
+    // parallel, and no per-column dispatch.  steady = 1 + LG (2^LG twin pairs per thread), 0 otherwise.
+    uint32_t steady;
     uint64_t in_off, out_off;      // 32-bit word offsets of the chain's state buffers
 };
 
@@ -89,6 +93,7 @@ struct TileSchedule {
     std::vector<Panel> panels;            // grouped by launch round
     std::vector<uint32_t> round_begin;    // panels of round r: [round_begin[r], round_begin[r+1])
     std::vector<uint32_t> round_tiles;    // CTAs per round
+    std::vector<int32_t> round_tile_log;  // log2 tiles per panel if every panel of the round has the same number, else -1
     uint64_t state_words = 0;             // total size of the per-chain state double buffers
     uint64_t bp_words = 0;
     uint64_t state_traffic_bytes = 0;     // bytes of state written + read through global memory
