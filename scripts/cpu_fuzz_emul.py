@@ -3,6 +3,7 @@ incl. the steady-state column `column_fast`) against the compiled reference (ora
     python scripts/cpu_fuzz_emul.py <seed> <seconds>          # six pedigree shapes + single individuals, coverage <= 12
     python scripts/cpu_fuzz_emul.py <seed> <seconds> fast     # single individuals, coverage 11-15: every tile runs column_fast
     python scripts/cpu_fuzz_emul.py <seed> <seconds> mirror   # single individuals, coverage 15-19: mirrored multi-tile panels
+    python scripts/cpu_fuzz_emul.py <seed> <seconds> fused    # trios through the fused pedigree sweep (csrc/ped_fused.h)
 Set WHMEC_TILE_PACKED_BP=1 to fuzz the thread-packed back-pointer layout."""
 import ctypes as C
 import os
@@ -40,7 +41,48 @@ def run(lib, prob, tile, chunk):
     return sol
 
 
+def run_fused(prob):
+    lib = libs["libwhemul.so"]
+    lib.whemul_ped_fused_solve.argtypes = [C.POINTER(CProblem), C.POINTER(CSolution), C.c_char_p, C.c_size_t]
+    sol = FlatSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+    cp, cs, err = prob.as_c(), sol.as_c(), C.create_string_buffer(512)
+    rc = lib.whemul_ped_fused_solve(C.byref(cp), C.byref(cs), err, 512)
+    if rc == 100:
+        return None
+    raise_for(rc, err.value.decode())
+    sol.cost = int(cs.cost)
+    return sol
+
+
 seed, budget = int(sys.argv[1]), float(sys.argv[2])
+if len(sys.argv) > 3 and sys.argv[3] == "fused":  # trios through the fused sweep's per-item code (csrc/ped_fused.h)
+    rng = np.random.default_rng(seed)
+    ref = checker.reference()
+    t0 = time.time()
+    n = done = 0
+    while time.time() - t0 < budget:
+        prob = synth.random_problem(rng, int(rng.integers(1, 60)), int(rng.integers(1, 7)), ["trio", "trio_child_first"][n % 2], distrust=False,
+                                    gap=float(rng.random() * 0.3), mean_len=float(rng.uniform(1.5, 12)), burst=int(rng.integers(2, 6)),
+                                    conflict_free=bool(rng.integers(0, 5)), max_phred=int(rng.choice([1, 5, 40])))
+        if n % 7 == 0:
+            prob.recombcost = rng.integers(0, 60, prob.n_cols).astype(np.uint32)
+        n += 1
+        try:
+            want, werr = ref.solve(prob), ""
+        except RuntimeError as e:
+            want, werr = None, str(e)
+        try:
+            got, gerr = run_fused(prob), ""
+        except RuntimeError as e:
+            got, gerr = None, str(e)
+        if got is None and not gerr:
+            continue
+        assert gerr == werr, (seed, n, gerr, werr)
+        if want is not None:
+            assert got.same_as(want), (seed, n, got.diff(want))
+        done += 1
+    print("seed", seed, "trios", n, "through the fused sweep", done, "OK")
+    sys.exit(0)
 fast_mode = len(sys.argv) > 3 and sys.argv[3] in ("fast", "mirror")
 mirror_mode = len(sys.argv) > 3 and sys.argv[3] == "mirror"  # coverage 15-19: several tiles per panel, mirrored panels, both parities of km
 rng = np.random.default_rng(seed)

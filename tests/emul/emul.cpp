@@ -15,6 +15,8 @@
 #include "../../whatshap_b200/csrc/hostpool.h"
 #include "../../whatshap_b200/csrc/pack.h"
 #include "../../whatshap_b200/csrc/dp_device.h"
+#include "../../whatshap_b200/csrc/ped_fused.h"
+#include <memory>
 
 using namespace whmec;
 
@@ -269,92 +271,106 @@ extern "C" int whemul_segment_finish(whemul_segment *sg, int entry, whmec_soluti
     return WHMEC_OK;
 }
 
-// ---- host mirror of ped_chain_kernel (csrc/whmec.cu, WHMEC_PED_CHAIN): the same phases in the same order, every
-// ---- phase run for all 1024 "threads" one after the other; checks the scheme (lanes per entry, merge of partial
-// ---- keys, buffers R / M / A, unit instances + prefix + true instances), not the CUDA glue itself
+// ---- host mirror of ped_fused_kernel (csrc/whmec.cu): the same phases in the same order, every phase run item by item
+// ---- with the per-item code of ped_fused.h; checks the scheme (slots, tables, lanes per entry, merge of partial keys,
+// ---- buffers M / R / A, one unit row per chain + symmetry + prefix + true inputs), not the CUDA glue itself
 namespace {
-constexpr uint32_t CHAIN_THREADS = 1024;
 
-void chain_instance(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool write_bp, std::vector<uint32_t> &arena, uint32_t *out_vec) {
-    const uint32_t T = pk.T, tb = pk.tb;
+void fused_chain(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool unit, std::vector<uint32_t> &arena, uint32_t *out_vec) {
     const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1];
-    uint64_t max_ent = 1;
-    for (uint32_t k = k0; k < k1; ++k) max_ent = std::max<uint64_t>(max_ent, ((uint64_t)1 << pk.cols[k].f) * T);
-    std::vector<uint32_t> R(max_ent), M(max_ent), invec(in_vec, in_vec + T);
-    std::vector<uint8_t> A(max_ent);
-    std::vector<uint64_t> skeys(CHAIN_THREADS);
-    bool have_m = false;
+    const uint32_t max_ent = PF_T << PF_MAX_F;
+    std::vector<uint32_t> M(max_ent, 0xDEADBEEF), R(max_ent, 0xDEADBEEF);
+    std::vector<uint8_t> A(max_ent, 0xEE);
+    std::vector<uint64_t> keys(max_ent);
+    auto Cp = std::make_unique<PedFusedCol>();
+    PedFusedCol &C = *Cp;
     for (uint32_t k = k0; k < k1; ++k) {
-        const ColMeta &m = pk.cols[k];
-        const uint32_t d = m.d, nent = (1u << m.f) * T;
-        uint32_t lc = 0;
-        while ((nent << lc) < CHAIN_THREADS && lc < d) ++lc;
-        const uint32_t total = nent << lc, per = 1u << (d - lc);
-        if (lc) std::fill(skeys.begin(), skeys.begin() + nent, KEY_INF);
-        const uint32_t *prev = have_m ? M.data() : invec.data();
-        for (uint32_t base = 0; base < total; base += CHAIN_THREADS)
-            for (uint32_t tid = 0; tid < CHAIN_THREADS; ++tid) {
-                const uint32_t g = base + tid, e = g >> lc, chunk = g & ((1u << lc) - 1u);
-                if (g >= total) continue;
-                ColView v;
-                const uint32_t i = e & (T - 1), o = e >> tb;
-                const uint32_t g0 = pk.fn_group[m.grp_off + i], g1 = pk.fn_group[m.grp_off + i + 1];
-                v.m = &m; v.T = T; v.tb = tb;
-                v.fn_c0 = pk.fn_c0.data() + m.fn_off + g0;
-                v.fn_delta = pk.fn_delta.data() + (size_t)(m.fn_off + g0) * FN_STRIDE;
-                v.nf = g1 - g0;
-                v.prev = prev;
-                v.tab = nullptr; v.tab_fn0 = g0;
-                v.prevm = have_m ? M.data() : nullptr;
-                v.prevarg = have_m ? A.data() : nullptr;
-                const uint64_t key = eval_candidates(v, o, i, chunk * per, (chunk + 1) * per);
+        C.m = pk.cols[k];
+        const ColMeta &m = C.m;
+        for (uint32_t s = 0; s < PF_SLOTS; ++s) pf_stage_slot(C, s, pk.fn_c0.data(), pk.fn_delta.data(), pk.fn_group.data() + m.grp_off);
+        C.drop = ~m.keep & low_mask(m.a);
+        C.rc_next = k + 1 < k1 ? pk.cols[k + 1].rc : 0u;
+        for (uint32_t v = 0; v < 2 * TAB_SIZE; ++v) pf_stage_pdep(C, v);
+        if (k == k0) {
+            uint32_t invec[PF_T];
+            for (uint32_t j = 0; j < PF_T; ++j) invec[j] = unit ? (j == 0 ? 0u : UMAX) : in_vec[j];
+            pf_first_row(m, invec, M.data(), A.data());
+        }
+        for (uint32_t run = 0; run < PF_SLOTS * 32; ++run) pf_stage_table_run(C, run);
+        const uint32_t f = m.f, d = m.d, nout = 1u << f, nent = nout * PF_T;
+        const uint32_t lc = pf_lane_bits(f, d), per = 1u << (d - lc), items = nout << lc;
+        if (lc) std::fill(keys.begin(), keys.begin() + nent, KEY_INF);
+        for (uint32_t item = 0; item < items; ++item) {
+            const uint32_t o = item & (nout - 1u), chunk = item >> f;
+            PedQuad q;
+            pf_walk(C, M.data(), o, chunk * per, (chunk + 1) * per, q);
+            for (uint32_t t = 0; t < PF_T; ++t) {
                 if (lc) {
-                    skeys[e] = std::min(skeys[e], key);
+                    keys[o * PF_T + t] = std::min(keys[o * PF_T + t], ((uint64_t)q.val[t] << 32) | q.r[t]);
                 } else {
-                    R[e] = (uint32_t)(key >> 32);
-                    if (write_bp) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e, (uint32_t)key & low_mask(d + tb));
+                    R[o * PF_T + t] = q.val[t];
+                    if (!unit) bp_store_serial(arena.data(), m.bp_off, m.bp_width, (uint64_t)o * PF_T + t,
+                                               pf_backpointer(C, A.data(), o, t, q.val[t], q.r[t]) & low_mask(d + 2));
                 }
             }
+        }
         if (lc)
             for (uint32_t e = 0; e < nent; ++e) {
-                R[e] = (uint32_t)(skeys[e] >> 32);
-                if (write_bp) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e, (uint32_t)skeys[e] & low_mask(d + tb));
+                R[e] = (uint32_t)(keys[e] >> 32);
+                if (!unit) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e,
+                                           pf_backpointer(C, A.data(), e >> 2, e & 3u, R[e], (uint32_t)keys[e]) & low_mask(d + 2));
             }
-        if (k + 1 < k1) {
-            for (uint32_t e = 0; e < nent; ++e) {
-                uint32_t arg;
-                M[e] = transition_min(&R[e & ~(T - 1)], T, e & (T - 1), pk.cols[k + 1].rc, &arg);
-                A[e] = (uint8_t)arg;
+        if (k + 1 < k1)
+            for (uint32_t o = 0; o < nout; ++o) {
+                uint32_t row[PF_T], mv[PF_T], arg[PF_T];
+                for (uint32_t j = 0; j < PF_T; ++j) row[j] = R[o * PF_T + j];
+                for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(row, i, C.rc_next, &arg[i]);
+                for (uint32_t i = 0; i < PF_T; ++i) {
+                    M[o * PF_T + i] = mv[i];
+                    A[o * PF_T + i] = (uint8_t)arg[i];
+                }
             }
-            have_m = true;
-        }
     }
-    std::memcpy(out_vec, R.data(), (size_t)T * 4);
+    for (uint32_t t = 0; t < PF_T; ++t) out_vec[t] = R[t] < PF_INF ? R[t] : UMAX;
 }
 }  // namespace
 
-extern "C" int whemul_ped_chain_solve(const whmec_problem *p, whmec_solution *s, char *err, size_t errlen) {
+// returns 100 when the problem is outside the fused path's shape
+extern "C" int whemul_ped_fused_solve(const whmec_problem *p, whmec_solution *s, char *err, size_t errlen) {
     Packed pk;
     std::string msg;
     int rc = pack_problem(p, pk, msg);
     if (rc != WHMEC_OK) return fail_with(msg, err, errlen, rc);
     const uint32_t n = pk.n, T = pk.T;
-    if (n == 0 || T == 1 || !pk.safe31) return fail_with("not a pedigree problem for the chain kernel", err, errlen, 100);
-    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
-    std::vector<uint32_t> arena(pk.bp_words + 1, 0), matrices((size_t)C * T * T), in_vecs((size_t)C * T, 0), out_vecs((size_t)C * T);
-    if (C > 1) {
-        for (uint32_t c = 0; c < C; ++c)
-            for (uint32_t u = 0; u < T; ++u) {
-                std::vector<uint32_t> unit(T, UMAX);
-                unit[u] = 0;
-                chain_instance(pk, c, unit.data(), false, arena, &matrices[((size_t)c * T + u) * T]);
-            }
-        uint32_t in[MAX_T];
-        for (uint32_t i = 0; i < T; ++i) in[i] = matrices[i];
-        fold_chains(T, 1, C, in, [&](uint32_t c, uint32_t u) { return &matrices[((size_t)c * T + u) * T]; },
-                    [&](uint32_t c, const uint32_t *cur) { std::memcpy(&in_vecs[(size_t)c * T], cur, (size_t)T * 4); });
+    if (n == 0 || T != PF_T || !pk.safe31) return fail_with("not a problem for the fused pedigree sweep", err, errlen, 100);
+    for (uint32_t k = 0; k < n; ++k)
+        if (!pf_column_ok(pk.cols[k], pk.fn_group.data() + pk.cols[k].grp_off)) return fail_with("column outside the fused shape", err, errlen, 100);
+    {   // the symmetry group of a trio is all of Z_2^2
+        uint32_t masks[PF_T];
+        if (pf_symmetry_group(p->n_ind, p->n_trios, p->trios, masks) != PF_T) return fail_with("unexpected symmetry group", err, errlen, 101);
     }
-    for (uint32_t c = 0; c < C; ++c) chain_instance(pk, c, &in_vecs[(size_t)c * T], true, arena, &out_vecs[(size_t)c * T]);
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+    std::vector<uint32_t> arena(pk.bp_words + 1, 0), rows((size_t)C * T), in_vecs((size_t)C * T, 0), out_vecs((size_t)C * T);
+    for (uint32_t c = 0; c < C; ++c) fused_chain(pk, c, nullptr, true, arena, &rows[(size_t)c * T]);
+    {   // ped_fused_prefix_kernel
+        uint32_t in[PF_T], out[PF_T];
+        for (uint32_t i = 0; i < T; ++i) in[i] = rows[i];
+        for (uint32_t c = 1; c < C; ++c) {
+            for (uint32_t i = 0; i < T; ++i) {
+                in_vecs[(size_t)c * T + i] = in[i];
+                out[i] = UMAX;
+            }
+            for (uint32_t u = 0; u < T; ++u) {
+                if (in[u] == UMAX) continue;
+                for (uint32_t i = 0; i < T; ++i) {
+                    const uint32_t mv = rows[(size_t)c * T + (i ^ u)];
+                    if (mv != UMAX && in[u] + mv < out[i]) out[i] = in[u] + mv;
+                }
+            }
+            for (uint32_t i = 0; i < T; ++i) in[i] = out[i];
+        }
+    }
+    for (uint32_t c = 0; c < C; ++c) fused_chain(pk, c, &in_vecs[(size_t)c * T], false, arena, &out_vecs[(size_t)c * T]);
     std::vector<uint32_t> pidx(n), ptv(n);
     BtView bv{pk.cols.data(), arena.data(), T, pk.tb};
     uint32_t cost, x, tv, ptvv;

@@ -28,8 +28,7 @@ SWITCHES = {
 }
 PED_SWITCHES = {
     "default": {},
-    "ped_chain": {"WHMEC_PED_CHAIN": "1"},
-    "ped_batched": {"WHMEC_PED_CHAIN": "0"},
+    "ped_batched": {"WHMEC_PED_FUSED": "0"},
     "ped_sequential": {"WHMEC_PED_SEQUENTIAL": "1"},
 }
 ALL_ENV = sorted({k for d in list(SWITCHES.values()) + list(PED_SWITCHES.values()) for k in d})
@@ -97,6 +96,8 @@ def test_trio_shapes(gpu, checker, monkeypatch, key, switch):
     set_switch(monkeypatch, PED_SWITCHES[switch])
     stats = check(gpu, checker, key, TRIO[key])
     assert stats["path_kind"] == (2 if switch == "ped_sequential" else 3), stats
+    if switch == "default":
+        assert stats["kernel_launches"] == 3, stats  # the fused trio sweep: unit pass, prefix, true pass
 
 
 @pytest.mark.parametrize("segments", [2, 3])

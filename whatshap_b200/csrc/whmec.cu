@@ -24,6 +24,7 @@
 #include "../../include/whmec.h"
 #include "common.h"
 #include "dp_device.h"
+#include "ped_fused.h"
 #include "grouped.h"
 #include "pack.h"
 #include "tile.cuh"
@@ -376,108 +377,157 @@ __global__ void __launch_bounds__(256) col_multi_kernel(const PedStep *__restric
 }
 
 // ------------------------------------------------------------------------------------------
-// Fused pedigree sweep, one thread block per chain (EXPERIMENTAL, WHMEC_PED_CHAIN=1).
-// The batched sweep above issues one launch per column step and keeps the projection in global memory; at
-// pedigree sizes (cfg5: 16 K entries per column) that is bound by launch latency and by every block
-// re-staging the column.  Here a block of 1024 threads owns one (chain, input) instance and walks all its
-// columns: the projection (raw values R, transition minima M + their argmins A) lives in shared memory,
-// the column is staged once, only back-pointers and the chain's final T values go to HBM.  Same per-entry
-// code (eval_candidates, transition_min) and same back-pointer layout as the other column kernels, so the
-// backtrace kernels are unchanged.
-//   unit == 1: instance (chain c, unit vector u) = block c*T + u, values only, row u of the chain's transfer
-//              matrix -> out_vecs[(c*T + u)*T ..];   unit == 0: block c, true input in_vecs[c*T ..], back-pointers.
+// Fused pedigree sweep for one trio (T == 4): one thread block per DP-independent chain walks ALL columns of its chain
+// with the projection (transition minima M + argmins A of the previous column, raw values R of the current one) in
+// shared memory; the per-item code is ped_fused.h.  Pass 1 sweeps every chain once with the unit input e_0 (values only)
+// -- by the symmetry of ped_fused.h that single row determines the chain's whole transfer matrix, Mat[u][i] = row[i ^ u];
+// a one-thread prefix folds the matrices into every chain's true input; pass 2 sweeps every chain with its true input and
+// writes exactly the back-pointers of the column-by-column sweep.  Three launches for the whole table.
 // ------------------------------------------------------------------------------------------
-struct PedChainArgs {
+struct PedFusedArgs {
     const ColMeta *cols;
     const uint32_t *chain_begin, *fn_c0, *fn_group;
     const int32_t *fn_delta;
     uint32_t *arena;
-    const uint32_t *in_vecs;
-    uint32_t *out_vecs;
-    uint32_t T, tb, max_ent, unit;
+    const uint32_t *in_vecs;  // [chains][4] true inputs (pass 2)
+    uint32_t *out_vecs;       // [chains][4]: pass 1: row 0 of the chain's transfer matrix; pass 2: the chain's true output
+    uint32_t unit;            // 1: pass 1 (input e_0, values only), 0: pass 2
 };
 
-constexpr uint32_t PED_CHAIN_THREADS = 1024;
+constexpr uint32_t PF_MAX_ENT = PF_T << PF_MAX_F;
+constexpr size_t PF_COL_BYTES = (sizeof(PedFusedCol) + 15) & ~(size_t)15;
+constexpr size_t PF_SMEM = PF_COL_BYTES + (size_t)PF_MAX_ENT * (4 + 4 + 1);
 
-__global__ void __launch_bounds__(PED_CHAIN_THREADS) ped_chain_kernel(const PedChainArgs a) {
-    extern __shared__ __align__(16) uint32_t ped_dyn[];
-    __shared__ ColShared S;
-    const uint32_t T = a.T, tb = a.tb, tid = threadIdx.x;
-    uint32_t *R = ped_dyn;                                              // raw values of the current column
-    uint32_t *M = R + a.max_ent;                                        // transition minima handed to the next column
-    unsigned long long *skeys = reinterpret_cast<unsigned long long *>(M + a.max_ent);  // partial minima of small columns
-    uint32_t *invec = reinterpret_cast<uint32_t *>(skeys + PED_CHAIN_THREADS);          // the chain's input vector
-    uint8_t *A = reinterpret_cast<uint8_t *>(invec + MAX_T);            // argmins of M
-    const uint32_t c = a.unit ? blockIdx.x / T : blockIdx.x, u = blockIdx.x % T;
+// back-pointers of the four entries of projection index o (entry e = 4 o + t, `w` bits each)
+__device__ __forceinline__ void pf_store_bp(uint32_t *arena, uint64_t bp_off, uint32_t w, uint32_t o, const uint32_t *v, bool valid) {
+    if (w <= 8) {  // the four entries share one element of 4 w bits
+        const uint32_t packed = valid ? (v[0] | (v[1] << w) | (v[2] << (2 * w)) | (v[3] << (3 * w))) : 0u;
+        bp_store_warp(arena, bp_off, 4 * w, o, packed, valid);
+    } else if (valid) {
+        if (w == 16) {
+            arena[bp_off + 2 * (uint64_t)o] = v[0] | (v[1] << 16);
+            arena[bp_off + 2 * (uint64_t)o + 1] = v[2] | (v[3] << 16);
+        } else {
+            for (uint32_t t = 0; t < PF_T; ++t) arena[bp_off + 4 * (uint64_t)o + t] = v[t];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFusedArgs a) {
+    extern __shared__ __align__(16) unsigned char pf_raw[];
+    PedFusedCol &C = *reinterpret_cast<PedFusedCol *>(pf_raw);
+    uint32_t *M = reinterpret_cast<uint32_t *>(pf_raw + PF_COL_BYTES);  // transition minima of the previous column [2^bw][4]
+    uint32_t *R = M + PF_MAX_ENT;                                       // raw values of the current column [2^f][4]
+    uint8_t *A = reinterpret_cast<uint8_t *>(R + PF_MAX_ENT);           // argmins belonging to M
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(R + PF_MAX_ENT / 2);  // small columns only (< 4096 entries)
+    const uint32_t tid = threadIdx.x, c = blockIdx.x;
     const uint32_t k0 = a.chain_begin[c], k1 = a.chain_begin[c + 1];
-    if (tid < T) invec[tid] = a.unit ? (tid == u ? 0u : UMAX) : a.in_vecs[(size_t)c * T + tid];
-    bool have_m = false;
+    const bool write_bp = !a.unit;
     for (uint32_t k = k0; k < k1; ++k) {
-        const ColMeta &cm = a.cols[k];
-        __syncthreads();  // the previous column is complete (R, M, A) and S may be overwritten
-        stage_column(S, cm, a.fn_group[cm.grp_off + T], T, a.fn_c0, a.fn_delta, a.fn_group);
-        const uint32_t d = S.m.d;
-        const uint32_t nent = (1u << S.m.f) * T;
-        uint32_t lc = 0;  // lanes per entry: small columns (chain ends) spread an entry's 2^d candidates over threads
-        while ((nent << lc) < PED_CHAIN_THREADS && lc < d) ++lc;
-        const uint32_t total = nent << lc, per = 1u << (d - lc);
-        if (lc) {
-            for (uint32_t e = tid; e < nent; e += PED_CHAIN_THREADS) skeys[e] = KEY_INF;
-            __syncthreads();
-        }
-        const bool write_bp = !a.unit;
-        const uint32_t *prev = have_m ? M : invec;
-        const uint8_t *prevarg = have_m ? A : nullptr;
-        for (uint32_t base = 0; base < total; base += PED_CHAIN_THREADS) {
-            const uint32_t g = base + tid, e = g >> lc, chunk = g & ((1u << lc) - 1u);
-            unsigned long long key = KEY_INF;
-            if (g < total) {
-                const uint32_t o = e >> tb, i = e & (T - 1);
-                ColView v = make_view(S, T, tb, a.fn_c0, a.fn_delta, prev, i, prevarg);
-                key = eval_candidates(v, o, i, chunk * per, (chunk + 1) * per);
-            }
-            if (lc) {
-                if (g < total) atomicMin(&skeys[e], key);
-            } else {
-                if (g < total) R[e] = (uint32_t)(key >> 32);
-                if (write_bp) bp_store_warp(a.arena, S.m.bp_off, S.m.bp_width, e, (uint32_t)key & low_mask(d + tb), g < total);
-            }
-        }
-        if (lc) {
-            __syncthreads();
-            for (uint32_t base = 0; base < nent; base += PED_CHAIN_THREADS) {
-                const uint32_t e = base + tid;
-                const unsigned long long key = e < nent ? skeys[e] : KEY_INF;
-                if (e < nent) R[e] = (uint32_t)(key >> 32);
-                if (write_bp) bp_store_warp(a.arena, S.m.bp_off, S.m.bp_width, e, (uint32_t)key & low_mask(d + tb), e < nent);
+        __syncthreads();  // column k - 1 complete: C may be overwritten, M / A hold its transition minima
+        if (tid < sizeof(ColMeta) / 4) ((uint32_t *)&C.m)[tid] = ((const uint32_t *)&a.cols[k])[tid];
+        __syncthreads();
+        {
+            const ColMeta &m = C.m;
+            if (tid < PF_SLOTS) pf_stage_slot(C, tid, a.fn_c0, a.fn_delta, a.fn_group + m.grp_off);
+            else if (tid == 32) {
+                C.drop = ~m.keep & low_mask(m.a);
+                C.rc_next = k + 1 < k1 ? a.cols[k + 1].rc : 0u;
+            } else if (tid >= 64 && tid < 64 + 2 * TAB_SIZE) pf_stage_pdep(C, tid - 64);
+            else if (tid == 1023 && k == k0) {  // the row the chain's first column reads
+                uint32_t invec[PF_T];
+                for (uint32_t j = 0; j < PF_T; ++j) invec[j] = a.unit ? (j == 0 ? 0u : UMAX) : a.in_vecs[(size_t)c * PF_T + j];
+                pf_first_row(m, invec, M, A);
             }
         }
         __syncthreads();
-        if (k + 1 < k1) {  // hand the next column min_j(value_j + popcount(i^j) * rc) and its argmin
-            const uint32_t rc_next = a.cols[k + 1].rc;
-            for (uint32_t e = tid; e < nent; e += PED_CHAIN_THREADS) {
-                uint32_t arg;
-                M[e] = transition_min(&R[e & ~(T - 1)], T, e & (T - 1), rc_next, &arg);
-                A[e] = (uint8_t)arg;
+        if (tid < PF_SLOTS * 32) pf_stage_table_run(C, tid);
+        const uint32_t f = C.m.f, d = C.m.d, nout = 1u << f, nent = nout * PF_T;
+        const uint32_t lc = pf_lane_bits(f, d), per = 1u << (d - lc), items = nout << lc;
+        if (lc)
+            for (uint32_t e = tid; e < nent; e += PF_THREADS) keys[e] = KEY_INF;
+        __syncthreads();
+        // ---- phase A: candidates
+        for (uint32_t base = 0; base < items; base += PF_THREADS) {
+            const uint32_t item = base + tid;
+            const bool valid = item < items;
+            PedQuad q;
+            uint32_t o = 0;
+            if (valid) {
+                o = item & (nout - 1u);
+                const uint32_t chunk = item >> f;
+                pf_walk(C, M, o, chunk * per, (chunk + 1) * per, q);
             }
-            have_m = true;
+            if (lc) {
+                if (valid)
+                    for (uint32_t t = 0; t < PF_T; ++t) atomicMin(&keys[o * PF_T + t], ((unsigned long long)q.val[t] << 32) | q.r[t]);
+            } else {
+                if (valid) *reinterpret_cast<uint4 *>(R + (size_t)o * PF_T) = make_uint4(q.val[0], q.val[1], q.val[2], q.val[3]);
+                if (write_bp) {
+                    uint32_t v[PF_T] = {0, 0, 0, 0};
+                    if (valid)
+                        for (uint32_t t = 0; t < PF_T; ++t) v[t] = pf_backpointer(C, A, o, t, q.val[t], q.r[t]) & low_mask(d + 2);
+                    pf_store_bp(a.arena, C.m.bp_off, C.m.bp_width, o, v, valid);
+                }
+            }
+        }
+        if (lc) {
+            __syncthreads();
+            for (uint32_t base = 0; base < nent; base += PF_THREADS) {
+                const uint32_t e = base + tid;
+                const bool valid = e < nent;
+                const unsigned long long key = valid ? keys[e] : KEY_INF;
+                const uint32_t val = (uint32_t)(key >> 32);
+                uint32_t bp = 0;
+                if (valid && write_bp) bp = pf_backpointer(C, A, e >> 2, e & 3u, val, (uint32_t)key) & low_mask(d + 2);
+                __syncwarp();
+                if (valid) R[e] = val;
+                if (write_bp) bp_store_warp(a.arena, C.m.bp_off, C.m.bp_width, e, bp, valid);
+            }
+        }
+        __syncthreads();
+        // ---- phase B: what the next column reads
+        if (k + 1 < k1) {
+            const uint32_t rc_next = C.rc_next;
+            for (uint32_t o = tid; o < nout; o += PF_THREADS) {
+                const uint4 r4 = *reinterpret_cast<const uint4 *>(R + (size_t)o * PF_T);
+                const uint32_t row[PF_T] = {r4.x, r4.y, r4.z, r4.w};
+                uint32_t mv[PF_T], arg[PF_T];
+#pragma unroll
+                for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(row, i, rc_next, &arg[i]);
+                *reinterpret_cast<uint4 *>(M + (size_t)o * PF_T) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
+                *reinterpret_cast<uint32_t *>(A + (size_t)o * PF_T) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+            }
         }
     }
     __syncthreads();
-    if (tid < T) a.out_vecs[(size_t)blockIdx.x * T + tid] = R[tid];  // a chain ends with f == 0: T raw values
+    if (tid < PF_T) a.out_vecs[(size_t)c * PF_T + tid] = R[tid] < PF_INF ? R[tid] : UMAX;  // a chain ends with f == 0
 }
 
-// true input vector of every chain from the chains' transfer matrices (compact form of ped_prefix_kernel)
-__global__ void ped_chain_prefix_kernel(const uint32_t *__restrict__ matrices, uint32_t T, uint32_t n_chains,
-                                        uint32_t *__restrict__ in_vecs) {
+// Pass 1 -> pass 2: chain 0 starts the table (its first column ignores the input: its row IS its output); every other
+// chain's transfer matrix is Mat[u][i] = row[i ^ u].  One thread folds them left to right (min-plus) into the true inputs.
+__global__ void ped_fused_prefix_kernel(const uint32_t *__restrict__ rows, uint32_t n_chains, uint32_t *__restrict__ in_vecs) {
     if (blockIdx.x || threadIdx.x) return;
-    uint32_t in[MAX_T];
-    for (uint32_t i = 0; i < T; ++i) in[i] = matrices[i];  // chain 0 starts the table: every row is its true output
-    fold_chains(
-        T, 1, n_chains, in, [&](uint32_t c, uint32_t u) { return matrices + ((size_t)c * T + u) * T; },
-        [&](uint32_t c, const uint32_t *cur) {
-            for (uint32_t i = 0; i < T; ++i) in_vecs[(size_t)c * T + i] = cur[i];
-        });
+    uint32_t in[PF_T], out[PF_T];
+    for (uint32_t i = 0; i < PF_T; ++i) {
+        in[i] = rows[i];
+        in_vecs[i] = 0;  // unused: the table's first column ignores its input
+    }
+    for (uint32_t c = 1; c < n_chains; ++c) {
+        for (uint32_t i = 0; i < PF_T; ++i) {
+            in_vecs[(size_t)c * PF_T + i] = in[i];
+            out[i] = UMAX;
+        }
+        const uint32_t *row = rows + (size_t)c * PF_T;
+        for (uint32_t u = 0; u < PF_T; ++u) {
+            if (in[u] == UMAX) continue;
+            for (uint32_t i = 0; i < PF_T; ++i) {
+                const uint32_t mv = row[i ^ u];
+                if (mv != UMAX && in[u] + mv < out[i]) out[i] = in[u] + mv;
+            }
+        }
+        for (uint32_t i = 0; i < PF_T; ++i) in[i] = out[i];
+    }
 }
 
 // pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
@@ -721,9 +771,8 @@ struct whmec_plan {
     int exits_mode = 0;  // 0: not computed since the last sweep; 1: last chain entered at the optimum; 2: like any chain
     DevBuf<uint32_t> d_in_vec, d_matrix, d_bt_exits, d_bt_entries;
     // fused per-chain pedigree sweep (ped_chain_kernel, experimental)
-    bool use_ped_chain = false;
-    DevBuf<uint32_t> d_chain_matrices, d_chain_in, d_chain_out;
-    size_t ped_chain_smem = 0;
+    bool use_ped_fused = false;
+    DevBuf<uint32_t> d_chain_rows, d_chain_in, d_chain_out;
     uint32_t sweeps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
     // tile path
@@ -736,7 +785,7 @@ struct whmec_plan {
         d_result.release(); d_fn_delta.release(); d_keys.release();
         d_ped_steps.release(); d_ped_vals.release(); d_chain_len.release(); d_ped_args.release();
         d_in_vec.release(); d_matrix.release(); d_bt_exits.release(); d_bt_entries.release();
-        d_chain_matrices.release(); d_chain_in.release(); d_chain_out.release();
+        d_chain_rows.release(); d_chain_in.release(); d_chain_out.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (ev0) cudaEventDestroy(ev0);
@@ -841,7 +890,23 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         // pedigrees with several chains: batched two-pass sweep
         const char *seq = std::getenv("WHMEC_PED_SEQUENTIAL");
         const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
-        if (pk.T > 1 && (C >= 2 || segment) && pk.safe31 && !(seq && seq[0] == '1' && !segment)) {
+        // one trio, shapes of ped_fused.h: one block per chain with the projection in shared memory (3 launches)
+        bool fused_ok = false;
+        {
+            const char *pf = std::getenv("WHMEC_PED_FUSED");
+            fused_ok = !(pf && pf[0] == '0') && pk.T == PF_T && C >= 2 && !segment && pk.safe31 && !(seq && seq[0] == '1');
+            for (uint32_t k = 0; k < n && fused_ok; ++k) fused_ok = pf_column_ok(pk.cols[k], pk.fn_group.data() + pk.cols[k].grp_off);
+        }
+        if (fused_ok) {
+            CUDA_TRY(pl->d_chain_rows.alloc((size_t)C * PF_T, pl->stream));
+            CUDA_TRY(pl->d_chain_in.alloc((size_t)C * PF_T, pl->stream));
+            CUDA_TRY(pl->d_chain_out.alloc((size_t)C * PF_T, pl->stream));
+            CUDA_TRY(cudaFuncSetAttribute(ped_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+            pl->use_ped_fused = true;
+            pl->use_ped_batch = true;  // two-pass sweep: the backtrace and the optimum read the chains' final values
+            pl->d_last_vals = pl->d_chain_out.p + (size_t)(C - 1) * PF_T;
+            pl->stats.path_kind = 3;
+        } else if (pk.T > 1 && (C >= 2 || segment) && pk.safe31 && !(seq && seq[0] == '1' && !segment)) {
             const uint32_t T = pk.T;
             const uint32_t slots = C * T + C;
             if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && (uint64_t)C * T <= 65535) {
@@ -916,20 +981,6 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
                 pl->stats.path_kind = 3;
             }
         }
-        if (const char *pc = std::getenv("WHMEC_PED_CHAIN")) {
-            // experimental: one block per chain with the projection in shared memory (ped_chain_kernel)
-            const size_t smem = (size_t)max_ent * 9 + PED_CHAIN_THREADS * 8 + MAX_T * 4;
-            if (pc[0] == '1' && pl->use_ped_batch && !segment && max_ent <= 16384 && pk.T <= 16) {
-                CUDA_TRY(pl->d_chain_matrices.alloc((size_t)C * pk.T * pk.T, pl->stream));
-                CUDA_TRY(pl->d_chain_in.alloc((size_t)C * pk.T, pl->stream));
-                CUDA_TRY(pl->d_chain_out.alloc((size_t)C * pk.T, pl->stream));
-                CUDA_TRY(cudaFuncSetAttribute(ped_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                pl->ped_chain_smem = smem;
-                pl->ped_max_ent = max_ent;
-                pl->use_ped_chain = true;
-                pl->d_last_vals = pl->d_chain_out.p + (size_t)(C - 1) * pk.T;
-            }
-        }
         if (segment && !pl->use_ped_batch) {
             msg = "unsupported: this segment cannot run the two-pass pedigree sweep (costs beyond 2^28 or state beyond the budget)";
             return WHMEC_ERR_UNSUPPORTED;
@@ -994,29 +1045,24 @@ int ped_prefix(whmec_plan *pl, const uint32_t *d_in_vec, uint32_t &launches, std
     return WHMEC_OK;
 }
 
-// three launches for the whole table: unit inputs of every chain, prefix, true inputs
-int ped_chain_sweep(whmec_plan *pl, std::string &msg) {
+// three launches for the whole table: unit input of every chain, prefix, true inputs
+int ped_fused_sweep(whmec_plan *pl, std::string &msg) {
     const Packed &pk = pl->pk;
-    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1, T = pk.T;
-    PedChainArgs a{pl->d_cols.p, pl->d_chain_begin.p, pl->d_fn_c0.p, pl->d_fn_group.p, pl->d_fn_delta.p, pl->d_arena.p,
-                   pl->d_chain_in.p, pl->d_chain_matrices.p, T, pk.tb, (uint32_t)pl->ped_max_ent, 1u};
-    uint32_t launches = 0;
-    if (C > 1) {
-        ped_chain_kernel<<<C * T, PED_CHAIN_THREADS, pl->ped_chain_smem, pl->stream>>>(a);
-        ped_chain_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_chain_matrices.p, T, C, pl->d_chain_in.p);
-        launches += 2;
-    }
+    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
+    PedFusedArgs a{pl->d_cols.p, pl->d_chain_begin.p, pl->d_fn_c0.p, pl->d_fn_group.p, pl->d_fn_delta.p, pl->d_arena.p,
+                   pl->d_chain_in.p, pl->d_chain_rows.p, 1u};
+    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(a);
+    ped_fused_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_chain_rows.p, C, pl->d_chain_in.p);
     a.unit = 0;
     a.out_vecs = pl->d_chain_out.p;
-    ped_chain_kernel<<<C, PED_CHAIN_THREADS, pl->ped_chain_smem, pl->stream>>>(a);
-    ++launches;
+    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(a);
     CUDA_TRY(cudaGetLastError());
-    pl->stats.kernel_launches = launches;
+    pl->stats.kernel_launches = 3;
     return WHMEC_OK;
 }
 
 int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
-    if (pl->use_ped_chain) return ped_chain_sweep(pl, msg);
+    if (pl->use_ped_fused) return ped_fused_sweep(pl, msg);
     uint32_t launches = 0;
     int rc = ped_pass(pl, 0, launches, msg);
     if (rc == WHMEC_OK) rc = ped_prefix(pl, nullptr, launches, msg);
