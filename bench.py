@@ -6,7 +6,8 @@
 One "step" = one complete forward sweep of the DP over the synthetic workload (all variant
 columns of all DP-independent blocks).  Metric: variant-columns per second (BASELINE.json).
 
-  value      device-timed sweep with the packed ReadSet already resident in HBM
+  value      device-timed forward sweep + backtrace (+ the 8 bytes / column of the optimal path coming back) with the packed
+             ReadSet already resident in HBM: everything the device does for PedigreeDPTable(...) + get_super_reads()
   e2e        the same workload through the C-ABI call `whmec_solve` with HOST buffers:
              packing, allocation, host->device copies, sweep, device backtrace, device->host
              copies and super-read construction are all inside the timed region
@@ -285,23 +286,26 @@ def main():
     plan = _lib.Plan(prob, device=local_rank)
     for _ in range(max(args.warmup, 3)):
         plan.sweep()
+        plan.finish()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    sweep_ms = []
+    sweep_ms, step_ms = [], []
     for _ in range(args.steps):
         flush.fill_(1)  # evict the previous step's state / back-pointers from L2 (not timed)
         torch.cuda.synchronize()
         plan.sweep()    # timed on the launching stream with CUDA events inside the library
-        sweep_ms.append(plan.stats()["sweep_ms"])
+        sol = plan.finish()  # device: backtrace kernels + D2H of the path (timed with events); host: super-reads (not in `value`, in `e2e`)
+        st = plan.stats()
+        sweep_ms.append(st["sweep_ms"])
+        step_ms.append(st["sweep_ms"] + st["d2h_ms"])
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     stats = plan.stats()
-    sol = plan.finish()
     plan.close()
-    total_ms = sum(sweep_ms)
+    total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     cols_t = torch.tensor([float(n_cols)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -325,6 +329,26 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_value = all_cols * e2e_steps / float(e2e_t.item())
+
+    # ---- the object-level call a user of the reference makes: PedigreeDPTable(readset, recombcost, pedigree) + get_super_reads()
+    # on this package's container objects (rank 0, N = 1): includes the Python-side flattening of the ReadSet
+    e2e_api = None
+    if world == 1:
+        from whatshap_b200 import PedigreeDPTable, synth
+
+        rs, rc_list, ped = synth.to_objects(prob)
+        PedigreeDPTable(rs, rc_list, ped).get_super_reads()  # warm-up
+        torch.cuda.synchronize()
+        api_t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            table = PedigreeDPTable(rs, rc_list, ped, device=local_rank)
+            superreads, tv = table.get_super_reads()
+            cost_api = table.get_optimal_cost()
+        api_dt = time.perf_counter() - api_t0
+        assert cost_api == int(sol.cost) and superreads[0][0]._allele == sol.sr_allele[0, 0].tolist(), "object-level and flat results disagree"
+        e2e_api = {"value": n_cols * e2e_steps / api_dt, "unit": UNIT, "ms_per_step": 1e3 * api_dt / e2e_steps,
+                   "note": "PedigreeDPTable(readset, recombcost, pedigree) + get_super_reads() on container objects: Python flattening of "
+                           "the ReadSet + whmec_solve + super-read objects"}
 
     # ---- strong scaling: ONE problem (rank 0's) sharded over all ranks, end to end from rank 0's host arrays --------
     sharded = None
@@ -357,6 +381,18 @@ def main():
         peak, peak_src = hbm_peak()
         launches = int(stats["kernel_launches"])
         achieved = stats["algorithmic_bytes"] / (statistics.mean(sweep_ms) / 1e3) / 1e9
+        issue = recorded_issue(name, stats["cells"] / max(launches, 1))
+        roofline_issue = None
+        if issue and clocks.get("sm_mhz"):
+            # warp instructions of one sweep (ncu capture of one launch x launches) against what the SMs can issue in that time
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            peak_issue = sms * 4 * clocks["sm_mhz"] * 1e6  # one warp instruction per scheduler and cycle
+            ach = issue["warp_instructions_per_launch"] * launches / (statistics.mean(sweep_ms) / 1e3)
+            roofline_issue = {"bound": "int-issue", "achieved": ach, "peak": peak_issue, "unit": "warp-instructions/s", "frac": ach / peak_issue,
+                              "thread_instructions_per_dp_cell": issue["thread_instructions_per_dp_cell"], "source": issue["source"],
+                              "note": "the bound that binds: the DP kernels issue integer min / add instructions, one warp instruction per "
+                                      "scheduler and cycle at best; instruction count from the committed ncu capture of this kernel, time "
+                                      "from this run"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -364,7 +400,8 @@ def main():
             "config": {
                 "workload": name, "description": WORKLOADS[name][0], "columns_per_gpu": n_cols,
                 "coverage": WORKLOADS[name][2], "transmission_vectors": WORKLOADS[name][3],
-                "chains": int(stats["n_chains"]), "kernel_path": {1: "tile", 2: "column", 3: "column (batched pedigree sweep)"}.get(int(stats["path_kind"]), "mixed"),
+                "chains": int(stats["n_chains"]), "kernel_path": {1: "tile (mirrored panels)", 2: "column", 3: "pedigree two-pass sweep (fused per chain)" if launches == 3 else "pedigree two-pass sweep (batched)"}.get(int(stats["path_kind"]), "mixed"),
+                "value_covers": "forward sweep + backtrace + path D2H, device-timed (CUDA events)",
                 "l2": "512 MiB buffer rewritten between timed steps (L2 flush)", "sharding": "one full-size workload per GPU, no collective on the data path",
                 "optimal_cost_rank0": int(sol.cost), "wall_s_timed_region": wall,
             },
@@ -372,8 +409,8 @@ def main():
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": recorded_traffic(name)[0], "traffic_source": recorded_traffic(name)[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stats["algorithmic_bytes"] / max(launches, 1),
-                "kernel": {1: "tile_panel_kernel", 2: "col_direct_kernel", 3: "col_batched_kernel"}.get(int(stats["path_kind"]), "col_direct_kernel"),
-                "issue": recorded_issue(name, stats["cells"] / max(launches, 1)),
+                "kernel": {1: "tile_panel_kernel", 2: "col_direct_kernel", 3: "ped_fused_kernel" if launches == 3 else "col_batched_kernel"}.get(int(stats["path_kind"]), "col_direct_kernel"),
+                "issue": issue,
                 "algorithmic_bytes_per_step": int(stats["algorithmic_bytes"]), "launches_per_step": launches,
                 "bytes_moved_per_step": {"backpointers": int(stats["backptr_bytes"]), "state": int(stats["state_bytes"])},
                 "note": ("algorithmic bytes follow the reference's data layout (u32 projection read + u32 value and u32 back-pointer "
@@ -381,12 +418,16 @@ def main():
                          "whole panel of columns and stores 1-bit back-pointers, so its real DRAM traffic (`traffic`, ncu) is far below "
                          "that and frac can exceed 1: the kernel is bound by integer issue, see dp_cells_per_s"),
                 "dp_cells_per_s": stats["cells"] / (statistics.mean(sweep_ms) / 1e3),
+                "sweep_ms": statistics.mean(sweep_ms), "backtrace_ms": statistics.mean(step_ms) - statistics.mean(sweep_ms),
             },
+            "roofline_issue": roofline_issue,
             "clocks": clocks,
+            "e2e_api": e2e_api,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(st2["h2d_bytes"]), "d2h_bytes_per_step": int(st2["d2h_bytes"]),
                     "ms_per_step": 1e3 * float(e2e_t.item()) / e2e_steps, "steps": e2e_steps,
                     "note": "whmec_solve: host CSR arrays in, host result arrays out (pack + alloc + H2D + sweep + backtrace + D2H)"},
-            "gpu_launches": launches * args.steps,
+            # forward-sweep kernels + backtrace kernels (1 for a single individual, 3 for a pedigree) per timed step
+            "gpu_launches": (launches + (3 if int(stats["transmissions"]) > 1 else 1)) * args.steps,
         }
         if sharded is not None:
             line["e2e_sharded"] = sharded

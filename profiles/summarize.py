@@ -55,8 +55,9 @@ def main(prefix):
             wl = name[len(prefix):].split(".")[0].split("_")[-1]
             kernel = r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].strip()
             num = lambda key: float(r[hdr.index(key)])
+            dur_unit = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
             traffic[wl] = {"bytes_per_launch": total, "kernel": kernel, "report": name,
-                           "grid": int(num("launch__grid_size")), "duration_us": num("gpu__time_duration.sum"),
+                           "grid": int(num("launch__grid_size")), "duration_us": num("gpu__time_duration.sum") * dur_unit,
                            "warp_inst_executed": num("smsp__inst_executed.sum"), "sm_cycles_elapsed": num("sm__cycles_elapsed.max"),
                            "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active")}
         open(os.path.join(ROOT, "profiles", name.replace(".ncu-rep", ".txt")), "w").write("\n".join(lines) + "\n")

@@ -287,16 +287,17 @@ void fused_chain(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool unit
     for (uint32_t k = k0; k < k1; ++k) {
         C.m = pk.cols[k];
         const ColMeta &m = C.m;
-        for (uint32_t s = 0; s < PF_SLOTS; ++s) pf_stage_slot(C, s, pk.fn_c0.data(), pk.fn_delta.data(), pk.fn_group.data() + m.grp_off);
+        const uint32_t *group = pk.fn_group.data() + m.grp_off;
+        for (uint32_t s = 0; s < PF_SLOTS; ++s) pf_stage_slot(C, m, s, pk.fn_c0.data(), pk.fn_delta.data(), group);
         C.drop = ~m.keep & low_mask(m.a);
         C.rc_next = k + 1 < k1 ? pk.cols[k + 1].rc : 0u;
-        for (uint32_t v = 0; v < 2 * TAB_SIZE; ++v) pf_stage_pdep(C, v);
+        for (uint32_t v = 0; v < 2 * TAB_SIZE; ++v) pf_stage_pdep(C, m, v);
         if (k == k0) {
             uint32_t invec[PF_T];
             for (uint32_t j = 0; j < PF_T; ++j) invec[j] = unit ? (j == 0 ? 0u : UMAX) : in_vec[j];
             pf_first_row(m, invec, M.data(), A.data());
         }
-        for (uint32_t run = 0; run < PF_SLOTS * 32; ++run) pf_stage_table_run(C, run);
+        for (uint32_t run = 0; run < PF_SLOTS * 32; ++run) pf_stage_table_run(C, m, run, pk.fn_delta.data(), group);
         const uint32_t f = m.f, d = m.d, nout = 1u << f, nent = nout * PF_T;
         const uint32_t lc = pf_lane_bits(f, d), per = 1u << (d - lc), items = nout << lc;
         if (lc) std::fill(keys.begin(), keys.begin() + nent, KEY_INF);
@@ -310,7 +311,7 @@ void fused_chain(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool unit
                 } else {
                     R[o * PF_T + t] = q.val[t];
                     if (!unit) bp_store_serial(arena.data(), m.bp_off, m.bp_width, (uint64_t)o * PF_T + t,
-                                               pf_backpointer(C, A.data(), o, t, q.val[t], q.r[t]) & low_mask(d + 2));
+                                               pf_backpointer(A.data(), t, q.val[t], q.r[t], q.b[t]) & low_mask(d + 2));
                 }
             }
         }
@@ -318,7 +319,7 @@ void fused_chain(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool unit
             for (uint32_t e = 0; e < nent; ++e) {
                 R[e] = (uint32_t)(keys[e] >> 32);
                 if (!unit) bp_store_serial(arena.data(), m.bp_off, m.bp_width, e,
-                                           pf_backpointer(C, A.data(), e >> 2, e & 3u, R[e], (uint32_t)keys[e]) & low_mask(d + 2));
+                                           pf_backpointer_of_key(C, A.data(), e >> 2, e & 3u, R[e], (uint32_t)keys[e]) & low_mask(d + 2));
             }
         if (k + 1 < k1)
             for (uint32_t o = 0; o < nout; ++o) {
@@ -326,8 +327,8 @@ void fused_chain(const Packed &pk, uint32_t c, const uint32_t *in_vec, bool unit
                 for (uint32_t j = 0; j < PF_T; ++j) row[j] = R[o * PF_T + j];
                 for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(row, i, C.rc_next, &arg[i]);
                 for (uint32_t i = 0; i < PF_T; ++i) {
-                    M[o * PF_T + i] = mv[i];
-                    A[o * PF_T + i] = (uint8_t)arg[i];
+                    M[pf_swz(o) * PF_T + i] = mv[i];
+                    A[pf_swz(o) * PF_T + i] = (uint8_t)arg[i];
                 }
             }
     }

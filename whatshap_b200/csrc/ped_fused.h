@@ -30,19 +30,27 @@ constexpr uint32_t PF_MAX_A = 16;       // active reads per column (two byte tab
 constexpr uint32_t PF_MAX_F = 12;       // log2 projection entries per transmission value
 constexpr uint32_t PF_THREADS = 1024;
 
+constexpr uint32_t PF_ROW = 20;         // words per row of a byte table: 16 slots + 4 words of skew (rows 0..7 start in 8 different
+                                        // groups of four banks, so the 128-bit loads of a quarter warp spread over all banks)
+
 struct PedFusedCol {                    // one column, staged in shared memory
     ColMeta m;
     uint32_t drop;                      // dropped positions as a bit set
     uint32_t rc_next;                   // recombination cost of the next column of the chain (0 at the chain's end)
-    uint32_t c0[PF_SLOTS];
-    int32_t sd[PF_MAX_A][2][PF_SLOTS];  // signed step of slot s when bit `pos` becomes 1 / 0:  +delta / -delta
+    alignas(16) uint32_t c0[PF_SLOTS];
+    alignas(16) int32_t sd[PF_MAX_A][2][PF_SLOTS];  // signed step of slot s when bit `pos` becomes 1 / 0:  +delta / -delta
     uint32_t pd_lo[TAB_SIZE], pd_hi[TAB_SIZE];
-    int32_t tlo[PF_SLOTS][TAB_SIZE], thi[PF_SLOTS][TAB_SIZE];
+    alignas(16) int32_t tab[2][TAB_SIZE][PF_ROW];   // [half][byte value][slot]: sum of the slot's deltas over cell bits 0..7 / 8..15
 };
 
 struct PedQuad {
-    uint32_t val[PF_T], r[PF_T];
+    uint32_t val[PF_T], r[PF_T], b[PF_T];  // per transmission value: best value, rank of its candidate, that candidate's index into M
 };
+
+// Row b of the previous column's transition minima sits at row pf_swz(b): within a warp the candidates of neighbouring outputs
+// share their low index bits (the reads that end are the oldest = lowest bits), the swizzle moves the bits that do differ into
+// the bank-selecting position (128-bit row loads: 8 rows per wavefront).
+WHMEC_HD uint32_t pf_swz(uint32_t b) { return b ^ ((b >> 3) & 7u); }
 
 // Is the fused sweep applicable to column `m` with the given function groups?
 WHMEC_HD bool pf_column_ok(const ColMeta &m, const uint32_t *group /* [T + 1] */) {
@@ -53,29 +61,40 @@ WHMEC_HD bool pf_column_ok(const ColMeta &m, const uint32_t *group /* [T + 1] */
 }
 
 // Slot s = t * PF_GS + q holds the q-th function of transmission value t (or +inf).  One call fills slot `s`.
-WHMEC_HD void pf_stage_slot(PedFusedCol &C, uint32_t s, const uint32_t *fn_c0, const int32_t *fn_delta, const uint32_t *group) {
+// (the staging functions read the column's ColMeta `m` and the function arrays from global memory, so that one barrier
+// separates "stage column k" from "sweep column k")
+WHMEC_HD void pf_stage_slot(PedFusedCol &C, const ColMeta &m, uint32_t s, const uint32_t *fn_c0, const int32_t *fn_delta, const uint32_t *group) {
     const uint32_t t = s / PF_GS, q = s % PF_GS;
     const uint32_t g0 = group[t], g1 = group[t + 1];
     const bool used = g0 + q < g1;
-    const uint32_t F = C.m.fn_off + g0 + q;
+    const uint32_t F = m.fn_off + g0 + q;
     C.c0[s] = used ? fn_c0[F] : PF_INF;
     for (uint32_t pos = 0; pos < PF_MAX_A; ++pos) {
-        const int32_t d = (used && pos < C.m.a) ? fn_delta[(size_t)F * FN_STRIDE + pos] : 0;
+        const int32_t d = (used && pos < m.a) ? fn_delta[(size_t)F * FN_STRIDE + pos] : 0;
         C.sd[pos][1][s] = d;
         C.sd[pos][0][s] = (int32_t)(0u - (uint32_t)d);
     }
 }
 
-// 16 consecutive entries of one byte table of slot s (see build_cost_table_run): run = s * 32 + half * 16 + hi4.
-WHMEC_HD void pf_stage_table_run(PedFusedCol &C, uint32_t run) {
+// 16 consecutive entries of one byte table of slot s (subset sums, one add per entry): run = s * 32 + half * 16 + hi4.
+WHMEC_HD void pf_stage_table_run(PedFusedCol &C, const ColMeta &m, uint32_t run, const int32_t *fn_delta, const uint32_t *group) {
     const uint32_t s = run >> 5, half = (run >> 4) & 1u, hi4 = run & 15u;
-    int32_t delta[2 * TAB_BITS];
-    for (uint32_t j = 0; j < 2 * TAB_BITS; ++j) delta[j] = C.sd[j][1][s];
-    build_cost_table_run(delta, half, hi4, (half ? C.thi[s] : C.tlo[s]) + 16 * hi4);
+    const uint32_t t = s / PF_GS, q = s % PF_GS;
+    const bool used = group[t] + q < group[t + 1];
+    const int32_t *dl = fn_delta + (size_t)(m.fn_off + group[t] + q) * FN_STRIDE + half * TAB_BITS;
+    uint32_t d[TAB_BITS];
+    for (uint32_t j = 0; j < TAB_BITS; ++j) d[j] = (used && half * TAB_BITS + j < m.a) ? (uint32_t)dl[j] : 0u;
+    uint32_t base = 0;  // sums wrap like the reference's unsigned costs
+    for (uint32_t b = 0; b < 4; ++b)
+        if ((hi4 >> b) & 1u) base += d[4 + b];
+    uint32_t sub[16];
+    sub[0] = base;
+    for (uint32_t i = 1; i < 16; ++i) sub[i] = sub[i & (i - 1)] + d[ctz32(i)];
+    for (uint32_t i = 0; i < 16; ++i) C.tab[half][16 * hi4 + i][s] = (int32_t)sub[i];
 }
 
-WHMEC_HD void pf_stage_pdep(PedFusedCol &C, uint32_t v /* < 2 * TAB_SIZE */) {
-    const uint32_t keep_lo = lowest_set_bits(C.m.keep, TAB_BITS), keep_hi = lowest_set_bits(C.m.keep & ~keep_lo, TAB_BITS);
+WHMEC_HD void pf_stage_pdep(PedFusedCol &C, const ColMeta &m, uint32_t v /* < 2 * TAB_SIZE */) {
+    const uint32_t keep_lo = lowest_set_bits(m.keep, TAB_BITS), keep_hi = lowest_set_bits(m.keep & ~keep_lo, TAB_BITS);
     if (v < TAB_SIZE) C.pd_lo[v] = pdep32(v, keep_lo);
     else C.pd_hi[v - TAB_SIZE] = pdep32(v - TAB_SIZE, keep_hi);
 }
@@ -89,9 +108,11 @@ WHMEC_HD void pf_walk(const PedFusedCol &C, const uint32_t *__restrict__ M, uint
     const uint32_t cg = rank_offset(m, kept);
     uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cg, C.drop);
     uint32_t cost[PF_SLOTS];
+    {
+        const int32_t *lo = C.tab[0][x & (TAB_SIZE - 1)], *hi = C.tab[1][(x >> TAB_BITS) & (TAB_SIZE - 1)];
 #pragma unroll
-    for (uint32_t s = 0; s < PF_SLOTS; ++s)
-        cost[s] = C.c0[s] + (uint32_t)(C.tlo[s][x & (TAB_SIZE - 1)] + C.thi[s][(x >> TAB_BITS) & (TAB_SIZE - 1)]);
+        for (uint32_t s = 0; s < PF_SLOTS; ++s) cost[s] = C.c0[s] + (uint32_t)(lo[s] + hi[s]);
+    }
     const uint32_t bmask = low_mask(m.bw);
     uint32_t best[PF_T], br[PF_T];
 #pragma unroll
@@ -100,7 +121,7 @@ WHMEC_HD void pf_walk(const PedFusedCol &C, const uint32_t *__restrict__ M, uint
         br[t] = r0;
     }
     for (uint32_t r = r0; r < r1; ++r) {
-        const uint32_t *mrow = M + (size_t)(x & bmask) * PF_T;
+        const uint32_t *mrow = M + (size_t)pf_swz(x & bmask) * PF_T;
 #pragma unroll
         for (uint32_t t = 0; t < PF_T; ++t) {
             uint32_t cur = cost[t * PF_GS];
@@ -124,18 +145,21 @@ WHMEC_HD void pf_walk(const PedFusedCol &C, const uint32_t *__restrict__ M, uint
     for (uint32_t t = 0; t < PF_T; ++t) {
         out.val[t] = best[t] < PF_INF ? best[t] : PF_INF;
         out.r[t] = br[t];
+        out.b[t] = (kept | pdep32((br[t] ^ (br[t] >> 1)) ^ cg, C.drop)) & bmask;  // index of the winner into M / A
     }
 }
 
-// Back-pointer of entry (o, t) from its winner's rank: (r << tb) | argmin j of the transition the winner was reached
-// through (A: argmins belonging to M).
-WHMEC_HD uint32_t pf_backpointer(const PedFusedCol &C, const uint8_t *__restrict__ A, uint32_t o, uint32_t t, uint32_t val, uint32_t r) {
-    uint32_t j = 0;
-    if (val < PF_INF) {
-        const uint32_t x = candidate_index(C.m, o, r);
-        j = A[(size_t)(x & low_mask(C.m.bw)) * PF_T + t];
-    }
+// Back-pointer of entry (o, t) from its winner: (r << tb) | argmin j of the transition the winner was reached through
+// (A: argmins belonging to M, same swizzled rows); b = the winner's index into M (PedQuad::b).
+WHMEC_HD uint32_t pf_backpointer(const uint8_t *__restrict__ A, uint32_t t, uint32_t val, uint32_t r, uint32_t b) {
+    const uint32_t j = val < PF_INF ? A[(size_t)pf_swz(b) * PF_T + t] : 0u;
     return (r << 2) | j;
+}
+
+// the same from a merged key (small columns): the winner's index is rebuilt from its rank
+WHMEC_HD uint32_t pf_backpointer_of_key(const PedFusedCol &C, const uint8_t *__restrict__ A, uint32_t o, uint32_t t, uint32_t val, uint32_t r) {
+    const uint32_t b = val < PF_INF ? (candidate_index(C.m, o, r) & low_mask(C.m.bw)) : 0u;
+    return pf_backpointer(A, t, val, r, b);
 }
 
 // min_j(row[j] + popcount(i ^ j) * rc) with the smallest minimising j (transition_min of dp_device.h on this path's +inf).

@@ -580,15 +580,44 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     }  // work loop
 }
 
-__global__ void tile_backtrace_kernel(const ColMeta *__restrict__ cols, const TileCol *__restrict__ tcols,
-                                      const uint32_t *__restrict__ arena, const uint32_t *__restrict__ chain_begin,
-                                      uint32_t n_chains, const unsigned long long *__restrict__ chain_keys,
-                                      uint32_t *__restrict__ path_index, uint32_t *__restrict__ result) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// Backtrace: one warp per DP-independent chain.  The walk itself is sequential (the cell of column k - 1 is read through the
+// cell of column k), but the per-column records it needs (ColMeta + TileCol, ~360 bytes) are not: the lanes stage them 16
+// columns at a time into shared memory, lane 0 then walks those 16 columns paying only for the dependent back-pointer loads.
+constexpr uint32_t BT_CHUNK = 16;
+
+__global__ void __launch_bounds__(32) tile_backtrace_kernel(const ColMeta *__restrict__ cols, const TileCol *__restrict__ tcols,
+                                                            const uint32_t *__restrict__ arena, const uint32_t *__restrict__ chain_begin,
+                                                            uint32_t n_chains, const unsigned long long *__restrict__ chain_keys,
+                                                            uint32_t *__restrict__ path_index, uint32_t *__restrict__ result) {
+    __shared__ ColMeta s_cols[BT_CHUNK + 1];  // columns lo .. lo + n (the extra one supplies cols[k].bw of the chunk's top step)
+    __shared__ TileCol s_tcols[BT_CHUNK];
+    __shared__ uint32_t s_path[BT_CHUNK];
+    const uint32_t c = blockIdx.x, lane = threadIdx.x;
     if (c >= n_chains) return;
     const unsigned long long key = chain_keys[c];
-    tile_backtrace_chain(cols, tcols, arena, chain_begin[c], chain_begin[c + 1] - 1, key, path_index);
-    atomicAdd(&result[0], (uint32_t)(key >> 32));  // cost = sum over DP-independent chains
+    const uint32_t k_first = chain_begin[c], k_last = chain_begin[c + 1] - 1;
+    uint32_t r = (uint32_t)key;
+    uint32_t x = r ^ (r >> 1);  // Gray code of the winning rank = canonical index in the last column
+    if (lane == 0) {
+        path_index[k_last] = x;
+        atomicAdd(&result[0], (uint32_t)(key >> 32));  // cost = sum over DP-independent chains
+    }
+    for (uint32_t hi = k_last; hi > k_first;) {  // steps hi -> hi - 1, ..., lo + 1 -> lo
+        const uint32_t lo = hi - k_first > BT_CHUNK ? hi - BT_CHUNK : k_first, n = hi - lo;
+        constexpr uint32_t CW = sizeof(ColMeta) / 4, TW = sizeof(TileCol) / 4;
+        for (uint32_t w = lane; w < (n + 1) * CW; w += 32) ((uint32_t *)s_cols)[w] = ((const uint32_t *)(cols + lo))[w];
+        for (uint32_t w = lane; w < n * TW; w += 32) ((uint32_t *)s_tcols)[w] = ((const uint32_t *)(tcols + lo))[w];
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t k = hi; k > lo; --k) {
+                x = tile_backtrace_step(s_cols[k - lo].bw, s_cols[k - 1 - lo], s_tcols[k - 1 - lo], arena, x);
+                s_path[k - 1 - lo] = x;
+            }
+        __syncwarp();
+        if (lane < n) path_index[lo + lane] = s_path[lane];
+        __syncwarp();
+        hi = lo;
+    }
 }
 
 struct TileImpl {
@@ -638,7 +667,7 @@ PinnedStage g_stage;
 
 bool pinned_staging_enabled() {
     const char *e = std::getenv("WHMEC_PINNED_STAGING");
-    return e && e[0] == '1';
+    return !(e && e[0] == '0');  // default since round 2 (B200: 1.5 ms of a 17 MB upload); "0": pageable copies
 }
 
 }  // namespace
@@ -760,7 +789,7 @@ int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
 int TilePlan::backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg) {
     TileImpl *I = (TileImpl *)impl;
     CUDA_TRY(cudaMemsetAsync(d_result, 0, 16, stream));
-    tile_backtrace_kernel<<<(I->n_chains + 63) / 64, 64, 0, stream>>>(I->d_cols, I->d_tcols, I->d_arena, I->d_chain_begin,
+    tile_backtrace_kernel<<<I->n_chains, 32, 0, stream>>>(I->d_cols, I->d_tcols, I->d_arena, I->d_chain_begin,
                                                                        I->n_chains, I->d_chain_keys, d_path_index, d_result);
     CUDA_TRY(cudaGetLastError());
     return WHMEC_OK;

@@ -135,6 +135,25 @@ WHMEC_HD uint32_t tile_packed_bit_index(const TileCol &tc, uint32_t lo) {
 }
 
 
+// One backtrace step (pedigreedptable.cpp:155-160): from the cell x of column k (whose backward width is `bw`) to the cell of
+// column k - 1 (records pm / pt) through the tile-layout back-pointers.
+WHMEC_HD uint32_t tile_backtrace_step(uint32_t bw, const ColMeta &pm, const TileCol &pt, const uint32_t *arena, uint32_t x) {
+    const uint32_t o = x & low_mask(bw);   // canonical forward-projection entry of column k-1
+    const uint32_t fmask = low_mask(pm.f);
+    uint32_t tile = pext32(o, pt.gmask_out);
+    uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
+    uint64_t section = 0;
+    if (pt.half && ((tile >> (pt.g - 1)) & 1u)) {  // output of an uncomputed tile: stored by its mirror image
+        tile = ~tile & low_mask(pt.g);
+        lo = ~lo & low_mask(pt.l_out);
+        if (pt.km != 0) section = pt.bp_tile_words;
+    }
+    uint32_t at = lo;
+    if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);  // thread-packed bits
+    const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_stride + section, pt.bp_width, at);
+    return candidate_index(pm, o, bp);
+}
+
 // Backtrace of one chain through the tile-layout back-pointers (pedigreedptable.cpp:144-160).
 WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, const uint32_t *arena, uint32_t k_first,
                                    uint32_t k_last, uint64_t end_key, uint32_t *path_index) {
@@ -142,22 +161,7 @@ WHMEC_HD void tile_backtrace_chain(const ColMeta *cols, const TileCol *tcols, co
     uint32_t x = r ^ (r >> 1);  // Gray code of the winning rank = canonical index in the last column
     path_index[k_last] = x;
     for (uint32_t k = k_last; k > k_first; --k) {
-        const uint32_t o = x & low_mask(cols[k].bw);   // canonical forward-projection entry of column k-1
-        const ColMeta &pm = cols[k - 1];
-        const TileCol &pt = tcols[k - 1];
-        const uint32_t fmask = low_mask(pm.f);
-        uint32_t tile = pext32(o, pt.gmask_out);
-        uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
-        uint64_t section = 0;
-        if (pt.half && ((tile >> (pt.g - 1)) & 1u)) {  // output of an uncomputed tile: stored by its mirror image
-            tile = ~tile & low_mask(pt.g);
-            lo = ~lo & low_mask(pt.l_out);
-            if (pt.km != 0) section = pt.bp_tile_words;
-        }
-        uint32_t at = lo;
-        if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);  // thread-packed bits
-        const uint32_t bp = bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_stride + section, pt.bp_width, at);
-        x = candidate_index(pm, o, bp);
+        x = tile_backtrace_step(cols[k].bw, cols[k - 1], tcols[k - 1], arena, x);
         path_index[k - 1] = x;
     }
 }

@@ -413,40 +413,44 @@ __device__ __forceinline__ void pf_store_bp(uint32_t *arena, uint64_t bp_off, ui
     }
 }
 
+// stage column k of the chain (tables, slots, scatter tables; the chain's first column also gets the row it reads)
+__device__ __forceinline__ void pf_stage_column(PedFusedCol &C, const PedFusedArgs &a, uint32_t c, uint32_t k, uint32_t k0, uint32_t k1,
+                                                uint32_t *M, uint8_t *A, uint32_t tid) {
+    const ColMeta &m = a.cols[k];  // global (L1 / L2): every staging thread reads what it needs itself
+    const uint32_t *group = a.fn_group + m.grp_off;
+    if (tid < PF_SLOTS * 32) pf_stage_table_run(C, m, tid, a.fn_delta, group);
+    else if (tid < PF_SLOTS * 32 + PF_SLOTS) pf_stage_slot(C, m, tid - PF_SLOTS * 32, a.fn_c0, a.fn_delta, group);
+    else if (tid >= 576 && tid < 576 + sizeof(ColMeta) / 4) ((uint32_t *)&C.m)[tid - 576] = ((const uint32_t *)&m)[tid - 576];
+    else if (tid == 640) {
+        C.drop = ~m.keep & low_mask(m.a);
+        C.rc_next = k + 1 < k1 ? a.cols[k + 1].rc : 0u;
+    } else if (tid == 641 && k == k0) {  // the row the chain's first column reads (row 0 is its own swizzle image)
+        uint32_t invec[PF_T];
+        for (uint32_t j = 0; j < PF_T; ++j) invec[j] = a.unit ? (j == 0 ? 0u : UMAX) : a.in_vecs[(size_t)c * PF_T + j];
+        pf_first_row(m, invec, M, A);
+    }
+    if (tid >= 512) pf_stage_pdep(C, m, tid - 512);
+}
+
 __global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFusedArgs a) {
     extern __shared__ __align__(16) unsigned char pf_raw[];
     PedFusedCol &C = *reinterpret_cast<PedFusedCol *>(pf_raw);
-    uint32_t *M = reinterpret_cast<uint32_t *>(pf_raw + PF_COL_BYTES);  // transition minima of the previous column [2^bw][4]
+    uint32_t *M = reinterpret_cast<uint32_t *>(pf_raw + PF_COL_BYTES);  // transition minima of the previous column [2^bw][4], rows swizzled
     uint32_t *R = M + PF_MAX_ENT;                                       // raw values of the current column [2^f][4]
     uint8_t *A = reinterpret_cast<uint8_t *>(R + PF_MAX_ENT);           // argmins belonging to M
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(R + PF_MAX_ENT / 2);  // small columns only (< 4096 entries)
     const uint32_t tid = threadIdx.x, c = blockIdx.x;
     const uint32_t k0 = a.chain_begin[c], k1 = a.chain_begin[c + 1];
     const bool write_bp = !a.unit;
+    pf_stage_column(C, a, c, k0, k0, k1, M, A, tid);
     for (uint32_t k = k0; k < k1; ++k) {
-        __syncthreads();  // column k - 1 complete: C may be overwritten, M / A hold its transition minima
-        if (tid < sizeof(ColMeta) / 4) ((uint32_t *)&C.m)[tid] = ((const uint32_t *)&a.cols[k])[tid];
-        __syncthreads();
-        {
-            const ColMeta &m = C.m;
-            if (tid < PF_SLOTS) pf_stage_slot(C, tid, a.fn_c0, a.fn_delta, a.fn_group + m.grp_off);
-            else if (tid == 32) {
-                C.drop = ~m.keep & low_mask(m.a);
-                C.rc_next = k + 1 < k1 ? a.cols[k + 1].rc : 0u;
-            } else if (tid >= 64 && tid < 64 + 2 * TAB_SIZE) pf_stage_pdep(C, tid - 64);
-            else if (tid == 1023 && k == k0) {  // the row the chain's first column reads
-                uint32_t invec[PF_T];
-                for (uint32_t j = 0; j < PF_T; ++j) invec[j] = a.unit ? (j == 0 ? 0u : UMAX) : a.in_vecs[(size_t)c * PF_T + j];
-                pf_first_row(m, invec, M, A);
-            }
-        }
-        __syncthreads();
-        if (tid < PF_SLOTS * 32) pf_stage_table_run(C, tid);
+        __syncthreads();  // column k staged; M / A hold the transition minima of column k - 1
         const uint32_t f = C.m.f, d = C.m.d, nout = 1u << f, nent = nout * PF_T;
         const uint32_t lc = pf_lane_bits(f, d), per = 1u << (d - lc), items = nout << lc;
-        if (lc)
+        if (lc) {
             for (uint32_t e = tid; e < nent; e += PF_THREADS) keys[e] = KEY_INF;
-        __syncthreads();
+            __syncthreads();
+        }
         // ---- phase A: candidates
         for (uint32_t base = 0; base < items; base += PF_THREADS) {
             const uint32_t item = base + tid;
@@ -466,7 +470,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFused
                 if (write_bp) {
                     uint32_t v[PF_T] = {0, 0, 0, 0};
                     if (valid)
-                        for (uint32_t t = 0; t < PF_T; ++t) v[t] = pf_backpointer(C, A, o, t, q.val[t], q.r[t]) & low_mask(d + 2);
+                        for (uint32_t t = 0; t < PF_T; ++t) v[t] = pf_backpointer(A, t, q.val[t], q.r[t], q.b[t]) & low_mask(d + 2);
                     pf_store_bp(a.arena, C.m.bp_off, C.m.bp_width, o, v, valid);
                 }
             }
@@ -479,43 +483,60 @@ __global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFused
                 const unsigned long long key = valid ? keys[e] : KEY_INF;
                 const uint32_t val = (uint32_t)(key >> 32);
                 uint32_t bp = 0;
-                if (valid && write_bp) bp = pf_backpointer(C, A, e >> 2, e & 3u, val, (uint32_t)key) & low_mask(d + 2);
-                __syncwarp();
-                if (valid) R[e] = val;
+                if (valid && write_bp) bp = pf_backpointer_of_key(C, A, e >> 2, e & 3u, val, (uint32_t)key) & low_mask(d + 2);
                 if (write_bp) bp_store_warp(a.arena, C.m.bp_off, C.m.bp_width, e, bp, valid);
             }
+            __syncthreads();  // every key consumed before R (which the key array overlaps) is written
+            for (uint32_t e = tid; e < nent; e += PF_THREADS) {
+                const uint32_t val = (uint32_t)(keys[e] >> 32);
+                __syncwarp();
+                R[e] = val;  // nent < 4096: R[0 .. nent) lies below the key array (R + 8192 words)
+            }
         }
-        __syncthreads();
-        // ---- phase B: what the next column reads
+        const uint32_t rc_next = C.rc_next;
+        __syncthreads();  // R complete, C / M / A no longer read
+        // ---- phase B: what the next column reads; and the next column's tables (disjoint memory)
         if (k + 1 < k1) {
-            const uint32_t rc_next = C.rc_next;
             for (uint32_t o = tid; o < nout; o += PF_THREADS) {
                 const uint4 r4 = *reinterpret_cast<const uint4 *>(R + (size_t)o * PF_T);
                 const uint32_t row[PF_T] = {r4.x, r4.y, r4.z, r4.w};
                 uint32_t mv[PF_T], arg[PF_T];
 #pragma unroll
                 for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(row, i, rc_next, &arg[i]);
-                *reinterpret_cast<uint4 *>(M + (size_t)o * PF_T) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
-                *reinterpret_cast<uint32_t *>(A + (size_t)o * PF_T) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+                const uint32_t at = pf_swz(o);
+                *reinterpret_cast<uint4 *>(M + (size_t)at * PF_T) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
+                *reinterpret_cast<uint32_t *>(A + (size_t)at * PF_T) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
             }
+            pf_stage_column(C, a, c, k + 1, k0, k1, M, A, tid);
         }
     }
     __syncthreads();
     if (tid < PF_T) a.out_vecs[(size_t)c * PF_T + tid] = R[tid] < PF_INF ? R[tid] : UMAX;  // a chain ends with f == 0
 }
 
-// Pass 1 -> pass 2: chain 0 starts the table (its first column ignores the input: its row IS its output); every other
-// chain's transfer matrix is Mat[u][i] = row[i ^ u].  One thread folds them left to right (min-plus) into the true inputs.
-__global__ void ped_fused_prefix_kernel(const uint32_t *__restrict__ rows, uint32_t n_chains, uint32_t *__restrict__ in_vecs) {
-    if (blockIdx.x || threadIdx.x) return;
+// Pass 1 -> pass 2.  Every chain's transfer matrix is Mat[u][i] = row[i ^ u] (ped_fused.h); a chain that starts the table
+// ignores its input (its row IS its output).  Folded left to right in min-plus arithmetic:
+//   matrix == nullptr (one thread): every chain's true input vector -> in_vecs; the first chain's input is `in_vec`
+//     (a segment that continues a table, whmec_segment_sweep) or irrelevant (the table starts here);
+//   matrix != nullptr (4 threads): thread u folds e_u through all chains -> row u of the segment's own transfer matrix
+//     (whmec_segment_transfer); nothing else is written.
+__global__ void ped_fused_prefix_kernel(const uint32_t *__restrict__ rows, uint32_t n_chains, const uint32_t *__restrict__ in_vec,
+                                        uint32_t continues, uint32_t *__restrict__ in_vecs, uint32_t *__restrict__ matrix) {
+    const uint32_t u0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u0 >= (matrix ? PF_T : 1u)) return;
     uint32_t in[PF_T], out[PF_T];
-    for (uint32_t i = 0; i < PF_T; ++i) {
-        in[i] = rows[i];
-        in_vecs[i] = 0;  // unused: the table's first column ignores its input
+    uint32_t c_first = 0;
+    if (continues) {
+        for (uint32_t i = 0; i < PF_T; ++i) in[i] = matrix ? (i == u0 ? 0u : UMAX) : in_vec[i];
+    } else {
+        for (uint32_t i = 0; i < PF_T; ++i) in[i] = rows[i];  // the table starts here: chain 0's row is its true output
+        if (!matrix)
+            for (uint32_t i = 0; i < PF_T; ++i) in_vecs[i] = 0;  // (ignored by the table's first column)
+        c_first = 1;
     }
-    for (uint32_t c = 1; c < n_chains; ++c) {
+    for (uint32_t c = c_first; c < n_chains; ++c) {
         for (uint32_t i = 0; i < PF_T; ++i) {
-            in_vecs[(size_t)c * PF_T + i] = in[i];
+            if (!matrix) in_vecs[(size_t)c * PF_T + i] = in[i];
             out[i] = UMAX;
         }
         const uint32_t *row = rows + (size_t)c * PF_T;
@@ -528,6 +549,8 @@ __global__ void ped_fused_prefix_kernel(const uint32_t *__restrict__ rows, uint3
         }
         for (uint32_t i = 0; i < PF_T; ++i) in[i] = out[i];
     }
+    if (matrix)
+        for (uint32_t i = 0; i < PF_T; ++i) matrix[(size_t)u0 * PF_T + i] = in[i];
 }
 
 // pass 1 -> pass 2: the T x T transfer matrices of the chains, folded left to right in min-plus
@@ -894,7 +917,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         bool fused_ok = false;
         {
             const char *pf = std::getenv("WHMEC_PED_FUSED");
-            fused_ok = !(pf && pf[0] == '0') && pk.T == PF_T && C >= 2 && !segment && pk.safe31 && !(seq && seq[0] == '1');
+            fused_ok = !(pf && pf[0] == '0') && pk.T == PF_T && (C >= 2 || segment) && pk.safe31 && !(seq && seq[0] == '1' && !segment);
             for (uint32_t k = 0; k < n && fused_ok; ++k) fused_ok = pf_column_ok(pk.cols[k], pk.fn_group.data() + pk.cols[k].grp_off);
         }
         if (fused_ok) {
@@ -1045,20 +1068,33 @@ int ped_prefix(whmec_plan *pl, const uint32_t *d_in_vec, uint32_t &launches, std
     return WHMEC_OK;
 }
 
-// three launches for the whole table: unit input of every chain, prefix, true inputs
-int ped_fused_sweep(whmec_plan *pl, std::string &msg) {
-    const Packed &pk = pl->pk;
-    const uint32_t C = (uint32_t)pk.chain_begin.size() - 1;
-    PedFusedArgs a{pl->d_cols.p, pl->d_chain_begin.p, pl->d_fn_c0.p, pl->d_fn_group.p, pl->d_fn_delta.p, pl->d_arena.p,
-                   pl->d_chain_in.p, pl->d_chain_rows.p, 1u};
-    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(a);
-    ped_fused_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_chain_rows.p, C, pl->d_chain_in.p);
-    a.unit = 0;
-    a.out_vecs = pl->d_chain_out.p;
-    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(a);
+// the fused sweep in pieces: pass 1 (unit input e_0 of every chain, values only), prefix, pass 2 (true inputs, back-pointers)
+PedFusedArgs ped_fused_args(whmec_plan *pl, bool unit) {
+    return PedFusedArgs{pl->d_cols.p, pl->d_chain_begin.p, pl->d_fn_c0.p, pl->d_fn_group.p, pl->d_fn_delta.p, pl->d_arena.p,
+                        pl->d_chain_in.p, unit ? pl->d_chain_rows.p : pl->d_chain_out.p, unit ? 1u : 0u};
+}
+
+int ped_fused_pass(whmec_plan *pl, bool unit, std::string &msg) {
+    const uint32_t C = (uint32_t)pl->pk.chain_begin.size() - 1;
+    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(ped_fused_args(pl, unit));
     CUDA_TRY(cudaGetLastError());
-    pl->stats.kernel_launches = 3;
     return WHMEC_OK;
+}
+
+int ped_fused_prefix(whmec_plan *pl, const uint32_t *d_in_vec, uint32_t *d_matrix, std::string &msg) {
+    const uint32_t C = (uint32_t)pl->pk.chain_begin.size() - 1;
+    ped_fused_prefix_kernel<<<1, 32, 0, pl->stream>>>(pl->d_chain_rows.p, C, d_in_vec, pl->segment == 2, pl->d_chain_in.p, d_matrix);
+    CUDA_TRY(cudaGetLastError());
+    return WHMEC_OK;
+}
+
+// three launches for the whole table
+int ped_fused_sweep(whmec_plan *pl, std::string &msg) {
+    int rc = ped_fused_pass(pl, true, msg);
+    if (rc == WHMEC_OK) rc = ped_fused_prefix(pl, nullptr, nullptr, msg);
+    if (rc == WHMEC_OK) rc = ped_fused_pass(pl, false, msg);
+    pl->stats.kernel_launches = 3;
+    return rc;
 }
 
 int ped_batched_sweep(whmec_plan *pl, std::string &msg) {
@@ -1256,11 +1292,18 @@ int segment_transfer_impl(whmec_plan *pl, uint32_t *matrix, std::string &msg) {
     CUDA_TRY(cudaSetDevice(pl->device));
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     uint32_t launches = 0;
-    rc = ped_pass(pl, 0, launches, msg);
-    if (rc != WHMEC_OK) return rc;
-    ped_prefix_kernel<<<(pk.T + 31) / 32, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, pk.T, C, pl->d_chain_len.p, nullptr,
-                                                                pl->segment == 2, pl->d_matrix.p);
-    ++launches;
+    if (pl->use_ped_fused) {
+        rc = ped_fused_pass(pl, true, msg);
+        if (rc == WHMEC_OK) rc = ped_fused_prefix(pl, nullptr, pl->d_matrix.p, msg);
+        if (rc != WHMEC_OK) return rc;
+        launches = 2;
+    } else {
+        rc = ped_pass(pl, 0, launches, msg);
+        if (rc != WHMEC_OK) return rc;
+        ped_prefix_kernel<<<(pk.T + 31) / 32, 32, 0, pl->stream>>>(pl->d_ped_vals.p, pl->ped_max_ent, pk.T, C, pl->d_chain_len.p, nullptr,
+                                                                    pl->segment == 2, pl->d_matrix.p);
+        ++launches;
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(matrix, pl->d_matrix.p, (size_t)pk.T * pk.T * 4, cudaMemcpyDeviceToHost, pl->stream));
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
@@ -1287,8 +1330,14 @@ int segment_sweep_impl(whmec_plan *pl, const uint32_t *in_vec, uint32_t *out_vec
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     if (in_vec) CUDA_TRY(cudaMemcpyAsync(pl->d_in_vec.p, in_vec, (size_t)T * 4, cudaMemcpyHostToDevice, pl->stream));
     uint32_t launches = 0;
-    rc = ped_prefix(pl, in_vec ? pl->d_in_vec.p : nullptr, launches, msg);
-    if (rc == WHMEC_OK) rc = ped_pass(pl, 1, launches, msg);
+    if (pl->use_ped_fused) {
+        rc = ped_fused_prefix(pl, in_vec ? pl->d_in_vec.p : nullptr, nullptr, msg);
+        if (rc == WHMEC_OK) rc = ped_fused_pass(pl, false, msg);
+        launches = 2;
+    } else {
+        rc = ped_prefix(pl, in_vec ? pl->d_in_vec.p : nullptr, launches, msg);
+        if (rc == WHMEC_OK) rc = ped_pass(pl, 1, launches, msg);
+    }
     if (rc != WHMEC_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(out_vec, pl->d_last_vals, (size_t)T * 4, cudaMemcpyDeviceToHost, pl->stream));
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));

@@ -383,3 +383,33 @@ def genotyping_problem(
         gt=None,
         gl=gl,
     )
+
+
+def to_objects(prob: FlatProblem):
+    """The container objects a `whatshap phase` run would hand to `PedigreeDPTable` for this flat problem:
+    (ReadSet, recombcost list, Pedigree).  Trusted genotypes only (the generators above).  Used by bench.py to time the
+    object-level call `PedigreeDPTable(readset, recombcost, pedigree)` + `get_super_reads()`."""
+    from .core import Genotype, NumericSampleIds, Pedigree, Read, ReadSet
+
+    positions = prob.positions.tolist()
+    rs = ReadSet()
+    off = prob.read_off.astype(np.int64)
+    cols, alleles, phreds = prob.ent_col, prob.ent_allele.tolist(), prob.ent_phred.tolist()
+    pos_of = prob.positions[cols].tolist()
+    reads = []
+    for r in range(prob.n_reads):
+        read = Read("r%07d" % r, 60, 0, int(prob.read_ind[r]))
+        a, b = int(off[r]), int(off[r + 1])
+        read._pos, read._allele, read._quality = pos_of[a:b], alleles[a:b], phreds[a:b]
+        reads.append(read)
+    rs._reads = reads  # already in ReadSet order (sorted by first position)
+    ids = NumericSampleIds()
+    ped = Pedigree(ids)
+    gts = [Genotype([0, 0]), Genotype([0, 1]), Genotype([1, 1])]
+    for i in range(prob.n_ind):
+        ids[i]
+        ped.add_individual(i, [gts[g] for g in prob.gt[i].tolist()])
+    tr = prob.trios.tolist()
+    for t in range(prob.n_trios):
+        ped.add_relationship(tr[3 * t], tr[3 * t + 1], tr[3 * t + 2])
+    return rs, prob.recombcost.tolist(), ped
