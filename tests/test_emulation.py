@@ -304,11 +304,12 @@ def test_extreme_values_and_pedigree_sizes(emul, checker):
     assert n == 16
 
 
-def test_more_than_thirty_active_reads_is_refused(emul):
+def test_more_than_thirty_two_active_reads_is_refused(emul):
+    """32 active reads is the reference's own limit (graycodes.cpp:12): one more is refused by the packer."""
     from whatshap_b200._abi import Unsupported
 
-    with pytest.raises(Unsupported, match="more than 30 reads are active"):
-        run_column(emul["libwhemul.so"], synth.sliding_window(40, 31, block_len=40, seed=1), 0)
+    with pytest.raises(Unsupported, match="more than 32 reads are active"):
+        run_column(emul["libwhemul.so"], synth.sliding_window(40, 33, block_len=40, seed=1), 0)
 
 
 def test_host_worker_pool_serves_concurrent_callers(emul):

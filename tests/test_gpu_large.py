@@ -62,3 +62,48 @@ def test_pedigree_batched_sweep_equals_sequential_sweep(gpu, monkeypatch):
     assert (st1["path_kind"], st2["path_kind"]) == (3, 2)
     assert batched.same_as(sequential), batched.diff(sequential)
     assert st1["kernel_launches"] < st2["kernel_launches"] / 2
+
+
+@pytest.mark.parametrize("name,cols,block", [("many chains", 3000, 500), ("one chain", 400, 400)])
+def test_memory_bounded_sweep_equals_the_resident_one(gpu, monkeypatch, name, cols, block):
+    """Back-pointers that do not fit the arena budget: the launch rounds are cut into segments, the forward sweep keeps a
+    checkpoint of the projection state in front of every segment, the backtrace re-sweeps the earlier segments from their
+    checkpoints (the reference's sqrt(n) checkpointing, pedigreedptable.cpp:103-134,146-173, with large segments).  Same
+    result as with everything resident, for budgets that give 2 ... many segments; an impossible budget is refused."""
+    from whatshap_b200._abi import Unsupported
+
+    prob = synth.sliding_window(cols, 18, block_len=block, seed=cols)
+    monkeypatch.delenv("WHMEC_TILE_ARENA_BUDGET", raising=False)
+    whole, st = gpu.solve(prob)
+    assert st["path_kind"] == 1
+    resident = st["backptr_bytes"]
+    seen = set()
+    for divisor in (1.5, 3, 8, 16):
+        monkeypatch.setenv("WHMEC_TILE_ARENA_BUDGET", str(int(resident / divisor)))  # bytes for the arena; checkpoints come on top
+        got, st2 = gpu.solve(prob)
+        assert got.same_as(whole), (name, divisor, got.diff(whole))
+        assert st2["backptr_bytes"] < resident
+        seen.add(st2["kernel_launches"])
+    assert len(seen) >= 2  # different budgets re-sweep different numbers of rounds
+    monkeypatch.setenv("WHMEC_TILE_ARENA_BUDGET", "4096")
+    with pytest.raises((Unsupported, RuntimeError)):
+        gpu.solve(prob)
+
+
+@pytest.mark.parametrize("cov", [31, 32])
+def test_up_to_thirty_two_active_reads(gpu, monkeypatch, cov):
+    """The reference's own limit (graycodes.cpp:12: 32 reads, 2^32 cells per column).  The CPU reference needs ~3 minutes and
+    48 GB per such column, so the check is internal: the reported optimum is the cost of the reported path, and (coverage 31)
+    the general column kernel -- different device code, 64-bit entry counts -- finds the same solution."""
+    n = cov + 6
+    prob = synth.sliding_window(n, cov, block_len=n, seed=cov)
+    monkeypatch.delenv("WHMEC_FORCE_COLUMN_KERNEL", raising=False)
+    sol, stats = gpu.solve(prob)
+    assert stats["max_active"] == cov and stats["path_kind"] == 1
+    assert sol.cost == synth.het_path_cost(prob, sol.path_index)
+    assert set(np.unique(sol.partition)) <= {0, 1}
+    if cov == 31:
+        monkeypatch.setenv("WHMEC_FORCE_COLUMN_KERNEL", "1")
+        col, st2 = gpu.solve(prob)
+        assert st2["path_kind"] == 2
+        assert col.same_as(sol), col.diff(sol)

@@ -11,6 +11,7 @@ fallback: constructing a `PedigreeDPTable` without the CUDA library or a GPU rai
 from __future__ import annotations
 
 import copy
+from array import array
 from itertools import chain
 from math import comb
 from typing import Dict, Iterable, Iterator, List, Optional, Sequence, Tuple
@@ -57,6 +58,16 @@ class NumericSampleIds:
         self.mapping, self.frozen = state
 
 
+def _typed(values) -> array:
+    """array('q') from a numpy array or a sequence of ints."""
+    out = array("q")
+    if isinstance(values, np.ndarray):
+        out.frombytes(np.ascontiguousarray(values, np.int64).tobytes())
+    else:
+        out.extend(values)
+    return out
+
+
 class Read:
     """A read: metadata plus (position, allele, quality) variants (core.pyx:62-273, src/read.cpp)."""
 
@@ -82,9 +93,11 @@ class Read:
         self._sub_alignment_id = sub_alignment_id or ""
         self._is_supplementary = bool(is_supplementary)
         self._is_reverse = bool(is_reverse)
-        self._pos: List[int] = []
-        self._allele: List[int] = []
-        self._quality: List[int] = []
+        # variants as three typed arrays (array('q')): appended to like lists, read by `_flatten_reads` through the buffer
+        # protocol without a Python object per entry
+        self._pos = array("q")
+        self._allele = array("q")
+        self._quality = array("q")
 
     # -- metadata -------------------------------------------------------------------------
     def _check(self):
@@ -168,9 +181,9 @@ class Read:
         """Sort variants by position; duplicates raise like Read::sortVariants (src/read.cpp:66-75)."""
         self._check()
         order = sorted(range(len(self._pos)), key=self._pos.__getitem__)  # stable, like std::sort on distinct keys
-        self._pos = [self._pos[i] for i in order]
-        self._allele = [self._allele[i] for i in order]
-        self._quality = [self._quality[i] for i in order]
+        self._pos = array("q", [self._pos[i] for i in order])
+        self._allele = array("q", [self._allele[i] for i in order])
+        self._quality = array("q", [self._quality[i] for i in order])
         for i in range(1, len(self._pos)):
             if self._pos[i - 1] == self._pos[i]:
                 raise RuntimeError("Duplicate variant in read {} at position {}".format(self._name, self._pos[i]))
@@ -193,7 +206,7 @@ class Read:
         r = Read.__new__(Read)
         for slot in Read.__slots__:
             v = getattr(self, slot)
-            setattr(r, slot, list(v) if isinstance(v, list) else v)
+            setattr(r, slot, list(v) if isinstance(v, list) else (array("q", v) if isinstance(v, array) else v))
         return r
 
     def __getstate__(self):
@@ -541,9 +554,9 @@ def _flatten_reads(readset: ReadSet, positions: Optional[Sequence[int]], index_o
     if m and int(lens.min()) == 0:
         raise RuntimeError("No variants present")
     total = int(lens.sum())
-    pos = np.fromiter(chain.from_iterable(r._pos for r in reads), np.int64, count=total)
-    allele = np.fromiter(chain.from_iterable(r._allele for r in reads), np.int64, count=total)
-    quality = np.fromiter(chain.from_iterable(r._quality for r in reads), np.int64, count=total)
+    pos = np.frombuffer(b"".join(r._pos for r in reads), np.int64, count=total)  # the arrays' memory, concatenated in C
+    allele = np.frombuffer(b"".join(r._allele for r in reads), np.int64, count=total)
+    quality = np.frombuffer(b"".join(r._quality for r in reads), np.int64, count=total)
     off = np.zeros(m + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     if m:
@@ -654,15 +667,15 @@ class PedigreeDPTable:
         `superread_1_<k>`, plus the transmission vector (src/pedigreedptable.cpp:344-388)."""
         prob, sol = self._problem, self._solution
         results = []
-        positions = prob.positions.tolist()
+        positions = prob.positions
         for k in range(len(self.pedigree)):
             rs = ReadSet()
-            quality = sol.sr_quality[k].tolist()
+            quality = sol.sr_quality[k]
             for h in range(2):
                 read = Read("superread_{}_{}".format(h, k), -1, -1, self.pedigree.index_to_id(k))
-                read._pos = list(positions)
-                read._allele = sol.sr_allele[k, h].tolist()
-                read._quality = list(quality)
+                read._pos = _typed(positions)
+                read._allele = _typed(sol.sr_allele[k, h])
+                read._quality = _typed(quality)
                 rs.add(read)
             results.append(rs)
         return results, sol.path_tv.tolist()

@@ -16,7 +16,7 @@
 namespace whmec {
 
 constexpr uint32_t UMAX = 0xFFFFFFFFu;  // +infinity of the reference's unsigned arithmetic
-constexpr uint32_t MAX_ACTIVE = 30;     // reference limit is 32 (graycodes.cpp:12); 2^a cells must stay addressable
+constexpr uint32_t MAX_ACTIVE = 32;     // the reference's limit (graycodes.cpp:12, columnindexingscheme.cpp:42-44): a cell index is 32 bits
 constexpr uint32_t MAX_T = 256;         // 4 trios
 constexpr uint32_t FN_STRIDE = 32;      // deltas per cost function
 

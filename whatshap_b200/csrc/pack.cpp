@@ -316,7 +316,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
                 if (na == MAX_ACTIVE) {
                     ch.rc = WHMEC_ERR_UNSUPPORTED;
                     ch.err_col = k;
-                    ch.err = "more than 30 reads are active in one column (coverage too high)";
+                    ch.err = "more than 32 reads are active in one column (coverage too high)";
                     return;
                 }
                 active[na] = next_read;

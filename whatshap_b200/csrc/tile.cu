@@ -583,10 +583,13 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
 // Backtrace: one warp per DP-independent chain.  The walk itself is sequential (the cell of column k - 1 is read through the
 // cell of column k), but the per-column records it needs (ColMeta + TileCol, ~360 bytes) are not: the lanes stage them 16
 // columns at a time into shared memory, lane 0 then walks those 16 columns paying only for the dependent back-pointer loads.
+// seg_lo / seg_hi: the chain's columns whose back-pointers are resident (the whole chain, or its part inside the segment of
+// a memory-bounded sweep; the walk then continues from path_index[hi + 1], written by the segment before).
 constexpr uint32_t BT_CHUNK = 16;
 
 __global__ void __launch_bounds__(32) tile_backtrace_kernel(const ColMeta *__restrict__ cols, const TileCol *__restrict__ tcols,
                                                             const uint32_t *__restrict__ arena, const uint32_t *__restrict__ chain_begin,
+                                                            const uint32_t *__restrict__ seg_lo, const uint32_t *__restrict__ seg_hi,
                                                             uint32_t n_chains, const unsigned long long *__restrict__ chain_keys,
                                                             uint32_t *__restrict__ path_index, uint32_t *__restrict__ result) {
     __shared__ ColMeta s_cols[BT_CHUNK + 1];  // columns lo .. lo + n (the extra one supplies cols[k].bw of the chunk's top step)
@@ -594,13 +597,22 @@ __global__ void __launch_bounds__(32) tile_backtrace_kernel(const ColMeta *__res
     __shared__ uint32_t s_path[BT_CHUNK];
     const uint32_t c = blockIdx.x, lane = threadIdx.x;
     if (c >= n_chains) return;
-    const unsigned long long key = chain_keys[c];
-    const uint32_t k_first = chain_begin[c], k_last = chain_begin[c + 1] - 1;
-    uint32_t r = (uint32_t)key;
-    uint32_t x = r ^ (r >> 1);  // Gray code of the winning rank = canonical index in the last column
-    if (lane == 0) {
-        path_index[k_last] = x;
-        atomicAdd(&result[0], (uint32_t)(key >> 32));  // cost = sum over DP-independent chains
+    const uint32_t k_first = seg_lo[c], k_res = seg_hi[c];
+    if (k_first > k_res) return;  // no column of this chain in the segment
+    const uint32_t chain_last = chain_begin[c + 1] - 1;
+    uint32_t x, k_last;
+    if (k_res == chain_last) {
+        const unsigned long long key = chain_keys[c];
+        const uint32_t r = (uint32_t)key;
+        x = r ^ (r >> 1);  // Gray code of the winning rank = canonical index in the last column
+        k_last = k_res;
+        if (lane == 0) {
+            path_index[k_last] = x;
+            atomicAdd(&result[0], (uint32_t)(key >> 32));  // cost = sum over DP-independent chains
+        }
+    } else {
+        x = path_index[k_res + 1];  // the walk arrives from the columns of the following segment
+        k_last = k_res + 1;
     }
     for (uint32_t hi = k_last; hi > k_first;) {  // steps hi -> hi - 1, ..., lo + 1 -> lo
         const uint32_t lo = hi - k_first > BT_CHUNK ? hi - BT_CHUNK : k_first, n = hi - lo;
@@ -620,8 +632,17 @@ __global__ void __launch_bounds__(32) tile_backtrace_kernel(const ColMeta *__res
     }
 }
 
+struct TileSeg {
+    uint32_t r0, r1;       // rounds [r0, r1)
+    uint64_t words;        // back-pointer words of the segment
+};
+
 struct TileImpl {
     TileSchedule ts;
+    std::vector<TileSeg> segs;          // one segment: everything resident (the usual case)
+    uint32_t *d_ckpt = nullptr;         // projection state before segments 1 .. K-1 (state_words each)
+    uint32_t *d_seg_lo = nullptr, *d_seg_hi = nullptr;  // [segment][chain]: columns of the chain inside the segment (lo > hi: none)
+    uint64_t arena_words = 0;
     ColMeta *d_cols = nullptr;
     TileCol *d_tcols = nullptr;
     Panel *d_panels = nullptr;
@@ -702,20 +723,110 @@ bool TilePlan::plan(const Packed &pk) {
 
 int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::string &msg) {
     TileImpl *I = (TileImpl *)impl;
-    const TileSchedule &ts = I->ts;
-    const size_t free_b = device_available_bytes();
-    const uint64_t need = (ts.state_words + ts.bp_words + 2) * 4 + (uint64_t)pk.n * (sizeof(TileCol) + sizeof(ColMeta)) +
-                          ts.panels.size() * sizeof(Panel);
-    if (need + (512ull << 20) > free_b) {
-        msg = "tile path: state + back-pointer storage exceeds the free HBM of this device";
-        return WHMEC_ERR_UNSUPPORTED;
-    }
+    TileSchedule &ts = I->ts;
     I->n_chains = (uint32_t)pk.chain_begin.size() - 1;
+    const size_t free_b = device_available_bytes();
+    const uint64_t fixed = (ts.state_words + 2) * 4 + (uint64_t)pk.n * (sizeof(TileCol) + sizeof(ColMeta)) + ts.panels.size() * sizeof(Panel) +
+                           (512ull << 20);
+    // Memory-bounded sweep.  The reference bounds its memory by keeping every sqrt(n)-th column and recomputing
+    // (pedigreedptable.cpp:103-134,146-173).  Here the 1-bit back-pointers of ALL columns normally stay resident; when they do
+    // not fit (coverage 25 beyond ~90k columns, coverage 26+), the launch rounds are cut into segments whose back-pointers share
+    // one arena: the forward sweep keeps the projection state in front of every segment (a checkpoint) and the back-pointers of
+    // the last segment; the backtrace walks the last segment, then re-sweeps the one before from its checkpoint, and so on.
+    // The last segment is made as large as fits, so the re-swept fraction is small.  WHMEC_TILE_ARENA_BUDGET (bytes): test hook.
+    uint64_t budget = free_b > fixed ? free_b - fixed : 0;
+    uint64_t arena_override = 0;  // test hook: bytes the ARENA may take (checkpoints are not counted against it)
+    if (const char *e = std::getenv("WHMEC_TILE_ARENA_BUDGET")) arena_override = std::max<uint64_t>(8, std::strtoull(e, nullptr, 10));
+    const size_t n_rounds = ts.round_tiles.size();
+    I->segs.clear();
+    const uint64_t resident_limit = arena_override ? std::min(arena_override, budget) : budget;
+    if ((ts.bp_words + 1) * 4 <= resident_limit || n_rounds <= 1) {
+        if ((ts.bp_words + 1) * 4 > resident_limit) {
+            msg = "tile path: state + back-pointer storage exceeds the free HBM of this device";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
+        I->segs.push_back(TileSeg{0, (uint32_t)n_rounds, ts.bp_words});
+        I->arena_words = ts.bp_words;
+    } else {
+        std::vector<uint64_t> round_words(n_rounds, 0);
+        for (size_t r = 0; r < n_rounds; ++r)
+            for (uint32_t q = ts.round_begin[r]; q < ts.round_begin[r + 1]; ++q) {
+                const Panel &P = ts.panels[q];
+                for (uint32_t k = P.col_begin; k < P.col_end; ++k)
+                    round_words[r] += (uint64_t)ts.cols[k].bp_tile_stride << (ts.cols[k].g - ts.cols[k].half);
+            }
+        bool ok = false;
+        for (uint32_t guess = 2; guess <= n_rounds && !ok; ++guess) {  // `guess` segments -> guess - 1 checkpoints
+            const uint64_t ckpt = (uint64_t)(guess - 1) * ts.state_words * 4;
+            if (ckpt + 4096 >= budget) break;
+            const uint64_t cap = (arena_override ? std::min(arena_override, budget - ckpt) : budget - ckpt) / 4 - 1;  // arena words
+            std::vector<TileSeg> segs;
+            size_t r1 = n_rounds;
+            bool fits = true;
+            while (r1 > 0) {  // greedy from the end: the segment that is swept only once is the largest
+                uint64_t words = 0;
+                size_t r0 = r1;
+                while (r0 > 0 && words + round_words[r0 - 1] <= cap) words += round_words[--r0];
+                if (r0 == r1) {
+                    fits = false;
+                    break;
+                }
+                segs.push_back(TileSeg{(uint32_t)r0, (uint32_t)r1, words});
+                r1 = r0;
+            }
+            if (fits && segs.size() <= guess) {
+                std::reverse(segs.begin(), segs.end());
+                I->segs = segs;
+                ok = true;
+            }
+        }
+        if (!ok) {
+            msg = "tile path: state + back-pointer storage exceeds the free HBM of this device";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
+        // segment-local back-pointer offsets: the columns of a segment are laid out round by round, panel by panel
+        I->arena_words = 0;
+        for (const TileSeg &sg : I->segs) {
+            uint64_t at = 0;
+            for (uint32_t r = sg.r0; r < sg.r1; ++r)
+                for (uint32_t q = ts.round_begin[r]; q < ts.round_begin[r + 1]; ++q) {
+                    const Panel &P = ts.panels[q];
+                    for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
+                        ts.cols[k].bp_off = at;
+                        at += (uint64_t)ts.cols[k].bp_tile_stride << (ts.cols[k].g - ts.cols[k].half);
+                    }
+                }
+            I->arena_words = std::max(I->arena_words, at);
+        }
+        backptr_bytes = I->arena_words * 4;
+    }
+    // columns of every chain inside every segment
+    const size_t K = I->segs.size();
+    std::vector<uint32_t> seg_lo(K * I->n_chains, 1), seg_hi(K * I->n_chains, 0);
+    for (size_t sgi = 0; sgi < K; ++sgi)
+        for (uint32_t r = I->segs[sgi].r0; r < I->segs[sgi].r1; ++r)
+            for (uint32_t q = ts.round_begin[r]; q < ts.round_begin[r + 1]; ++q) {
+                const Panel &P = ts.panels[q];
+                uint32_t &lo = seg_lo[sgi * I->n_chains + P.chain], &hi = seg_hi[sgi * I->n_chains + P.chain];
+                if (lo > hi) {
+                    lo = P.col_begin;
+                    hi = P.col_end - 1;
+                } else {
+                    lo = std::min(lo, P.col_begin);
+                    hi = std::max(hi, P.col_end - 1);
+                }
+            }
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_seg_lo, seg_lo.size() * 4, stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_seg_hi, seg_hi.size() * 4, stream));
+    CUDA_TRY(cudaMemcpyAsync(I->d_seg_lo, seg_lo.data(), seg_lo.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(I->d_seg_hi, seg_hi.data(), seg_hi.size() * 4, cudaMemcpyHostToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));  // seg_lo / seg_hi are stack-local
+    if (K > 1) CUDA_TRY(cudaMallocAsync((void **)&I->d_ckpt, (uint64_t)(K - 1) * (ts.state_words + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_panels, ts.panels.size() * sizeof(Panel), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_state, (ts.state_words + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync((void **)&I->d_arena, (ts.bp_words + 1) * 4, stream));
+    CUDA_TRY(cudaMallocAsync((void **)&I->d_arena, (I->arena_words + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_begin, pk.chain_begin.size() * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_keys, (size_t)I->n_chains * 8, stream));
     auto up = [&](void *dst, const void *src, size_t bytes) {
@@ -770,17 +881,29 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     return WHMEC_OK;
 }
 
-int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
-    TileImpl *I = (TileImpl *)impl;
+namespace {
+// the launch rounds [r0, r1) of a schedule
+void launch_rounds(TileImpl *I, uint32_t r0, uint32_t r1, cudaStream_t stream, uint32_t &launches) {
     const TileSchedule &ts = I->ts;
-    CUDA_TRY(cudaMemsetAsync(I->d_chain_keys, 0xFF, (size_t)I->n_chains * 8, stream));
-    launches = 0;
-    for (size_t r = 0; r + 1 < ts.round_begin.size(); ++r) {
+    for (uint32_t r = r0; r < r1; ++r) {
         const uint32_t p0 = ts.round_begin[r], p1 = ts.round_begin[r + 1];
         const uint32_t grid = std::min<uint32_t>(ts.round_tiles[r], I->n_sm);
         tile_panel_kernel<<<grid, NT, sizeof(TileSmem), stream>>>(I->d_panels + p0, p1 - p0, ts.round_tiles[r], ts.round_tile_log[r], I->d_tcols, I->d_cols,
                                                                                 I->d_state, I->d_arena, I->d_chain_keys);
         ++launches;
+    }
+}
+}  // namespace
+
+int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
+    TileImpl *I = (TileImpl *)impl;
+    const TileSchedule &ts = I->ts;
+    CUDA_TRY(cudaMemsetAsync(I->d_chain_keys, 0xFF, (size_t)I->n_chains * 8, stream));
+    launches = 0;
+    for (size_t sgi = 0; sgi < I->segs.size(); ++sgi) {
+        if (sgi > 0)  // checkpoint: the projection state in front of segment sgi
+            CUDA_TRY(cudaMemcpyAsync(I->d_ckpt + (sgi - 1) * (ts.state_words + 1), I->d_state, (ts.state_words + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+        launch_rounds(I, I->segs[sgi].r0, I->segs[sgi].r1, stream, launches);
     }
     CUDA_TRY(cudaGetLastError());
     return WHMEC_OK;
@@ -788,9 +911,19 @@ int TilePlan::sweep(const Packed &pk, cudaStream_t stream, std::string &msg) {
 
 int TilePlan::backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg) {
     TileImpl *I = (TileImpl *)impl;
+    const TileSchedule &ts = I->ts;
     CUDA_TRY(cudaMemsetAsync(d_result, 0, 16, stream));
-    tile_backtrace_kernel<<<I->n_chains, 32, 0, stream>>>(I->d_cols, I->d_tcols, I->d_arena, I->d_chain_begin,
-                                                                       I->n_chains, I->d_chain_keys, d_path_index, d_result);
+    for (size_t sgi = I->segs.size(); sgi-- > 0;) {
+        if (sgi + 1 < I->segs.size()) {  // its back-pointers were overwritten by the later segments: sweep it again from its checkpoint
+            if (sgi > 0)
+                CUDA_TRY(cudaMemcpyAsync(I->d_state, I->d_ckpt + (sgi - 1) * (ts.state_words + 1), (ts.state_words + 1) * 4, cudaMemcpyDeviceToDevice, stream));
+            uint32_t again = 0;
+            launch_rounds(I, I->segs[sgi].r0, I->segs[sgi].r1, stream, again);
+            launches += again;
+        }
+        tile_backtrace_kernel<<<I->n_chains, 32, 0, stream>>>(I->d_cols, I->d_tcols, I->d_arena, I->d_chain_begin, I->d_seg_lo + sgi * I->n_chains,
+                                                              I->d_seg_hi + sgi * I->n_chains, I->n_chains, I->d_chain_keys, d_path_index, d_result);
+    }
     CUDA_TRY(cudaGetLastError());
     return WHMEC_OK;
 }
@@ -799,7 +932,7 @@ void TilePlan::release(cudaStream_t stream) {
     TileImpl *I = (TileImpl *)impl;
     if (!I) return;
     for (void *q : {(void *)I->d_cols, (void *)I->d_tcols, (void *)I->d_panels, (void *)I->d_state, (void *)I->d_arena,
-                    (void *)I->d_chain_begin, (void *)I->d_chain_keys})
+                    (void *)I->d_chain_begin, (void *)I->d_chain_keys, (void *)I->d_ckpt, (void *)I->d_seg_lo, (void *)I->d_seg_hi})
         if (q) cudaFreeAsync(q, stream);
     delete I;
     impl = nullptr;

@@ -46,7 +46,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     std::vector<uint64_t> chain_state_words(n_chains, 0), chain_bp_words(n_chains, 0), chain_traffic(n_chains, 0);
     std::vector<std::string> chain_why(n_chains);
 
-    // Sets of reads are small (at most 30 reads are active in a column) and are kept as ascending arrays;
+    // Sets of reads are small (at most 32 reads are active in a column) and are kept as ascending arrays;
     // "where does read r sit in the current column / in the tile's local order" are O(1) look-ups in
     // per-chain tables indexed by (read - first read of the chain) and validated by a stamp.
     struct Small {

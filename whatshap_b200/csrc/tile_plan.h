@@ -25,7 +25,7 @@ namespace whmec {
 #endif
 constexpr uint32_t TILE_SMAX = WHMEC_TILE_SMAX;      // log2 entries of a tile's state buffer (2 x 64 KB of shared memory)
 constexpr uint32_t TILE_MMAX = WHMEC_TILE_SMAX + 1;  // log2 cells a tile evaluates per column
-constexpr uint32_t TILE_GMAX = 16;   // log2 tiles per panel
+constexpr uint32_t TILE_GMAX = 18;   // log2 tiles per panel (32 active reads = 14 local + 18 global)
 constexpr uint32_t TILE_KINF = 1u << 30;
 constexpr uint64_t TILE_SAFE_BOUND = 1ull << 28;  // every real cost must stay below this
 
@@ -48,7 +48,7 @@ struct TileCol {            // one column as seen by a tile (device + host)
     uint32_t gmask_out;     // canonical mask (over f_k bits) of the global reads after this column
     uint32_t lmask_col;     // canonical mask (over a_k bits) of the local reads of this column
     int32_t w_local[16];    // signed weight of local bit q:  +phred if allele 0, -phred if allele 1
-    int32_t w_global[16];   // same for the read behind tile-id bit b
+    int32_t w_global[TILE_GMAX];  // same for the read behind tile-id bit b
     uint32_t gabove[16];    // per dropped local bit i: tile-id bits of global reads canonically above it
     uint8_t dpos[16];       // local positions of the dropped bits, ascending
 };

@@ -389,6 +389,8 @@ def to_objects(prob: FlatProblem):
     """The container objects a `whatshap phase` run would hand to `PedigreeDPTable` for this flat problem:
     (ReadSet, recombcost list, Pedigree).  Trusted genotypes only (the generators above).  Used by bench.py to time the
     object-level call `PedigreeDPTable(readset, recombcost, pedigree)` + `get_super_reads()`."""
+    from array import array
+
     from .core import Genotype, NumericSampleIds, Pedigree, Read, ReadSet
 
     positions = prob.positions.tolist()
@@ -400,7 +402,7 @@ def to_objects(prob: FlatProblem):
     for r in range(prob.n_reads):
         read = Read("r%07d" % r, 60, 0, int(prob.read_ind[r]))
         a, b = int(off[r]), int(off[r + 1])
-        read._pos, read._allele, read._quality = pos_of[a:b], alleles[a:b], phreds[a:b]
+        read._pos, read._allele, read._quality = array("q", pos_of[a:b]), array("q", alleles[a:b]), array("q", phreds[a:b])
         reads.append(read)
     rs._reads = reads  # already in ReadSet order (sorted by first position)
     ids = NumericSampleIds()
