@@ -688,7 +688,7 @@ PinnedStage g_stage;
 
 bool pinned_staging_enabled() {
     const char *e = std::getenv("WHMEC_PINNED_STAGING");
-    return !(e && e[0] == '0');  // default since round 2 (B200: 1.5 ms of a 17 MB upload); "0": pageable copies
+    return e && e[0] == '1';  // measured on the B200 (round 2): not faster than the driver's pageable path (h2d 3.0 vs 2.4 ms of a 17 MB upload) -> off
 }
 
 }  // namespace

@@ -487,11 +487,7 @@ __global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFused
                 if (write_bp) bp_store_warp(a.arena, C.m.bp_off, C.m.bp_width, e, bp, valid);
             }
             __syncthreads();  // every key consumed before R (which the key array overlaps) is written
-            for (uint32_t e = tid; e < nent; e += PF_THREADS) {
-                const uint32_t val = (uint32_t)(keys[e] >> 32);
-                __syncwarp();
-                R[e] = val;  // nent < 4096: R[0 .. nent) lies below the key array (R + 8192 words)
-            }
+            for (uint32_t e = tid; e < nent; e += PF_THREADS) R[e] = (uint32_t)(keys[e] >> 32);  // nent < 4096: R[0 .. nent) lies below the key array (R + 8192 words)
         }
         const uint32_t rc_next = C.rc_next;
         __syncthreads();  // R complete, C / M / A no longer read
