@@ -319,10 +319,13 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         elif prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or no columns: one GPU
             rows = [_wire.join([np.array([MODE["single"]], np.int64).view(np.uint8)])] * world
         else:
-            shares = assign_blocks(block_work(prob, blocks), world)
+            # every rank gets ONE sub-problem: a contiguous run of whole blocks with about 1 / world of the DP cells (one
+            # whmec_solve per rank sweeps all its chains together; block-by-block calls would be launch-latency bound)
+            runs = contiguous_shares(block_work(prob, blocks), world)
+            spans = [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in runs]
             rows = [_wire.join([np.array([MODE["blocks"]], np.int64).view(np.uint8)] +
-                               [_wire.encode_problem(prob.slice_columns(*blocks[b]), tag=b, lo=blocks[b][0]) for b in share])
-                    for share in shares]
+                               ([_wire.encode_problem(prob.slice_columns(*sp), tag=r, lo=sp[0])] if sp is not None else []))
+                    for r, sp in enumerate(spans)]
     t1 = time.perf_counter()
     pieces = _wire.separate(comm.scatter_rows(rows))
     head = pieces[0].view(np.int64)
@@ -349,24 +352,25 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
     mine, err = [], None
     try:
         for row in pieces[1:]:
-            sub, b, _ = _wire.decode_problem(row)
-            mine.append(_wire.encode_solution(solver(sub), tag=b))
+            sub, r, lo = _wire.decode_problem(row)
+            mine.append(_wire.encode_solution(solver(sub), tag=lo, extra=np.array([sub.n_cols], np.uint32)))
     except Exception as e:  # noqa: BLE001 - e.g. more active reads than supported, CUDA out of memory
         err = e
     t3 = time.perf_counter()
     _wire.raise_first_error(comm.all_status(*_wire.status_of(err)), "solve")
-    gathered = comm.gather_rows(_wire.join(mine))  # per-block super-reads back to rank 0
+    gathered = comm.gather_rows(_wire.join(mine))  # per-rank super-reads back to rank 0
     t4 = time.perf_counter()
     if timings is not None:
         timings.update({"solve": (t3 - t2) * 1e3, "gather": (t4 - t3) * 1e3})
     if rank != 0:
         return None
-    by_block = {}
+    parts = []
     for row in gathered:
         for enc in _wire.separate(row):
-            sol, b, _ = _wire.decode_solution(enc)
-            by_block[b] = sol
-    out = merge_block_solutions(prob, blocks, [by_block[b] for b in range(len(blocks))])
+            sol, lo, extra = _wire.decode_solution(enc)
+            parts.append(((lo, lo + int(extra[0])), sol))
+    parts.sort(key=lambda p: p[0][0])
+    out = merge_block_solutions(prob, [sp for sp, _ in parts], [sol for _, sol in parts])
     if timings is not None:
         timings["merge"] = (time.perf_counter() - t4) * 1e3
     return out
