@@ -4,11 +4,11 @@ TAG=${1:-r02f}
 set -x
 mkdir -p gpurun_out
 timeout -k 5 150 python scripts/_san2.py 2>&1 | tail -4 | tee gpurun_out/${TAG}_trio_smoke.log
-timeout -k 5 420 python -m pytest tests/test_gpu_configs.py tests/test_gpu_large.py tests/test_gpu_sharded.py -q -m gpu --timeout 200 --timeout-method=thread -p no:cacheprovider -x -k "trio or pedigree or memory_bounded or thirty_two or two_ranks or segments" 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_new.log
+timeout -k 5 900 python -m pytest tests -q -m gpu --timeout 200 --timeout-method=thread -p no:cacheprovider -x 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_new.log
 WHMEC_TIMING=1 timeout -k 5 200 python bench.py --workload cfg5 --steps 5 --warmup 3 > gpurun_out/${TAG}_bench_cfg5.json 2> gpurun_out/${TAG}_bench_cfg5_timing.err
 timeout -k 5 200 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_cfg3.json 2> gpurun_out/${TAG}_bench_cfg3.err
-timeout -k 5 300 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/_san2.py 2>&1 | tail -6 | tee gpurun_out/${TAG}_racecheck_ped.log
-timeout -k 5 300 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/_san.py 2>&1 | tail -8 | tee gpurun_out/${TAG}_memcheck.log
+
+
 timeout -k 5 400 ncu --set full --clock-control none --import-source on -k regex:ped_fused_kernel -s 2 -c 2 -o gpurun_out/${TAG}_pedfused_cfg5 python bench.py --workload cfg5 --steps 2 --warmup 1 --no-cpu-baseline > /dev/null 2>&1
 for f in gpurun_out/${TAG}_bench_*.json; do
   python - "$f" <<'PY'

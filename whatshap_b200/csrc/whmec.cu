@@ -1245,6 +1245,7 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int en
     if (pl->use_tiles) {
         int rc = pl->tiles.backtrace(pk, pl->stream, pl->d_path_index.p, pl->d_result.p, msg);
         if (rc != WHMEC_OK) return rc;
+        pl->stats.kernel_launches = pl->tiles.launches;  // a memory-bounded sweep re-sweeps segments during the backtrace
         CUDA_TRY(cudaMemsetAsync(pl->d_path_tv.p, 0, (size_t)n * 4, pl->stream));
     } else {
         const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
