@@ -40,6 +40,8 @@ struct PedFusedCol {                    // one column, staged in shared memory
     alignas(16) uint32_t c0[PF_SLOTS];
     alignas(16) int32_t sd[PF_MAX_A][2][PF_SLOTS];  // signed step of slot s when bit `pos` becomes 1 / 0:  +delta / -delta
     uint32_t pd_lo[TAB_SIZE], pd_hi[TAB_SIZE];
+    uint32_t pd_drop[32];               // scatter of a d-bit pattern into the dropped positions (d <= 5; else computed)
+    uint32_t above[8];                  // per dropped position i (i < 8): the OUTPUT-index bits whose kept position lies above it
     alignas(16) int32_t tab[2][TAB_SIZE][PF_ROW];   // [half][byte value][slot]: sum of the slot's deltas over cell bits 0..7 / 8..15
 };
 
@@ -50,7 +52,13 @@ struct PedQuad {
 // Row b of the previous column's transition minima sits at row pf_swz(b): within a warp the candidates of neighbouring outputs
 // share their low index bits (the reads that end are the oldest = lowest bits), the swizzle moves the bits that do differ into
 // the bank-selecting position (128-bit row loads: 8 rows per wavefront).
-WHMEC_HD uint32_t pf_swz(uint32_t b) { return b ^ ((b >> 3) & 7u); }
+// The low bits in question are gray(r) ^ cg(o), and cg(o) flips bit 2 with the parity of o (three reads end at the three lowest
+// positions: the steady state of a trio) -- so the XOR term is (o0, o1, o0 ^ o1), which together with that parity flip is a
+// bijection of the 8 neighbours (o0, o1, o2); a plain (o0, o1, o2) term would collide pairwise.
+WHMEC_HD uint32_t pf_swz(uint32_t b) {
+    const uint32_t h = b >> 3;
+    return b ^ ((h & 3u) | (((h ^ (h >> 1)) & 1u) << 2));
+}
 
 // Is the fused sweep applicable to column `m` with the given function groups?
 WHMEC_HD bool pf_column_ok(const ColMeta &m, const uint32_t *group /* [T + 1] */) {
@@ -76,9 +84,10 @@ WHMEC_HD void pf_stage_slot(PedFusedCol &C, const ColMeta &m, uint32_t s, const 
     }
 }
 
-// 16 consecutive entries of one byte table of slot s (subset sums, one add per entry): run = s * 32 + half * 16 + hi4.
+// 16 consecutive entries of one byte table of slot s (subset sums, one add per entry): run = (hi4 * 2 + half) * 16 + s
+// (neighbouring lanes fill neighbouring slots of the same rows: conflict-free stores).
 WHMEC_HD void pf_stage_table_run(PedFusedCol &C, const ColMeta &m, uint32_t run, const int32_t *fn_delta, const uint32_t *group) {
-    const uint32_t s = run >> 5, half = (run >> 4) & 1u, hi4 = run & 15u;
+    const uint32_t s = run & 15u, half = (run >> 4) & 1u, hi4 = run >> 5;
     const uint32_t t = s / PF_GS, q = s % PF_GS;
     const bool used = group[t] + q < group[t + 1];
     const int32_t *dl = fn_delta + (size_t)(m.fn_off + group[t] + q) * FN_STRIDE + half * TAB_BITS;
@@ -90,13 +99,35 @@ WHMEC_HD void pf_stage_table_run(PedFusedCol &C, const ColMeta &m, uint32_t run,
     uint32_t sub[16];
     sub[0] = base;
     for (uint32_t i = 1; i < 16; ++i) sub[i] = sub[i & (i - 1)] + d[ctz32(i)];
-    for (uint32_t i = 0; i < 16; ++i) C.tab[half][16 * hi4 + i][s] = (int32_t)sub[i];
+    for (uint32_t i = 0; i < 16; ++i) {
+        const uint32_t idx = 16 * hi4 + i;
+        C.tab[half][half ? idx : pf_swz(idx)][s] = (int32_t)sub[i];  // low table: rows swizzled like the rows of M (same index bits)
+    }
 }
 
 WHMEC_HD void pf_stage_pdep(PedFusedCol &C, const ColMeta &m, uint32_t v /* < 2 * TAB_SIZE */) {
     const uint32_t keep_lo = lowest_set_bits(m.keep, TAB_BITS), keep_hi = lowest_set_bits(m.keep & ~keep_lo, TAB_BITS);
     if (v < TAB_SIZE) C.pd_lo[v] = pdep32(v, keep_lo);
     else C.pd_hi[v - TAB_SIZE] = pdep32(v - TAB_SIZE, keep_hi);
+    const uint32_t drop = ~m.keep & low_mask(m.a);
+    if (v < 32) C.pd_drop[v] = pdep32(v, drop);
+    else if (v < 40) {
+        const uint32_t i = v - 32;
+        C.above[i] = i < m.d ? pext32(m.keep & ~low_mask(m.dpos[i] + 1u), m.keep) : 0u;  // kept positions above dropped position i, as output bits
+    }
+}
+
+// scatter of a candidate's dropped-bit pattern
+WHMEC_HD uint32_t pf_scatter_drop(const PedFusedCol &C, uint32_t pattern) {
+    return C.m.d <= 5 ? C.pd_drop[pattern] : pdep32(pattern, C.drop);
+}
+
+// Gray-rank offset of output o (common.h: rank_offset): bit i = parity of the kept bits above the i-th dropped position
+WHMEC_HD uint32_t pf_rank_offset(const PedFusedCol &C, uint32_t o, uint32_t kept) {
+    if (C.m.d > 8) return rank_offset(C.m, kept);
+    uint32_t c = 0;
+    for (uint32_t i = 0; i < C.m.d; ++i) c |= (popc32(o & C.above[i]) & 1u) << i;
+    return c ^ (c >> 1);
 }
 
 // Candidates r in [r0, r1) of projection entry `o`, all four transmission values: per value the smallest
@@ -105,11 +136,11 @@ WHMEC_HD void pf_stage_pdep(PedFusedCol &C, const ColMeta &m, uint32_t v /* < 2 
 WHMEC_HD void pf_walk(const PedFusedCol &C, const uint32_t *__restrict__ M, uint32_t o, uint32_t r0, uint32_t r1, PedQuad &out) {
     const ColMeta &m = C.m;
     const uint32_t kept = C.pd_lo[o & (TAB_SIZE - 1)] | C.pd_hi[(o >> TAB_BITS) & (TAB_SIZE - 1)];
-    const uint32_t cg = rank_offset(m, kept);
-    uint32_t x = kept | pdep32((r0 ^ (r0 >> 1)) ^ cg, C.drop);
+    const uint32_t cg = pf_rank_offset(C, o, kept);
+    uint32_t x = kept | pf_scatter_drop(C, (r0 ^ (r0 >> 1)) ^ cg);
     uint32_t cost[PF_SLOTS];
     {
-        const int32_t *lo = C.tab[0][x & (TAB_SIZE - 1)], *hi = C.tab[1][(x >> TAB_BITS) & (TAB_SIZE - 1)];
+        const int32_t *lo = C.tab[0][pf_swz(x & (TAB_SIZE - 1))], *hi = C.tab[1][(x >> TAB_BITS) & (TAB_SIZE - 1)];
 #pragma unroll
         for (uint32_t s = 0; s < PF_SLOTS; ++s) cost[s] = C.c0[s] + (uint32_t)(lo[s] + hi[s]);
     }
@@ -145,7 +176,7 @@ WHMEC_HD void pf_walk(const PedFusedCol &C, const uint32_t *__restrict__ M, uint
     for (uint32_t t = 0; t < PF_T; ++t) {
         out.val[t] = best[t] < PF_INF ? best[t] : PF_INF;
         out.r[t] = br[t];
-        out.b[t] = (kept | pdep32((br[t] ^ (br[t] >> 1)) ^ cg, C.drop)) & bmask;  // index of the winner into M / A
+        out.b[t] = (kept | pf_scatter_drop(C, (br[t] ^ (br[t] >> 1)) ^ cg)) & bmask;  // index of the winner into M / A
     }
 }
 
