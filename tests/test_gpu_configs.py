@@ -29,6 +29,8 @@ SWITCHES = {
 PED_SWITCHES = {
     "default": {},
     "ped_batched": {"WHMEC_PED_FUSED": "0"},
+    "ped_one_cta": {"WHMEC_PED_CLUSTER": "1"},   # default: a cluster of up to 8 CTAs per chain when there are fewer chains than SMs
+    "ped_cluster2": {"WHMEC_PED_CLUSTER": "2"},
     "ped_sequential": {"WHMEC_PED_SEQUENTIAL": "1"},
 }
 ALL_ENV = sorted({k for d in list(SWITCHES.values()) + list(PED_SWITCHES.values()) for k in d})
@@ -96,7 +98,7 @@ def test_trio_shapes(gpu, checker, monkeypatch, key, switch):
     set_switch(monkeypatch, PED_SWITCHES[switch])
     stats = check(gpu, checker, key, TRIO[key])
     assert stats["path_kind"] == (2 if switch == "ped_sequential" else 3), stats
-    if switch == "default":
+    if switch in ("default", "ped_one_cta", "ped_cluster2"):
         assert stats["kernel_launches"] == 3, stats  # the fused trio sweep: unit pass, prefix, true pass
 
 

@@ -6,6 +6,7 @@
 //
 // There is deliberately NO CPU execution path in this library: if CUDA is unavailable every
 // entry point that computes returns WHMEC_ERR_CUDA.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <malloc.h>
 
@@ -510,6 +511,137 @@ __global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_kernel(const PedFused
     if (tid < PF_T) a.out_vecs[(size_t)c * PF_T + tid] = R[tid] < PF_INF ? R[tid] : UMAX;  // a chain ends with f == 0
 }
 
+// ---- the same sweep with a CLUSTER of CTAs per chain (fewer chains than SMs: cfg5 has 40 chains for 148 SMs, a table segment
+// on one of 8 GPUs five).  Every CTA of the cluster holds the whole previous column (transition minima M + argmins A, double
+// buffered) and the column's tables; a large column's outputs are split between the CTAs, and the thread that finishes an
+// output forms its transition minima from registers and writes that row into the NEXT-column buffer of every CTA of the
+// cluster through distributed shared memory.  One cluster barrier per column orders those writes against the next column's
+// reads; columns with fewer than 32 outputs per CTA are computed by every CTA redundantly (no exchange).
+constexpr size_t PF_CLUSTER_SMEM = PF_COL_BYTES + (size_t)PF_MAX_ENT * 2 * (4 + 1);
+constexpr uint32_t PF_MAX_CLUSTER = 8;
+
+__global__ void __launch_bounds__(PF_THREADS, 1) ped_fused_cluster_kernel(const PedFusedArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const uint32_t cs = cluster.num_blocks(), cr = cluster.block_rank();
+    extern __shared__ __align__(16) unsigned char pf_raw[];
+    PedFusedCol &C = *reinterpret_cast<PedFusedCol *>(pf_raw);
+    uint32_t *Mb = reinterpret_cast<uint32_t *>(pf_raw + PF_COL_BYTES);     // [2][PF_MAX_ENT]
+    uint8_t *Ab = reinterpret_cast<uint8_t *>(Mb + 2 * PF_MAX_ENT);          // [2][PF_MAX_ENT]
+    const uint32_t tid = threadIdx.x, c = blockIdx.x / cs;
+    const uint32_t k0 = a.chain_begin[c], k1 = a.chain_begin[c + 1];
+    const bool write_bp = !a.unit;
+    pf_stage_column(C, a, c, k0, k0, k1, Mb, Ab, tid);
+    const uint32_t *lastR = Mb;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t cur = (k - k0) & 1u;
+        const uint32_t *M = Mb + cur * PF_MAX_ENT;
+        const uint8_t *A = Ab + cur * PF_MAX_ENT;
+        uint32_t *Mn = Mb + (cur ^ 1u) * PF_MAX_ENT;
+        uint8_t *An = Ab + (cur ^ 1u) * PF_MAX_ENT;
+        cluster.sync();  // column k staged here; every CTA's rows of column k - 1 have arrived; nobody reads the other buffer any more
+        const uint32_t f = C.m.f, d = C.m.d, nout = 1u << f, nent = nout * PF_T;
+        const uint32_t lc = pf_lane_bits(f, d), per = 1u << (d - lc), items = nout << lc;
+        const uint32_t rc_next = C.rc_next;
+        const bool more = k + 1 < k1;
+        if (lc == 0 && nout >= 32u * cs) {
+            // ---- large column: this CTA's share of the outputs
+            const uint32_t share = ((nout / cs + 31u) / 32u) * 32u;
+            const uint32_t lo = cr * share, hi = lo + share < nout ? lo + share : nout;
+            for (uint32_t base = lo; base < hi; base += PF_THREADS) {
+                const uint32_t o = base + tid;
+                const bool valid = o < hi;
+                PedQuad q;
+                if (valid) pf_walk(C, M, o, 0, per, q);
+                if (write_bp) {
+                    uint32_t v[PF_T] = {0, 0, 0, 0};
+                    if (valid)
+                        for (uint32_t t = 0; t < PF_T; ++t) v[t] = pf_backpointer(A, t, q.val[t], q.r[t], q.b[t]) & low_mask(d + 2);
+                    pf_store_bp(a.arena, C.m.bp_off, C.m.bp_width, o, v, valid);
+                }
+                if (valid && more) {
+                    uint32_t mv[PF_T], arg[PF_T];
+#pragma unroll
+                    for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(q.val, i, rc_next, &arg[i]);
+                    const uint32_t at = pf_swz(o);
+                    const uint4 m4 = make_uint4(mv[0], mv[1], mv[2], mv[3]);
+                    const uint32_t a4 = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+                    uint32_t *mrow = Mn + (size_t)at * PF_T;
+                    uint8_t *arow = An + (size_t)at * PF_T;
+                    for (uint32_t r = 0; r < cs; ++r) {  // the same row in every CTA of the cluster (distributed shared memory)
+                        *reinterpret_cast<uint4 *>(cluster.map_shared_rank(mrow, r)) = m4;
+                        *reinterpret_cast<uint32_t *>(cluster.map_shared_rank(arow, r)) = a4;
+                    }
+                }
+            }
+        } else {
+            // ---- small column (< 4096 entries): every CTA computes all of it; R and the merge keys live in the unused part of
+            // the next-column buffer (rows of the next column: words [0, nent); R: [4096, 8192); keys: [8192, 16384))
+            uint32_t *R = Mn + 4096;
+            unsigned long long *keys = reinterpret_cast<unsigned long long *>(Mn + 8192);
+            lastR = R;
+            const bool bp_here = write_bp && cr == 0;
+            if (lc) {
+                for (uint32_t e = tid; e < nent; e += PF_THREADS) keys[e] = KEY_INF;
+                __syncthreads();
+            }
+            for (uint32_t base = 0; base < items; base += PF_THREADS) {
+                const uint32_t item = base + tid;
+                const bool valid = item < items;
+                PedQuad q;
+                uint32_t o = 0;
+                if (valid) {
+                    o = item & (nout - 1u);
+                    const uint32_t chunk = item >> f;
+                    pf_walk(C, M, o, chunk * per, (chunk + 1) * per, q);
+                }
+                if (lc) {
+                    if (valid)
+                        for (uint32_t t = 0; t < PF_T; ++t) atomicMin(&keys[o * PF_T + t], ((unsigned long long)q.val[t] << 32) | q.r[t]);
+                } else {
+                    if (valid) *reinterpret_cast<uint4 *>(R + (size_t)o * PF_T) = make_uint4(q.val[0], q.val[1], q.val[2], q.val[3]);
+                    if (bp_here) {
+                        uint32_t v[PF_T] = {0, 0, 0, 0};
+                        if (valid)
+                            for (uint32_t t = 0; t < PF_T; ++t) v[t] = pf_backpointer(A, t, q.val[t], q.r[t], q.b[t]) & low_mask(d + 2);
+                        pf_store_bp(a.arena, C.m.bp_off, C.m.bp_width, o, v, valid);
+                    }
+                }
+            }
+            if (lc) {
+                __syncthreads();
+                for (uint32_t base = 0; base < nent; base += PF_THREADS) {
+                    const uint32_t e = base + tid;
+                    const bool valid = e < nent;
+                    const unsigned long long key = valid ? keys[e] : KEY_INF;
+                    const uint32_t val = (uint32_t)(key >> 32);
+                    uint32_t bp = 0;
+                    if (valid && bp_here) bp = pf_backpointer_of_key(C, A, e >> 2, e & 3u, val, (uint32_t)key) & low_mask(d + 2);
+                    if (bp_here) bp_store_warp(a.arena, C.m.bp_off, C.m.bp_width, e, bp, valid);
+                    if (valid) R[e] = val;
+                }
+            }
+            __syncthreads();  // R complete
+            if (more)
+                for (uint32_t o = tid; o < nout; o += PF_THREADS) {
+                    const uint4 r4 = *reinterpret_cast<const uint4 *>(R + (size_t)o * PF_T);
+                    const uint32_t row[PF_T] = {r4.x, r4.y, r4.z, r4.w};
+                    uint32_t mv[PF_T], arg[PF_T];
+#pragma unroll
+                    for (uint32_t i = 0; i < PF_T; ++i) mv[i] = pf_transition(row, i, rc_next, &arg[i]);
+                    const uint32_t at = pf_swz(o);
+                    *reinterpret_cast<uint4 *>(Mn + (size_t)at * PF_T) = make_uint4(mv[0], mv[1], mv[2], mv[3]);
+                    *reinterpret_cast<uint32_t *>(An + (size_t)at * PF_T) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+                }
+        }
+        __syncthreads();  // this CTA no longer reads C
+        if (more) pf_stage_column(C, a, c, k + 1, k0, k1, Mb, Ab, tid);
+    }
+    __syncthreads();
+    if (cr == 0 && tid < PF_T) a.out_vecs[(size_t)c * PF_T + tid] = lastR[tid] < PF_INF ? lastR[tid] : UMAX;  // a chain ends with f == 0
+    cluster.sync();  // no CTA exits while a peer may still write into its shared memory
+}
+
 // Pass 1 -> pass 2.  Every chain's transfer matrix is Mat[u][i] = row[i ^ u] (ped_fused.h); a chain that starts the table
 // ignores its input (its row IS its output).  Folded left to right in min-plus arithmetic:
 //   matrix == nullptr (one thread): every chain's true input vector -> in_vecs; the first chain's input is `in_vec`
@@ -791,6 +923,7 @@ struct whmec_plan {
     DevBuf<uint32_t> d_in_vec, d_matrix, d_bt_exits, d_bt_entries;
     // fused per-chain pedigree sweep (ped_chain_kernel, experimental)
     bool use_ped_fused = false;
+    uint32_t ped_cluster = 1;  // CTAs per chain of the fused pedigree sweep
     DevBuf<uint32_t> d_chain_rows, d_chain_in, d_chain_out;
     uint32_t sweeps_done = 0;
     cudaGraphExec_t graph_exec = nullptr;
@@ -921,6 +1054,19 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
             CUDA_TRY(pl->d_chain_in.alloc((size_t)C * PF_T, pl->stream));
             CUDA_TRY(pl->d_chain_out.alloc((size_t)C * PF_T, pl->stream));
             CUDA_TRY(cudaFuncSetAttribute(ped_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_SMEM));
+            CUDA_TRY(cudaFuncSetAttribute(ped_fused_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PF_CLUSTER_SMEM));
+            {   // fewer chains than SMs: a cluster of 2 / 4 / 8 CTAs per chain (WHMEC_PED_CLUSTER=n forces n, 1 = off)
+                int dev = 0, sms = 148;
+                CUDA_TRY(cudaGetDevice(&dev));
+                CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+                uint32_t cs = 1;
+                while (cs * 2 <= PF_MAX_CLUSTER && (uint64_t)C * cs * 2 <= (uint64_t)sms) cs *= 2;
+                if (const char *e = std::getenv("WHMEC_PED_CLUSTER")) {
+                    const int want = std::atoi(e);
+                    if (want == 1 || want == 2 || want == 4 || want == 8) cs = (uint32_t)want;
+                }
+                pl->ped_cluster = cs;
+            }
             pl->use_ped_fused = true;
             pl->use_ped_batch = true;  // two-pass sweep: the backtrace and the optimum read the chains' final values
             pl->d_last_vals = pl->d_chain_out.p + (size_t)(C - 1) * PF_T;
@@ -1072,7 +1218,23 @@ PedFusedArgs ped_fused_args(whmec_plan *pl, bool unit) {
 
 int ped_fused_pass(whmec_plan *pl, bool unit, std::string &msg) {
     const uint32_t C = (uint32_t)pl->pk.chain_begin.size() - 1;
-    ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(ped_fused_args(pl, unit));
+    if (pl->ped_cluster > 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(C * pl->ped_cluster);
+        cfg.blockDim = dim3(PF_THREADS);
+        cfg.dynamicSmemBytes = PF_CLUSTER_SMEM;
+        cfg.stream = pl->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = pl->ped_cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, ped_fused_cluster_kernel, ped_fused_args(pl, unit)));
+    } else {
+        ped_fused_kernel<<<C, PF_THREADS, PF_SMEM, pl->stream>>>(ped_fused_args(pl, unit));
+    }
     CUDA_TRY(cudaGetLastError());
     return WHMEC_OK;
 }
