@@ -314,8 +314,7 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         if prob.n_trios > 0 and world > 1 and len(blocks) > 1:  # transmission vectors couple the blocks: segments of the table
             ranges = segment_ranges(prob, world)
             flat = np.array([MODE["segments"]] + [x for r in ranges for x in (r if r is not None else (0, 0))], np.int64)
-            rows = [_wire.join([flat.view(np.uint8)] + ([_wire.encode_problem(prob.slice_columns(*r), lo=r[0])] if r is not None else []))
-                    for r in ranges]
+            rows = [_wire.join([flat.view(np.uint8)] + ([enc] if enc is not None else [])) for enc in _wire.encode_problem_slices(prob, ranges)]
         elif prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or no columns: one GPU
             rows = [_wire.join([np.array([MODE["single"]], np.int64).view(np.uint8)])] * world
         else:
@@ -323,9 +322,8 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
             # whmec_solve per rank sweeps all its chains together; block-by-block calls would be launch-latency bound)
             runs = contiguous_shares(block_work(prob, blocks), world)
             spans = [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in runs]
-            rows = [_wire.join([np.array([MODE["blocks"]], np.int64).view(np.uint8)] +
-                               ([_wire.encode_problem(prob.slice_columns(*sp), tag=r, lo=sp[0])] if sp is not None else []))
-                    for r, sp in enumerate(spans)]
+            rows = [_wire.join([np.array([MODE["blocks"]], np.int64).view(np.uint8)] + ([enc] if enc is not None else []))
+                    for enc in _wire.encode_problem_slices(prob, spans)]
     t1 = time.perf_counter()
     pieces = _wire.separate(comm.scatter_rows(rows))
     head = pieces[0].view(np.int64)
