@@ -1074,7 +1074,9 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         } else if (pk.T > 1 && (C >= 2 || segment) && pk.safe31 && !(seq && seq[0] == '1' && !segment)) {
             const uint32_t T = pk.T;
             const uint32_t slots = C * T + C;
-            if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && (uint64_t)C * T <= 65535) {
+            // the batch buffers (values + argmins of every (chain, unit vector) instance) count against the free HBM as well
+            if ((uint64_t)slots * 2 * max_ent * 4 < (8ull << 30) && (uint64_t)C * T <= 65535 &&
+                need + (uint64_t)slots * 2 * max_ent * 5 + (512ull << 20) <= free_b) {
                 std::vector<PedStep> steps;
                 std::vector<uint32_t> clen(C);
                 uint32_t maxlen = 0;
