@@ -59,8 +59,19 @@ WHMEC_HD uint32_t ctz32(uint32_t x) {
 
 WHMEC_HD uint32_t low_mask(uint32_t bits) { return bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u); }
 
-// pdep(v, mask): scatter the low bits of v to the set positions of mask (no hardware pdep on GPUs).
+// pdep(v, mask): scatter the low bits of v to the set positions of mask (no hardware pdep on GPUs).  Masks that are one
+// contiguous run of bits -- the usual case: reads are ordered by their start, the reads that end are the lowest bits and the
+// long-lived ones the highest -- take one shift instead of a loop over the bits (the backtrace walks through these per column).
+WHMEC_HD bool mask_is_one_run(uint32_t mask, uint32_t *shift) {
+    if (mask == 0) return false;
+    const uint32_t s = ctz32(mask), m = mask >> s;
+    *shift = s;
+    return (m & (m + 1u)) == 0;
+}
+
 WHMEC_HD uint32_t pdep32(uint32_t v, uint32_t mask) {
+    uint32_t shift;
+    if (mask_is_one_run(mask, &shift)) return (v << shift) & mask;
     uint32_t out = 0;
     while (mask) {
         uint32_t low = mask & (0u - mask);
@@ -72,6 +83,8 @@ WHMEC_HD uint32_t pdep32(uint32_t v, uint32_t mask) {
 }
 
 WHMEC_HD uint32_t pext32(uint32_t v, uint32_t mask) {
+    uint32_t shift;
+    if (mask_is_one_run(mask, &shift)) return (v & mask) >> shift;
     uint32_t out = 0, o = 0;
     while (mask) {
         uint32_t low = mask & (0u - mask);

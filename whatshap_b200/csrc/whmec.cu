@@ -820,14 +820,61 @@ __device__ __forceinline__ void bt_chain_start(const BtArgs &a, const BtView &bv
     }
 }
 
-__global__ void bt_exits_kernel(const BtArgs a, uint32_t *__restrict__ exits) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+// backtrace_range (dp_device.h) by one warp: the walk is sequential, but the column records it reads are not -- the lanes stage
+// them 16 columns at a time into shared memory, lane 0 walks them paying only for the dependent back-pointer loads.  Returns
+// (on every lane) the transmission value handed to column k_first - 1.
+constexpr uint32_t BTW_CHUNK = 16;
+struct BtWarpSmem {
+    ColMeta cols[BTW_CHUNK + 1];
+    uint32_t x[BTW_CHUNK], tv[BTW_CHUNK];
+};
+
+__device__ __forceinline__ uint32_t backtrace_range_warp(const BtView &v, BtWarpSmem &S, uint32_t k_last, uint32_t k_first, uint32_t x,
+                                                         uint32_t tv, uint32_t prev_tv, uint32_t *path_index, uint32_t *path_tv) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (path_index && lane == 0) {
+        path_index[k_last] = x;
+        path_tv[k_last] = tv;
+    }
+    for (uint32_t hi = k_last; hi > k_first;) {
+        const uint32_t lo = hi - k_first > BTW_CHUNK ? hi - BTW_CHUNK : k_first, n = hi - lo;
+        constexpr uint32_t CW = sizeof(ColMeta) / 4;
+        for (uint32_t w = lane; w < (n + 1) * CW; w += 32) ((uint32_t *)S.cols)[w] = ((const uint32_t *)(v.cols + lo))[w];
+        __syncwarp();
+        if (lane == 0)
+            for (uint32_t k = hi; k > lo; --k) {
+                const uint32_t b = x & low_mask(S.cols[k - lo].bw);
+                const ColMeta &pm = S.cols[k - 1 - lo];
+                const uint32_t bp = bp_load(v.arena, pm.bp_off, pm.bp_width, (uint64_t)b * v.T + prev_tv);
+                uint32_t j;
+                x = backpointer_to_index(pm, v.tb, b, bp, &j);
+                tv = prev_tv;
+                prev_tv = j;
+                S.x[k - 1 - lo] = x;
+                S.tv[k - 1 - lo] = tv;
+            }
+        __syncwarp();
+        if (path_index && lane < n) {
+            path_index[lo + lane] = S.x[lane];
+            path_tv[lo + lane] = S.tv[lane];
+        }
+        __syncwarp();
+        hi = lo;
+    }
+    return __shfl_sync(0xFFFFFFFFu, prev_tv, 0);
+}
+
+// one warp per (chain, entry value)
+__global__ void __launch_bounds__(32) bt_exits_kernel(const BtArgs a, uint32_t *__restrict__ exits) {
+    __shared__ BtWarpSmem S;
+    const uint32_t idx = blockIdx.x;
     if (idx >= a.n_chains * a.T) return;
     const uint32_t c = idx / a.T, u = idx % a.T;
     BtView bv{a.cols, a.arena, a.T, a.tb};
     uint32_t x, tv, ptv, cost;
     bt_chain_start(a, bv, c, u, &x, &tv, &ptv, &cost);
-    exits[idx] = backtrace_range(bv, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, nullptr, nullptr);
+    const uint32_t out = backtrace_range_warp(bv, S, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, nullptr, nullptr);
+    if (threadIdx.x == 0) exits[idx] = out;
 }
 
 __global__ void bt_entries_kernel(const BtArgs a, const uint32_t *__restrict__ exits, uint32_t *__restrict__ entries,
@@ -848,15 +895,17 @@ __global__ void bt_entries_kernel(const BtArgs a, const uint32_t *__restrict__ e
     }
 }
 
-__global__ void bt_paths_kernel(const BtArgs a, const uint32_t *__restrict__ entries, uint32_t *__restrict__ path_index,
-                                uint32_t *__restrict__ path_tv, uint32_t *__restrict__ result) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per chain
+__global__ void __launch_bounds__(32) bt_paths_kernel(const BtArgs a, const uint32_t *__restrict__ entries, uint32_t *__restrict__ path_index,
+                                                      uint32_t *__restrict__ path_tv, uint32_t *__restrict__ result) {
+    __shared__ BtWarpSmem S;
+    const uint32_t c = blockIdx.x;
     if (c >= a.n_chains) return;
     BtView bv{a.cols, a.arena, a.T, a.tb};
     uint32_t x, tv, ptv, cost = 0;
     bt_chain_start(a, bv, c, entries[c], &x, &tv, &ptv, &cost);
-    backtrace_range(bv, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, path_index, path_tv);
-    if (c + 1 == a.n_chains) result[0] = cost;
+    backtrace_range_warp(bv, S, a.chain_begin[c + 1] - 1, a.chain_begin[c], x, tv, ptv, path_index, path_tv);
+    if (c + 1 == a.n_chains && threadIdx.x == 0) result[0] = cost;
 }
 
 // Device buffers come from the device's stream-ordered memory pool with an unlimited release
@@ -1366,7 +1415,7 @@ BtArgs bt_args(const whmec_plan *pl, int entry) {
 int pedigree_exits(whmec_plan *pl, int entry, std::string &msg) {
     const BtArgs a = bt_args(pl, entry);
     const uint32_t threads = a.n_chains * a.T;
-    bt_exits_kernel<<<(threads + 63) / 64, 64, 0, pl->stream>>>(a, pl->d_bt_exits.p);
+    bt_exits_kernel<<<threads, 32, 0, pl->stream>>>(a, pl->d_bt_exits.p);
     CUDA_TRY(cudaGetLastError());
     pl->exits_mode = entry < 0 ? 1 : 2;
     return WHMEC_OK;
@@ -1381,8 +1430,7 @@ int pedigree_backtrace(whmec_plan *pl, int entry, std::string &msg) {
     }
     const BtArgs a = bt_args(pl, entry);
     bt_entries_kernel<<<1, 32, 0, pl->stream>>>(a, pl->d_bt_exits.p, pl->d_bt_entries.p, nullptr);
-    bt_paths_kernel<<<(a.n_chains + 63) / 64, 64, 0, pl->stream>>>(a, pl->d_bt_entries.p, pl->d_path_index.p, pl->d_path_tv.p,
-                                                                    pl->d_result.p);
+    bt_paths_kernel<<<a.n_chains, 32, 0, pl->stream>>>(a, pl->d_bt_entries.p, pl->d_path_index.p, pl->d_path_tv.p, pl->d_result.p);
     CUDA_TRY(cudaGetLastError());
     return WHMEC_OK;
 }
