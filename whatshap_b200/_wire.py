@@ -184,6 +184,16 @@ class Comm:
         self.device = torch.device("cuda", torch.cuda.current_device()) if self.cuda else torch.device("cpu")
         self.root = dist.get_global_rank(group, 0) if group is not None else 0
 
+        self._pinned = {}  # page-locked staging buffers, kept for the life of the communicator (cudaHostAlloc costs milliseconds)
+
+    def _staging(self, key: str, nbytes: int):
+        """A page-locked uint8 tensor of at least `nbytes` (NCCL) or a plain one (gloo), reused between calls."""
+        t = self._pinned.get(key)
+        if t is None or t.numel() < nbytes:
+            t = self.torch.empty(max(nbytes, 1 << 16), dtype=self.torch.uint8, pin_memory=self.cuda)
+            self._pinned[key] = t
+        return t[:nbytes]
+
     def _to_device(self, a: np.ndarray):
         t = self.torch.from_numpy(a)
         if self.cuda:
@@ -199,24 +209,49 @@ class Comm:
         self.dist.all_gather(box, t, group=self.group)
         return [int(x.item()) for x in box]
 
-    def scatter_rows(self, rows: Optional[Sequence[np.ndarray]]) -> np.ndarray:
-        """Rank 0 passes one uint8 row per rank; every rank returns its row."""
+    def scatter_rows(self, rows) -> np.ndarray:
+        """Rank 0 passes one row per rank -- a uint8 array, or a list of uint8 arrays that `join` would concatenate (they are
+        then written straight into the page-locked send buffer, one copy); every rank returns its row."""
         torch, dist = self.torch, self.dist
         sizes = torch.zeros(self.world, dtype=torch.int64, device=self.device)
+        layouts = None
         if self.rank == 0:
-            sizes = self._to_device(np.array([r.nbytes for r in rows], np.int64))
+            layouts = []
+            for r in rows:
+                if isinstance(r, np.ndarray):
+                    layouts.append((None, r.nbytes))
+                else:
+                    head = np.array([len(r)] + [b.nbytes for b in r], np.uint64)
+                    layouts.append((head, _pad(head.nbytes) + sum(_pad(b.nbytes) for b in r)))
+            sizes = self._to_device(np.array([n for _, n in layouts], np.int64))
         dist.broadcast(sizes, src=self.root, group=self.group)
         sizes = [int(x) for x in self._to_host(sizes)]
         width = max(_pad(max(sizes)), _ALIGN)
         recv = torch.empty(width, dtype=torch.uint8, device=self.device)
         parts = None
         if self.rank == 0:
-            big = np.zeros((self.world, width), np.uint8)
+            stage = self._staging("scatter", self.world * width)
+            big = stage.numpy().reshape(self.world, width)
             for i, r in enumerate(rows):
-                big[i, : r.nbytes] = r
-            parts = list(self._to_device(big).unbind(0))
+                head, n = layouts[i]
+                if head is None:
+                    big[i, :n] = r
+                else:
+                    big[i, : head.nbytes] = head.view(np.uint8)
+                    off = _pad(head.nbytes)
+                    for b in r:
+                        big[i, off : off + b.nbytes] = b
+                        off += _pad(b.nbytes)
+                # (padding bytes are never read: every reader goes by the recorded lengths)
+            dev = stage.to(self.device, non_blocking=True) if self.cuda else stage
+            parts = list(dev.reshape(self.world, width).unbind(0))
         dist.scatter(recv, parts, src=self.root, group=self.group)
-        return self._to_host(recv)[: sizes[self.rank]].copy()
+        if self.cuda:
+            out = self._staging("scatter_recv", width)
+            out.copy_(recv)
+            torch.cuda.current_stream().synchronize()
+            return out.numpy()[: sizes[self.rank]].copy()
+        return recv.numpy()[: sizes[self.rank]].copy()
 
     def gather_rows(self, row: np.ndarray) -> Optional[List[np.ndarray]]:
         """Every rank passes one uint8 row; rank 0 returns all of them (others None)."""

@@ -33,8 +33,7 @@ def independent_blocks(prob: FlatProblem) -> List[Tuple[int, int]]:
         ends = prob.read_off[1:].astype(np.int64) - 1
         first = prob.ent_col[starts].astype(np.int64)
         last = prob.ent_col[ends].astype(np.int64)
-        np.add.at(span, first + 1, 1)
-        np.add.at(span, last + 1, -1)
+        span += np.bincount(first + 1, minlength=n + 2) - np.bincount(last + 1, minlength=n + 2)
     crossing = np.cumsum(span)[1:n]  # crossing[k-1] > 0: some read is active in columns k-1 and k
     cuts = [0] + [int(k) for k in (np.nonzero(crossing == 0)[0] + 1)] + [n]
     return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
@@ -47,11 +46,11 @@ def block_work(prob: FlatProblem, blocks: Sequence[Tuple[int, int]]) -> np.ndarr
     if prob.n_reads:
         starts = prob.read_off[:-1].astype(np.int64)
         ends = prob.read_off[1:].astype(np.int64) - 1
-        np.add.at(cov, prob.ent_col[starts].astype(np.int64), 1)
-        np.add.at(cov, prob.ent_col[ends].astype(np.int64) + 1, -1)
+        cov += np.bincount(prob.ent_col[starts].astype(np.int64), minlength=n + 1) - np.bincount(prob.ent_col[ends].astype(np.int64) + 1, minlength=n + 1)
     a = np.cumsum(cov)[:n]
     cells = np.exp2(np.minimum(a, 40).astype(np.float64))
-    return np.array([cells[lo:hi].sum() for lo, hi in blocks])
+    prefix = np.concatenate([[0.0], np.cumsum(cells)])
+    return np.array([prefix[hi] - prefix[lo] for lo, hi in blocks])
 
 
 def assign_blocks(work: np.ndarray, world: int) -> List[List[int]]:
@@ -314,15 +313,15 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         if prob.n_trios > 0 and world > 1 and len(blocks) > 1:  # transmission vectors couple the blocks: segments of the table
             ranges = segment_ranges(prob, world)
             flat = np.array([MODE["segments"]] + [x for r in ranges for x in (r if r is not None else (0, 0))], np.int64)
-            rows = [_wire.join([flat.view(np.uint8)] + ([enc] if enc is not None else [])) for enc in _wire.encode_problem_slices(prob, ranges)]
+            rows = [[flat.view(np.uint8)] + ([enc] if enc is not None else []) for enc in _wire.encode_problem_slices(prob, ranges)]
         elif prob.n_trios > 0 or prob.n_cols == 0:  # one chain, one rank, or no columns: one GPU
-            rows = [_wire.join([np.array([MODE["single"]], np.int64).view(np.uint8)])] * world
+            rows = [[np.array([MODE["single"]], np.int64).view(np.uint8)]] * world
         else:
             # every rank gets ONE sub-problem: a contiguous run of whole blocks with about 1 / world of the DP cells (one
             # whmec_solve per rank sweeps all its chains together; block-by-block calls would be launch-latency bound)
             runs = contiguous_shares(block_work(prob, blocks), world)
             spans = [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in runs]
-            rows = [_wire.join([np.array([MODE["blocks"]], np.int64).view(np.uint8)] + ([enc] if enc is not None else []))
+            rows = [[np.array([MODE["blocks"]], np.int64).view(np.uint8)] + ([enc] if enc is not None else [])
                     for enc in _wire.encode_problem_slices(prob, spans)]
     t1 = time.perf_counter()
     pieces = _wire.separate(comm.scatter_rows(rows))
