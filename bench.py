@@ -60,47 +60,102 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md)."""
+    """SM clock / throttle-reason samples DURING the timed region (B200_PROFILING.md).  The timed region of the default run is a few
+    tens of milliseconds, shorter than the start-up of an `nvidia-smi -lms` loop, so the samples are taken through NVML (the library
+    nvidia-smi itself reads) every 2 ms by a thread of this process; `nvidia-smi` is the fallback when NVML cannot be loaded."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
         self.device_index = device_index
-        self.rows = []
+        self.rows = []      # (sm MHz, max MHz, set of reasons)
         self.proc = None
+        self.source = None
+        self._stop = threading.Event()
+        self._thread = None
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES may renumber the devices: resolve the NVML handle through the UUID of the CUDA device
+            handle = None
+            try:
+                import torch
+
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(device_index).uuid)
+                handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self._nvml, self._handle = pynvml, handle
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv, h = self._nvml, self._handle
+        bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(get_reasons(h))
+                self.rows.append((sm, self._max, {k for k, b in bits.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.002)
 
     def start(self):
+        if self._nvml is not None:
+            self._thread = threading.Thread(target=self._sample_nvml, daemon=True)
+            self._thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.device_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for name, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                self.rows.append((float(r[1]), float(r[2]), {n for n, v in zip(names, r[4:8]) if v.lower().startswith("active")}))
             except (ValueError, IndexError):
                 continue
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+
+    def mark(self) -> int:
+        """Index of the next sample: the caller brackets its timed region with two marks."""
+        return len(self.rows)
+
+    def stop(self, first: int = 0, last: int = None) -> dict:
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+        elif self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML and no nvidia-smi"], "samples": 0}
+        rows = self.rows[first:last]
+        window = "timed region"
+        if len(rows) < 3:  # a slow sampler (nvidia-smi fallback): fall back to everything sampled under load since start()
+            rows, window = self.rows, "warm-up + timed region"
+        reasons = set()
+        for r in rows:
+            reasons |= r[2]
+        sm = [r[0] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(r[1] for r in rows) if rows else None,
+                "reasons": sorted(reasons), "samples": len(rows), "source": self.source, "window": window}
 
 
 def hbm_peak():
@@ -284,12 +339,13 @@ def main():
 
     # ---- device-resident sweep ------------------------------------------------------------
     plan = _lib.Plan(prob, device=local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()  # before the warm-up, so that even a slow sampler has samples under load
     for _ in range(max(args.warmup, 3)):
         plan.sweep()
         plan.finish()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    mark0 = sampler.mark()
     wall0 = time.perf_counter()
     sweep_ms, step_ms = [], []
     for _ in range(args.steps):
@@ -302,7 +358,7 @@ def main():
         step_ms.append(st["sweep_ms"] + st["d2h_ms"])
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop()
+    clocks = sampler.stop(mark0, sampler.mark())
     stats = plan.stats()
     plan.close()
     total_ms = sum(step_ms)

@@ -8,6 +8,8 @@
 #include "tile.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -816,6 +818,9 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
                     hi = std::max(hi, P.col_end - 1);
                 }
             }
+    using cclk = std::chrono::steady_clock;
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    const auto tq0 = cclk::now();
     CUDA_TRY(cudaMallocAsync((void **)&I->d_seg_lo, seg_lo.size() * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_seg_hi, seg_hi.size() * 4, stream));
     CUDA_TRY(cudaMemcpyAsync(I->d_seg_lo, seg_lo.data(), seg_lo.size() * 4, cudaMemcpyHostToDevice, stream));
@@ -829,6 +834,7 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     CUDA_TRY(cudaMallocAsync((void **)&I->d_arena, (I->arena_words + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_begin, pk.chain_begin.size() * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_chain_keys, (size_t)I->n_chains * 8, stream));
+    const auto tq1 = cclk::now();
     auto up = [&](void *dst, const void *src, size_t bytes) {
         h2d += bytes;
         return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream);
@@ -878,6 +884,11 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
         I->n_sm = (uint32_t)sms;
     }
     CUDA_TRY(cudaFuncSetAttribute(tile_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
+    if (timing) {
+        auto qms = [](cclk::time_point a, cclk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        std::fprintf(stderr, "[whmec] tiles.create: segments + seg tables (1 sync) + %.1f MB of allocations %.2f ms, upload calls (%.1f MB) %.2f ms\n",
+                     (double)((I->arena_words + ts.state_words) * 4) / 1e6, qms(tq0, tq1), (double)total / 1e6, qms(tq1, cclk::now()));
+    }
     return WHMEC_OK;
 }
 

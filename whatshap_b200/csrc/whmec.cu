@@ -1019,10 +1019,16 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
     const bool forced_column = force && force[0] == '1';
     const bool tile_candidate = p->n_ind == 1 && p->n_trios == 0 && !forced_column && !segment;
+    using pclk = std::chrono::steady_clock;
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    auto pms = [](pclk::time_point a, pclk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto tc0 = pclk::now();
     int rc = pack_problem(p, pl->pk, msg, !tile_candidate);
     if (rc != WHMEC_OK) return rc;
     Packed &pk = pl->pk;
+    const auto tc1 = pclk::now();
     pl->use_tiles = tile_candidate && pk.n > 0 && pl->tiles.plan(pk);
+    const auto tc2 = pclk::now();
     if (tile_candidate && !pl->use_tiles && pk.n > 0) {  // planner declined: the column kernel needs the deltas
         rc = pack_problem(p, pl->pk, msg, true);
         if (rc != WHMEC_OK) return rc;
@@ -1054,10 +1060,14 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     CUDA_TRY(pl->d_result.alloc(4, pl->stream));
     CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
     uint64_t h2d = 0;
+    const auto tc3 = pclk::now();
 
     if (pl->use_tiles) {
         rc = pl->tiles.create(pk, pl->stream, h2d, msg);
         if (rc != WHMEC_OK) return rc;
+        if (timing)
+            std::fprintf(stderr, "[whmec] create: pack %.2f ms, plan %.2f ms, stream + events + result buffers %.2f ms, tiles.create (alloc + upload enqueue) %.2f ms\n",
+                         pms(tc0, tc1), pms(tc1, tc2), pms(tc2, tc3), pms(tc3, pclk::now()));
         pl->stats.path_kind = 1;
         pl->stats.backptr_bytes = pl->tiles.backptr_bytes;
     } else {
@@ -1448,6 +1458,9 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int en
         return WHMEC_ERR_INPUT;
     }
     CUDA_TRY(cudaSetDevice(pl->device));
+    using fclk = std::chrono::steady_clock;
+    const bool timing = std::getenv("WHMEC_TIMING") != nullptr;
+    const auto tf0 = fclk::now();
     if (pl->sweep_pending) {  // enqueued by plan_sweep_impl(wait = false): its events are reused below
         CUDA_TRY(cudaEventSynchronize(pl->ev1));
         CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
@@ -1481,7 +1494,12 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int en
     CUDA_TRY(cudaEventElapsedTime(&pl->stats.d2h_ms, pl->ev0, pl->ev1));
     pl->stats.d2h_bytes = (uint64_t)n * 8 + 16;
     s->cost = result[0];
-    return build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+    const auto tf1 = fclk::now();
+    const int orc = build_outputs(pk, pidx.data(), ptv.data(), s, msg);
+    if (timing)
+        std::fprintf(stderr, "[whmec] finish: backtrace + D2H %.2f ms, outputs %.2f ms\n", std::chrono::duration<double, std::milli>(tf1 - tf0).count(),
+                     std::chrono::duration<double, std::milli>(fclk::now() - tf1).count());
+    return orc;
 }
 
 // ---- segments of a pedigree table (include/whmec.h) ----
