@@ -165,25 +165,30 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def recorded_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the
-    committed `ncu --set full` capture of this workload (profiles/traffic.json), else None."""
+def recorded_traffic(workload, launches=1):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this workload (profiles/traffic.json), else None.  A report that holds every big launch of one sweep (the two
+    passes of the fused pedigree sweep) is averaged over the launches of a sweep, like `algorithmic_bytes_per_launch`."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         rec = json.load(open(path)).get(workload)
         if rec:
-            return rec["bytes_per_launch"], rec["report"]
+            per_sweep = rec.get("launches_in_report", 1) > 1
+            return rec["bytes_per_launch"] / (launches if per_sweep else 1), rec["report"]
     return None, None
 
 
-def recorded_issue(workload, cells_per_launch):
+def recorded_issue(workload, cells_per_launch, launches=1):
     """Instruction-issue view of the same ncu capture: the DP kernels are bound by integer issue, not by HBM."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(path):
         rec = json.load(open(path)).get(workload)
         if rec and "warp_inst_executed" in rec:
-            return {"issue_active_pct_of_peak": rec["issue_active_pct"], "warp_instructions_per_launch": rec["warp_inst_executed"],
-                    "thread_instructions_per_dp_cell": 32.0 * rec["warp_inst_executed"] / max(cells_per_launch, 1.0),
+            # a report that holds every big launch of one sweep (the two passes of the fused pedigree sweep) gives totals per sweep
+            per_sweep = rec.get("launches_in_report", 1) > 1
+            inst = rec["warp_inst_executed"] / (launches if per_sweep else 1)
+            return {"issue_active_pct_of_peak": rec["issue_active_pct"], "warp_instructions_per_launch": inst,
+                    "thread_instructions_per_dp_cell": 32.0 * inst / max(cells_per_launch, 1.0),
                     "source": rec["report"], "note": "ncu capture of one launch of the dominant kernel; 100 % = one warp instruction per scheduler per cycle"}
     return None
 
@@ -437,7 +442,7 @@ def main():
         peak, peak_src = hbm_peak()
         launches = int(stats["kernel_launches"])
         achieved = stats["algorithmic_bytes"] / (statistics.mean(sweep_ms) / 1e3) / 1e9
-        issue = recorded_issue(name, stats["cells"] / max(launches, 1))
+        issue = recorded_issue(name, stats["cells"] / max(launches, 1), launches)
         roofline_issue = None
         if issue and clocks.get("sm_mhz"):
             # warp instructions of one sweep (ncu capture of one launch x launches) against what the SMs can issue in that time
@@ -463,7 +468,7 @@ def main():
             },
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": recorded_traffic(name)[0], "traffic_source": recorded_traffic(name)[1], "peak_source": peak_src,
+                "traffic": recorded_traffic(name, launches)[0], "traffic_source": recorded_traffic(name, launches)[1], "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": stats["algorithmic_bytes"] / max(launches, 1),
                 "kernel": {1: "tile_panel_kernel", 2: "col_direct_kernel", 3: "ped_fused_kernel" if launches == 3 else "col_batched_kernel"}.get(int(stats["path_kind"]), "col_direct_kernel"),
                 "issue": issue,

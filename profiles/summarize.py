@@ -42,6 +42,7 @@ def main(prefix):
     for name in sorted(os.listdir(os.path.join(ROOT, "gpurun_out"))):
         if not (name.startswith(prefix) and name.endswith(".ncu-rep")):
             continue
+        traffic = {k: v for k, v in traffic.items() if v.get("report") != name}
         hdr, units, rows = raw(os.path.join(ROOT, "gpurun_out", name))
         lines = [f"# ncu --set full --clock-control none, report {name} (one launch of the dominant kernel)"]
         for r in rows:
@@ -56,10 +57,20 @@ def main(prefix):
             kernel = r[hdr.index("Kernel Name")].split("(")[0].split("::")[-1].strip()
             num = lambda key: float(r[hdr.index(key)])
             dur_unit = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
-            traffic[wl] = {"bytes_per_launch": total, "kernel": kernel, "report": name,
-                           "grid": int(num("launch__grid_size")), "duration_us": num("gpu__time_duration.sum") * dur_unit,
-                           "warp_inst_executed": num("smsp__inst_executed.sum"), "sm_cycles_elapsed": num("sm__cycles_elapsed.max"),
-                           "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active")}
+            rec = {"bytes_per_launch": total, "kernel": kernel, "report": name,
+                   "grid": int(num("launch__grid_size")), "duration_us": num("gpu__time_duration.sum") * dur_unit,
+                   "warp_inst_executed": num("smsp__inst_executed.sum"), "sm_cycles_elapsed": num("sm__cycles_elapsed.max"),
+                   "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"), "launches_in_report": 1}
+            prev = traffic.get(wl)
+            if prev and prev.get("report") == name:
+                # several launches of one sweep in the same report (the two passes of the fused pedigree sweep): totals of the sweep,
+                # issue activity weighted by duration
+                w0, w1 = prev["duration_us"], rec["duration_us"]
+                rec["issue_active_pct"] = (prev["issue_active_pct"] * w0 + rec["issue_active_pct"] * w1) / (w0 + w1)
+                for key in ("bytes_per_launch", "duration_us", "warp_inst_executed", "sm_cycles_elapsed"):
+                    rec[key] += prev[key]
+                rec["launches_in_report"] = prev["launches_in_report"] + 1
+            traffic[wl] = rec
         open(os.path.join(ROOT, "profiles", name.replace(".ncu-rep", ".txt")), "w").write("\n".join(lines) + "\n")
         print("\n".join(lines))
     json.dump(traffic, open(tpath, "w"), indent=1, sort_keys=True)

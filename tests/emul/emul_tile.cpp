@@ -317,6 +317,31 @@ extern "C" int whemul_time_host_product(const whmec_problem *p, double *out3) {
     return 0;
 }
 
+// Host phases of a pedigree solve: packer WITH the cost-function deltas + output pass on an arbitrary path (out2: ms)
+extern "C" int whemul_time_host_pedigree(const whmec_problem *p, double *out2) {
+    keep_heap_like_the_library();
+    Packed pk;
+    std::string msg;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = pack_problem(p, pk, msg, true);
+    auto t1 = std::chrono::steady_clock::now();
+    if (rc != WHMEC_OK) return rc;
+    std::vector<uint32_t> pidx(pk.n), ptv(pk.n, 0);
+    for (uint32_t k = 0; k < pk.n; ++k) pidx[k] = (k * 2654435761u) & low_mask(pk.cols[k].a);
+    std::vector<uint8_t> part(p->n_reads), sra((size_t)p->n_ind * 2 * pk.n);
+    std::vector<uint32_t> srq((size_t)p->n_ind * pk.n);
+    whmec_solution s{};
+    s.partition = part.data();
+    s.sr_allele = sra.data();
+    s.sr_quality = srq.data();
+    auto t3 = std::chrono::steady_clock::now();
+    build_outputs(pk, pidx.data(), ptv.data(), &s, msg);
+    auto t4 = std::chrono::steady_clock::now();
+    out2[0] = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    out2[1] = std::chrono::duration<double, std::milli>(t4 - t3).count();
+    return 0;
+}
+
 // FNV-1a digest of everything the planner produces (to hold planner rewrites to byte-identical schedules)
 extern "C" int whemul_plan_digest(const whmec_problem *p, uint64_t *digest) {
     Packed pk;
