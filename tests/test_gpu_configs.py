@@ -23,7 +23,7 @@ SWITCHES = {
     "ballot_bp": {"WHMEC_TILE_PACKED_BP": "0"},
     "mirror_off": {"WHMEC_TILE_MIRROR": "0"},
     "groups4": {"WHMEC_SOLVE_GROUPS": "4"},
-    "pinned": {"WHMEC_PINNED_STAGING": "1"},
+    "pageable_upload": {"WHMEC_PINNED_UPLOAD": "0"},  # upload arrays on the heap instead of the page-locked pool
     "column": {"WHMEC_FORCE_COLUMN_KERNEL": "1"},
 }
 PED_SWITCHES = {
@@ -32,6 +32,7 @@ PED_SWITCHES = {
     "ped_one_cta": {"WHMEC_PED_CLUSTER": "1"},   # default: a cluster of up to 8 CTAs per chain when there are fewer chains than SMs
     "ped_cluster2": {"WHMEC_PED_CLUSTER": "2"},
     "ped_sequential": {"WHMEC_PED_SEQUENTIAL": "1"},
+    "pageable_upload": {"WHMEC_PINNED_UPLOAD": "0"},
 }
 ALL_ENV = sorted({k for d in list(SWITCHES.values()) + list(PED_SWITCHES.values()) for k in d})
 

@@ -10,9 +10,33 @@
 #include <cstdlib>
 #include <exception>
 #include <mutex>
+#include <new>
 #include <thread>
 
 namespace whmec {
+
+namespace {
+std::atomic<void *(*)(size_t)> g_stage_alloc{nullptr};
+std::atomic<bool (*)(void *)> g_stage_release{nullptr};
+}  // namespace
+
+void set_stage_hooks(const StageHooks &hooks) {
+    g_stage_release.store(hooks.release);
+    g_stage_alloc.store(hooks.alloc);
+}
+
+void *stage_alloc(size_t bytes) {
+    if (auto fn = g_stage_alloc.load(std::memory_order_acquire))
+        if (void *p = fn(bytes)) return p;
+    return ::operator new(bytes);
+}
+
+void stage_free(void *p) {
+    if (!p) return;
+    if (auto fn = g_stage_release.load(std::memory_order_acquire))
+        if (fn(p)) return;
+    ::operator delete(p);
+}
 
 uint32_t host_threads(uint32_t cap) {
     uint32_t cores = std::max(1u, std::thread::hardware_concurrency());

@@ -44,4 +44,44 @@ struct NoInitAlloc : std::allocator<T> {
 template <class T>
 using RawVec = std::vector<T, NoInitAlloc<T>>;
 
+// Arrays that are uploaded to the device as they are (per-column records, cost functions, panels): their memory comes
+// from a hook that the CUDA side of the library installs (a pool of page-locked blocks, whmec.cu), so that the packer and the
+// planner write straight into DMA-able memory and the upload is one asynchronous copy per array with no staging pass.
+// Without a hook (host-only builds: tests/emul) and for small arrays it is plain heap memory.
+struct StageHooks {
+    void *(*alloc)(size_t bytes);      // nullptr result: fall back to the heap
+    bool (*release)(void *p);          // false: `p` is not one of the hook's blocks (heap memory)
+};
+void set_stage_hooks(const StageHooks &hooks);
+void *stage_alloc(size_t bytes);
+void stage_free(void *p);
+
+template <class T>
+struct StageAlloc {
+    using value_type = T;
+    template <class U>
+    struct rebind {
+        using other = StageAlloc<U>;
+    };
+    StageAlloc() = default;
+    template <class U>
+    StageAlloc(const StageAlloc<U> &) {}
+    T *allocate(size_t n) { return static_cast<T *>(stage_alloc(n * sizeof(T))); }
+    void deallocate(T *p, size_t) { stage_free(p); }
+    template <class U>
+    void construct(U *p) {
+        ::new ((void *)p) U;  // default-initialisation: resize() leaves trivial elements untouched
+    }
+    template <class U, class... A>
+    void construct(U *p, A &&...a) {
+        ::new ((void *)p) U(std::forward<A>(a)...);
+    }
+    template <class U>
+    bool operator==(const StageAlloc<U> &) const { return true; }
+    template <class U>
+    bool operator!=(const StageAlloc<U> &) const { return false; }
+};
+template <class T>
+using StagedVec = std::vector<T, StageAlloc<T>>;
+
 }  // namespace whmec

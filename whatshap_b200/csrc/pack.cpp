@@ -208,6 +208,8 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         size_t act_base = 0, act_count = 0;  // this chunk's slice of the (column, active read) arrays
         uint32_t max_a = 0;
         uint64_t base_total = 0, rc_total = 0;
+        uint64_t words = 0, cells = 0, alg_bytes = 0;  // back-pointer words (column-kernel layout), DP cells, algorithmic bytes of the chunk
+        std::vector<uint32_t> chain_starts;            // columns of this chunk that begin a DP-independent chain
         int rc = WHMEC_OK;
         uint32_t err_col = 0;
         std::string err;
@@ -418,6 +420,19 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
             }
             ch.base_total += max_base;
             ch.rc_total += (uint64_t)m.rc * pk.tb;
+            // chains, back-pointer layout (chunk-relative until the chunks' sizes are known), accounting.
+            // A chunk starts at a chain boundary, so "the previous column forwards nothing" is decided inside the chunk.
+            if (k == kb || pk.cols[k - 1].f == 0) ch.chain_starts.push_back(k);
+            // the last column stores its winner too (f == 0); columns that drop many reads have few entries and
+            // keep one word per entry (a thread block owns one entry there and writes its word alone)
+            m.bp_width = m.d >= 8 ? 32 : round_bp_width(m.d + pk.tb);
+            m.bp_off = ch.words;
+            const uint64_t entries = ((uint64_t)1 << m.f) * T;
+            ch.words += (entries * m.bp_width + 31) / 32;
+            ch.cells += ((uint64_t)1 << m.a) * T;
+            uint64_t bytes = (uint64_t)4 * T * ((uint64_t)1 << m.bw);
+            if (k + 1 != n) bytes += (uint64_t)(8 + (T > 1 ? 4 : 0)) * T * ((uint64_t)1 << m.f);
+            ch.alg_bytes += bytes;
         }
     };
     parallel_tasks(n_chunks, pack_threads, build_chunk);
@@ -442,24 +457,22 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         std::fprintf(stderr, "[whmec] pack: validate %.2f ms, count + chunks(%u) %.2f ms, totals %.2f ms\n", tms(t_start, t_valid), n_chunks,
                      tms(t_valid, t_chunks), tms(t_chunks, t_merge));
 
-    // ---- chains, back-pointer layout, accounting
+    // ---- chains, back-pointer layout, accounting: per-chunk results, made absolute here
     uint64_t words = 0;
     whmec_stats &st = pk.stats;
-    for (uint32_t k = 0; k < n; ++k) {
-        ColMeta &m = pk.cols[k];
-        if (k == 0 || pk.cols[k - 1].f == 0) pk.chain_begin.push_back(k);
-        const bool lastcol = (k + 1 == n);
-        // the last column stores its winner too (f == 0); columns that drop many reads have few entries and
-        // keep one word per entry (a thread block owns one entry there and writes its word alone)
-        m.bp_width = m.d >= 8 ? 32 : round_bp_width(m.d + pk.tb);
-        m.bp_off = words;
-        uint64_t entries = ((uint64_t)1 << m.f) * T;
-        words += (entries * m.bp_width + 31) / 32;
-        st.cells += ((uint64_t)1 << m.a) * T;
-        uint64_t bytes = (uint64_t)4 * T * ((uint64_t)1 << m.bw);
-        if (!lastcol) bytes += (uint64_t)(8 + (T > 1 ? 4 : 0)) * T * ((uint64_t)1 << m.f);
-        st.algorithmic_bytes += bytes;
+    std::vector<uint64_t> word_base(n_chunks, 0);
+    for (uint32_t ci = 0; ci < n_chunks; ++ci) {
+        const Chunk &ch = chunks[ci];
+        word_base[ci] = words;
+        words += ch.words;
+        st.cells += ch.cells;
+        st.algorithmic_bytes += ch.alg_bytes;
+        pk.chain_begin.insert(pk.chain_begin.end(), ch.chain_starts.begin(), ch.chain_starts.end());
     }
+    parallel_tasks(n_chunks, pack_threads, [&](uint32_t ci) {
+        if (word_base[ci])
+            for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) pk.cols[k].bp_off += word_base[ci];
+    });
     pk.chain_begin.push_back(n);
     pk.bp_words = words;
     st.backptr_bytes = words * 4;

@@ -16,7 +16,7 @@ struct Packed {
     bool has_deltas = true;              // fn_delta filled
     bool safe31 = false;                 // every reachable cost value < 2^30 (tile-kernel arithmetic is exact)
     // (RawVec: resize() does not zero-fill; every element is written by the packer)
-    RawVec<ColMeta> cols;                // [n]
+    StagedVec<ColMeta> cols;             // [n]  (uploaded as it is: page-locked when the CUDA side installed its pool)
     // active reads per column, CSR aligned with cols[k].a
     RawVec<uint64_t> act_off;            // [n+1]
     RawVec<uint32_t> act_read;           // read index of bit j
@@ -24,11 +24,11 @@ struct Packed {
     RawVec<uint32_t> act_phred;
     RawVec<uint8_t> act_ind;
     // cost functions (see common.h), grouped per column and transmission value
-    RawVec<uint32_t> fn_c0;
-    RawVec<int32_t> fn_delta;            // [nf][FN_STRIDE]
+    StagedVec<uint32_t> fn_c0;
+    StagedVec<int32_t> fn_delta;         // [nf][FN_STRIDE]
     RawVec<uint32_t> fn_asg;             // allele assignment A of the function
     RawVec<uint32_t> fn_base;            // genotype-likelihood base cost of A
-    RawVec<uint32_t> fn_group;           // per column T+1 offsets relative to cols[k].fn_off
+    StagedVec<uint32_t> fn_group;        // per column T+1 offsets relative to cols[k].fn_off
     std::vector<int8_t> h2p;             // [T][n_ind][2]
     std::vector<uint32_t> read_first, read_last;  // column span of every read
     // chains: maximal runs of columns with f > 0 between them (T == 1 only uses them)

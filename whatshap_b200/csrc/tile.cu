@@ -38,6 +38,7 @@ struct TileSmem {
     uint32_t buf[3][TILE_ENTRIES];  // [0],[1]: ping-pong projection; [2]: staging / prefetch of the next tile's input
     uint32_t stage_pad[STAGE_PAD_WORDS];  // directly behind buf[2]: bulk-copied chunks are laid out with a 16-byte skew each
     unsigned long long stage_bar;   // mbarrier of the bulk copies into the staging buffer
+    unsigned long long col_bar;     // column barrier of the steady-state panels (split: arrive, prepare the next column, wait)
     int32_t TL[2][TILE_TL_SIZE];
     int32_t TH[2][TILE_TH_SIZE];
     int32_t TW[2][32];    // fast path, per warp: K2 + E(global bits of the tile) + weights of the warp's output bits
@@ -236,6 +237,40 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t pari
     } while (!done);
 }
 
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Steady-state panel (see tile_panel_kernel): `ncol` fast twin columns of one tile size, tables already in shared memory.
+// One barrier per column, split: a warp ARRIVES when its outputs of column j are stored, computes everything of column j + 1
+// that does not read the projection (addresses, constants, the subset sums of its outputs: column_fast_prep), and only then
+// WAITS for the other warps -- the block's drift at the barrier is filled with work instead of idle issue slots.
+// The barrier is an mbarrier with one arrival per warp (the warp's lanes are ordered by __syncwarp before lane 0 arrives;
+// arrive = release, try_wait = acquire at CTA scope).  Every thread of the block runs the same number of iterations.
+template <int LG, bool MR>
+__device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint32_t tile, uint32_t *__restrict__ arena, uint32_t &cur,
+                                               uint32_t &col_phase, uint32_t tid) {
+    constexpr int BITS = 2 << LG;  // outputs (= back-pointer bits) per thread and column: 2^LG twins
+    FastPrep<LG> pr;
+    column_fast_prep<LG, true>(pr, S.tcs[0], S.TWs[0], S.T5s[0], S.cgs[0], S.buf[cur], S.buf[cur ^ 1], tid);
+    uint32_t *bpw = arena + S.tcs[0].bp_off + (uint64_t)tile * S.tcs[0].bp_tile_stride;
+    uint32_t section = S.tcs[0].bp_tile_words;
+    for (uint32_t j = 0; j < ncol; ++j) {
+        column_fast_body<LG, false, true, true, MR>(pr, PackedEmit<BITS>{bpw, tid, section});
+        __syncwarp();
+        if ((tid & 31u) == 0) mbar_arrive(&S.col_bar);
+        cur ^= 1;
+        if (j + 1 < ncol) {
+            const TileCol &tn = S.tcs[j + 1];
+            column_fast_prep<LG, true>(pr, tn, S.TWs[j + 1], S.T5s[j + 1], S.cgs[j + 1], S.buf[cur], S.buf[cur ^ 1], tid);
+            bpw = arena + tn.bp_off + (uint64_t)tile * tn.bp_tile_stride;
+            section = tn.bp_tile_words;
+        }
+        mbar_wait(&S.col_bar, col_phase);
+        col_phase ^= 1u;
+    }
+}
+
 // Tile-major hand-offs whose chunks are at least 128 bytes travel as one bulk copy per producer tile.
 __device__ __forceinline__ bool bulk_handoff(uint32_t gA, uint32_t jb) { return gA <= BULK_MAX_GA && jb >= BULK_MIN_J; }
 
@@ -294,7 +329,11 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     uint32_t pi = 0;            // panel of the current work item; panels[] is sorted by tile_begin
     uint32_t staged = 0;        // the staging buffer holds (or is receiving) the current tile's input: 1 = cp.async, 2 = bulk copies
     uint32_t bar_phase = 0;     // parity of the staging mbarrier's current phase
-    if (tid == 0) mbar_init(&S.stage_bar, 1);
+    uint32_t col_phase = 0;     // parity of the column barrier's current phase
+    if (tid == 0) {
+        mbar_init(&S.stage_bar, 1);
+        mbar_init(&S.col_bar, NT / 32);
+    }
     __syncthreads();
     for (uint32_t work = blockIdx.x; work < total_tiles; work += gridDim.x) {
     if (tile_log >= 0) pi = work >> tile_log;  // every panel of this launch has 2^tile_log tiles
@@ -407,19 +446,13 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
         }
         const bool mirror = S.tcs[0].half && S.tcs[0].km != 0;
         const uint32_t lg = P.steady - 1u;
-        for (uint32_t j = 0; j < ncol; ++j) {
-            __syncthreads();  // tables ready (j == 0); column j - 1 complete
-            const TileCol &tc = S.tcs[j];
-            uint32_t *bpw = arena + tc.bp_off + (uint64_t)tile * tc.bp_tile_stride;
-#define WHMEC_STEADY(LGV, BITS, MR) \
-    column_fast<LGV, false, true, true, MR>(tc, S.TWs[j], S.T5s[j], S.cgs[j], S.buf[cur], S.buf[cur ^ 1], PackedEmit<BITS>{bpw, tid, tc.bp_tile_words}, tid)
-            if (lg == 3) {
-                if (mirror) WHMEC_STEADY(3, 16, true); else WHMEC_STEADY(3, 16, false);
-            } else {
-                if (mirror) WHMEC_STEADY(2, 8, true); else WHMEC_STEADY(2, 8, false);
-            }
-#undef WHMEC_STEADY
-            cur ^= 1;
+        __syncthreads();  // tables ready; the tile's input is in place
+        if (lg == 3) {
+            if (mirror) steady_columns<3, true>(S, ncol, tile, arena, cur, col_phase, tid);
+            else steady_columns<3, false>(S, ncol, tile, arena, cur, col_phase, tid);
+        } else {
+            if (mirror) steady_columns<2, true>(S, ncol, tile, arena, cur, col_phase, tid);
+            else steady_columns<2, false>(S, ncol, tile, arena, cur, col_phase, tid);
         }
     } else
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {
@@ -644,6 +677,7 @@ struct TileImpl {
     std::vector<TileSeg> segs;          // one segment: everything resident (the usual case)
     uint32_t *d_ckpt = nullptr;         // projection state before segments 1 .. K-1 (state_words each)
     uint32_t *d_seg_lo = nullptr, *d_seg_hi = nullptr;  // [segment][chain]: columns of the chain inside the segment (lo > hi: none)
+    std::vector<uint32_t> seg_lo, seg_hi;  // their host copies (kept: the upload is asynchronous)
     uint64_t arena_words = 0;
     ColMeta *d_cols = nullptr;
     TileCol *d_tcols = nullptr;
@@ -653,45 +687,6 @@ struct TileImpl {
     uint32_t n_chains = 0;
     uint32_t n_sm = 148;
 };
-
-}  // namespace
-
-namespace {
-
-// Page-locked staging buffer for the per-column records (one per process, grown on demand, kept for the life of the
-// process): cudaMemcpyAsync from pageable memory goes through the driver's bounce buffer (~3 ms for the 17 MB of a
-// 50k-column problem), from page-locked memory the DMA engine reads it directly.  WHMEC_PINNED_STAGING=1 (experimental,
-// off by default until it has been timed on a GPU); any failure falls back to the pageable copies.
-struct PinnedStage {
-    std::mutex m;
-    char *p = nullptr;
-    size_t cap = 0;
-    // Locks the buffer and returns at least `bytes` of page-locked memory, or nullptr (nothing locked).
-    char *acquire(size_t bytes) {
-        m.lock();
-        if (cap < bytes) {
-            if (p) cudaFreeHost(p);
-            p = nullptr;
-            cap = 0;
-            const size_t want = bytes + bytes / 4;
-            if (cudaHostAlloc((void **)&p, want, cudaHostAllocPortable) != cudaSuccess) {
-                cudaGetLastError();  // clear the sticky error of the failed allocation
-                p = nullptr;
-                m.unlock();
-                return nullptr;
-            }
-            cap = want;
-        }
-        return p;
-    }
-    void release() { m.unlock(); }
-};
-PinnedStage g_stage;
-
-bool pinned_staging_enabled() {
-    const char *e = std::getenv("WHMEC_PINNED_STAGING");
-    return e && e[0] == '1';  // measured on the B200 (round 2): not faster than the driver's pageable path (h2d 3.0 vs 2.4 ms of a 17 MB upload) -> off
-}
 
 }  // namespace
 
@@ -804,7 +799,9 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     }
     // columns of every chain inside every segment
     const size_t K = I->segs.size();
-    std::vector<uint32_t> seg_lo(K * I->n_chains, 1), seg_hi(K * I->n_chains, 0);
+    std::vector<uint32_t> &seg_lo = I->seg_lo, &seg_hi = I->seg_hi;
+    seg_lo.assign(K * I->n_chains, 1);
+    seg_hi.assign(K * I->n_chains, 0);
     for (size_t sgi = 0; sgi < K; ++sgi)
         for (uint32_t r = I->segs[sgi].r0; r < I->segs[sgi].r1; ++r)
             for (uint32_t q = ts.round_begin[r]; q < ts.round_begin[r + 1]; ++q) {
@@ -825,7 +822,6 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     CUDA_TRY(cudaMallocAsync((void **)&I->d_seg_hi, seg_hi.size() * 4, stream));
     CUDA_TRY(cudaMemcpyAsync(I->d_seg_lo, seg_lo.data(), seg_lo.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(I->d_seg_hi, seg_hi.data(), seg_hi.size() * 4, cudaMemcpyHostToDevice, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));  // seg_lo / seg_hi are stack-local
     if (K > 1) CUDA_TRY(cudaMallocAsync((void **)&I->d_ckpt, (uint64_t)(K - 1) * (ts.state_words + 1) * 4, stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol), stream));
@@ -853,30 +849,10 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
         q.off = total;
         total += (q.bytes + 255) & ~(size_t)255;
     }
-    char *stage = pinned_staging_enabled() ? g_stage.acquire(total) : nullptr;
-    if (stage) {
-        // host copy into the page-locked buffer by the worker pool (1 MB tasks), then four DMA transfers
-        constexpr size_t TASK = 1 << 20;
-        std::vector<std::pair<uint32_t, size_t>> tasks;  // (piece, offset inside the piece)
-        for (uint32_t q = 0; q < 4; ++q)
-            for (size_t o = 0; o < pieces[q].bytes; o += TASK) tasks.emplace_back(q, o);
-        parallel_tasks((uint32_t)tasks.size(), host_threads(16), [&](uint32_t t) {
-            const Piece &q = pieces[tasks[t].first];
-            const size_t o = tasks[t].second;
-            std::memcpy(stage + q.off + o, (const char *)q.src + o, std::min(TASK, q.bytes - o));
-        });
-        cudaError_t e = cudaSuccess;
-        for (const Piece &q : pieces)
-            if (e == cudaSuccess && q.bytes) {
-                h2d += q.bytes;
-                e = cudaMemcpyAsync(q.dst, stage + q.off, q.bytes, cudaMemcpyHostToDevice, stream);
-            }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // the buffer is shared: hold it until the DMA is done
-        g_stage.release();
-        CUDA_TRY(e);
-    } else {
-        for (const Piece &q : pieces) CUDA_TRY(up(q.dst, q.src, q.bytes));
-    }
+    // the records sit in page-locked memory when the library's staging pool is installed (hostpool.h: StagedVec): each array
+    // is then ONE asynchronous DMA transfer that the sweep's first launch queues behind; from pageable memory (pool off or
+    // exhausted) the same calls go through the driver's bounce buffer
+    for (const Piece &q : pieces) CUDA_TRY(up(q.dst, q.src, q.bytes));
     {
         int dev = 0, sms = 148;
         CUDA_TRY(cudaGetDevice(&dev));
@@ -886,7 +862,7 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     CUDA_TRY(cudaFuncSetAttribute(tile_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem)));
     if (timing) {
         auto qms = [](cclk::time_point a, cclk::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        std::fprintf(stderr, "[whmec] tiles.create: segments + seg tables (1 sync) + %.1f MB of allocations %.2f ms, upload calls (%.1f MB) %.2f ms\n",
+        std::fprintf(stderr, "[whmec] tiles.create: segments + seg tables + %.1f MB of allocations %.2f ms, upload calls (%.1f MB) %.2f ms\n",
                      (double)((I->arena_words + ts.state_words) * 4) / 1e6, qms(tq0, tq1), (double)total / 1e6, qms(tq1, cclk::now()));
     }
     return WHMEC_OK;

@@ -65,31 +65,50 @@ WHMEC_HD uint32_t tile_shift_in_sign(uint32_t bits, uint32_t t) {
 // MIRROR (column of a mirrored panel with TileCol::km == 1, see tile_device.h): the back-pointer of the mirror output ~o,
 // which no tile computes, is the same comparison with the opposite tie-break parity: sign(v1 - v0 - !par) ^ !par.  It goes to
 // `emit.mirror(word, bit)` / `emit.store_mirror(bits)` (the second section of the tile's slice).
-template <int LG, bool HASK0, bool SHARE, bool PACKED = false, bool MIRROR = false, class Emit>
-WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
-                          uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
+// The part of a fast column that does not touch the previous projection: the thread's addresses, the column's constants and
+// the subset sums E() of its outputs.  The kernel's steady-state loop computes it for column j + 1 between ARRIVING at the
+// column barrier and WAITING on it (split barrier), so that this work fills the time in which the warps of the block drift apart.
+template <int LG>
+struct FastPrep {
+    const TilePair *sin2;
+    uint32_t *so;
+    uint32_t half, wp, wn, K0, K12, par0;
+    uint32_t ue[1 << LG];
+};
+
+template <int LG, bool SHARE>
+WHMEC_HD void column_fast_prep(FastPrep<LG> &pr, const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
+                               uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, uint32_t tid) {
     constexpr int IT = 1 << LG;
     const uint32_t lane = tid & 31u, warp = tid >> 5;
     const uint32_t obase = warp * (IT * 32u) + lane;      // o = obase + 32*it  (+ nout/2 for the shared twin)
     const uint32_t pmask = (1u << (tc.l_in - 1)) - 1u;    // candidate pairs of the previous projection
-    const TilePair *sin2 = reinterpret_cast<const TilePair *>(Sin) + (obase & pmask);
-    uint32_t *so = Sout + obase;
-    const uint32_t half = 1u << (tc.l_out - 1);
-    const uint32_t wp = (uint32_t)tc.w_local[0];
-    const uint32_t wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
-    const uint32_t K0 = tc.K0, K12 = tc.K12;
-    const uint32_t par0 = (WHMEC_POPC(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
-    uint32_t bits = 0, mbits = 0;
-    uint32_t ue[IT];
-    ue[0] = (uint32_t)(TW[warp] + T5[lane]);
+    pr.sin2 = reinterpret_cast<const TilePair *>(Sin) + (obase & pmask);
+    pr.so = Sout + obase;
+    pr.half = 1u << (tc.l_out - 1);
+    pr.wp = (uint32_t)tc.w_local[0];
+    pr.wn = SHARE ? (uint32_t)tc.w_local[tc.l_out] : 0u;  // the read that starts in this column
+    pr.K0 = tc.K0;
+    pr.K12 = tc.K12;
+    pr.par0 = (WHMEC_POPC(obase) + (cg & 1u)) & 1u;  // parity of the bits above the dropped one
+    pr.ue[0] = (uint32_t)(TW[warp] + T5[lane]);
 #pragma unroll
-    for (int it = 1; it < IT; ++it) ue[it] = ue[it & (it - 1)] + (uint32_t)tc.w_local[6 + cx_ctz(it)];
+    for (int it = 1; it < IT; ++it) pr.ue[it] = pr.ue[it & (it - 1)] + (uint32_t)tc.w_local[6 + cx_ctz(it)];
+}
+
+template <int LG, bool HASK0, bool SHARE, bool PACKED, bool MIRROR, class Emit>
+WHMEC_HD void column_fast_body(const FastPrep<LG> &pr, Emit emit) {
+    constexpr int IT = 1 << LG;
+    const TilePair *sin2 = pr.sin2;
+    uint32_t *so = pr.so;
+    const uint32_t half = pr.half, wp = pr.wp, wn = pr.wn, K0 = pr.K0, K12 = pr.K12, par0 = pr.par0;
+    uint32_t bits = 0, mbits = 0;
 #pragma unroll
     for (int it = 0; it < IT; ++it) {
         const TilePair s = sin2[it * 32];
         const uint32_t par = par0 ^ (uint32_t)cx_parity(it);
         {
-            const uint32_t u0 = ue[it], u1 = u0 + wp;
+            const uint32_t u0 = pr.ue[it], u1 = u0 + wp;
             uint32_t c0 = WHMEC_UMIN(u0, K12 - u0), c1 = WHMEC_UMIN(u1, K12 - u1);
             if (HASK0) { c0 = WHMEC_UMIN(c0, K0); c1 = WHMEC_UMIN(c1, K0); }
             const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
@@ -104,7 +123,7 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
             }
         }
         if (SHARE) {  // twin output: the new read on side 1 (one more bit above the dropped one)
-            const uint32_t u0 = ue[it] + wn, u1 = u0 + wp;
+            const uint32_t u0 = pr.ue[it] + wn, u1 = u0 + wp;
             uint32_t c0 = WHMEC_UMIN(u0, K12 - u0), c1 = WHMEC_UMIN(u1, K12 - u1);
             if (HASK0) { c0 = WHMEC_UMIN(c0, K0); c1 = WHMEC_UMIN(c1, K0); }
             const uint32_t v0 = c0 + s.x, v1 = c1 + s.y;
@@ -133,6 +152,14 @@ WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, con
         emit.store((bits ^ cm ^ (par0 ? all : 0u)) & all);
         if (MIRROR) emit.store_mirror((mbits ^ cm ^ all ^ (par0 ? all : 0u)) & all);  // q = !par throughout
     }
+}
+
+template <int LG, bool HASK0, bool SHARE, bool PACKED = false, bool MIRROR = false, class Emit>
+WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
+                          uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
+    FastPrep<LG> pr;
+    column_fast_prep<LG, SHARE>(pr, tc, TW, T5, cg, Sin, Sout, tid);
+    column_fast_body<LG, HASK0, SHARE, PACKED, MIRROR>(pr, emit);
 }
 
 }  // namespace whmec

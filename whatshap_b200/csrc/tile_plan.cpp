@@ -367,21 +367,25 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         }
     }
     const auto t1 = tnow();
-    // make the chain-relative offsets absolute
-    uint64_t state_words = 0, bp_words = 0;
+    // make the chain-relative offsets absolute: a prefix over the chains, then every chain on its own (host threads)
+    std::vector<uint64_t> state_base(n_chains + 1, 0), bp_base(n_chains + 1, 0);
+    size_t max_panels = 0;
     for (uint32_t c = 0; c < n_chains; ++c) {
-        for (Panel &P : per_chain[c]) {
-            P.in_off += state_words;
-            P.out_off += state_words;
-        }
-        for (uint32_t k = pk.chain_begin[c]; k < pk.chain_begin[c + 1]; ++k) ts.cols[k].bp_off += bp_words;
-        state_words += chain_state_words[c];
-        bp_words += chain_bp_words[c];
+        state_base[c + 1] = state_base[c] + chain_state_words[c];
+        bp_base[c + 1] = bp_base[c] + chain_bp_words[c];
         ts.state_traffic_bytes += chain_traffic[c];
+        max_panels = std::max(max_panels, per_chain[c].size());
     }
-
-    // hand-off layouts between consecutive panels of a chain (see Panel in tile_plan.h)
-    for (uint32_t c = 0; c < n_chains; ++c)
+    const uint64_t state_words = state_base[n_chains], bp_words = bp_base[n_chains];
+    const uint32_t asm_threads = std::min(host_threads(32), std::max(1u, n_chains / 2));
+    parallel_tasks(n_chains, asm_threads, [&](uint32_t c) {
+        for (Panel &P : per_chain[c]) {
+            P.in_off += state_base[c];
+            P.out_off += state_base[c];
+        }
+        if (bp_base[c])
+            for (uint32_t k = pk.chain_begin[c]; k < pk.chain_begin[c + 1]; ++k) ts.cols[k].bp_off += bp_base[c];
+        // hand-off layouts between consecutive panels of the chain (see Panel in tile_plan.h)
         for (size_t q = 0; q + 1 < per_chain[c].size(); ++q) {
             Panel &A = per_chain[c][q], &B = per_chain[c][q + 1];
             const PanelSets &sa = per_chain_sets[c][q], &sb = per_chain_sets[c][q + 1];
@@ -393,39 +397,44 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             if (sb.Lold.size() < sa.G.size()) continue;
             const size_t j = sb.Lold.size() - sa.G.size();
             if (j < 2 || j > sa.Lout.size()) continue;  // chunks of at least 4 entries
-            std::vector<uint32_t> want = sa.G;
-            want.insert(want.end(), sa.Lout.begin(), sa.Lout.begin() + j);
-            if (want != sb.Lold) continue;
+            // the consumer's old local reads must be the producer's global reads followed by its first j local reads
+            if (!std::equal(sa.G.begin(), sa.G.end(), sb.Lold.begin()) ||
+                !std::equal(sa.Lout.begin(), sa.Lout.begin() + j, sb.Lold.begin() + sa.G.size()))
+                continue;
             A.out_layout = 1;
             B.in_layout = 1;
             B.in_gA = (uint32_t)sa.G.size();
             B.in_j = (uint32_t)j;
             B.in_sA = A.s_out;
         }
+    });
 
-    // launch rounds: round r = r-th panel of every chain that has one
-    size_t max_panels = 0;
-    for (auto &v : per_chain) max_panels = std::max(max_panels, v.size());
-    for (size_t r = 0; r < max_panels; ++r) {
-        ts.round_begin.push_back((uint32_t)ts.panels.size());
-        uint32_t tiles = 0;
+    // launch rounds: round r = r-th panel of every chain that has one; every round fills its own slice of the panel array
+    ts.round_begin.assign(max_panels + 1, 0);
+    for (uint32_t c = 0; c < n_chains; ++c)
+        for (size_t r = 0; r < per_chain[c].size(); ++r) ++ts.round_begin[r + 1];
+    for (size_t r = 0; r < max_panels; ++r) ts.round_begin[r + 1] += ts.round_begin[r];
+    ts.panels.resize(ts.round_begin[max_panels]);
+    ts.round_tiles.assign(max_panels, 0);
+    ts.round_tile_log.assign(max_panels, -1);
+    parallel_tasks((uint32_t)max_panels, asm_threads, [&](uint32_t r) {
+        uint32_t tiles = 0, at = ts.round_begin[r];
+        int32_t tlog = -1;
+        bool uniform = true;
         for (uint32_t c = 0; c < n_chains; ++c)
             if (r < per_chain[c].size()) {
-                Panel P = per_chain[c][r];
+                Panel &P = ts.panels[at];
+                P = per_chain[c][r];
                 P.tile_begin = tiles;
                 tiles += 1u << (P.g - P.half);
-                ts.panels.push_back(P);
+                const int32_t mine = (int32_t)(P.g - P.half);
+                if (at == ts.round_begin[r]) tlog = mine;
+                else if (tlog != mine) uniform = false;
+                ++at;
             }
-        ts.round_tiles.push_back(tiles);
-        int32_t tlog = -1;
-        for (uint32_t q = ts.round_begin.back(); q < ts.panels.size(); ++q) {
-            const int32_t mine = (int32_t)(ts.panels[q].g - ts.panels[q].half);
-            tlog = (q == ts.round_begin.back() || tlog == mine) ? mine : -2;
-            if (tlog == -2) break;
-        }
-        ts.round_tile_log.push_back(tlog < 0 ? -1 : tlog);
-    }
-    ts.round_begin.push_back((uint32_t)ts.panels.size());
+        ts.round_tiles[r] = tiles;
+        ts.round_tile_log[r] = (uniform && tlog >= 0) ? tlog : -1;
+    });
     ts.state_words = state_words;
     ts.bp_words = bp_words;
     ts.eligible = true;

@@ -89,8 +89,8 @@ struct Panel {
 struct TileSchedule {
     bool eligible = false;
     std::string why;                      // reason when not eligible
-    RawVec<TileCol> cols;                 // [n] indexed by global column
-    std::vector<Panel> panels;            // grouped by launch round
+    StagedVec<TileCol> cols;              // [n] indexed by global column (uploaded as it is)
+    StagedVec<Panel> panels;              // grouped by launch round (uploaded as it is)
     std::vector<uint32_t> round_begin;    // panels of round r: [round_begin[r], round_begin[r+1])
     std::vector<uint32_t> round_tiles;    // CTAs per round
     std::vector<int32_t> round_tile_log;  // log2 tiles per panel if every panel of the round has the same number, else -1

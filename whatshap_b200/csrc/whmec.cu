@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <stdexcept>
 #include <string>
@@ -926,6 +927,135 @@ struct DevBuf {
     }
 };
 
+// ---- page-locked staging blocks: the memory behind StagedVec (hostpool.h) ------------------------------------------------
+// The packer and the planner write the arrays that are uploaded as they are (per-column records, cost functions, panels)
+// straight into page-locked blocks, so that an upload is one asynchronous DMA transfer per array: from pageable memory
+// cudaMemcpyAsync goes through the driver's bounce buffer and blocks the calling thread (B200 box: 2.5 ms for the 18.8 MB
+// of cfg3, up to 8 ms for the cost functions of cfg5).  Blocks are kept for the life of the process and reused
+// (cudaHostAlloc costs milliseconds); small arrays stay on the heap.  WHMEC_PINNED_UPLOAD=0 switches the pool off (test hook).
+struct PinnedPool {
+    struct Block {
+        void *p;
+        size_t cap;
+    };
+    static constexpr size_t MIN_BYTES = 128u << 10;   // smaller arrays: heap (their upload is a latency-bound call either way)
+    static constexpr size_t MAX_CACHED = 2ull << 30;  // free blocks kept for reuse
+    std::mutex m;
+    std::vector<Block> free_blocks;
+    std::vector<Block> live;  // handed out (a handful per plan)
+    size_t cached = 0;
+    std::atomic<bool> enabled{true};  // re-read from the environment by every plan (test hook)
+
+    void *alloc(size_t bytes) {
+        if (bytes < MIN_BYTES || !enabled.load(std::memory_order_relaxed)) return nullptr;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            size_t best = SIZE_MAX;
+            for (size_t i = 0; i < free_blocks.size(); ++i)
+                if (free_blocks[i].cap >= bytes && free_blocks[i].cap <= 2 * bytes &&
+                    (best == SIZE_MAX || free_blocks[i].cap < free_blocks[best].cap))
+                    best = i;
+            if (best != SIZE_MAX) {
+                Block b = free_blocks[best];
+                free_blocks.erase(free_blocks.begin() + (long)best);
+                cached -= b.cap;
+                live.push_back(b);
+                return b.p;
+            }
+        }
+        const size_t cap = (bytes + bytes / 8 + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);  // 12.5 % slack, whole MiB
+        void *p = nullptr;
+        if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
+            cudaGetLastError();  // clear the error of the failed allocation: the caller falls back to the heap
+            return nullptr;
+        }
+        std::lock_guard<std::mutex> lk(m);
+        live.push_back(Block{p, cap});
+        return p;
+    }
+    bool release(void *p) {
+        Block b{nullptr, 0};
+        std::vector<Block> drop;
+        {
+            std::lock_guard<std::mutex> lk(m);
+            for (size_t i = 0; i < live.size(); ++i)
+                if (live[i].p == p) {
+                    b = live[i];
+                    live[i] = live.back();
+                    live.pop_back();
+                    break;
+                }
+            if (!b.p) return false;
+            free_blocks.push_back(b);
+            cached += b.cap;
+            while (cached > MAX_CACHED && !free_blocks.empty()) {  // oldest first
+                drop.push_back(free_blocks.front());
+                cached -= free_blocks.front().cap;
+                free_blocks.erase(free_blocks.begin());
+            }
+        }
+        for (const Block &d : drop) cudaFreeHost(d.p);
+        return true;
+    }
+};
+PinnedPool g_pinned;
+
+void install_stage_hooks() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        set_stage_hooks(StageHooks{[](size_t bytes) { return g_pinned.alloc(bytes); }, [](void *p) { return g_pinned.release(p); }});
+    });
+    const char *e = std::getenv("WHMEC_PINNED_UPLOAD");
+    g_pinned.enabled.store(!(e && e[0] == '0'), std::memory_order_relaxed);
+}
+
+// ---- streams and events are reused across plans (creating them costs ~0.5 ms per solve) -----------------------------------
+struct StreamSet {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+struct StreamCache {
+    static constexpr int MAX_DEV = 64;
+    static constexpr size_t KEEP = 8;
+    std::mutex m;
+    std::vector<StreamSet> idle[MAX_DEV];
+    cudaError_t acquire(int device, StreamSet &out) {
+        if (device >= 0 && device < MAX_DEV) {
+            std::lock_guard<std::mutex> lk(m);
+            if (!idle[device].empty()) {
+                out = idle[device].back();
+                idle[device].pop_back();
+                return cudaSuccess;
+            }
+        }
+        out = StreamSet{};
+        cudaError_t e = cudaStreamCreateWithFlags(&out.stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&out.ev0);
+        if (e == cudaSuccess) e = cudaEventCreate(&out.ev1);
+        if (e != cudaSuccess) destroy(out);
+        return e;
+    }
+    static void destroy(StreamSet &s) {
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = StreamSet{};
+    }
+    // the stream must be idle (synchronised) and healthy
+    void give_back(int device, StreamSet s) {
+        if (!s.stream) return;
+        if (device >= 0 && device < MAX_DEV) {
+            std::lock_guard<std::mutex> lk(m);
+            if (idle[device].size() < KEEP) {
+                idle[device].push_back(s);
+                return;
+            }
+        }
+        destroy(s);
+    }
+};
+StreamCache g_streams;
+
 void keep_pool_memory(int device) {
     static std::atomic<bool> done[64];  // zero-initialised; a second thread repeating the call is harmless
     if (device < 0 || device >= 64 || done[device].load()) return;
@@ -981,6 +1111,9 @@ struct whmec_plan {
 
     ~whmec_plan() {
         cudaSetDevice(device);
+        // nothing of this plan may still be in flight when its buffers go back to their pools: the page-locked host blocks
+        // behind pk / the tile schedule are the sources of asynchronous uploads
+        const bool healthy = !stream || cudaStreamSynchronize(stream) == cudaSuccess;
         d_cols.release(); d_fn_c0.release(); d_fn_group.release(); d_val[0].release(); d_val[1].release();
         d_arena.release(); d_chain_begin.release(); d_path_index.release(); d_path_tv.release();
         d_result.release(); d_fn_delta.release(); d_keys.release();
@@ -989,12 +1122,9 @@ struct whmec_plan {
         d_chain_rows.release(); d_chain_in.release(); d_chain_out.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        if (ev0) cudaEventDestroy(ev0);
-        if (ev1) cudaEventDestroy(ev1);
-        if (stream) {
-            cudaStreamSynchronize(stream);
-            cudaStreamDestroy(stream);
-        }
+        StreamSet set{stream, ev0, ev1};
+        if (stream && healthy) g_streams.give_back(device, set);  // (the frees above are stream-ordered: whoever takes the stream next queues behind them)
+        else StreamCache::destroy(set);
     }
 };
 
@@ -1014,6 +1144,11 @@ void keep_host_memory() {
 
 int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::string &msg, int segment = 0) {
     keep_host_memory();
+    // the packer's upload arrays come from page-locked blocks, which belong to a CUDA context: select the device first
+    // (a failure here is reported by the checked call below, after the input has been validated as before)
+    if (cudaSetDevice(device) == cudaSuccess) install_stage_hooks();
+    else cudaGetLastError();
+    pl->device = device;
     pl->segment = segment;
     // single-individual problems normally run on the tile kernel, which needs no per-read cost deltas
     const char *force = std::getenv("WHMEC_FORCE_COLUMN_KERNEL");  // test hook: exercise the general path on T == 1
@@ -1050,9 +1185,13 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         }
     CUDA_TRY(cudaSetDevice(device));
     keep_pool_memory(device);
-    CUDA_TRY(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreate(&pl->ev0));
-    CUDA_TRY(cudaEventCreate(&pl->ev1));
+    {
+        StreamSet set;
+        CUDA_TRY(g_streams.acquire(device, set));
+        pl->stream = set.stream;
+        pl->ev0 = set.ev0;
+        pl->ev1 = set.ev1;
+    }
     const uint32_t n = pk.n;
 
     CUDA_TRY(pl->d_path_index.alloc(n, pl->stream));
