@@ -50,6 +50,20 @@ void fast_column(const TileCol &tc, const int32_t *TW, const int32_t *T5, uint32
     for (uint32_t tid = 0; tid < 1024; ++tid) {
         RecordEmit emit{bpw + (tid >> 5) * IT, tid & 31u, bpw, tid, tile_fast_bits_per_thread(tc), tc.bp_tile_words};
         const bool k0 = tc.K0 < TILE_KINF, packed = (tc.pad2 & 1u) != 0;
+        if constexpr (SHARE && (LG == 2 || LG == 3)) {
+            // the shape of the kernel's steady-state panels: run the kernel's own preparation of such a column (SteadyCol record +
+            // constants of the panel, tile.cu: steady_columns) instead of column_fast_prep
+            if (packed && !k0) {
+                const SteadyCol sc = steady_col(tc, cg);
+                const uint32_t obase = (tid >> 5) * (IT * 32u) + (tid & 31u);
+                FastPrep<LG> pr;
+                steady_prep<LG>(pr, sc, TW[tid >> 5], T5[tid & 31u], Sin, Sout, obase, obase & ((1u << (tc.l_in - 1)) - 1u),
+                                1u << (tc.l_out - 1), popc32(obase));
+                if (mirror) column_fast_body<LG, false, true, true, true>(pr, emit);
+                else column_fast_body<LG, false, true, true, false>(pr, emit);
+                continue;
+            }
+        }
 #define EMUL_FAST(HK, PK, MR) column_fast<LG, HK, SHARE, PK, MR>(tc, TW, T5, cg, Sin, Sout, emit, tid)
         if (mirror) {
             if (packed) { if (k0) EMUL_FAST(true, true, true); else EMUL_FAST(false, true, true); }

@@ -49,6 +49,8 @@ struct TileSmem {
     int32_t TWs[TC_CHUNK][32];  // steady-state panels: the tables of every column of the panel, built once
     int32_t T5s[TC_CHUNK][32];
     uint32_t cgs[TC_CHUNK];
+    SteadyCol scs[TC_CHUNK];            // steady-state panels: the per-column constants of column_fast, 32 bytes each
+    unsigned long long bp_at[TC_CHUNK]; // steady-state panels: first back-pointer word of this tile in column j (bp_off + tile * stride)
     Panel P;
     uint32_t cg[2];
     uint32_t a_col[TC_CHUNK];
@@ -248,23 +250,28 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 // The barrier is an mbarrier with one arrival per warp (the warp's lanes are ordered by __syncwarp before lane 0 arrives;
 // arrive = release, try_wait = acquire at CTA scope).  Every thread of the block runs the same number of iterations.
 template <int LG, bool MR>
-__device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint32_t tile, uint32_t *__restrict__ arena, uint32_t &cur,
-                                               uint32_t &col_phase, uint32_t tid) {
+__device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint32_t *__restrict__ arena, uint32_t &cur, uint32_t &col_phase,
+                                               uint32_t tid) {
     constexpr int BITS = 2 << LG;  // outputs (= back-pointer bits) per thread and column: 2^LG twins
+    constexpr uint32_t IT = 1u << LG;
+    // constants of the panel (l_in, l_out are those of its first column)
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t obase = warp * (IT * 32u) + lane;
+    const uint32_t pair_off = obase & ((1u << (S.tcs[0].l_in - 1)) - 1u);
+    const uint32_t half = 1u << (S.tcs[0].l_out - 1);
+    const uint32_t pop = popc32(obase);
+    const uint32_t section = S.tcs[0].bp_tile_words;
     FastPrep<LG> pr;
-    column_fast_prep<LG, true>(pr, S.tcs[0], S.TWs[0], S.T5s[0], S.cgs[0], S.buf[cur], S.buf[cur ^ 1], tid);
-    uint32_t *bpw = arena + S.tcs[0].bp_off + (uint64_t)tile * S.tcs[0].bp_tile_stride;
-    uint32_t section = S.tcs[0].bp_tile_words;
+    steady_prep<LG>(pr, S.scs[0], S.TWs[0][warp], S.T5s[0][lane], S.buf[cur], S.buf[cur ^ 1], obase, pair_off, half, pop);
+    uint32_t *bpw = arena + S.bp_at[0];
     for (uint32_t j = 0; j < ncol; ++j) {
         column_fast_body<LG, false, true, true, MR>(pr, PackedEmit<BITS>{bpw, tid, section});
         __syncwarp();
-        if ((tid & 31u) == 0) mbar_arrive(&S.col_bar);
+        if (lane == 0) mbar_arrive(&S.col_bar);
         cur ^= 1;
         if (j + 1 < ncol) {
-            const TileCol &tn = S.tcs[j + 1];
-            column_fast_prep<LG, true>(pr, tn, S.TWs[j + 1], S.T5s[j + 1], S.cgs[j + 1], S.buf[cur], S.buf[cur ^ 1], tid);
-            bpw = arena + tn.bp_off + (uint64_t)tile * tn.bp_tile_stride;
-            section = tn.bp_tile_words;
+            steady_prep<LG>(pr, S.scs[j + 1], S.TWs[j + 1][warp], S.T5s[j + 1][lane], S.buf[cur], S.buf[cur ^ 1], obase, pair_off, half, pop);
+            bpw = arena + S.bp_at[j + 1];
         }
         mbar_wait(&S.col_bar, col_phase);
         col_phase ^= 1u;
@@ -441,18 +448,23 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
             if (j < ncol) {
                 if (idx < 32) S.TWs[j][idx] = tile_fast_warp_entry(S.tcs[j], tile, idx);
                 else S.T5s[j][idx - 32] = tile_fast_lane_entry(S.tcs[j], idx - 32);
-                if (idx == 63) S.cgs[j] = tile_cg(S.tcs[j], tile);
+                if (idx == 63) {
+                    const uint32_t cg = tile_cg(S.tcs[j], tile);
+                    S.cgs[j] = cg;
+                    S.scs[j] = steady_col(S.tcs[j], cg);
+                    S.bp_at[j] = S.tcs[j].bp_off + (uint64_t)tile * S.tcs[j].bp_tile_stride;
+                }
             }
         }
         const bool mirror = S.tcs[0].half && S.tcs[0].km != 0;
         const uint32_t lg = P.steady - 1u;
         __syncthreads();  // tables ready; the tile's input is in place
         if (lg == 3) {
-            if (mirror) steady_columns<3, true>(S, ncol, tile, arena, cur, col_phase, tid);
-            else steady_columns<3, false>(S, ncol, tile, arena, cur, col_phase, tid);
+            if (mirror) steady_columns<3, true>(S, ncol, arena, cur, col_phase, tid);
+            else steady_columns<3, false>(S, ncol, arena, cur, col_phase, tid);
         } else {
-            if (mirror) steady_columns<2, true>(S, ncol, tile, arena, cur, col_phase, tid);
-            else steady_columns<2, false>(S, ncol, tile, arena, cur, col_phase, tid);
+            if (mirror) steady_columns<2, true>(S, ncol, arena, cur, col_phase, tid);
+            else steady_columns<2, false>(S, ncol, arena, cur, col_phase, tid);
         }
     } else
     for (uint32_t k = P.col_begin; k < P.col_end; ++k) {

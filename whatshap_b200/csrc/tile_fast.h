@@ -154,6 +154,48 @@ WHMEC_HD void column_fast_body(const FastPrep<LG> &pr, Emit emit) {
     }
 }
 
+// Steady-state panels (every column the twin fast column of one tile size): what column_fast_prep reads from the 288-byte
+// TileCol, as one 32-byte record per column (two 128-bit loads), built once per (tile, panel) next to the warp / lane tables.
+struct alignas(16) SteadyCol {
+    int32_t wp, wn;   // w_local[0] (the read that ends), w_local[l_out] (the read that starts)
+    int32_t w[3];     // w_local[6 .. 8]: output bits 5 .. 7, the bits a thread's 2^LG outputs differ in
+    uint32_t K12, cg, pad;
+};
+
+WHMEC_HD SteadyCol steady_col(const TileCol &tc, uint32_t cg) {
+    SteadyCol sc;
+    sc.wp = tc.w_local[0];
+    sc.wn = tc.w_local[tc.l_out];
+    sc.w[0] = tc.w_local[6];
+    sc.w[1] = tc.w_local[7];
+    sc.w[2] = tc.w_local[8];
+    sc.K12 = tc.K12;
+    sc.cg = cg;
+    sc.pad = 0;
+    return sc;
+}
+
+// column_fast_prep<LG, true> of a steady-state column from its SteadyCol and the constants of the panel:
+// pair_off = obase & pmask, half = 2^(l_out - 1) and popc(obase) do not change inside a panel (l_in and l_out are the same for
+// all its columns).  K0 is not used (steady columns have no homozygous term).
+template <int LG>
+WHMEC_HD void steady_prep(FastPrep<LG> &pr, const SteadyCol &sc, int32_t tw, int32_t t5, const uint32_t *__restrict__ Sin,
+                          uint32_t *__restrict__ Sout, uint32_t obase, uint32_t pair_off, uint32_t half, uint32_t pop_obase) {
+    constexpr int IT = 1 << LG;
+    static_assert(LG <= 3, "SteadyCol holds the weights of three output bits");
+    pr.sin2 = reinterpret_cast<const TilePair *>(Sin) + pair_off;
+    pr.so = Sout + obase;
+    pr.half = half;
+    pr.wp = (uint32_t)sc.wp;
+    pr.wn = (uint32_t)sc.wn;
+    pr.K0 = 0;
+    pr.K12 = sc.K12;
+    pr.par0 = (pop_obase + (sc.cg & 1u)) & 1u;
+    pr.ue[0] = (uint32_t)(tw + t5);
+#pragma unroll
+    for (int it = 1; it < IT; ++it) pr.ue[it] = pr.ue[it & (it - 1)] + (uint32_t)sc.w[cx_ctz(it)];
+}
+
 template <int LG, bool HASK0, bool SHARE, bool PACKED = false, bool MIRROR = false, class Emit>
 WHMEC_HD void column_fast(const TileCol &tc, const int32_t *__restrict__ TW, const int32_t *__restrict__ T5,
                           uint32_t cg, const uint32_t *__restrict__ Sin, uint32_t *__restrict__ Sout, Emit emit, uint32_t tid) {
