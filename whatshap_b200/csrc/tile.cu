@@ -667,11 +667,39 @@ __global__ void __launch_bounds__(32) tile_backtrace_kernel(const ColMeta *__res
         for (uint32_t w = lane; w < (n + 1) * CW; w += 32) ((uint32_t *)s_cols)[w] = ((const uint32_t *)(cols + lo))[w];
         for (uint32_t w = lane; w < n * TW; w += 32) ((uint32_t *)s_tcols)[w] = ((const uint32_t *)(tcols + lo))[w];
         __syncwarp();
-        if (lane == 0)
-            for (uint32_t k = hi; k > lo; --k) {
+        // The walk is a chain of dependent loads (one back-pointer per column, ~1 us each from HBM).  Runs of columns with 1-bit
+        // back-pointers (the steady state) are walked SPECULATIVELY, up to 5 columns per memory round trip: lane l stands for
+        // the node (level L, hypothesis h) of the binary tree of possible paths, l + 1 = 2^L + h; it applies the L assumed
+        // back-pointer bits of h to x (index arithmetic only) and loads the back-pointer its node would read; the true path is
+        // then picked out of the 2^D - 1 loaded bits with D shuffles.  Other columns take the ordinary step (all lanes alike).
+        for (uint32_t k = hi; k > lo;) {
+            uint32_t D = 0;
+            while (D < 5 && k - D > lo && s_tcols[k - 1 - D - lo].bp_width == 1) ++D;
+            if (D >= 2) {
+                const uint32_t L = 31u - (uint32_t)__clz((int)(lane + 1)), h = lane + 1 - (1u << L);
+                uint32_t xl = x, b = 0;
+                if (L < D) {
+                    for (uint32_t i = 0; i < L; ++i)
+                        xl = candidate_index(s_cols[k - 1 - i - lo], xl & low_mask(s_cols[k - i - lo].bw), (h >> i) & 1u);
+                    b = tile_backtrace_bp(s_cols[k - L - lo].bw, s_cols[k - 1 - L - lo], s_tcols[k - 1 - L - lo], arena, xl);
+                }
+                uint32_t hh = 0, xi = x, bi = 0;
+                for (uint32_t i = 0; i < D; ++i) {  // level i of the true path: column k - i, whose cell is xi
+                    const uint32_t src = (1u << i) - 1u + hh;
+                    xi = __shfl_sync(0xFFFFFFFFu, xl, src);
+                    bi = __shfl_sync(0xFFFFFFFFu, b, src);
+                    if (i > 0 && lane == 0) s_path[k - i - lo] = xi;
+                    hh |= bi << i;
+                }
+                x = candidate_index(s_cols[k - D - lo], xi & low_mask(s_cols[k - D + 1 - lo].bw), bi);
+                if (lane == 0) s_path[k - D - lo] = x;
+                k -= D;
+            } else {
                 x = tile_backtrace_step(s_cols[k - lo].bw, s_cols[k - 1 - lo], s_tcols[k - 1 - lo], arena, x);
-                s_path[k - 1 - lo] = x;
+                if (lane == 0) s_path[k - 1 - lo] = x;
+                --k;
             }
+        }
         __syncwarp();
         if (lane < n) path_index[lo + lane] = s_path[lane];
         __syncwarp();

@@ -137,6 +137,24 @@ WHMEC_HD uint32_t tile_packed_bit_index(const TileCol &tc, uint32_t lo) {
 
 // One backtrace step (pedigreedptable.cpp:155-160): from the cell x of column k (whose backward width is `bw`) to the cell of
 // column k - 1 (records pm / pt) through the tile-layout back-pointers.
+// The back-pointer read by that step (the rank of the winning candidate of the entry x projects to), apart from the step itself:
+// the warp backtrace of tile.cu reads the back-pointers of several columns ahead speculatively.
+WHMEC_HD uint32_t tile_backtrace_bp(uint32_t bw, const ColMeta &pm, const TileCol &pt, const uint32_t *arena, uint32_t x) {
+    const uint32_t o = x & low_mask(bw);   // canonical forward-projection entry of column k-1
+    const uint32_t fmask = low_mask(pm.f);
+    uint32_t tile = pext32(o, pt.gmask_out);
+    uint32_t lo = pext32(o, ~pt.gmask_out & fmask);
+    uint64_t section = 0;
+    if (pt.half && ((tile >> (pt.g - 1)) & 1u)) {  // output of an uncomputed tile: stored by its mirror image
+        tile = ~tile & low_mask(pt.g);
+        lo = ~lo & low_mask(pt.l_out);
+        if (pt.km != 0) section = pt.bp_tile_words;
+    }
+    uint32_t at = lo;
+    if (pt.pad2 & 1u) at = tile_packed_bit_index(pt, lo);  // thread-packed bits
+    return bp_load(arena, pt.bp_off + (uint64_t)tile * pt.bp_tile_stride + section, pt.bp_width, at);
+}
+
 WHMEC_HD uint32_t tile_backtrace_step(uint32_t bw, const ColMeta &pm, const TileCol &pt, const uint32_t *arena, uint32_t x) {
     const uint32_t o = x & low_mask(bw);   // canonical forward-projection entry of column k-1
     const uint32_t fmask = low_mask(pm.f);
