@@ -408,8 +408,9 @@ def main():
         api_dt = time.perf_counter() - api_t0
         assert cost_api == int(sol.cost) and list(superreads[0][0]._allele) == sol.sr_allele[0, 0].tolist(), "object-level and flat results disagree"
         e2e_api = {"value": n_cols * e2e_steps / api_dt, "unit": UNIT, "ms_per_step": 1e3 * api_dt / e2e_steps,
-                   "note": "PedigreeDPTable(readset, recombcost, pedigree) + get_super_reads() on container objects: Python flattening of "
-                           "the ReadSet + whmec_solve + super-read objects"}
+                   "note": "PedigreeDPTable(readset, recombcost, pedigree) + get_super_reads() on container objects: flattening of the "
+                           "ReadSet (from the columnar copy its add() keeps, numpy passes every call, nothing cached between calls) + "
+                           "whmec_solve + super-read objects"}
 
     # ---- strong scaling: ONE problem (rank 0's) sharded over all ranks, end to end from rank 0's host arrays --------
     sharded = None

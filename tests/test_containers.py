@@ -196,3 +196,50 @@ def test_flatten_restates_column_iterator_inputs():
         other = ReadSet()
         other.add(make_read("q", [(10, 0, 1), (20, 0, 1)], sample_id=9))
         _flatten(other, [1, 1], ped, False, None)
+
+
+def _columns_from_objects(rs):
+    """What ReadSet._flat_columns must return: collected again from the Read objects."""
+    import numpy as np
+
+    reads = list(rs)
+    return (np.array([len(r) for r in reads], np.int64), np.array([r.sample_id for r in reads], np.int64),
+            np.array([v.position for r in reads for v in r], np.int64), np.array([v.allele for r in reads for v in r], np.int64),
+            np.array([v.quality for r in reads for v in r], np.int64))
+
+
+def test_readset_columnar_copy_follows_add_sort_and_mutation():
+    """ReadSet keeps a columnar copy of all variants (what the DP is flattened from): it must follow add / sort / subset /
+    pickling and every change made to a stored read through a reference."""
+    import numpy as np
+    import random
+
+    rnd = random.Random(5)
+    rs = ReadSet()
+    for i in range(40):
+        r = Read("read{}".format(rnd.randrange(10 ** 6)) + "_%d" % i, 50, rnd.randrange(3), rnd.randrange(2))
+        start = rnd.randrange(0, 300, 10)
+        for j in range(1 + rnd.randrange(5)):
+            r.add_variant(start + 10 * j, rnd.randrange(2), rnd.randrange(1, 40))
+        rs.add(r)
+        r.add_variant(10 ** 6, 0, 1)  # the set holds a copy: changing the original afterwards does not reach it
+
+    def same():
+        got, want = rs._flat_columns(), _columns_from_objects(rs)
+        return all(np.array_equal(g, w) for g, w in zip(got, want))
+
+    assert same()
+    rs.sort()
+    assert rs._columns is not None and same()  # reordered, not rebuilt
+    assert rs.get_positions() == sorted({v.position for r in rs for v in r})
+    rs[3].add_variant(5000, 1, 7)  # a stored read changed through a reference
+    assert rs._columns is None and same()
+    rs[5][0] = Variant(rs[5][0].position, 1, 99)
+    assert same()
+    sub = rs.subset([0, 2, 5, 7])
+    assert [r.name for r in sub] == [rs[i].name for i in (0, 2, 5, 7)]
+    got, want = sub._flat_columns(), _columns_from_objects(sub)
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))
+    clone = pickle.loads(pickle.dumps(rs))
+    got, want = clone._flat_columns(), _columns_from_objects(rs)
+    assert all(np.array_equal(g, w) for g, w in zip(got, want))

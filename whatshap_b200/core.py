@@ -68,12 +68,24 @@ def _typed(values) -> array:
     return out
 
 
+def _distinct_sorted(values: np.ndarray) -> np.ndarray:
+    """Sorted distinct values of an int64 array (np.sort + neighbour comparison: several times faster than np.unique)."""
+    if values.size == 0:
+        return values
+    s = np.sort(values)
+    keep = np.empty(s.size, np.bool_)
+    keep[0] = True
+    np.not_equal(s[1:], s[:-1], out=keep[1:])
+    return s[keep]
+
+
 class Read:
     """A read: metadata plus (position, allele, quality) variants (core.pyx:62-273, src/read.cpp)."""
 
     __slots__ = (
         "_name", "_mapqs", "_source_id", "_sample_id", "_reference_start", "_reference_end", "_BX_tag", "_HP_tag",
         "_PS_tag", "_chromosome", "_sub_alignment_id", "_is_supplementary", "_is_reverse", "_pos", "_allele", "_quality",
+        "_owner",
     )
 
     def __init__(self, name: Optional[str] = None, mapq: int = 0, source_id: int = 0, sample_id: int = 0,
@@ -98,6 +110,11 @@ class Read:
         self._pos = array("q")
         self._allele = array("q")
         self._quality = array("q")
+        self._owner = None  # the ReadSet this object is stored in (its columnar copy of the variants is dropped when the read changes)
+
+    def _touch(self):
+        if self._owner is not None:
+            self._owner._columns = None
 
     # -- metadata -------------------------------------------------------------------------
     def _check(self):
@@ -161,6 +178,7 @@ class Read:
         self._pos[index] = int(variant.position)
         self._allele[index] = int(variant.allele)
         self._quality[index] = int(variant.quality)
+        self._touch()
 
     def __contains__(self, position):
         self._check()
@@ -172,6 +190,8 @@ class Read:
         self._pos.append(int(position))
         self._allele.append(int(allele))
         self._quality.append(int(quality))
+        if self._owner is not None:
+            self._owner._columns = None
 
     def add_mapq(self, mapq: int):
         self._check()
@@ -184,6 +204,7 @@ class Read:
         self._pos = array("q", [self._pos[i] for i in order])
         self._allele = array("q", [self._allele[i] for i in order])
         self._quality = array("q", [self._quality[i] for i in order])
+        self._touch()
         for i in range(1, len(self._pos)):
             if self._pos[i - 1] == self._pos[i]:
                 raise RuntimeError("Duplicate variant in read {} at position {}".format(self._name, self._pos[i]))
@@ -207,6 +228,7 @@ class Read:
         for slot in Read.__slots__:
             v = getattr(self, slot)
             setattr(r, slot, list(v) if isinstance(v, list) else (array("q", v) if isinstance(v, array) else v))
+        r._owner = None
         return r
 
     def __getstate__(self):
@@ -232,6 +254,11 @@ class ReadSet:
     def __init__(self):
         self._reads: List[Read] = []
         self._by_name: Dict[Tuple[str, int], int] = {}
+        # Columnar copy of all variants in read order: [lens, sample ids, positions, alleles, qualities] as array('q').  The
+        # reference's ReadSet copies every added read into one C++ container that the DP then walks in place; here `add` appends
+        # the read's three typed arrays to the set's (memcpy), so that `_flatten_reads` starts from five flat arrays instead of
+        # visiting 50k Python objects.  None = stale (a stored read was changed through a reference): rebuilt on demand.
+        self._columns = [array("q"), array("q"), array("q"), array("q"), array("q")]
 
     def add(self, read: Read):
         """Adds a COPY of the read (core.pyx:282-287); duplicate (name, source_id) raises
@@ -240,7 +267,28 @@ class ReadSet:
         if key in self._by_name:
             raise RuntimeError("ReadSet::add: duplicate read name.")
         self._by_name[key] = len(self._reads)
-        self._reads.append(read._clone())
+        clone = read._clone()
+        clone._owner = self
+        self._reads.append(clone)
+        cols = self._columns
+        if cols is not None:
+            cols[0].append(len(clone._pos))
+            cols[1].append(clone._sample_id)
+            cols[2].extend(clone._pos)
+            cols[3].extend(clone._allele)
+            cols[4].extend(clone._quality)
+
+    def _flat_columns(self):
+        """(lens, sample ids, positions, alleles, qualities) of all reads as int64 numpy arrays (copies)."""
+        cols = self._columns
+        if cols is None:  # a stored read was modified: collect again from the objects
+            reads = self._reads
+            cols = [array("q", (len(r._pos) for r in reads)), array("q", (r._sample_id for r in reads)), array("q"), array("q"), array("q")]
+            cols[2].frombytes(b"".join(r._pos for r in reads))
+            cols[3].frombytes(b"".join(r._allele for r in reads))
+            cols[4].frombytes(b"".join(r._quality for r in reads))
+            self._columns = cols
+        return tuple(np.array(c, np.int64) for c in cols)
 
     def __str__(self):
         lines = ["ReadSet:"]
@@ -294,7 +342,20 @@ class ReadSet:
             first = r._pos[0] if r._pos else -1
             return (len(r._pos) > 0, first, _lib.read_sort_key(r._name, r._source_id), r._name.encode("utf-8"), r._source_id)
 
-        self._reads.sort(key=key)
+        order = sorted(range(len(self._reads)), key=lambda i: key(self._reads[i]))  # stable, like list.sort
+        cols = self._columns
+        if cols is not None and order != list(range(len(order))):
+            # reorder the columnar copy with the same permutation (vectorised gather)
+            lens, samples, pos, allele, quality = (np.array(c, np.int64) for c in cols)
+            perm = np.array(order, np.int64)
+            off = np.zeros(len(lens) + 1, np.int64)
+            np.cumsum(lens, out=off[1:])
+            new_lens = lens[perm]
+            new_off = np.zeros(len(lens) + 1, np.int64)
+            np.cumsum(new_lens, out=new_off[1:])
+            idx = np.repeat(off[:-1][perm] - new_off[:-1], new_lens) + np.arange(int(new_off[-1]), dtype=np.int64)
+            self._columns = [_typed(new_lens), _typed(samples[perm]), _typed(pos[idx]), _typed(allele[idx]), _typed(quality[idx])]
+        self._reads = [self._reads[i] for i in order]
         self._by_name = {(r._name, r._source_id): i for i, r in enumerate(self._reads)}
 
     def subset(self, reads_to_select: Iterable[int]) -> "ReadSet":
@@ -305,10 +366,7 @@ class ReadSet:
         return result
 
     def get_positions(self) -> List[int]:
-        positions = set()
-        for r in self._reads:
-            positions.update(r._pos)
-        return sorted(positions)
+        return _distinct_sorted(self._flat_columns()[2]).tolist()
 
 
 class Genotype:
@@ -454,6 +512,9 @@ class PhredGenotypeLikelihoods:
         return self._nr_alleles
 
 
+_GT_CODE = {(0, 0): 0, (0, 1): 1, (1, 1): 2}
+
+
 class Pedigree:
     """Individuals with per-variant genotypes (and likelihoods) plus trio relationships
     (core.pyx:419-466, src/pedigree.cpp)."""
@@ -463,6 +524,7 @@ class Pedigree:
         self._ids: List[int] = []
         self._index: Dict[int, int] = {}
         self._genotypes: List[List[Genotype]] = []
+        self._gt_codes: List[np.ndarray] = []
         self._gls: List[List[Optional[PhredGenotypeLikelihoods]]] = []
         self._triples: List[Tuple[int, int, int]] = []
         self._variant_count = -1
@@ -486,6 +548,8 @@ class Pedigree:
         assert len(gts) == self._variant_count
         assert len(gls) == self._variant_count
         numeric = self.numeric_sample_ids[id]
+        # canonical index of the diploid biallelic genotypes (genotype.cpp:82-93) as one byte per variant, for `_flatten`
+        self._gt_codes.append(np.fromiter((_GT_CODE.get(g._alleles, GT_OTHER) for g in gts), np.uint8, count=len(gts)))
         self._genotypes.append(gts)
         self._gls.append(gls)
         self._ids.append(numeric)
@@ -541,22 +605,28 @@ class Pedigree:
 def _flatten_reads(readset: ReadSet, positions: Optional[Sequence[int]], index_of_sample):
     """The read side of `_flatten`: (pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind).
     `index_of_sample(sample_id)` gives the pedigree index of a read's sample."""
-    if positions is None:
-        pos_list = readset.get_positions()
-    else:
-        pos_list = [int(p) for p in positions]
-    n = len(pos_list)
     reads = readset._reads
     m = len(reads)
-    # -- reads: one vectorised pass over all variants (the containers keep plain Python lists) ------------
-    read_ind = np.fromiter((index_of_sample(r._sample_id) for r in reads), np.uint32, count=m)  # raises like id_to_index
-    lens = np.fromiter((len(r._pos) for r in reads), np.int64, count=m)
+    lens, samples, pos, allele, quality = readset._flat_columns()
+    if positions is None:
+        pos_arr = _distinct_sorted(pos)
+        pos_list = pos_arr.tolist()
+    else:
+        pos_list = [int(p) for p in positions]
+        pos_arr = np.array(pos_list, np.int64)
+    n = len(pos_list)
+    # sample id -> pedigree index, once per distinct sample (raises like id_to_index for an unknown one)
+    if m:
+        uniq, first_at, inverse = np.unique(samples, return_index=True, return_inverse=True)
+        index_of = np.zeros(len(uniq), np.uint32)
+        for u in np.argsort(first_at, kind="stable"):  # in read order: the first read with an unknown sample raises
+            index_of[u] = index_of_sample(int(uniq[u]))
+        read_ind = index_of[inverse]
+    else:
+        read_ind = np.zeros(0, np.uint32)
     if m and int(lens.min()) == 0:
         raise RuntimeError("No variants present")
     total = int(lens.sum())
-    pos = np.frombuffer(b"".join(r._pos for r in reads), np.int64, count=total)  # the arrays' memory, concatenated in C
-    allele = np.frombuffer(b"".join(r._allele for r in reads), np.int64, count=total)
-    quality = np.frombuffer(b"".join(r._quality for r in reads), np.int64, count=total)
     off = np.zeros(m + 1, np.int64)
     np.cumsum(lens, out=off[1:])
     if m:
@@ -567,31 +637,45 @@ def _flatten_reads(readset: ReadSet, positions: Optional[Sequence[int]], index_o
         step[last_i[:-1]] = 1  # differences across read boundaries do not count
         if bool((step <= 0).any()):
             raise RuntimeError("ColumnIterator: encountered read with unsorted variants.")
-    pos_arr = np.array(pos_list, np.int64)
     if n and bool((np.diff(pos_arr) <= 0).any()):
         # unsorted / repeated explicit positions: the last occurrence defines the column, as in a dict
         col_of = {p: i for i, p in enumerate(pos_list)}
         col = np.fromiter((col_of.get(int(p), -1) for p in pos), np.int64, count=total)
+    elif n and int(pos_arr[-1]) - int(pos_arr[0]) <= 16 * n + 1024:
+        # densely numbered positions: a look-up table over the position range instead of a binary search per entry
+        lo_p, hi_p = int(pos_arr[0]), int(pos_arr[-1])
+        lut = np.full(hi_p - lo_p + 1, -1, np.int64)
+        lut[pos_arr - lo_p] = np.arange(n, dtype=np.int64)
+        inside = (pos >= lo_p) & (pos <= hi_p)
+        col = np.where(inside, lut[np.clip(pos, lo_p, hi_p) - lo_p], -1)
+    elif n and positions is None:
+        col = np.searchsorted(pos_arr, pos)  # every position of a read is a column
     elif n:
         col = np.searchsorted(pos_arr, pos)
         col = np.where((col < n) & (pos_arr[np.minimum(col, n - 1)] == pos), col, -1)
     else:
         col = np.full(total, -1, np.int64)
-    valid = col >= 0
-    if m:
+    all_valid = bool(n) and (positions is None or int(col.min(initial=0)) >= 0)
+    valid = None if all_valid else col >= 0
+    if m and not all_valid:
         bad = np.nonzero(~(valid[first] & valid[last_i]))[0]
         if bad.size:
             # the reference asserts here (columniterator.cpp:36-39) and aborts the process
             raise RuntimeError("read {!r}: first/last variant position is not among the given positions".format(reads[int(bad[0])].name))
     # interior variants outside `positions` are skipped (columniterator.cpp:101-104)
-    wrong = np.nonzero(valid & ((allele < 0) | (allele > 2)))[0]
-    if wrong.size:
-        r_idx = int(np.searchsorted(off, wrong[0], side="right") - 1)
-        raise RuntimeError("read {!r}: allele {} is not 0 (REF), 1 (ALT) or 2 (BLANK)".format(reads[r_idx].name, int(allele[wrong[0]])))
-    if bool((valid & (quality < 0)).any()):
+    if total and (int(allele.min()) < 0 or int(allele.max()) > 2):
+        outside = (allele < 0) | (allele > 2)
+        wrong = np.nonzero(outside if all_valid else (valid & outside))[0]
+        if wrong.size:
+            r_idx = int(np.searchsorted(off, wrong[0], side="right") - 1)
+            raise RuntimeError("read {!r}: allele {} is not 0 (REF), 1 (ALT) or 2 (BLANK)".format(reads[r_idx].name, int(allele[wrong[0]])))
+    if total and int(quality.min()) < 0 and bool(((quality < 0) if all_valid else (valid & (quality < 0))).any()):
         raise OverflowError("negative quality")
-    kept = np.add.reduceat(valid.astype(np.int64), off[:-1]) if m else np.zeros(0, np.int64)
     read_off = np.zeros(m + 1, np.uint64)
+    if all_valid:
+        read_off[1:] = off[1:]
+        return pos_list, read_off, col, allele, quality, read_ind
+    kept = np.add.reduceat(valid.astype(np.int64), off[:-1]) if m else np.zeros(0, np.int64)
     np.cumsum(kept, out=read_off[1:])
     return pos_list, read_off, col[valid], allele[valid], quality[valid], read_ind
 
@@ -611,17 +695,16 @@ def _flatten(readset: ReadSet, recombcost: Sequence[int], pedigree: Pedigree, di
         raise RuntimeError("pedigree without individuals")
     if n > 0 and pedigree.variant_count != -1 and pedigree.variant_count < n:
         raise RuntimeError("pedigree holds genotypes for {} variants but the DP has {} columns".format(pedigree.variant_count, n))
-    rc = [int(x) for x in recombcost]
+    rc = recombcost.tolist() if isinstance(recombcost, np.ndarray) else [int(x) for x in recombcost]
     if len(rc) < n:
         # The reference indexes recombcost[column] without a bounds check (pedigreedptable.cpp:291) and
         # its own tests pass lists that are one short (tests/test_pedigreephasing.py:247,266); reading
         # past the end is undefined there, here the last given cost is repeated.
         rc = rc + [rc[-1] if rc else 0] * (n - len(rc))
-    code = {(0, 0): 0, (0, 1): 1, (1, 1): 2}  # canonical index of diploid biallelic genotypes (genotype.cpp:82-93)
     gt = np.full((n_ind, n), GT_OTHER, np.uint8)
     gl = np.zeros((n_ind, n, 3), np.float64) if distrust_genotypes else None
     for i in range(n_ind):
-        gt[i, :] = np.fromiter((code.get(g._alleles, GT_OTHER) for g in pedigree._genotypes[i][:n]), np.uint8, count=n)
+        gt[i, :] = pedigree._gt_codes[i][:n]
         if distrust_genotypes:
             for k in range(n):
                 lk = pedigree._gls[i][k]

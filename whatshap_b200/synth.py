@@ -398,13 +398,11 @@ def to_objects(prob: FlatProblem):
     off = prob.read_off.astype(np.int64)
     cols, alleles, phreds = prob.ent_col, prob.ent_allele.tolist(), prob.ent_phred.tolist()
     pos_of = prob.positions[cols].tolist()
-    reads = []
     for r in range(prob.n_reads):
         read = Read("r%07d" % r, 60, 0, int(prob.read_ind[r]))
         a, b = int(off[r]), int(off[r + 1])
         read._pos, read._allele, read._quality = array("q", pos_of[a:b]), array("q", alleles[a:b]), array("q", phreds[a:b])
-        reads.append(read)
-    rs._reads = reads  # already in ReadSet order (sorted by first position)
+        rs.add(read)  # already in ReadSet order (sorted by first position)
     ids = NumericSampleIds()
     ped = Pedigree(ids)
     gts = [Genotype([0, 0]), Genotype([0, 1]), Genotype([1, 1])]
