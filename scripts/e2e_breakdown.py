@@ -31,7 +31,7 @@ print("RESULT %%s threads=%%s  wrapper+call %%.2f ms  C call %%.2f ms" %% (name,
 ''' % ROOT
 
 for name in sys.argv[1:] or ["cfg3", "cfg2", "cfg5"]:
-    for threads, extra in ((None, {}), ("64", {}), ("32", {}), ("16", {}), ("8", {}), ("16", {"WHMEC_PINNED_STAGING": "1"})) if name == "cfg3" else ((None, {}), ("16", {})):
+    for threads, extra in ((None, {}), ("32", {}), ("16", {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})) if name == "cfg3" else ((None, {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})):
         env = dict(os.environ, WHMEC_TIMING="1", **extra)
         if threads:
             env["WHMEC_HOST_THREADS"] = threads
