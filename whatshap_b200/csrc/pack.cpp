@@ -206,7 +206,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
     const uint32_t n_chunks = n ? (uint32_t)cut.size() - 1 : 0;
     struct Chunk {
         size_t act_base = 0, act_count = 0;  // this chunk's slice of the (column, active read) arrays
-        uint32_t max_a = 0;
+        uint32_t max_a = 0, max_d = 0;
         uint64_t base_total = 0, rc_total = 0;
         uint64_t words = 0, cells = 0, alg_bytes = 0;  // back-pointer words (column-kernel layout), DP cells, algorithmic bytes of the chunk
         std::vector<uint32_t> chain_starts;            // columns of this chunk that begin a DP-independent chain
@@ -358,6 +358,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
             m.keep = keep;
             m.f = popc32(keep);
             m.d = m.a - m.f;
+            ch.max_d = std::max(ch.max_d, m.d);
             {
                 uint32_t di = 0;
                 for (uint32_t drop = ~keep & low_mask(na); drop; drop &= drop - 1) m.dpos[di++] = (uint8_t)ctz32(drop);
@@ -447,6 +448,7 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
     uint64_t base_total = 0, rc_total = 0;
     for (uint32_t ci = 0; ci < n_chunks; ++ci) {
         max_a = std::max(max_a, chunks[ci].max_a);
+        pk.max_d = std::max(pk.max_d, chunks[ci].max_d);
         base_total += chunks[ci].base_total;
         rc_total += chunks[ci].rc_total;
     }

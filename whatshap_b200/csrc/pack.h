@@ -33,6 +33,7 @@ struct Packed {
     std::vector<uint32_t> read_first, read_last;  // column span of every read
     // chains: maximal runs of columns with f > 0 between them (T == 1 only uses them)
     std::vector<uint32_t> chain_begin;   // first column of each chain; chain c = [begin[c], begin[c+1])
+    uint32_t max_d = 0;                  // most reads that end in one column
     uint64_t bp_words = 0;               // arena size in 32-bit words (column-kernel layout)
     whmec_stats stats{};
 };

@@ -39,7 +39,12 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     ts.cols.resize(n);  // every column is written by exactly one committed panel
     const uint32_t n_chains = (uint32_t)pk.chain_begin.size() - 1;
     std::vector<std::vector<Panel>> per_chain(n_chains);
-    struct PanelSets { std::vector<uint32_t> G, Lout, Lold, Gold; };
+    struct Small {
+        uint32_t v[32];
+        uint32_t n = 0;
+        void push(uint32_t x) { v[n++] = x; }
+    };
+    struct PanelSets { Small G, Lout, Lold, Gold; };  // fixed-size sets: no heap traffic per panel
     std::vector<std::vector<PanelSets>> per_chain_sets(n_chains);
     // per-chain results; offsets are chain-relative until all chains are planned (chains are planned by
     // independent host threads)
@@ -49,12 +54,6 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
     // Sets of reads are small (at most 32 reads are active in a column) and are kept as ascending arrays;
     // "where does read r sit in the current column / in the tile's local order" are O(1) look-ups in
     // per-chain tables indexed by (read - first read of the chain) and validated by a stamp.
-    struct Small {
-        uint32_t v[32];
-        uint32_t n = 0;
-        void push(uint32_t x) { v[n++] = x; }
-        std::vector<uint32_t> vec() const { return std::vector<uint32_t>(v, v + n); }
-    };
     auto plan_chain = [&](uint32_t c) -> bool {
         const uint32_t k0 = pk.chain_begin[c], k1 = pk.chain_begin[c + 1] - 1;
         uint32_t fmax = 0, rbase = 0xFFFFFFFFu, rtop = 0;
@@ -337,7 +336,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                     P.steady = steady ? 1u + t0.pad1 : 0u;
                 }
                 per_chain[c].push_back(P);
-                per_chain_sets[c].push_back(PanelSets{G.vec(), Lcur.vec(), Lold.vec(), Gold.vec()});
+                per_chain_sets[c].push_back(PanelSets{G, Lcur, Lold, Gold});
                 ++pcount;
                 state = kept;
                 k = j;
@@ -393,17 +392,15 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
             B.in_half = A.half;
             B.in_top = 0;
             for (uint32_t gmk = A.gmask_out; gmk; gmk &= gmk - 1) B.in_top = gmk & (0u - gmk);  // highest set bit = top global read
-            if (!sa.G.empty() && !sa.Lout.empty() && sa.G.back() > sa.Lout.front()) continue;  // producer's global reads must be the oldest
-            if (sb.Lold.size() < sa.G.size()) continue;
-            const size_t j = sb.Lold.size() - sa.G.size();
-            if (j < 2 || j > sa.Lout.size()) continue;  // chunks of at least 4 entries
+            if (sa.G.n && sa.Lout.n && sa.G.v[sa.G.n - 1] > sa.Lout.v[0]) continue;  // producer's global reads must be the oldest
+            if (sb.Lold.n < sa.G.n) continue;
+            const size_t j = sb.Lold.n - sa.G.n;
+            if (j < 2 || j > sa.Lout.n) continue;  // chunks of at least 4 entries
             // the consumer's old local reads must be the producer's global reads followed by its first j local reads
-            if (!std::equal(sa.G.begin(), sa.G.end(), sb.Lold.begin()) ||
-                !std::equal(sa.Lout.begin(), sa.Lout.begin() + j, sb.Lold.begin() + sa.G.size()))
-                continue;
+            if (!std::equal(sa.G.v, sa.G.v + sa.G.n, sb.Lold.v) || !std::equal(sa.Lout.v, sa.Lout.v + j, sb.Lold.v + sa.G.n)) continue;
             A.out_layout = 1;
             B.in_layout = 1;
-            B.in_gA = (uint32_t)sa.G.size();
+            B.in_gA = sa.G.n;
             B.in_j = (uint32_t)j;
             B.in_sA = A.s_out;
         }

@@ -946,13 +946,25 @@ struct PinnedPool {
     size_t cached = 0;
     std::atomic<bool> enabled{true};  // re-read from the environment by every plan (test hook)
 
+    // Block sizes come in classes (1 MiB, then eight steps per power of two), so that a request of the same size as an earlier
+    // one always finds that earlier block again: repeated solves of same-sized problems never call cudaHostAlloc (which costs
+    // milliseconds and, holding the address-space lock, stalls every other thread of the process that takes a page fault).
+    static size_t size_class(size_t bytes) {
+        size_t cap = (size_t)1 << 20;
+        if (bytes <= cap) return cap;
+        while (cap * 2 < bytes) cap *= 2;  // cap < bytes <= 2 * cap
+        const size_t step = cap / 8;
+        return cap + (bytes - cap + step - 1) / step * step;
+    }
+
     void *alloc(size_t bytes) {
         if (bytes < MIN_BYTES || !enabled.load(std::memory_order_relaxed)) return nullptr;
+        const size_t want = size_class(bytes);
         {
             std::lock_guard<std::mutex> lk(m);
             size_t best = SIZE_MAX;
             for (size_t i = 0; i < free_blocks.size(); ++i)
-                if (free_blocks[i].cap >= bytes && free_blocks[i].cap <= 2 * bytes &&
+                if (free_blocks[i].cap >= bytes && free_blocks[i].cap <= 2 * want &&
                     (best == SIZE_MAX || free_blocks[i].cap < free_blocks[best].cap))
                     best = i;
             if (best != SIZE_MAX) {
@@ -963,7 +975,7 @@ struct PinnedPool {
                 return b.p;
             }
         }
-        const size_t cap = (bytes + bytes / 8 + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1);  // 12.5 % slack, whole MiB
+        const size_t cap = want;
         void *p = nullptr;
         if (cudaHostAlloc(&p, cap, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();  // clear the error of the failed allocation: the caller falls back to the heap
@@ -1012,7 +1024,8 @@ void install_stage_hooks() {
 // ---- streams and events are reused across plans (creating them costs ~0.5 ms per solve) -----------------------------------
 struct StreamSet {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;    // sweep / backtrace
+    cudaEvent_t evh0 = nullptr, evh1 = nullptr;  // uploads of plan_create (read after the first synchronisation that follows)
 };
 struct StreamCache {
     static constexpr int MAX_DEV = 64;
@@ -1032,12 +1045,16 @@ struct StreamCache {
         cudaError_t e = cudaStreamCreateWithFlags(&out.stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreate(&out.ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&out.ev1);
+        if (e == cudaSuccess) e = cudaEventCreate(&out.evh0);
+        if (e == cudaSuccess) e = cudaEventCreate(&out.evh1);
         if (e != cudaSuccess) destroy(out);
         return e;
     }
     static void destroy(StreamSet &s) {
         if (s.ev0) cudaEventDestroy(s.ev0);
         if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.evh0) cudaEventDestroy(s.evh0);
+        if (s.evh1) cudaEventDestroy(s.evh1);
         if (s.stream) cudaStreamDestroy(s.stream);
         s = StreamSet{};
     }
@@ -1072,7 +1089,8 @@ void keep_pool_memory(int device) {
 struct whmec_plan {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evh0 = nullptr, evh1 = nullptr;
+    bool h2d_pending = false;  // the uploads of plan_create are enqueued, their duration has not been read yet
     Packed pk;
     whmec_stats stats{};
     bool swept = false;
@@ -1122,7 +1140,7 @@ struct whmec_plan {
         d_chain_rows.release(); d_chain_in.release(); d_chain_out.release();
         tiles.release(stream);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
-        StreamSet set{stream, ev0, ev1};
+        StreamSet set{stream, ev0, ev1, evh0, evh1};
         if (stream && healthy) g_streams.give_back(device, set);  // (the frees above are stream-ordered: whoever takes the stream next queues behind them)
         else StreamCache::destroy(set);
     }
@@ -1178,11 +1196,10 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         if (segment == 2) pk.cols[0].first = 0;  // column 0 reads the vector handed over by the preceding segment
     }
     if (pk.n == 0) return WHMEC_OK;
-    for (const ColMeta &m : pk.cols)
-        if (m.d + pk.tb > 32) {
-            msg = "unsupported: dropped reads + transmission bits exceed 32";
-            return WHMEC_ERR_UNSUPPORTED;
-        }
+    if (pk.max_d + pk.tb > 32) {  // (most reads ending in one column: found by the packer's workers, not by another pass over the columns)
+        msg = "unsupported: dropped reads + transmission bits exceed 32";
+        return WHMEC_ERR_UNSUPPORTED;
+    }
     CUDA_TRY(cudaSetDevice(device));
     keep_pool_memory(device);
     {
@@ -1191,13 +1208,15 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         pl->stream = set.stream;
         pl->ev0 = set.ev0;
         pl->ev1 = set.ev1;
+        pl->evh0 = set.evh0;
+        pl->evh1 = set.evh1;
     }
     const uint32_t n = pk.n;
 
     CUDA_TRY(pl->d_path_index.alloc(n, pl->stream));
     CUDA_TRY(pl->d_path_tv.alloc(n, pl->stream));
     CUDA_TRY(pl->d_result.alloc(4, pl->stream));
-    CUDA_TRY(cudaEventRecord(pl->ev0, pl->stream));
+    CUDA_TRY(cudaEventRecord(pl->evh0, pl->stream));
     uint64_t h2d = 0;
     const auto tc3 = pclk::now();
 
@@ -1359,11 +1378,22 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
             CUDA_TRY(pl->d_matrix.alloc((size_t)pk.T * pk.T, pl->stream));
         }
     }
-    CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
-    CUDA_TRY(cudaStreamSynchronize(pl->stream));
-    CUDA_TRY(cudaEventElapsedTime(&pl->stats.h2d_ms, pl->ev0, pl->ev1));
+    // No synchronisation here: the uploads (asynchronous DMA from the page-locked arrays of `pk` / the tile schedule, which live
+    // as long as the plan) overlap whatever the host does next; the sweep's first launch queues behind them on the same stream.
+    CUDA_TRY(cudaEventRecord(pl->evh1, pl->stream));
+    pl->h2d_pending = true;
     pl->stats.h2d_bytes = h2d;
     return WHMEC_OK;
+}
+
+// after a synchronisation of the plan's stream: the duration of the uploads of plan_create
+void read_h2d_time(whmec_plan *pl) {
+    if (!pl->h2d_pending) return;
+    pl->h2d_pending = false;
+    if (cudaEventElapsedTime(&pl->stats.h2d_ms, pl->evh0, pl->evh1) != cudaSuccess) {
+        cudaGetLastError();
+        pl->stats.h2d_ms = 0;
+    }
 }
 
 // One pass of the batched pedigree sweep.  pass 0: unit input vectors, values only (transfer matrices);
@@ -1551,6 +1581,7 @@ int plan_sweep_impl(whmec_plan *pl, std::string &msg, bool wait = true) {
     if (!wait) return WHMEC_OK;
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     CUDA_TRY(cudaEventElapsedTime(&pl->stats.sweep_ms, pl->ev0, pl->ev1));
+    read_h2d_time(pl);
     return WHMEC_OK;
 }
 
@@ -1631,6 +1662,7 @@ int plan_finish_impl(whmec_plan *pl, whmec_solution *s, std::string &msg, int en
     CUDA_TRY(cudaEventRecord(pl->ev1, pl->stream));
     CUDA_TRY(cudaStreamSynchronize(pl->stream));
     CUDA_TRY(cudaEventElapsedTime(&pl->stats.d2h_ms, pl->ev0, pl->ev1));
+    read_h2d_time(pl);
     pl->stats.d2h_bytes = (uint64_t)n * 8 + 16;
     s->cost = result[0];
     const auto tf1 = fclk::now();
