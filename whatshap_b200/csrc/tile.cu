@@ -719,7 +719,7 @@ struct TileImpl {
     uint32_t *d_seg_lo = nullptr, *d_seg_hi = nullptr;  // [segment][chain]: columns of the chain inside the segment (lo > hi: none)
     std::vector<uint32_t> seg_lo, seg_hi;  // their host copies (kept: the upload is asynchronous)
     uint64_t arena_words = 0;
-    ColMeta *d_cols = nullptr;
+    const ColMeta *d_cols = nullptr;  // owned by the plan that owns this schedule (uploaded before the planner ran)
     TileCol *d_tcols = nullptr;
     Panel *d_panels = nullptr;
     uint32_t *d_state = nullptr, *d_arena = nullptr, *d_chain_begin = nullptr;
@@ -758,7 +758,7 @@ bool TilePlan::plan(const Packed &pk) {
     return true;
 }
 
-int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::string &msg) {
+int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::string &msg, const ColMeta *d_cols) {
     TileImpl *I = (TileImpl *)impl;
     TileSchedule &ts = I->ts;
     I->n_chains = (uint32_t)pk.chain_begin.size() - 1;
@@ -863,7 +863,7 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
     CUDA_TRY(cudaMemcpyAsync(I->d_seg_lo, seg_lo.data(), seg_lo.size() * 4, cudaMemcpyHostToDevice, stream));
     CUDA_TRY(cudaMemcpyAsync(I->d_seg_hi, seg_hi.data(), seg_hi.size() * 4, cudaMemcpyHostToDevice, stream));
     if (K > 1) CUDA_TRY(cudaMallocAsync((void **)&I->d_ckpt, (uint64_t)(K - 1) * (ts.state_words + 1) * 4, stream));
-    CUDA_TRY(cudaMallocAsync((void **)&I->d_cols, (size_t)pk.n * sizeof(ColMeta), stream));
+    I->d_cols = d_cols;
     CUDA_TRY(cudaMallocAsync((void **)&I->d_tcols, (size_t)pk.n * sizeof(TileCol), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_panels, ts.panels.size() * sizeof(Panel), stream));
     CUDA_TRY(cudaMallocAsync((void **)&I->d_state, (ts.state_words + 1) * 4, stream));
@@ -880,8 +880,7 @@ int TilePlan::create(const Packed &pk, cudaStream_t stream, uint64_t &h2d, std::
         const void *src;
         size_t bytes, off;
     };
-    Piece pieces[4] = {{I->d_cols, pk.cols.data(), (size_t)pk.n * sizeof(ColMeta), 0},
-                       {I->d_tcols, ts.cols.data(), (size_t)pk.n * sizeof(TileCol), 0},
+    Piece pieces[3] = {{I->d_tcols, ts.cols.data(), (size_t)pk.n * sizeof(TileCol), 0},
                        {I->d_panels, ts.panels.data(), ts.panels.size() * sizeof(Panel), 0},
                        {I->d_chain_begin, pk.chain_begin.data(), pk.chain_begin.size() * 4, 0}};
     size_t total = 0;
@@ -958,7 +957,7 @@ int TilePlan::backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_
 void TilePlan::release(cudaStream_t stream) {
     TileImpl *I = (TileImpl *)impl;
     if (!I) return;
-    for (void *q : {(void *)I->d_cols, (void *)I->d_tcols, (void *)I->d_panels, (void *)I->d_state, (void *)I->d_arena,
+    for (void *q : {(void *)I->d_tcols, (void *)I->d_panels, (void *)I->d_state, (void *)I->d_arena,
                     (void *)I->d_chain_begin, (void *)I->d_chain_keys, (void *)I->d_ckpt, (void *)I->d_seg_lo, (void *)I->d_seg_hi})
         if (q) cudaFreeAsync(q, stream);
     delete I;

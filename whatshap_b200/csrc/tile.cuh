@@ -19,7 +19,8 @@ struct TilePlan {
     void *impl = nullptr;
     // Host-only: decide whether the tile path applies and build its schedule.
     bool plan(const Packed &pk);
-    int create(const Packed &pk, cudaStream_t stream, uint64_t &h2d_bytes, std::string &msg);
+    // `d_cols`: the packer's per-column records on the device (uploaded by the caller while the host planned; owned by the caller)
+    int create(const Packed &pk, cudaStream_t stream, uint64_t &h2d_bytes, std::string &msg, const ColMeta *d_cols);
     int sweep(const Packed &pk, cudaStream_t stream, std::string &msg);
     int backtrace(const Packed &pk, cudaStream_t stream, uint32_t *d_path_index, uint32_t *d_result, std::string &msg);
     void release(cudaStream_t stream);

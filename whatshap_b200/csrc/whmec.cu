@@ -1180,9 +1180,33 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
     if (rc != WHMEC_OK) return rc;
     Packed &pk = pl->pk;
     const auto tc1 = pclk::now();
+    uint64_t h2d = 0;
+    auto device_setup = [&]() -> int {  // device, stream + events (reused across plans), start of the upload window
+        CUDA_TRY(cudaSetDevice(device));
+        keep_pool_memory(device);
+        StreamSet set;
+        CUDA_TRY(g_streams.acquire(device, set));
+        pl->stream = set.stream;
+        pl->ev0 = set.ev0;
+        pl->ev1 = set.ev1;
+        pl->evh0 = set.evh0;
+        pl->evh1 = set.evh1;
+        CUDA_TRY(cudaEventRecord(pl->evh0, pl->stream));
+        return WHMEC_OK;
+    };
+    if (tile_candidate && pk.n > 0) {
+        // the per-column records of the packer (4 MB for 50k columns) travel while the host plans the tiles
+        rc = device_setup();
+        if (rc != WHMEC_OK) return rc;
+        CUDA_TRY(pl->d_cols.alloc(pk.n, pl->stream));
+        CUDA_TRY(cudaMemcpyAsync(pl->d_cols.p, pk.cols.data(), (size_t)pk.n * sizeof(ColMeta), cudaMemcpyHostToDevice, pl->stream));
+        h2d += (uint64_t)pk.n * sizeof(ColMeta);
+    }
     pl->use_tiles = tile_candidate && pk.n > 0 && pl->tiles.plan(pk);
     const auto tc2 = pclk::now();
     if (tile_candidate && !pl->use_tiles && pk.n > 0) {  // planner declined: the column kernel needs the deltas
+        CUDA_TRY(cudaStreamSynchronize(pl->stream));  // the upload above reads the arrays that are packed again now
+        h2d = 0;
         rc = pack_problem(p, pl->pk, msg, true);
         if (rc != WHMEC_OK) return rc;
     }
@@ -1200,28 +1224,19 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
         msg = "unsupported: dropped reads + transmission bits exceed 32";
         return WHMEC_ERR_UNSUPPORTED;
     }
-    CUDA_TRY(cudaSetDevice(device));
-    keep_pool_memory(device);
-    {
-        StreamSet set;
-        CUDA_TRY(g_streams.acquire(device, set));
-        pl->stream = set.stream;
-        pl->ev0 = set.ev0;
-        pl->ev1 = set.ev1;
-        pl->evh0 = set.evh0;
-        pl->evh1 = set.evh1;
+    if (!pl->stream) {
+        rc = device_setup();
+        if (rc != WHMEC_OK) return rc;
     }
     const uint32_t n = pk.n;
 
     CUDA_TRY(pl->d_path_index.alloc(n, pl->stream));
     CUDA_TRY(pl->d_path_tv.alloc(n, pl->stream));
     CUDA_TRY(pl->d_result.alloc(4, pl->stream));
-    CUDA_TRY(cudaEventRecord(pl->evh0, pl->stream));
-    uint64_t h2d = 0;
     const auto tc3 = pclk::now();
 
     if (pl->use_tiles) {
-        rc = pl->tiles.create(pk, pl->stream, h2d, msg);
+        rc = pl->tiles.create(pk, pl->stream, h2d, msg, pl->d_cols.p);
         if (rc != WHMEC_OK) return rc;
         if (timing)
             std::fprintf(stderr, "[whmec] create: pack %.2f ms, plan %.2f ms, stream + events + result buffers %.2f ms, tiles.create (alloc + upload enqueue) %.2f ms\n",
@@ -1237,7 +1252,7 @@ int plan_create_impl(const whmec_problem *p, int device, whmec_plan *pl, std::st
             msg = "back-pointer storage exceeds the free HBM of this device";
             return WHMEC_ERR_UNSUPPORTED;
         }
-        CUDA_TRY(pl->d_cols.alloc(n, pl->stream));
+        if (!pl->d_cols.p) CUDA_TRY(pl->d_cols.alloc(n, pl->stream));  // (already there when the tile planner declined the problem)
         CUDA_TRY(pl->d_fn_c0.alloc(pk.fn_c0.size(), pl->stream));
         CUDA_TRY(pl->d_fn_delta.alloc(pk.fn_delta.size(), pl->stream));
         CUDA_TRY(pl->d_fn_group.alloc(pk.fn_group.size(), pl->stream));
