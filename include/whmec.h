@@ -213,6 +213,25 @@ uint32_t whmec_selector_bridge(whmec_selector *sel, const uint32_t *items, const
  * as computed by libstdc++ (64-bit murmur, seed 0xc70f6907); src/readset.h:68-72. */
 uint64_t whmec_read_sort_key(const char *name, size_t len, int32_t source_id);
 
+/* ---- PedMecHeuristic: the reference's row-limited heuristic PedMEC solver (`whatshap phase --algorithm=heuristic`) -------------
+ * Replaces cpp.PedMecHeuristic(readset, recombcost, pedigree, distrust_genotypes, positions, row_limit, allow_mutations, verbosity)
+ * + solve() + getOptBipartition / getOptTransmission / getOptHaplotypes / getMutations / getOptScore
+ * (whatshap/cpp.pxd:261-272, whatshap/core.pyx:674-734, src/pedmecheuristic.cpp:9-81,121-409).
+ * HOST code: the heuristic is a sequential beam search over float scores (at most row_limit partial solutions per column, each
+ * extended read by read), not the exact DP of this library's CUDA path; it is built for completeness of the operator surface.
+ * `p->read_ind` carries the reads' SAMPLE ids, which the reference requires to be the zero-based pedigree indices
+ * (src/pedmecheuristic.h:66); p->gt must hold a diploid biallelic genotype (0, 1, 2) for every sample and column. */
+typedef struct whmec_heuristic_solution {
+    float score;            /* out: getOptScore() -- the reference never assigns its optScore, so this is 0 */
+    uint32_t n_samples;     /* out: distinct sample ids among the reads and the trio members */
+    uint8_t *partition;     /* [n_reads]  getOptBipartition(): 1 = true (core.pyx:719 reports 0 for true, 1 for false) */
+    uint32_t *transmission; /* [n_cols]   getOptTransmission() */
+    int8_t *haplotypes;     /* [n_ind][2][n_cols] getOptHaplotypes(), rows of samples >= n_samples untouched */
+    uint8_t *mutated;       /* [n_ind][2][n_cols] 1 = getMutations() lists (haplotype, column) for the sample */
+} whmec_heuristic_solution;
+int whmec_heuristic(const whmec_problem *p, uint32_t row_limit, int allow_mutations, whmec_heuristic_solution *s, char *err,
+                    size_t errlen);
+
 #ifdef __cplusplus
 }
 #endif

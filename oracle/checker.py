@@ -64,6 +64,19 @@ class _Checker:
         sol.cost = int(cs.cost)
         return sol
 
+    def heuristic(self, prob: FlatProblem, row_limit: int = 256, allow_mutations: bool = True):
+        """The reference's PedMecHeuristic (compiled reference only): a HeuristicSolution."""
+        from whatshap_b200._abi import CHeuristicSolution, HeuristicSolution
+
+        fn = self.lib.whref_heuristic
+        fn.argtypes = [C.POINTER(CProblem), C.c_uint32, C.c_int, C.POINTER(CHeuristicSolution), C.c_char_p, C.c_size_t]
+        fn.restype = C.c_int
+        sol = HeuristicSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+        cp, cs, err = prob.as_c(), sol.as_c(), C.create_string_buffer(512)
+        raise_for(fn(C.byref(cp), int(row_limit), int(bool(allow_mutations)), C.byref(cs), err, len(err)), err.value.decode())
+        sol.score, sol.n_samples = float(cs.score), int(cs.n_samples)
+        return sol
+
     def genotype(self, prob: FlatProblem):
         """Genotype likelihoods [n_ind, n_cols, 3] of the reference's GenotypeDPTable (`prob.gl` = priors)."""
         import numpy as np

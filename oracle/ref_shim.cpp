@@ -14,6 +14,7 @@
 //   get_optimal_partitioning        src/pedigreedptable.cpp:391-406  (+ core.pyx:414 true->0 mapping)
 //   get_optimal_score               src/pedigreedptable.cpp:338-341
 //   GenotypeDPTable ctor / get_genotype_likelihoods   src/genotypedptable.cpp:17-48,445-451  (sibling DP)
+//   PedMecHeuristic ctor / solve / getOpt*            src/pedmecheuristic.cpp:9-81,121-409         (row-limited heuristic)
 
 #include <chrono>
 #include <cstring>
@@ -37,6 +38,7 @@
 #include <cassert>
 #include "genotypedistribution.h"
 #include "genotyper.h"
+#include "pedmecheuristic.h"
 
 #include "../include/whmec.h"
 
@@ -240,4 +242,39 @@ extern "C" int whref_sort_order(uint32_t n, const char *const *names, const int3
     rs.sort();
     for (uint32_t i = 0; i < n; ++i) order[i] = (uint32_t)rs.get(i)->getSampleID();
     return 0;
+}
+
+// The reference's row-limited heuristic solver (src/pedmecheuristic.cpp) on the same flat arrays: outputs in the layout of
+// whmec_heuristic_solution (include/whmec.h).  Sample ids are the pedigree indices (the reference asks for zero-indexed ids).
+extern "C" int whref_heuristic(const whmec_problem *p, uint32_t row_limit, int allow_mutations, whmec_heuristic_solution *s, char *err,
+                               size_t errlen) {
+    try {
+        Built b;
+        build(p, b);
+        PedMecHeuristic h(b.rs.get(), b.recomb, b.ped.get(), p->distrust != 0, &b.positions, row_limit, allow_mutations != 0, 0);
+        h.solve();
+        std::unique_ptr<Bipartition> part(h.getOptBipartition());
+        std::unique_ptr<std::vector<Transmission>> tv(h.getOptTransmission());
+        const auto haps = h.getOptHaplotypes();
+        std::unique_ptr<std::vector<std::vector<std::pair<uint32_t, uint32_t>>>> mut(h.getMutations());
+        s->score = h.getOptScore();
+        s->n_samples = (uint32_t)haps.size();
+        if (s->partition)
+            for (uint32_t r = 0; r < p->n_reads; ++r) s->partition[r] = (*part)[r] ? 1 : 0;
+        if (s->transmission)
+            for (uint32_t k = 0; k < p->n_cols; ++k) s->transmission[k] = (*tv)[k];
+        const size_t n = p->n_cols;
+        if (s->mutated) std::memset(s->mutated, 0, haps.size() * 2 * n);
+        for (size_t sid = 0; sid < haps.size(); ++sid) {
+            for (int hp = 0; hp < 2; ++hp)
+                for (size_t k = 0; k < n; ++k)
+                    if (s->haplotypes) s->haplotypes[(sid * 2 + hp) * n + k] = haps[sid][hp][k];
+            if (s->mutated)
+                for (const auto &m : (*mut)[sid]) s->mutated[(sid * 2 + m.first) * n + m.second] = 1;
+        }
+        return WHMEC_OK;
+    } catch (const std::exception &e) {
+        set_err(err, errlen, e.what());
+        return WHMEC_ERR_INPUT;
+    }
 }

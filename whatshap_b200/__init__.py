@@ -6,6 +6,7 @@ from .core import (  # noqa: F401
     NumericSampleIds,
     Pedigree,
     PedigreeDPTable,
+    PedMecHeuristic,
     PhredGenotypeLikelihoods,
     Read,
     ReadSet,
@@ -18,8 +19,9 @@ from .types import PhasingAlgorithm  # noqa: F401
 from .variant import Variant  # noqa: F401
 
 PhasingAlgorithm.register(PedigreeDPTable)
+PhasingAlgorithm.register(PedMecHeuristic)
 
 __all__ = [
-    "Genotype", "GenotypeDPTable", "NumericSampleIds", "Pedigree", "PedigreeDPTable", "PhredGenotypeLikelihoods", "Read", "ReadSet",
+    "Genotype", "GenotypeDPTable", "NumericSampleIds", "Pedigree", "PedigreeDPTable", "PedMecHeuristic", "PhredGenotypeLikelihoods", "Read", "ReadSet",
     "Variant", "PhasingAlgorithm", "compute_genotypes",
 ]

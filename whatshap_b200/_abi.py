@@ -57,6 +57,41 @@ class CSolution(C.Structure):
     ]
 
 
+class CHeuristicSolution(C.Structure):
+    """whmec_heuristic_solution (include/whmec.h)."""
+
+    _fields_ = [
+        ("score", C.c_float),
+        ("n_samples", C.c_uint32),
+        ("partition", _u8p),
+        ("transmission", _u32p),
+        ("haplotypes", C.POINTER(C.c_int8)),
+        ("mutated", _u8p),
+    ]
+
+
+class HeuristicSolution:
+    """Host arrays behind a whmec_heuristic_solution."""
+
+    def __init__(self, n_cols: int, n_reads: int, n_ind: int):
+        self.score = 0.0
+        self.n_samples = 0
+        self.partition = np.zeros(n_reads, np.uint8)
+        self.transmission = np.zeros(n_cols, np.uint32)
+        self.haplotypes = np.full((n_ind, 2, n_cols), -1, np.int8)
+        self.mutated = np.zeros((n_ind, 2, n_cols), np.uint8)
+
+    def as_c(self) -> "CHeuristicSolution":
+        return CHeuristicSolution(0.0, 0, self.partition.ctypes.data_as(_u8p), self.transmission.ctypes.data_as(_u32p),
+                                  self.haplotypes.ctypes.data_as(C.POINTER(C.c_int8)), self.mutated.ctypes.data_as(_u8p))
+
+    def same_as(self, other: "HeuristicSolution") -> bool:
+        return (self.n_samples == other.n_samples and self.score == other.score and np.array_equal(self.partition, other.partition)
+                and np.array_equal(self.transmission, other.transmission)
+                and np.array_equal(self.haplotypes[: self.n_samples], other.haplotypes[: self.n_samples])
+                and np.array_equal(self.mutated[: self.n_samples], other.mutated[: self.n_samples]))
+
+
 class CStats(C.Structure):
     _fields_ = [
         ("cells", C.c_uint64),

@@ -13,7 +13,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from ._abi import CProblem, CSolution, CStats, FlatProblem, FlatSolution, raise_for
+from ._abi import CHeuristicSolution, CProblem, CSolution, CStats, FlatProblem, FlatSolution, HeuristicSolution, raise_for
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libwhmec.so")
@@ -43,6 +43,7 @@ EXPORTS = (
     "whmec_read_sort_key",
     "whmec_genotype",
     "whmec_compute_genotypes",
+    "whmec_heuristic",
 )
 
 
@@ -76,6 +77,8 @@ def lib() -> C.CDLL:
     L.whmec_genotype.restype = C.c_int
     L.whmec_compute_genotypes.argtypes = [C.POINTER(CProblem), C.POINTER(C.c_double), C.POINTER(C.c_int8), C.c_char_p, C.c_size_t]
     L.whmec_compute_genotypes.restype = C.c_int
+    L.whmec_heuristic.argtypes = [C.POINTER(CProblem), C.c_uint32, C.c_int, C.POINTER(CHeuristicSolution), C.c_char_p, C.c_size_t]
+    L.whmec_heuristic.restype = C.c_int
     L.whmec_read_sort_key.argtypes = [C.c_char_p, C.c_size_t, C.c_int32]
     L.whmec_read_sort_key.restype = C.c_uint64
     u32p = C.POINTER(C.c_uint32)
@@ -128,6 +131,17 @@ def genotype(prob: FlatProblem, device: int = 0) -> Tuple[np.ndarray, dict]:
     rc = lib().whmec_genotype(C.byref(cp), out.ctypes.data_as(C.POINTER(C.c_double)), device, C.byref(st), err, len(err))
     raise_for(rc, err.value.decode())
     return out, st.as_dict()
+
+
+def heuristic(prob: FlatProblem, row_limit: int = 256, allow_mutations: bool = True) -> HeuristicSolution:
+    """The row-limited heuristic PedMEC solver (`whmec_heuristic`, host code): `prob.read_ind` holds the reads' sample ids."""
+    sol = HeuristicSolution(prob.n_cols, prob.n_reads, prob.n_ind)
+    cp, cs = prob.as_c(), sol.as_c()
+    err = C.create_string_buffer(512)
+    rc = lib().whmec_heuristic(C.byref(cp), int(row_limit), int(bool(allow_mutations)), C.byref(cs), err, len(err))
+    raise_for(rc, err.value.decode())
+    sol.score, sol.n_samples = float(cs.score), int(cs.n_samples)
+    return sol
 
 
 def compute_genotypes(prob: FlatProblem) -> Tuple[np.ndarray, np.ndarray]:

@@ -772,6 +772,82 @@ class PedigreeDPTable:
         return self._solution.partition.tolist()
 
 
+class PedMecHeuristic:
+    """Row-limited heuristic PedMEC solver, `whatshap phase --algorithm=heuristic` (core.pyx:674-734, src/pedmecheuristic.cpp).
+
+    Same constructor and methods as the reference binding.  Unlike `PedigreeDPTable` this is HOST code (`whmec_heuristic`,
+    csrc/heuristic.cpp): a sequential beam search over float scores whose results equal the reference's bit for bit.
+    The reads' sample ids must be the zero-based indices of the pedigree's individuals (src/pedmecheuristic.h:66)."""
+
+    def __init__(self, readset: ReadSet, recombcost, pedigree: Pedigree, row_limit: int = 256, distrust_genotypes: bool = False,
+                 positions=None, allow_mutations: bool = True, verbosity: int = 0):
+        if not isinstance(readset, ReadSet):
+            raise TypeError("Argument 'readset' has incorrect type")
+        if not isinstance(pedigree, Pedigree):
+            raise TypeError("Argument 'pedigree' has incorrect type")
+        self.pedigree = pedigree
+        n_ind = len(pedigree)
+
+        def sample_index(sample_id: int) -> int:
+            if not 0 <= sample_id < n_ind:
+                raise RuntimeError("PedMecHeuristic: sample id {} is not a zero-based index into the pedigree".format(sample_id))
+            return sample_id
+
+        pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind = _flatten_reads(readset, positions, sample_index)
+        n = len(pos_list)
+        if n_ind == 0:
+            raise RuntimeError("pedigree without individuals")
+        if n > 0 and pedigree.variant_count != -1 and pedigree.variant_count < n:
+            raise RuntimeError("pedigree holds genotypes for {} variants but there are {} columns".format(pedigree.variant_count, n))
+        rc = [int(x) for x in recombcost]
+        if len(rc) < n:
+            rc = rc + [rc[-1] if rc else 0] * (n - len(rc))
+        gt = np.full((n_ind, n), GT_OTHER, np.uint8)
+        for i in range(n_ind):
+            gt[i, :] = pedigree._gt_codes[i][:n]
+        self._problem = FlatProblem(
+            positions=np.array(pos_list, np.uint32), read_off=np.array(read_off, np.uint64), ent_col=np.array(ent_col, np.uint32),
+            ent_allele=np.array(ent_allele, np.uint8), ent_phred=np.array(ent_phred, np.uint32), read_ind=np.array(read_ind, np.uint32),
+            recombcost=np.array(rc[:n], np.uint32), n_ind=n_ind, trios=np.array([x for t in pedigree._triples for x in t], np.uint32),
+            distrust=bool(distrust_genotypes), gt=gt, gl=None)
+        self._solution = _lib.heuristic(self._problem, min(max(int(row_limit), 0), 65535), bool(allow_mutations))
+        # the samples the solver knows: ids of the reads and of the trio members, ascending (pedmecheuristic.cpp:52-63)
+        self._sample_ids = sorted(set(self._problem.read_ind.tolist()) | set(self._problem.trios.tolist()))
+
+    def get_super_reads(self) -> Tuple[List[ReadSet], List[int]]:
+        """One ReadSet per sample with `superread_0` / `superread_1` (quality 30 everywhere, pedmecheuristic.cpp:104-117),
+        plus the transmission vector."""
+        prob, sol = self._problem, self._solution
+        results = []
+        quality = np.full(prob.n_cols, 30, np.int64)
+        for k, sid in enumerate(self._sample_ids):
+            rs = ReadSet()
+            for h in range(2):
+                read = Read("superread_{}".format(h), -1, -1, sid)
+                read._pos = _typed(prob.positions)
+                read._allele = _typed(sol.haplotypes[k, h].astype(np.int64))
+                read._quality = _typed(quality)
+                rs.add(read)
+            results.append(rs)
+        return results, sol.transmission.tolist()
+
+    def get_optimal_cost(self) -> float:
+        """The reference's getOptScore(): a member its solve() never assigns, i.e. always 0.0 (pedmecheuristic.cpp:84-86)."""
+        return float(self._solution.score)
+
+    def get_optimal_partitioning(self) -> List[int]:
+        return [0 if x else 1 for x in self._solution.partition.tolist()]  # core.pyx:719
+
+    def get_mutations(self) -> List[List[Tuple[int, int]]]:
+        """Per sample the (haplotype, column) pairs whose allele does not follow the parent (core.pyx:722-734)."""
+        sol = self._solution
+        out = []
+        for k in range(sol.n_samples):
+            cols, haps = np.nonzero(sol.mutated[k].T)  # column-major: per column haplotype 0 before 1
+            out.append([(int(h), int(c)) for c, h in zip(cols, haps)])
+        return out
+
+
 class GenotypeDPTable:
     """Genotype likelihoods by the forward-backward algorithm over the same bipartition DP; the constructor
     does all the work (core.pyx:581-600, src/genotypedptable.cpp:17-48).  `pedigree` must carry genotype
