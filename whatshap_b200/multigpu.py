@@ -22,35 +22,41 @@ import numpy as np
 from ._abi import FlatProblem, FlatSolution
 
 
-def independent_blocks(prob: FlatProblem) -> List[Tuple[int, int]]:
+def _read_spans(prob: FlatProblem) -> Tuple[np.ndarray, np.ndarray]:
+    """(first column, last column) of every read, int64."""
+    starts = prob.read_off[:-1].astype(np.int64)
+    ends = prob.read_off[1:].astype(np.int64) - 1
+    return prob.ent_col[starts].astype(np.int64), prob.ent_col[ends].astype(np.int64)
+
+
+def independent_blocks(prob: FlatProblem, spans=None) -> List[Tuple[int, int]]:
     """Maximal column ranges [lo, hi) that no read crosses (chains of the DP)."""
     n = prob.n_cols
     if n == 0:
         return []
     span = np.zeros(n + 2, np.int64)
     if prob.n_reads:
-        starts = prob.read_off[:-1].astype(np.int64)
-        ends = prob.read_off[1:].astype(np.int64) - 1
-        first = prob.ent_col[starts].astype(np.int64)
-        last = prob.ent_col[ends].astype(np.int64)
+        first, last = spans if spans is not None else _read_spans(prob)
         span += np.bincount(first + 1, minlength=n + 2) - np.bincount(last + 1, minlength=n + 2)
     crossing = np.cumsum(span)[1:n]  # crossing[k-1] > 0: some read is active in columns k-1 and k
-    cuts = [0] + [int(k) for k in (np.nonzero(crossing == 0)[0] + 1)] + [n]
-    return [(cuts[i], cuts[i + 1]) for i in range(len(cuts) - 1)]
+    cuts = [0] + (np.nonzero(crossing == 0)[0] + 1).tolist() + [n]
+    return list(zip(cuts[:-1], cuts[1:]))
 
 
-def block_work(prob: FlatProblem, blocks: Sequence[Tuple[int, int]]) -> np.ndarray:
+def block_work(prob: FlatProblem, blocks: Sequence[Tuple[int, int]], spans=None) -> np.ndarray:
     """DP cells per block, sum_k 2^{a_k} (the quantity the sweep time is proportional to)."""
     n = prob.n_cols
     cov = np.zeros(n + 1, np.int64)
     if prob.n_reads:
-        starts = prob.read_off[:-1].astype(np.int64)
-        ends = prob.read_off[1:].astype(np.int64) - 1
-        cov += np.bincount(prob.ent_col[starts].astype(np.int64), minlength=n + 1) - np.bincount(prob.ent_col[ends].astype(np.int64) + 1, minlength=n + 1)
+        first, last = spans if spans is not None else _read_spans(prob)
+        cov += np.bincount(first, minlength=n + 1) - np.bincount(last + 1, minlength=n + 1)
     a = np.cumsum(cov)[:n]
     cells = np.exp2(np.minimum(a, 40).astype(np.float64))
     prefix = np.concatenate([[0.0], np.cumsum(cells)])
-    return np.array([prefix[hi] - prefix[lo] for lo, hi in blocks])
+    if not len(blocks):
+        return np.zeros(0)
+    bounds = np.asarray(blocks, np.int64)
+    return prefix[bounds[:, 1]] - prefix[bounds[:, 0]]
 
 
 def assign_blocks(work: np.ndarray, world: int) -> List[List[int]]:
@@ -92,19 +98,23 @@ def contiguous_shares(work: np.ndarray, world: int) -> List[Tuple[int, int]]:
     (a run may be empty when there are fewer blocks than ranks)."""
     work = np.asarray(work, np.float64)
     n = len(work)
+    from bisect import bisect_right
 
-    def runs_for(limit):  # greedy: fewest runs with no run above `limit`
-        cuts, acc = [0], 0.0
-        for i, w in enumerate(work):
-            if acc > 0 and acc + w > limit:
-                cuts.append(i)
-                acc = 0.0
-            acc += w
-        cuts.append(n)
+    pre = [0.0] + np.cumsum(work).tolist()  # the loads are sums of powers of two: exact in float64 for any realistic table
+
+    def runs_for(limit):  # greedy: fewest runs with no run above `limit` (a block heavier than the limit is a run of its own)
+        cuts, s = [0], 0
+        while s < n:
+            e = max(bisect_right(pre, pre[s] + limit) - 1, s + 1)  # largest e with load(s, e) <= limit, at least one block
+            s = min(e, n)
+            cuts.append(s)
+            if len(cuts) > world + 2:  # already more runs than ranks: the caller only compares with `world`
+                cuts[-1] = n
+                return cuts
         return cuts
 
     lo, hi = (float(work.max()) if n else 0.0), float(work.sum())
-    for _ in range(60):  # bisection on the largest run (the classic linear-partition bound)
+    for _ in range(48):  # bisection on the largest run (the classic linear-partition bound)
         mid = (lo + hi) / 2
         if len(runs_for(mid)) - 1 <= world:
             hi = mid
@@ -309,7 +319,8 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
     blocks = None
     MODE = {"single": 0, "blocks": 1, "segments": 2}
     if rank == 0:
-        blocks = independent_blocks(prob)
+        spans = _read_spans(prob) if prob.n_reads else None
+        blocks = independent_blocks(prob, spans)
         if prob.n_trios > 0 and world > 1 and len(blocks) > 1:  # transmission vectors couple the blocks: segments of the table
             ranges = segment_ranges(prob, world)
             flat = np.array([MODE["segments"]] + [x for r in ranges for x in (r if r is not None else (0, 0))], np.int64)
@@ -319,10 +330,10 @@ def solve_sharded(prob: Optional[FlatProblem], solver: Optional[Callable[[FlatPr
         else:
             # every rank gets ONE sub-problem: a contiguous run of whole blocks with about 1 / world of the DP cells (one
             # whmec_solve per rank sweeps all its chains together; block-by-block calls would be launch-latency bound)
-            runs = contiguous_shares(block_work(prob, blocks), world)
-            spans = [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in runs]
+            runs = contiguous_shares(block_work(prob, blocks, spans), world)
+            cuts = [(blocks[b0][0], blocks[b1 - 1][1]) if b1 > b0 else None for b0, b1 in runs]
             rows = [[np.array([MODE["blocks"]], np.int64).view(np.uint8)] + ([enc] if enc is not None else [])
-                    for enc in _wire.encode_problem_slices(prob, spans)]
+                    for enc in _wire.encode_problem_slices(prob, cuts)]
     t1 = time.perf_counter()
     pieces = _wire.separate(comm.scatter_rows(rows))
     head = pieces[0].view(np.int64)
