@@ -1073,9 +1073,18 @@ struct StreamCache {
 };
 StreamCache g_streams;
 
+// The device's default memory pool keeps what a solve frees (release threshold = unlimited): a process that phases many
+// chromosomes pays cudaMalloc for its largest problem once.  The memory stays with this process until it exits; a host
+// application that shares the GPU with other allocators opts out with WHMEC_KEEP_DEVICE_MEMORY=0 (the pool then trims at every
+// synchronisation, the CUDA default).
 void keep_pool_memory(int device) {
     static std::atomic<bool> done[64];  // zero-initialised; a second thread repeating the call is harmless
     if (device < 0 || device >= 64 || done[device].load()) return;
+    const char *e = std::getenv("WHMEC_KEEP_DEVICE_MEMORY");
+    if (e && e[0] == '0') {
+        done[device].store(true);
+        return;
+    }
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
         uint64_t threshold = UINT64_MAX;
