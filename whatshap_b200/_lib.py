@@ -16,7 +16,7 @@ import numpy as np
 from ._abi import CHeuristicSolution, CProblem, CSolution, CStats, FlatProblem, FlatSolution, HeuristicSolution, raise_for
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libwhmec.so")
+LIB_PATH = os.environ.get("WHMEC_LIBRARY") or os.path.join(HERE, "libwhmec.so")  # WHMEC_LIBRARY: another build of the same library (A/B runs)
 
 #: every symbol include/whmec.h declares (checked by tests/test_abi.py)
 EXPORTS = (

@@ -34,6 +34,11 @@ constexpr uint32_t BULK_MIN_J = 5;      // ... of at least 2^5 entries (128 byte
 constexpr uint32_t BULK_SKEW = 4;       // words of skew between consecutive chunks in the staging buffer (keeps 16-byte alignment)
 constexpr uint32_t STAGE_PAD_WORDS = BULK_SKEW << BULK_MAX_GA;
 
+// 0 (default): one arrival per warp at the split column barrier (lane 0, after __syncwarp); 1: one arrival per thread
+#ifndef WHMEC_COL_ARRIVE_ALL
+#define WHMEC_COL_ARRIVE_ALL 0
+#endif
+
 struct TileSmem {
     uint32_t buf[3][TILE_ENTRIES];  // [0],[1]: ping-pong projection; [2]: staging / prefetch of the next tile's input
     uint32_t stage_pad[STAGE_PAD_WORDS];  // directly behind buf[2]: bulk-copied chunks are laid out with a 16-byte skew each
@@ -266,8 +271,12 @@ __device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint3
     uint32_t *bpw = arena + S.bp_at[0];
     for (uint32_t j = 0; j < ncol; ++j) {
         column_fast_body<LG, false, true, true, MR>(pr, PackedEmit<BITS>{bpw, tid, section});
+#if WHMEC_COL_ARRIVE_ALL
+        mbar_arrive(&S.col_bar);  // every thread releases its own stores (build variant for compute-sanitizer racecheck)
+#else
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.col_bar);
+#endif
         cur ^= 1;
         if (j + 1 < ncol) {
             steady_prep<LG>(pr, S.scs[j + 1], S.TWs[j + 1][warp], S.T5s[j + 1][lane], S.buf[cur], S.buf[cur ^ 1], obase, pair_off, half, pop);
@@ -339,7 +348,7 @@ tile_panel_kernel(const Panel *__restrict__ panels, uint32_t n_panels, uint32_t 
     uint32_t col_phase = 0;     // parity of the column barrier's current phase
     if (tid == 0) {
         mbar_init(&S.stage_bar, 1);
-        mbar_init(&S.col_bar, NT / 32);
+        mbar_init(&S.col_bar, WHMEC_COL_ARRIVE_ALL ? NT : NT / 32);
     }
     __syncthreads();
     for (uint32_t work = blockIdx.x; work < total_tiles; work += gridDim.x) {
