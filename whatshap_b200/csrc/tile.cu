@@ -34,9 +34,12 @@ constexpr uint32_t BULK_MIN_J = 5;      // ... of at least 2^5 entries (128 byte
 constexpr uint32_t BULK_SKEW = 4;       // words of skew between consecutive chunks in the staging buffer (keeps 16-byte alignment)
 constexpr uint32_t STAGE_PAD_WORDS = BULK_SKEW << BULK_MAX_GA;
 
-// 0 (default): one arrival per warp at the split column barrier (lane 0, after __syncwarp); 1: one arrival per thread
+// Arrivals at the split column barrier.  1 (default): every thread arrives -- its release covers its own stores, which is also
+// what compute-sanitizer's racecheck can follow (0 hazards); 0: one arrival per warp (lane 0 after __syncwarp: correct by
+// cumulativity, but racecheck then reports the other lanes' stores as unordered; measured 0.4 % faster: 8.85 vs 8.88 ms per
+// cfg3 sweep, profiles/r02/r02n_*).
 #ifndef WHMEC_COL_ARRIVE_ALL
-#define WHMEC_COL_ARRIVE_ALL 0
+#define WHMEC_COL_ARRIVE_ALL 1
 #endif
 
 struct TileSmem {
@@ -252,8 +255,8 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
 // One barrier per column, split: a warp ARRIVES when its outputs of column j are stored, computes everything of column j + 1
 // that does not read the projection (addresses, constants, the subset sums of its outputs: column_fast_prep), and only then
 // WAITS for the other warps -- the block's drift at the barrier is filled with work instead of idle issue slots.
-// The barrier is an mbarrier with one arrival per warp (the warp's lanes are ordered by __syncwarp before lane 0 arrives;
-// arrive = release, try_wait = acquire at CTA scope).  Every thread of the block runs the same number of iterations.
+// The barrier is an mbarrier (arrive = release, try_wait = acquire at CTA scope) with one arrival per thread (or per warp, see
+// WHMEC_COL_ARRIVE_ALL).  Every thread of the block runs the same number of iterations.
 template <int LG, bool MR>
 __device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint32_t *__restrict__ arena, uint32_t &cur, uint32_t &col_phase,
                                                uint32_t tid) {
@@ -272,7 +275,7 @@ __device__ __forceinline__ void steady_columns(TileSmem &S, uint32_t ncol, uint3
     for (uint32_t j = 0; j < ncol; ++j) {
         column_fast_body<LG, false, true, true, MR>(pr, PackedEmit<BITS>{bpw, tid, section});
 #if WHMEC_COL_ARRIVE_ALL
-        mbar_arrive(&S.col_bar);  // every thread releases its own stores (build variant for compute-sanitizer racecheck)
+        mbar_arrive(&S.col_bar);  // every thread releases its own stores
 #else
         __syncwarp();
         if (lane == 0) mbar_arrive(&S.col_bar);
