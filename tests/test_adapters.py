@@ -233,3 +233,29 @@ def test_prior_genotyper_adapter_on_real_objects(ref_core):
         assert [g.as_vector() for g in got_gt] == [g.as_vector() for g in want_gt]
         assert [tuple(x) for x in got_gl] == [tuple(x) for x in want_gl]
         assert all(isinstance(g, ref_core.Genotype) for g in got_gt)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in tp.CASES if not tp.CASES[n].get("distrust") and tp.CASES[n]["reads"].strip()
+                                        and tp.CASES[n].get("positions") is None))
+def test_heuristic_adapter_on_real_objects_equals_the_real_class(ref_core, name):
+    """`make_heuristic_class` (the host solver `whmec_heuristic`) against the REAL whatshap.core.PedMecHeuristic on real objects:
+    same super-reads, transmission vector, bipartition and mutation list (core.pyx:674-734)."""
+    case = tp.CASES[name]
+    my_rs = string_to_readset_pedigree(case["reads"])
+    real_rs = to_real(ref_core, my_rs)
+    ped = real_pedigree(ref_core, case, False)
+    recomb = [max(int(x), 1) for x in case["recomb"]]  # a zero mutation cost leaves the reference undefined with distrusted genotypes
+    recomb = recomb + [recomb[-1]] * 4
+    Mine = adapters.make_heuristic_class(ref_core)
+    for row_limit in (2, 64):
+        a = Mine(real_rs, recomb, ped, row_limit)
+        b = ref_core.PedMecHeuristic(real_rs, recomb[: len(real_rs.get_positions())], ped, row_limit)
+        (sa, ta), (sb, tb) = a.get_super_reads(), b.get_super_reads()
+        assert ta == tb and len(sa) == len(sb)
+        for ra, rb in zip(sa, sb):
+            for x, y in zip(ra, rb):
+                assert (x.name, x.sample_id) == (y.name, y.sample_id)
+                assert [(v.position, v.allele, v.quality) for v in x] == [(v.position, v.allele, v.quality) for v in y]
+        assert a.get_optimal_partitioning() == b.get_optimal_partitioning()
+        assert a.get_mutations() == [[tuple(m) for m in ms] for ms in b.get_mutations()]
+        assert a.get_optimal_cost() == b.get_optimal_cost()

@@ -241,6 +241,55 @@ def make_dp_table_class(core_module, solver=None):
     return PedigreeDPTable
 
 
+def make_heuristic_class(core_module):
+    """A `PedMecHeuristic` look-alike (constructor and methods of whatshap/core.pyx:674-734) for `core_module`'s own objects:
+    `whatshap.cli.phase.PedMecHeuristic = make_heuristic_class(whatshap.core)` (name imported at cli/phase.py:41).  Runs the host
+    solver `whmec_heuristic` (bit-identical to src/pedmecheuristic.cpp) and answers with `core_module`'s Read / ReadSet objects.
+    The reference requires the reads' sample ids to be the zero-based indices of the pedigree's individuals."""
+    Read, ReadSet = core_module.Read, core_module.ReadSet
+
+    class PedMecHeuristic:
+        def __init__(self, readset, recombcost, pedigree, row_limit=256, distrust_genotypes=False, positions=None, allow_mutations=True,
+                     verbosity=0):
+            self.pedigree = pedigree
+            # genotype likelihoods play no role in the heuristic: flatten with trusted genotypes, keep the flag for the solver
+            self._problem, ids = flatten_objects(readset, recombcost, pedigree, False, positions)
+            if list(ids) != list(range(len(ids))):
+                raise RuntimeError("PedMecHeuristic: sample ids must be the zero-based indices of the pedigree's individuals")
+            self._problem.distrust = bool(distrust_genotypes)
+            self._solution = _lib.heuristic(self._problem, min(max(int(row_limit), 0), 65535), bool(allow_mutations))
+            self._sample_ids = sorted(set(self._problem.read_ind.tolist()) | set(self._problem.trios.tolist()))
+
+        def get_super_reads(self):
+            prob, sol = self._problem, self._solution
+            positions = prob.positions.tolist()
+            results = []
+            for k, sid in enumerate(self._sample_ids):
+                rs = ReadSet()
+                for h in range(2):
+                    read = Read("superread_{}".format(h), -1, -1, sid)
+                    for p, a in zip(positions, sol.haplotypes[k, h].tolist()):
+                        read.add_variant(p, a, 30)
+                    rs.add(read)
+                results.append(rs)
+            return results, sol.transmission.tolist()
+
+        def get_optimal_cost(self):
+            return float(self._solution.score)
+
+        def get_optimal_partitioning(self):
+            return [0 if x else 1 for x in self._solution.partition.tolist()]
+
+        def get_mutations(self):
+            sol, out = self._solution, []
+            for k in range(sol.n_samples):
+                cols, haps = np.nonzero(sol.mutated[k].T)
+                out.append([(int(h), int(c)) for c, h in zip(cols, haps)])
+            return out
+
+    return PedMecHeuristic
+
+
 def make_genotype_table_class(core_module, solver=None):
     """A `GenotypeDPTable` look-alike (constructor and `get_genotype_likelihoods` of whatshap/core.pyx:581-600) that
     runs the forward-backward DP on the GPU from `core_module`'s own objects and answers with its
