@@ -30,14 +30,15 @@ for it in range(6):
 print("RESULT %%s threads=%%s  wrapper+call %%.2f ms  C call %%.2f ms" %% (name, os.environ.get("WHMEC_HOST_THREADS", "all"), best_py * 1e3, best_c * 1e3), flush=True)
 ''' % ROOT
 
-for name in sys.argv[1:] or ["cfg3", "cfg2", "cfg5"]:
-    for threads, extra in ((None, {}), ("32", {}), ("16", {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})) if name == "cfg3" else ((None, {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})):
-        env = dict(os.environ, WHMEC_TIMING="1", **extra)
-        if threads:
-            env["WHMEC_HOST_THREADS"] = threads
-        r = subprocess.run([sys.executable, "-c", CHILD, name], env=env, capture_output=True, text=True, timeout=300)
-        lines = [l for l in r.stderr.splitlines() if l.startswith("[whmec]")]
-        print("==", name, "threads", threads or "all", extra, flush=True)
-        for l in lines[-8:]:
-            print("   ", l)
-        print("   ", (r.stdout.strip().splitlines() or ["(no result) " + r.stderr[-300:]])[-1], flush=True)
+if __name__ == "__main__":
+    for name in sys.argv[1:] or ["cfg3", "cfg2", "cfg5"]:
+        for threads, extra in ((None, {}), ("32", {}), ("16", {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})) if name == "cfg3" else ((None, {}), (None, {"WHMEC_PINNED_UPLOAD": "0"})):
+            env = dict(os.environ, WHMEC_TIMING="1", **extra)
+            if threads:
+                env["WHMEC_HOST_THREADS"] = threads
+            r = subprocess.run([sys.executable, "-c", CHILD, name], env=env, capture_output=True, text=True, timeout=300)
+            lines = [l for l in r.stderr.splitlines() if l.startswith("[whmec]")]
+            print("==", name, "threads", threads or "all", extra, flush=True)
+            for l in lines[-8:]:
+                print("   ", l)
+            print("   ", (r.stdout.strip().splitlines() or ["(no result) " + r.stderr[-300:]])[-1], flush=True)

@@ -7,6 +7,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdint>
 #include <cstdlib>
 #include <exception>
 #include <mutex>
@@ -36,6 +37,25 @@ void stage_free(void *p) {
     if (auto fn = g_stage_release.load(std::memory_order_acquire))
         if (fn(p)) return;
     ::operator delete(p);
+}
+
+bool stage_flush_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("WHMEC_FLUSH_UPLOAD");
+        return e && e[0] == '1';
+    }();
+    return on && g_stage_alloc.load(std::memory_order_relaxed) != nullptr;  // only page-locked arrays are read by the DMA engine directly
+}
+
+void stage_flush(const void *p, size_t bytes) {
+#if defined(__x86_64__)
+    const uintptr_t a = (uintptr_t)p & ~(uintptr_t)63, e = (uintptr_t)p + bytes;
+    for (uintptr_t q = a; q < e; q += 64) __builtin_ia32_clflush((const void *)q);
+    __builtin_ia32_sfence();
+#else
+    (void)p;
+    (void)bytes;
+#endif
 }
 
 uint32_t host_threads(uint32_t cap) {

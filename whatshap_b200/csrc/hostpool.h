@@ -56,6 +56,13 @@ void set_stage_hooks(const StageHooks &hooks);
 void *stage_alloc(size_t bytes);
 void stage_free(void *p);
 
+// Writes the cache lines of [p, p + bytes) back to memory (x86: clflush; elsewhere a no-op).  An upload array that up to 128
+// host threads have just written sits in dirty lines of many caches (on a two-socket box also the remote socket's); the DMA
+// engine then has to pull every line out of a cache.  A writer that flushes its own part when it is done hands the DMA plain
+// memory.  Only used when WHMEC_FLUSH_UPLOAD=1 (see stage_flush_enabled).
+void stage_flush(const void *p, size_t bytes);
+bool stage_flush_enabled();
+
 template <class T>
 struct StageAlloc {
     using value_type = T;

@@ -471,9 +471,11 @@ int pack_problem(const whmec_problem *p, Packed &pk, std::string &err, bool want
         st.algorithmic_bytes += ch.alg_bytes;
         pk.chain_begin.insert(pk.chain_begin.end(), ch.chain_starts.begin(), ch.chain_starts.end());
     }
+    const bool flush = stage_flush_enabled();
     parallel_tasks(n_chunks, pack_threads, [&](uint32_t ci) {
         if (word_base[ci])
             for (uint32_t k = cut[ci]; k < cut[ci + 1]; ++k) pk.cols[k].bp_off += word_base[ci];
+        if (flush) stage_flush(&pk.cols[cut[ci]], (size_t)(cut[ci + 1] - cut[ci]) * sizeof(ColMeta));  // (hostpool.h: stage_flush)
     });
     pk.chain_begin.push_back(n);
     pk.bp_words = words;

@@ -384,6 +384,9 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
         }
         if (bp_base[c])
             for (uint32_t k = pk.chain_begin[c]; k < pk.chain_begin[c + 1]; ++k) ts.cols[k].bp_off += bp_base[c];
+        // the chain's records are final: out of this thread's cache, ready for the DMA engine (WHMEC_FLUSH_UPLOAD=1)
+        if (stage_flush_enabled())
+            stage_flush(&ts.cols[pk.chain_begin[c]], (size_t)(pk.chain_begin[c + 1] - pk.chain_begin[c]) * sizeof(TileCol));
         // hand-off layouts between consecutive panels of the chain (see Panel in tile_plan.h)
         for (size_t q = 0; q + 1 < per_chain[c].size(); ++q) {
             Panel &A = per_chain[c][q], &B = per_chain[c][q + 1];
