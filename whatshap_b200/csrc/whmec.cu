@@ -1010,7 +1010,8 @@ struct PinnedPool {
         return true;
     }
 };
-PinnedPool g_pinned;
+// (heap singletons, never destroyed: a plan that outlives static destruction at process exit must still find them)
+PinnedPool &g_pinned = *new PinnedPool();
 
 void install_stage_hooks() {
     static std::once_flag once;
@@ -1071,7 +1072,7 @@ struct StreamCache {
         destroy(s);
     }
 };
-StreamCache g_streams;
+StreamCache &g_streams = *new StreamCache();
 
 // The device's default memory pool keeps what a solve frees (release threshold = unlimited): a process that phases many
 // chromosomes pays cudaMalloc for its largest problem once.  The memory stays with this process until it exits; a host
