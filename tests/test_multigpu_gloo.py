@@ -167,3 +167,28 @@ def test_wire_encoding_round_trips():
     assert back.same_as(sol) and tag == 3 and extra.tolist() == [0, 1, 2, 3]
     rows = _wire.separate(_wire.join([np.arange(5, dtype=np.uint8), np.zeros(0, np.uint8), np.arange(40, dtype=np.uint8)]))
     assert [r.tolist() for r in rows] == [list(range(5)), [], list(range(40))]
+
+
+def test_contiguous_shares_minimise_the_largest_run():
+    """The block runs handed to the ranks: contiguous, covering, at most `world` of them, and the heaviest run is as light as a
+    brute-force search over all cut positions can make it (the bisection over prefix sums of multigpu.contiguous_shares)."""
+    import itertools
+
+    import numpy as np
+
+    from whatshap_b200 import multigpu
+
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        n, world = int(rng.integers(1, 9)), int(rng.integers(1, 6))
+        work = np.exp2(rng.integers(0, 12, n)).astype(np.float64)
+        runs = multigpu.contiguous_shares(work, world)
+        assert len(runs) == world
+        real = [r for r in runs if r[1] > r[0]]
+        assert real[0][0] == 0 and real[-1][1] == n and all(a[1] == b[0] for a, b in zip(real, real[1:]))
+        heaviest = max(work[a:b].sum() for a, b in real)
+        best = min(max(work[a:b].sum() for a, b in zip((0,) + cuts, cuts + (n,)))
+                   for k in range(min(world, n)) for cuts in itertools.combinations(range(1, n), k))
+        assert heaviest == best, (work, world, runs)
+        if n >= world:  # no rank idles while another holds two blocks
+            assert len(real) == world
