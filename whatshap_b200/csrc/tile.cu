@@ -141,7 +141,7 @@ struct BallotEmit {
     __device__ __forceinline__ void store_mirror(uint32_t) const {}
 };
 
-// Thread-packed layout (TileCol::pad2 == 1, experimental): thread `tid` owns element `tid` of BITS bits; a warp's 32
+// Thread-packed layout (TileCol::pad2 == 1, the default): thread `tid` owns element `tid` of BITS bits; a warp's 32
 // elements are contiguous (one 32- or 64-byte transaction).
 template <int BITS>
 struct PackedEmit {

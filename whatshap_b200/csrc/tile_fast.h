@@ -57,7 +57,7 @@ WHMEC_HD uint32_t tile_shift_in_sign(uint32_t bits, uint32_t t) {
 // candidate cells of an output share one 64-bit load (and with SHARE the two outputs that differ
 // only in the newly started read share it too), back-pointers leave as warp ballots.
 // `emit(word, bit)`: this thread's bit of back-pointer word `word` of its warp (words are numbered from the warp's first).
-// PACKED (TileCol::pad2 == 1, experimental): the thread keeps the bits of its own 2^LG (x 2 with SHARE) outputs in a
+// PACKED (TileCol::pad2 == 1, the default layout since round 2): the thread keeps the bits of its own 2^LG (x 2 with SHARE) outputs in a
 // register and hands them to `emit.store(bits)` once per column.  No predicate is formed: with all values below 2^28
 // (the tile path's precondition) "candidate 1 wins" is the sign of v1 - v0 - par, and one funnel shift moves that sign
 // bit into the register — IADD3 + SHF per output instead of IADD + ISETP + VOTE + STG.  The outputs arrive in the order

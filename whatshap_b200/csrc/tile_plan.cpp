@@ -259,7 +259,7 @@ void plan_tiles(const Packed &pk, TileSchedule &ts) {
                             tc.pad1 = (uint8_t)(tc.l_out - 10);
                         }
                     }
-                    // experimental (WHMEC_TILE_PACKED_BP=1): thread-packed back-pointer bits where a thread owns 8 or 16 outputs
+                    // thread-packed back-pointer bits where a thread owns 8 or 16 outputs (default; WHMEC_TILE_PACKED_BP=0: warp ballots)
                     if (packed_bp && tc.pad0) {
                         const uint32_t per_thread = (1u << tc.pad1) << (tc.pad0 == 2 ? 1 : 0);
                         if (per_thread == 8 || per_thread == 16) tc.pad2 = 1;

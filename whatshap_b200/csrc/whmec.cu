@@ -1128,7 +1128,7 @@ struct whmec_plan {
     bool transferred = false;
     int exits_mode = 0;  // 0: not computed since the last sweep; 1: last chain entered at the optimum; 2: like any chain
     DevBuf<uint32_t> d_in_vec, d_matrix, d_bt_exits, d_bt_entries;
-    // fused per-chain pedigree sweep (ped_chain_kernel, experimental)
+    // fused trio sweep (ped_fused_kernel / ped_fused_cluster_kernel, ped_fused.h)
     bool use_ped_fused = false;
     uint32_t ped_cluster = 1;  // CTAs per chain of the fused pedigree sweep
     DevBuf<uint32_t> d_chain_rows, d_chain_in, d_chain_out;
