@@ -270,7 +270,11 @@ def bench_reference(args, rank, world):
 
     # FIXED sample (no time-based calibration: the ratio against this arm must be reproducible): one independent
     # block prefix of REF_SAMPLE_COLS columns per host thread, every instance single-threaded like the reference.
-    cols = REF_SAMPLE_COLS[name]
+    # A step of that size takes ~20 s at coverage 20 on 128 threads; so that `--steps K --warmup W` still ends within a few
+    # minutes whatever K and W the caller picks, the prefix is shortened as a function of K + W alone (deterministic: the same
+    # flags give the same sample): full length up to 6 calls, e.g. 4 columns for --steps 20 --warmup 5.
+    calls = args.steps + args.warmup + 1
+    cols = max(2, min(REF_SAMPLE_COLS[name], (REF_SAMPLE_COLS[name] * 13 // 2) // calls))
     threads = min(threads, REF_MAX_THREADS.get(name, threads))
     probs = make(cols, threads)
     if ref is not None:
@@ -301,7 +305,8 @@ def bench_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": name, "description": WORKLOADS[name][0],
-                   "sample": f"{len(probs)} independent {cols}-column block prefixes per step, one per host thread"},
+                   "sample": f"{len(probs)} independent {cols}-column block prefixes per step, one per host thread "
+                             f"(prefix length fixed by --steps + --warmup = {args.steps + args.warmup})"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads if kind == "reference" else 1, "kind": kind,
                          "sample": f"{len(probs)} x {cols} columns per step (fixed sample)",
                          "single_thread_value": single},
