@@ -1,7 +1,7 @@
 """CPU fuzz of the host heuristic solver `whmec_heuristic` (csrc/heuristic.cpp) against the reference's PedMecHeuristic compiled in
 place (oracle/_ref, whref_heuristic).  Every problem runs in a forked child: on some inputs the REFERENCE itself crashes (e.g. empty
 phasing lists with distrusted genotypes index out of bounds, src/pedmecheuristic.cpp:505-530); those are counted and skipped.
-    python scripts/cpu_fuzz_heuristic.py <seed> <seconds>"""
+    python scripts/cpu_fuzz_heuristic.py <seed> <seconds> [no-mutations]"""
 import os
 import sys
 import time
@@ -24,8 +24,13 @@ def make(seed):
     return prob, int(rng.choice([1, 2, 4, 16, 256])), ped, distrust
 
 
+ALLOW = True
+
+
 def main():
+    global ALLOW
     seed0, secs = int(sys.argv[1]), float(sys.argv[2])
+    ALLOW = not (len(sys.argv) > 3 and sys.argv[3] == "no-mutations")  # third argument: allow_mutations = False (NaN costs, Q2)
     ref = checker.reference()
     _lib.lib()
     t0, k, bad, ref_crash, ours_crash = time.time(), 0, 0, 0, 0
@@ -39,12 +44,12 @@ def main():
         if pid == 0:
             code = 0
             try:
-                want = ref.heuristic(prob, rl, True)
+                want = ref.heuristic(prob, rl, ALLOW)
             except Exception:
                 os._exit(3)
             os.write(1, b"")  # (reference survived)
             try:
-                got = _lib.heuristic(prob, rl, True)
+                got = _lib.heuristic(prob, rl, ALLOW)
                 code = 0 if got.same_as(want) else 1
             except Exception:
                 code = 2
@@ -55,7 +60,7 @@ def main():
             pid2 = os.fork()
             if pid2 == 0:
                 try:
-                    _lib.heuristic(prob, rl, True)
+                    _lib.heuristic(prob, rl, ALLOW)
                 except Exception:
                     pass
                 os._exit(0)

@@ -444,6 +444,12 @@ int Solver::run(whmec_heuristic_solution *out, std::string &err) {
                 q.score += best_phasing(firsts, q.tv, col, nullptr, nullptr);
             }
         }
+        if (sols.empty()) {
+            // every total is NaN (allow_mutations == false: `false * inf`, Q2) and NaN survives no comparison of the pruning step;
+            // the reference walks back through empty columns here (undefined)
+            err = "the heuristic kept no solution (scores are not numbers: allow_mutations = false is not usable, as in the reference)";
+            return WHMEC_ERR_UNSUPPORTED;
+        }
         // record the column
         back[col].reserve(sols.size());
         placed_all[col].reserve(sols.size() * n_new);
