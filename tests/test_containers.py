@@ -243,3 +243,34 @@ def test_readset_columnar_copy_follows_add_sort_and_mutation():
     clone = pickle.loads(pickle.dumps(rs))
     got, want = clone._flat_columns(), _columns_from_objects(rs)
     assert all(np.array_equal(g, w) for g, w in zip(got, want))
+
+
+def test_flatten_columns_of_reads_with_gaps():
+    """`_flatten_reads` maps a read's positions to columns with one binary search per read plus one per entry behind a gap
+    (a position of another read that this read skips): compared with a dictionary look-up per entry."""
+    import random
+
+    import numpy as np
+
+    from whatshap_b200.core import _flatten_reads
+
+    rnd = random.Random(9)
+    all_pos = sorted(rnd.sample(range(1000, 5000), 300))
+    rs = ReadSet()
+    start = 0
+    for i in range(120):
+        start += rnd.randrange(0, 4)
+        span = all_pos[start : start + rnd.randrange(1, 12)]
+        if not span:
+            break
+        kept = [p for j, p in enumerate(span) if j in (0, len(span) - 1) or rnd.random() < 0.7]  # interior gaps
+        r = Read("g%03d" % i, 30, 0, 0)
+        for p in kept:
+            r.add_variant(p, rnd.randrange(2), rnd.randrange(1, 30))
+        rs.add(r)
+    pos_list, read_off, ent_col, ent_allele, ent_phred, read_ind = _flatten_reads(rs, None, lambda sid: 0)
+    col_of = {p: i for i, p in enumerate(pos_list)}
+    want = [col_of[v.position] for r in rs for v in r]
+    assert pos_list == sorted({v.position for r in rs for v in r})
+    assert np.asarray(ent_col).tolist() == want
+    assert np.asarray(read_off).tolist() == [0] + list(np.cumsum([len(r) for r in rs]))

@@ -649,7 +649,15 @@ def _flatten_reads(readset: ReadSet, positions: Optional[Sequence[int]], index_o
         inside = (pos >= lo_p) & (pos <= hi_p)
         col = np.where(inside, lut[np.clip(pos, lo_p, hi_p) - lo_p], -1)
     elif n and positions is None:
-        col = np.searchsorted(pos_arr, pos)  # every position of a read is a column
+        # every position of a read is a column.  Reads mostly cover consecutive columns: one binary search per READ, then
+        # column = first column + offset inside the read wherever the position found there is the entry's, and a binary search
+        # only for the entries behind a gap
+        first_col = np.searchsorted(pos_arr, pos[off[:-1]]) if m else np.zeros(0, np.int64)
+        col = np.repeat(first_col - off[:-1], lens) + np.arange(total, dtype=np.int64)
+        np.minimum(col, n - 1, out=col)
+        behind_gap = np.nonzero(pos_arr[col] != pos)[0]
+        if behind_gap.size:
+            col[behind_gap] = np.searchsorted(pos_arr, pos[behind_gap])
     elif n:
         col = np.searchsorted(pos_arr, pos)
         col = np.where((col < n) & (pos_arr[np.minimum(col, n - 1)] == pos), col, -1)
