@@ -60,14 +60,28 @@ def encode_problem(p: FlatProblem, tag: int = 0, lo: int = 0) -> np.ndarray:
     )
 
 
-def encode_problem_slices(p: FlatProblem, spans: Sequence[Optional[Tuple[int, int]]]) -> List[Optional[np.ndarray]]:
+class Lazy:
+    """A payload whose size is known before its bytes exist: `write(view)` fills a uint8 view of `nbytes` bytes.  `Comm.scatter_rows`
+    lets such a payload write itself straight into the page-locked send buffer (one pass over the data on rank 0 instead of two)."""
+
+    def __init__(self, nbytes: int, write):
+        self.nbytes = int(nbytes)
+        self.write = write
+
+    def materialize(self) -> np.ndarray:
+        out = np.empty(self.nbytes, np.uint8)
+        self.write(out)
+        return out
+
+
+def encode_problem_slices(p: FlatProblem, spans: Sequence[Optional[Tuple[int, int]]]) -> List[Optional[Lazy]]:
     """`encode_problem(p.slice_columns(lo, hi), tag=i, lo=lo)` for every span (lo, hi) -- no read may cross a span's ends --
-    without materialising the slices: read / entry ranges from one pass over the reads' first columns, every array written
-    once, straight into its row."""
+    without materialising the slices: read / entry ranges from one pass over the reads' first columns; every row is returned as a
+    `Lazy` payload that writes each array once, straight into wherever the row is wanted."""
     m = p.n_reads
     first = p.ent_col[p.read_off[:-1].astype(np.int64)] if m else np.zeros(0, np.uint32)
     gl_all = p.gl
-    rows: List[Optional[np.ndarray]] = []
+    rows: List[Optional[Lazy]] = []
     for i, sp in enumerate(spans):
         if sp is None:
             rows.append(None)
@@ -76,44 +90,46 @@ def encode_problem_slices(p: FlatProblem, spans: Sequence[Optional[Tuple[int, in
         r0, r1 = (int(x) for x in np.searchsorted(first, [lo, hi], side="left"))  # reads are sorted by first column
         e0, e1 = int(p.read_off[r0]), int(p.read_off[r1])
         n = hi - lo
+        if e1 > e0 and int(p.ent_col[e0:e1].max()) >= hi:
+            raise ValueError("a read crosses the requested cut")
         sizes = [4 * n, 8 * (r1 - r0 + 1), 4 * (e1 - e0), e1 - e0, 4 * (e1 - e0), 4 * (r1 - r0), 4 * n, p.trios.nbytes, p.n_ind * n,
                  (p.n_ind * n * 3 * 8) if gl_all is not None else 0]
         head = np.array([_MAGIC_PROBLEM, n, r1 - r0, p.n_ind, 1 if p.distrust else 0, 1 if gl_all is not None else 0, i, lo] + sizes, np.uint64)
         total = _pad(head.nbytes) + sum(_pad(x) for x in sizes)
-        out = np.empty(total, np.uint8)
-        out[: head.nbytes] = head.view(np.uint8)
-        out[head.nbytes : _pad(head.nbytes)] = 0
-        off = _pad(head.nbytes)
 
-        def put(arr, dtype, nbytes):
-            nonlocal off
-            if nbytes:
-                out[off : off + nbytes].view(dtype)[:] = arr.reshape(-1)
-            out[off + nbytes : off + _pad(nbytes)] = 0
-            off += _pad(nbytes)
+        def write(out, lo=lo, hi=hi, r0=r0, r1=r1, e0=e0, e1=e1, head=head, sizes=sizes):
+            out[: head.nbytes] = head.view(np.uint8)
+            out[head.nbytes : _pad(head.nbytes)] = 0
+            off = _pad(head.nbytes)
 
-        put(p.positions[lo:hi], np.uint32, sizes[0])
-        ro = out[off : off + sizes[1]].view(np.uint64)
-        np.subtract(p.read_off[r0 : r1 + 1], p.read_off[r0], out=ro)
-        out[off + sizes[1] : off + _pad(sizes[1])] = 0
-        off += _pad(sizes[1])
-        ec = out[off : off + sizes[2]].view(np.uint32)
-        np.subtract(p.ent_col[e0:e1], np.uint32(lo), out=ec)
-        if e1 > e0 and int(ec.max()) >= n:
-            raise ValueError("a read crosses the requested cut")
-        out[off + sizes[2] : off + _pad(sizes[2])] = 0
-        off += _pad(sizes[2])
-        put(p.ent_allele[e0:e1], np.uint8, sizes[3])
-        put(p.ent_phred[e0:e1], np.uint32, sizes[4])
-        put(p.read_ind[r0:r1], np.uint32, sizes[5])
-        put(p.recombcost[lo:hi], np.uint32, sizes[6])
-        put(p.trios, np.uint32, sizes[7])
-        put(np.ascontiguousarray(p.gt[:, lo:hi]), np.uint8, sizes[8])
-        if gl_all is not None:
-            put(np.ascontiguousarray(gl_all[:, lo:hi]), np.float64, sizes[9])
-        else:
-            put(np.zeros(0, np.float64), np.float64, 0)
-        rows.append(out)
+            def put(arr, dtype, nbytes):
+                nonlocal off
+                if nbytes:
+                    out[off : off + nbytes].view(dtype)[:] = arr.reshape(-1)
+                out[off + nbytes : off + _pad(nbytes)] = 0
+                off += _pad(nbytes)
+
+            put(p.positions[lo:hi], np.uint32, sizes[0])
+            ro = out[off : off + sizes[1]].view(np.uint64)
+            np.subtract(p.read_off[r0 : r1 + 1], p.read_off[r0], out=ro)
+            out[off + sizes[1] : off + _pad(sizes[1])] = 0
+            off += _pad(sizes[1])
+            ec = out[off : off + sizes[2]].view(np.uint32)
+            np.subtract(p.ent_col[e0:e1], np.uint32(lo), out=ec)
+            out[off + sizes[2] : off + _pad(sizes[2])] = 0
+            off += _pad(sizes[2])
+            put(p.ent_allele[e0:e1], np.uint8, sizes[3])
+            put(p.ent_phred[e0:e1], np.uint32, sizes[4])
+            put(p.read_ind[r0:r1], np.uint32, sizes[5])
+            put(p.recombcost[lo:hi], np.uint32, sizes[6])
+            put(p.trios, np.uint32, sizes[7])
+            put(np.ascontiguousarray(p.gt[:, lo:hi]), np.uint8, sizes[8])
+            if gl_all is not None:
+                put(np.ascontiguousarray(gl_all[:, lo:hi]), np.float64, sizes[9])
+            else:
+                put(np.zeros(0, np.float64), np.float64, 0)
+
+        rows.append(Lazy(total, write))
     return rows
 
 
@@ -240,7 +256,10 @@ class Comm:
                     big[i, : head.nbytes] = head.view(np.uint8)
                     off = _pad(head.nbytes)
                     for b in r:
-                        big[i, off : off + b.nbytes] = b
+                        if isinstance(b, Lazy):
+                            b.write(big[i, off : off + b.nbytes])  # encoded in place: no intermediate copy of the payload
+                        else:
+                            big[i, off : off + b.nbytes] = b
                         off += _pad(b.nbytes)
                 # (padding bytes are never read: every reader goes by the recorded lengths)
             dev = stage.to(self.device, non_blocking=True) if self.cuda else stage
