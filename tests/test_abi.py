@@ -35,18 +35,20 @@ def test_struct_layout_matches_header(tmp_path):
     """sizeof/offsetof as laid out by the C compiler for include/whmec.h == the ctypes mirror."""
     import subprocess
 
-    from whatshap_b200._abi import CSolution
+    from whatshap_b200._abi import CHeuristicSolution, CSolution
 
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "whmec.h"\n'
-        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu\\n\", sizeof(whmec_problem), sizeof(whmec_solution),"
-        " sizeof(whmec_stats), offsetof(whmec_problem, gl), offsetof(whmec_stats, sweep_ms), offsetof(whmec_solution, sr_quality));return 0;}\n"
+        "int main(void){printf(\"%zu %zu %zu %zu %zu %zu %zu %zu\\n\", sizeof(whmec_problem), sizeof(whmec_solution),"
+        " sizeof(whmec_stats), offsetof(whmec_problem, gl), offsetof(whmec_stats, sweep_ms), offsetof(whmec_solution, sr_quality),"
+        " sizeof(whmec_heuristic_solution), offsetof(whmec_heuristic_solution, mutated));return 0;}\n"
     )
     exe = tmp_path / "layout"
     subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
-    want = [C.sizeof(CProblem), C.sizeof(CSolution), C.sizeof(CStats), CProblem.gl.offset, CStats.sweep_ms.offset, CSolution.sr_quality.offset]
+    want = [C.sizeof(CProblem), C.sizeof(CSolution), C.sizeof(CStats), CProblem.gl.offset, CStats.sweep_ms.offset, CSolution.sr_quality.offset,
+            C.sizeof(CHeuristicSolution), CHeuristicSolution.mutated.offset]
     assert got == want
 
 
