@@ -940,6 +940,7 @@ struct PinnedPool {
     };
     static constexpr size_t MIN_BYTES = 128u << 10;   // smaller arrays: heap (their upload is a latency-bound call either way)
     static constexpr size_t MAX_CACHED = 2ull << 30;  // free blocks kept for reuse
+    static constexpr size_t MAX_BLOCK = 512ull << 20; // larger arrays (millions of columns) stay pageable: pinning gigabytes takes seconds
     std::mutex m;
     std::vector<Block> free_blocks;
     std::vector<Block> live;  // handed out (a handful per plan)
@@ -958,7 +959,7 @@ struct PinnedPool {
     }
 
     void *alloc(size_t bytes) {
-        if (bytes < MIN_BYTES || !enabled.load(std::memory_order_relaxed)) return nullptr;
+        if (bytes < MIN_BYTES || bytes > MAX_BLOCK || !enabled.load(std::memory_order_relaxed)) return nullptr;
         const size_t want = size_class(bytes);
         {
             std::lock_guard<std::mutex> lk(m);
